@@ -1,0 +1,109 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (build container only).
+
+    python oracle/make_golden.py            # all fixtures
+    python oracle/make_golden.py --quick    # skip the 11x7 pitch (its constructor takes ~30 s)
+
+Fixtures (all produced by /root/reference code, never by the oracle or the CUDA path):
+  ref_table_<w>x<h>_s<slip>_<mode>.npz   constructor products, full P / P_readable dump,
+                                         Pmat (COO) and Rmat
+  ref_rollout_<w>x<h>_s<slip>_<mode>.npz injected-randomness auto-reset rollouts
+                                         (inputs and outputs)
+mode: multi | a_free (player_b_policy folded) | b_free (player_a_policy folded)
+
+The inputs are regenerated from fixed numpy RandomState seeds and stored alongside the
+outputs, so the tests never depend on numpy's stream staying stable.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import ref_harness as rh  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def slip_tag(s):
+    return f"{int(round(s * 100)):03d}"
+
+
+def random_policy(nS, seed):
+    """Same construction as the reference's utils/policies.py:4-9 get_random_policy."""
+    rs = np.random.RandomState(seed)
+    return {s: int(rs.randint(0, 5)) for s in range(nS)}
+
+
+def make_env(width, height, slip, mode, pol_seed=0):
+    Env = rh.import_reference()
+    f = width * height
+    nS = 1 + 2 * f * (f - 1)
+    pol = random_policy(nS, pol_seed)
+    if mode == "multi":
+        return Env(width=width, height=height, slip_prob=slip), None
+    if mode == "a_free":
+        return Env(width=width, height=height, slip_prob=slip, player_b_policy=pol), pol
+    if mode == "b_free":
+        return Env(width=width, height=height, slip_prob=slip, player_a_policy=pol), pol
+    raise ValueError(mode)
+
+
+def gen(width, height, slip, mode, T, N, dense=True):
+    t0 = time.time()
+    env, pol = make_env(width, height, slip, mode)
+    tag = f"{width}x{height}_s{slip_tag(slip)}_{mode}"
+    d = {}
+    d.update(rh.dump_model(env))
+    d.update(rh.dump_table(env))
+    if dense:
+        d.update(rh.dump_dense(env))
+    d["slip_prob"] = np.float64(slip)
+    if pol is not None:
+        d["policy"] = np.array([pol[s] for s in range(env.nS)], np.int8)
+    np.savez_compressed(os.path.join(OUT, f"ref_table_{tag}.npz"), **d)
+    t1 = time.time()
+
+    rs = np.random.RandomState(1000 + width * 100 + height * 10 + int(slip * 100))
+    act_a = rs.randint(0, 5, (T, N)).astype(np.uint8)
+    act_b = rs.randint(0, 5, (T, N)).astype(np.uint8) if mode == "multi" else None
+    rng8 = rs.randint(0, 16, (T, N)).astype(np.uint8)
+    rng32 = rs.randint(0, 2 ** 32, (T, N), dtype=np.uint64).astype(np.uint32) if slip > 0 else None
+    init_rng = rs.randint(0, 4, N).astype(np.uint8)
+    obs, rew, flg, rob, inf, init_obs = rh.replay_rollout(env, act_a, act_b, rng8, rng32, init_rng)
+    r = dict(act_a=act_a, rng8=rng8, init_rng=init_rng, obs=obs, reward=rew, flags=flg,
+             reset_obs=rob, info_p=inf, init_obs=init_obs, slip_prob=np.float64(slip))
+    if act_b is not None:
+        r["act_b"] = act_b
+    if rng32 is not None:
+        r["rng32"] = rng32
+    if pol is not None:
+        r["policy"] = d["policy"]
+    np.savez_compressed(os.path.join(OUT, f"ref_rollout_{tag}.npz"), **r)
+    print(f"{tag}: nS={env.nS} table {t1 - t0:.1f}s rollout {time.time() - t1:.1f}s "
+          f"(episodes={int((flg != 0).sum())})", flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--quick", action="store_true")
+    args = ap.parse_args()
+    os.makedirs(OUT, exist_ok=True)
+    gen(5, 4, 0.0, "multi", T=1500, N=64)
+    gen(5, 4, 0.2, "multi", T=1500, N=64)
+    gen(5, 4, 0.2, "a_free", T=600, N=32)
+    gen(5, 4, 0.2, "b_free", T=600, N=32)
+    gen(5, 4, 0.0, "a_free", T=600, N=32)
+    gen(6, 4, 0.0, "multi", T=600, N=32)
+    gen(7, 5, 0.0, "multi", T=600, N=32)
+    gen(7, 5, 0.2, "multi", T=400, N=16, dense=False)
+    if not args.quick:
+        gen(9, 6, 0.0, "multi", T=300, N=16, dense=False)
+        gen(11, 7, 0.0, "multi", T=300, N=16, dense=False)
+
+
+if __name__ == "__main__":
+    main()
