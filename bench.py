@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py -- lock-step env-steps/s of the Littman'94 soccer step path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...     (N > 1)
+
+Workload (config.workload): the K1 streaming step -- host-supplied joint actions, injected 2-bit
+draws, auto-reset fused -- over 2^24 lock-step 5x4 envs PER GPU, the size BASELINE.md grades the
+HBM roofline on (BASELINE.json configs[1] semantics; configs[1]'s own N = 4096 moves 82 KB per
+step and is launch-latency bound, it is reported under "extra").  One "step" = one kernel launch
+advancing every env by one transition.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "lockstep_env_steps_per_sec"
+UNIT = "env-steps/s"
+BYTES_PER_ENV_STEP = 20   # state u32 r+w (8) + act_a, act_b, rng u8 (3) + obs i32 (4) + reward f32 (4) + flags u8 (1)
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:  # noqa: BLE001
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:  # noqa: BLE001
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def time_cpu_port(total_budget_s, n_threads, T=64, N=1 << 15):
+    """The oracle port (oracle/soccer_oracle.c: table build once, then lookup + categorical draw
+    per step, like the reference) timed on host cores.  Returns (env_steps_per_s, sample text)."""
+    import numpy as np
+    from oracle import soccer_oracle as so
+    m = so.OracleModel(5, 4, 0.0)
+    rs = np.random.RandomState(123)
+    act_a = rs.randint(0, 5, (T, N)).astype(np.uint8)
+    act_b = rs.randint(0, 5, (T, N)).astype(np.uint8)
+    rng8 = rs.randint(0, 16, (T, N)).astype(np.uint8)
+    states = np.zeros(N, so.STATE_DTYPE)
+    for i in range(N):
+        states[i] = m.isd[i & 3][1]
+    ts = np.zeros(N, np.int32)
+    m.rollout_injected(states, ts, act_a[:4], act_b[:4], rng8[:4], n_threads=n_threads)   # warm
+    reps, t0 = 0, time.perf_counter()
+    while True:
+        m.rollout_injected(states, ts, act_a, act_b, rng8, n_threads=n_threads)
+        reps += 1
+        el = time.perf_counter() - t0
+        if el >= total_budget_s or reps >= 4096:
+            break
+    return reps * T * N / el, f"{reps} x ({N} envs x {T} lock-steps), {el:.1f} s, 5x4 slip 0, injected draws"
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path, timed on this box's host
+    cores.  The reference itself is Python and cannot travel to the GPU box, so this times the C
+    oracle port of it (kind = "port") with all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    T, N = 64, 1 << 15
+    import numpy as np
+    from oracle import soccer_oracle as so
+    m = so.OracleModel(5, 4, 0.0)
+    rs = np.random.RandomState(123)
+    act_a = rs.randint(0, 5, (T, N)).astype(np.uint8)
+    act_b = rs.randint(0, 5, (T, N)).astype(np.uint8)
+    rng8 = rs.randint(0, 16, (T, N)).astype(np.uint8)
+    states = np.zeros(N, so.STATE_DTYPE)
+    for i in range(N):
+        states[i] = m.isd[i & 3][1]
+    ts = np.zeros(N, np.int32)
+    for _ in range(max(args.warmup, 1)):
+        m.rollout_injected(states, ts, act_a, act_b, rng8, n_threads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        m.rollout_injected(states, ts, act_a, act_b, rng8, n_threads=cores)
+    el = time.perf_counter() - t0
+    v = args.steps * T * N / el
+    sample = f"each step = {N} envs x {T} lock-steps through the oracle port, {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8/u32 integer state + fp64 categorical draw", "data": "synthetic",
+        "config": {"workload": "K1 lock-step step, 5x4 pitch, slip 0, host-supplied joint actions, injected draws, "
+                               "auto-reset; CPU sample of the 2^24-env workload", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from gym_soccer_littman94_b200.envs import SoccerVecEnv
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a B200; there is no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    N = args.envs_per_gpu
+    K, W = args.steps, max(args.warmup, 3)
+    RING = 4
+
+    env = SoccerVecEnv(N, device=dev, kernel=args.kernel, rng_mode="injected", env_id_base=rank * N,
+                       want_reset_obs=False)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+
+    def rnd(hi):
+        return torch.randint(0, hi, (N,), dtype=torch.uint8, device=dev, generator=g)
+    ins = [(rnd(5), rnd(5), rnd(16)) for _ in range(RING)]
+    outs = [(torch.empty(N, dtype=torch.int32, device=dev), torch.empty(N, dtype=torch.float32, device=dev),
+             torch.empty(N, dtype=torch.uint8, device=dev), None) for _ in range(RING)]
+    env.reset(rnd(16))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput (value) + per-launch roofline
+    for i in range(W):
+        env.step(*ins[i % RING], out=outs[i % RING])
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    barrier()
+    ev[0].record()
+    for i in range(K):
+        env.step(*ins[i % RING], out=outs[i % RING])
+        ev[i + 1].record()
+    stats = None
+    if world > 1:
+        # the one collective of the path: episode statistics of the last step
+        f = outs[(K - 1) % RING][2]
+        stats = torch.stack([(f != 0).sum(), (f & 1).sum(), (f & 2).sum() // 2]).to(torch.int64)
+        dist.all_reduce(stats)
+    end = torch.cuda.Event(enable_timing=True)
+    end.record()
+    barrier()
+    total_ms = ev[0].elapsed_time(end)
+    per_launch = [ev[i].elapsed_time(ev[i + 1]) for i in range(K)]
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = world * N * K / (total_ms * 1e-3)
+    kern_ms = sum(per_launch) / K
+    peak, peak_src = measured_peaks()
+    achieved = BYTES_PER_ENV_STEP * N / (kern_ms * 1e-3) / 1e9
+
+    # ---------------- end to end: pinned host buffers in, pinned host buffers out, every step
+    h_in = [tuple(x.cpu().pin_memory() for x in ins[i]) for i in range(2)]
+    for i in range(2):
+        env.step_host(*h_in[i % 2])
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    Ke = max(3, min(K, 10))
+    e0.record()
+    for i in range(Ke):
+        h_obs, h_rew, h_flg = env.step_host(*h_in[i % 2])
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * N * Ke / (float(t.item()) * 1e-3)
+    checksum = int(h_obs[:1024].sum())   # the result really is on the host
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- extra: BASELINE configs 2 and 3 (reported, not the headline)
+    extra = {}
+    try:
+        n2 = 4096
+        e2 = SoccerVecEnv(n2, device=dev, kernel=args.kernel, want_reset_obs=False)
+        a, b, r = (torch.randint(0, hi, (n2,), dtype=torch.uint8, device=dev) for hi in (5, 5, 16))
+        e2.reset(r)
+        for _ in range(20):
+            e2.step(a, b, r)
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(200):
+            e2.step(a, b, r)
+        s1.record()
+        torch.cuda.synchronize()
+        us = s0.elapsed_time(s1) * 1e3 / 200
+        extra["config2_4096_envs"] = {"us_per_step": us, "env_steps_per_s": n2 / (us * 1e-6), "note": "launch-latency bound"}
+        n3, K3 = 1 << 20, 64
+        e3 = SoccerVecEnv(n3, device=dev, kernel=args.kernel, rng_mode="philox", seed=0)
+        e3.reset()
+        bufs = (torch.empty((K3, n3), dtype=torch.int32, device=dev), torch.empty((K3, n3), dtype=torch.float32, device=dev),
+                torch.empty((K3, n3), dtype=torch.uint8, device=dev))
+        e3.rollout(K3, out=bufs)
+        torch.cuda.synchronize()
+        s0.record()
+        for _ in range(4):
+            e3.rollout(K3, out=bufs)
+        s1.record()
+        torch.cuda.synchronize()
+        ms = s0.elapsed_time(s1) / 4
+        v3 = n3 * K3 / (ms * 1e-3)
+        extra["config3_rollout_2^20_K64"] = {"ms_per_launch": ms, "env_steps_per_s": v3,
+                                             "hbm_gbs_at_9.125B": v3 * 9.125 / 1e9, "frac_of_hbm_peak": v3 * 9.125 / 1e9 / peak}
+    except Exception as e:  # noqa: BLE001
+        extra["error"] = repr(e)
+
+    cores = os.cpu_count() or 1
+    cpu_v, cpu_sample = time_cpu_port(args.cpu_seconds, 1)
+    cpu_all_v, _ = time_cpu_port(min(args.cpu_seconds, 5.0), cores)
+
+    print(json.dumps({
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8/u32 integer (f32 reward stream)", "data": "synthetic",
+        "config": {"workload": "K1 streaming lock-step step: 2^24 5x4 envs per GPU, host-supplied joint actions, "
+                               "injected 2-bit draws, fused auto-reset (BASELINE configs[1] semantics at the N "
+                               "BASELINE.md grades the roofline on)",
+                   "envs_per_gpu": N, "kernel": env.kernel, "pitch": "5x4", "slip_prob": 0.0,
+                   "l2": f"per-step traffic {BYTES_PER_ENV_STEP * N / 1e6:.0f} MB > 126 MB L2; inputs and outputs "
+                         f"cycle through {RING}-deep rings", "parallelism": f"independent env shards x{world}"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "kernel": "k_step_table" if env.kernel == "table" else "k_step_fast",
+                     "bytes_per_env_step": BYTES_PER_ENV_STEP, "avg_launch_ms": kern_ms, "min_launch_ms": min(per_launch)},
+        "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": 1, "kind": "port", "sample": cpu_sample,
+                         "all_cores": {"value": cpu_all_v, "cores": cores}},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 3 * N, "d2h_bytes_per_step": 9 * N,
+                "steps": Ke, "checksum": checksum},
+        "gpu_launches": K,
+        "clocks": clocks,
+        "extra": extra,
+        "stats_allreduce": None if stats is None else [int(x) for x in stats.cpu()],
+    }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs-per-gpu", type=int, default=1 << 24)
+    ap.add_argument("--kernel", default="auto", choices=["auto", "rules", "table"])
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

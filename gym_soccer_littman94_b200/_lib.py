@@ -1,0 +1,141 @@
+"""ctypes binding of libsoccer_b200.so (the C ABI in include/soccer_b200.h).
+
+There is NO CPU fallback: if the shared library is missing it is built with nvcc, and if
+that fails, or a kernel entry point returns a CUDA error, the call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_HERE, "csrc")
+SO_PATH = os.path.join(_HERE, "libsoccer_b200.so")
+
+ABI_VERSION = 1
+
+EXPORTS = (
+    "soccer_abi_version", "soccer_pitch_info_host", "soccer_pack_state_host", "soccer_unpack_state_host",
+    "soccer_state_to_obs_host", "soccer_obs_to_state_host", "soccer_reset", "soccer_reset_philox",
+    "soccer_set_state", "soccer_get_obs", "soccer_step", "soccer_step_philox", "soccer_step_ex",
+    "soccer_rollout", "soccer_sweep", "soccer_dense", "soccer_build_step_table", "soccer_step_table",
+    "soccer_rollout_table", "soccer_step_table_bytes_host", "soccer_convert_state",
+)
+
+
+class SoccerB200Error(RuntimeError):
+    pass
+
+
+class Pitch(C.Structure):
+    """struct soccer_pitch: the reference constructor's width/height/slip_prob (SIM:35)."""
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("slip_prob", C.c_double)]
+
+
+class PitchInfo(C.Structure):
+    _fields_ = [("padded_width", C.c_int32), ("height", C.c_int32), ("n_field_cells", C.c_int32),
+                ("nS", C.c_int32), ("nA", C.c_int32), ("n_goal_rows", C.c_int32),
+                ("goal_rows", C.c_int32 * 3), ("n_isd", C.c_int32), ("isd_obs", C.c_int32 * 4),
+                ("isd_state", C.c_uint32 * 4), ("isd_tuple", (C.c_int32 * 5) * 4),
+                ("slip_combo_prob", C.c_double * 9)]
+
+
+class StepArgs(C.Structure):
+    _fields_ = [("state", C.c_void_p), ("act_a", C.c_void_p), ("act_b", C.c_void_p), ("rng8", C.c_void_p),
+                ("rng32", C.c_void_p), ("rngf64", C.c_void_p), ("policy_a", C.c_void_p),
+                ("policy_b", C.c_void_p), ("obs", C.c_void_p), ("reward", C.c_void_p),
+                ("flags", C.c_void_p), ("reset_obs", C.c_void_p), ("n", C.c_int64),
+                ("auto_reset", C.c_int32), ("use_philox", C.c_int32), ("detail", C.c_int32),
+                ("reserved", C.c_int32), ("seed", C.c_uint64), ("step", C.c_uint64),
+                ("env_id_base", C.c_uint64)]
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/ for sm_100a with nvcc (cross-compiles without a GPU)."""
+    srcs = [os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith((".cu", ".cuh"))]
+    srcs.append(os.path.join(os.path.dirname(_HERE), "include", "soccer_b200.h"))
+    stale = (not os.path.exists(SO_PATH)) or any(
+        os.path.getmtime(s) > os.path.getmtime(SO_PATH) for s in srcs if os.path.exists(s))
+    if force or stale:
+        cmd = ["make", "-C", _CSRC] + (["-B"] if force else [])
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if verbose:
+            print(r.stdout)
+        if r.returncode != 0 or not os.path.exists(SO_PATH):
+            raise SoccerB200Error("building libsoccer_b200.so failed (there is no CPU fallback):\n" + r.stdout)
+    return SO_PATH
+
+
+_lib = None
+
+
+def lib():
+    """The loaded library; builds it first if needed.  Raises if it cannot be had."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = build()
+    try:
+        L = C.CDLL(path)
+    except OSError as e:  # pragma: no cover
+        raise SoccerB200Error(f"cannot load {path}: {e} (there is no CPU fallback)") from e
+    missing = [n for n in EXPORTS if not hasattr(L, n)]
+    if missing:
+        raise SoccerB200Error(f"{path} lacks symbols {missing}")
+    vp, i32, i64, u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64
+    PP = C.POINTER(Pitch)
+    L.soccer_abi_version.restype = C.c_int
+    L.soccer_abi_version.argtypes = []
+    if L.soccer_abi_version() != ABI_VERSION:
+        raise SoccerB200Error("libsoccer_b200.so ABI version mismatch")
+    sig = {
+        "soccer_pitch_info_host": [PP, C.POINTER(PitchInfo)],
+        "soccer_pack_state_host": [PP, C.POINTER(C.c_int32 * 5), i32, i32, C.POINTER(C.c_uint32)],
+        "soccer_unpack_state_host": [PP, C.c_uint32, C.POINTER(C.c_int32 * 5), C.POINTER(i32), C.POINTER(i32)],
+        "soccer_state_to_obs_host": [PP, C.c_uint32, C.POINTER(i32)],
+        "soccer_obs_to_state_host": [PP, i32, C.POINTER(C.c_uint32)],
+        "soccer_reset": [PP, vp, vp, vp, vp, i64, vp],
+        "soccer_reset_philox": [PP, vp, vp, vp, u64, u64, u64, i64, vp],
+        "soccer_set_state": [PP, vp, vp, vp, i64, vp],
+        "soccer_get_obs": [PP, vp, vp, i64, vp],
+        "soccer_step": [PP, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp],
+        "soccer_step_philox": [PP, vp, vp, vp, u64, u64, u64, vp, vp, vp, vp, i64, vp],
+        "soccer_step_ex": [PP, C.POINTER(StepArgs), vp],
+        "soccer_rollout": [PP, vp, vp, vp, u64, u64, i32, u64, vp, vp, vp, vp, i64, vp],
+        "soccer_sweep": [PP, i32, vp, vp, vp, vp, vp, vp],
+        "soccer_dense": [PP, vp, vp, vp, vp, vp],
+        "soccer_step_table_bytes_host": [PP, C.POINTER(i64)],
+        "soccer_build_step_table": [PP, vp, vp],
+        "soccer_step_table": [PP, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp],
+        "soccer_rollout_table": [PP, vp, vp, u64, u64, i32, u64, vp, vp, vp, vp, i64, vp],
+        "soccer_convert_state": [PP, vp, vp, i32, i64, vp],
+    }
+    for name, argtypes in sig.items():
+        fn = getattr(L, name)
+        fn.restype = C.c_int
+        fn.argtypes = argtypes
+    _lib = L
+    return L
+
+
+_ERR = {-1: "SOCCER_EINVAL (bad argument)", -2: "SOCCER_EPITCH (unsupported pitch)",
+        -3: "SOCCER_ESLIP (slip_prob > 0 needs rng32/rngf64, or is unsupported by this entry point)",
+        -4: "SOCCER_EPOLICY (both players cannot have a policy)",
+        -5: "SOCCER_ETABLE (pitch too large for the shared-memory step table)"}
+
+
+def check(rc: int, what: str):
+    if rc == 0:
+        return
+    if rc < 0:
+        raise SoccerB200Error(f"{what}: {_ERR.get(rc, rc)}")
+    raise SoccerB200Error(f"{what}: CUDA error {rc} (no CPU fallback exists; a B200 is required)")
+
+
+def pitch_info(width: int, height: int, slip_prob: float = 0.0) -> PitchInfo:
+    """Host-only: constructor products (SIM:48-65, 146-165).  Needs no GPU."""
+    p = Pitch(int(width), int(height), float(slip_prob))
+    out = PitchInfo()
+    check(lib().soccer_pitch_info_host(C.byref(p), C.byref(out)), "soccer_pitch_info_host")
+    return out

@@ -1,0 +1,1160 @@
+// soccer_kernels.cu -- sm_100a kernels + the C ABI of include/soccer_b200.h.
+//
+//   K1  k_step_fast / k_step_generic   one lock-step step() of n envs, auto-reset fused
+//   K2  k_rollout                      K steps with state in registers, Philox, on-device policy
+//   K3  k_sweep                        exhaustive (state, joint action, slip combo, slot) table
+//   K4  k_reset / k_set_state / k_get_obs
+//       k_dense                        Pmat / Rmat in the reference's accumulation order
+//
+// All of them are HBM-streaming or issue-bound integer kernels: there is no dense contraction,
+// so no tensor-core path.  SIM = /root/reference/gym_soccer/envs/soccer_simultaneous_env.py.
+#include "../../include/soccer_b200.h"
+#include "soccer_rules.cuh"
+
+#include <cuda_runtime.h>
+
+using namespace soccer;
+
+namespace soccer {
+
+constexpr int kThreads = 256;
+
+// ------------------------------------------------------------------ host: pitch
+bool pitch_ok(const soccer_pitch* p)
+{
+    return p && p->width >= 5 && p->height >= 4 && p->height <= 16 &&
+           (int64_t)p->width * p->height <= kMaxField && p->slip_prob >= 0.0 && p->slip_prob <= 1.0;
+}
+
+void goal_rows_of(int H, int rows[3], int* n)
+{
+    if (H % 2 == 0) { *n = 2; rows[0] = (H - 1) / 2; rows[1] = H / 2; rows[2] = -1; }   // SIM:60
+    else { *n = 3; rows[0] = H / 2 - 1; rows[1] = H / 2; rows[2] = H / 2 + 1; }
+}
+
+uint32_t field_code(int w, int row, int col_padded) { return (uint32_t)(row * w + col_padded - 1); }
+
+int host_obs_index(int F, uint32_t a, uint32_t b, uint32_t p)
+{
+    return 1 + 2 * ((int)a * (F - 1) + (int)b - (b > a ? 1 : 0)) + (int)p;
+}
+
+int fill_info(const soccer_pitch* p, soccer_pitch_info* o)
+{
+    if (!p || !o) return SOCCER_EINVAL;
+    if (!pitch_ok(p)) return SOCCER_EPITCH;
+    const int w = p->width, H = p->height, F = w * H, W = w + 2;
+    o->padded_width = W; o->height = H; o->n_field_cells = F;
+    o->nS = 1 + 2 * F * (F - 1); o->nA = 5;
+    goal_rows_of(H, o->goal_rows, &o->n_goal_rows);
+    // SIM:146-165
+    const int col_a = 2, col_b = W - 3;
+    int tup[4][5]; int n = 0;
+    if (o->n_goal_rows % 2 == 0) {
+        const int mid = o->n_goal_rows / 2;
+        const int opt[2] = { o->goal_rows[mid - 1], o->goal_rows[mid] };
+        for (int i = 0; i < 2; ++i)
+            for (int poss = 0; poss < 2; ++poss) {
+                const int ra = opt[i], rb = (ra == opt[0]) ? opt[1] : opt[0];
+                const int t[5] = { ra, col_a, rb, col_b, poss };
+                for (int k = 0; k < 5; ++k) tup[n][k] = t[k];
+                ++n;
+            }
+    } else {
+        const int mid = o->goal_rows[o->n_goal_rows / 2];
+        for (int poss = 0; poss < 2; ++poss) {
+            const int t[5] = { mid, col_a, mid, col_b, poss };
+            for (int k = 0; k < 5; ++k) tup[n][k] = t[k];
+            ++n;
+        }
+    }
+    o->n_isd = n;
+    for (int i = 0; i < 4; ++i) {
+        const int j = i < n ? i : n - 1;
+        for (int k = 0; k < 5; ++k) o->isd_tuple[i][k] = tup[j][k];
+        const uint32_t a = field_code(w, tup[j][0], tup[j][1]), b = field_code(w, tup[j][2], tup[j][3]);
+        o->isd_state[i] = a | (b << 8) | ((uint32_t)tup[j][4] << 24);
+        o->isd_obs[i] = host_obs_index(F, a, b, (uint32_t)tup[j][4]);
+    }
+    // SIM:209-223: identical fp64 expressions, evaluated in the same order
+    const double s = p->slip_prob;
+    o->slip_combo_prob[0] = (1 - s) * (1 - s);
+    o->slip_combo_prob[1] = (1 - s) * s * 0.5;
+    o->slip_combo_prob[2] = (1 - s) * s * 0.5;
+    o->slip_combo_prob[3] = s * (1 - s) * 0.5;
+    o->slip_combo_prob[4] = s * (1 - s) * 0.5;
+    for (int c = 5; c < 9; ++c) o->slip_combo_prob[c] = s * s * 0.25;
+    return SOCCER_OK;
+}
+
+int make_pitch_dev(const soccer_pitch* p, PitchDev* d)
+{
+    soccer_pitch_info info;
+    const int rc = fill_info(p, &info);
+    if (rc) return rc;
+    d->w = p->width; d->H = p->height; d->F = info.n_field_cells; d->Fm1 = d->F - 1; d->nS = info.nS;
+    d->goal_row_mask = 0;
+    for (int i = 0; i < info.n_goal_rows; ++i) d->goal_row_mask |= 1u << info.goal_rows[i];
+    // injected 2-bit draw r -> isd index floor(n_isd * (r+0.5)/4): r for 4 starts, r>>1 for 2
+    for (int r = 0; r < 4; ++r) {
+        const int idx = info.n_isd == 4 ? r : (r >> 1);
+        d->isd_state[r] = info.isd_state[idx];
+        d->isd_obs[r] = info.isd_obs[idx];
+    }
+    d->isd_d1 = d->isd_state[1] - d->isd_state[0];
+    d->isd_d2 = d->isd_state[2] - d->isd_state[0];
+    d->obs_d1 = d->isd_obs[1] - d->isd_obs[0];
+    d->obs_d2 = d->isd_obs[2] - d->isd_obs[0];
+    if (d->isd_state[3] != d->isd_state[0] + d->isd_d1 + d->isd_d2 ||
+        d->isd_obs[3] != d->isd_obs[0] + d->obs_d1 + d->obs_d2)
+        return SOCCER_EPITCH;   // cannot happen for the reference's start distributions
+    for (int c = 0; c < 9; ++c) d->mp[c] = info.slip_combo_prob[c];
+    d->slip = p->slip_prob != 0.0;
+    return SOCCER_OK;
+}
+
+int sm_count()
+{
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) return 148;
+    return sms;
+}
+
+template <typename K>
+int resident_blocks(K kernel)
+{
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, kThreads, 0) != cudaSuccess || nb < 1) nb = 1;
+    return nb;
+}
+
+inline int launch_status() { return (int)cudaGetLastError(); }
+
+inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
+
+// ------------------------------------------------------------------ streaming loads / stores
+__device__ __forceinline__ uint4 ld_stream(const uint4* p) { return __ldcs(p); }
+__device__ __forceinline__ uint32_t ld_stream(const uint32_t* p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream(uint4* p, uint4 v) { __stcs(p, v); }
+__device__ __forceinline__ void st_stream(uint32_t* p, uint32_t v) { __stcs(p, v); }
+
+// ------------------------------------------------------------------ K1 fast path
+// slip_prob == 0, joint actions + rng8 from the caller, auto-reset fused.  One thread owns
+// groups of 4 consecutive envs: 128-bit accesses on the 32-bit streams (state, obs, reward),
+// 32-bit accesses on the byte streams (actions, rng, flags); a warp therefore touches 512 B /
+// 128 B contiguous per instruction.  Persistent grid-stride loop, two groups in flight.
+struct Group4 { uint4 s; uint32_t a, b, r; };
+
+__device__ __forceinline__ Group4 load_group(const uint4* st, const uint32_t* aa, const uint32_t* ab,
+                                             const uint32_t* rg, int64_t g)
+{
+    Group4 x;
+    x.s = st[g];              // state is re-read by the next step: default caching
+    x.a = ld_stream(aa + g);
+    x.b = ld_stream(ab + g);
+    x.r = ld_stream(rg + g);
+    return x;
+}
+
+template <bool RESET_OBS>
+__device__ __forceinline__ void step_group(const PitchDev& P, const uint8_t* lut, const Group4& x, int64_t g,
+                                           uint4* st, uint4* obs, uint4* rew, uint32_t* flg, uint4* rob)
+{
+    const uint32_t sv[4] = { x.s.x, x.s.y, x.s.z, x.s.w };
+    uint32_t so[4], oo[4], ro[4], rr[4], ff = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const uint32_t aa = (x.a >> (8 * e)) & 0xFFu, ab = (x.b >> (8 * e)) & 0xFFu, rg = (x.r >> (8 * e)) & 0xFFu;
+        const StepOut o = step_noslip<true, false>(P, lut, sv[e], aa, ab, rg, false);
+        so[e] = o.state; oo[e] = (uint32_t)o.obs; rr[e] = __float_as_uint(o.reward);
+        ro[e] = (uint32_t)o.reset_obs;
+        ff |= o.flags << (8 * e);
+    }
+    st[g] = make_uint4(so[0], so[1], so[2], so[3]);
+    st_stream(obs + g, make_uint4(oo[0], oo[1], oo[2], oo[3]));
+    st_stream(rew + g, make_uint4(rr[0], rr[1], rr[2], rr[3]));
+    st_stream(flg + g, ff);
+    if (RESET_OBS) st_stream(rob + g, make_uint4(ro[0], ro[1], ro[2], ro[3]));
+}
+
+template <bool RESET_OBS>
+__global__ void __launch_bounds__(kThreads)
+k_step_fast(const PitchDev P, uint32_t* __restrict__ state, const uint8_t* __restrict__ act_a,
+            const uint8_t* __restrict__ act_b, const uint8_t* __restrict__ rng, int32_t* __restrict__ obs,
+            float* __restrict__ reward, uint8_t* __restrict__ flags, int32_t* __restrict__ reset_obs,
+            int64_t n_groups)
+{
+    __shared__ __align__(16) uint8_t lut[kLutBytes];
+    build_cand_lut(lut, P);
+
+    uint4* st4 = reinterpret_cast<uint4*>(state);
+    const uint32_t* a4 = reinterpret_cast<const uint32_t*>(act_a);
+    const uint32_t* b4 = reinterpret_cast<const uint32_t*>(act_b);
+    const uint32_t* r4 = reinterpret_cast<const uint32_t*>(rng);
+    uint4* o4 = reinterpret_cast<uint4*>(obs);
+    uint4* w4 = reinterpret_cast<uint4*>(reward);
+    uint32_t* f4 = reinterpret_cast<uint32_t*>(flags);
+    uint4* q4 = reinterpret_cast<uint4*>(reset_obs);
+
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_groups; g += 2 * stride) {
+        const int64_t g2 = g + stride;
+        const bool two = g2 < n_groups;
+        const Group4 x0 = load_group(st4, a4, b4, r4, g);
+        Group4 x1 = x0;
+        if (two) x1 = load_group(st4, a4, b4, r4, g2);
+        step_group<RESET_OBS>(P, lut, x0, g, st4, o4, w4, f4, q4);
+        if (two) step_group<RESET_OBS>(P, lut, x1, g2, st4, o4, w4, f4, q4);
+    }
+}
+
+// ------------------------------------------------------------------ K1 generic path
+// Every option of soccer_step_args, one env per thread (scalar but warp-coalesced accesses).
+struct StepOpts {
+    uint32_t* state; const uint8_t* act_a; const uint8_t* act_b; const uint8_t* rng8;
+    const uint32_t* rng32; const double* rngf64; const int8_t* policy_a; const int8_t* policy_b;
+    int32_t* obs; float* reward; uint8_t* flags; int32_t* reset_obs;
+    int64_t n; int32_t auto_reset; int32_t use_philox; int32_t detail; uint64_t seed, step, env_id_base;
+};
+
+__global__ void __launch_bounds__(kThreads) k_step_generic(const PitchDev P, const StepOpts o)
+{
+    __shared__ __align__(16) uint8_t lut[kLutBytes];
+    build_cand_lut(lut, P);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < o.n; i += stride) {
+        const uint32_t s = o.state[i];
+        const uint32_t a = s & 0xFFu, b = (s >> 8) & 0xFFu, p = (s >> 24) & 1u;
+        const bool terminal_in = ((a | b) & kGoalBit) != 0;
+        if (s & kNeedsReset) {                       // the assert at SIM:376: leave the env alone
+            if (o.obs) o.obs[i] = terminal_in ? 0 : obs_index(P, a, b, p);
+            if (o.reward) o.reward[i] = 0.0f;
+            if (o.flags) o.flags[i] = 0xFFu;
+            if (o.reset_obs) o.reset_obs[i] = terminal_in ? 0 : obs_index(P, a, b, p);
+            continue;
+        }
+        uint32_t rng = 0;
+        if (o.use_philox) rng = philox_rng8(philox_word(o.seed, o.env_id_base + (uint64_t)i, o.step));
+        else if (o.rng8) rng = o.rng8[i];
+        const int32_t cur = terminal_in ? 0 : obs_index(P, a, b, p);
+        // SIM:187-188: a folded player's action is its table policy at the current observation
+        const uint32_t aa = o.policy_a ? (uint32_t)o.policy_a[cur] : (uint32_t)o.act_a[i];
+        const uint32_t ab = o.policy_b ? (uint32_t)o.policy_b[cur] : (uint32_t)o.act_b[i];
+        const bool flip = o.policy_a != nullptr;     // return agent is player_b (SIM:243-244)
+        StepOut r;
+        if (terminal_in) {
+            // a goal tuple injected through `env.state = ...`: absorbing, done, reward 0 (SIM:235-236, 300-301)
+            const uint32_t t1 = ((s >> 16) & 0xFFu) + 1u;
+            const bool trunc = t1 >= (uint32_t)kMaxT;
+            r.obs = 0; r.reward = flip ? -0.0f : 0.0f; r.flags = 1u | (trunc ? 2u : 0u);
+            if (o.auto_reset) { r.state = P.isd_state[(rng >> 2) & 3u]; r.reset_obs = P.isd_obs[(rng >> 2) & 3u]; }
+            else { r.state = (s & 0x0100FFFFu) | (t1 << 16) | kNeedsReset; r.reset_obs = 0; }
+        } else if (P.slip) {
+            double u;
+            if (o.rngf64) u = o.rngf64[i];
+            else if (o.rng32) u = ((double)o.rng32[i] + 0.5) * (1.0 / 4294967296.0);
+            else {   // philox mode with slip: 53-bit uniform from two fresh words of a separate counter lane
+                uint32_t w[4];
+                const uint64_t e = o.env_id_base + (uint64_t)i;
+                philox4x32_10((uint32_t)e, (uint32_t)(e >> 32), (uint32_t)o.step, (uint32_t)(o.step >> 32) | 0x80000000u,
+                              (uint32_t)o.seed, (uint32_t)(o.seed >> 32), w);
+                u = ((double)(((uint64_t)(w[0] >> 5) << 26) | (uint64_t)(w[1] >> 6))) * (1.0 / 9007199254740992.0);
+            }
+            r = o.auto_reset ? step_slip<true>(P, lut, s, aa, ab, u, (rng >> 2) & 3u, flip)
+                             : step_slip<false>(P, lut, s, aa, ab, u, (rng >> 2) & 3u, flip);
+        } else {
+            r = o.auto_reset ? step_noslip<true>(P, lut, s, aa, ab, rng, flip)
+                             : step_noslip<false>(P, lut, s, aa, ab, rng, flip);
+        }
+        o.state[i] = r.state;
+        if (o.obs) o.obs[i] = r.obs;
+        if (o.reward) o.reward[i] = r.reward;
+        if (o.flags) o.flags[i] = (uint8_t)(o.detail ? r.flags : (r.flags & 3u));
+        if (o.reset_obs) o.reset_obs[i] = r.reset_obs;
+    }
+}
+
+// ------------------------------------------------------------------ K2 fused rollout
+// Each thread owns VEC envs for all K steps; state, timestep and the current Philox block stay
+// in registers; only the obs / reward / flags streams ([K][n]) are written, as 128-bit / 32-bit
+// stores when VEC == 4.  Episode statistics: registers -> warp reduce -> smem -> 6 atomics/CTA.
+template <int VEC>
+__global__ void __launch_bounds__(kThreads)
+k_rollout(const PitchDev P, uint32_t* __restrict__ state, const int8_t* __restrict__ policy_a,
+          const int8_t* __restrict__ policy_b, uint64_t seed, uint64_t step0, int32_t K,
+          uint64_t env_id_base, int32_t* __restrict__ obs, float* __restrict__ reward,
+          uint8_t* __restrict__ flags, unsigned long long* __restrict__ stats, int64_t n)
+{
+    __shared__ __align__(16) uint8_t lut[kLutBytes];
+    __shared__ unsigned int blk_stats[6];
+    build_cand_lut(lut, P);
+    if (threadIdx.x < 6) blk_stats[threadIdx.x] = 0;
+    __syncthreads();
+
+    uint32_t c_ep = 0, c_ga = 0, c_gb = 0, c_tr = 0, c_len = 0, c_steps = 0;
+    const int64_t n_groups = n / VEC;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_groups; g += stride) {
+        const int64_t i0 = g * VEC;
+        uint32_t s[VEC], w[VEC][4];
+        if (VEC == 4) {
+            const uint4 v = reinterpret_cast<const uint4*>(state)[g];
+            s[0] = v.x; s[1 % VEC] = v.y; s[2 % VEC] = v.z; s[3 % VEC] = v.w;
+        } else {
+            s[0] = state[i0];
+        }
+        for (int32_t k = 0; k < K; ++k) {
+            const uint64_t step = step0 + (uint64_t)k;
+            const uint32_t wi = (uint32_t)step & 3u;
+            if (k == 0 || wi == 0) {
+                const uint64_t blk = step >> 2;
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) {
+                    const uint64_t env = env_id_base + (uint64_t)(i0 + e);
+                    philox4x32_10((uint32_t)env, (uint32_t)(env >> 32), (uint32_t)blk, (uint32_t)(blk >> 32),
+                                  (uint32_t)seed, (uint32_t)(seed >> 32), w[e]);
+                }
+            }
+            uint32_t oo[VEC], rr[VEC], ff = 0;
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                const uint32_t word = wi == 0 ? w[e][0] : (wi == 1 ? w[e][1] : (wi == 2 ? w[e][2] : w[e][3]));
+                uint32_t aa, ab;
+                philox_actions(word, aa, ab);
+                if (policy_a || policy_b) {
+                    const uint32_t a = s[e] & 0xFFu, b = (s[e] >> 8) & 0xFFu, p = (s[e] >> 24) & 1u;
+                    const int32_t cur = obs_index(P, a, b, p);
+                    if (policy_a) aa = (uint32_t)policy_a[cur];
+                    if (policy_b) ab = (uint32_t)policy_b[cur];
+                }
+                const uint32_t t_before = (s[e] >> 16) & 0xFFu;
+                const StepOut o = step_noslip<true, false>(P, lut, s[e], aa, ab, philox_rng8(word), false);
+                s[e] = o.state;
+                oo[e] = (uint32_t)o.obs; rr[e] = __float_as_uint(o.reward); ff |= (o.flags & 0xFFu) << (8 * e);
+                const bool done = o.flags & 1u, ended = (o.flags & 3u) != 0;
+                c_ep += ended; c_len += ended ? t_before + 1u : 0u;
+                c_ga += done && o.reward > 0.0f; c_gb += done && o.reward < 0.0f; c_tr += ended && !done;
+            }
+            c_steps += VEC;
+            const int64_t off = (int64_t)k * n;
+            if (VEC == 4) {
+                if (obs) st_stream(reinterpret_cast<uint4*>(obs + off) + g, make_uint4(oo[0], oo[1 % VEC], oo[2 % VEC], oo[3 % VEC]));
+                if (reward) st_stream(reinterpret_cast<uint4*>(reward + off) + g, make_uint4(rr[0], rr[1 % VEC], rr[2 % VEC], rr[3 % VEC]));
+                if (flags) st_stream(reinterpret_cast<uint32_t*>(flags + off) + g, ff);
+            } else {
+                if (obs) obs[off + i0] = (int32_t)oo[0];
+                if (reward) reward[off + i0] = __uint_as_float(rr[0]);
+                if (flags) flags[off + i0] = (uint8_t)ff;
+            }
+        }
+        if (VEC == 4) reinterpret_cast<uint4*>(state)[g] = make_uint4(s[0], s[1 % VEC], s[2 % VEC], s[3 % VEC]);
+        else state[i0] = s[0];
+    }
+    if (stats) {
+        uint32_t v[6] = { c_ep, c_ga, c_gb, c_tr, c_steps, c_len };
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            const uint32_t r = __reduce_add_sync(0xFFFFFFFFu, v[j]);
+            if ((threadIdx.x & 31) == 0 && r) atomicAdd(&blk_stats[j], r);
+        }
+        __syncthreads();
+        if (threadIdx.x < 6 && blk_stats[threadIdx.x])
+            atomicAdd(&stats[threadIdx.x], (unsigned long long)blk_stats[threadIdx.x]);
+    }
+}
+
+// ------------------------------------------------------------------ K3 sweep
+__global__ void __launch_bounds__(kThreads)
+k_sweep(const PitchDev P, int32_t n_combos, int32_t nS, uint8_t* __restrict__ n_out,
+        uint32_t* __restrict__ next_state, int32_t* __restrict__ next_obs, int8_t* __restrict__ reward,
+        uint8_t* __restrict__ done)
+{
+    __shared__ __align__(16) uint8_t lut[kLutBytes];
+    build_cand_lut(lut, P);
+    const int64_t total = (int64_t)(nS - 1) * 25 * n_combos;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int c = (int)(i % n_combos);
+        const int64_t sj = i / n_combos;
+        const uint32_t ja = (uint32_t)(sj % 25), aa = ja / 5u, ab = ja % 5u;
+        const int32_t s_obs = (int32_t)(sj / 25) + 1;
+        const uint32_t st = obs_to_packed(P, s_obs);
+        const uint32_t a = st & 0xFFu, b = (st >> 8) & 0xFFu, p = (st >> 24) & 1u;
+        const int ca = combo_a(c), cb = combo_b(c);
+        const uint32_t ma = ca == 0 ? aa : slip_move(aa, ca - 1);
+        const uint32_t mb = cb == 0 ? ab : slip_move(ab, cb - 1);
+        const Resolved o0 = resolve(lut, a, b, p, ma, mb, aa == 0, ab == 0, 0u);
+        const uint32_t n = 1u << o0.nlog2;
+        if (n_out) n_out[i] = (uint8_t)n;
+#pragma unroll
+        for (uint32_t k = 0; k < 4; ++k) {
+            uint32_t ns = 0; int32_t no = 0; int8_t rw = 0; uint8_t dn = 0;
+            if (k < n) {
+                const Resolved o = resolve(lut, a, b, p, ma, mb, aa == 0, ab == 0, n == 2 ? (k << 1) : k);
+                const StepOut f = finish_step<false>(P, o, 0u, 0u, 0u, false);
+                ns = o.a | (o.b << 8) | (o.p << 24); no = f.obs; rw = (int8_t)f.reward; dn = (uint8_t)(f.flags & 1u);
+            }
+            const int64_t e = i * 4 + k;
+            if (next_state) next_state[e] = ns;
+            if (next_obs) next_obs[e] = no;
+            if (reward) reward[e] = rw;
+            if (done) done[e] = dn;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ dense Pmat / Rmat
+// One thread per (observation s, key): it alone owns column Pmat[s][:][key] and Rmat[s][key], so
+// plain fp64 read-modify-writes in list order reproduce the reference's accumulation order
+// (SIM:258-279) bit for bit.  Row s == 0 reproduces the reference quirk that every goal state
+// adds its self-loop into P[0] / Pmat[0][0] (SIM:182-183, 262).
+__global__ void __launch_bounds__(kThreads)
+k_dense(const PitchDev P, int32_t nS, int32_t n_goal_states, const int8_t* __restrict__ policy_a,
+        const int8_t* __restrict__ policy_b, double* __restrict__ Pmat, double* __restrict__ Rmat)
+{
+    __shared__ __align__(16) uint8_t lut[kLutBytes];
+    build_cand_lut(lut, P);
+    const bool multi = !policy_a && !policy_b;
+    const int nkeys = multi ? 25 : 5;
+    const int64_t total = (int64_t)nS * nkeys;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int key = (int)(i % nkeys);
+        const int32_t s_obs = (int32_t)(i / nkeys);
+        double* col = Pmat + (int64_t)s_obs * nS * nkeys + key;     // Pmat[s][ns][key] = col[ns*nkeys]
+        double racc = 0.0;                                          // SIM:260
+        if (s_obs == 0) {
+            double acc = 0.0;
+            for (int gsi = 0; gsi < n_goal_states; ++gsi)
+                for (int c = 0; c < 9; ++c)
+                    if (P.mp[c] != 0.0) acc = __dadd_rn(acc, __dmul_rn(P.mp[c], 1.0));
+            col[0] = acc;
+            Rmat[i] = 0.0;
+            continue;
+        }
+        const uint32_t st = obs_to_packed(P, s_obs);
+        const uint32_t a = st & 0xFFu, b = (st >> 8) & 0xFFu, p = (st >> 24) & 1u;
+        uint32_t aa, ab;
+        if (multi) { aa = (uint32_t)key / 5u; ab = (uint32_t)key % 5u; }
+        else if (policy_b) { aa = (uint32_t)key; ab = (uint32_t)policy_b[s_obs]; }
+        else { aa = (uint32_t)policy_a[s_obs]; ab = (uint32_t)key; }
+        const bool flip = policy_a != nullptr;
+        for (int c = 0; c < 9; ++c) {
+            const double mp = P.mp[c];
+            if (mp == 0.0) continue;
+            const int ca = combo_a(c), cb = combo_b(c);
+            const uint32_t ma = ca == 0 ? aa : slip_move(aa, ca - 1);
+            const uint32_t mb = cb == 0 ? ab : slip_move(ab, cb - 1);
+            const Resolved o0 = resolve(lut, a, b, p, ma, mb, aa == 0, ab == 0, 0u);
+            const uint32_t n = 1u << o0.nlog2;
+            const double pr = __dmul_rn(mp, n == 4 ? 0.25 : (n == 2 ? 0.5 : 1.0));
+            for (uint32_t k = 0; k < n; ++k) {
+                const Resolved o = resolve(lut, a, b, p, ma, mb, aa == 0, ab == 0, n == 2 ? (k << 1) : k);
+                const StepOut f = finish_step<false>(P, o, 0u, 0u, 0u, flip);
+                double* cell = col + (int64_t)f.obs * nkeys;
+                *cell = __dadd_rn(*cell, pr);                                   // SIM:262
+                racc = __dadd_rn(racc, __dmul_rn(pr, (double)f.reward));        // SIM:263
+            }
+        }
+        Rmat[i] = racc;
+    }
+}
+
+// ------------------------------------------------------------------ K4
+__global__ void __launch_bounds__(kThreads)
+k_reset(const PitchDev P, uint32_t* __restrict__ state, int32_t* __restrict__ obs_out,
+        const uint8_t* __restrict__ rng8, const uint8_t* __restrict__ mask, int use_philox, uint64_t seed,
+        uint64_t step, uint64_t env_id_base, int64_t n)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        if (mask && !mask[i]) continue;
+        uint32_t r;
+        if (use_philox) r = philox_rng8(philox_word(seed, env_id_base + (uint64_t)i, step));
+        else r = rng8 ? rng8[i] : 0u;
+        const uint32_t sel = (r >> 2) & 3u;
+        state[i] = P.isd_state[sel];
+        if (obs_out) obs_out[i] = P.isd_obs[sel];
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_set_state(const PitchDev P, int32_t nS, uint32_t* __restrict__ state, const int32_t* __restrict__ obs_in,
+            const int32_t* __restrict__ timestep_in, int64_t n)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int32_t o = obs_in[i];
+        int32_t t = timestep_in ? timestep_in[i] : 0;
+        t = t < 0 ? 0 : (t > 255 ? 255 : t);
+        if (o >= 1 && o < nS) state[i] = obs_to_packed(P, o) | ((uint32_t)t << 16);
+        else state[i] = kNeedsReset | kGoalBit | ((uint32_t)t << 16);   // terminal / invalid: needs reset
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_get_obs(const PitchDev P, const uint32_t* __restrict__ state, int32_t* __restrict__ obs_out, int64_t n)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t s = state[i];
+        const uint32_t a = s & 0xFFu, b = (s >> 8) & 0xFFu, p = (s >> 24) & 1u;
+        obs_out[i] = ((a | b) & kGoalBit) ? 0 : obs_index(P, a, b, p);
+    }
+}
+
+// ------------------------------------------------------------------ shared-memory step table
+// K3's product, compacted: table[(obs-1)*100 + aa*20 + ab*4 + r] = next_obs | nonzero<<10 |
+// negative<<11 | nlog2<<12.  Built on the device by the rules path; (nS-1)*200 bytes.
+constexpr int kTableThreads = 1024;          // one CTA per SM owns the whole shared memory
+constexpr int kMaxTableStates = 1023;        // next_obs must fit 10 bits
+constexpr uint32_t kTblObsMask = 0x3FFu, kTblNonzero = 0x400u, kTblNegative = 0x800u;
+
+__global__ void __launch_bounds__(kThreads)
+k_build_step_table(const PitchDev P, int32_t nS, uint16_t* __restrict__ table)
+{
+    __shared__ __align__(16) uint8_t lut[kLutBytes];
+    build_cand_lut(lut, P);
+    const int64_t total = (int64_t)(nS - 1) * 100;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const uint32_t r = (uint32_t)(i & 3), ja = (uint32_t)((i >> 2) % 25), aa = ja / 5u, ab = ja % 5u;
+        const uint32_t st = obs_to_packed(P, (int32_t)(i / 100) + 1);
+        const uint32_t a = st & 0xFFu, b = (st >> 8) & 0xFFu, p = (st >> 24) & 1u;
+        const Resolved o = resolve(lut, a, b, p, aa, ab, aa == 0, ab == 0, r);
+        const StepOut f = finish_step<false>(P, o, 0u, 0u, 0u, false);
+        table[i] = (uint16_t)((uint32_t)f.obs | (f.reward != 0.0f ? kTblNonzero : 0u) |
+                              (f.reward < 0.0f ? kTblNegative : 0u) | (o.nlog2 << 12));
+    }
+}
+
+// ---- TMA 1-D bulk copy global -> shared, completion on an mbarrier
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+
+// Stage the table into shared memory: one elected thread issues 16 KB bulk copies; everybody
+// waits on the mbarrier (bounded spin -> trap, so a fault cannot hang the GPU).
+__device__ __forceinline__ void stage_table(uint16_t* smem_tbl, const uint16_t* gtable, uint32_t bytes, uint64_t* bar)
+{
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(bar, bytes);
+        const uint32_t chunk = 16384;
+        for (uint32_t off = 0; off < bytes; off += chunk) {
+            const uint32_t nb = bytes - off < chunk ? bytes - off : chunk;
+            tma_load_1d(reinterpret_cast<uint8_t*>(smem_tbl) + off, reinterpret_cast<const uint8_t*>(gtable) + off, nb, bar);
+        }
+    }
+    __syncthreads();    // barrier init visible to all before anyone polls it
+}
+__device__ __forceinline__ void wait_table(uint64_t* bar)
+{
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, 0)) {
+        if (++spins > (1u << 22)) __trap();
+    }
+}
+
+// one env-step on an INDEX-layout state word through the shared-memory table
+struct TblOut { uint32_t state, obs, rew_bits, flags, reset_obs; };
+__device__ __forceinline__ TblOut table_step(const PitchDev& P, const uint16_t* __restrict__ tbl, uint32_t s,
+                                             uint32_t aa, uint32_t ab, uint32_t rg)
+{
+    const uint32_t sidx = (s & 0xFFFFu) - 1u, t = (s >> 16) & 0xFFu;
+    // clamp: a corrupt state word or action byte must not read outside the table
+    const uint32_t e = tbl[min(sidx * 100u + aa * 20u + ab * 4u + (rg & 3u), (uint32_t)(P.nS - 1) * 100u - 1u)];
+    const uint32_t nobs = e & kTblObsMask;
+    const bool done = nobs == 0;                                          // SIM:493: goal -> obs 0
+    const uint32_t t1 = t + 1u;                                           // SIM:399
+    const bool trunc = t1 >= (uint32_t)kMaxT;                             // SIM:404
+    const bool reset = done | trunc;                                      // SIM:406
+    const uint32_t m1 = (rg & 4u) ? 0xFFFFFFFFu : 0u, m2 = (rg & 8u) ? 0xFFFFFFFFu : 0u;
+    const uint32_t ro = (uint32_t)P.isd_obs[0] + (m1 & (uint32_t)P.obs_d1) + (m2 & (uint32_t)P.obs_d2); // SIM:414-415
+    TblOut o;
+    o.obs = nobs;
+    o.rew_bits = ((e & kTblNonzero) ? 0x3F800000u : 0u) | ((e & kTblNegative) << 20);   // +1.0f / -1.0f / 0.0f
+    o.flags = (done ? 1u : 0u) | (trunc ? 2u : 0u);
+    o.state = reset ? ro : (nobs | (t1 << 16));
+    o.reset_obs = reset ? ro : nobs;
+    return o;
+}
+
+template <bool RESET_OBS>
+__device__ __forceinline__ void table_step_group(const PitchDev& P, const uint16_t* tbl, const Group4& x, int64_t g,
+                                                 uint4* st, uint4* obs, uint4* rew, uint32_t* flg, uint4* rob)
+{
+    const uint32_t sv[4] = { x.s.x, x.s.y, x.s.z, x.s.w };
+    uint32_t so[4], oo[4], ro[4], rr[4], ff = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const uint32_t aa = __byte_perm(x.a, 0, 0x4440 + e), ab = __byte_perm(x.b, 0, 0x4440 + e),
+                       rg = __byte_perm(x.r, 0, 0x4440 + e);
+        const TblOut o = table_step(P, tbl, sv[e], aa, ab, rg);
+        so[e] = o.state; oo[e] = o.obs; rr[e] = o.rew_bits; ro[e] = o.reset_obs;
+        ff |= o.flags << (8 * e);
+    }
+    st[g] = make_uint4(so[0], so[1], so[2], so[3]);
+    st_stream(obs + g, make_uint4(oo[0], oo[1], oo[2], oo[3]));
+    st_stream(rew + g, make_uint4(rr[0], rr[1], rr[2], rr[3]));
+    st_stream(flg + g, ff);
+    if (RESET_OBS) st_stream(rob + g, make_uint4(ro[0], ro[1], ro[2], ro[3]));
+}
+
+// K1, table variant: persistent, one 1024-thread CTA per SM, table (152 KB for 5x4) TMA-staged
+// into shared memory while the first groups' HBM loads are already in flight.
+template <bool RESET_OBS>
+__global__ void __launch_bounds__(kTableThreads, 1)
+k_step_table(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t table_bytes,
+             uint32_t* __restrict__ state, const uint8_t* __restrict__ act_a, const uint8_t* __restrict__ act_b,
+             const uint8_t* __restrict__ rng, int32_t* __restrict__ obs, float* __restrict__ reward,
+             uint8_t* __restrict__ flags, int32_t* __restrict__ reset_obs, int64_t n_groups)
+{
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint16_t* tbl = reinterpret_cast<uint16_t*>(smem_raw);
+    __shared__ __align__(8) uint64_t bar;
+    stage_table(tbl, gtable, table_bytes, &bar);
+
+    uint4* st4 = reinterpret_cast<uint4*>(state);
+    const uint32_t* a4 = reinterpret_cast<const uint32_t*>(act_a);
+    const uint32_t* b4 = reinterpret_cast<const uint32_t*>(act_b);
+    const uint32_t* r4 = reinterpret_cast<const uint32_t*>(rng);
+    uint4* o4 = reinterpret_cast<uint4*>(obs);
+    uint4* w4 = reinterpret_cast<uint4*>(reward);
+    uint32_t* f4 = reinterpret_cast<uint32_t*>(flags);
+    uint4* q4 = reinterpret_cast<uint4*>(reset_obs);
+
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // first pair of groups: issue the HBM loads, THEN wait for the table
+    bool one = g < n_groups, two = g + stride < n_groups;
+    Group4 x0 = {}, x1 = {};
+    if (one) x0 = load_group(st4, a4, b4, r4, g);
+    if (two) x1 = load_group(st4, a4, b4, r4, g + stride);
+    wait_table(&bar);
+    while (one) {
+        const int64_t gn = g + 2 * stride;
+        const bool n_one = gn < n_groups, n_two = gn + stride < n_groups;
+        Group4 y0 = x0, y1 = x1;
+        if (n_one) y0 = load_group(st4, a4, b4, r4, gn);          // prefetch the next pair
+        if (n_two) y1 = load_group(st4, a4, b4, r4, gn + stride);
+        table_step_group<RESET_OBS>(P, tbl, x0, g, st4, o4, w4, f4, q4);
+        if (two) table_step_group<RESET_OBS>(P, tbl, x1, g + stride, st4, o4, w4, f4, q4);
+        x0 = y0; x1 = y1; g = gn; one = n_one; two = n_two;
+    }
+}
+
+// scalar tail / misaligned fallback of the table path (global-memory table, one env per thread)
+__global__ void __launch_bounds__(kThreads)
+k_step_table_scalar(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t* __restrict__ state,
+                    const uint8_t* __restrict__ act_a, const uint8_t* __restrict__ act_b,
+                    const uint8_t* __restrict__ rng, int32_t* __restrict__ obs, float* __restrict__ reward,
+                    uint8_t* __restrict__ flags, int32_t* __restrict__ reset_obs, int64_t n)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const TblOut o = table_step(P, gtable, state[i], act_a[i], act_b[i], rng[i]);
+        state[i] = o.state; obs[i] = (int32_t)o.obs; reward[i] = __uint_as_float(o.rew_bits);
+        flags[i] = (uint8_t)o.flags;
+        if (reset_obs) reset_obs[i] = (int32_t)o.reset_obs;
+    }
+}
+
+// K2, table variant: uniform random policy from Philox, state (obs | t<<16) in registers.
+template <int VEC>
+__global__ void __launch_bounds__(kTableThreads, 1)
+k_rollout_table(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t table_bytes,
+                uint32_t* __restrict__ state, uint64_t seed, uint64_t step0, int32_t K, uint64_t env_id_base,
+                int32_t* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ flags,
+                unsigned long long* __restrict__ stats, int64_t n)
+{
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint16_t* tbl = reinterpret_cast<uint16_t*>(smem_raw);
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ unsigned int blk_stats[6];
+    if (threadIdx.x < 6) blk_stats[threadIdx.x] = 0;
+    stage_table(tbl, gtable, table_bytes, &bar);
+    wait_table(&bar);
+
+    uint32_t c_ep = 0, c_ga = 0, c_gb = 0, c_tr = 0, c_len = 0, c_steps = 0;
+    const int64_t n_groups = n / VEC;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_groups; g += stride) {
+        const int64_t i0 = g * VEC;
+        uint32_t s[VEC], w[VEC][4];
+        if (VEC == 4) {
+            const uint4 v = reinterpret_cast<const uint4*>(state)[g];
+            s[0] = v.x; s[1 % VEC] = v.y; s[2 % VEC] = v.z; s[3 % VEC] = v.w;
+        } else {
+            s[0] = state[i0];
+        }
+        for (int32_t k = 0; k < K; ++k) {
+            const uint64_t step = step0 + (uint64_t)k;
+            const uint32_t wi = (uint32_t)step & 3u;
+            if (k == 0 || wi == 0) {
+                const uint64_t blk = step >> 2;
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) {
+                    const uint64_t env = env_id_base + (uint64_t)(i0 + e);
+                    philox4x32_10((uint32_t)env, (uint32_t)(env >> 32), (uint32_t)blk, (uint32_t)(blk >> 32),
+                                  (uint32_t)seed, (uint32_t)(seed >> 32), w[e]);
+                }
+            }
+            uint32_t oo[VEC], rr[VEC], ff = 0;
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                const uint32_t word = wi == 0 ? w[e][0] : (wi == 1 ? w[e][1] : (wi == 2 ? w[e][2] : w[e][3]));
+                uint32_t aa, ab;
+                philox_actions(word, aa, ab);
+                const uint32_t t_before = (s[e] >> 16) & 0xFFu;
+                const TblOut o = table_step(P, tbl, s[e], aa, ab, philox_rng8(word));
+                s[e] = o.state; oo[e] = o.obs; rr[e] = o.rew_bits; ff |= o.flags << (8 * e);
+                const bool done = o.flags & 1u, ended = o.flags != 0;
+                c_ep += ended; c_len += ended ? t_before + 1u : 0u;
+                c_ga += done && (o.rew_bits >> 31) == 0; c_gb += done && (o.rew_bits >> 31) != 0; c_tr += ended && !done;
+            }
+            c_steps += VEC;
+            const int64_t off = (int64_t)k * n;
+            if (VEC == 4) {
+                if (obs) st_stream(reinterpret_cast<uint4*>(obs + off) + g, make_uint4(oo[0], oo[1 % VEC], oo[2 % VEC], oo[3 % VEC]));
+                if (reward) st_stream(reinterpret_cast<uint4*>(reward + off) + g, make_uint4(rr[0], rr[1 % VEC], rr[2 % VEC], rr[3 % VEC]));
+                if (flags) st_stream(reinterpret_cast<uint32_t*>(flags + off) + g, ff);
+            } else {
+                if (obs) obs[off + i0] = (int32_t)oo[0];
+                if (reward) reward[off + i0] = __uint_as_float(rr[0]);
+                if (flags) flags[off + i0] = (uint8_t)ff;
+            }
+        }
+        if (VEC == 4) reinterpret_cast<uint4*>(state)[g] = make_uint4(s[0], s[1 % VEC], s[2 % VEC], s[3 % VEC]);
+        else state[i0] = s[0];
+    }
+    if (stats) {
+        uint32_t v[6] = { c_ep, c_ga, c_gb, c_tr, c_steps, c_len };
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            const uint32_t r = __reduce_add_sync(0xFFFFFFFFu, v[j]);
+            if ((threadIdx.x & 31) == 0 && r) atomicAdd(&blk_stats[j], r);
+        }
+        __syncthreads();
+        if (threadIdx.x < 6 && blk_stats[threadIdx.x])
+            atomicAdd(&stats[threadIdx.x], (unsigned long long)blk_stats[threadIdx.x]);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_convert_state(const PitchDev P, int32_t nS, const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
+                int32_t to_layout, int64_t n)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t s = in[i];
+        if (to_layout == SOCCER_LAYOUT_INDEX) {
+            const uint32_t a = s & 0xFFu, b = (s >> 8) & 0xFFu, p = (s >> 24) & 1u, t = (s >> 16) & 0xFFu;
+            const bool bad = ((a | b) & kGoalBit) || (s & kNeedsReset);
+            out[i] = (bad ? 0u : (uint32_t)obs_index(P, a, b, p)) | (t << 16);
+        } else {
+            const int32_t o = (int32_t)(s & 0xFFFFu);
+            const uint32_t t = (s >> 16) & 0xFFu;
+            out[i] = (o >= 1 && o < nS) ? (obs_to_packed(P, o) | (t << 16)) : (kNeedsReset | kGoalBit | (t << 16));
+        }
+    }
+}
+
+int table_bytes_of(const PitchDev& P, int64_t* bytes)
+{
+    const int64_t nS = 1 + 2 * (int64_t)P.F * P.Fm1;
+    if (nS - 1 > kMaxTableStates || P.slip) return SOCCER_ETABLE;
+    *bytes = ((nS - 1) * 200 + 15) / 16 * 16;
+    return SOCCER_OK;
+}
+
+int grid_for(int64_t work_items, int blocks_per_sm)
+{
+    const int64_t need = (work_items + kThreads - 1) / kThreads;
+    const int64_t cap = (int64_t)sm_count() * blocks_per_sm;
+    int64_t g = need < cap ? need : cap;
+    return (int)(g < 1 ? 1 : g);
+}
+
+int launch_generic(const PitchDev& P, const StepOpts& o, cudaStream_t stream)
+{
+    if (o.n == 0) return SOCCER_OK;
+    static const int nb = resident_blocks(k_step_generic);
+    k_step_generic<<<grid_for(o.n, nb), kThreads, 0, stream>>>(P, o);
+    return launch_status();
+}
+
+int table_grid(int64_t n_groups)
+{
+    const int64_t need = (n_groups + kTableThreads - 1) / kTableThreads;
+    const int64_t cap = sm_count();
+    return (int)(need < cap ? (need < 1 ? 1 : need) : cap);
+}
+
+template <typename Kern>
+int allow_big_smem(Kern k, int64_t bytes)
+{
+    return (int)cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+} // namespace soccer
+
+// ====================================================================== C ABI
+extern "C" {
+
+int soccer_abi_version(void) { return SOCCER_ABI_VERSION; }
+
+int soccer_pitch_info_host(const soccer_pitch* pitch, soccer_pitch_info* out) { return fill_info(pitch, out); }
+
+int soccer_pack_state_host(const soccer_pitch* pitch, const int32_t tuple[5], int32_t timestep,
+                           int32_t needs_reset, uint32_t* packed)
+{
+    if (!pitch || !tuple || !packed) return SOCCER_EINVAL;
+    if (!pitch_ok(pitch)) return SOCCER_EPITCH;
+    const int w = pitch->width, H = pitch->height, W = w + 2;
+    int rows[3], ng; goal_rows_of(H, rows, &ng);
+    const int xa = tuple[0], ya = tuple[1], xb = tuple[2], yb = tuple[3], p = tuple[4];
+    if (xa < 0 || xa >= H || xb < 0 || xb >= H || ya < 0 || ya >= W || yb < 0 || yb >= W || p < 0 || p > 1 ||
+        timestep < 0 || timestep > 255)
+        return SOCCER_EINVAL;
+    auto in_gr = [&](int x) { for (int i = 0; i < ng; ++i) if (rows[i] == x) return true; return false; };
+    auto code = [&](int x, int y, bool has, uint32_t* c) {
+        if (y == 0 || y == W - 1) {
+            if (!in_gr(x) || !has) return false;            // SIM:74-83 unreachable
+            *c = kGoalBit | (y != 0 ? kRightBit : 0u) | (uint32_t)x;
+        } else *c = field_code(w, x, y);
+        return true;
+    };
+    uint32_t a, b;
+    if (!code(xa, ya, p == 0, &a) || !code(xb, yb, p == 1, &b)) return SOCCER_EINVAL;
+    if (xa == xb && ya == yb) return SOCCER_EINVAL;         // SIM:86-88
+    *packed = a | (b << 8) | ((uint32_t)timestep << 16) | ((uint32_t)p << 24) | (needs_reset ? kNeedsReset : 0u);
+    return SOCCER_OK;
+}
+
+int soccer_unpack_state_host(const soccer_pitch* pitch, uint32_t packed, int32_t tuple[5],
+                             int32_t* timestep, int32_t* needs_reset)
+{
+    if (!pitch || !tuple) return SOCCER_EINVAL;
+    if (!pitch_ok(pitch)) return SOCCER_EPITCH;
+    const int w = pitch->width;
+    auto dec = [&](uint32_t c, int32_t* x, int32_t* y) {
+        if (c & kGoalBit) { *x = (int32_t)(c & 0x3Fu); *y = (c & kRightBit) ? w + 1 : 0; }
+        else { *x = (int32_t)c / w; *y = (int32_t)c % w + 1; }
+    };
+    dec(packed & 0xFFu, &tuple[0], &tuple[1]);
+    dec((packed >> 8) & 0xFFu, &tuple[2], &tuple[3]);
+    tuple[4] = (int32_t)((packed >> 24) & 1u);
+    if (timestep) *timestep = (int32_t)((packed >> 16) & 0xFFu);
+    if (needs_reset) *needs_reset = (packed & kNeedsReset) ? 1 : 0;
+    return SOCCER_OK;
+}
+
+int soccer_state_to_obs_host(const soccer_pitch* pitch, uint32_t packed, int32_t* obs)
+{
+    if (!pitch || !obs) return SOCCER_EINVAL;
+    if (!pitch_ok(pitch)) return SOCCER_EPITCH;
+    const uint32_t a = packed & 0xFFu, b = (packed >> 8) & 0xFFu, p = (packed >> 24) & 1u;
+    const int F = pitch->width * pitch->height;
+    if ((a | b) & kGoalBit) { *obs = 0; return SOCCER_OK; }   // SIM:493
+    if ((int)a >= F || (int)b >= F || a == b) return SOCCER_EINVAL;
+    *obs = host_obs_index(F, a, b, p);
+    return SOCCER_OK;
+}
+
+int soccer_obs_to_state_host(const soccer_pitch* pitch, int32_t obs, uint32_t* packed)
+{
+    if (!pitch || !packed) return SOCCER_EINVAL;
+    if (!pitch_ok(pitch)) return SOCCER_EPITCH;
+    const int F = pitch->width * pitch->height;
+    if (obs < 1 || obs >= 1 + 2 * F * (F - 1)) return SOCCER_EINVAL;
+    const uint32_t idx = (uint32_t)(obs - 1), p = idx & 1u, q = idx >> 1;
+    const uint32_t a = q / (uint32_t)(F - 1), rb = q % (uint32_t)(F - 1), b = rb + (rb >= a ? 1u : 0u);
+    *packed = a | (b << 8) | (p << 24);
+    return SOCCER_OK;
+}
+
+int soccer_reset(const soccer_pitch* pitch, uint32_t* state, int32_t* obs_out, const uint8_t* rng8,
+                 const uint8_t* mask, int64_t n, soccer_stream_t stream)
+{
+    if (!state || !rng8 || n < 0) return SOCCER_EINVAL;
+    PitchDev P; const int rc = make_pitch_dev(pitch, &P); if (rc) return rc;
+    if (n == 0) return SOCCER_OK;
+    k_reset<<<grid_for(n, 8), kThreads, 0, (cudaStream_t)stream>>>(P, state, obs_out, rng8, mask, 0, 0, 0, 0, n);
+    return launch_status();
+}
+
+int soccer_reset_philox(const soccer_pitch* pitch, uint32_t* state, int32_t* obs_out, const uint8_t* mask,
+                        uint64_t seed, uint64_t step, uint64_t env_id_base, int64_t n, soccer_stream_t stream)
+{
+    if (!state || n < 0) return SOCCER_EINVAL;
+    PitchDev P; const int rc = make_pitch_dev(pitch, &P); if (rc) return rc;
+    if (n == 0) return SOCCER_OK;
+    k_reset<<<grid_for(n, 8), kThreads, 0, (cudaStream_t)stream>>>(P, state, obs_out, nullptr, mask, 1, seed, step,
+                                                                    env_id_base, n);
+    return launch_status();
+}
+
+int soccer_set_state(const soccer_pitch* pitch, uint32_t* state, const int32_t* obs_in,
+                     const int32_t* timestep_in, int64_t n, soccer_stream_t stream)
+{
+    if (!state || !obs_in || n < 0) return SOCCER_EINVAL;
+    PitchDev P; const int rc = make_pitch_dev(pitch, &P); if (rc) return rc;
+    if (n == 0) return SOCCER_OK;
+    const int nS = 1 + 2 * P.F * P.Fm1;
+    k_set_state<<<grid_for(n, 8), kThreads, 0, (cudaStream_t)stream>>>(P, nS, state, obs_in, timestep_in, n);
+    return launch_status();
+}
+
+int soccer_get_obs(const soccer_pitch* pitch, const uint32_t* state, int32_t* obs_out, int64_t n,
+                   soccer_stream_t stream)
+{
+    if (!state || !obs_out || n < 0) return SOCCER_EINVAL;
+    PitchDev P; const int rc = make_pitch_dev(pitch, &P); if (rc) return rc;
+    if (n == 0) return SOCCER_OK;
+    k_get_obs<<<grid_for(n, 8), kThreads, 0, (cudaStream_t)stream>>>(P, state, obs_out, n);
+    return launch_status();
+}
+
+int soccer_step_ex(const soccer_pitch* pitch, const soccer_step_args* a, soccer_stream_t stream)
+{
+    if (!a || !a->state || a->n < 0) return SOCCER_EINVAL;
+    if (a->policy_a && a->policy_b) return SOCCER_EPOLICY;                 // SIM:38
+    if ((!a->policy_a && !a->act_a) || (!a->policy_b && !a->act_b)) return SOCCER_EINVAL;
+    if (!a->use_philox && !a->rng8) return SOCCER_EINVAL;
+    PitchDev P; const int rc = make_pitch_dev(pitch, &P); if (rc) return rc;
+    if (P.slip && !a->use_philox && !a->rng32 && !a->rngf64) return SOCCER_ESLIP;
+    if (a->n == 0) return SOCCER_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+
+    if (a->reserved != 0) return SOCCER_EINVAL;
+    const bool fast_ok = !P.slip && !a->use_philox && a->auto_reset && !a->detail && !a->policy_a && !a->policy_b &&
+                         a->obs && a->reward && a->flags && a->n >= 4 &&
+                         aligned(a->state, 16) && aligned(a->obs, 16) && aligned(a->reward, 16) &&
+                         (!a->reset_obs || aligned(a->reset_obs, 16)) && aligned(a->act_a, 4) &&
+                         aligned(a->act_b, 4) && aligned(a->rng8, 4) && aligned(a->flags, 4);
+    int64_t done_n = 0;
+    if (fast_ok) {
+        const int64_t n_groups = a->n / 4;
+        if (a->reset_obs) {
+            static const int nb = resident_blocks(k_step_fast<true>);
+            k_step_fast<true><<<grid_for(n_groups, nb), kThreads, 0, st>>>(
+                P, a->state, a->act_a, a->act_b, a->rng8, a->obs, a->reward, a->flags, a->reset_obs, n_groups);
+        } else {
+            static const int nb = resident_blocks(k_step_fast<false>);
+            k_step_fast<false><<<grid_for(n_groups, nb), kThreads, 0, st>>>(
+                P, a->state, a->act_a, a->act_b, a->rng8, a->obs, a->reward, a->flags, nullptr, n_groups);
+        }
+        const int e = launch_status();
+        if (e) return e;
+        done_n = n_groups * 4;
+        if (done_n == a->n) return SOCCER_OK;
+    }
+    StepOpts o;
+    const int64_t k = done_n;
+    o.state = a->state + k;
+    o.act_a = a->act_a ? a->act_a + k : nullptr;
+    o.act_b = a->act_b ? a->act_b + k : nullptr;
+    o.rng8 = a->rng8 ? a->rng8 + k : nullptr;
+    o.rng32 = a->rng32 ? a->rng32 + k : nullptr;
+    o.rngf64 = a->rngf64 ? a->rngf64 + k : nullptr;
+    o.policy_a = a->policy_a; o.policy_b = a->policy_b;
+    o.obs = a->obs ? a->obs + k : nullptr;
+    o.reward = a->reward ? a->reward + k : nullptr;
+    o.flags = a->flags ? a->flags + k : nullptr;
+    o.reset_obs = a->reset_obs ? a->reset_obs + k : nullptr;
+    o.n = a->n - k; o.auto_reset = a->auto_reset; o.use_philox = a->use_philox; o.detail = a->detail;
+    o.seed = a->seed; o.step = a->step; o.env_id_base = a->env_id_base + (uint64_t)k;
+    return launch_generic(P, o, st);
+}
+
+int soccer_step(const soccer_pitch* pitch, uint32_t* state, const uint8_t* act_a, const uint8_t* act_b,
+                const uint8_t* rng8, int32_t* obs, float* reward, uint8_t* flags, int32_t* reset_obs,
+                int64_t n, soccer_stream_t stream)
+{
+    if (!obs || !reward || !flags) return SOCCER_EINVAL;
+    if (pitch && pitch->slip_prob != 0.0) return SOCCER_ESLIP;
+    soccer_step_args a = {};
+    a.state = state; a.act_a = act_a; a.act_b = act_b; a.rng8 = rng8; a.obs = obs; a.reward = reward;
+    a.flags = flags; a.reset_obs = reset_obs; a.n = n; a.auto_reset = 1;
+    return soccer_step_ex(pitch, &a, stream);
+}
+
+int soccer_step_philox(const soccer_pitch* pitch, uint32_t* state, const uint8_t* act_a, const uint8_t* act_b,
+                       uint64_t seed, uint64_t step, uint64_t env_id_base, int32_t* obs, float* reward,
+                       uint8_t* flags, int32_t* reset_obs, int64_t n, soccer_stream_t stream)
+{
+    if (!obs || !reward || !flags) return SOCCER_EINVAL;
+    soccer_step_args a = {};
+    a.state = state; a.act_a = act_a; a.act_b = act_b; a.obs = obs; a.reward = reward; a.flags = flags;
+    a.reset_obs = reset_obs; a.n = n; a.auto_reset = 1; a.use_philox = 1; a.seed = seed; a.step = step;
+    a.env_id_base = env_id_base;
+    return soccer_step_ex(pitch, &a, stream);
+}
+
+int soccer_rollout(const soccer_pitch* pitch, uint32_t* state, const int8_t* policy_a, const int8_t* policy_b,
+                   uint64_t seed, uint64_t step0, int32_t K, uint64_t env_id_base, int32_t* obs, float* reward,
+                   uint8_t* flags, unsigned long long* stats, int64_t n, soccer_stream_t stream)
+{
+    if (!state || n < 0 || K < 0) return SOCCER_EINVAL;
+    PitchDev P; const int rc = make_pitch_dev(pitch, &P); if (rc) return rc;
+    if (P.slip) return SOCCER_ESLIP;
+    if (n == 0 || K == 0) return SOCCER_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool vec = (n % 4 == 0) && aligned(state, 16) && (!obs || aligned(obs, 16)) &&
+                     (!reward || aligned(reward, 16)) && (!flags || aligned(flags, 4));
+    if (vec) {
+        static const int nb = resident_blocks(k_rollout<4>);
+        k_rollout<4><<<grid_for(n / 4, nb), kThreads, 0, st>>>(P, state, policy_a, policy_b, seed, step0, K,
+                                                                env_id_base, obs, reward, flags, stats, n);
+    } else {
+        static const int nb = resident_blocks(k_rollout<1>);
+        k_rollout<1><<<grid_for(n, nb), kThreads, 0, st>>>(P, state, policy_a, policy_b, seed, step0, K,
+                                                            env_id_base, obs, reward, flags, stats, n);
+    }
+    return launch_status();
+}
+
+int soccer_sweep(const soccer_pitch* pitch, int32_t n_combos, uint8_t* n_out, uint32_t* next_state,
+                 int32_t* next_obs, int8_t* reward, uint8_t* done, soccer_stream_t stream)
+{
+    if (n_combos != 1 && n_combos != 9) return SOCCER_EINVAL;
+    PitchDev P; const int rc = make_pitch_dev(pitch, &P); if (rc) return rc;
+    const int nS = 1 + 2 * P.F * P.Fm1;
+    const int64_t total = (int64_t)(nS - 1) * 25 * n_combos;
+    k_sweep<<<grid_for(total, 4), kThreads, 0, (cudaStream_t)stream>>>(P, n_combos, nS, n_out, next_state,
+                                                                        next_obs, reward, done);
+    return launch_status();
+}
+
+int soccer_step_table_bytes_host(const soccer_pitch* pitch, int64_t* bytes)
+{
+    if (!bytes) return SOCCER_EINVAL;
+    PitchDev P; const int rc = make_pitch_dev(pitch, &P); if (rc) return rc;
+    return table_bytes_of(P, bytes);
+}
+
+int soccer_build_step_table(const soccer_pitch* pitch, uint16_t* table, soccer_stream_t stream)
+{
+    if (!table) return SOCCER_EINVAL;
+    PitchDev P; int rc = make_pitch_dev(pitch, &P); if (rc) return rc;
+    int64_t bytes; rc = table_bytes_of(P, &bytes); if (rc) return rc;
+    k_build_step_table<<<grid_for((int64_t)(P.nS - 1) * 100, 4), kThreads, 0, (cudaStream_t)stream>>>(P, P.nS, table);
+    return launch_status();
+}
+
+int soccer_step_table(const soccer_pitch* pitch, const uint16_t* table, uint32_t* state, const uint8_t* act_a,
+                      const uint8_t* act_b, const uint8_t* rng8, int32_t* obs, float* reward, uint8_t* flags,
+                      int32_t* reset_obs, int64_t n, soccer_stream_t stream)
+{
+    if (!table || !state || !act_a || !act_b || !rng8 || !obs || !reward || !flags || n < 0) return SOCCER_EINVAL;
+    PitchDev P; int rc = make_pitch_dev(pitch, &P); if (rc) return rc;
+    int64_t bytes; rc = table_bytes_of(P, &bytes); if (rc) return rc;
+    if (!aligned(table, 16)) return SOCCER_EINVAL;
+    if (n == 0) return SOCCER_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool vec = n >= 4 && aligned(state, 16) && aligned(obs, 16) && aligned(reward, 16) &&
+                     (!reset_obs || aligned(reset_obs, 16)) && aligned(act_a, 4) && aligned(act_b, 4) &&
+                     aligned(rng8, 4) && aligned(flags, 4);
+    int64_t done_n = 0;
+    if (vec) {
+        const int64_t n_groups = n / 4;
+        if (reset_obs) {
+            static const int e0 = allow_big_smem(k_step_table<true>, 227 * 1024);
+            if (e0) return e0;
+            k_step_table<true><<<table_grid(n_groups), kTableThreads, bytes, st>>>(
+                P, table, (uint32_t)bytes, state, act_a, act_b, rng8, obs, reward, flags, reset_obs, n_groups);
+        } else {
+            static const int e0 = allow_big_smem(k_step_table<false>, 227 * 1024);
+            if (e0) return e0;
+            k_step_table<false><<<table_grid(n_groups), kTableThreads, bytes, st>>>(
+                P, table, (uint32_t)bytes, state, act_a, act_b, rng8, obs, reward, flags, nullptr, n_groups);
+        }
+        const int e = launch_status();
+        if (e) return e;
+        done_n = n_groups * 4;
+        if (done_n == n) return SOCCER_OK;
+    }
+    const int64_t k = done_n, m = n - k;
+    k_step_table_scalar<<<grid_for(m, 8), kThreads, 0, st>>>(P, table, state + k, act_a + k, act_b + k, rng8 + k,
+                                                             obs + k, reward + k, flags + k,
+                                                             reset_obs ? reset_obs + k : nullptr, m);
+    return launch_status();
+}
+
+int soccer_rollout_table(const soccer_pitch* pitch, const uint16_t* table, uint32_t* state, uint64_t seed,
+                         uint64_t step0, int32_t K, uint64_t env_id_base, int32_t* obs, float* reward,
+                         uint8_t* flags, unsigned long long* stats, int64_t n, soccer_stream_t stream)
+{
+    if (!table || !state || n < 0 || K < 0) return SOCCER_EINVAL;
+    PitchDev P; int rc = make_pitch_dev(pitch, &P); if (rc) return rc;
+    int64_t bytes; rc = table_bytes_of(P, &bytes); if (rc) return rc;
+    if (!aligned(table, 16)) return SOCCER_EINVAL;
+    if (n == 0 || K == 0) return SOCCER_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool vec = (n % 4 == 0) && aligned(state, 16) && (!obs || aligned(obs, 16)) &&
+                     (!reward || aligned(reward, 16)) && (!flags || aligned(flags, 4));
+    if (vec) {
+        static const int e0 = allow_big_smem(k_rollout_table<4>, 227 * 1024);
+        if (e0) return e0;
+        k_rollout_table<4><<<table_grid(n / 4), kTableThreads, bytes, st>>>(P, table, (uint32_t)bytes, state, seed, step0, K,
+                                                                            env_id_base, obs, reward, flags, stats, n);
+    } else {
+        static const int e0 = allow_big_smem(k_rollout_table<1>, 227 * 1024);
+        if (e0) return e0;
+        k_rollout_table<1><<<table_grid(n), kTableThreads, bytes, st>>>(P, table, (uint32_t)bytes, state, seed, step0, K,
+                                                                        env_id_base, obs, reward, flags, stats, n);
+    }
+    return launch_status();
+}
+
+int soccer_convert_state(const soccer_pitch* pitch, const uint32_t* in, uint32_t* out, int32_t to_layout, int64_t n,
+                         soccer_stream_t stream)
+{
+    if (!in || !out || n < 0 || (to_layout != SOCCER_LAYOUT_CELL && to_layout != SOCCER_LAYOUT_INDEX)) return SOCCER_EINVAL;
+    PitchDev P; const int rc = make_pitch_dev(pitch, &P); if (rc) return rc;
+    if (n == 0) return SOCCER_OK;
+    k_convert_state<<<grid_for(n, 8), kThreads, 0, (cudaStream_t)stream>>>(P, P.nS, in, out, to_layout, n);
+    return launch_status();
+}
+
+int soccer_dense(const soccer_pitch* pitch, const int8_t* policy_a, const int8_t* policy_b, double* Pmat,
+                 double* Rmat, soccer_stream_t stream)
+{
+    if (!Pmat || !Rmat) return SOCCER_EINVAL;
+    if (policy_a && policy_b) return SOCCER_EPOLICY;
+    PitchDev P; const int rc = make_pitch_dev(pitch, &P); if (rc) return rc;
+    soccer_pitch_info info; fill_info(pitch, &info);
+    const int nS = info.nS, nkeys = (policy_a || policy_b) ? 5 : 25;
+    // goal states (SIM:91-103): holder in one of 2*n_goal_rows goal cells, the other player on any
+    // field cell, either player holding
+    const int n_goal_states = 2 * (2 * info.n_goal_rows) * info.n_field_cells;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(Pmat, 0, sizeof(double) * (size_t)nS * nS * nkeys, st);
+    if (e != cudaSuccess) return (int)e;
+    k_dense<<<grid_for((int64_t)nS * nkeys, 4), kThreads, 0, st>>>(P, nS, n_goal_states, policy_a, policy_b, Pmat, Rmat);
+    return launch_status();
+}
+
+} // extern "C"

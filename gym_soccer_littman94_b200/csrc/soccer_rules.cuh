@@ -1,0 +1,264 @@
+// soccer_rules.cuh -- device-side game rules shared by every kernel (sm_100a).
+//
+// Formulation (NOT the reference's): players live on cell codes (one byte), the wall clamp and
+// goal-mouth rule of SIM:364-373 are folded into a per-CTA shared-memory candidate table
+// cand[cell][has_ball][move] that every CTA computes arithmetically at start-up (<= 2 KB), and
+// the four collision cases of SIM:315-356 collapse into five byte compares and a handful of
+// predicate ops.  SIM = /root/reference/gym_soccer/envs/soccer_simultaneous_env.py.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace soccer {
+
+constexpr int kMaxField = 126;          // F = width*height must fit a 7-bit cell code
+constexpr int kLutBytes = 256 * 16;     // cand[cell][has][8 moves]; sized so ANY byte-valued cell code stays in bounds
+constexpr uint32_t kGoalBit = 0x80u;    // cell code of a goal cell: 0x80 | right<<6 | row
+constexpr uint32_t kRightBit = 0x40u;
+constexpr uint32_t kNeedsReset = 1u << 25;
+constexpr int kMaxT = 100;              // SIM:404
+
+// Kernel-parameter copy of the pitch (constructor products, SIM:48-65, 146-165).
+struct PitchDev {
+    int32_t  w;              // unpadded width
+    int32_t  H;
+    int32_t  F;              // w*H
+    int32_t  Fm1;
+    int32_t  nS;             // 1 + 2F(F-1)
+    uint32_t goal_row_mask;  // bit r set iff r in goal_rows (SIM:60)
+    uint32_t isd_state[4];   // packed start states (2-start pitches: s0,s0,s1,s1 so idx = r)
+    int32_t  isd_obs[4];
+    uint32_t isd_d1, isd_d2; // isd_state[r] == isd_state[0] + (r&1)*d1 + (r>>1)*d2  (mod 2^32)
+    int32_t  obs_d1, obs_d2; // same for isd_obs
+    double   mp[9];          // slip-combination probabilities (SIM:209-223)
+    int32_t  slip;           // 1 iff slip_prob != 0
+};
+
+// slipped move ids in the order of SIM:205-206: mas[0] = (-dr, dc), mas[1] = (dr, -dc)
+//   NOOP->NOOP, N->(E,W), S->(W,E), E->(S,N), W->(N,S)
+__device__ __forceinline__ uint32_t slip_move(uint32_t act, int which)
+{
+    // nibble tables indexed by action: which==0: [0,3,4,2,1], which==1: [0,4,3,1,2]
+    const uint32_t t = which == 0 ? 0x12430u : 0x21340u;
+    return (t >> (act * 4)) & 7u;
+}
+// move used by player A / B in slip combination c (SIM:209-223): 0 intended, 1 mas[0], 2 mas[1]
+__device__ __forceinline__ int combo_a(int c) { return (int)((0x221121000ull >> (c * 4)) & 3ull); } // [0,0,0,1,2,1,1,2,2]
+__device__ __forceinline__ int combo_b(int c) { return (int)((0x212100210ull >> (c * 4)) & 3ull); } // [0,1,2,0,0,1,2,1,2]
+
+// SIM:364-373 for one (cell, has_ball, move) -> candidate cell code.
+__device__ __forceinline__ uint32_t next_cell_code(const PitchDev& P, uint32_t cell, uint32_t has, uint32_t move)
+{
+    int row = (int)cell / P.w;
+    int col = (int)cell - row * P.w + 1;                 // padded column 1..w
+    int dr = (move == 2) - (move == 1);                  // SIM:26-29 (d_col, d_row)
+    int dc = (move == 3) - (move == 4);
+    int nx = min(max(row + dr, 0), P.H - 1);             // SIM:365
+    int ny = col + dc;                                   // SIM:366
+    bool xoob = (ny == 0) || (ny == P.w + 1);            // SIM:369
+    bool goal = xoob && ((P.goal_row_mask >> nx) & 1u) && has; // SIM:370
+    if (xoob && !goal) ny = col;                         // SIM:371-372
+    if (ny == 0 || ny == P.w + 1)
+        return kGoalBit | (ny != 0 ? kRightBit : 0u) | (uint32_t)nx;
+    return (uint32_t)(nx * P.w + ny - 1);
+}
+
+// Every CTA fills its own candidate table; index = cell*16 + has*8 + move.
+__device__ __forceinline__ void build_cand_lut(uint8_t* lut, const PitchDev& P)
+{
+    for (int i = threadIdx.x; i < kLutBytes; i += blockDim.x) {
+        uint32_t move = i & 7, has = (i >> 3) & 1, cell = i >> 4;
+        // cells >= F never occur in a valid state; map them to themselves so garbage stays inert
+        lut[i] = cell < (uint32_t)P.F ? (uint8_t)next_cell_code(P, cell, has, move > 4 ? 0u : move) : (uint8_t)cell;
+    }
+    __syncthreads();
+}
+
+// Simultaneous-move resolution, SIM:296-362, for field-cell states.
+//   a, b    current cell codes; p possession; ma, mb the moves actually attempted (slipped or
+//   not); a_noop / b_noop whether the ORIGINAL actions were NOOP (SIM:330-331, 338-339);
+//   r       2-bit outcome index: 4-way outcome r (SIM:352-356 order), 2-way outcome r >> 1.
+// Returns final cells / possession and log2(number of outcomes).
+//
+// With cell codes the four cases reduce to (proof in DESIGN.md "Collision algebra"):
+//   aib = A's candidate is B's cell, bia = B's candidate is A's cell,
+//   ast / bst = candidate equals own cell (NOOP or bounce)
+//   stay  = (aib & (bia | bst)) | (bia & ast)          cases 1, 2, 3: nobody moves
+//   c2    = (aib & b_noop) | (bia & a_noop)            case 2: possession flips
+//   four  = (na == nb) & !stay                         case 4
+struct Resolved { uint32_t a, b, p, nlog2; };
+
+__device__ __forceinline__ Resolved resolve(const uint8_t* __restrict__ lut, uint32_t a, uint32_t b,
+                                            uint32_t p, uint32_t ma, uint32_t mb, bool a_noop,
+                                            bool b_noop, uint32_t r)
+{
+    const uint32_t p8 = p << 3;
+    const uint32_t na = lut[(a << 4) + 8u - p8 + (ma & 7u)];   // A has the ball iff p == 0 (SIM:308)
+    const uint32_t nb = lut[(b << 4) + p8 + (mb & 7u)];        // SIM:309
+    // bitwise (not short-circuit) boolean algebra keeps this branch-free
+    const bool aib = na == b, bia = nb == a, ast = na == a, bst = nb == b;
+    const bool stay = (aib & (bia | bst)) | (bia & ast);
+    const bool c2 = (aib & b_noop) | (bia & a_noop);
+    const bool four = (na == nb) & !stay;
+    const bool rhi = (r & 2u) != 0;
+    const bool move_a = !stay & (!four | rhi);          // SIM:352-356: slots 0,1 B moves; 2,3 A moves
+    const bool move_b = !stay & (!four | !rhi);
+    Resolved o;
+    o.a = move_a ? na : a;
+    o.b = move_b ? nb : b;
+    const uint32_t rsel = four ? (r & 1u) : (r >> 1);
+    const uint32_t pc = c2 ? (p ^ 1u) : rsel;
+    o.p = (stay | four) ? pc : p;
+    o.nlog2 = four ? 2u : ((stay & !c2) ? 1u : 0u);
+    return o;
+}
+
+// SIM:487-494 closed form (field-cell states only).
+__device__ __forceinline__ int32_t obs_index(const PitchDev& P, uint32_t a, uint32_t b, uint32_t p)
+{
+    return 1 + 2 * ((int)a * P.Fm1 + (int)b - (b > a ? 1 : 0)) + (int)p;
+}
+
+// inverse of obs_index for 1 <= obs < nS
+__device__ __forceinline__ uint32_t obs_to_packed(const PitchDev& P, int32_t obs)
+{
+    uint32_t idx = (uint32_t)(obs - 1);
+    uint32_t p = idx & 1u, q = idx >> 1;
+    uint32_t a = q / (uint32_t)P.Fm1;
+    uint32_t rb = q - a * (uint32_t)P.Fm1;
+    uint32_t b = rb + (rb >= a ? 1u : 0u);
+    return a | (b << 8) | (p << 24);
+}
+
+// ---- Philox4x32-10 (Salmon et al. SC'11), one call = the words of 4 consecutive steps ----
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t out[4])
+{
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const unsigned long long p0 = (unsigned long long)0xD2511F53u * c0;
+        const unsigned long long p1 = (unsigned long long)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__device__ __forceinline__ uint32_t philox_word(uint64_t seed, uint64_t env_id, uint64_t step)
+{
+    const uint64_t blk = step >> 2;
+    uint32_t o[4];
+    philox4x32_10((uint32_t)env_id, (uint32_t)(env_id >> 32), (uint32_t)blk, (uint32_t)(blk >> 32),
+                  (uint32_t)seed, (uint32_t)(seed >> 32), o);
+    const uint32_t k = (uint32_t)step & 3u;
+    return k == 0 ? o[0] : (k == 1 ? o[1] : (k == 2 ? o[2] : o[3]));
+}
+
+// decode: joint action uniform on 0..24 from the low 24 bits; rng8-compatible nibble from 24..27
+__device__ __forceinline__ void philox_actions(uint32_t w, uint32_t& aa, uint32_t& ab)
+{
+    const uint32_t ja = ((w & 0xFFFFFFu) * 25u) >> 24;
+    aa = (ja * 52u) >> 8;      // ja / 5 for ja < 25
+    ab = ja - aa * 5u;
+}
+__device__ __forceinline__ uint32_t philox_rng8(uint32_t w) { return (w >> 24) & 0xFu; }
+
+// ---- one env-step given the chosen outcome: terminal detection, reward, obs, bookkeeping ----
+struct StepOut {
+    uint32_t state;     // next packed state (post-reset when auto-reset fired)
+    int32_t  obs;       // what the reference's step() returned
+    float    reward;
+    uint32_t flags;
+    int32_t  reset_obs;
+};
+
+template <bool AUTO_RESET, bool DETAIL = true>
+__device__ __forceinline__ StepOut finish_step(const PitchDev& P, Resolved o, uint32_t t, uint32_t combo,
+                                               uint32_t reset_sel, bool flip_reward)
+{
+    StepOut out;
+    const uint32_t hc = o.p ? o.b : o.a;                    // cell of the ball holder
+    const bool done = (hc & kGoalBit) != 0;                 // SIM:237-238 (goal states, SIM:91-103)
+    // +1 in the right-hand goal column (A scores / B own goal), -1 in the left (SIM:94-102);
+    // flipped for a single-agent player_b env (SIM:243-244; compared by value, -0.0 == 0.0)
+    const bool plus = ((hc & kRightBit) != 0) != flip_reward;
+    const float rew = done ? (plus ? 1.0f : -1.0f) : 0.0f;
+    const int32_t q = (int)o.a * P.Fm1 + (int)o.b;          // SIM:487-494 closed form
+    const int32_t obs_live = 2 * q + (int)o.p + (o.b > o.a ? -1 : 1);
+    const int32_t obs = done ? 0 : obs_live;                // SIM:493
+    const uint32_t t1 = t + 1;                              // SIM:399
+    const bool trunc = t1 >= (uint32_t)kMaxT;               // SIM:404
+    const bool reset = done | trunc;                        // SIM:406
+    const uint32_t st = __byte_perm(__byte_perm(o.a, o.b, 0x4440), t1 | (o.p << 8), 0x5410);
+    out.obs = obs;
+    out.reward = rew;
+    out.flags = (done ? 1u : 0u) | (trunc ? 2u : 0u);
+    if (DETAIL) out.flags |= (o.nlog2 << 2) | (combo << 4);
+    if (AUTO_RESET) {
+        // SIM:410-424 fused: isd index = floor(n_isd * u) for the injected 2-bit draw
+        const uint32_t m1 = (reset_sel & 1u) ? 0xFFFFFFFFu : 0u, m2 = (reset_sel & 2u) ? 0xFFFFFFFFu : 0u;
+        const uint32_t rs = P.isd_state[0] + (m1 & P.isd_d1) + (m2 & P.isd_d2);
+        const int32_t ro = P.isd_obs[0] + (int32_t)(m1 & (uint32_t)P.obs_d1) + (int32_t)(m2 & (uint32_t)P.obs_d2);
+        out.state = reset ? rs : st;
+        out.reset_obs = reset ? ro : obs;
+    } else {
+        out.state = st | (reset ? kNeedsReset : 0u);
+        out.reset_obs = obs;
+    }
+    return out;
+}
+
+// slip_prob == 0 step of one env (the hot path)
+template <bool AUTO_RESET, bool DETAIL = true>
+__device__ __forceinline__ StepOut step_noslip(const PitchDev& P, const uint8_t* __restrict__ lut,
+                                               uint32_t s, uint32_t aa, uint32_t ab, uint32_t rng,
+                                               bool flip_reward)
+{
+    const uint32_t a = s & 0xFFu, b = (s >> 8) & 0xFFu, t = (s >> 16) & 0xFFu, p = (s >> 24) & 1u;
+    const Resolved o = resolve(lut, a, b, p, aa, ab, aa == 0, ab == 0, rng & 3u);
+    return finish_step<AUTO_RESET, DETAIL>(P, o, t, 0u, (rng >> 2) & 3u, flip_reward);
+}
+
+// slip_prob > 0 step of one env: walk the outcome list of SIM:209-256 in order, accumulating
+// p = mp * nsp sequentially in fp64 (no FMA), and take the first entry whose running sum
+// exceeds u -- gym's categorical_sample (argmax(cumsum > u), all-False -> 0).
+template <bool AUTO_RESET>
+__device__ __forceinline__ StepOut step_slip(const PitchDev& P, const uint8_t* __restrict__ lut,
+                                             uint32_t s, uint32_t aa, uint32_t ab, double u,
+                                             uint32_t reset_sel, bool flip_reward)
+{
+    const uint32_t a = s & 0xFFu, b = (s >> 8) & 0xFFu, t = (s >> 16) & 0xFFu, p = (s >> 24) & 1u;
+    const uint32_t as0 = slip_move(aa, 0), as1 = slip_move(aa, 1);
+    const uint32_t bs0 = slip_move(ab, 0), bs1 = slip_move(ab, 1);
+    double cs = 0.0;
+    bool found = false, have_first = false;
+    Resolved pick = { a, b, p, 0u }, first = pick;
+    uint32_t pick_c = 0, first_c = 0;
+#pragma unroll 1
+    for (int c = 0; c < 9; ++c) {
+        const double mp = P.mp[c];
+        if (mp == 0.0) continue;                            // SIM:226-227
+        const int ca = combo_a(c), cb = combo_b(c);
+        const uint32_t ma = ca == 0 ? aa : (ca == 1 ? as0 : as1);
+        const uint32_t mb = cb == 0 ? ab : (cb == 1 ? bs0 : bs1);
+        const Resolved o0 = resolve(lut, a, b, p, ma, mb, aa == 0, ab == 0, 0u);
+        if (!have_first) { first = o0; first_c = (uint32_t)c; have_first = true; }
+        const uint32_t n = 1u << o0.nlog2;
+        const double pr = __dmul_rn(mp, o0.nlog2 == 2 ? 0.25 : (o0.nlog2 == 1 ? 0.5 : 1.0)); // SIM:241
+        for (uint32_t k = 0; k < n; ++k) {
+            cs = __dadd_rn(cs, pr);
+            if (!found && cs > u) {
+                found = true;
+                pick = resolve(lut, a, b, p, ma, mb, aa == 0, ab == 0, n == 2 ? (k << 1) : k);
+                pick_c = (uint32_t)c;
+            }
+        }
+        if (found) break;
+    }
+    if (!found) { pick = first; pick_c = first_c; }
+    return finish_step<AUTO_RESET>(P, pick, t, pick_c, reset_sel, flip_reward);
+}
+
+} // namespace soccer

@@ -1,0 +1,280 @@
+"""SoccerVecEnv -- N lock-step Littman'94 soccer environments on one B200.
+
+The batched, drop-in counterpart of the reference's single-env path
+(SIM = /root/reference/gym_soccer/envs/soccer_simultaneous_env.py): same observation index
+(SIM:487-497), same action encoding (SIM:8-12), same rules (SIM:296-373), same reward / done /
+truncation (SIM:235-240, 399-406); `reset` (SIM:410-424) is fused into `step` (auto-reset).
+
+PyTorch supplies device memory and streams only; every transition is computed by the CUDA
+kernels behind include/soccer_b200.h.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from .. import _lib
+from .._lib import Pitch, StepArgs, check
+
+LAYOUT_CELL, LAYOUT_INDEX = 0, 1
+INITIAL_RESET_STEP = (1 << 64) - 1   # Philox step index reserved for the very first reset draw
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class SoccerVecEnv:
+    """num_envs independent soccer games stepped by one kernel launch.
+
+    Parameters mirror the reference constructor (SIM:35) plus the batch controls:
+      num_envs, device
+      rng_mode   "injected": the caller passes the draws (bit-exact replay of the reference);
+                 "philox":   Philox4x32-10 keyed (seed, env_id_base + i, step)
+      kernel     "rules": rules evaluated inline (any pitch / option);
+                 "table": transition table resident in shared memory (slip_prob == 0, nS <= 1024);
+                 "auto":  table when it applies, else rules
+      env_id_base  global id of env 0 (rank * envs_per_rank when sharded over GPUs)
+    """
+
+    def __init__(self, num_envs: int, width: int = 5, height: int = 4, slip_prob: float = 0.0,
+                 player_a_policy=None, player_b_policy=None, seed: int = 0,
+                 device="cuda", rng_mode: str = "injected", kernel: str = "auto",
+                 env_id_base: int = 0, want_reset_obs: bool = True):
+        assert not (player_a_policy is not None and player_b_policy is not None), \
+            "Both players cannot have a policy. At least one must be None."          # SIM:38
+        assert width >= 5, "Width must be at least 5 columns."                       # SIM:45
+        assert height >= 4, "Height must be at least 4 rows."                        # SIM:46
+        assert rng_mode in ("injected", "philox") and kernel in ("auto", "rules", "table")
+        self.lib = _lib.lib()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.SoccerB200Error("SoccerVecEnv needs a CUDA device; there is no CPU fallback")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.num_envs = int(num_envs)
+        self.pitch = Pitch(int(width), int(height), float(slip_prob))
+        self.info = _lib.pitch_info(width, height, slip_prob)
+        self.width = self.info.padded_width                                          # SIM:48
+        self.height = int(height)
+        self.slip_prob = float(slip_prob)
+        self.nS, self.nA = self.info.nS, self.info.nA
+        self.seed = int(seed)
+        self.rng_mode = rng_mode
+        self.env_id_base = int(env_id_base)
+        self.multiagent = player_a_policy is None and player_b_policy is None        # SIM:54
+        self.return_agent = ['player_a', 'player_b'] if self.multiagent else \
+            (['player_a'] if player_a_policy is None else ['player_b'])              # SIM:55-56
+        self.policy_a = self._policy_tensor(player_a_policy)
+        self.policy_b = self._policy_tensor(player_b_policy)
+        self.want_reset_obs = bool(want_reset_obs)
+
+        table_ok = self.slip_prob == 0.0 and self.multiagent and (self.nS - 1) <= 1023
+        if kernel == "table" and not table_ok:
+            raise _lib.SoccerB200Error("kernel='table' needs slip_prob == 0, no folded policy and nS <= 1024")
+        self.kernel = "table" if (kernel in ("auto", "table") and table_ok) else "rules"
+        self.layout = LAYOUT_INDEX if self.kernel == "table" else LAYOUT_CELL
+
+        n, dev = self.num_envs, self.device
+        self.state = torch.zeros(n, dtype=torch.int32, device=dev)       # packed uint32 words
+        self.obs = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.reward = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.flags = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self.reset_obs = torch.zeros(n, dtype=torch.int32, device=dev) if self.want_reset_obs else None
+        self.step_count = 0
+        self.table = None
+        if self.kernel == "table":
+            nbytes = C.c_int64()
+            check(self.lib.soccer_step_table_bytes_host(C.byref(self.pitch), C.byref(nbytes)), "step_table_bytes")
+            self.table = torch.zeros(nbytes.value // 2, dtype=torch.int16, device=dev)
+            with torch.cuda.device(dev):
+                check(self.lib.soccer_build_step_table(C.byref(self.pitch), _ptr(self.table), _stream(dev)),
+                      "soccer_build_step_table")
+
+    # ------------------------------------------------------------------ helpers
+    def _policy_tensor(self, policy):
+        if policy is None:
+            return None
+        if isinstance(policy, dict):                         # utils/policies.py:4-15 format
+            policy = [int(policy[s]) for s in range(self.nS)]
+        t = torch.as_tensor(policy, dtype=torch.int8).reshape(-1)
+        assert t.numel() == self.nS, "a table policy needs one action per observation index"
+        return t.to(self.device).contiguous()
+
+    def _check_vec(self, t, dtype, name):
+        if t is None:
+            return None
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == dtype and t.is_contiguous()
+                and t.numel() == self.num_envs):
+            raise ValueError(f"{name} must be a contiguous {dtype} CUDA tensor with {self.num_envs} elements")
+        return t
+
+    def _to_layout(self):
+        if self.layout == LAYOUT_INDEX:
+            check(self.lib.soccer_convert_state(C.byref(self.pitch), _ptr(self.state), _ptr(self.state),
+                                                LAYOUT_INDEX, self.num_envs, _stream(self.device)),
+                  "soccer_convert_state")
+
+    # ------------------------------------------------------------------ API
+    def reset(self, rng8: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """reset() of every env (SIM:410-424).  injected mode: start state from rng8 bits 2..3."""
+        if self.num_envs == 0:
+            return self.obs
+        with torch.cuda.device(self.device):
+            st = _stream(self.device)
+            cell_state = self.state
+            if self.layout == LAYOUT_INDEX and mask is not None:
+                raise NotImplementedError("masked reset is only offered on the rules kernel")
+            if self.rng_mode == "injected":
+                rng8 = self._check_vec(rng8, torch.uint8, "rng8")
+                if rng8 is None:
+                    raise ValueError("rng_mode='injected' needs rng8")
+                check(self.lib.soccer_reset(C.byref(self.pitch), _ptr(cell_state), _ptr(self.obs), _ptr(rng8),
+                                            _ptr(mask), self.num_envs, st), "soccer_reset")
+            else:
+                check(self.lib.soccer_reset_philox(C.byref(self.pitch), _ptr(cell_state), _ptr(self.obs),
+                                                   _ptr(mask), self.seed, INITIAL_RESET_STEP, self.env_id_base,
+                                                   self.num_envs, st), "soccer_reset_philox")
+            self._to_layout()
+        self.step_count = 0
+        return self.obs
+
+    def set_state(self, obs: torch.Tensor, timestep: Optional[torch.Tensor] = None):
+        """`env.state = ...` for every env, from observation indices (SIM:496-497)."""
+        obs = self._check_vec(obs, torch.int32, "obs")
+        timestep = self._check_vec(timestep, torch.int32, "timestep")
+        with torch.cuda.device(self.device):
+            check(self.lib.soccer_set_state(C.byref(self.pitch), _ptr(self.state), _ptr(obs), _ptr(timestep),
+                                            self.num_envs, _stream(self.device)), "soccer_set_state")
+            self._to_layout()
+
+    def current_obs(self) -> torch.Tensor:
+        """_state_to_observation of every env's current state (SIM:487-494)."""
+        if self.layout == LAYOUT_INDEX:
+            return (self.state & 0xFFFF).to(torch.int32)
+        out = torch.empty(self.num_envs, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.soccer_get_obs(C.byref(self.pitch), _ptr(self.state), _ptr(out), self.num_envs,
+                                          _stream(self.device)), "soccer_get_obs")
+        return out
+
+    def timesteps(self) -> torch.Tensor:
+        return (self.state >> 16) & 0xFF
+
+    def step(self, act_a: Optional[torch.Tensor], act_b: Optional[torch.Tensor] = None,
+             rng8: Optional[torch.Tensor] = None, rng32: Optional[torch.Tensor] = None,
+             rngf64: Optional[torch.Tensor] = None, out=None, detail: bool = False, auto_reset: bool = True):
+        """One lock-step step() of all envs (SIM:375-408) + fused reset (SIM:410-424).
+
+        Returns (obs, reward, flags, reset_obs) device tensors: obs is what the reference's
+        step() returned (0 on a goal), reward the first return agent's reward, flags bit 0
+        terminated / bit 1 truncated, reset_obs the observation the next step starts from.
+        `out` may supply the four output tensors (e.g. rows of a [T, N] buffer).
+        """
+        obs, reward, flags, reset_obs = out if out is not None else (self.obs, self.reward, self.flags, self.reset_obs)
+        if self.num_envs == 0:
+            return obs, reward, flags, reset_obs
+        with torch.cuda.device(self.device):
+            st = _stream(self.device)
+            philox = self.rng_mode == "philox"
+            if self.kernel == "table":
+                if philox or detail or not auto_reset:
+                    raise NotImplementedError("kernel='table' offers the injected-draw auto-reset step; "
+                                              "use kernel='rules' for the other options")
+                check(self.lib.soccer_step_table(
+                    C.byref(self.pitch), _ptr(self.table), _ptr(self.state),
+                    _ptr(self._check_vec(act_a, torch.uint8, "act_a")), _ptr(self._check_vec(act_b, torch.uint8, "act_b")),
+                    _ptr(self._check_vec(rng8, torch.uint8, "rng8")), _ptr(obs), _ptr(reward), _ptr(flags),
+                    _ptr(reset_obs), self.num_envs, st), "soccer_step_table")
+            else:
+                a = StepArgs()
+                a.state = self.state.data_ptr()
+                a.act_a = None if self.policy_a is not None else self._check_vec(act_a, torch.uint8, "act_a").data_ptr()
+                a.act_b = None if self.policy_b is not None else self._check_vec(act_b, torch.uint8, "act_b").data_ptr()
+                if not philox:
+                    a.rng8 = self._check_vec(rng8, torch.uint8, "rng8").data_ptr()
+                a.rng32 = None if rng32 is None else self._check_vec(rng32, torch.int32, "rng32").data_ptr()
+                a.rngf64 = None if rngf64 is None else self._check_vec(rngf64, torch.float64, "rngf64").data_ptr()
+                a.policy_a = None if self.policy_a is None else self.policy_a.data_ptr()
+                a.policy_b = None if self.policy_b is None else self.policy_b.data_ptr()
+                a.obs, a.reward, a.flags = obs.data_ptr(), reward.data_ptr(), flags.data_ptr()
+                a.reset_obs = None if reset_obs is None else reset_obs.data_ptr()
+                a.n = self.num_envs
+                a.auto_reset = 1 if auto_reset else 0
+                a.use_philox = 1 if philox else 0
+                a.detail = 1 if detail else 0
+                a.seed, a.step, a.env_id_base = self.seed, self.step_count, self.env_id_base
+                check(self.lib.soccer_step_ex(C.byref(self.pitch), C.byref(a), st), "soccer_step_ex")
+        self.step_count += 1
+        return obs, reward, flags, reset_obs
+
+    # ------------------------------------------------------------------ host-buffer path (end to end)
+    def _host_buffers(self):
+        if getattr(self, "_hb", None) is None:
+            n, dev = self.num_envs, self.device
+            self._hb = dict(
+                d_in=[torch.empty(n, dtype=torch.uint8, device=dev) for _ in range(3)],
+                h_obs=torch.empty(n, dtype=torch.int32).pin_memory(),
+                h_reward=torch.empty(n, dtype=torch.float32).pin_memory(),
+                h_flags=torch.empty(n, dtype=torch.uint8).pin_memory())
+        return self._hb
+
+    def step_host(self, act_a: torch.Tensor, act_b: torch.Tensor, rng8: torch.Tensor, sync: bool = True):
+        """step() with HOST buffers: uint8 CPU tensors in (pinned memory makes the copies
+        asynchronous), CPU tensors out (obs int32, reward float32, flags uint8; pinned, owned by
+        the env and overwritten by the next call).  Host->device and device->host copies are
+        part of the call -- this is the end-to-end path bench.py reports as `e2e`."""
+        hb = self._host_buffers()
+        with torch.cuda.device(self.device):
+            for d, h in zip(hb["d_in"], (act_a, act_b, rng8)):
+                d.copy_(h, non_blocking=True)
+            self.step(hb["d_in"][0], hb["d_in"][1], hb["d_in"][2])
+            hb["h_obs"].copy_(self.obs, non_blocking=True)
+            hb["h_reward"].copy_(self.reward, non_blocking=True)
+            hb["h_flags"].copy_(self.flags, non_blocking=True)
+            if sync:
+                torch.cuda.current_stream(self.device).synchronize()
+        return hb["h_obs"], hb["h_reward"], hb["h_flags"]
+
+    def rollout(self, K: int, policy_a=None, policy_b=None, want_streams: bool = True, stats: Optional[torch.Tensor] = None,
+                out=None):
+        """K fused steps with on-device Philox draws and a uniform or table policy (K2).
+
+        Returns (obs[K,N], reward[K,N], flags[K,N], stats[6]); stats accumulates
+        [episodes, goals_A, goals_B, truncations, steps, sum_episode_len].
+        """
+        n, dev = self.num_envs, self.device
+        if out is not None:
+            obs, reward, flags = out
+        elif want_streams:
+            obs = torch.empty((K, n), dtype=torch.int32, device=dev)
+            reward = torch.empty((K, n), dtype=torch.float32, device=dev)
+            flags = torch.empty((K, n), dtype=torch.uint8, device=dev)
+        else:
+            obs = reward = flags = None
+        if stats is None:
+            stats = torch.zeros(6, dtype=torch.int64, device=dev)
+        pa = self._policy_tensor(policy_a) if policy_a is not None else self.policy_a
+        pb = self._policy_tensor(policy_b) if policy_b is not None else self.policy_b
+        if n == 0 or K == 0:
+            return obs, reward, flags, stats
+        with torch.cuda.device(dev):
+            st = _stream(dev)
+            if self.kernel == "table":
+                if pa is not None or pb is not None:
+                    raise NotImplementedError("kernel='table' rollouts use the uniform random policy")
+                check(self.lib.soccer_rollout_table(C.byref(self.pitch), _ptr(self.table), _ptr(self.state), self.seed,
+                                                    self.step_count, int(K), self.env_id_base, _ptr(obs), _ptr(reward),
+                                                    _ptr(flags), _ptr(stats), n, st), "soccer_rollout_table")
+            else:
+                check(self.lib.soccer_rollout(C.byref(self.pitch), _ptr(self.state), _ptr(pa), _ptr(pb), self.seed,
+                                              self.step_count, int(K), self.env_id_base, _ptr(obs), _ptr(reward),
+                                              _ptr(flags), _ptr(stats), n, st), "soccer_rollout")
+        self.step_count += int(K)
+        return obs, reward, flags, stats

@@ -1,0 +1,220 @@
+/*
+ * soccer_b200.h -- C ABI of libsoccer_b200.so: the Littman'94 soccer step/reset hot path
+ * as hand-written sm_100a CUDA kernels.
+ *
+ * The reference (mimoralea/gym-soccer-littman94) is pure Python and has no FFI; the
+ * boundary this library sits under is the Python class surface of
+ *   SIM = /root/reference/gym_soccer/envs/soccer_simultaneous_env.py
+ * Each entry point cites the reference code it replaces.  INTEGRATION.md shows the ctypes
+ * stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - Every pointer named in a kernel call is a DEVICE pointer into caller-owned memory
+ *     (e.g. a torch tensor's data_ptr()).  The library never allocates, keeps no global
+ *     state, and is re-entrant across streams.  Entry points ending in _host() are pure
+ *     host helpers and need no GPU.
+ *   - Every kernel call is asynchronous on `stream` (a cudaStream_t / CUstream).
+ *   - Return value: 0 = OK, negative = argument error (SOCCER_E*), positive = cudaError_t.
+ *   - There is no CPU fallback: without a CUDA device kernel calls return a cudaError_t.
+ *
+ * Packed environment state (one uint32 per env, structure-of-arrays):
+ *   bits  0..7   cell code of player A      bits 16..23  timestep (0..100, SIM:399)
+ *   bits  8..15  cell code of player B      bit  24      possession p (0 = A has the ball)
+ *                                           bit  25      needs_reset (SIM:406; only ever set
+ *                                                        when auto_reset == 0)
+ *   cell code: field cell = row * width + (col - 1), col being the reference's padded column
+ *   1..width; goal cell = 0x80 | (right_goal << 6) | row (only the ball holder can be there,
+ *   SIM:369-372, and such a state is terminal, SIM:91-103).
+ *
+ * Observation index (SIM:63-109, 487-497), closed form checked against the reference's
+ * enumeration for every state of 5x4, 6x4, 7x5, 9x6 and 11x7:
+ *   obs = 0 for a goal state, else 1 + 2*(a*(F-1) + b - (b > a)) + p,  F = width*height.
+ *
+ * Injected randomness (bit-exact replay of the reference):
+ *   rng8  : bits 0..1 = step draw r  -> u = (r + 0.5)/4      (slip_prob == 0: outcome r of 4,
+ *                                                            r>>1 of 2, 0 of 1)
+ *           bits 2..3 = reset draw r -> u = (r + 0.5)/4      (start state r of 4, r>>1 of 2)
+ *   rng32 : step draw for slip_prob > 0, u = (r + 0.5)/2^32
+ *   rngf64: step draw for slip_prob > 0 as the raw fp64 uniform the reference's
+ *           np_random.random() returned (SIM:395)
+ * Counter-based randomness: Philox4x32-10, key = seed, counter = (env_id, step >> 2),
+ *   output word step & 3:  bits 0..23 -> joint action (w24 * 25) >> 24, aa = ja / 5,
+ *   ab = ja % 5;  bits 24..25 = step draw;  bits 26..27 = reset draw.
+ *
+ * flags byte: bit 0 terminated (SIM:403), bit 1 truncated (SIM:404).  Only when
+ *   soccer_step_args.detail != 0: bits 2..3 = log2(number of outcomes the chosen slip
+ *   combination had), bits 4..7 = index (0..8) of the chosen slip combination in the order of
+ *   SIM:209-223.  0xFF = env skipped because its needs_reset bit was set (the assert at SIM:376).
+ *
+ * Two state layouts exist (a state tensor is in exactly one; soccer_convert_state translates):
+ *   SOCCER_LAYOUT_CELL   the packed word above; used by the rules kernels (any pitch, any option)
+ *   SOCCER_LAYOUT_INDEX  bits 0..15 observation index of the current state (1..nS-1), bits
+ *                        16..23 timestep; used by the *_table kernels, which keep the whole
+ *                        (state, joint action, draw) -> (next state, reward, done) table -- the
+ *                        reference's P (SIM:167-293), produced on the device by the rules path --
+ *                        resident in shared memory (5x4 pitch: 152 KB of the 227 KB per SM).
+ */
+#ifndef SOCCER_B200_H
+#define SOCCER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SOCCER_ABI_VERSION 1
+
+#define SOCCER_OK        0
+#define SOCCER_EINVAL   (-1)  /* NULL where a pointer is required, n < 0, bad option */
+#define SOCCER_EPITCH   (-2)  /* width < 5, height < 4 (SIM:45-46) or width*height > 126 / height > 16 */
+#define SOCCER_ESLIP    (-3)  /* slip_prob > 0 without rng32 / rngf64, or unsupported here */
+#define SOCCER_EPOLICY  (-4)  /* both policies given (SIM:38) */
+
+#define SOCCER_MAX_EPISODE_STEPS 100  /* SIM:404 */
+
+typedef struct CUstream_st *soccer_stream_t; /* == cudaStream_t */
+
+/* Constructor arguments of the reference class (SIM:35). */
+typedef struct soccer_pitch {
+    int32_t width;      /* unpadded, >= 5 */
+    int32_t height;     /* >= 4 */
+    double  slip_prob;  /* SIM:50 */
+} soccer_pitch;
+
+/* Constructor products (SIM:48-65, 146-165), computed on the host in closed form. */
+typedef struct soccer_pitch_info {
+    int32_t  padded_width;   /* SIM:48 */
+    int32_t  height;
+    int32_t  n_field_cells;  /* F */
+    int32_t  nS;             /* 1 + 2F(F-1), SIM:105-108 */
+    int32_t  nA;             /* 5, SIM:112 */
+    int32_t  n_goal_rows;    /* SIM:60 */
+    int32_t  goal_rows[3];
+    int32_t  n_isd;          /* 4 or 2, SIM:151-163 */
+    int32_t  isd_obs[4];
+    uint32_t isd_state[4];   /* packed */
+    int32_t  isd_tuple[4][5];
+    double   slip_combo_prob[9]; /* mp of SIM:209-223, same fp64 expressions */
+} soccer_pitch_info;
+
+/* ---- host helpers (no GPU) ---- */
+int soccer_abi_version(void);
+/* SIM:45-65, 146-165 */
+int soccer_pitch_info_host(const soccer_pitch *pitch, soccer_pitch_info *out);
+/* tuple (xa, ya, xb, yb, p) <-> packed state; SIM:487-497 for the observation index.
+ * pack returns SOCCER_EINVAL for tuples the reference classifies unreachable (SIM:74-88). */
+int soccer_pack_state_host(const soccer_pitch *pitch, const int32_t tuple[5], int32_t timestep,
+                           int32_t needs_reset, uint32_t *packed);
+int soccer_unpack_state_host(const soccer_pitch *pitch, uint32_t packed, int32_t tuple[5],
+                             int32_t *timestep, int32_t *needs_reset);
+int soccer_state_to_obs_host(const soccer_pitch *pitch, uint32_t packed, int32_t *obs);
+int soccer_obs_to_state_host(const soccer_pitch *pitch, int32_t obs, uint32_t *packed);
+
+/* ---- K4: batched reset / state injection ---- */
+/* reset() for n envs (SIM:410-424): start state from rng8 bits 2..3; mask (optional, [n])
+ * selects the envs to reset; obs_out optional. */
+int soccer_reset(const soccer_pitch *pitch, uint32_t *state, int32_t *obs_out,
+                 const uint8_t *rng8, const uint8_t *mask, int64_t n, soccer_stream_t stream);
+/* same, reset draw = Philox word (seed, env_id_base + i, step) bits 26..27 */
+int soccer_reset_philox(const soccer_pitch *pitch, uint32_t *state, int32_t *obs_out,
+                        const uint8_t *mask, uint64_t seed, uint64_t step, uint64_t env_id_base,
+                        int64_t n, soccer_stream_t stream);
+/* `env.state = ...` of the reference's tests, from observation indices 1..nS-1 (obs 0 or out of
+ * range -> the env is left with needs_reset set); timestep_in optional (default 0). */
+int soccer_set_state(const soccer_pitch *pitch, uint32_t *state, const int32_t *obs_in,
+                     const int32_t *timestep_in, int64_t n, soccer_stream_t stream);
+/* _state_to_observation (SIM:487-494) of the packed states */
+int soccer_get_obs(const soccer_pitch *pitch, const uint32_t *state, int32_t *obs_out, int64_t n,
+                   soccer_stream_t stream);
+
+/* ---- K1: one lock-step step() of n envs (SIM:375-408) with fused auto-reset (SIM:410-424) ---- */
+/* slip_prob == 0, joint actions and draws supplied by the caller; reset_obs optional */
+int soccer_step(const soccer_pitch *pitch, uint32_t *state, const uint8_t *act_a,
+                const uint8_t *act_b, const uint8_t *rng8, int32_t *obs, float *reward,
+                uint8_t *flags, int32_t *reset_obs, int64_t n, soccer_stream_t stream);
+/* same with Philox draws keyed (seed, env_id_base + i, step) */
+int soccer_step_philox(const soccer_pitch *pitch, uint32_t *state, const uint8_t *act_a,
+                       const uint8_t *act_b, uint64_t seed, uint64_t step, uint64_t env_id_base,
+                       int32_t *obs, float *reward, uint8_t *flags, int32_t *reset_obs,
+                       int64_t n, soccer_stream_t stream);
+
+/* every option of the step path */
+typedef struct soccer_step_args {
+    uint32_t       *state;      /* [n] in/out */
+    const uint8_t  *act_a;      /* [n]; NULL iff policy_a folds player A's action */
+    const uint8_t  *act_b;      /* [n]; NULL iff policy_b folds player B's action */
+    const uint8_t  *rng8;       /* [n] injected draws; NULL iff use_philox */
+    const uint32_t *rng32;      /* [n] injected step draw, slip_prob > 0 */
+    const double   *rngf64;     /* [n] injected step draw as raw fp64, slip_prob > 0 */
+    const int8_t   *policy_a;   /* [nS] obs -> action, player A folded (SIM:187), reward sign
+                                   flipped because the return agent is player_b (SIM:243-244) */
+    const int8_t   *policy_b;   /* [nS] obs -> action, player B folded (SIM:188) */
+    int32_t        *obs;        /* [n] out: what step() returned (0 on a goal) */
+    float          *reward;     /* [n] out: player_a's reward (the single agent's when folded) */
+    uint8_t        *flags;      /* [n] out */
+    int32_t        *reset_obs;  /* [n] out, optional: observation the next step starts from */
+    int64_t         n;
+    int32_t         auto_reset; /* 1: reset fused (vector env); 0: set needs_reset like SIM:406 */
+    int32_t         use_philox;
+    int32_t         detail;     /* 1: fill flags bits 2..7 (needed for info["p"], SIM:405) */
+    int32_t         reserved;   /* must be 0 */
+    uint64_t        seed, step, env_id_base;
+} soccer_step_args;
+int soccer_step_ex(const soccer_pitch *pitch, const soccer_step_args *args, soccer_stream_t stream);
+
+/* ---- K2: fused K-step rollout, state register-resident, on-device policy ---- */
+/* policy_* == NULL -> uniform random joint action from the Philox word; else int8[nS] table.
+ * obs/reward/flags are [K][n] streams (each optional).  stats[6] (optional, uint64, accumulated
+ * with atomics): episodes, goals_A, goals_B, truncations, steps, sum_episode_len.
+ * slip_prob must be 0 here. */
+int soccer_rollout(const soccer_pitch *pitch, uint32_t *state, const int8_t *policy_a,
+                   const int8_t *policy_b, uint64_t seed, uint64_t step0, int32_t K,
+                   uint64_t env_id_base, int32_t *obs, float *reward, uint8_t *flags,
+                   unsigned long long *stats, int64_t n, soccer_stream_t stream);
+
+/* ---- K3: exhaustive sweep = the transition table builder (SIM:167-293) ---- */
+/* For every observation s in 1..nS-1, joint action ja = aa*5+ab, slip combination c
+ * (n_combos = 1: only the no-slip moves; 9: all of SIM:209-223) and outcome slot k < 4:
+ *   n_out[s-1][ja][c]            1, 2 or 4 (SIM:296-362)
+ *   next_state[s-1][ja][c][k]    packed next state (goal cells kept, like P_readable)
+ *   next_obs / reward / done     SIM:235-250; slots k >= n_out are zero-filled
+ * Any output pointer may be NULL. */
+int soccer_sweep(const soccer_pitch *pitch, int32_t n_combos, uint8_t *n_out, uint32_t *next_state,
+                 int32_t *next_obs, int8_t *reward, uint8_t *done, soccer_stream_t stream);
+
+/* ---- shared-memory-table variants of K1 / K2 (slip_prob == 0, pitches with nS <= 1024) ---- */
+#define SOCCER_LAYOUT_CELL  0
+#define SOCCER_LAYOUT_INDEX 1
+#define SOCCER_ETABLE (-5)   /* pitch too large for the shared-memory step table / slip_prob != 0 */
+/* bytes of the step table for this pitch: (nS-1) * 100 * sizeof(uint16_t), rounded up to 16 */
+int soccer_step_table_bytes_host(const soccer_pitch *pitch, int64_t *bytes);
+/* Fill table[(obs-1)*100 + aa*20 + ab*4 + r] for every state, joint action and 2-bit draw by
+ * running the rules path (SIM:296-373, 235-240) on the device.  Entry: bits 0..9 next
+ * observation (0 = goal), bit 10 reward != 0, bit 11 reward < 0, bits 12..13 log2(#outcomes). */
+int soccer_build_step_table(const soccer_pitch *pitch, uint16_t *table, soccer_stream_t stream);
+/* soccer_step on SOCCER_LAYOUT_INDEX states with the table staged into shared memory by TMA */
+int soccer_step_table(const soccer_pitch *pitch, const uint16_t *table, uint32_t *state,
+                      const uint8_t *act_a, const uint8_t *act_b, const uint8_t *rng8, int32_t *obs,
+                      float *reward, uint8_t *flags, int32_t *reset_obs, int64_t n,
+                      soccer_stream_t stream);
+/* soccer_rollout (uniform random policy) on SOCCER_LAYOUT_INDEX states */
+int soccer_rollout_table(const soccer_pitch *pitch, const uint16_t *table, uint32_t *state,
+                         uint64_t seed, uint64_t step0, int32_t K, uint64_t env_id_base,
+                         int32_t *obs, float *reward, uint8_t *flags, unsigned long long *stats,
+                         int64_t n, soccer_stream_t stream);
+/* translate a state tensor between layouts (in place allowed); goal / needs_reset states map
+ * to observation 0 in the INDEX layout and cannot be converted back */
+int soccer_convert_state(const soccer_pitch *pitch, const uint32_t *in, uint32_t *out,
+                         int32_t to_layout, int64_t n, soccer_stream_t stream);
+
+/* Dense Pmat / Rmat (SIM:170-171, 258-279), fp64, accumulated in the reference's order.
+ * Multi-agent: Pmat[nS][nS][5][5], Rmat[nS][5][5]; with a folded policy: Pmat[nS][nS][5],
+ * Rmat[nS][5].  The call zero-fills both. */
+int soccer_dense(const soccer_pitch *pitch, const int8_t *policy_a, const int8_t *policy_b,
+                 double *Pmat, double *Rmat, soccer_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOCCER_B200_H */

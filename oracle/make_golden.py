@@ -87,11 +87,58 @@ def gen(width, height, slip, mode, T, N, dense=True):
           f"(episodes={int((flg != 0).sum())})", flush=True)
 
 
+def gen_native(width, height, slip, mode, seed, T):
+    """The reference driven through its OWN np.random.RandomState(seed): the trajectory a user
+    of the reference sees.  The drop-in single-env wrapper must reproduce it draw for draw."""
+    Env = rh.import_reference()
+    f = width * height
+    pol = random_policy(1 + 2 * f * (f - 1), 0)
+    kw = {}
+    if mode == "a_free":
+        kw["player_b_policy"] = pol
+    elif mode == "b_free":
+        kw["player_a_policy"] = pol
+    env = Env(width=width, height=height, slip_prob=slip, seed=seed, **kw)
+    a0 = env.return_agent[0]
+    rs = np.random.RandomState(4242 + seed)
+    acts = rs.randint(0, 5, (T, 2)).astype(np.uint8)
+    obs = np.zeros(T, np.int32); rew = np.zeros(T, np.float32); flg = np.zeros(T, np.uint8)
+    inf = np.zeros(T, np.float64); tup = np.zeros((T, 5), np.int16); rob = np.zeros(T, np.int32)
+    o, _ = env.reset()
+    init_obs = o[a0]
+    for t in range(T):
+        action = {"player_a": int(acts[t, 0]), "player_b": int(acts[t, 1])} if env.multiagent \
+            else {a0: int(acts[t, 0])}
+        o, r, d, tr, info = env.step(action)
+        obs[t], rew[t], inf[t] = o[a0], r[a0], info[a0]["p"]
+        flg[t] = (1 if d[a0] else 0) | (2 if tr[a0] else 0)
+        tup[t] = env.state
+        rob[t] = o[a0]
+        if d[a0] or tr[a0]:
+            o2, _ = env.reset()
+            rob[t] = o2[a0]
+    tag = f"{width}x{height}_s{slip_tag(slip)}_{mode}"
+    d = dict(seed=np.int64(seed), acts=acts, obs=obs, reward=rew, flags=flg, info_p=inf, state=tup,
+             reset_obs=rob, init_obs=np.int32(init_obs), slip_prob=np.float64(slip))
+    if mode != "multi":
+        d["policy"] = np.array([pol[s] for s in range(env.nS)], np.int8)
+    np.savez_compressed(os.path.join(OUT, f"ref_native_{tag}.npz"), **d)
+    print(f"native {tag}: episodes={int((flg != 0).sum())}", flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--native-only", action="store_true")
     args = ap.parse_args()
     os.makedirs(OUT, exist_ok=True)
+    gen_native(5, 4, 0.0, "multi", seed=0, T=3000)
+    gen_native(5, 4, 0.2, "multi", seed=7, T=3000)
+    gen_native(5, 4, 0.2, "a_free", seed=3, T=1500)
+    gen_native(5, 4, 0.2, "b_free", seed=5, T=1500)
+    gen_native(7, 5, 0.2, "multi", seed=11, T=1500)
+    if args.native_only:
+        return
     gen(5, 4, 0.0, "multi", T=1500, N=64)
     gen(5, 4, 0.2, "multi", T=1500, N=64)
     gen(5, 4, 0.2, "a_free", T=600, N=32)

@@ -1,0 +1,356 @@
+"""GPU parity tests: the CUDA path (through the C ABI / its Python mirror) against
+  (1) golden vectors produced by the unmodified reference (tests/golden/, oracle/make_golden.py)
+  (2) the CPU oracle (oracle/soccer_oracle.c) on the same seeded inputs.
+Bar: bit-exact for obs / flags / state; rewards are exactly representable (+1, -1, 0) and are
+compared with ==; fp64 probabilities / Pmat / Rmat are compared with == (same operation order).
+"""
+import numpy as np
+import pytest
+
+from .conftest import golden_tags, load_golden, parse_tag
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda", 0)
+
+
+def _t(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def _policy(g):
+    return None if "policy" not in g else {s: int(a) for s, a in enumerate(g["policy"])}
+
+
+def _env_kwargs(tag, g):
+    w, h, slip, mode = parse_tag(tag)
+    kw = dict(width=w, height=h, slip_prob=slip)
+    if mode == "a_free":
+        kw["player_b_policy"] = _policy(g)
+    elif mode == "b_free":
+        kw["player_a_policy"] = _policy(g)
+    return kw, mode
+
+
+# ----------------------------------------------------------------------------- K3: sweep / tables
+@pytest.mark.parametrize("tag", golden_tags("table"))
+def test_sweep_tables_match_reference(dev, tag):
+    """env.P / env.P_readable built from the sweep kernel == the reference's (SIM:167-293):
+    list lengths and order, fp64 probabilities (==), next observation, next tuple, reward, done."""
+    from gym_soccer_littman94_b200.envs import SoccerSimultaneousEnv
+    g = load_golden("table", tag)
+    kw, mode = _env_kwargs(tag, g)
+    env = SoccerSimultaneousEnv(device=dev, **kw)
+    assert env.nS == int(g["nS"]) and env.width == int(g["width"])
+    assert len(env.unreachable_states) == int(g["n_unreachable"])
+    assert {tuple(int(v) for v in r[:5]): float(r[5]) for r in g["goal_states"]} == env.goal_states
+    assert [(p, st) for p, st in env.isd] == [(float(p), tuple(int(v) for v in s))
+                                              for p, s in zip(g["isd_prob"], g["isd_state"])]
+    tuples = g["tuples"]
+    for obs in range(1, env.nS):
+        st = tuple(int(v) for v in tuples[obs])
+        assert env.state_space[st] == obs and env._observation_to_state(obs) == st
+    P, PR = env.P, env.P_readable
+    keys = [(a, b) for a in range(5) for b in range(5)] if mode == "multi" else list(range(5))
+    names = env.ACTION_STRING
+    cnt, prob, nxt, rew, done, ntup = (g[k] for k in ("count", "prob", "next_obs", "reward", "done", "next_tuple"))
+    assert sorted(P.keys()) == list(range(env.nS))
+    for s in range(env.nS):
+        assert sorted(P[s].keys()) == sorted(keys)
+        for ki, k in enumerate(keys):
+            tl = P[s][k]
+            n = int(cnt[s, ki])
+            assert len(tl) == n, (s, k)
+            for j, (p, ns, r, d) in enumerate(tl):
+                assert p == prob[s, ki, j] and ns == nxt[s, ki, j] and r == rew[s, ki, j] and d == bool(done[s, ki, j])
+                assert isinstance(p, float) and isinstance(ns, int) and isinstance(r, float) and isinstance(d, bool)
+            if s >= 1:
+                kk = (names[k[0]], names[k[1]]) if mode == "multi" else names[k]
+                trl = PR[tuple(int(v) for v in tuples[s])][kk]
+                assert [t[1] for t in trl] == [tuple(int(v) for v in ntup[s, ki, j]) for j in range(n)]
+
+
+@pytest.mark.parametrize("tag", [t for t in golden_tags("table") if "pmat_val" in load_golden("table", t)])
+def test_dense_pmat_rmat_match_reference(dev, tag):
+    from gym_soccer_littman94_b200.envs import SoccerSimultaneousEnv
+    g = load_golden("table", tag)
+    kw, _ = _env_kwargs(tag, g)
+    env = SoccerSimultaneousEnv(device=dev, **kw)
+    P, R = env.Pmat, env.Rmat
+    assert tuple(g["pmat_shape"]) == P.shape
+    nz = np.nonzero(P)
+    assert np.array_equal(np.stack(nz, axis=1), g["pmat_idx"].astype(np.int64))
+    assert np.array_equal(P[nz], g["pmat_val"])
+    assert np.array_equal(R, g["rmat"])
+
+
+# ----------------------------------------------------------------------------- K1: lock-step step
+def _run_vec(dev, g, kw, kernel, n_pad=0, misalign=0):
+    """Replay a golden rollout through SoccerVecEnv.  n_pad extra envs (copies of env 0) make N
+    not a multiple of 4; misalign > 0 offsets every input/output pointer by that many elements."""
+    from gym_soccer_littman94_b200.envs import SoccerVecEnv
+    T, N0 = g["act_a"].shape
+    N = N0 + n_pad
+
+    def widen(a):
+        return a if n_pad == 0 else np.concatenate([a, np.repeat(a[..., :1], n_pad, axis=-1)], axis=-1)
+    act_a = _t(widen(g["act_a"]), dev)
+    act_b = _t(widen(g["act_b"]), dev) if "act_b" in g else None
+    rng8 = _t(widen(g["rng8"]), dev)
+    rng32 = _t(widen(g["rng32"]).view(np.int32), dev) if "rng32" in g else None
+    env = SoccerVecEnv(N, device=dev, rng_mode="injected", kernel=kernel, **kw)
+    init = _t((widen(g["init_rng"]) & 3) << 2, dev)
+    init_obs = env.reset(init).cpu().numpy()
+    assert np.array_equal(init_obs[:N0], g["init_obs"])
+    m = misalign
+    obs = torch.zeros((T, N + m), dtype=torch.int32, device=dev)
+    rew = torch.zeros((T, N + m), dtype=torch.float32, device=dev)
+    flg = torch.zeros((T, N + m), dtype=torch.uint8, device=dev)
+    rob = torch.zeros((T, N + m), dtype=torch.int32, device=dev)
+    if m:
+        # shift the inputs by m elements as well so that every pointer is misaligned
+        def shift(x):
+            buf = torch.zeros(x.numel() + m, dtype=x.dtype, device=dev)
+            buf[m:] = x.reshape(-1)
+            return buf
+    for t in range(T):
+        ins = [act_a[t], None if act_b is None else act_b[t], rng8[t], None if rng32 is None else rng32[t]]
+        if m:
+            ins = [None if x is None else shift(x)[m:] for x in ins]
+        env.step(ins[0], ins[1], ins[2], rng32=ins[3], out=(obs[t, m:], rew[t, m:], flg[t, m:], rob[t, m:]))
+    torch.cuda.synchronize()
+    return [x[:, m:m + N0].cpu().numpy() for x in (obs, rew, flg, rob)]
+
+
+@pytest.mark.parametrize("tag", golden_tags("rollout"))
+def test_step_injected_matches_reference(dev, tag):
+    """obs / reward / terminated / truncated / post-reset obs, step by step, against the replayed
+    reference (every golden rollout: slip 0 and 0.2, folded policies, 5x4 ... 11x7)."""
+    g = load_golden("rollout", tag)
+    kw, _ = _env_kwargs(tag, g)
+    obs, rew, flg, rob = _run_vec(dev, g, kw, "rules")
+    assert np.array_equal(obs, g["obs"])
+    assert np.array_equal(rew, g["reward"])
+    assert np.array_equal(flg & 3, g["flags"])
+    assert np.array_equal(rob, g["reset_obs"])
+
+
+def test_step_table_kernel_matches_reference(dev):
+    g = load_golden("rollout", "5x4_s000_multi")
+    obs, rew, flg, rob = _run_vec(dev, g, dict(width=5, height=4, slip_prob=0.0), "table")
+    assert np.array_equal(obs, g["obs"]) and np.array_equal(rew, g["reward"])
+    assert np.array_equal(flg, g["flags"]) and np.array_equal(rob, g["reset_obs"])
+
+
+@pytest.mark.parametrize("kernel", ["rules", "table"])
+@pytest.mark.parametrize("n_pad,misalign", [(1, 0), (3, 0), (0, 1), (2, 3)])
+def test_step_ragged_and_misaligned(dev, kernel, n_pad, misalign):
+    """N not a multiple of 4 and pointers off the 16-byte grid take the scalar path: same answers."""
+    g = load_golden("rollout", "5x4_s000_multi")
+    sub = {k: (g[k][:300] if g[k].ndim == 2 else g[k]) for k in g.files}
+    obs, rew, flg, rob = _run_vec(dev, sub, dict(width=5, height=4, slip_prob=0.0), kernel, n_pad, misalign)
+    assert np.array_equal(obs, sub["obs"]) and np.array_equal(rew, sub["reward"])
+    assert np.array_equal(flg & 3, sub["flags"]) and np.array_equal(rob, sub["reset_obs"])
+
+
+def test_step_empty_batch(dev):
+    from gym_soccer_littman94_b200.envs import SoccerVecEnv
+    env = SoccerVecEnv(0, device=dev, kernel="rules")
+    e = torch.zeros(0, dtype=torch.uint8, device=dev)
+    env.reset(e)
+    env.step(e, e, e)
+    env.rollout(4)
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("kernel", ["rules", "table"])
+def test_config2_4096_envs_vs_oracle(dev, oracle, kernel):
+    """BASELINE config 2: 4096 lock-step envs, host-supplied joint actions, injected draws,
+    T = 10,000 steps, bit-exact against the oracle (itself pinned to the reference)."""
+    from gym_soccer_littman94_b200.envs import SoccerVecEnv
+    N, T, CH = 4096, 10000, 500
+    rs = np.random.RandomState(2024)
+    m = oracle.OracleModel(5, 4, 0.0)
+    init = rs.randint(0, 4, N).astype(np.uint8)
+    states = np.zeros(N, oracle.STATE_DTYPE)
+    for i in range(N):
+        states[i] = m.isd[int(init[i])][1]
+    ts = np.zeros(N, np.int32)
+    env = SoccerVecEnv(N, device=dev, kernel=kernel)
+    env.reset(_t(init << 2, dev))
+    n_eps = 0
+    for c in range(T // CH):
+        act_a = rs.randint(0, 5, (CH, N)).astype(np.uint8)
+        act_b = rs.randint(0, 5, (CH, N)).astype(np.uint8)
+        rng8 = rs.randint(0, 16, (CH, N)).astype(np.uint8)
+        eo, er, ef, ero = m.rollout_injected(states, ts, act_a, act_b, rng8, n_threads=8)
+        da, db, dr = _t(act_a, dev), _t(act_b, dev), _t(rng8, dev)
+        obs = torch.empty((CH, N), dtype=torch.int32, device=dev)
+        rew = torch.empty((CH, N), dtype=torch.float32, device=dev)
+        flg = torch.empty((CH, N), dtype=torch.uint8, device=dev)
+        rob = torch.empty((CH, N), dtype=torch.int32, device=dev)
+        for t in range(CH):
+            env.step(da[t], db[t], dr[t], out=(obs[t], rew[t], flg[t], rob[t]))
+        assert np.array_equal(obs.cpu().numpy(), eo), f"obs mismatch in chunk {c}"
+        assert np.array_equal(rew.cpu().numpy(), er)
+        assert np.array_equal(flg.cpu().numpy(), ef)
+        assert np.array_equal(rob.cpu().numpy(), ero)
+        n_eps += int((ef != 0).sum())
+    assert np.array_equal(env.current_obs().cpu().numpy(), m.obs_from_states(states))
+    assert np.array_equal(env.timesteps().cpu().numpy(), ts)
+    assert n_eps > 1_000_000   # ~34-step episodes: the fused reset really is exercised
+
+
+def test_exhaustive_single_steps_vs_golden(dev):
+    """Every state x 25 joint actions x 4 draw values in ONE launch of each kernel, against the
+    reference's table: the sweep of BASELINE config 5 done through the step entry points."""
+    from gym_soccer_littman94_b200.envs import SoccerVecEnv
+    g = load_golden("table", "5x4_s000_multi")
+    nS = int(g["nS"])
+    s, ja, r = np.meshgrid(np.arange(1, nS), np.arange(25), np.arange(4), indexing="ij")
+    s, ja, r = s.ravel(), ja.ravel(), r.ravel()
+    cnt = g["count"][s, ja].astype(np.int64)
+    slot = np.where(cnt == 4, r, np.where(cnt == 2, r >> 1, 0))
+    want_obs = g["next_obs"][s, ja, slot]
+    want_rew = g["reward"][s, ja, slot].astype(np.float32)
+    want_done = g["done"][s, ja, slot]
+    N = len(s)
+    for kernel in ("rules", "table"):
+        env = SoccerVecEnv(N, device=dev, kernel=kernel)
+        env.set_state(_t(s.astype(np.int32), dev))
+        obs, rew, flg, rob = env.step(_t((ja // 5).astype(np.uint8), dev), _t((ja % 5).astype(np.uint8), dev),
+                                      _t(r.astype(np.uint8), dev))
+        assert np.array_equal(obs.cpu().numpy(), want_obs), kernel
+        assert np.array_equal(rew.cpu().numpy(), want_rew), kernel
+        assert np.array_equal(flg.cpu().numpy() & 1, want_done), kernel
+        # fused reset: terminated envs restart from isd[0] (reset draw bits are 0 here)
+        ro = rob.cpu().numpy()
+        assert np.array_equal(ro[want_done == 1], np.full(int(want_done.sum()), int(g["isd_obs"][0])))
+        assert np.array_equal(ro[want_done == 0], want_obs[want_done == 0])
+
+
+# ----------------------------------------------------------------------------- K2 / Philox
+@pytest.mark.parametrize("kernel", ["rules", "table"])
+def test_rollout_philox_vs_oracle(dev, oracle, kernel):
+    from gym_soccer_littman94_b200.envs import SoccerVecEnv
+    N, K, seed, base = 2048, 150, 1234567, 10_000_000_000
+    m = oracle.OracleModel(5, 4, 0.0)
+    env = SoccerVecEnv(N, device=dev, rng_mode="philox", kernel=kernel, seed=seed, env_id_base=base)
+    init_obs = env.reset().cpu().numpy()
+    # initial reset draw = reset bits of word(seed, env, 2^64-1)
+    want0 = np.array([m.state_to_obs(m.isd[oracle.philox_decode(oracle.philox_word(seed, base + i, (1 << 64) - 1))[3]][1])
+                      for i in range(N)], np.int32)
+    assert np.array_equal(init_obs, want0)
+    states = m.states_from_obs(init_obs)
+    ts = np.zeros(N, np.int32)
+    # two launches with an unaligned step0 in between (K = 150 then 61)
+    for kk in (K, 61):
+        step0 = env.step_count
+        eo, er, ef, es = m.rollout_philox(states, ts, kk, seed, step0=step0, env_id_base=base, n_threads=8)
+        obs, rew, flg, stats = env.rollout(kk)
+        assert np.array_equal(obs.cpu().numpy(), eo)
+        assert np.array_equal(rew.cpu().numpy(), er)
+        assert np.array_equal(flg.cpu().numpy(), ef)
+        assert np.array_equal(stats.cpu().numpy(), es)
+    assert np.array_equal(env.current_obs().cpu().numpy(), m.obs_from_states(states))
+
+
+def test_rollout_table_policy_and_ragged(dev, oracle):
+    """Table policies for both players (utils/policies.py format) and N % 4 != 0."""
+    from gym_soccer_littman94_b200.envs import SoccerVecEnv
+    N, K, seed = 1023, 120, 99
+    m = oracle.OracleModel(5, 4, 0.0)
+    rs = np.random.RandomState(5)
+    pa, pb = rs.randint(0, 5, m.nS).astype(np.int8), rs.randint(0, 5, m.nS).astype(np.int8)
+    env = SoccerVecEnv(N, device=dev, rng_mode="philox", kernel="rules", seed=seed)
+    states = m.states_from_obs(env.reset().cpu().numpy())
+    ts = np.zeros(N, np.int32)
+    eo, er, ef, es = m.rollout_philox(states, ts, K, seed, policy_a=pa, policy_b=pb, n_threads=4)
+    obs, rew, flg, stats = env.rollout(K, policy_a=pa, policy_b=pb)
+    assert np.array_equal(obs.cpu().numpy(), eo) and np.array_equal(rew.cpu().numpy(), er)
+    assert np.array_equal(flg.cpu().numpy(), ef) and np.array_equal(stats.cpu().numpy(), es)
+
+
+def test_step_philox_equals_rollout(dev):
+    """K1 in Philox mode fed the actions K2 draws for itself follows the same trajectory."""
+    from gym_soccer_littman94_b200.envs import SoccerVecEnv
+    from oracle import soccer_oracle as so
+    N, K, seed = 512, 40, 31337
+    a = SoccerVecEnv(N, device=dev, rng_mode="philox", kernel="rules", seed=seed)
+    b = SoccerVecEnv(N, device=dev, rng_mode="philox", kernel="rules", seed=seed)
+    a.reset(); b.reset()
+    obs, rew, flg, _ = a.rollout(K)
+    for k in range(K):
+        acts = np.array([so.philox_decode(so.philox_word(seed, i, k))[:2] for i in range(N)], np.uint8)
+        o, r, f, _ = b.step(_t(acts[:, 0].copy(), dev), _t(acts[:, 1].copy(), dev))
+        assert torch.equal(o, obs[k]) and torch.equal(r, rew[k]) and torch.equal(f, flg[k])
+
+
+def test_rollout_gpu_count_independence(dev):
+    """Sharding contract: envs [0, N) stepped as one batch == two half batches with env_id_base."""
+    from gym_soccer_littman94_b200.envs import SoccerVecEnv
+    N, K, seed = 4096, 64, 7
+    full = SoccerVecEnv(N, device=dev, rng_mode="philox", seed=seed)
+    full.reset()
+    fo, fr, ff, fs = full.rollout(K)
+    tot = torch.zeros(6, dtype=torch.int64, device=dev)
+    for half in range(2):
+        e = SoccerVecEnv(N // 2, device=dev, rng_mode="philox", seed=seed, env_id_base=half * N // 2)
+        e.reset()
+        o, r, f, s = e.rollout(K)
+        sl = slice(half * N // 2, (half + 1) * N // 2)
+        assert torch.equal(o, fo[:, sl]) and torch.equal(r, fr[:, sl]) and torch.equal(f, ff[:, sl])
+        tot += s
+    assert torch.equal(tot, fs)
+
+
+def test_philox_uniform_policy_distribution(dev):
+    """Distributional check against the reference's uniform-random play (100k
+    reference steps gave mean episode length 34.0, A/B wins balanced, 6.2 % truncated)."""
+    from gym_soccer_littman94_b200.envs import SoccerVecEnv
+    env = SoccerVecEnv(1 << 16, device=dev, rng_mode="philox", seed=2)
+    env.reset()
+    _, _, _, st = env.rollout(512, want_streams=False)
+    ep, ga, gb, tr, steps, length = [int(x) for x in st.cpu().numpy()]
+    assert steps == (1 << 16) * 512 and ep == ga + gb + tr
+    assert abs(length / ep - 34.0) < 1.0
+    assert abs(ga / gb - 1.0) < 0.02
+    assert abs(tr / ep - 0.062) < 0.01
+
+
+# ----------------------------------------------------------------------------- full-size properties
+def test_full_size_properties_2_24(dev):
+    """BASELINE's bandwidth configuration (2^24 envs): the two K1 kernels agree bit for bit, and
+    size-independent invariants hold (reward != 0 iff terminated; obs == 0 iff terminated; reset_obs
+    is a start state wherever flags != 0; timestep resets)."""
+    from gym_soccer_littman94_b200.envs import SoccerVecEnv
+    N = 1 << 24
+    g = torch.Generator(device=dev).manual_seed(0)
+    outs = {}
+    for kernel in ("rules", "table"):
+        env = SoccerVecEnv(N, device=dev, kernel=kernel)
+        g.manual_seed(0)
+        env.reset(torch.randint(0, 16, (N,), dtype=torch.uint8, device=dev, generator=g))
+        acc = torch.zeros(4, dtype=torch.int64, device=dev)
+        for t in range(40):
+            a = torch.randint(0, 5, (N,), dtype=torch.uint8, device=dev, generator=g)
+            b = torch.randint(0, 5, (N,), dtype=torch.uint8, device=dev, generator=g)
+            r = torch.randint(0, 16, (N,), dtype=torch.uint8, device=dev, generator=g)
+            obs, rew, flg, rob = env.step(a, b, r)
+            term = (flg & 1) != 0
+            assert torch.equal(term, rew != 0) and torch.equal(term, obs == 0)
+            ended = flg != 0
+            starts = torch.tensor([253, 254, 435, 436], device=dev, dtype=torch.int32)
+            assert torch.isin(rob[ended], starts).all()
+            assert torch.equal(rob[~ended], obs[~ended])
+            assert torch.equal(env.current_obs(), rob)
+            assert (env.timesteps()[ended] == 0).all()
+            acc += torch.stack([obs.sum(dtype=torch.int64), (rew > 0).sum(), (rew < 0).sum(), rob.sum(dtype=torch.int64)])
+        outs[kernel] = acc.cpu().numpy()
+        del env
+    assert np.array_equal(outs["rules"], outs["table"])
