@@ -1081,12 +1081,12 @@ int soccer_step_table(const soccer_pitch* pitch, const uint16_t* table, uint32_t
     if (vec) {
         const int64_t n_groups = n / 4;
         if (reset_obs) {
-            static const int e0 = allow_big_smem(k_step_table<true>, 227 * 1024);
+            const int e0 = allow_big_smem(k_step_table<true>, bytes);
             if (e0) return e0;
             k_step_table<true><<<table_grid(n_groups), kTableThreads, bytes, st>>>(
                 P, table, (uint32_t)bytes, state, act_a, act_b, rng8, obs, reward, flags, reset_obs, n_groups);
         } else {
-            static const int e0 = allow_big_smem(k_step_table<false>, 227 * 1024);
+            const int e0 = allow_big_smem(k_step_table<false>, bytes);
             if (e0) return e0;
             k_step_table<false><<<table_grid(n_groups), kTableThreads, bytes, st>>>(
                 P, table, (uint32_t)bytes, state, act_a, act_b, rng8, obs, reward, flags, nullptr, n_groups);
@@ -1116,12 +1116,12 @@ int soccer_rollout_table(const soccer_pitch* pitch, const uint16_t* table, uint3
     const bool vec = (n % 4 == 0) && aligned(state, 16) && (!obs || aligned(obs, 16)) &&
                      (!reward || aligned(reward, 16)) && (!flags || aligned(flags, 4));
     if (vec) {
-        static const int e0 = allow_big_smem(k_rollout_table<4>, 227 * 1024);
+        const int e0 = allow_big_smem(k_rollout_table<4>, bytes);
         if (e0) return e0;
         k_rollout_table<4><<<table_grid(n / 4), kTableThreads, bytes, st>>>(P, table, (uint32_t)bytes, state, seed, step0, K,
                                                                             env_id_base, obs, reward, flags, stats, n);
     } else {
-        static const int e0 = allow_big_smem(k_rollout_table<1>, 227 * 1024);
+        const int e0 = allow_big_smem(k_rollout_table<1>, bytes);
         if (e0) return e0;
         k_rollout_table<1><<<table_grid(n), kTableThreads, bytes, st>>>(P, table, (uint32_t)bytes, state, seed, step0, K,
                                                                         env_id_base, obs, reward, flags, stats, n);

@@ -1,0 +1,51 @@
+"""Short driver for ncu captures: a few launches of each hot kernel at its bench size.
+
+    python profiles/run_kernels.py [k1_table|k1_rules|k2_table|k2_rules|all] [--envs N]
+"""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from gym_soccer_littman94_b200.envs import SoccerVecEnv  # noqa: E402
+
+
+def k1(kernel, n, iters):
+    dev = torch.device("cuda", 0)
+    env = SoccerVecEnv(n, device=dev, kernel=kernel, want_reset_obs=False)
+    g = torch.Generator(device=dev).manual_seed(0)
+    a, b, r = (torch.randint(0, hi, (n,), dtype=torch.uint8, device=dev, generator=g) for hi in (5, 5, 16))
+    env.reset(r)
+    for _ in range(iters):
+        env.step(a, b, r)
+    torch.cuda.synchronize()
+
+
+def k2(kernel, n, K, iters):
+    dev = torch.device("cuda", 0)
+    env = SoccerVecEnv(n, device=dev, kernel=kernel, rng_mode="philox", seed=0)
+    env.reset()
+    bufs = (torch.empty((K, n), dtype=torch.int32, device=dev), torch.empty((K, n), dtype=torch.float32, device=dev),
+            torch.empty((K, n), dtype=torch.uint8, device=dev))
+    for _ in range(iters):
+        env.rollout(K, out=bufs)
+    torch.cuda.synchronize()
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("what", nargs="?", default="all")
+    ap.add_argument("--envs", type=int, default=1 << 24)
+    ap.add_argument("--iters", type=int, default=6)
+    args = ap.parse_args()
+    if args.what in ("k1_table", "all"):
+        k1("table", args.envs, args.iters)
+    if args.what in ("k1_rules", "all"):
+        k1("rules", args.envs, args.iters)
+    if args.what in ("k2_table", "all"):
+        k2("table", 1 << 20, 64, args.iters)
+    if args.what in ("k2_rules", "all"):
+        k2("rules", 1 << 20, 64, args.iters)
+    print("done")

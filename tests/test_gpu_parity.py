@@ -122,6 +122,8 @@ def _run_vec(dev, g, kw, kernel, n_pad=0, misalign=0):
         ins = [act_a[t], None if act_b is None else act_b[t], rng8[t], None if rng32 is None else rng32[t]]
         if m:
             ins = [None if x is None else shift(x)[m:] for x in ins]
+        if env.policy_a is not None:      # b_free: the golden's single action column drives player B
+            ins[0], ins[1] = None, ins[0]
         env.step(ins[0], ins[1], ins[2], rng32=ins[3], out=(obs[t, m:], rew[t, m:], flg[t, m:], rob[t, m:]))
     torch.cuda.synchronize()
     return [x[:, m:m + N0].cpu().numpy() for x in (obs, rew, flg, rob)]
@@ -313,14 +315,17 @@ def test_philox_uniform_policy_distribution(dev):
     """Distributional check against the reference's uniform-random play (100k
     reference steps gave mean episode length 34.0, A/B wins balanced, 6.2 % truncated)."""
     from gym_soccer_littman94_b200.envs import SoccerVecEnv
-    env = SoccerVecEnv(1 << 16, device=dev, rng_mode="philox", seed=2)
+    env = SoccerVecEnv(1 << 15, device=dev, rng_mode="philox", seed=2)
     env.reset()
-    _, _, _, st = env.rollout(512, want_streams=False)
+    _, _, _, st = env.rollout(2048, want_streams=False)
     ep, ga, gb, tr, steps, length = [int(x) for x in st.cpu().numpy()]
-    assert steps == (1 << 16) * 512 and ep == ga + gb + tr
-    assert abs(length / ep - 34.0) < 1.0
+    assert steps == (1 << 15) * 2048 and ep == ga + gb + tr
+    # the unmodified reference, 400,000 native-RNG steps (build container): 33.75 steps/episode,
+    # 5.4 % truncated, A/B wins 0.99; 100,000 steps (BASELINE.md): 34.0, 6.2 %
+    assert abs(steps / ep - 33.7) < 0.4
+    assert 0 <= steps - length <= (1 << 15) * 100       # sum_episode_len counts finished episodes only
     assert abs(ga / gb - 1.0) < 0.02
-    assert abs(tr / ep - 0.062) < 0.01
+    assert abs(tr / ep - 0.056) < 0.006
 
 
 # ----------------------------------------------------------------------------- full-size properties

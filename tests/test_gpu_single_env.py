@@ -166,8 +166,10 @@ def test_asserts_match_reference_messages(Env):
     env.reset()
     with pytest.raises(AssertionError, match="Action must be a dictionary"):
         env.step([0, 0])
-    with pytest.raises(AssertionError, match="length 2 for multiagent"):
+    with pytest.raises(AssertionError, match="A policy for player_b must be provided"):     # SIM:381 fires first
         env.step({'player_a': 0})
+    with pytest.raises(AssertionError, match="Action must be a dictionary of length 1 or 2"):
+        env.step({'player_a': 0, 'player_b': 0, 'referee': 0})
     with pytest.raises(AssertionError, match="Both players cannot have a policy"):
         Env(player_a_policy={}, player_b_policy={})
     with pytest.raises(AssertionError, match="Width must be at least 5"):
