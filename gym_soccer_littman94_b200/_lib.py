@@ -11,7 +11,9 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
-SO_PATH = os.path.join(_HERE, "libsoccer_b200.so")
+_DEFAULT_SO = os.path.join(_HERE, "libsoccer_b200.so")
+# SOCCER_B200_LIB points at an alternative build of the SAME sources (A/B kernel experiments)
+SO_PATH = os.environ.get("SOCCER_B200_LIB", _DEFAULT_SO)
 
 ABI_VERSION = 1
 
@@ -53,6 +55,10 @@ class StepArgs(C.Structure):
 
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/ for sm_100a with nvcc (cross-compiles without a GPU)."""
+    if SO_PATH != _DEFAULT_SO:
+        if not os.path.exists(SO_PATH):
+            raise SoccerB200Error(f"SOCCER_B200_LIB={SO_PATH} does not exist")
+        return SO_PATH
     srcs = [os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith((".cu", ".cuh"))]
     srcs.append(os.path.join(os.path.dirname(_HERE), "include", "soccer_b200.h"))
     stale = (not os.path.exists(SO_PATH)) or any(

@@ -10,6 +10,7 @@
 // so no tensor-core path.  SIM = /root/reference/gym_soccer/envs/soccer_simultaneous_env.py.
 #include "../../include/soccer_b200.h"
 #include "soccer_rules.cuh"
+#include "soccer_table.cuh"
 
 #include <cuda_runtime.h>
 
@@ -17,7 +18,7 @@ using namespace soccer;
 
 namespace soccer {
 
-constexpr int kThreads = 256;
+
 
 // ------------------------------------------------------------------ host: pitch
 bool pitch_ok(const soccer_pitch* p)
@@ -133,29 +134,6 @@ inline int launch_status() { return (int)cudaGetLastError(); }
 
 inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 
-// ------------------------------------------------------------------ streaming loads / stores
-__device__ __forceinline__ uint4 ld_stream(const uint4* p) { return __ldcs(p); }
-__device__ __forceinline__ uint32_t ld_stream(const uint32_t* p) { return __ldcs(p); }
-__device__ __forceinline__ void st_stream(uint4* p, uint4 v) { __stcs(p, v); }
-__device__ __forceinline__ void st_stream(uint32_t* p, uint32_t v) { __stcs(p, v); }
-
-// ------------------------------------------------------------------ K1 fast path
-// slip_prob == 0, joint actions + rng8 from the caller, auto-reset fused.  One thread owns
-// groups of 4 consecutive envs: 128-bit accesses on the 32-bit streams (state, obs, reward),
-// 32-bit accesses on the byte streams (actions, rng, flags); a warp therefore touches 512 B /
-// 128 B contiguous per instruction.  Persistent grid-stride loop, two groups in flight.
-struct Group4 { uint4 s; uint32_t a, b, r; };
-
-__device__ __forceinline__ Group4 load_group(const uint4* st, const uint32_t* aa, const uint32_t* ab,
-                                             const uint32_t* rg, int64_t g)
-{
-    Group4 x;
-    x.s = st[g];              // state is re-read by the next step: default caching
-    x.a = ld_stream(aa + g);
-    x.b = ld_stream(ab + g);
-    x.r = ld_stream(rg + g);
-    return x;
-}
 
 template <bool RESET_OBS>
 __device__ __forceinline__ void step_group(const PitchDev& P, const uint8_t* lut, const Group4& x, int64_t g,
@@ -171,7 +149,7 @@ __device__ __forceinline__ void step_group(const PitchDev& P, const uint8_t* lut
         ro[e] = (uint32_t)o.reset_obs;
         ff |= o.flags << (8 * e);
     }
-    st[g] = make_uint4(so[0], so[1], so[2], so[3]);
+    st_keep(st + g, make_uint4(so[0], so[1], so[2], so[3]));
     st_stream(obs + g, make_uint4(oo[0], oo[1], oo[2], oo[3]));
     st_stream(rew + g, make_uint4(rr[0], rr[1], rr[2], rr[3]));
     st_stream(flg + g, ff);
@@ -504,288 +482,11 @@ k_get_obs(const PitchDev P, const uint32_t* __restrict__ state, int32_t* __restr
     }
 }
 
-// ------------------------------------------------------------------ shared-memory step table
-// K3's product, compacted: table[(obs-1)*100 + aa*20 + ab*4 + r] = next_obs | nonzero<<10 |
-// negative<<11 | nlog2<<12.  Built on the device by the rules path; (nS-1)*200 bytes.
-constexpr int kTableThreads = 1024;          // one CTA per SM owns the whole shared memory
-constexpr int kMaxTableStates = 1023;        // next_obs must fit 10 bits
-constexpr uint32_t kTblObsMask = 0x3FFu, kTblNonzero = 0x400u, kTblNegative = 0x800u;
-
-__global__ void __launch_bounds__(kThreads)
-k_build_step_table(const PitchDev P, int32_t nS, uint16_t* __restrict__ table)
-{
-    __shared__ __align__(16) uint8_t lut[kLutBytes];
-    build_cand_lut(lut, P);
-    const int64_t total = (int64_t)(nS - 1) * 100;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        const uint32_t r = (uint32_t)(i & 3), ja = (uint32_t)((i >> 2) % 25), aa = ja / 5u, ab = ja % 5u;
-        const uint32_t st = obs_to_packed(P, (int32_t)(i / 100) + 1);
-        const uint32_t a = st & 0xFFu, b = (st >> 8) & 0xFFu, p = (st >> 24) & 1u;
-        const Resolved o = resolve(lut, a, b, p, aa, ab, aa == 0, ab == 0, r);
-        const StepOut f = finish_step<false>(P, o, 0u, 0u, 0u, false);
-        table[i] = (uint16_t)((uint32_t)f.obs | (f.reward != 0.0f ? kTblNonzero : 0u) |
-                              (f.reward < 0.0f ? kTblNegative : 0u) | (o.nlog2 << 12));
-    }
-}
-
-// ---- TMA 1-D bulk copy global -> shared, completion on an mbarrier
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
-{
-    uint32_t ok;
-    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    return ok != 0;
-}
-
-// Stage the table into shared memory: one elected thread issues 16 KB bulk copies; everybody
-// waits on the mbarrier (bounded spin -> trap, so a fault cannot hang the GPU).
-__device__ __forceinline__ void stage_table(uint16_t* smem_tbl, const uint16_t* gtable, uint32_t bytes, uint64_t* bar)
-{
-    if (threadIdx.x == 0) {
-        mbar_init(bar, 1);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(bar, bytes);
-        const uint32_t chunk = 16384;
-        for (uint32_t off = 0; off < bytes; off += chunk) {
-            const uint32_t nb = bytes - off < chunk ? bytes - off : chunk;
-            tma_load_1d(reinterpret_cast<uint8_t*>(smem_tbl) + off, reinterpret_cast<const uint8_t*>(gtable) + off, nb, bar);
-        }
-    }
-    __syncthreads();    // barrier init visible to all before anyone polls it
-}
-__device__ __forceinline__ void wait_table(uint64_t* bar)
-{
-    uint32_t spins = 0;
-    while (!mbar_try_wait(bar, 0)) {
-        if (++spins > (1u << 22)) __trap();
-    }
-}
-
-// one env-step on an INDEX-layout state word through the shared-memory table
-struct TblOut { uint32_t state, obs, rew_bits, flags, reset_obs; };
-__device__ __forceinline__ TblOut table_step(const PitchDev& P, const uint16_t* __restrict__ tbl, uint32_t s,
-                                             uint32_t aa, uint32_t ab, uint32_t rg)
-{
-    const uint32_t sidx = (s & 0xFFFFu) - 1u, t = (s >> 16) & 0xFFu;
-    // clamp: a corrupt state word or action byte must not read outside the table
-    const uint32_t e = tbl[min(sidx * 100u + aa * 20u + ab * 4u + (rg & 3u), (uint32_t)(P.nS - 1) * 100u - 1u)];
-    const uint32_t nobs = e & kTblObsMask;
-    const bool done = nobs == 0;                                          // SIM:493: goal -> obs 0
-    const uint32_t t1 = t + 1u;                                           // SIM:399
-    const bool trunc = t1 >= (uint32_t)kMaxT;                             // SIM:404
-    const bool reset = done | trunc;                                      // SIM:406
-    const uint32_t m1 = (rg & 4u) ? 0xFFFFFFFFu : 0u, m2 = (rg & 8u) ? 0xFFFFFFFFu : 0u;
-    const uint32_t ro = (uint32_t)P.isd_obs[0] + (m1 & (uint32_t)P.obs_d1) + (m2 & (uint32_t)P.obs_d2); // SIM:414-415
-    TblOut o;
-    o.obs = nobs;
-    o.rew_bits = ((e & kTblNonzero) ? 0x3F800000u : 0u) | ((e & kTblNegative) << 20);   // +1.0f / -1.0f / 0.0f
-    o.flags = (done ? 1u : 0u) | (trunc ? 2u : 0u);
-    o.state = reset ? ro : (nobs | (t1 << 16));
-    o.reset_obs = reset ? ro : nobs;
-    return o;
-}
-
-template <bool RESET_OBS>
-__device__ __forceinline__ void table_step_group(const PitchDev& P, const uint16_t* tbl, const Group4& x, int64_t g,
-                                                 uint4* st, uint4* obs, uint4* rew, uint32_t* flg, uint4* rob)
-{
-    const uint32_t sv[4] = { x.s.x, x.s.y, x.s.z, x.s.w };
-    uint32_t so[4], oo[4], ro[4], rr[4], ff = 0;
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        const uint32_t aa = __byte_perm(x.a, 0, 0x4440 + e), ab = __byte_perm(x.b, 0, 0x4440 + e),
-                       rg = __byte_perm(x.r, 0, 0x4440 + e);
-        const TblOut o = table_step(P, tbl, sv[e], aa, ab, rg);
-        so[e] = o.state; oo[e] = o.obs; rr[e] = o.rew_bits; ro[e] = o.reset_obs;
-        ff |= o.flags << (8 * e);
-    }
-    st[g] = make_uint4(so[0], so[1], so[2], so[3]);
-    st_stream(obs + g, make_uint4(oo[0], oo[1], oo[2], oo[3]));
-    st_stream(rew + g, make_uint4(rr[0], rr[1], rr[2], rr[3]));
-    st_stream(flg + g, ff);
-    if (RESET_OBS) st_stream(rob + g, make_uint4(ro[0], ro[1], ro[2], ro[3]));
-}
-
-// K1, table variant: persistent, one 1024-thread CTA per SM, table (152 KB for 5x4) TMA-staged
-// into shared memory while the first groups' HBM loads are already in flight.
-template <bool RESET_OBS>
-__global__ void __launch_bounds__(kTableThreads, 1)
-k_step_table(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t table_bytes,
-             uint32_t* __restrict__ state, const uint8_t* __restrict__ act_a, const uint8_t* __restrict__ act_b,
-             const uint8_t* __restrict__ rng, int32_t* __restrict__ obs, float* __restrict__ reward,
-             uint8_t* __restrict__ flags, int32_t* __restrict__ reset_obs, int64_t n_groups)
-{
-    extern __shared__ __align__(128) uint8_t smem_raw[];
-    uint16_t* tbl = reinterpret_cast<uint16_t*>(smem_raw);
-    __shared__ __align__(8) uint64_t bar;
-    stage_table(tbl, gtable, table_bytes, &bar);
-
-    uint4* st4 = reinterpret_cast<uint4*>(state);
-    const uint32_t* a4 = reinterpret_cast<const uint32_t*>(act_a);
-    const uint32_t* b4 = reinterpret_cast<const uint32_t*>(act_b);
-    const uint32_t* r4 = reinterpret_cast<const uint32_t*>(rng);
-    uint4* o4 = reinterpret_cast<uint4*>(obs);
-    uint4* w4 = reinterpret_cast<uint4*>(reward);
-    uint32_t* f4 = reinterpret_cast<uint32_t*>(flags);
-    uint4* q4 = reinterpret_cast<uint4*>(reset_obs);
-
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    // first pair of groups: issue the HBM loads, THEN wait for the table
-    bool one = g < n_groups, two = g + stride < n_groups;
-    Group4 x0 = {}, x1 = {};
-    if (one) x0 = load_group(st4, a4, b4, r4, g);
-    if (two) x1 = load_group(st4, a4, b4, r4, g + stride);
-    wait_table(&bar);
-    while (one) {
-        const int64_t gn = g + 2 * stride;
-        const bool n_one = gn < n_groups, n_two = gn + stride < n_groups;
-        Group4 y0 = x0, y1 = x1;
-        if (n_one) y0 = load_group(st4, a4, b4, r4, gn);          // prefetch the next pair
-        if (n_two) y1 = load_group(st4, a4, b4, r4, gn + stride);
-        table_step_group<RESET_OBS>(P, tbl, x0, g, st4, o4, w4, f4, q4);
-        if (two) table_step_group<RESET_OBS>(P, tbl, x1, g + stride, st4, o4, w4, f4, q4);
-        x0 = y0; x1 = y1; g = gn; one = n_one; two = n_two;
-    }
-}
-
-// scalar tail / misaligned fallback of the table path (global-memory table, one env per thread)
-__global__ void __launch_bounds__(kThreads)
-k_step_table_scalar(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t* __restrict__ state,
-                    const uint8_t* __restrict__ act_a, const uint8_t* __restrict__ act_b,
-                    const uint8_t* __restrict__ rng, int32_t* __restrict__ obs, float* __restrict__ reward,
-                    uint8_t* __restrict__ flags, int32_t* __restrict__ reset_obs, int64_t n)
-{
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const TblOut o = table_step(P, gtable, state[i], act_a[i], act_b[i], rng[i]);
-        state[i] = o.state; obs[i] = (int32_t)o.obs; reward[i] = __uint_as_float(o.rew_bits);
-        flags[i] = (uint8_t)o.flags;
-        if (reset_obs) reset_obs[i] = (int32_t)o.reset_obs;
-    }
-}
-
-// K2, table variant: uniform random policy from Philox, state (obs | t<<16) in registers.
-template <int VEC>
-__global__ void __launch_bounds__(kTableThreads, 1)
-k_rollout_table(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t table_bytes,
-                uint32_t* __restrict__ state, uint64_t seed, uint64_t step0, int32_t K, uint64_t env_id_base,
-                int32_t* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ flags,
-                unsigned long long* __restrict__ stats, int64_t n)
-{
-    extern __shared__ __align__(128) uint8_t smem_raw[];
-    uint16_t* tbl = reinterpret_cast<uint16_t*>(smem_raw);
-    __shared__ __align__(8) uint64_t bar;
-    __shared__ unsigned int blk_stats[6];
-    if (threadIdx.x < 6) blk_stats[threadIdx.x] = 0;
-    stage_table(tbl, gtable, table_bytes, &bar);
-    wait_table(&bar);
-
-    uint32_t c_ep = 0, c_ga = 0, c_gb = 0, c_tr = 0, c_len = 0, c_steps = 0;
-    const int64_t n_groups = n / VEC;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_groups; g += stride) {
-        const int64_t i0 = g * VEC;
-        uint32_t s[VEC], w[VEC][4];
-        if (VEC == 4) {
-            const uint4 v = reinterpret_cast<const uint4*>(state)[g];
-            s[0] = v.x; s[1 % VEC] = v.y; s[2 % VEC] = v.z; s[3 % VEC] = v.w;
-        } else {
-            s[0] = state[i0];
-        }
-        for (int32_t k = 0; k < K; ++k) {
-            const uint64_t step = step0 + (uint64_t)k;
-            const uint32_t wi = (uint32_t)step & 3u;
-            if (k == 0 || wi == 0) {
-                const uint64_t blk = step >> 2;
-#pragma unroll
-                for (int e = 0; e < VEC; ++e) {
-                    const uint64_t env = env_id_base + (uint64_t)(i0 + e);
-                    philox4x32_10((uint32_t)env, (uint32_t)(env >> 32), (uint32_t)blk, (uint32_t)(blk >> 32),
-                                  (uint32_t)seed, (uint32_t)(seed >> 32), w[e]);
-                }
-            }
-            uint32_t oo[VEC], rr[VEC], ff = 0;
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) {
-                const uint32_t word = wi == 0 ? w[e][0] : (wi == 1 ? w[e][1] : (wi == 2 ? w[e][2] : w[e][3]));
-                uint32_t aa, ab;
-                philox_actions(word, aa, ab);
-                const uint32_t t_before = (s[e] >> 16) & 0xFFu;
-                const TblOut o = table_step(P, tbl, s[e], aa, ab, philox_rng8(word));
-                s[e] = o.state; oo[e] = o.obs; rr[e] = o.rew_bits; ff |= o.flags << (8 * e);
-                const bool done = o.flags & 1u, ended = o.flags != 0;
-                c_ep += ended; c_len += ended ? t_before + 1u : 0u;
-                c_ga += done && (o.rew_bits >> 31) == 0; c_gb += done && (o.rew_bits >> 31) != 0; c_tr += ended && !done;
-            }
-            c_steps += VEC;
-            const int64_t off = (int64_t)k * n;
-            if (VEC == 4) {
-                if (obs) st_stream(reinterpret_cast<uint4*>(obs + off) + g, make_uint4(oo[0], oo[1 % VEC], oo[2 % VEC], oo[3 % VEC]));
-                if (reward) st_stream(reinterpret_cast<uint4*>(reward + off) + g, make_uint4(rr[0], rr[1 % VEC], rr[2 % VEC], rr[3 % VEC]));
-                if (flags) st_stream(reinterpret_cast<uint32_t*>(flags + off) + g, ff);
-            } else {
-                if (obs) obs[off + i0] = (int32_t)oo[0];
-                if (reward) reward[off + i0] = __uint_as_float(rr[0]);
-                if (flags) flags[off + i0] = (uint8_t)ff;
-            }
-        }
-        if (VEC == 4) reinterpret_cast<uint4*>(state)[g] = make_uint4(s[0], s[1 % VEC], s[2 % VEC], s[3 % VEC]);
-        else state[i0] = s[0];
-    }
-    if (stats) {
-        uint32_t v[6] = { c_ep, c_ga, c_gb, c_tr, c_steps, c_len };
-#pragma unroll
-        for (int j = 0; j < 6; ++j) {
-            const uint32_t r = __reduce_add_sync(0xFFFFFFFFu, v[j]);
-            if ((threadIdx.x & 31) == 0 && r) atomicAdd(&blk_stats[j], r);
-        }
-        __syncthreads();
-        if (threadIdx.x < 6 && blk_stats[threadIdx.x])
-            atomicAdd(&stats[threadIdx.x], (unsigned long long)blk_stats[threadIdx.x]);
-    }
-}
-
-__global__ void __launch_bounds__(kThreads)
-k_convert_state(const PitchDev P, int32_t nS, const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
-                int32_t to_layout, int64_t n)
-{
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const uint32_t s = in[i];
-        if (to_layout == SOCCER_LAYOUT_INDEX) {
-            const uint32_t a = s & 0xFFu, b = (s >> 8) & 0xFFu, p = (s >> 24) & 1u, t = (s >> 16) & 0xFFu;
-            const bool bad = ((a | b) & kGoalBit) || (s & kNeedsReset);
-            out[i] = (bad ? 0u : (uint32_t)obs_index(P, a, b, p)) | (t << 16);
-        } else {
-            const int32_t o = (int32_t)(s & 0xFFFFu);
-            const uint32_t t = (s >> 16) & 0xFFu;
-            out[i] = (o >= 1 && o < nS) ? (obs_to_packed(P, o) | (t << 16)) : (kNeedsReset | kGoalBit | (t << 16));
-        }
-    }
-}
-
 int table_bytes_of(const PitchDev& P, int64_t* bytes)
 {
     const int64_t nS = 1 + 2 * (int64_t)P.F * P.Fm1;
     if (nS - 1 > kMaxTableStates || P.slip) return SOCCER_ETABLE;
-    *bytes = ((nS - 1) * 200 + 15) / 16 * 16;
+    *bytes = (nS * 200 + 15) / 16 * 16;     // nS rows: row 0 is the absorbing terminal observation
     return SOCCER_OK;
 }
 
@@ -805,9 +506,9 @@ int launch_generic(const PitchDev& P, const StepOpts& o, cudaStream_t stream)
     return launch_status();
 }
 
-int table_grid(int64_t n_groups)
+int table_grid(int64_t n_groups, int threads = kTableThreads)
 {
-    const int64_t need = (n_groups + kTableThreads - 1) / kTableThreads;
+    const int64_t need = (n_groups + threads - 1) / threads;
     const int64_t cap = sm_count();
     return (int)(need < cap ? (need < 1 ? 1 : need) : cap);
 }
@@ -1060,7 +761,7 @@ int soccer_build_step_table(const soccer_pitch* pitch, uint16_t* table, soccer_s
     if (!table) return SOCCER_EINVAL;
     PitchDev P; int rc = make_pitch_dev(pitch, &P); if (rc) return rc;
     int64_t bytes; rc = table_bytes_of(P, &bytes); if (rc) return rc;
-    k_build_step_table<<<grid_for((int64_t)(P.nS - 1) * 100, 4), kThreads, 0, (cudaStream_t)stream>>>(P, P.nS, table);
+    k_build_step_table<<<grid_for((int64_t)P.nS * 100, 4), kThreads, 0, (cudaStream_t)stream>>>(P, P.nS, table);
     return launch_status();
 }
 
@@ -1081,14 +782,14 @@ int soccer_step_table(const soccer_pitch* pitch, const uint16_t* table, uint32_t
     if (vec) {
         const int64_t n_groups = n / 4;
         if (reset_obs) {
-            const int e0 = allow_big_smem(k_step_table<true>, bytes);
+            const int e0 = allow_big_smem(k_step_table<true>, bytes + 16);
             if (e0) return e0;
-            k_step_table<true><<<table_grid(n_groups), kTableThreads, bytes, st>>>(
+            k_step_table<true><<<table_grid(n_groups), kTableThreads, bytes + 16, st>>>(
                 P, table, (uint32_t)bytes, state, act_a, act_b, rng8, obs, reward, flags, reset_obs, n_groups);
         } else {
-            const int e0 = allow_big_smem(k_step_table<false>, bytes);
+            const int e0 = allow_big_smem(k_step_table<false>, bytes + 16);
             if (e0) return e0;
-            k_step_table<false><<<table_grid(n_groups), kTableThreads, bytes, st>>>(
+            k_step_table<false><<<table_grid(n_groups), kTableThreads, bytes + 16, st>>>(
                 P, table, (uint32_t)bytes, state, act_a, act_b, rng8, obs, reward, flags, nullptr, n_groups);
         }
         const int e = launch_status();
@@ -1116,14 +817,14 @@ int soccer_rollout_table(const soccer_pitch* pitch, const uint16_t* table, uint3
     const bool vec = (n % 4 == 0) && aligned(state, 16) && (!obs || aligned(obs, 16)) &&
                      (!reward || aligned(reward, 16)) && (!flags || aligned(flags, 4));
     if (vec) {
-        const int e0 = allow_big_smem(k_rollout_table<4>, bytes);
+        const int e0 = allow_big_smem(k_rollout_table<4>, bytes + 16);
         if (e0) return e0;
-        k_rollout_table<4><<<table_grid(n / 4), kTableThreads, bytes, st>>>(P, table, (uint32_t)bytes, state, seed, step0, K,
+        k_rollout_table<4><<<table_grid(n / 4, kRolloutThreads), kRolloutThreads, bytes + 16, st>>>(P, table, (uint32_t)bytes, state, seed, step0, K,
                                                                             env_id_base, obs, reward, flags, stats, n);
     } else {
-        const int e0 = allow_big_smem(k_rollout_table<1>, bytes);
+        const int e0 = allow_big_smem(k_rollout_table<1>, bytes + 16);
         if (e0) return e0;
-        k_rollout_table<1><<<table_grid(n), kTableThreads, bytes, st>>>(P, table, (uint32_t)bytes, state, seed, step0, K,
+        k_rollout_table<1><<<table_grid(n, kRolloutThreads), kRolloutThreads, bytes + 16, st>>>(P, table, (uint32_t)bytes, state, seed, step0, K,
                                                                         env_id_base, obs, reward, flags, stats, n);
     }
     return launch_status();

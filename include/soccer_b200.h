@@ -38,8 +38,9 @@
  *   rngf64: step draw for slip_prob > 0 as the raw fp64 uniform the reference's
  *           np_random.random() returned (SIM:395)
  * Counter-based randomness: Philox4x32-10, key = seed, counter = (env_id, step >> 2),
- *   output word step & 3:  bits 0..23 -> joint action (w24 * 25) >> 24, aa = ja / 5,
- *   ab = ja % 5;  bits 24..25 = step draw;  bits 26..27 = reset draw.
+ *   output word step & 3:  jr = ((w & 0xFFFFFF) * 100) >> 24 is uniform on 0..99 and carries the
+ *   joint action and the step draw at once: ja = jr >> 2, aa = ja / 5, ab = ja % 5, step draw
+ *   = jr & 3;  bits 24..25 of w = reset draw.
  *
  * flags byte: bit 0 terminated (SIM:403), bit 1 truncated (SIM:404).  Only when
  *   soccer_step_args.detail != 0: bits 2..3 = log2(number of outcomes the chosen slip
@@ -116,7 +117,7 @@ int soccer_obs_to_state_host(const soccer_pitch *pitch, int32_t obs, uint32_t *p
  * selects the envs to reset; obs_out optional. */
 int soccer_reset(const soccer_pitch *pitch, uint32_t *state, int32_t *obs_out,
                  const uint8_t *rng8, const uint8_t *mask, int64_t n, soccer_stream_t stream);
-/* same, reset draw = Philox word (seed, env_id_base + i, step) bits 26..27 */
+/* same, reset draw = Philox word (seed, env_id_base + i, step) bits 24..25 */
 int soccer_reset_philox(const soccer_pitch *pitch, uint32_t *state, int32_t *obs_out,
                         const uint8_t *mask, uint64_t seed, uint64_t step, uint64_t env_id_base,
                         int64_t n, soccer_stream_t stream);
@@ -187,11 +188,12 @@ int soccer_sweep(const soccer_pitch *pitch, int32_t n_combos, uint8_t *n_out, ui
 #define SOCCER_LAYOUT_CELL  0
 #define SOCCER_LAYOUT_INDEX 1
 #define SOCCER_ETABLE (-5)   /* pitch too large for the shared-memory step table / slip_prob != 0 */
-/* bytes of the step table for this pitch: (nS-1) * 100 * sizeof(uint16_t), rounded up to 16 */
+/* bytes of the step table for this pitch: nS * 100 * sizeof(int16_t), rounded up to 16 */
 int soccer_step_table_bytes_host(const soccer_pitch *pitch, int64_t *bytes);
-/* Fill table[(obs-1)*100 + aa*20 + ab*4 + r] for every state, joint action and 2-bit draw by
- * running the rules path (SIM:296-373, 235-240) on the device.  Entry: bits 0..9 next
- * observation (0 = goal), bit 10 reward != 0, bit 11 reward < 0, bits 12..13 log2(#outcomes). */
+/* Fill table[obs*100 + aa*20 + ab*4 + r] for every state, joint action and 2-bit draw by
+ * running the rules path (SIM:296-373, 235-240) on the device.  Entry (int16): bits 0..9 next
+ * observation (0 = goal), bits 10..11 log2(#outcomes), bits 14..15 the reward as a signed 2-bit
+ * field, so reward = entry >> 14 (arithmetic).  Row 0 is the absorbing terminal observation. */
 int soccer_build_step_table(const soccer_pitch *pitch, uint16_t *table, soccer_stream_t stream);
 /* soccer_step on SOCCER_LAYOUT_INDEX states with the table staged into shared memory by TMA */
 int soccer_step_table(const soccer_pitch *pitch, const uint16_t *table, uint32_t *state,

@@ -60,7 +60,7 @@ def test_argument_errors_without_gpu(L):
     a.state, a.policy_a, a.policy_b, a.n = 16, 16, 16, 4
     assert lib.soccer_step_ex(C.byref(p), C.byref(a), None) == -4                                  # SIM:38
     nbytes = C.c_int64()
-    assert lib.soccer_step_table_bytes_host(C.byref(p), C.byref(nbytes)) == 0 and nbytes.value == 760 * 200
+    assert lib.soccer_step_table_bytes_host(C.byref(p), C.byref(nbytes)) == 0 and nbytes.value == 152208   # 761 rows * 100 * 2 B, up to 16
     assert lib.soccer_step_table_bytes_host(C.byref(L.Pitch(6, 4, 0.0)), C.byref(nbytes)) == -5
     assert lib.soccer_step_table_bytes_host(C.byref(L.Pitch(5, 4, 0.2)), C.byref(nbytes)) == -5
 
