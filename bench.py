@@ -184,8 +184,13 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---------------- device-resident throughput (value) + per-launch roofline
+    def episode_stats(o):
+        return env.step_stats(flags=o[2], reward=o[1])
+
     for i in range(W):
         env.step(*ins[i % RING], out=outs[i % RING])
+    if world > 1:
+        dist.all_reduce(episode_stats(outs[0]))        # warm the communicator
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -200,8 +205,7 @@ def run_ours(args):
     stats = None
     if world > 1:
         # the one collective of the path: episode statistics of the last step
-        f = outs[(K - 1) % RING][2]
-        stats = torch.stack([(f != 0).sum(), (f & 1).sum(), (f & 2).sum() // 2]).to(torch.int64)
+        stats = episode_stats(outs[(K - 1) % RING])
         dist.all_reduce(stats)
     end = torch.cuda.Event(enable_timing=True)
     end.record()
@@ -219,23 +223,27 @@ def run_ours(args):
     achieved = BYTES_PER_ENV_STEP * N / (kern_ms * 1e-3) / 1e9
 
     # ---------------- end to end: pinned host buffers in, pinned host buffers out, every step
+    # every step is a closed loop: upload this step's actions/draws, step, download obs/reward/flags,
+    # and wait for them (a host-side policy needs them to pick the next actions)
     h_in = [tuple(x.cpu().pin_memory() for x in ins[i]) for i in range(2)]
-    for i in range(2):
-        env.step_host(*h_in[i % 2])
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     Ke = max(3, min(K, 10))
-    e0.record()
-    for i in range(Ke):
-        h_obs, h_rew, h_flg = env.step_host(*h_in[i % 2])
-    e1.record()
-    barrier()
-    e2e_ms = e0.elapsed_time(e1)
-    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * N * Ke / (float(t.item()) * 1e-3)
-    checksum = int(h_obs[:1024].sum())   # the result really is on the host
+    e2e = {}
+    for narrow in (True, False):
+        for i in range(2):
+            env.step_host(*h_in[i % 2], narrow=narrow, n_chunks=args.chunks)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        cur = torch.cuda.current_stream(dev)
+        e0.record()
+        for i in range(Ke):
+            h_obs, h_rew, h_flg = env.step_host(*h_in[i % 2], narrow=narrow, n_chunks=args.chunks)   # syncs
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e[narrow] = (world * N * Ke / (float(t.item()) * 1e-3), int(h_obs[:1024].to(torch.int64).sum()))
+    e2e_value, checksum = e2e[True]      # the result really is on the host
 
     if rank != 0:
         if world > 1:
@@ -298,8 +306,12 @@ def run_ours(args):
                      "bytes_per_env_step": BYTES_PER_ENV_STEP, "avg_launch_ms": kern_ms, "min_launch_ms": min(per_launch)},
         "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": 1, "kind": "port", "sample": cpu_sample,
                          "all_cores": {"value": cpu_all_v, "cores": cores}},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 3 * N, "d2h_bytes_per_step": 9 * N,
-                "steps": Ke, "checksum": checksum},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 3 * N, "d2h_bytes_per_step": 4 * N,
+                "steps": Ke, "checksum": checksum, "chunks": args.chunks,
+                "api": "SoccerVecEnv.step_host(narrow=True): uint8 actions/draws up; obs uint16, reward int8, "
+                       "flags uint8 down; every step waits for its results",
+                "wide": {"value": e2e[False][0], "d2h_bytes_per_step": 9 * N,
+                         "api": "step_host(narrow=False): obs int32, reward float32, flags uint8 down"}},
         "gpu_launches": K,
         "clocks": clocks,
         "extra": extra,
@@ -318,6 +330,7 @@ def main():
     ap.add_argument("--envs-per-gpu", type=int, default=1 << 24)
     ap.add_argument("--kernel", default="auto", choices=["auto", "rules", "table"])
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--chunks", type=int, default=8, help="pipeline slices of the host-buffer step")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -22,7 +22,8 @@ EXPORTS = (
     "soccer_state_to_obs_host", "soccer_obs_to_state_host", "soccer_reset", "soccer_reset_philox",
     "soccer_set_state", "soccer_get_obs", "soccer_step", "soccer_step_philox", "soccer_step_ex",
     "soccer_rollout", "soccer_sweep", "soccer_dense", "soccer_build_step_table", "soccer_step_table",
-    "soccer_rollout_table", "soccer_step_table_bytes_host", "soccer_convert_state",
+    "soccer_rollout_table", "soccer_step_table_bytes_host", "soccer_convert_state", "soccer_step_stats",
+    "soccer_step_host", "soccer_step_host_scratch_bytes_host",
 )
 
 
@@ -51,6 +52,13 @@ class StepArgs(C.Structure):
                 ("auto_reset", C.c_int32), ("use_philox", C.c_int32), ("detail", C.c_int32),
                 ("reserved", C.c_int32), ("seed", C.c_uint64), ("step", C.c_uint64),
                 ("env_id_base", C.c_uint64)]
+
+
+class StepHostArgs(C.Structure):
+    _fields_ = [("state", C.c_void_p), ("table", C.c_void_p), ("scratch", C.c_void_p), ("h_act_a", C.c_void_p),
+                ("h_act_b", C.c_void_p), ("h_rng8", C.c_void_p), ("h_obs", C.c_void_p), ("h_reward", C.c_void_p),
+                ("h_flags", C.c_void_p), ("n", C.c_int64), ("narrow", C.c_int32), ("n_chunks", C.c_int32),
+                ("s_in", C.c_void_p), ("s_compute", C.c_void_p), ("s_out", C.c_void_p)]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -116,6 +124,9 @@ def lib():
         "soccer_step_table": [PP, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp],
         "soccer_rollout_table": [PP, vp, vp, u64, u64, i32, u64, vp, vp, vp, vp, i64, vp],
         "soccer_convert_state": [PP, vp, vp, i32, i64, vp],
+        "soccer_step_stats": [vp, vp, i64, vp, vp],
+        "soccer_step_host": [PP, C.POINTER(StepHostArgs)],
+        "soccer_step_host_scratch_bytes_host": [i64, C.POINTER(i64)],
     }
     for name, argtypes in sig.items():
         fn = getattr(L, name)

@@ -490,6 +490,94 @@ int table_bytes_of(const PitchDev& P, int64_t* bytes)
     return SOCCER_OK;
 }
 
+// Episode statistics of ONE lock-step step from its flags (+ reward) streams: the K1 counterpart
+// of K2's fused statistics.  16 envs per thread (one 128-bit flags load), warp redux, 4 atomics/CTA.
+__global__ void __launch_bounds__(kThreads)
+k_step_stats(const uint8_t* __restrict__ flags, const float* __restrict__ reward, int64_t n,
+             unsigned long long* __restrict__ stats)
+{
+    __shared__ unsigned int blk[4];
+    if (threadIdx.x < 4) blk[threadIdx.x] = 0;
+    __syncthreads();
+    uint32_t ended = 0, trunc_only = 0, ga = 0, gb = 0;
+    const int64_t n16 = n / 16;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const bool vec = (reinterpret_cast<uintptr_t>(flags) & 15) == 0;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; vec && g < n16; g += stride) {
+        const uint4 f = __ldcs(reinterpret_cast<const uint4*>(flags) + g);
+        const uint32_t w[4] = { f.x, f.y, f.z, f.w };
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t d = w[k] & 0x01010101u, t = (w[k] >> 1) & ~w[k] & 0x01010101u;
+            ended = __dp4a(d | t, 0x01010101u, ended);
+            trunc_only = __dp4a(t, 0x01010101u, trunc_only);
+            if (reward && d) {                              // goals are rare (~3 % of env-steps)
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if ((d >> (8 * e)) & 1u) {
+                        const float r = reward[g * 16 + k * 4 + e];
+                        ga += r > 0.0f; gb += r < 0.0f;
+                    }
+            }
+        }
+    }
+    const int64_t tail0 = vec ? n16 * 16 : 0;
+    for (int64_t i = tail0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t f = flags[i];
+        ended += (f & 3u) != 0; trunc_only += (f & 3u) == 2u;
+        if (reward && (f & 1u)) { const float r = reward[i]; ga += r > 0.0f; gb += r < 0.0f; }
+    }
+    uint32_t v[4] = { ended, ga, gb, trunc_only };
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t r = __reduce_add_sync(0xFFFFFFFFu, v[j]);
+        if ((threadIdx.x & 31) == 0 && r) atomicAdd(&blk[j], r);
+    }
+    __syncthreads();
+    if (threadIdx.x < 4 && blk[threadIdx.x]) atomicAdd(&stats[threadIdx.x], (unsigned long long)blk[threadIdx.x]);
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&stats[4], (unsigned long long)n);
+}
+
+// obs int32 -> uint16, reward float32 -> int8 for the narrow host download (values are exact:
+// obs < nS <= 31501, reward in {-1, 0, +1})
+__global__ void __launch_bounds__(kThreads)
+k_narrow(const int32_t* __restrict__ obs, const float* __restrict__ reward, uint16_t* __restrict__ obs16,
+         int8_t* __restrict__ rew8, int64_t n)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n4 = n / 4;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n4; g += stride) {
+        const uint4 o = __ldcs(reinterpret_cast<const uint4*>(obs) + g);
+        const float4 r = __ldcs(reinterpret_cast<const float4*>(reward) + g);
+        const uint32_t lo = __byte_perm(o.x, o.y, 0x5410), hi = __byte_perm(o.z, o.w, 0x5410);
+        __stcs(reinterpret_cast<uint2*>(obs16) + g, make_uint2(lo, hi));
+        const uint32_t rb = ((uint32_t)(int)r.x & 0xFFu) | (((uint32_t)(int)r.y & 0xFFu) << 8) |
+                            (((uint32_t)(int)r.z & 0xFFu) << 16) | (((uint32_t)(int)r.w & 0xFFu) << 24);
+        __stcs(reinterpret_cast<uint32_t*>(rew8) + g, rb);
+    }
+    for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        obs16[i] = (uint16_t)obs[i];
+        rew8[i] = (int8_t)(int)reward[i];
+    }
+}
+
+int64_t round_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+// scratch layout of soccer_step_host: three input byte streams, flags, obs, reward, obs16, rew8
+struct HostScratch { uint8_t *a, *b, *r, *f; int32_t* obs; float* rew; uint16_t* obs16; int8_t* rew8; int64_t bytes; };
+HostScratch host_scratch(void* base, int64_t n)
+{
+    HostScratch s;
+    uint8_t* p = reinterpret_cast<uint8_t*>(base);
+    const int64_t nb = round_up(n, 256);
+    s.a = p; p += nb; s.b = p; p += nb; s.r = p; p += nb; s.f = p; p += nb;
+    s.obs = reinterpret_cast<int32_t*>(p); p += 4 * nb;
+    s.rew = reinterpret_cast<float*>(p); p += 4 * nb;
+    s.obs16 = reinterpret_cast<uint16_t*>(p); p += 2 * nb;
+    s.rew8 = reinterpret_cast<int8_t*>(p); p += nb;
+    s.bytes = p - reinterpret_cast<uint8_t*>(base);
+    return s;
+}
+
 int grid_for(int64_t work_items, int blocks_per_sm)
 {
     const int64_t need = (work_items + kThreads - 1) / kThreads;
@@ -838,6 +926,86 @@ int soccer_convert_state(const soccer_pitch* pitch, const uint32_t* in, uint32_t
     if (n == 0) return SOCCER_OK;
     k_convert_state<<<grid_for(n, 8), kThreads, 0, (cudaStream_t)stream>>>(P, P.nS, in, out, to_layout, n);
     return launch_status();
+}
+
+int soccer_step_stats(const uint8_t* flags, const float* reward, int64_t n, unsigned long long* stats,
+                      soccer_stream_t stream)
+{
+    if (!flags || !stats || n < 0) return SOCCER_EINVAL;
+    if (n == 0) return SOCCER_OK;
+    k_step_stats<<<grid_for((n + 15) / 16, 8), kThreads, 0, (cudaStream_t)stream>>>(flags, reward, n, stats);
+    return launch_status();
+}
+
+int soccer_step_host_scratch_bytes_host(int64_t n, int64_t* bytes)
+{
+    if (!bytes || n < 0) return SOCCER_EINVAL;
+    *bytes = host_scratch(nullptr, n).bytes;
+    return SOCCER_OK;
+}
+
+int soccer_step_host(const soccer_pitch* pitch, const soccer_step_host_args* a)
+{
+    if (!a || !a->state || !a->scratch || !a->h_act_a || !a->h_act_b || !a->h_rng8 || !a->h_obs || !a->h_reward ||
+        !a->h_flags || a->n < 0 || a->n_chunks < 1)
+        return SOCCER_EINVAL;
+    if (pitch && pitch->slip_prob != 0.0) return SOCCER_ESLIP;
+    if (a->n == 0) return SOCCER_OK;
+    cudaStream_t s_in = (cudaStream_t)a->s_in, s_k = (cudaStream_t)a->s_compute, s_out = (cudaStream_t)a->s_out;
+    const HostScratch sc = host_scratch(a->scratch, a->n);
+    const int64_t chunk = round_up((a->n + a->n_chunks - 1) / a->n_chunks, 256);
+#define SOCCER_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { rc = (int)e_; goto done; } } while (0)
+    int rc = SOCCER_OK;
+    cudaEvent_t ev_prev_k = nullptr, ev_prev_out = nullptr, ev_in = nullptr, ev_k = nullptr;
+    // cross-call hazards on the scratch buffers: this call's uploads overwrite inputs the previous
+    // call's kernels read, and its kernels overwrite outputs the previous call's downloads read
+    SOCCER_CUDA(cudaEventCreateWithFlags(&ev_prev_k, cudaEventDisableTiming));
+    SOCCER_CUDA(cudaEventCreateWithFlags(&ev_prev_out, cudaEventDisableTiming));
+    SOCCER_CUDA(cudaEventRecord(ev_prev_k, s_k));
+    SOCCER_CUDA(cudaStreamWaitEvent(s_in, ev_prev_k, 0));
+    SOCCER_CUDA(cudaEventRecord(ev_prev_out, s_out));
+    SOCCER_CUDA(cudaStreamWaitEvent(s_k, ev_prev_out, 0));
+    for (int64_t lo = 0; lo < a->n; lo += chunk) {
+        const int64_t m = a->n - lo < chunk ? a->n - lo : chunk;
+        SOCCER_CUDA(cudaMemcpyAsync(sc.a + lo, a->h_act_a + lo, m, cudaMemcpyHostToDevice, s_in));
+        SOCCER_CUDA(cudaMemcpyAsync(sc.b + lo, a->h_act_b + lo, m, cudaMemcpyHostToDevice, s_in));
+        SOCCER_CUDA(cudaMemcpyAsync(sc.r + lo, a->h_rng8 + lo, m, cudaMemcpyHostToDevice, s_in));
+        SOCCER_CUDA(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
+        SOCCER_CUDA(cudaEventRecord(ev_in, s_in));
+        SOCCER_CUDA(cudaStreamWaitEvent(s_k, ev_in, 0));
+        SOCCER_CUDA(cudaEventDestroy(ev_in)); ev_in = nullptr;
+        if (a->table)
+            rc = soccer_step_table(pitch, a->table, a->state + lo, sc.a + lo, sc.b + lo, sc.r + lo, sc.obs + lo,
+                                   sc.rew + lo, sc.f + lo, nullptr, m, (soccer_stream_t)s_k);
+        else
+            rc = soccer_step(pitch, a->state + lo, sc.a + lo, sc.b + lo, sc.r + lo, sc.obs + lo, sc.rew + lo,
+                             sc.f + lo, nullptr, m, (soccer_stream_t)s_k);
+        if (rc) goto done;
+        if (a->narrow) {
+            k_narrow<<<grid_for(m / 4 + 1, 8), kThreads, 0, s_k>>>(sc.obs + lo, sc.rew + lo, sc.obs16 + lo, sc.rew8 + lo, m);
+            rc = launch_status();
+            if (rc) goto done;
+        }
+        SOCCER_CUDA(cudaEventCreateWithFlags(&ev_k, cudaEventDisableTiming));
+        SOCCER_CUDA(cudaEventRecord(ev_k, s_k));
+        SOCCER_CUDA(cudaStreamWaitEvent(s_out, ev_k, 0));
+        SOCCER_CUDA(cudaEventDestroy(ev_k)); ev_k = nullptr;
+        if (a->narrow) {
+            SOCCER_CUDA(cudaMemcpyAsync((uint16_t*)a->h_obs + lo, sc.obs16 + lo, 2 * m, cudaMemcpyDeviceToHost, s_out));
+            SOCCER_CUDA(cudaMemcpyAsync((int8_t*)a->h_reward + lo, sc.rew8 + lo, m, cudaMemcpyDeviceToHost, s_out));
+        } else {
+            SOCCER_CUDA(cudaMemcpyAsync((int32_t*)a->h_obs + lo, sc.obs + lo, 4 * m, cudaMemcpyDeviceToHost, s_out));
+            SOCCER_CUDA(cudaMemcpyAsync((float*)a->h_reward + lo, sc.rew + lo, 4 * m, cudaMemcpyDeviceToHost, s_out));
+        }
+        SOCCER_CUDA(cudaMemcpyAsync(a->h_flags + lo, sc.f + lo, m, cudaMemcpyDeviceToHost, s_out));
+    }
+done:
+#undef SOCCER_CUDA
+    if (ev_prev_k) cudaEventDestroy(ev_prev_k);
+    if (ev_prev_out) cudaEventDestroy(ev_prev_out);
+    if (ev_in) cudaEventDestroy(ev_in);
+    if (ev_k) cudaEventDestroy(ev_k);
+    return rc;
 }
 
 int soccer_dense(const soccer_pitch* pitch, const int8_t* policy_a, const int8_t* policy_b, double* Pmat,

@@ -214,33 +214,71 @@ class SoccerVecEnv:
         self.step_count += 1
         return obs, reward, flags, reset_obs
 
-    # ------------------------------------------------------------------ host-buffer path (end to end)
-    def _host_buffers(self):
-        if getattr(self, "_hb", None) is None:
-            n, dev = self.num_envs, self.device
-            self._hb = dict(
-                d_in=[torch.empty(n, dtype=torch.uint8, device=dev) for _ in range(3)],
-                h_obs=torch.empty(n, dtype=torch.int32).pin_memory(),
-                h_reward=torch.empty(n, dtype=torch.float32).pin_memory(),
-                h_flags=torch.empty(n, dtype=torch.uint8).pin_memory())
-        return self._hb
-
-    def step_host(self, act_a: torch.Tensor, act_b: torch.Tensor, rng8: torch.Tensor, sync: bool = True):
-        """step() with HOST buffers: uint8 CPU tensors in (pinned memory makes the copies
-        asynchronous), CPU tensors out (obs int32, reward float32, flags uint8; pinned, owned by
-        the env and overwritten by the next call).  Host->device and device->host copies are
-        part of the call -- this is the end-to-end path bench.py reports as `e2e`."""
-        hb = self._host_buffers()
+    def step_stats(self, flags: Optional[torch.Tensor] = None, reward: Optional[torch.Tensor] = None,
+                   stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Accumulate [episodes, goals_A, goals_B, truncations, steps, -] of one step's streams."""
+        flags = self.flags if flags is None else flags
+        reward = self.reward if reward is None else reward
+        if stats is None:
+            stats = torch.zeros(6, dtype=torch.int64, device=self.device)
+        if flags.numel() == 0:
+            return stats
         with torch.cuda.device(self.device):
-            for d, h in zip(hb["d_in"], (act_a, act_b, rng8)):
-                d.copy_(h, non_blocking=True)
-            self.step(hb["d_in"][0], hb["d_in"][1], hb["d_in"][2])
-            hb["h_obs"].copy_(self.obs, non_blocking=True)
-            hb["h_reward"].copy_(self.reward, non_blocking=True)
-            hb["h_flags"].copy_(self.flags, non_blocking=True)
-            if sync:
-                torch.cuda.current_stream(self.device).synchronize()
-        return hb["h_obs"], hb["h_reward"], hb["h_flags"]
+            check(self.lib.soccer_step_stats(_ptr(flags), _ptr(reward), flags.numel(), _ptr(stats), _stream(self.device)),
+                  "soccer_step_stats")
+        return stats
+
+    # ------------------------------------------------------------------ host-buffer path (end to end)
+    def _host_buffers(self, narrow: bool):
+        key = "_hb_narrow" if narrow else "_hb_wide"
+        if getattr(self, key, None) is None:
+            n, dev = self.num_envs, self.device
+            if getattr(self, "_host_common", None) is None:
+                nbytes = C.c_int64()
+                check(self.lib.soccer_step_host_scratch_bytes_host(n, C.byref(nbytes)), "scratch_bytes")
+                self._host_common = dict(scratch=torch.empty(nbytes.value, dtype=torch.uint8, device=dev),
+                                         streams=[torch.cuda.Stream(device=dev) for _ in range(3)],
+                                         h_flags=torch.empty(n, dtype=torch.uint8).pin_memory())
+            setattr(self, key, dict(
+                h_obs=torch.empty(n, dtype=torch.int16 if narrow else torch.int32).pin_memory(),
+                h_reward=torch.empty(n, dtype=torch.int8 if narrow else torch.float32).pin_memory()))
+        return self._host_common, getattr(self, key)
+
+    def step_host(self, act_a: torch.Tensor, act_b: torch.Tensor, rng8: torch.Tensor, narrow: bool = False,
+                  n_chunks: int = 8, sync: bool = True):
+        """step() with HOST buffers -- the end-to-end path bench.py reports as `e2e`.
+
+        In: uint8 CPU tensors (pinned memory keeps the copies asynchronous).  Out: CPU tensors
+        owned by the env and overwritten by the next call -- obs int32 / reward float32 / flags
+        uint8, or with narrow=True obs uint16 (viewed as int16 by torch) / reward int8: same values,
+        4 instead of 9 bytes per env over PCIe.  The batch is cut into n_chunks slices whose upload,
+        kernel and download overlap on three streams (soccer_step_host in the C ABI)."""
+        if self.slip_prob != 0.0 or not self.multiagent or self.rng_mode != "injected":
+            raise NotImplementedError("step_host covers the multi-agent, slip_prob == 0, injected-draw step")
+        for name, t in (("act_a", act_a), ("act_b", act_b), ("rng8", rng8)):
+            if not (isinstance(t, torch.Tensor) and not t.is_cuda and t.dtype == torch.uint8 and t.is_contiguous()
+                    and t.numel() == self.num_envs):
+                raise ValueError(f"{name} must be a contiguous uint8 CPU tensor with {self.num_envs} elements")
+        common, hb = self._host_buffers(narrow)
+        if self.num_envs == 0:
+            return hb["h_obs"], hb["h_reward"], common["h_flags"]
+        s_in, s_k, s_out = common["streams"]
+        cur = torch.cuda.current_stream(self.device)
+        s_k.wait_stream(cur)                       # state may have been touched on the caller's stream
+        a = _lib.StepHostArgs()
+        a.state, a.table = self.state.data_ptr(), (None if self.table is None else self.table.data_ptr())
+        a.scratch = common["scratch"].data_ptr()
+        a.h_act_a, a.h_act_b, a.h_rng8 = act_a.data_ptr(), act_b.data_ptr(), rng8.data_ptr()
+        a.h_obs, a.h_reward, a.h_flags = hb["h_obs"].data_ptr(), hb["h_reward"].data_ptr(), common["h_flags"].data_ptr()
+        a.n, a.narrow, a.n_chunks = self.num_envs, int(bool(narrow)), max(1, int(n_chunks))
+        a.s_in, a.s_compute, a.s_out = s_in.cuda_stream, s_k.cuda_stream, s_out.cuda_stream
+        with torch.cuda.device(self.device):
+            check(self.lib.soccer_step_host(C.byref(self.pitch), C.byref(a)), "soccer_step_host")
+        cur.wait_stream(s_k)                       # later work on the caller's stream sees the new state
+        self.step_count += 1
+        if sync:
+            s_out.synchronize()
+        return hb["h_obs"], hb["h_reward"], common["h_flags"]
 
     def rollout(self, K: int, policy_a=None, policy_b=None, want_streams: bool = True, stats: Optional[torch.Tensor] = None,
                 out=None):

@@ -164,6 +164,13 @@ typedef struct soccer_step_args {
 } soccer_step_args;
 int soccer_step_ex(const soccer_pitch *pitch, const soccer_step_args *args, soccer_stream_t stream);
 
+/* Episode statistics of one lock-step step, from its flags (and, optionally, reward) streams:
+ * stats[0] += episodes ended, [1] += goals_A (reward > 0), [2] += goals_B, [3] += truncations
+ * without a goal, [4] += n (steps); [5] (sum_episode_len) is left alone.  This vector is what the
+ * multi-GPU path all-reduces (the one collective of the path). */
+int soccer_step_stats(const uint8_t *flags, const float *reward, int64_t n,
+                      unsigned long long *stats, soccer_stream_t stream);
+
 /* ---- K2: fused K-step rollout, state register-resident, on-device policy ---- */
 /* policy_* == NULL -> uniform random joint action from the Philox word; else int8[nS] table.
  * obs/reward/flags are [K][n] streams (each optional).  stats[6] (optional, uint64, accumulated
@@ -209,6 +216,31 @@ int soccer_rollout_table(const soccer_pitch *pitch, const uint16_t *table, uint3
  * to observation 0 in the INDEX layout and cannot be converted back */
 int soccer_convert_state(const soccer_pitch *pitch, const uint32_t *in, uint32_t *out,
                          int32_t to_layout, int64_t n, soccer_stream_t stream);
+
+/* ---- step() with HOST buffers (the end-to-end path) ----
+ * Uploads the joint actions / draws, steps, downloads the results, software-pipelined over
+ * n_chunks slices of the batch on three caller-supplied streams (upload of slice c+1, kernel of
+ * slice c and download of slice c-1 overlap; PCIe is full duplex).  Host pointers should be
+ * pinned (page-locked); pageable memory works but serialises.  The call only ENQUEUES: results
+ * are valid once s_out has been synchronised.  slip_prob must be 0 here.
+ *   narrow = 0: h_obs int32[n], h_reward float32[n]      (9 bytes per env come back)
+ *   narrow = 1: h_obs uint16[n], h_reward int8[n]        (4 bytes per env come back; same values)
+ * scratch: device memory, soccer_step_host_scratch_bytes_host(n) bytes, 256-byte aligned. */
+typedef struct soccer_step_host_args {
+    uint32_t       *state;      /* device [n]; INDEX layout iff table != NULL, else CELL layout */
+    const uint16_t *table;      /* device step table (soccer_build_step_table) or NULL: rules kernel */
+    void           *scratch;    /* device */
+    const uint8_t  *h_act_a, *h_act_b, *h_rng8;   /* host [n] */
+    void           *h_obs;      /* host [n] */
+    void           *h_reward;   /* host [n] */
+    uint8_t        *h_flags;    /* host [n] */
+    int64_t         n;
+    int32_t         narrow;
+    int32_t         n_chunks;   /* >= 1 */
+    soccer_stream_t s_in, s_compute, s_out;
+} soccer_step_host_args;
+int soccer_step_host_scratch_bytes_host(int64_t n, int64_t *bytes);
+int soccer_step_host(const soccer_pitch *pitch, const soccer_step_host_args *args);
 
 /* Dense Pmat / Rmat (SIM:170-171, 258-279), fp64, accumulated in the reference's order.
  * Multi-agent: Pmat[nS][nS][5][5], Rmat[nS][5][5]; with a folded policy: Pmat[nS][nS][5],

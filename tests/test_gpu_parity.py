@@ -170,6 +170,49 @@ def test_step_empty_batch(dev):
     torch.cuda.synchronize()
 
 
+@pytest.mark.parametrize("kernel", ["table", "rules"])
+@pytest.mark.parametrize("n,chunks", [(1000, 1), (4099, 3), (70001, 8)])
+def test_step_host_equals_device_path(dev, kernel, n, chunks):
+    """The host-buffer C entry point (pipelined chunks, wide and narrow downloads) returns exactly
+    what the device-resident step returns, step after step (state carried across calls)."""
+    from gym_soccer_littman94_b200.envs import SoccerVecEnv
+    rs = np.random.RandomState(n)
+    ref = SoccerVecEnv(n, device=dev, kernel=kernel)
+    envs = {nr: SoccerVecEnv(n, device=dev, kernel=kernel) for nr in (False, True)}
+    init = rs.randint(0, 16, n).astype(np.uint8)
+    for e in [ref] + list(envs.values()):
+        e.reset(_t(init, dev))
+    for t in range(60):
+        a, b, r = (rs.randint(0, hi, n).astype(np.uint8) for hi in (5, 5, 16))
+        obs, rew, flg, _ = ref.step(_t(a, dev), _t(b, dev), _t(r, dev))
+        ha, hb, hr = (torch.from_numpy(x).pin_memory() for x in (a, b, r))
+        for nr, e in envs.items():
+            ho, hw, hf = e.step_host(ha, hb, hr, narrow=nr, n_chunks=chunks)
+            ho = ho.numpy().view(np.uint16) if nr else ho.numpy()
+            assert np.array_equal(ho.astype(np.int32), obs.cpu().numpy()), (t, nr)
+            assert np.array_equal(hw.numpy().astype(np.float32), rew.cpu().numpy())
+            assert np.array_equal(hf.numpy(), flg.cpu().numpy())
+    for e in envs.values():
+        assert torch.equal(e.state, ref.state)
+
+
+@pytest.mark.parametrize("n,off", [(0, 0), (5, 0), (4096, 0), (100003, 0), (70000, 3)])
+def test_step_stats_kernel(dev, n, off):
+    """soccer_step_stats == the same counts taken with numpy (vector path, tail, misaligned)."""
+    from gym_soccer_littman94_b200.envs import SoccerVecEnv
+    env = SoccerVecEnv(8, device=dev, kernel="rules")
+    rs = np.random.RandomState(n + off)
+    f = rs.choice([0, 0, 0, 1, 2, 3], size=n + off).astype(np.uint8)
+    r = np.where(f & 1, rs.choice([-1.0, 1.0], size=n + off), 0.0).astype(np.float32)
+    st = torch.zeros(6, dtype=torch.int64, device=dev)
+    st[5] = 77
+    for _ in range(2):
+        env.step_stats(flags=_t(f, dev)[off:], reward=_t(r, dev)[off:], stats=st)
+    f, r = f[off:], r[off:]
+    want = 2 * np.array([(f != 0).sum(), (r > 0).sum(), (r < 0).sum(), (f == 2).sum(), n, 0]) + [0, 0, 0, 0, 0, 77]
+    assert np.array_equal(st.cpu().numpy(), want)
+
+
 @pytest.mark.parametrize("kernel", ["rules", "table"])
 def test_config2_4096_envs_vs_oracle(dev, oracle, kernel):
     """BASELINE config 2: 4096 lock-step envs, host-supplied joint actions, injected draws,
