@@ -937,6 +937,23 @@ int soccer_step_stats(const uint8_t* flags, const float* reward, int64_t n, unsi
     return launch_status();
 }
 
+int soccer_step_many(const soccer_pitch* pitch, const uint16_t* table, uint32_t* state, int32_t T,
+                     const uint8_t* act_a, const uint8_t* act_b, const uint8_t* rng8, int32_t* obs, float* reward,
+                     uint8_t* flags, int32_t* reset_obs, int64_t n, soccer_stream_t stream)
+{
+    if (T < 0 || n < 0 || !state || !act_a || !act_b || !rng8 || !obs || !reward || !flags) return SOCCER_EINVAL;
+    for (int32_t t = 0; t < T; ++t) {
+        const int64_t o = (int64_t)t * n;
+        const int rc = table
+            ? soccer_step_table(pitch, table, state, act_a + o, act_b + o, rng8 + o, obs + o, reward + o, flags + o,
+                                reset_obs ? reset_obs + o : nullptr, n, stream)
+            : soccer_step(pitch, state, act_a + o, act_b + o, rng8 + o, obs + o, reward + o, flags + o,
+                          reset_obs ? reset_obs + o : nullptr, n, stream);
+        if (rc) return rc;
+    }
+    return SOCCER_OK;
+}
+
 int soccer_step_host_scratch_bytes_host(int64_t n, int64_t* bytes)
 {
     if (!bytes || n < 0) return SOCCER_EINVAL;

@@ -78,7 +78,11 @@ class SoccerVecEnv:
         table_ok = self.slip_prob == 0.0 and self.multiagent and (self.nS - 1) <= 1023
         if kernel == "table" and not table_ok:
             raise _lib.SoccerB200Error("kernel='table' needs slip_prob == 0, no folded policy and nS <= 1024")
-        self.kernel = "table" if (kernel in ("auto", "table") and table_ok) else "rules"
+        # "auto": the table kernel pays a 152 KB shared-memory fill per CTA per launch, which only
+        # amortises over large batches; small batches are launch-latency bound either way
+        if kernel == "auto":
+            kernel = "table" if (table_ok and self.num_envs >= 65536) else "rules"
+        self.kernel = kernel
         self.layout = LAYOUT_INDEX if self.kernel == "table" else LAYOUT_CELL
 
         n, dev = self.num_envs, self.device
@@ -212,6 +216,28 @@ class SoccerVecEnv:
                 a.seed, a.step, a.env_id_base = self.seed, self.step_count, self.env_id_base
                 check(self.lib.soccer_step_ex(C.byref(self.pitch), C.byref(a), st), "soccer_step_ex")
         self.step_count += 1
+        return obs, reward, flags, reset_obs
+
+    def step_many(self, act_a: torch.Tensor, act_b: torch.Tensor, rng8: torch.Tensor, out=None):
+        """T lock-steps from [T, N] uint8 CUDA tensors, enqueued by one C call (no per-step Python
+        round trip; capturable into a CUDA graph).  Returns [T, N] obs / reward / flags / reset_obs."""
+        if self.slip_prob != 0.0 or not self.multiagent or self.rng_mode != "injected":
+            raise NotImplementedError("step_many covers the multi-agent, slip_prob == 0, injected-draw step")
+        T, n, dev = act_a.shape[0], self.num_envs, self.device
+        for name, t in (("act_a", act_a), ("act_b", act_b), ("rng8", rng8)):
+            if not (t.is_cuda and t.dtype == torch.uint8 and t.is_contiguous() and tuple(t.shape) == (T, n)):
+                raise ValueError(f"{name} must be a contiguous uint8 CUDA tensor of shape ({T}, {n})")
+        if out is None:
+            out = (torch.empty((T, n), dtype=torch.int32, device=dev), torch.empty((T, n), dtype=torch.float32, device=dev),
+                   torch.empty((T, n), dtype=torch.uint8, device=dev),
+                   torch.empty((T, n), dtype=torch.int32, device=dev) if self.want_reset_obs else None)
+        obs, reward, flags, reset_obs = out
+        if n and T:
+            with torch.cuda.device(dev):
+                check(self.lib.soccer_step_many(C.byref(self.pitch), _ptr(self.table), _ptr(self.state), T, _ptr(act_a),
+                                                _ptr(act_b), _ptr(rng8), _ptr(obs), _ptr(reward), _ptr(flags),
+                                                _ptr(reset_obs), n, _stream(dev)), "soccer_step_many")
+        self.step_count += T
         return obs, reward, flags, reset_obs
 
     def step_stats(self, flags: Optional[torch.Tensor] = None, reward: Optional[torch.Tensor] = None,

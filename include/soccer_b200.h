@@ -217,6 +217,15 @@ int soccer_rollout_table(const soccer_pitch *pitch, const uint16_t *table, uint3
 int soccer_convert_state(const soccer_pitch *pitch, const uint32_t *in, uint32_t *out,
                          int32_t to_layout, int64_t n, soccer_stream_t stream);
 
+/* T consecutive lock-steps from [T][n] action / draw arrays into [T][n] output arrays, enqueued
+ * by ONE call (T kernel launches back to back: no per-step host round trip; the whole call can be
+ * captured into a CUDA graph).  table == NULL -> rules kernel on CELL-layout states, else the table
+ * kernel on INDEX-layout states.  slip_prob must be 0.  reset_obs optional. */
+int soccer_step_many(const soccer_pitch *pitch, const uint16_t *table, uint32_t *state, int32_t T,
+                     const uint8_t *act_a, const uint8_t *act_b, const uint8_t *rng8, int32_t *obs,
+                     float *reward, uint8_t *flags, int32_t *reset_obs, int64_t n,
+                     soccer_stream_t stream);
+
 /* ---- step() with HOST buffers (the end-to-end path) ----
  * Uploads the joint actions / draws, steps, downloads the results, software-pipelined over
  * n_chunks slices of the batch on three caller-supplied streams (upload of slice c+1, kernel of

@@ -239,8 +239,11 @@ def test_config2_4096_envs_vs_oracle(dev, oracle, kernel):
         rew = torch.empty((CH, N), dtype=torch.float32, device=dev)
         flg = torch.empty((CH, N), dtype=torch.uint8, device=dev)
         rob = torch.empty((CH, N), dtype=torch.int32, device=dev)
-        for t in range(CH):
-            env.step(da[t], db[t], dr[t], out=(obs[t], rew[t], flg[t], rob[t]))
+        if c % 2 == 0:                      # alternate the per-step entry point and the T-step one
+            for t in range(CH):
+                env.step(da[t], db[t], dr[t], out=(obs[t], rew[t], flg[t], rob[t]))
+        else:
+            env.step_many(da, db, dr, out=(obs, rew, flg, rob))
         assert np.array_equal(obs.cpu().numpy(), eo), f"obs mismatch in chunk {c}"
         assert np.array_equal(rew.cpu().numpy(), er)
         assert np.array_equal(flg.cpu().numpy(), ef)
