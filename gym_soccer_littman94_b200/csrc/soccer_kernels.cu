@@ -10,7 +10,9 @@
 // so no tensor-core path.  SIM = /root/reference/gym_soccer/envs/soccer_simultaneous_env.py.
 #include "../../include/soccer_b200.h"
 #include "soccer_rules.cuh"
+#include "soccer_rules4.cuh"
 #include "soccer_table.cuh"
+#include "soccer_rollout.cuh"
 
 #include <cuda_runtime.h>
 
@@ -107,7 +109,9 @@ int make_pitch_dev(const soccer_pitch* p, PitchDev* d)
     d->obs_d1 = d->isd_obs[1] - d->isd_obs[0];
     d->obs_d2 = d->isd_obs[2] - d->isd_obs[0];
     if (d->isd_state[3] != d->isd_state[0] + d->isd_d1 + d->isd_d2 ||
-        d->isd_obs[3] != d->isd_obs[0] + d->obs_d1 + d->obs_d2)
+        d->isd_obs[3] != d->isd_obs[0] + d->obs_d1 + d->obs_d2 ||
+        d->isd_state[3] != (d->isd_state[0] ^ d->isd_state[1] ^ d->isd_state[2]) ||     // bytewise XOR form (rules4)
+        d->obs_d1 < 0 || d->obs_d2 < 0 || d->isd_obs[3] > 0xFFFF)
         return SOCCER_EPITCH;   // cannot happen for the reference's start distributions
     for (int c = 0; c < 9; ++c) d->mp[c] = info.slip_combo_prob[c];
     d->slip = p->slip_prob != 0.0;
@@ -136,24 +140,17 @@ inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_
 
 
 template <bool RESET_OBS>
-__device__ __forceinline__ void step_group(const PitchDev& P, const uint8_t* lut, const Group4& x, int64_t g,
-                                           uint4* st, uint4* obs, uint4* rew, uint32_t* flg, uint4* rob)
+__device__ __forceinline__ void step_group(const PitchDev& P, const Isd4& I, const uint8_t* lut, const Group4& x,
+                                           int64_t g, uint4* st, uint4* obs, uint4* rew, uint32_t* flg, uint4* rob)
 {
     const uint32_t sv[4] = { x.s.x, x.s.y, x.s.z, x.s.w };
-    uint32_t so[4], oo[4], ro[4], rr[4], ff = 0;
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        const uint32_t aa = (x.a >> (8 * e)) & 0xFFu, ab = (x.b >> (8 * e)) & 0xFFu, rg = (x.r >> (8 * e)) & 0xFFu;
-        const StepOut o = step_noslip<true, false>(P, lut, sv[e], aa, ab, rg, false);
-        so[e] = o.state; oo[e] = (uint32_t)o.obs; rr[e] = __float_as_uint(o.reward);
-        ro[e] = (uint32_t)o.reset_obs;
-        ff |= o.flags << (8 * e);
-    }
-    st_keep(st + g, make_uint4(so[0], so[1], so[2], so[3]));
-    st_stream(obs + g, make_uint4(oo[0], oo[1], oo[2], oo[3]));
-    st_stream(rew + g, make_uint4(rr[0], rr[1], rr[2], rr[3]));
-    st_stream(flg + g, ff);
-    if (RESET_OBS) st_stream(rob + g, make_uint4(ro[0], ro[1], ro[2], ro[3]));
+    Step4 o;
+    step4_noslip<RESET_OBS>(P, I, lut, sv, x.a, x.b, x.r, o);     // byte-parallel over the 4 envs
+    st_keep(st + g, make_uint4(o.s[0], o.s[1], o.s[2], o.s[3]));
+    st_stream(obs + g, make_uint4(o.obs[0], o.obs[1], o.obs[2], o.obs[3]));
+    st_stream(rew + g, make_uint4(o.rew[0], o.rew[1], o.rew[2], o.rew[3]));
+    st_stream(flg + g, o.flags4);
+    if (RESET_OBS) st_stream(rob + g, make_uint4(o.robs[0], o.robs[1], o.robs[2], o.robs[3]));
 }
 
 template <bool RESET_OBS>
@@ -165,6 +162,7 @@ k_step_fast(const PitchDev P, uint32_t* __restrict__ state, const uint8_t* __res
 {
     __shared__ __align__(16) uint8_t lut[kLutBytes];
     build_cand_lut(lut, P);
+    const Isd4 I = make_isd4(P);
 
     uint4* st4 = reinterpret_cast<uint4*>(state);
     const uint32_t* a4 = reinterpret_cast<const uint32_t*>(act_a);
@@ -182,8 +180,8 @@ k_step_fast(const PitchDev P, uint32_t* __restrict__ state, const uint8_t* __res
         const Group4 x0 = load_group(st4, a4, b4, r4, g);
         Group4 x1 = x0;
         if (two) x1 = load_group(st4, a4, b4, r4, g2);
-        step_group<RESET_OBS>(P, lut, x0, g, st4, o4, w4, f4, q4);
-        if (two) step_group<RESET_OBS>(P, lut, x1, g2, st4, o4, w4, f4, q4);
+        step_group<RESET_OBS>(P, I, lut, x0, g, st4, o4, w4, f4, q4);
+        if (two) step_group<RESET_OBS>(P, I, lut, x1, g2, st4, o4, w4, f4, q4);
     }
 }
 
@@ -250,95 +248,6 @@ __global__ void __launch_bounds__(kThreads) k_step_generic(const PitchDev P, con
         if (o.reward) o.reward[i] = r.reward;
         if (o.flags) o.flags[i] = (uint8_t)(o.detail ? r.flags : (r.flags & 3u));
         if (o.reset_obs) o.reset_obs[i] = r.reset_obs;
-    }
-}
-
-// ------------------------------------------------------------------ K2 fused rollout
-// Each thread owns VEC envs for all K steps; state, timestep and the current Philox block stay
-// in registers; only the obs / reward / flags streams ([K][n]) are written, as 128-bit / 32-bit
-// stores when VEC == 4.  Episode statistics: registers -> warp reduce -> smem -> 6 atomics/CTA.
-template <int VEC>
-__global__ void __launch_bounds__(kThreads)
-k_rollout(const PitchDev P, uint32_t* __restrict__ state, const int8_t* __restrict__ policy_a,
-          const int8_t* __restrict__ policy_b, uint64_t seed, uint64_t step0, int32_t K,
-          uint64_t env_id_base, int32_t* __restrict__ obs, float* __restrict__ reward,
-          uint8_t* __restrict__ flags, unsigned long long* __restrict__ stats, int64_t n)
-{
-    __shared__ __align__(16) uint8_t lut[kLutBytes];
-    __shared__ unsigned int blk_stats[6];
-    build_cand_lut(lut, P);
-    if (threadIdx.x < 6) blk_stats[threadIdx.x] = 0;
-    __syncthreads();
-
-    uint32_t c_ep = 0, c_ga = 0, c_gb = 0, c_tr = 0, c_len = 0, c_steps = 0;
-    const int64_t n_groups = n / VEC;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_groups; g += stride) {
-        const int64_t i0 = g * VEC;
-        uint32_t s[VEC], w[VEC][4];
-        if (VEC == 4) {
-            const uint4 v = reinterpret_cast<const uint4*>(state)[g];
-            s[0] = v.x; s[1 % VEC] = v.y; s[2 % VEC] = v.z; s[3 % VEC] = v.w;
-        } else {
-            s[0] = state[i0];
-        }
-        for (int32_t k = 0; k < K; ++k) {
-            const uint64_t step = step0 + (uint64_t)k;
-            const uint32_t wi = (uint32_t)step & 3u;
-            if (k == 0 || wi == 0) {
-                const uint64_t blk = step >> 2;
-#pragma unroll
-                for (int e = 0; e < VEC; ++e) {
-                    const uint64_t env = env_id_base + (uint64_t)(i0 + e);
-                    philox4x32_10((uint32_t)env, (uint32_t)(env >> 32), (uint32_t)blk, (uint32_t)(blk >> 32),
-                                  (uint32_t)seed, (uint32_t)(seed >> 32), w[e]);
-                }
-            }
-            uint32_t oo[VEC], rr[VEC], ff = 0;
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) {
-                const uint32_t word = wi == 0 ? w[e][0] : (wi == 1 ? w[e][1] : (wi == 2 ? w[e][2] : w[e][3]));
-                uint32_t aa, ab;
-                philox_actions(word, aa, ab);
-                if (policy_a || policy_b) {
-                    const uint32_t a = s[e] & 0xFFu, b = (s[e] >> 8) & 0xFFu, p = (s[e] >> 24) & 1u;
-                    const int32_t cur = obs_index(P, a, b, p);
-                    if (policy_a) aa = (uint32_t)policy_a[cur];
-                    if (policy_b) ab = (uint32_t)policy_b[cur];
-                }
-                const uint32_t t_before = (s[e] >> 16) & 0xFFu;
-                const StepOut o = step_noslip<true, false>(P, lut, s[e], aa, ab, philox_rng8(word), false);
-                s[e] = o.state;
-                oo[e] = (uint32_t)o.obs; rr[e] = __float_as_uint(o.reward); ff |= (o.flags & 0xFFu) << (8 * e);
-                const bool done = o.flags & 1u, ended = (o.flags & 3u) != 0;
-                c_ep += ended; c_len += ended ? t_before + 1u : 0u;
-                c_ga += done && o.reward > 0.0f; c_gb += done && o.reward < 0.0f; c_tr += ended && !done;
-            }
-            c_steps += VEC;
-            const int64_t off = (int64_t)k * n;
-            if (VEC == 4) {
-                if (obs) st_stream(reinterpret_cast<uint4*>(obs + off) + g, make_uint4(oo[0], oo[1 % VEC], oo[2 % VEC], oo[3 % VEC]));
-                if (reward) st_stream(reinterpret_cast<uint4*>(reward + off) + g, make_uint4(rr[0], rr[1 % VEC], rr[2 % VEC], rr[3 % VEC]));
-                if (flags) st_stream(reinterpret_cast<uint32_t*>(flags + off) + g, ff);
-            } else {
-                if (obs) obs[off + i0] = (int32_t)oo[0];
-                if (reward) reward[off + i0] = __uint_as_float(rr[0]);
-                if (flags) flags[off + i0] = (uint8_t)ff;
-            }
-        }
-        if (VEC == 4) reinterpret_cast<uint4*>(state)[g] = make_uint4(s[0], s[1 % VEC], s[2 % VEC], s[3 % VEC]);
-        else state[i0] = s[0];
-    }
-    if (stats) {
-        uint32_t v[6] = { c_ep, c_ga, c_gb, c_tr, c_steps, c_len };
-#pragma unroll
-        for (int j = 0; j < 6; ++j) {
-            const uint32_t r = __reduce_add_sync(0xFFFFFFFFu, v[j]);
-            if ((threadIdx.x & 31) == 0 && r) atomicAdd(&blk_stats[j], r);
-        }
-        __syncthreads();
-        if (threadIdx.x < 6 && blk_stats[threadIdx.x])
-            atomicAdd(&stats[threadIdx.x], (unsigned long long)blk_stats[threadIdx.x]);
     }
 }
 
