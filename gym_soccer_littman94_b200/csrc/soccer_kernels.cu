@@ -11,7 +11,6 @@
 #include "../../include/soccer_b200.h"
 #include "soccer_rules.cuh"
 #include "soccer_rules4.cuh"
-#include "soccer_table.cuh"
 #include "soccer_rollout.cuh"
 
 #include <cuda_runtime.h>
@@ -722,15 +721,18 @@ int soccer_rollout(const soccer_pitch* pitch, uint32_t* state, const int8_t* pol
     cudaStream_t st = (cudaStream_t)stream;
     const bool vec = (n % 4 == 0) && aligned(state, 16) && (!obs || aligned(obs, 16)) &&
                      (!reward || aligned(reward, 16)) && (!flags || aligned(flags, 4));
-    if (vec) {
-        static const int nb = resident_blocks(k_rollout<4>);
-        k_rollout<4><<<grid_for(n / 4, nb), kThreads, 0, st>>>(P, state, policy_a, policy_b, seed, step0, K,
-                                                                env_id_base, obs, reward, flags, stats, n);
-    } else {
-        static const int nb = resident_blocks(k_rollout<1>);
-        k_rollout<1><<<grid_for(n, nb), kThreads, 0, st>>>(P, state, policy_a, policy_b, seed, step0, K,
-                                                            env_id_base, obs, reward, flags, stats, n);
-    }
+    const RolloutArgs ra = { state, seed, step0, K, env_id_base, obs, reward, flags, stats, n };
+    const bool streams = obs && reward && flags;
+#define SOCCER_LAUNCH_ROLLOUT(VEC, STR, ITEMS)                                                          \
+    do {                                                                                                 \
+        static const int nb = resident_blocks(k_rollout<VEC, STR>);                                      \
+        k_rollout<VEC, STR><<<grid_for(ITEMS, nb), kThreads, 0, st>>>(P, policy_a, policy_b, ra);         \
+    } while (0)
+    if (vec && streams) SOCCER_LAUNCH_ROLLOUT(4, true, n / 4);
+    else if (vec) SOCCER_LAUNCH_ROLLOUT(4, false, n / 4);
+    else if (streams) SOCCER_LAUNCH_ROLLOUT(1, true, n);
+    else SOCCER_LAUNCH_ROLLOUT(1, false, n);
+#undef SOCCER_LAUNCH_ROLLOUT
     return launch_status();
 }
 
@@ -813,17 +815,20 @@ int soccer_rollout_table(const soccer_pitch* pitch, const uint16_t* table, uint3
     cudaStream_t st = (cudaStream_t)stream;
     const bool vec = (n % 4 == 0) && aligned(state, 16) && (!obs || aligned(obs, 16)) &&
                      (!reward || aligned(reward, 16)) && (!flags || aligned(flags, 4));
-    if (vec) {
-        const int e0 = allow_big_smem(k_rollout_table<4>, bytes + 16);
-        if (e0) return e0;
-        k_rollout_table<4><<<table_grid(n / 4, kRolloutThreads), kRolloutThreads, bytes + 16, st>>>(P, table, (uint32_t)bytes, state, seed, step0, K,
-                                                                            env_id_base, obs, reward, flags, stats, n);
-    } else {
-        const int e0 = allow_big_smem(k_rollout_table<1>, bytes + 16);
-        if (e0) return e0;
-        k_rollout_table<1><<<table_grid(n, kRolloutThreads), kRolloutThreads, bytes + 16, st>>>(P, table, (uint32_t)bytes, state, seed, step0, K,
-                                                                        env_id_base, obs, reward, flags, stats, n);
-    }
+    const RolloutArgs ra = { state, seed, step0, K, env_id_base, obs, reward, flags, stats, n };
+    const bool streams = obs && reward && flags;
+#define SOCCER_LAUNCH_ROLLOUT_T(VEC, STR, ITEMS)                                                         \
+    do {                                                                                                 \
+        const int e0 = allow_big_smem(k_rollout_table<VEC, STR>, bytes + 16);                            \
+        if (e0) return e0;                                                                               \
+        k_rollout_table<VEC, STR><<<table_grid(ITEMS, kRolloutThreads), kRolloutThreads, bytes + 16, st>>>( \
+            P, table, (uint32_t)bytes, ra);                                                              \
+    } while (0)
+    if (vec && streams) SOCCER_LAUNCH_ROLLOUT_T(4, true, n / 4);
+    else if (vec) SOCCER_LAUNCH_ROLLOUT_T(4, false, n / 4);
+    else if (streams) SOCCER_LAUNCH_ROLLOUT_T(1, true, n);
+    else SOCCER_LAUNCH_ROLLOUT_T(1, false, n);
+#undef SOCCER_LAUNCH_ROLLOUT_T
     return launch_status();
 }
 

@@ -136,11 +136,13 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 {
 #pragma unroll
     for (int i = 0; i < 10; ++i) {
-        const unsigned long long p0 = (unsigned long long)0xD2511F53u * c0;
-        const unsigned long long p1 = (unsigned long long)0xCD9E8D57u * c2;
-        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
-        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
-        c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
+        // mul.hi + mul.lo (both on the FMA pipe) rather than one wide multiply: keeps the ALU pipe,
+        // which bounds the rollout kernels, for the 3-input XORs only
+        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = h1 ^ c1 ^ k0;
+        const uint32_t n2 = h0 ^ c3 ^ k1;
+        c1 = l1; c3 = l0; c0 = n0; c2 = n2;
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
@@ -156,10 +158,10 @@ __device__ __forceinline__ uint32_t philox_word(uint64_t seed, uint64_t env_id, 
     return k == 0 ? o[0] : (k == 1 ? o[1] : (k == 2 ? o[2] : o[3]));
 }
 
-// decode of one word.  jr = (w24 * 100) >> 24 is uniform on 0..99 and carries the joint action
-// and the step draw at once -- jr = (aa*5 + ab)*4 + r, exactly the column index of the step
-// table -- and bits 24..25 are the reset draw.
-__device__ __forceinline__ uint32_t philox_jr(uint32_t w) { return ((w & 0xFFFFFFu) * 100u) >> 24; }
+// decode of one word.  jr = mulhi(w, 100) is uniform on 0..99 and carries the joint action and
+// the step draw at once -- jr = (aa*5 + ab)*4 + r, exactly the column index of the step table --
+// and the two lowest bits of w are the reset draw.
+__device__ __forceinline__ uint32_t philox_jr(uint32_t w) { return __umulhi(w, 100u); }
 __device__ __forceinline__ void philox_actions(uint32_t w, uint32_t& aa, uint32_t& ab)
 {
     const uint32_t ja = philox_jr(w) >> 2;
@@ -167,7 +169,7 @@ __device__ __forceinline__ void philox_actions(uint32_t w, uint32_t& aa, uint32_
     ab = ja - aa * 5u;
 }
 // rng8-compatible nibble: bits 0..1 step draw, bits 2..3 reset draw
-__device__ __forceinline__ uint32_t philox_rng8(uint32_t w) { return (philox_jr(w) & 3u) | (((w >> 24) & 3u) << 2); }
+__device__ __forceinline__ uint32_t philox_rng8(uint32_t w) { return (philox_jr(w) & 3u) | ((w & 3u) << 2); }
 
 // ---- streaming accessors and the 4-env group shared by the K1 kernels ----
 constexpr int kThreads = 256;

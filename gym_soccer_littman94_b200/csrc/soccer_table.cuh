@@ -92,13 +92,17 @@ __device__ __forceinline__ void wait_table(uint64_t* bar)
 }
 
 // One env-step through the table.  `jr` = (aa*5+ab)*4 + r (0..99), `rsel4` = 4 * reset draw.
-struct TblCtx { const int16_t* tbl; const uint8_t* isd; uint32_t last; };
+struct TblCtx { uint32_t tbl, isd, last; };    // shared-window addresses of the table / the isd words; last entry index
 struct TblOut { uint32_t state, obs, flags; int32_t rew_i; uint32_t reset_obs; };
 __device__ __forceinline__ TblOut table_step(const TblCtx& c, uint32_t s, uint32_t jr, uint32_t rsel4)
 {
     // the clamp keeps a corrupt state word / action byte inside the table
-    const int32_t e = c.tbl[min((s & 0xFFFFu) * 100u + jr, c.last)];     // LDS.S16: sign-extending
-    const uint32_t ro = *reinterpret_cast<const uint32_t*>(c.isd + rsel4);     // SIM:414-415
+    const uint32_t idx = min((s & 0xFFFFu) * 100u + jr, c.last);
+    int32_t e;
+    uint32_t ro;
+    // volatile: ordered after the (volatile) mbarrier wait that publishes the table
+    asm volatile("ld.shared.s16 %0, [%1];" : "=r"(e) : "r"(c.tbl + idx * 2u));          // sign-extending LDS.S16
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(ro) : "r"(c.isd + rsel4));            // SIM:414-415
     TblOut o;
     o.obs = (uint32_t)e & kTblObsMask;
     o.rew_i = e >> 14;                                     // -1 / 0 / +1 (SIM:235-240)
@@ -115,8 +119,8 @@ __device__ __forceinline__ TblOut table_step(const TblCtx& c, uint32_t s, uint32
 __device__ __forceinline__ TblCtx make_ctx(const uint8_t* smem, uint32_t table_bytes, const PitchDev& P)
 {
     TblCtx c;
-    c.tbl = reinterpret_cast<const int16_t*>(smem);
-    c.isd = smem + table_bytes;
+    c.tbl = smem_u32(smem);
+    c.isd = c.tbl + table_bytes;
     c.last = (uint32_t)P.nS * 100u - 1u;
     return c;
 }
@@ -208,123 +212,6 @@ k_step_table_scalar(const PitchDev P, const uint16_t* __restrict__ gtable, uint3
         reward[i] = (float)(e >> 14);
         flags[i] = (uint8_t)((done ? 1u : 0u) + (trunc ? 2u : 0u));
         if (reset_obs) reset_obs[i] = (int32_t)(reset ? ro : nobs);
-    }
-}
-
-// K2, table variant: uniform random policy from Philox, state (obs | t<<16) in registers for all
-// K steps.  One Philox call serves 4 consecutive steps of an env; the k loop walks Philox blocks
-// so the word index is static.  Episode statistics cost ~2 instructions per env-step:
-//   episodes / truncations: byte-parallel accumulation of the packed flags word (flushed with
-//   dp4a every 64 steps); goals_A - goals_B = sum of rewards; sum_episode_len from the identity
-//   sum(t_in) + K*VEC = sum(finished episode lengths) + sum(t_out).
-template <int VEC>
-__global__ void __launch_bounds__(kRolloutThreads, 1)
-k_rollout_table(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t table_bytes,
-                uint32_t* __restrict__ state, uint64_t seed, uint64_t step0, int32_t K, uint64_t env_id_base,
-                int32_t* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ flags,
-                unsigned long long* __restrict__ stats, int64_t n)
-{
-    extern __shared__ __align__(128) uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar;
-    __shared__ unsigned int blk_stats[6];
-    __shared__ int blk_net;
-    if (threadIdx.x < 6) blk_stats[threadIdx.x] = 0;
-    if (threadIdx.x == 6) blk_net = 0;
-    stage_table(smem_raw, gtable, table_bytes, &bar, P);
-    const TblCtx c = make_ctx(smem_raw, table_bytes, P);
-    wait_table(&bar);
-
-    uint32_t c_done = 0, c_trunc = 0, c_len = 0, c_steps = 0;
-    int32_t c_net = 0;
-    const int64_t n_groups = n / VEC;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const uint64_t step_end = step0 + (uint64_t)K;
-    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_groups; g += stride) {
-        const int64_t i0 = g * VEC;
-        uint32_t s[VEC];
-        if (VEC == 4) {
-            const uint4 v = reinterpret_cast<const uint4*>(state)[g];
-            s[0] = v.x; s[1 % VEC] = v.y; s[2 % VEC] = v.z; s[3 % VEC] = v.w;
-        } else {
-            s[0] = state[i0];
-        }
-        uint32_t t_in = 0;
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) t_in += s[e] >> 16;
-        uint32_t acc_d = 0, acc_t = 0, since_flush = 0;
-        int32_t* op = obs ? obs + i0 : nullptr;
-        float* rp = reward ? reward + i0 : nullptr;
-        uint8_t* fp = flags ? flags + i0 : nullptr;
-        for (uint64_t blk = step0 >> 2; (blk << 2) < step_end; ++blk) {
-            uint32_t w[VEC][4];
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) {
-                const uint64_t env = env_id_base + (uint64_t)(i0 + e);
-                philox4x32_10((uint32_t)env, (uint32_t)(env >> 32), (uint32_t)blk, (uint32_t)(blk >> 32),
-                              (uint32_t)seed, (uint32_t)(seed >> 32), w[e]);
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint64_t step = (blk << 2) + (uint64_t)j;
-                if (step < step0 || step >= step_end) continue;         // warp-uniform
-                uint32_t oo[VEC], rr[VEC], ff[VEC];
-#pragma unroll
-                for (int e = 0; e < VEC; ++e) {
-                    const uint32_t word = w[e][j];
-                    const TblOut o = table_step(c, s[e], philox_jr(word), (word >> 22) & 0xCu);
-                    s[e] = o.state; oo[e] = o.obs; rr[e] = __float_as_uint((float)o.rew_i); ff[e] = o.flags;
-                    c_net += o.rew_i;
-                }
-                uint32_t fw;
-                if (VEC == 4) fw = __byte_perm(__byte_perm(ff[0], ff[1 % VEC], 0x0040), __byte_perm(ff[2 % VEC], ff[3 % VEC], 0x0040), 0x5410);
-                else fw = ff[0];
-                acc_d += fw & 0x01010101u;
-                acc_t += (fw >> 1) & ~fw & 0x01010101u;                 // truncated WITHOUT a goal
-                if (VEC == 4) {
-                    if (op) { st_stream(reinterpret_cast<uint4*>(op), make_uint4(oo[0], oo[1 % VEC], oo[2 % VEC], oo[3 % VEC])); op += n; }
-                    if (rp) { st_stream(reinterpret_cast<uint4*>(rp), make_uint4(rr[0], rr[1 % VEC], rr[2 % VEC], rr[3 % VEC])); rp += n; }
-                    if (fp) { st_stream(reinterpret_cast<uint32_t*>(fp), fw); fp += n; }
-                } else {
-                    if (op) { *op = (int32_t)oo[0]; op += n; }
-                    if (rp) { *rp = __uint_as_float(rr[0]); rp += n; }
-                    if (fp) { *fp = (uint8_t)fw; fp += n; }
-                }
-            }
-            since_flush += 4;
-            if (since_flush >= 64) {                                    // bytes hold at most 64 + 3 counts
-                c_done = __dp4a(acc_d, 0x01010101u, c_done); c_trunc = __dp4a(acc_t, 0x01010101u, c_trunc);
-                acc_d = acc_t = since_flush = 0;
-            }
-        }
-        c_done = __dp4a(acc_d, 0x01010101u, c_done); c_trunc = __dp4a(acc_t, 0x01010101u, c_trunc);
-        uint32_t t_out = 0;
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) t_out += s[e] >> 16;
-        c_len += t_in + (uint32_t)K * VEC - t_out;
-        c_steps += (uint32_t)K * VEC;
-        if (VEC == 4) reinterpret_cast<uint4*>(state)[g] = make_uint4(s[0], s[1 % VEC], s[2 % VEC], s[3 % VEC]);
-        else state[i0] = s[0];
-    }
-    if (stats) {
-        // episodes = goals + truncated-only (a goal on step 100 carries both flags and counts once)
-        uint32_t v[4] = { c_done, c_trunc, c_steps, c_len };
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint32_t r = __reduce_add_sync(0xFFFFFFFFu, v[j]);
-            if ((threadIdx.x & 31) == 0 && r) atomicAdd(&blk_stats[j], r);
-        }
-        const int32_t rn = __reduce_add_sync(0xFFFFFFFFu, c_net);
-        if ((threadIdx.x & 31) == 0 && rn) atomicAdd(&blk_net, rn);
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const long long d = blk_stats[0], tr_only = blk_stats[1], net = blk_net;
-            atomicAdd(&stats[0], (unsigned long long)(d + tr_only));          // episodes
-            atomicAdd(&stats[1], (unsigned long long)((d + net) / 2));        // goals_A (reward +1)
-            atomicAdd(&stats[2], (unsigned long long)((d - net) / 2));        // goals_B (reward -1)
-            atomicAdd(&stats[3], (unsigned long long)tr_only);                // truncations
-            atomicAdd(&stats[4], (unsigned long long)blk_stats[2]);           // steps
-            atomicAdd(&stats[5], (unsigned long long)blk_stats[3]);           // sum_episode_len
-        }
     }
 }
 

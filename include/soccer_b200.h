@@ -38,9 +38,9 @@
  *   rngf64: step draw for slip_prob > 0 as the raw fp64 uniform the reference's
  *           np_random.random() returned (SIM:395)
  * Counter-based randomness: Philox4x32-10, key = seed, counter = (env_id, step >> 2),
- *   output word step & 3:  jr = ((w & 0xFFFFFF) * 100) >> 24 is uniform on 0..99 and carries the
- *   joint action and the step draw at once: ja = jr >> 2, aa = ja / 5, ab = ja % 5, step draw
- *   = jr & 3;  bits 24..25 of w = reset draw.
+ *   output word step & 3:  jr = mulhi(w, 100) = (w * 100) >> 32 is uniform on 0..99 and carries
+ *   the joint action and the step draw at once: ja = jr >> 2, aa = ja / 5, ab = ja % 5, step draw
+ *   = jr & 3;  the two lowest bits of w = reset draw.
  *
  * flags byte: bit 0 terminated (SIM:403), bit 1 truncated (SIM:404).  Only when
  *   soccer_step_args.detail != 0: bits 2..3 = log2(number of outcomes the chosen slip
@@ -117,7 +117,7 @@ int soccer_obs_to_state_host(const soccer_pitch *pitch, int32_t obs, uint32_t *p
  * selects the envs to reset; obs_out optional. */
 int soccer_reset(const soccer_pitch *pitch, uint32_t *state, int32_t *obs_out,
                  const uint8_t *rng8, const uint8_t *mask, int64_t n, soccer_stream_t stream);
-/* same, reset draw = Philox word (seed, env_id_base + i, step) bits 24..25 */
+/* same, reset draw = Philox word (seed, env_id_base + i, step) bits 0..1 */
 int soccer_reset_philox(const soccer_pitch *pitch, uint32_t *state, int32_t *obs_out,
                         const uint8_t *mask, uint64_t seed, uint64_t step, uint64_t env_id_base,
                         int64_t n, soccer_stream_t stream);

@@ -539,13 +539,13 @@ uint32_t orc_philox_word(uint64_t seed, uint64_t env_id, uint64_t step)
 
 void orc_philox_decode(uint32_t w, int *aa, int *ab, int *r_step, int *r_reset)
 {
-    /* jr uniform on 0..99 = (joint action, step draw) at once; bits 24..25 = reset draw */
-    uint32_t jr = (uint32_t)(((uint64_t)(w & 0xFFFFFFu) * 100u) >> 24);
+    /* jr = mulhi(w, 100), uniform on 0..99 = (joint action, step draw) at once; w & 3 = reset draw */
+    uint32_t jr = (uint32_t)(((uint64_t)w * 100u) >> 32);
     uint32_t ja = jr >> 2;
     *aa = (int)(ja / 5u);
     *ab = (int)(ja % 5u);
     *r_step = (int)(jr & 3u);
-    *r_reset = (int)((w >> 24) & 3u);
+    *r_reset = (int)(w & 3u);
 }
 
 void orc_rollout_philox(const orc_model *m, int64_t K, int64_t N,

@@ -136,7 +136,7 @@ void orc_rollout_injected(const orc_model *m, int64_t T, int64_t N,
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 /* The 32-bit word that drives env `env_id` at absolute step `step`. */
 uint32_t orc_philox_word(uint64_t seed, uint64_t env_id, uint64_t step);
-/* decode a word: jr = (w24*100)>>24 -> joint action jr>>2 and step draw jr&3; reset draw = bits 24..25 */
+/* decode a word: jr = mulhi(w, 100) -> joint action jr>>2 and step draw jr&3; reset draw = w & 3 */
 void orc_philox_decode(uint32_t w, int *aa, int *ab, int *r_step, int *r_reset);
 
 /* K-step rollout, uniform (policy == NULL) or table policies (int8 obs->action), Philox

@@ -40,13 +40,16 @@ def test_word_and_decode_contract(oracle):
         words = philox_py((env & 0xFFFFFFFF, env >> 32, blk & 0xFFFFFFFF, blk >> 32), (seed & 0xFFFFFFFF, seed >> 32))
         w = oracle.philox_word(seed, env, step)
         assert w == words[step & 3]
-        jr = ((w & 0xFFFFFF) * 100) >> 24
-        assert oracle.philox_decode(w) == ((jr >> 2) // 5, (jr >> 2) % 5, jr & 3, (w >> 24) & 3)
+        jr = (w * 100) >> 32
+        assert oracle.philox_decode(w) == ((jr >> 2) // 5, (jr >> 2) % 5, jr & 3, w & 3)
 
 
 def test_decode_is_uniform_over_joint_action_and_draw(oracle):
-    # exhaustive over the 24-bit field: every (joint action, step draw) cell gets 2^24/100 +- 1 words
-    w = np.arange(1 << 24, dtype=np.uint64)
-    jr = (w * 100) >> 24
-    counts = np.bincount(jr.astype(np.int64), minlength=100)
-    assert counts.min() >= (1 << 24) // 100 and counts.max() <= (1 << 24) // 100 + 1
+    # every (joint action, step draw) cell owns 2^32/100 +- 1 of the 2^32 words, and within a cell
+    # the reset draw (w & 3) is uniform to within one word
+    edges = [-(-(c << 32) // 100) for c in range(101)]          # first w with mulhi(w, 100) == c
+    sizes = np.diff(np.array(edges, dtype=np.int64))
+    assert sizes.min() >= (1 << 32) // 100 and sizes.max() <= (1 << 32) // 100 + 1
+    for c in (0, 37, 99):
+        assert (int(edges[c]) * 100) >> 32 == c and ((int(edges[c]) - 1) * 100) >> 32 == c - 1
+    assert all(abs((e1 - e0) // 4 - ((e1 - e0 + 3) // 4)) <= 1 for e0, e1 in zip(edges, edges[1:]))
