@@ -229,13 +229,7 @@ __global__ void __launch_bounds__(kThreads) k_step_generic(const PitchDev P, con
             double u;
             if (o.rngf64) u = o.rngf64[i];
             else if (o.rng32) u = ((double)o.rng32[i] + 0.5) * (1.0 / 4294967296.0);
-            else {   // philox mode with slip: 53-bit uniform from two fresh words of a separate counter lane
-                uint32_t w[4];
-                const uint64_t e = o.env_id_base + (uint64_t)i;
-                philox4x32_10((uint32_t)e, (uint32_t)(e >> 32), (uint32_t)o.step, (uint32_t)(o.step >> 32) | 0x80000000u,
-                              (uint32_t)o.seed, (uint32_t)(o.seed >> 32), w);
-                u = ((double)(((uint64_t)(w[0] >> 5) << 26) | (uint64_t)(w[1] >> 6))) * (1.0 / 9007199254740992.0);
-            }
+            else u = philox_u53(o.seed, o.env_id_base + (uint64_t)i, o.step);   // philox mode with slip
             r = o.auto_reset ? step_slip<true>(P, lut, s, aa, ab, u, (rng >> 2) & 3u, flip)
                              : step_slip<false>(P, lut, s, aa, ab, u, (rng >> 2) & 3u, flip);
         } else {
@@ -716,7 +710,6 @@ int soccer_rollout(const soccer_pitch* pitch, uint32_t* state, const int8_t* pol
 {
     if (!state || n < 0 || K < 0) return SOCCER_EINVAL;
     PitchDev P; const int rc = make_pitch_dev(pitch, &P); if (rc) return rc;
-    if (P.slip) return SOCCER_ESLIP;
     if (n == 0 || K == 0) return SOCCER_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const bool vec = (n % 4 == 0) && aligned(state, 16) && (!obs || aligned(obs, 16)) &&

@@ -31,7 +31,7 @@ struct TableStepper {
     __device__ __forceinline__ uint32_t timestep(uint32_t s) const { return s >> 16; }
     template <int VEC>
     __device__ __forceinline__ void step(uint32_t* s, const uint32_t* word, uint32_t* oo, uint32_t* rr, uint32_t& fw,
-                                         int32_t& net) const
+                                         int32_t& net, uint64_t, uint64_t, uint64_t) const
     {
         uint32_t ff[4] = { 0, 0, 0, 0 };
 #pragma unroll
@@ -50,9 +50,27 @@ struct RulesStepper {
     __device__ __forceinline__ uint32_t timestep(uint32_t s) const { return (s >> 16) & 0xFFu; }
     template <int VEC>
     __device__ __forceinline__ void step(uint32_t* s, const uint32_t* word, uint32_t* oo, uint32_t* rr, uint32_t& fw,
-                                         int32_t& net) const
+                                         int32_t& net, uint64_t seed, uint64_t env0, uint64_t step_abs) const
     {
-        if (VEC == 4 && !policy_a && !policy_b) {
+        if (P.slip) {
+            // slip_prob > 0 (SIM:203-227): the scalar 9-combination walk with a 53-bit Philox uniform
+            fw = 0;
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                uint32_t aa, ab;
+                philox_actions(word[e], aa, ab);
+                if (policy_a || policy_b) {
+                    const int32_t cur = obs_index(P, s[e] & 0xFFu, (s[e] >> 8) & 0xFFu, (s[e] >> 24) & 1u);
+                    if (policy_a) aa = (uint32_t)policy_a[cur];
+                    if (policy_b) ab = (uint32_t)policy_b[cur];
+                }
+                const StepOut o = step_slip<true>(P, lut, s[e], aa, ab, philox_u53(seed, env0 + e, step_abs),
+                                                  word[e] & 3u, false);
+                s[e] = o.state; oo[e] = (uint32_t)o.obs; rr[e] = __float_as_uint(o.reward);
+                fw |= (o.flags & 3u) << (8 * e);
+                net += (o.reward > 0.0f) - (o.reward < 0.0f);
+            }
+        } else if (VEC == 4 && !policy_a && !policy_b) {
             uint32_t aa[4], ab[4], rg[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) { philox_actions(word[e % VEC], aa[e], ab[e]); rg[e] = philox_rng8(word[e % VEC]); }
@@ -131,7 +149,7 @@ __device__ __forceinline__ void rollout_body(const Stepper& S, const RolloutArgs
                 uint32_t word[4], oo[4], rr[4], fw;
 #pragma unroll
                 for (int e = 0; e < VEC; ++e) word[e] = w[e][j];
-                S.template step<VEC>(s, word, oo, rr, fw, c_net);
+                S.template step<VEC>(s, word, oo, rr, fw, c_net, a.seed, a.env_id_base + (uint64_t)i0, a.step0 + (uint64_t)k);
                 acc_d += fw & 0x01010101u;
                 acc_t += (fw >> 1) & ~fw & 0x01010101u;                 // truncated WITHOUT a goal
                 if (VEC == 4) {

@@ -171,6 +171,17 @@ __device__ __forceinline__ void philox_actions(uint32_t w, uint32_t& aa, uint32_
 // rng8-compatible nibble: bits 0..1 step draw, bits 2..3 reset draw
 __device__ __forceinline__ uint32_t philox_rng8(uint32_t w) { return (philox_jr(w) & 3u) | ((w & 3u) << 2); }
 
+// slip_prob > 0 needs a fine-grained uniform for the categorical draw over up to 15 outcomes
+// (SIM:395): a 53-bit uniform in [0, 1), like np.random.RandomState.random(), from words 0 and 1
+// of a SEPARATE counter lane (the top bit of the counter is never set by the per-step words).
+__device__ __forceinline__ double philox_u53(uint64_t seed, uint64_t env_id, uint64_t step)
+{
+    uint32_t w[4];
+    philox4x32_10((uint32_t)env_id, (uint32_t)(env_id >> 32), (uint32_t)step, (uint32_t)(step >> 32) | 0x80000000u,
+                  (uint32_t)seed, (uint32_t)(seed >> 32), w);
+    return (double)(((uint64_t)(w[0] >> 5) << 26) | (uint64_t)(w[1] >> 6)) * (1.0 / 9007199254740992.0);
+}
+
 // ---- streaming accessors and the 4-env group shared by the K1 kernels ----
 constexpr int kThreads = 256;
 __device__ __forceinline__ uint4 ld_stream(const uint4* p) { return __ldcs(p); }

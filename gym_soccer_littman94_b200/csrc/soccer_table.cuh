@@ -16,7 +16,10 @@
 namespace soccer {
 
 constexpr int kTableThreads = 1024;          // one CTA per SM owns the whole shared memory
-constexpr int kRolloutThreads = 512;         // K2 keeps 4 envs x 4 Philox words in registers: 128 registers per thread
+#ifndef SOCCER_ROLLOUT_THREADS
+#define SOCCER_ROLLOUT_THREADS 512           // K2 keeps 4 envs x 4 Philox words in registers: 128 registers per thread
+#endif
+constexpr int kRolloutThreads = SOCCER_ROLLOUT_THREADS;
 constexpr int kMaxTableStates = 1023;        // next_obs must fit 10 bits
 constexpr uint32_t kTblObsMask = 0x3FFu;
 constexpr uint32_t kTruncWord = (uint32_t)kMaxT << 16;   // (obs | t<<16) >= this  <=>  t >= 100

@@ -126,12 +126,35 @@ def gen_native(width, height, slip, mode, seed, T):
     print(f"native {tag}: episodes={int((flg != 0).sum())}", flush=True)
 
 
+def gen_planner(slip, mode, theta=1e-10, gamma=0.99):
+    """The reference's planners (utils/planners.py) on a single-agent env: value iteration over
+    env.P and modified policy iteration over env.Pmat / env.Rmat."""
+    sys.path.insert(0, rh.REFERENCE_ROOT)
+    env, pol = make_env(5, 4, slip, mode)
+    from gym_soccer.utils.planners import modified_policy_iteration, value_iteration
+    t0 = time.time()
+    pi, V, Q, cc = value_iteration(env, theta=theta, discount_factor=gamma)
+    t1 = time.time()
+    mpi, mV, mQ, mcc = modified_policy_iteration(env, k=1, theta=theta, discount_factor=gamma)
+    tag = f"5x4_s{slip_tag(slip)}_{mode}"
+    np.savez_compressed(os.path.join(OUT, f"ref_planner_{tag}.npz"), theta=theta, gamma=gamma,
+                        policy=np.array([pol[s] for s in range(env.nS)], np.int8),
+                        vi_pi=pi, vi_V=V, vi_Q=Q, vi_cc=cc, mpi_pi=mpi, mpi_V=mV, mpi_Q=mQ, mpi_cc=mcc,
+                        vi_seconds=t1 - t0, mpi_seconds=time.time() - t1)
+    print(f"planner {tag}: VI {cc} sweeps {t1 - t0:.1f}s, MPI {mcc} iterations {time.time() - t1:.1f}s", flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--native-only", action="store_true")
+    ap.add_argument("--planner-only", action="store_true")
     args = ap.parse_args()
     os.makedirs(OUT, exist_ok=True)
+    if args.planner_only:
+        gen_planner(0.2, "a_free")
+        gen_planner(0.0, "b_free")
+        return
     gen_native(5, 4, 0.0, "multi", seed=0, T=3000)
     gen_native(5, 4, 0.2, "multi", seed=7, T=3000)
     gen_native(5, 4, 0.2, "a_free", seed=3, T=1500)

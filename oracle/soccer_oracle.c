@@ -548,6 +548,18 @@ void orc_philox_decode(uint32_t w, int *aa, int *ab, int *r_step, int *r_reset)
     *r_reset = (int)(w & 3u);
 }
 
+/* slip_prob > 0: the categorical draw over up to 15 outcomes (SIM:395) needs a fine-grained
+ * uniform; 53 bits from words 0 and 1 of a separate Philox counter lane (top counter bit set). */
+double orc_philox_u53(uint64_t seed, uint64_t env_id, uint64_t step)
+{
+    uint32_t ctr[4] = { (uint32_t)env_id, (uint32_t)(env_id >> 32), (uint32_t)step,
+                        (uint32_t)(step >> 32) | 0x80000000u };
+    uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
+    uint32_t w[4];
+    orc_philox4x32_10(ctr, key, w);
+    return (double)(((uint64_t)(w[0] >> 5) << 26) | (uint64_t)(w[1] >> 6)) * (1.0 / 9007199254740992.0);
+}
+
 void orc_rollout_philox(const orc_model *m, int64_t K, int64_t N,
                         orc_state *state, int32_t *timestep,
                         const int8_t *policy_a, const int8_t *policy_b,
@@ -572,7 +584,9 @@ void orc_rollout_philox(const orc_model *m, int64_t K, int64_t N,
             if (policy_a) aa = policy_a[cur];
             if (policy_b) ab = policy_b[cur];
             int o, d, tr; double r;
-            orc_env_step(&e, aa * 5 + ab, ((double)rs + 0.5) / 4.0, &o, &r, &d, &tr, NULL);
+            double u = m->slip != 0.0 ? orc_philox_u53(seed, env_id_base + (uint64_t)i, step0 + (uint64_t)k)
+                                      : ((double)rs + 0.5) / 4.0;
+            orc_env_step(&e, aa * 5 + ab, u, &o, &r, &d, &tr, NULL);
             s4 += 1;
             if (d || tr) {
                 s0 += 1;

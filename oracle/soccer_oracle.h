@@ -139,6 +139,9 @@ uint32_t orc_philox_word(uint64_t seed, uint64_t env_id, uint64_t step);
 /* decode a word: jr = mulhi(w, 100) -> joint action jr>>2 and step draw jr&3; reset draw = w & 3 */
 void orc_philox_decode(uint32_t w, int *aa, int *ab, int *r_step, int *r_reset);
 
+/* 53-bit uniform for the slip_prob > 0 categorical draw (separate counter lane) */
+double orc_philox_u53(uint64_t seed, uint64_t env_id, uint64_t step);
+
 /* K-step rollout, uniform (policy == NULL) or table policies (int8 obs->action), Philox
  * draws keyed (seed, env_id_base + i, step0 + k).  stats[6] += {episodes, goals_A, goals_B,
  * truncations, steps, sum_episode_len}.  obs/reward/flags may be NULL. slip must be 0. */

@@ -324,6 +324,30 @@ def test_rollout_table_policy_and_ragged(dev, oracle):
     assert np.array_equal(flg.cpu().numpy(), ef) and np.array_equal(stats.cpu().numpy(), es)
 
 
+@pytest.mark.parametrize("w,h,n", [(5, 4, 516), (7, 5, 203)])
+def test_rollout_and_step_philox_with_slip_vs_oracle(dev, oracle, w, h, n):
+    """slip_prob = 0.2 (the commented registration default, gym_soccer/__init__.py:8) through K2 and
+    through K1 in Philox mode: 53-bit Philox uniform, fp64 cumulative sums in the reference's order."""
+    from gym_soccer_littman94_b200.envs import SoccerVecEnv
+    K, seed = 70, 4242
+    m = oracle.OracleModel(w, h, 0.2)
+    env = SoccerVecEnv(n, width=w, height=h, slip_prob=0.2, device=dev, rng_mode="philox", seed=seed)
+    init = env.reset().cpu().numpy()
+    states, ts = m.states_from_obs(init), np.zeros(n, np.int32)
+    eo, er, ef, es = m.rollout_philox(states, ts, K, seed, n_threads=8)
+    obs, rew, flg, stats = env.rollout(K)
+    assert np.array_equal(obs.cpu().numpy(), eo) and np.array_equal(rew.cpu().numpy(), er)
+    assert np.array_equal(flg.cpu().numpy(), ef) and np.array_equal(stats.cpu().numpy(), es)
+    assert (ef != 0).sum() > 50
+    # the same trajectory step by step through K1 (Philox draws, caller-supplied = Philox-decoded actions)
+    e1 = SoccerVecEnv(n, width=w, height=h, slip_prob=0.2, device=dev, rng_mode="philox", seed=seed)
+    e1.reset()
+    for k in range(K):
+        acts = np.array([oracle.philox_decode(oracle.philox_word(seed, i, k))[:2] for i in range(n)], np.uint8)
+        o, r, f, _ = e1.step(_t(acts[:, 0].copy(), dev), _t(acts[:, 1].copy(), dev))
+        assert np.array_equal(o.cpu().numpy(), eo[k]) and np.array_equal(f.cpu().numpy() & 3, ef[k]), k
+
+
 def test_step_philox_equals_rollout(dev):
     """K1 in Philox mode fed the actions K2 draws for itself follows the same trajectory."""
     from gym_soccer_littman94_b200.envs import SoccerVecEnv
