@@ -23,7 +23,7 @@ EXPORTS = (
     "soccer_set_state", "soccer_get_obs", "soccer_step", "soccer_step_philox", "soccer_step_ex",
     "soccer_rollout", "soccer_sweep", "soccer_dense", "soccer_build_step_table", "soccer_step_table",
     "soccer_rollout_table", "soccer_step_table_bytes_host", "soccer_convert_state", "soccer_step_stats",
-    "soccer_step_host", "soccer_step_host_scratch_bytes_host", "soccer_step_many",
+    "soccer_step_host", "soccer_step_host_scratch_bytes_host", "soccer_step_many", "soccer_bench_stream_mix",
 )
 
 
@@ -127,6 +127,7 @@ def lib():
         "soccer_step_stats": [vp, vp, i64, vp, vp],
         "soccer_step_host": [PP, C.POINTER(StepHostArgs)],
         "soccer_step_many": [PP, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, i64, vp],
+        "soccer_bench_stream_mix": [vp, vp, vp, vp, vp, vp, vp, i64, vp],
         "soccer_step_host_scratch_bytes_host": [i64, C.POINTER(i64)],
     }
     for name, argtypes in sig.items():

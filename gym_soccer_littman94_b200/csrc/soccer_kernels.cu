@@ -135,6 +135,22 @@ int resident_blocks(K kernel)
 
 inline int launch_status() { return (int)cudaGetLastError(); }
 
+// Launch with programmatic dependent launch allowed: the kernel's prologue (shared-memory table
+// fill by TMA, candidate-table build) may overlap the tail of the previous kernel in the stream;
+// the kernel itself orders its first global access after griddepcontrol.wait.
+template <typename... KArgs, typename... Args>
+int launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return (int)cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 
 
@@ -160,8 +176,10 @@ k_step_fast(const PitchDev P, uint32_t* __restrict__ state, const uint8_t* __res
             int64_t n_groups)
 {
     __shared__ __align__(16) uint8_t lut[kLutBytes];
+    pdl_launch_dependents();
     build_cand_lut(lut, P);
     const Isd4 I = make_isd4(P);
+    pdl_wait();                  // everything above overlaps the previous kernel's tail
 
     uint4* st4 = reinterpret_cast<uint4*>(state);
     const uint32_t* a4 = reinterpret_cast<const uint32_t*>(act_a);
@@ -390,6 +408,43 @@ int table_bytes_of(const PitchDev& P, int64_t* bytes)
     if (nS - 1 > kMaxTableStates || P.slip) return SOCCER_ETABLE;
     *bytes = (nS * 200 + 15) / 16 * 16;     // nS rows: row 0 is the absorbing terminal observation
     return SOCCER_OK;
+}
+
+// Measurement probe (bench / profiles only): K1's exact memory traffic -- same streams, same
+// access pattern, same cache hints, same launch shape -- with the game logic replaced by a few
+// XORs.  Its throughput is the practical HBM ceiling for K1's 7-bytes-read / 13-bytes-written mix,
+// which a read:write = 1:1 copy benchmark does not measure.
+__global__ void __launch_bounds__(kTableThreads, 1)
+k_stream_mix_probe(uint32_t* __restrict__ state, const uint8_t* __restrict__ act_a, const uint8_t* __restrict__ act_b,
+                   const uint8_t* __restrict__ rng, int32_t* __restrict__ obs, float* __restrict__ reward,
+                   uint8_t* __restrict__ flags, int64_t n_groups)
+{
+    uint4* st4 = reinterpret_cast<uint4*>(state);
+    const uint32_t* a4 = reinterpret_cast<const uint32_t*>(act_a);
+    const uint32_t* b4 = reinterpret_cast<const uint32_t*>(act_b);
+    const uint32_t* r4 = reinterpret_cast<const uint32_t*>(rng);
+    uint4* o4 = reinterpret_cast<uint4*>(obs);
+    uint4* w4 = reinterpret_cast<uint4*>(reward);
+    uint32_t* f4 = reinterpret_cast<uint32_t*>(flags);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_groups; g += 2 * stride) {
+        const int64_t g2 = g + stride;
+        const bool two = g2 < n_groups;
+        const Group4 x0 = load_group(st4, a4, b4, r4, g);
+        Group4 x1 = x0;
+        if (two) x1 = load_group(st4, a4, b4, r4, g2);
+        const uint32_t m0 = x0.a ^ x0.b ^ x0.r, m1 = x1.a ^ x1.b ^ x1.r;
+        st_keep(st4 + g, make_uint4(x0.s.x ^ m0, x0.s.y, x0.s.z, x0.s.w));
+        st_stream(o4 + g, make_uint4(x0.s.y, m0, x0.s.z, x0.s.w));
+        st_stream(w4 + g, make_uint4(m0, x0.s.x, x0.s.w, x0.s.z));
+        st_stream(f4 + g, m0);
+        if (two) {
+            st_keep(st4 + g2, make_uint4(x1.s.x ^ m1, x1.s.y, x1.s.z, x1.s.w));
+            st_stream(o4 + g2, make_uint4(x1.s.y, m1, x1.s.z, x1.s.w));
+            st_stream(w4 + g2, make_uint4(m1, x1.s.x, x1.s.w, x1.s.z));
+            st_stream(f4 + g2, m1);
+        }
+    }
 }
 
 // Episode statistics of ONE lock-step step from its flags (+ reward) streams: the K1 counterpart
@@ -650,12 +705,14 @@ int soccer_step_ex(const soccer_pitch* pitch, const soccer_step_args* a, soccer_
         const int64_t n_groups = a->n / 4;
         if (a->reset_obs) {
             static const int nb = resident_blocks(k_step_fast<true>);
-            k_step_fast<true><<<grid_for(n_groups, nb), kThreads, 0, st>>>(
-                P, a->state, a->act_a, a->act_b, a->rng8, a->obs, a->reward, a->flags, a->reset_obs, n_groups);
+            const int e1 = launch_pdl(k_step_fast<true>, grid_for(n_groups, nb), kThreads, 0, st,
+                                      P, a->state, a->act_a, a->act_b, a->rng8, a->obs, a->reward, a->flags, a->reset_obs, n_groups);
+            if (e1) return e1;
         } else {
             static const int nb = resident_blocks(k_step_fast<false>);
-            k_step_fast<false><<<grid_for(n_groups, nb), kThreads, 0, st>>>(
-                P, a->state, a->act_a, a->act_b, a->rng8, a->obs, a->reward, a->flags, nullptr, n_groups);
+            const int e1 = launch_pdl(k_step_fast<false>, grid_for(n_groups, nb), kThreads, 0, st,
+                                      P, a->state, a->act_a, a->act_b, a->rng8, a->obs, a->reward, a->flags, (int32_t*)nullptr, n_groups);
+            if (e1) return e1;
         }
         const int e = launch_status();
         if (e) return e;
@@ -776,13 +833,15 @@ int soccer_step_table(const soccer_pitch* pitch, const uint16_t* table, uint32_t
         if (reset_obs) {
             const int e0 = allow_big_smem(k_step_table<true>, bytes + 16);
             if (e0) return e0;
-            k_step_table<true><<<table_grid(n_groups), kTableThreads, bytes + 16, st>>>(
-                P, table, (uint32_t)bytes, state, act_a, act_b, rng8, obs, reward, flags, reset_obs, n_groups);
+            const int e1 = launch_pdl(k_step_table<true>, table_grid(n_groups), kTableThreads, (size_t)bytes + 16, st,
+                                      P, table, (uint32_t)bytes, state, act_a, act_b, rng8, obs, reward, flags, reset_obs, n_groups);
+            if (e1) return e1;
         } else {
             const int e0 = allow_big_smem(k_step_table<false>, bytes + 16);
             if (e0) return e0;
-            k_step_table<false><<<table_grid(n_groups), kTableThreads, bytes + 16, st>>>(
-                P, table, (uint32_t)bytes, state, act_a, act_b, rng8, obs, reward, flags, nullptr, n_groups);
+            const int e1 = launch_pdl(k_step_table<false>, table_grid(n_groups), kTableThreads, (size_t)bytes + 16, st,
+                                      P, table, (uint32_t)bytes, state, act_a, act_b, rng8, obs, reward, flags, (int32_t*)nullptr, n_groups);
+            if (e1) return e1;
         }
         const int e = launch_status();
         if (e) return e;
@@ -832,6 +891,18 @@ int soccer_convert_state(const soccer_pitch* pitch, const uint32_t* in, uint32_t
     PitchDev P; const int rc = make_pitch_dev(pitch, &P); if (rc) return rc;
     if (n == 0) return SOCCER_OK;
     k_convert_state<<<grid_for(n, 8), kThreads, 0, (cudaStream_t)stream>>>(P, P.nS, in, out, to_layout, n);
+    return launch_status();
+}
+
+int soccer_bench_stream_mix(uint32_t* state, const uint8_t* act_a, const uint8_t* act_b, const uint8_t* rng8,
+                            int32_t* obs, float* reward, uint8_t* flags, int64_t n, soccer_stream_t stream)
+{
+    if (!state || !act_a || !act_b || !rng8 || !obs || !reward || !flags || n < 4 || (n & 3)) return SOCCER_EINVAL;
+    if (!aligned(state, 16) || !aligned(obs, 16) || !aligned(reward, 16) || !aligned(act_a, 4) || !aligned(act_b, 4) ||
+        !aligned(rng8, 4) || !aligned(flags, 4))
+        return SOCCER_EINVAL;
+    k_stream_mix_probe<<<table_grid(n / 4), kTableThreads, 0, (cudaStream_t)stream>>>(state, act_a, act_b, rng8, obs,
+                                                                                      reward, flags, n / 4);
     return launch_status();
 }
 

@@ -182,6 +182,10 @@ __device__ __forceinline__ double philox_u53(uint64_t seed, uint64_t env_id, uin
     return (double)(((uint64_t)(w[0] >> 5) << 26) | (uint64_t)(w[1] >> 6)) * (1.0 / 9007199254740992.0);
 }
 
+// ---- programmatic dependent launch (no-ops unless the launch carries the PDL attribute) ----
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- streaming accessors and the 4-env group shared by the K1 kernels ----
 constexpr int kThreads = 256;
 __device__ __forceinline__ uint4 ld_stream(const uint4* p) { return __ldcs(p); }

@@ -159,8 +159,10 @@ k_step_table(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t tab
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar;
-    stage_table(smem_raw, gtable, table_bytes, &bar, P);
+    pdl_launch_dependents();
+    stage_table(smem_raw, gtable, table_bytes, &bar, P);     // the table is constant: safe before pdl_wait
     const TblCtx c = make_ctx(smem_raw, table_bytes, P);
+    pdl_wait();                  // the table fill overlaps the previous kernel's tail
 
     uint4* st4 = reinterpret_cast<uint4*>(state);
     const uint32_t* a4 = reinterpret_cast<const uint32_t*>(act_a);

@@ -100,6 +100,9 @@ class SoccerVecEnv:
             with torch.cuda.device(dev):
                 check(self.lib.soccer_build_step_table(C.byref(self.pitch), _ptr(self.table), _stream(dev)),
                       "soccer_build_step_table")
+                # the step kernels prefetch the table BEFORE their grid-dependency wait (programmatic
+                # dependent launch), so it must be complete before the first step is enqueued
+                torch.cuda.current_stream(dev).synchronize()
 
     # ------------------------------------------------------------------ helpers
     def _policy_tensor(self, policy):

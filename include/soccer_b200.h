@@ -171,6 +171,14 @@ int soccer_step_ex(const soccer_pitch *pitch, const soccer_step_args *args, socc
 int soccer_step_stats(const uint8_t *flags, const float *reward, int64_t n,
                       unsigned long long *stats, soccer_stream_t stream);
 
+/* Measurement probe, not part of the game: K1's memory traffic (7 bytes read, 13 written per env,
+ * same access pattern and cache hints) with no game logic.  bench.py times it next to K1 to show
+ * the practical HBM ceiling for K1's read:write mix.  n % 4 == 0, aligned pointers; it overwrites
+ * state / obs / reward / flags with meaningless values. */
+int soccer_bench_stream_mix(uint32_t *state, const uint8_t *act_a, const uint8_t *act_b,
+                            const uint8_t *rng8, int32_t *obs, float *reward, uint8_t *flags,
+                            int64_t n, soccer_stream_t stream);
+
 /* ---- K2: fused K-step rollout, state register-resident, on-device policy ---- */
 /* policy_* == NULL -> uniform random joint action from the Philox word; else int8[nS] table.
  * obs/reward/flags are [K][n] streams (each optional).  stats[6] (optional, uint64, accumulated
