@@ -160,6 +160,40 @@ def test_step_ragged_and_misaligned(dev, kernel, n_pad, misalign):
     assert np.array_equal(flg & 3, sub["flags"]) and np.array_equal(rob, sub["reset_obs"])
 
 
+@pytest.mark.parametrize("w,h,slip", [(14, 9, 0.0), (18, 7, 0.0), (31, 4, 0.0), (9, 6, 0.3)])
+def test_maximum_pitch_sizes_vs_oracle(dev, oracle, w, h, slip):
+    """The largest supported pitches (width*height = 126 field cells, nS = 31,501; odd and even
+    heights): K1 (byte-parallel and generic), K2 and the sweep against the oracle."""
+    from gym_soccer_littman94_b200.envs import SoccerVecEnv
+    m = oracle.OracleModel(w, h, slip)
+    assert m.nS == 1 + 2 * (w * h) * (w * h - 1)
+    N, T = 257, 160
+    rs = np.random.RandomState(w * 100 + h)
+    # start from random reachable states so that the whole pitch is exercised
+    obs0 = rs.randint(1, m.nS, N).astype(np.int32)
+    t0 = rs.randint(0, 99, N).astype(np.int32)
+    states, ts = m.states_from_obs(obs0), t0.copy()
+    act_a, act_b = (rs.randint(0, 5, (T, N)).astype(np.uint8) for _ in range(2))
+    rng8 = rs.randint(0, 16, (T, N)).astype(np.uint8)
+    rng32 = rs.randint(0, 2 ** 32, (T, N), dtype=np.uint64).astype(np.uint32) if slip else None
+    eo, er, ef, ero = m.rollout_injected(states, ts, act_a, act_b, rng8, rng32, n_threads=4)
+    env = SoccerVecEnv(N, width=w, height=h, slip_prob=slip, device=dev, kernel="rules")
+    env.set_state(_t(obs0, dev), _t(t0, dev))
+    for t in range(T):
+        o, r, f, ro = env.step(_t(act_a[t], dev), _t(act_b[t], dev), _t(rng8[t], dev),
+                               rng32=None if rng32 is None else _t(rng32[t].view(np.int32), dev))
+        assert np.array_equal(o.cpu().numpy(), eo[t]) and np.array_equal(r.cpu().numpy(), er[t]), t
+        assert np.array_equal(f.cpu().numpy() & 3, ef[t]) and np.array_equal(ro.cpu().numpy(), ero[t]), t
+    assert np.array_equal(env.current_obs().cpu().numpy(), m.obs_from_states(states))
+    # K2 with Philox draws
+    e2 = SoccerVecEnv(N - 1, width=w, height=h, slip_prob=slip, device=dev, rng_mode="philox", seed=9)
+    st2 = m.states_from_obs(e2.reset().cpu().numpy())
+    po, pr, pf, ps = m.rollout_philox(st2, np.zeros(N - 1, np.int32), 130, 9, n_threads=4)
+    o2, r2, f2, s2 = e2.rollout(130)
+    assert np.array_equal(o2.cpu().numpy(), po) and np.array_equal(f2.cpu().numpy(), pf)
+    assert np.array_equal(s2.cpu().numpy(), ps)
+
+
 def test_step_empty_batch(dev):
     from gym_soccer_littman94_b200.envs import SoccerVecEnv
     env = SoccerVecEnv(0, device=dev, kernel="rules")
