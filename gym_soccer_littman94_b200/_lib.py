@@ -24,6 +24,7 @@ EXPORTS = (
     "soccer_rollout", "soccer_sweep", "soccer_dense", "soccer_build_step_table", "soccer_step_table",
     "soccer_rollout_table", "soccer_step_table_bytes_host", "soccer_convert_state", "soccer_step_stats",
     "soccer_step_host", "soccer_step_host_scratch_bytes_host", "soccer_step_many", "soccer_bench_stream_mix",
+    "soccer_bench_rollout_probe",
 )
 
 
@@ -128,6 +129,7 @@ def lib():
         "soccer_step_host": [PP, C.POINTER(StepHostArgs)],
         "soccer_step_many": [PP, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, i64, vp],
         "soccer_bench_stream_mix": [vp, vp, vp, vp, vp, vp, vp, i64, vp],
+        "soccer_bench_rollout_probe": [vp, i32, vp, vp, vp, i64, i32, vp],
         "soccer_step_host_scratch_bytes_host": [i64, C.POINTER(i64)],
     }
     for name, argtypes in sig.items():

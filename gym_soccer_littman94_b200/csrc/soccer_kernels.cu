@@ -906,6 +906,26 @@ int soccer_bench_stream_mix(uint32_t* state, const uint8_t* act_a, const uint8_t
     return launch_status();
 }
 
+int soccer_bench_rollout_probe(uint32_t* state, int32_t K, int32_t* obs, float* reward, uint8_t* flags, int64_t n,
+                               int32_t mode, soccer_stream_t stream)
+{
+    if (!state || !obs || !reward || !flags || K < 0 || n < 8 || (n & 7)) return SOCCER_EINVAL;
+    if (!aligned(state, 16) || !aligned(obs, 16) || !aligned(reward, 16) || !aligned(flags, 4)) return SOCCER_EINVAL;
+    const RolloutArgs ra = { state, 0, 0, K, 0, obs, reward, flags, nullptr, n };
+    const int grid = table_grid(n / 4, kRolloutThreads);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (mode) {
+    case 0: k_rollout_probe<0><<<grid, kRolloutThreads, 0, st>>>(ra); break;
+    case 1: k_rollout_probe<1><<<grid, kRolloutThreads, 0, st>>>(ra); break;
+    case 2: k_rollout_probe<2><<<grid, kRolloutThreads, 0, st>>>(ra); break;
+    case 3: k_rollout_probe<3><<<grid, kRolloutThreads, 0, st>>>(ra); break;
+    case 4: k_rollout_probe<4><<<grid, kRolloutThreads, 0, st>>>(ra); break;
+    case 5: k_rollout_probe<5><<<grid, kRolloutThreads, 0, st>>>(ra); break;
+    default: return SOCCER_EINVAL;
+    }
+    return launch_status();
+}
+
 int soccer_step_stats(const uint8_t* flags, const float* reward, int64_t n, unsigned long long* stats,
                       soccer_stream_t stream)
 {

@@ -26,12 +26,17 @@ struct RolloutArgs {
 };
 
 // ---- steppers: advance the VEC envs of a thread by one step given their Philox words
+// A variant of this stepper that moved the selects / shifts / compares onto the FMA pipe (mul.hi carries, IMAD
+// packing, 2^23 magic-add int -> float; ALU pipe 81 % -> 71 % busy) measured 2 % SLOWER on B200 in three A/B
+// runs: with 2^20+ envs the kernel sits at the HBM write ceiling (0.92-0.99 of the traffic probe), not on issue.
 struct TableStepper {
     TblCtx c;
-    __device__ __forceinline__ uint32_t timestep(uint32_t s) const { return s >> 16; }
+    __device__ __forceinline__ void unpack(uint32_t&, uint32_t&) const {}
+    __device__ __forceinline__ uint32_t pack(uint32_t s, uint32_t) const { return s; }
+    __device__ __forceinline__ uint32_t timestep(uint32_t s, uint32_t) const { return s >> 16; }
     template <int VEC>
-    __device__ __forceinline__ void step(uint32_t* s, const uint32_t* word, uint32_t* oo, uint32_t* rr, uint32_t& fw,
-                                         int32_t& net, uint64_t, uint64_t, uint64_t) const
+    __device__ __forceinline__ void step(uint32_t* s, uint32_t*, const uint32_t* word, uint32_t* oo, uint32_t* rr,
+                                         uint32_t& fw, int32_t& net, uint64_t, uint64_t, uint64_t) const
     {
         uint32_t ff[4] = { 0, 0, 0, 0 };
 #pragma unroll
@@ -47,10 +52,12 @@ struct TableStepper {
 
 struct RulesStepper {
     const PitchDev& P; const uint8_t* lut; Isd4 I; const int8_t* policy_a; const int8_t* policy_b;
-    __device__ __forceinline__ uint32_t timestep(uint32_t s) const { return (s >> 16) & 0xFFu; }
+    __device__ __forceinline__ void unpack(uint32_t&, uint32_t&) const {}          // the packed CELL word as is
+    __device__ __forceinline__ uint32_t pack(uint32_t s, uint32_t) const { return s; }
+    __device__ __forceinline__ uint32_t timestep(uint32_t s, uint32_t) const { return (s >> 16) & 0xFFu; }
     template <int VEC>
-    __device__ __forceinline__ void step(uint32_t* s, const uint32_t* word, uint32_t* oo, uint32_t* rr, uint32_t& fw,
-                                         int32_t& net, uint64_t seed, uint64_t env0, uint64_t step_abs) const
+    __device__ __forceinline__ void step(uint32_t* s, uint32_t*, const uint32_t* word, uint32_t* oo, uint32_t* rr,
+                                         uint32_t& fw, int32_t& net, uint64_t seed, uint64_t env0, uint64_t step_abs) const
     {
         if (P.slip) {
             // slip_prob > 0 (SIM:203-227): the scalar 9-combination walk with a 53-bit Philox uniform
@@ -108,12 +115,26 @@ __device__ __forceinline__ void rollout_body(const Stepper& S, const RolloutArgs
     uint32_t c_done = 0, c_trunc = 0, c_len = 0, c_steps = 0;
     int32_t c_net = 0;
     const int64_t n_groups = a.n / VEC;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int32_t K = a.K;
     const int32_t k_first = -(int32_t)(a.step0 & 3u);         // relative index of word 0 of the first Philox block
     const uint64_t blk0 = a.step0 >> 2;
     const uint32_t key0 = (uint32_t)a.seed, key1 = (uint32_t)(a.seed >> 32);
-    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_groups; g += stride) {
+    // Slot order (a slot = 32 threads x VEC envs).  Full passes are CTA-major: the 16 warps of a CTA own 16
+    // adjacent slots, so every step the SM writes 8 KB / 8 KB / 2 KB contiguous per stream - measured with the
+    // traffic probe (profiles/probe_modes.py), 8 KB chunks written by ONE SM reach 5.9-6.4 TB/s where 512 B chunks
+    // whose neighbours come from other SMs (arbitrary skew) reach 5.7-5.9.  The last, partial pass is dealt
+    // warp by warp round-robin over the CTAs, so it leaves every SM the same number of busy warps instead of whole
+    // SMs idle: 2^20 envs are 8192 slots = 55.35 per SM, which pure CTA-major order ran as 4 passes on 68 SMs, 3 on 80.
+    const int64_t n_slots = (n_groups + 31) >> 5;
+    const int32_t wpc = blockDim.x >> 5, wib = threadIdx.x >> 5;
+    const int64_t per_pass = (int64_t)gridDim.x * wpc;
+    const int64_t full = n_slots / per_pass;
+    for (int64_t pass = 0; pass <= full; ++pass) {
+        const int64_t slot = pass < full ? (pass * gridDim.x + blockIdx.x) * wpc + wib
+                                         : full * per_pass + (int64_t)wib * gridDim.x + blockIdx.x;
+        if (slot >= n_slots) break;
+        const int64_t g = slot * 32 + (threadIdx.x & 31);
+        if (g >= n_groups) break;
         const int64_t i0 = g * VEC;
         uint32_t s[4] = { 0, 0, 0, 0 };
         if (VEC == 4) {
@@ -122,9 +143,10 @@ __device__ __forceinline__ void rollout_body(const Stepper& S, const RolloutArgs
         } else {
             s[0] = a.state[i0];
         }
+        uint32_t aux[4] = { 0, 0, 0, 0 };
         uint32_t t_in = 0;
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) t_in += S.timestep(s[e]);
+        for (int e = 0; e < VEC; ++e) { S.unpack(s[e], aux[e]); t_in += S.timestep(s[e], aux[e]); }
         uint32_t acc_d = 0, acc_t = 0;
         int32_t* op = a.obs ? a.obs + i0 : nullptr;
         float* rp = a.reward ? a.reward + i0 : nullptr;
@@ -149,7 +171,7 @@ __device__ __forceinline__ void rollout_body(const Stepper& S, const RolloutArgs
                 uint32_t word[4], oo[4], rr[4], fw;
 #pragma unroll
                 for (int e = 0; e < VEC; ++e) word[e] = w[e][j];
-                S.template step<VEC>(s, word, oo, rr, fw, c_net, a.seed, a.env_id_base + (uint64_t)i0, a.step0 + (uint64_t)k);
+                S.template step<VEC>(s, aux, word, oo, rr, fw, c_net, a.seed, a.env_id_base + (uint64_t)i0, a.step0 + (uint64_t)k);
                 acc_d += fw & 0x01010101u;
                 acc_t += (fw >> 1) & ~fw & 0x01010101u;                 // truncated WITHOUT a goal
                 if (VEC == 4) {
@@ -170,7 +192,7 @@ __device__ __forceinline__ void rollout_body(const Stepper& S, const RolloutArgs
         c_done = __dp4a(acc_d, 0x01010101u, c_done); c_trunc = __dp4a(acc_t, 0x01010101u, c_trunc);
         uint32_t t_out = 0;
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) t_out += S.timestep(s[e]);
+        for (int e = 0; e < VEC; ++e) { t_out += S.timestep(s[e], aux[e]); s[e] = S.pack(s[e], aux[e]); }
         c_len += t_in + (uint32_t)K * VEC - t_out;
         c_steps += (uint32_t)K * VEC;
         if (VEC == 4) reinterpret_cast<uint4*>(a.state)[g] = make_uint4(s[0], s[1], s[2], s[3]);
@@ -229,6 +251,62 @@ k_rollout(const PitchDev P, const int8_t* __restrict__ policy_a, const int8_t* _
     __syncthreads();
     const RulesStepper S = { P, lut, make_isd4(P), policy_a, policy_b };
     rollout_body<VEC, STREAMS>(S, a, blk_stats, &blk_net);
+}
+
+// Measurement probe, not part of the game: K2's memory traffic (state read and written once, K x
+// (16 + 16 + 4) bytes per 4-env group streamed out with the same stores, launch shape and slot order)
+// with no Philox and no game logic.  Its throughput is the practical HBM ceiling for K2's write-only mix.
+template <int MODE> __device__ __forceinline__ void st_probe(uint4* p, uint4 v)
+{
+    if (MODE == 1) *p = v;
+    else if (MODE == 2) asm volatile("st.global.wt.v4.u32 [%0], {%1, %2, %3, %4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    else if (MODE == 3) asm volatile("st.global.cg.v4.u32 [%0], {%1, %2, %3, %4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    else __stcs(p, v);
+}
+template <int MODE> __device__ __forceinline__ void st_probe(uint32_t* p, uint32_t v)
+{
+    if (MODE == 1) *p = v;
+    else if (MODE == 2) asm volatile("st.global.wt.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+    else if (MODE == 3) asm volatile("st.global.cg.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+    else __stcs(p, v);
+}
+
+// MODE 0: K2's stores (st.global.cs) and slot order, 1: default cache policy, 2: write-through, 3: .cg,
+// 4: pure CTA-major slot order, 5: pure warp round-robin slot order
+template <int MODE>
+__global__ void __launch_bounds__(kRolloutThreads, 1)
+k_rollout_probe(const RolloutArgs a)
+{
+    constexpr int G = 1;
+    const int64_t n_groups = a.n / (4 * G);
+    const int64_t n_slots = (n_groups + 31) >> 5;
+    const int32_t wpc = blockDim.x >> 5, wib = threadIdx.x >> 5;
+    const int64_t per_pass = (int64_t)gridDim.x * wpc;
+    const int64_t full = MODE == 4 ? (n_slots + per_pass - 1) / per_pass : MODE == 5 ? 0 : n_slots / per_pass;
+    const int64_t last = MODE == 5 ? (n_slots + per_pass - 1) / per_pass : full;
+    for (int64_t pass = 0; pass <= last; ++pass) {
+        const int64_t slot = pass < full ? (pass * gridDim.x + blockIdx.x) * wpc + wib
+                                         : pass * per_pass + (int64_t)wib * gridDim.x + blockIdx.x;
+        if (slot >= n_slots) break;
+        const int64_t g = slot * 32 + (threadIdx.x & 31);
+        if (g >= n_groups) break;
+        uint4 v = reinterpret_cast<const uint4*>(a.state)[g * G];
+        int32_t* op = a.obs + g * 4 * G;
+        float* rp = a.reward + g * 4 * G;
+        uint8_t* fp = a.flags + g * 4 * G;
+        for (int32_t k = 0; k < a.K; ++k) {
+            v.x += v.y; v.y ^= v.z; v.z += v.w; v.w += 0x9E3779B9u;
+#pragma unroll
+            for (int q = 0; q < G; ++q) {
+                st_probe<MODE>(reinterpret_cast<uint4*>(op) + q, v);
+                st_probe<MODE>(reinterpret_cast<uint4*>(rp) + q, make_uint4(v.y, v.x, v.w, v.z));
+                st_probe<MODE>(reinterpret_cast<uint32_t*>(fp) + q, v.x ^ v.w);
+            }
+            op += a.n; rp += a.n; fp += a.n;
+        }
+#pragma unroll
+        for (int q = 0; q < G; ++q) reinterpret_cast<uint4*>(a.state)[g * G + q] = v;
+    }
 }
 
 } // namespace soccer

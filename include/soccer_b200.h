@@ -179,6 +179,13 @@ int soccer_bench_stream_mix(uint32_t *state, const uint8_t *act_a, const uint8_t
                             const uint8_t *rng8, int32_t *obs, float *reward, uint8_t *flags,
                             int64_t n, soccer_stream_t stream);
 
+/* Measurement probe for K2: the fused rollout's memory traffic (state in/out once, K x 9 bytes per
+ * env streamed to the [K][n] obs / reward / flags arrays with K2's stores, launch shape and slot
+ * order) with no Philox and no game logic = practical HBM ceiling for a write-only stream mix.
+ * mode 0 = K2's stores; 1-5 = store-flavour / slot-order experiments (see k_rollout_probe). */
+int soccer_bench_rollout_probe(uint32_t *state, int32_t K, int32_t *obs, float *reward,
+                               uint8_t *flags, int64_t n, int32_t mode, soccer_stream_t stream);
+
 /* ---- K2: fused K-step rollout, state register-resident, on-device policy ---- */
 /* policy_* == NULL -> uniform random joint action from the Philox word; else int8[nS] table.
  * obs/reward/flags are [K][n] streams (each optional).  stats[6] (optional, uint64, accumulated
