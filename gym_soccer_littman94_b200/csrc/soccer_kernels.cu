@@ -12,6 +12,7 @@
 #include "soccer_rules.cuh"
 #include "soccer_rules4.cuh"
 #include "soccer_rollout.cuh"
+#include "soccer_replay.cuh"
 
 #include <cuda_runtime.h>
 
@@ -935,21 +936,76 @@ int soccer_step_stats(const uint8_t* flags, const float* reward, int64_t n, unsi
     return launch_status();
 }
 
+// launch shape of the fused replay: spread few envs over many SMs (one warp per CTA for a 4096-env
+// batch: the step chain is latency-bound, so every warp gets an SM sub-partition of its own), grow the
+// CTAs up to max_threads once every SM has one
+static void replay_shape(int64_t items, int max_threads, int cta_cap, int* grid, int* block)
+{
+    const int64_t slots = (items + 31) / 32;
+    int64_t wpc = (slots + cta_cap - 1) / cta_cap;
+    if (wpc < 1) wpc = 1;
+    if (wpc > max_threads / 32) wpc = max_threads / 32;
+    const int64_t need = (slots + wpc - 1) / wpc;
+    *block = (int)wpc * 32;
+    *grid = (int)(need < cta_cap ? (need < 1 ? 1 : need) : cta_cap);
+}
+
 int soccer_step_many(const soccer_pitch* pitch, const uint16_t* table, uint32_t* state, int32_t T,
                      const uint8_t* act_a, const uint8_t* act_b, const uint8_t* rng8, int32_t* obs, float* reward,
                      uint8_t* flags, int32_t* reset_obs, int64_t n, soccer_stream_t stream)
 {
     if (T < 0 || n < 0 || !state || !act_a || !act_b || !rng8 || !obs || !reward || !flags) return SOCCER_EINVAL;
-    for (int32_t t = 0; t < T; ++t) {
-        const int64_t o = (int64_t)t * n;
-        const int rc = table
-            ? soccer_step_table(pitch, table, state, act_a + o, act_b + o, rng8 + o, obs + o, reward + o, flags + o,
-                                reset_obs ? reset_obs + o : nullptr, n, stream)
-            : soccer_step(pitch, state, act_a + o, act_b + o, rng8 + o, obs + o, reward + o, flags + o,
-                          reset_obs ? reset_obs + o : nullptr, n, stream);
-        if (rc) return rc;
+    if (pitch && pitch->slip_prob != 0.0) return SOCCER_ESLIP;
+    PitchDev P; int rc = make_pitch_dev(pitch, &P); if (rc) return rc;
+    int64_t bytes = 0;
+    if (table) {
+        rc = table_bytes_of(P, &bytes); if (rc) return rc;
+        if (!aligned(table, 16)) return SOCCER_EINVAL;
     }
-    return SOCCER_OK;
+    if (T == 0 || n == 0) return SOCCER_OK;
+    if (T == 1)
+        return table ? soccer_step_table(pitch, table, state, act_a, act_b, rng8, obs, reward, flags, reset_obs, n, stream)
+                     : soccer_step(pitch, state, act_a, act_b, rng8, obs, reward, flags, reset_obs, n, stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    // rows t of the [T][n] arrays start at t * n: 128-bit / 32-bit accesses need n % 4 == 0 as well
+    const bool vec = (n % 4 == 0) && aligned(state, 16) && aligned(obs, 16) && aligned(reward, 16) &&
+                     (!reset_obs || aligned(reset_obs, 16)) && aligned(act_a, 4) && aligned(act_b, 4) &&
+                     aligned(rng8, 4) && aligned(flags, 4);
+    const ReplayArgs ra = { state, act_a, act_b, rng8, T, obs, reward, flags, reset_obs, n };
+    int grid = 1, block = 32;
+#ifndef SOCCER_REPLAY_VEC1_WARPS
+#define SOCCER_REPLAY_VEC1_WARPS 4      // measured: one env per thread wins up to 4 warps per SM (profiles/r01d_ab_replay4.log)
+#endif
+#define SOCCER_LAUNCH_REPLAY_T(VEC, RO, U, ITEMS)                                                         \
+    do {                                                                                                  \
+        const int e0 = allow_big_smem(k_replay_table<VEC, RO, U>, bytes + 16);                            \
+        if (e0) return e0;                                                                                \
+        replay_shape(ITEMS, kRolloutThreads, sms, &grid, &block);                                         \
+        k_replay_table<VEC, RO, U><<<grid, block, bytes + 16, st>>>(P, table, (uint32_t)bytes, ra);       \
+    } while (0)
+#define SOCCER_LAUNCH_REPLAY(VEC, RO, U, ITEMS)                                                           \
+    do {                                                                                                  \
+        static const int nb = resident_blocks(k_replay<VEC, RO, U>);                                      \
+        replay_shape(ITEMS, kThreads, sms * nb, &grid, &block);                                           \
+        k_replay<VEC, RO, U><<<grid, block, 0, st>>>(P, ra);                                              \
+    } while (0)
+#define SOCCER_REPLAY_PICK(LAUNCH)                                                                        \
+    do {                                                                                                  \
+        if (!vec || tiny) { if (reset_obs) LAUNCH(1, true, 8, n); else LAUNCH(1, false, 8, n); }          \
+        else if (!fills) { if (reset_obs) LAUNCH(4, true, 8, n / 4); else LAUNCH(4, false, 8, n / 4); }   \
+        else { if (reset_obs) LAUNCH(4, true, 4, n / 4); else LAUNCH(4, false, 4, n / 4); }               \
+    } while (0)
+    const int sms = sm_count();
+    // tiny: one env per thread still leaves the SMs at <= 4 warps -> shortest dependent chain per warp wins;
+    // fills: every SM gets a full CTA of 4-env threads -> HBM-bound regime, 4 rows of look-ahead suffice
+    const bool tiny = (n + 31) / 32 <= (int64_t)sms * SOCCER_REPLAY_VEC1_WARPS;
+    const bool fills = (n / 4 + 31) / 32 >= (int64_t)sms * (table ? kRolloutThreads / 32 : kThreads / 32);
+    if (table) SOCCER_REPLAY_PICK(SOCCER_LAUNCH_REPLAY_T);
+    else SOCCER_REPLAY_PICK(SOCCER_LAUNCH_REPLAY);
+#undef SOCCER_REPLAY_PICK
+#undef SOCCER_LAUNCH_REPLAY_T
+#undef SOCCER_LAUNCH_REPLAY
+    return launch_status();
 }
 
 int soccer_step_host_scratch_bytes_host(int64_t n, int64_t* bytes)

@@ -288,6 +288,42 @@ def test_config2_4096_envs_vs_oracle(dev, oracle, kernel):
     assert n_eps > 1_000_000   # ~34-step episodes: the fused reset really is exercised
 
 
+@pytest.mark.parametrize("kernel", ["rules", "table"])
+@pytest.mark.parametrize("n,T,want_ro", [(1, 1, True), (5, 3, True), (4096, 2, False), (4096, 37, True), (4099, 9, True),
+                                         (100000, 4, False), (33 * 148 * 4 + 8, 70, True), (0, 5, True)])
+def test_step_many_fused_equals_single_steps(dev, kernel, n, T, want_ro):
+    """soccer_step_many runs the T steps in ONE launch with the state in registers (k_replay*): same
+    streams and final state as T launches of K1, for vector / scalar shapes, T not a multiple of the
+    register buffer depth, T shorter than it, partial last pass, with and without reset_obs."""
+    from gym_soccer_littman94_b200.envs import SoccerVecEnv
+    g = torch.Generator(device=dev).manual_seed(n * 131 + T)
+    a, b, r = (torch.randint(0, hi, (T, n), dtype=torch.uint8, device=dev, generator=g) for hi in (5, 5, 16))
+    init = torch.randint(0, 16, (n,), dtype=torch.uint8, device=dev, generator=g)
+    e1 = SoccerVecEnv(n, device=dev, kernel=kernel, want_reset_obs=want_ro)
+    e2 = SoccerVecEnv(n, device=dev, kernel=kernel, want_reset_obs=want_ro)
+    e1.reset(init)
+    e2.reset(init)
+    # start mid-episode so that truncation (t >= 100) fires inside the window as well
+    warm = 80
+    for t in range(warm):
+        for e in (e1, e2):
+            e.step(a[t % T], b[(t * 7) % T], r[(t * 3) % T])
+    assert torch.equal(e1.state, e2.state)
+    want = [tuple(None if x is None else x.clone() for x in e1.step(a[t], b[t], r[t])) for t in range(T)]
+    obs, rew, flg, rob = e2.step_many(a, b, r)
+    for t in range(T):
+        assert torch.equal(obs[t], want[t][0]), (t, "obs")
+        assert torch.equal(rew[t], want[t][1]), (t, "reward")
+        assert torch.equal(flg[t], want[t][2]), (t, "flags")
+        if want_ro:
+            assert torch.equal(rob[t], want[t][3]), (t, "reset_obs")
+        else:
+            assert rob is None
+    assert torch.equal(e1.state, e2.state)
+    if n >= 4096 and T >= 30:
+        assert int((flg & 2).count_nonzero()) > 0 and int((flg & 1).count_nonzero()) > 0
+
+
 def test_exhaustive_single_steps_vs_golden(dev):
     """Every state x 25 joint actions x 4 draw values in ONE launch of each kernel, against the
     reference's table: the sweep of BASELINE config 5 done through the step entry points."""
