@@ -856,9 +856,10 @@ int soccer_step_table(const soccer_pitch* pitch, const uint16_t* table, uint32_t
     return launch_status();
 }
 
-int soccer_rollout_table(const soccer_pitch* pitch, const uint16_t* table, uint32_t* state, uint64_t seed,
-                         uint64_t step0, int32_t K, uint64_t env_id_base, int32_t* obs, float* reward,
-                         uint8_t* flags, unsigned long long* stats, int64_t n, soccer_stream_t stream)
+int soccer_rollout_table_policy(const soccer_pitch* pitch, const uint16_t* table, uint32_t* state,
+                                const int8_t* policy_a, const int8_t* policy_b, uint64_t seed, uint64_t step0, int32_t K,
+                                uint64_t env_id_base, int32_t* obs, float* reward, uint8_t* flags,
+                                unsigned long long* stats, int64_t n, soccer_stream_t stream)
 {
     if (!table || !state || n < 0 || K < 0) return SOCCER_EINVAL;
     PitchDev P; int rc = make_pitch_dev(pitch, &P); if (rc) return rc;
@@ -870,19 +871,35 @@ int soccer_rollout_table(const soccer_pitch* pitch, const uint16_t* table, uint3
                      (!reward || aligned(reward, 16)) && (!flags || aligned(flags, 4));
     const RolloutArgs ra = { state, seed, step0, K, env_id_base, obs, reward, flags, stats, n };
     const bool streams = obs && reward && flags;
-#define SOCCER_LAUNCH_ROLLOUT_T(VEC, STR, ITEMS)                                                         \
+    const bool pol = policy_a || policy_b;
+    const int64_t smem = bytes + 16 + (pol ? 2 * ((P.nS + 15) & ~15) : 0);
+#define SOCCER_LAUNCH_ROLLOUT_T(VEC, STR, POL, ITEMS)                                                    \
     do {                                                                                                 \
-        const int e0 = allow_big_smem(k_rollout_table<VEC, STR>, bytes + 16);                            \
+        const int e0 = allow_big_smem(k_rollout_table<VEC, STR, POL>, smem);                             \
         if (e0) return e0;                                                                               \
-        k_rollout_table<VEC, STR><<<table_grid(ITEMS, kRolloutThreads), kRolloutThreads, bytes + 16, st>>>( \
-            P, table, (uint32_t)bytes, ra);                                                              \
+        k_rollout_table<VEC, STR, POL><<<table_grid(ITEMS, kRolloutThreads), kRolloutThreads, smem, st>>>( \
+            P, table, (uint32_t)bytes, policy_a, policy_b, ra);                                          \
     } while (0)
-    if (vec && streams) SOCCER_LAUNCH_ROLLOUT_T(4, true, n / 4);
-    else if (vec) SOCCER_LAUNCH_ROLLOUT_T(4, false, n / 4);
-    else if (streams) SOCCER_LAUNCH_ROLLOUT_T(1, true, n);
-    else SOCCER_LAUNCH_ROLLOUT_T(1, false, n);
+#define SOCCER_PICK_ROLLOUT_T(POL)                                                                       \
+    do {                                                                                                 \
+        if (vec && streams) SOCCER_LAUNCH_ROLLOUT_T(4, true, POL, n / 4);                                \
+        else if (vec) SOCCER_LAUNCH_ROLLOUT_T(4, false, POL, n / 4);                                     \
+        else if (streams) SOCCER_LAUNCH_ROLLOUT_T(1, true, POL, n);                                      \
+        else SOCCER_LAUNCH_ROLLOUT_T(1, false, POL, n);                                                  \
+    } while (0)
+    if (pol) SOCCER_PICK_ROLLOUT_T(true);
+    else SOCCER_PICK_ROLLOUT_T(false);
+#undef SOCCER_PICK_ROLLOUT_T
 #undef SOCCER_LAUNCH_ROLLOUT_T
     return launch_status();
+}
+
+int soccer_rollout_table(const soccer_pitch* pitch, const uint16_t* table, uint32_t* state, uint64_t seed,
+                         uint64_t step0, int32_t K, uint64_t env_id_base, int32_t* obs, float* reward,
+                         uint8_t* flags, unsigned long long* stats, int64_t n, soccer_stream_t stream)
+{
+    return soccer_rollout_table_policy(pitch, table, state, nullptr, nullptr, seed, step0, K, env_id_base, obs, reward,
+                                       flags, stats, n, stream);
 }
 
 int soccer_convert_state(const soccer_pitch* pitch, const uint32_t* in, uint32_t* out, int32_t to_layout, int64_t n,

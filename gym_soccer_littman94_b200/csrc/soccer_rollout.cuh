@@ -29,8 +29,10 @@ struct RolloutArgs {
 // A variant of this stepper that moved the selects / shifts / compares onto the FMA pipe (mul.hi carries, IMAD
 // packing, 2^23 magic-add int -> float; ALU pipe 81 % -> 71 % busy) measured 2 % SLOWER on B200 in three A/B
 // runs: with 2^20+ envs the kernel sits at the HBM write ceiling (0.92-0.99 of the traffic probe), not on issue.
+template <bool POLICY>
 struct TableStepper {
     TblCtx c;
+    uint32_t pol_a, pol_b;      // shared-window addresses of the int8[nS] table policies, 0 = uniform (POLICY only)
     __device__ __forceinline__ void unpack(uint32_t&, uint32_t&) const {}
     __device__ __forceinline__ uint32_t pack(uint32_t s, uint32_t) const { return s; }
     __device__ __forceinline__ uint32_t timestep(uint32_t s, uint32_t) const { return s >> 16; }
@@ -42,7 +44,18 @@ struct TableStepper {
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
             // jr = mulhi(w, 100) is the table column; (w & 3) * 4 the byte offset of the start observation
-            const TblOut o = table_step(c, s[e], philox_jr(word[e]), (word[e] << 2) & 0xCu);
+            uint32_t jr = philox_jr(word[e]);
+            if (POLICY) {
+                // SIM:187-188: a table policy picks the player's action from the CURRENT observation;
+                // the other player's action and the 2-bit step draw stay the Philox ones
+                const uint32_t cur = min(s[e] & 0xFFFFu, c.last / 100u);
+                uint32_t aa, ab;
+                philox_actions(word[e], aa, ab);
+                if (pol_a) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(aa) : "r"(pol_a + cur));
+                if (pol_b) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(ab) : "r"(pol_b + cur));
+                jr = aa * 20u + ab * 4u + (jr & 3u);
+            }
+            const TblOut o = table_step(c, s[e], jr, (word[e] << 2) & 0xCu);
             s[e] = o.state; oo[e] = o.obs; rr[e] = __float_as_uint((float)o.rew_i); ff[e] = o.flags;
             net += o.rew_i;
         }
@@ -221,9 +234,12 @@ __device__ __forceinline__ void rollout_body(const Stepper& S, const RolloutArgs
     }
 }
 
-template <int VEC, bool STREAMS>
+// Shared-memory image: the table, the 4 start observations (16 bytes), then - POLICY only - the two int8[nS]
+// table policies (each padded to 16 bytes; an absent one is not copied and its address stays 0).
+template <int VEC, bool STREAMS, bool POLICY>
 __global__ void __launch_bounds__(kRolloutThreads, 1)
-k_rollout_table(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t table_bytes, const RolloutArgs a)
+k_rollout_table(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t table_bytes,
+                const int8_t* __restrict__ policy_a, const int8_t* __restrict__ policy_b, const RolloutArgs a)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar;
@@ -231,8 +247,19 @@ k_rollout_table(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t 
     __shared__ int blk_net;
     if (threadIdx.x < 4) blk_stats[threadIdx.x] = 0;
     if (threadIdx.x == 4) blk_net = 0;
-    stage_table(smem_raw, gtable, table_bytes, &bar, P);
-    TableStepper S;
+    TableStepper<POLICY> S;
+    S.pol_a = S.pol_b = 0;
+    if (POLICY) {
+        const uint32_t pol_bytes = ((uint32_t)P.nS + 15u) & ~15u;
+        uint8_t* pa = smem_raw + table_bytes + 16, *pb = pa + pol_bytes;
+        for (int i = threadIdx.x; i < P.nS; i += blockDim.x) {
+            if (policy_a) pa[i] = (uint8_t)min(max((int)policy_a[i], 0), 4);      // keep the column inside the row
+            if (policy_b) pb[i] = (uint8_t)min(max((int)policy_b[i], 0), 4);
+        }
+        if (policy_a) S.pol_a = smem_u32(pa);
+        if (policy_b) S.pol_b = smem_u32(pb);
+    }
+    stage_table(smem_raw, gtable, table_bytes, &bar, P);      // ends with __syncthreads(): policies visible
     S.c = make_ctx(smem_raw, table_bytes, P);
     wait_table(&bar);
     rollout_body<VEC, STREAMS>(S, a, blk_stats, &blk_net);

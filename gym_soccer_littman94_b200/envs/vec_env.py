@@ -334,11 +334,10 @@ class SoccerVecEnv:
         with torch.cuda.device(dev):
             st = _stream(dev)
             if self.kernel == "table":
-                if pa is not None or pb is not None:
-                    raise NotImplementedError("kernel='table' rollouts use the uniform random policy")
-                check(self.lib.soccer_rollout_table(C.byref(self.pitch), _ptr(self.table), _ptr(self.state), self.seed,
-                                                    self.step_count, int(K), self.env_id_base, _ptr(obs), _ptr(reward),
-                                                    _ptr(flags), _ptr(stats), n, st), "soccer_rollout_table")
+                check(self.lib.soccer_rollout_table_policy(
+                    C.byref(self.pitch), _ptr(self.table), _ptr(self.state), _ptr(pa), _ptr(pb), self.seed,
+                    self.step_count, int(K), self.env_id_base, _ptr(obs), _ptr(reward), _ptr(flags), _ptr(stats), n, st),
+                    "soccer_rollout_table_policy")
             else:
                 check(self.lib.soccer_rollout(C.byref(self.pitch), _ptr(self.state), _ptr(pa), _ptr(pb), self.seed,
                                               self.step_count, int(K), self.env_id_base, _ptr(obs), _ptr(reward),

@@ -227,6 +227,14 @@ int soccer_rollout_table(const soccer_pitch *pitch, const uint16_t *table, uint3
                          uint64_t seed, uint64_t step0, int32_t K, uint64_t env_id_base,
                          int32_t *obs, float *reward, uint8_t *flags, unsigned long long *stats,
                          int64_t n, soccer_stream_t stream);
+/* the same with on-device table policies (int8[nS] each, NULL = uniform random from the Philox
+ * word, SIM:187-188 semantics as in soccer_rollout); the policies ride in shared memory next to
+ * the table */
+int soccer_rollout_table_policy(const soccer_pitch *pitch, const uint16_t *table, uint32_t *state,
+                                const int8_t *policy_a, const int8_t *policy_b, uint64_t seed,
+                                uint64_t step0, int32_t K, uint64_t env_id_base, int32_t *obs,
+                                float *reward, uint8_t *flags, unsigned long long *stats,
+                                int64_t n, soccer_stream_t stream);
 /* translate a state tensor between layouts (in place allowed); goal / needs_reset states map
  * to observation 0 in the INDEX layout and cannot be converted back */
 int soccer_convert_state(const soccer_pitch *pitch, const uint32_t *in, uint32_t *out,

@@ -1,6 +1,6 @@
 """Short driver for ncu captures: a few launches of each hot kernel at its bench size.
 
-    python profiles/run_kernels.py [k1_table|k1_rules|k2_table|k2_rules|all] [--envs N]
+    python profiles/run_kernels.py [k1_table|k1_rules|k2_table|k2_rules|replay|all] [--envs N]
 """
 import argparse
 import os
@@ -34,11 +34,23 @@ def k2(kernel, n, K, iters):
     torch.cuda.synchronize()
 
 
+def replay(kernel, n, T, iters):
+    dev = torch.device("cuda", 0)
+    env = SoccerVecEnv(n, device=dev, kernel=kernel, want_reset_obs=False)
+    a, b, r = (torch.randint(0, hi, (T, n), dtype=torch.uint8, device=dev) for hi in (5, 5, 16))
+    out = (torch.empty((T, n), dtype=torch.int32, device=dev), torch.empty((T, n), dtype=torch.float32, device=dev),
+           torch.empty((T, n), dtype=torch.uint8, device=dev), None)
+    env.reset(r[0])
+    for _ in range(iters):
+        env.step_many(a, b, r, out=out)
+    torch.cuda.synchronize()
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("what", nargs="?", default="all")
     ap.add_argument("--envs", type=int, default=1 << 24)
-    ap.add_argument("--iters", type=int, default=6)
+    ap.add_argument("--iters", type=int, default=3)
     args = ap.parse_args()
     if args.what in ("k1_table", "all"):
         k1("table", args.envs, args.iters)
@@ -48,4 +60,7 @@ if __name__ == "__main__":
         k2("table", 1 << 20, 64, args.iters)
     if args.what in ("k2_rules", "all"):
         k2("rules", 1 << 20, 64, args.iters)
+    if args.what in ("replay", "all"):
+        replay("table", 1 << 22, 64, 3)
+        replay("table", 4096, 4000, 3)
     print("done")

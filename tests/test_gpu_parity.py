@@ -378,20 +378,25 @@ def test_rollout_philox_vs_oracle(dev, oracle, kernel):
     assert np.array_equal(env.current_obs().cpu().numpy(), m.obs_from_states(states))
 
 
-def test_rollout_table_policy_and_ragged(dev, oracle):
-    """Table policies for both players (utils/policies.py format) and N % 4 != 0."""
+@pytest.mark.parametrize("kernel", ["rules", "table"])
+@pytest.mark.parametrize("N,which", [(1023, "ab"), (1024, "a"), (2048, "b"), (77, "ab")])
+def test_rollout_table_policy_and_ragged(dev, oracle, kernel, N, which):
+    """Table policies for one or both players (utils/policies.py format), vector and N % 4 != 0
+    shapes, through the rules K2 and the shared-memory-table K2 (policies ride next to the table)."""
     from gym_soccer_littman94_b200.envs import SoccerVecEnv
-    N, K, seed = 1023, 120, 99
+    K, seed = 120, 99
     m = oracle.OracleModel(5, 4, 0.0)
     rs = np.random.RandomState(5)
-    pa, pb = rs.randint(0, 5, m.nS).astype(np.int8), rs.randint(0, 5, m.nS).astype(np.int8)
-    env = SoccerVecEnv(N, device=dev, rng_mode="philox", kernel="rules", seed=seed)
+    pa = rs.randint(0, 5, m.nS).astype(np.int8) if "a" in which else None
+    pb = rs.randint(0, 5, m.nS).astype(np.int8) if "b" in which else None
+    env = SoccerVecEnv(N, device=dev, rng_mode="philox", kernel=kernel, seed=seed)
     states = m.states_from_obs(env.reset().cpu().numpy())
     ts = np.zeros(N, np.int32)
     eo, er, ef, es = m.rollout_philox(states, ts, K, seed, policy_a=pa, policy_b=pb, n_threads=4)
     obs, rew, flg, stats = env.rollout(K, policy_a=pa, policy_b=pb)
     assert np.array_equal(obs.cpu().numpy(), eo) and np.array_equal(rew.cpu().numpy(), er)
     assert np.array_equal(flg.cpu().numpy(), ef) and np.array_equal(stats.cpu().numpy(), es)
+    assert np.array_equal(env.current_obs().cpu().numpy(), m.obs_from_states(states))
 
 
 @pytest.mark.parametrize("w,h,n", [(5, 4, 516), (7, 5, 203)])
