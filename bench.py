@@ -162,6 +162,20 @@ def run_reference(args):
     }))
 
 
+def host_info():
+    model = "?"
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    model = line.split(":", 1)[1].strip()
+                    break
+    except OSError:
+        pass
+    import numpy
+    return {"cpu": model, "logical_cpus": os.cpu_count(), "python": sys.version.split()[0], "numpy": numpy.__version__}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -320,6 +334,17 @@ def run_ours(args):
             if world > 1:
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item()) / L3
+            ar_us = None
+            if world > 1:                       # the one collective of the path, timed on its own
+                tmp = st3.clone()
+                dist.all_reduce(tmp)
+                barrier()
+                s0.record()
+                for _ in range(10):
+                    dist.all_reduce(tmp)
+                s1.record()
+                barrier()
+                ar_us = s0.elapsed_time(s1) * 100.0
             scratch = e3.state.clone()
 
             def rprobe():
@@ -341,7 +366,7 @@ def run_ours(args):
             rollouts[tag] = {"kernel": e3.kernel, "launches": L3, "ms_per_launch": ms, "env_steps_per_s": v3,
                              "per_gpu_hbm_gbs_at_9.125B": gbs, "frac_of_hbm_peak": gbs / peak,
                              "write_mix_probe_gbs": pgbs, "kernel_over_probe": gbs / pgbs,
-                             "stats_allreduce": [int(x) for x in st3.cpu()],
+                             "stats_allreduce": [int(x) for x in st3.cpu()], "allreduce_us": ar_us,
                              "note": "max over ranks; the all-reduce of the statistics vector is inside the timed region"}
             del e3, bufs, scratch
     except Exception as e:  # noqa: BLE001
@@ -434,7 +459,7 @@ def run_ours(args):
                                           "what": "k_stream_mix_probe: K1's streams, access pattern and launch shape "
                                                   "without the game logic = practical ceiling for its 7 B read / "
                                                   "13 B written mix"}},
-        "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": 1, "kind": "port", "sample": cpu_sample,
+        "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": 1, "kind": "port", "sample": cpu_sample, "host": host_info(),
                          "all_cores": {"value": cpu_all_v, "cores": cores}},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 3 * N, "d2h_bytes_per_step": 4 * N,
                 "steps": Ke, "checksum": checksum, "chunks": args.chunks,

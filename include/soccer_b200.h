@@ -240,10 +240,14 @@ int soccer_rollout_table_policy(const soccer_pitch *pitch, const uint16_t *table
 int soccer_convert_state(const soccer_pitch *pitch, const uint32_t *in, uint32_t *out,
                          int32_t to_layout, int64_t n, soccer_stream_t stream);
 
-/* T consecutive lock-steps from [T][n] action / draw arrays into [T][n] output arrays, enqueued
- * by ONE call (T kernel launches back to back: no per-step host round trip; the whole call can be
- * captured into a CUDA graph).  table == NULL -> rules kernel on CELL-layout states, else the table
- * kernel on INDEX-layout states.  slip_prob must be 0.  reset_obs optional. */
+/* T consecutive lock-steps -- the reference's `for t in range(T): env.step(actions[t])` replay loop
+ * (SIM:375-408, with reset() SIM:410-424 fused wherever an episode ended) -- from [T][n] action /
+ * draw arrays into [T][n] output arrays in ONE kernel launch: the state word stays in registers for
+ * the T steps (k_replay / k_replay_table), so an env-step moves 3 bytes in and 9 out (12 + 8/T)
+ * instead of K1's 20, and a small batch pays one dependent table look-up per step instead of one
+ * launch.  Bit-identical to T calls of soccer_step / soccer_step_table.  table == NULL -> rules
+ * kernel on CELL-layout states, else the table kernel on INDEX-layout states.  slip_prob must be 0.
+ * reset_obs optional.  T == 1 forwards to the single-step entry points. */
 int soccer_step_many(const soccer_pitch *pitch, const uint16_t *table, uint32_t *state, int32_t T,
                      const uint8_t *act_a, const uint8_t *act_b, const uint8_t *rng8, int32_t *obs,
                      float *reward, uint8_t *flags, int32_t *reset_obs, int64_t n,
