@@ -380,6 +380,29 @@ def run_ours(args):
     # ---------------- extra: BASELINE config 2 (reported, not the headline)
     extra = dict(rollouts)
     try:
+        # BASELINE config 1 through the single-env drop-in (the reference's own loop): every
+        # step() is one kernel launch on a 1-env batch + a stream synchronize, the draws come from
+        # np.random.RandomState like the reference's
+        import numpy as np
+        from gym_soccer_littman94_b200.envs import SoccerSimultaneousEnv
+        c1 = {}
+        for mode in ("zero_copy", "staged"):
+            os.environ["SOCCER_B200_SINGLE_ENV_STAGED"] = "1" if mode == "staged" else "0"
+            e1 = SoccerSimultaneousEnv(5, 4, slip_prob=0.0, seed=0, device=dev)
+            acts = np.random.RandomState(123).randint(0, 5, (20000, 2))
+            e1.reset()
+            t0 = time.perf_counter()
+            n_ep = 0
+            for aa, ab in acts:
+                _, _, dn, tr, _ = e1.step({'player_a': int(aa), 'player_b': int(ab)})
+                if dn['player_a'] or tr['player_a']:
+                    e1.reset()
+                    n_ep += 1
+            c1[mode] = {"steps_per_s": len(acts) / (time.perf_counter() - t0), "episodes": n_ep}
+        os.environ.pop("SOCCER_B200_SINGLE_ENV_STAGED", None)
+        extra["config1_single_env_dropin"] = dict(c1, note="20,000 step() calls of ONE env through the reference's class "
+                                                  "surface; latency-bound (one launch + sync per step), reported next to "
+                                                  "the reference's 29.6 k steps/s Python loop (BASELINE.md)")
         n2, T2 = 4096, 1000
         e2 = SoccerVecEnv(n2, device=dev, kernel="auto", want_reset_obs=False)
         a, b, r = (torch.randint(0, hi, (T2, n2), dtype=torch.uint8, device=dev) for hi in (5, 5, 16))

@@ -21,6 +21,7 @@ P / P_readable / Pmat / Rmat are built lazily from the sweep and dense kernels (
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -92,8 +93,21 @@ class SoccerSimultaneousEnv:
         self._dbuf = torch.zeros(self._BUF_BYTES, dtype=torch.uint8, device=self.device)
         self._hbuf = torch.zeros(self._BUF_BYTES, dtype=torch.uint8).pin_memory()
         self._hnp = self._hbuf.numpy()
+        self._staged = os.environ.get("SOCCER_B200_SINGLE_ENV_STAGED", "0") == "1"
+        # typed views of the mailbox fields and per-call objects built once: step() is latency-bound
+        # (one launch + one synchronize), so the host side is kept to a handful of scalar stores
+        h = self._hnp
+        self._v_u = h[self._OFF_U:self._OFF_U + 8].view(np.float64)
+        self._v_state = h[self._OFF_STATE:self._OFF_STATE + 4].view(np.uint32)
+        self._v_obs = h[self._OFF_OBS:self._OFF_OBS + 4].view(np.int32)
+        self._v_reward = h[self._OFF_REWARD:self._OFF_REWARD + 4].view(np.float32)
+        self._step_args = None
+        self._round_cache = {}
         self._pol_a = self._policy_tensor(player_a_policy)
         self._pol_b = self._policy_tensor(player_b_policy)
+        self._stream = torch.cuda.Stream(device=self.device)
+        self._stream_ptr = C.c_void_p(self._stream.cuda_stream)
+        torch.cuda.synchronize(self.device)      # mailbox zero-fill and policy uploads done before the first launch
 
         self._tables = None     # lazily built (P, P_readable)
         self._dense = None      # lazily built (Pmat, Rmat)
@@ -166,12 +180,23 @@ class SoccerSimultaneousEnv:
 
     # ------------------------------------------------------------------ device round trip
     def _roundtrip(self, launch):
+        """One kernel launch per call.  The 32-byte mailbox is pinned host memory, which under
+        unified addressing the kernel reads and writes directly over PCIe (zero copy): one launch +
+        one stream synchronize instead of copy / launch / copy / synchronize.
+        SOCCER_B200_SINGLE_ENV_STAGED=1 restores the staged copies (A/B measurements)."""
         dev = self.device
-        with torch.cuda.device(dev):
-            self._dbuf.copy_(self._hbuf, non_blocking=True)
-            launch(C.c_void_p(torch.cuda.current_stream(dev).cuda_stream), self._dbuf.data_ptr())
-            self._hbuf.copy_(self._dbuf, non_blocking=True)
-            torch.cuda.current_stream(dev).synchronize()
+        if torch.cuda.current_device() != dev.index:
+            with torch.cuda.device(dev):
+                return self._roundtrip(launch)
+        cur = self._stream          # the env's own stream: everything it touches lives in the mailbox
+        if self._staged:
+            with torch.cuda.stream(cur):
+                self._dbuf.copy_(self._hbuf, non_blocking=True)
+                launch(self._stream_ptr, self._dbuf.data_ptr())
+                self._hbuf.copy_(self._dbuf, non_blocking=True)
+        else:
+            launch(self._stream_ptr, self._hbuf.data_ptr())
+        cur.synchronize()
 
     def reset(self, seed=None, options=None):
         if seed is not None:
@@ -224,13 +249,13 @@ class SoccerSimultaneousEnv:
 
         u = self.np_random.random()                                  # the one draw of SIM:395
         h = self._hnp
-        h[self._OFF_U:self._OFF_U + 8].view(np.float64)[0] = u
-        word = (self._state_word & self._STATE_MASK) | ((int(self.timestep) & 0xFF) << 16)
-        h[self._OFF_STATE:self._OFF_STATE + 4].view(np.uint32)[0] = word
+        self._v_u[0] = u
+        self._v_state[0] = (self._state_word & self._STATE_MASK) | ((int(self.timestep) & 0xFF) << 16)
         h[self._OFF_ACT_A], h[self._OFF_ACT_B] = aa, ab
         h[self._OFF_RNG8] = min(int(u * 4.0), 3)                     # floor(4u): exact 2-bit form of u
 
-        def launch(stream, base):
+        if self._step_args is None:
+            base = self._dbuf.data_ptr() if self._staged else self._hbuf.data_ptr()
             a = StepArgs()
             a.state = base + self._OFF_STATE
             a.act_a = None if self._pol_a is not None else base + self._OFF_ACT_A
@@ -242,12 +267,16 @@ class SoccerSimultaneousEnv:
             a.obs, a.reward, a.flags = base + self._OFF_OBS, base + self._OFF_REWARD, base + self._OFF_FLAGS
             a.reset_obs = None
             a.n, a.auto_reset, a.use_philox, a.detail = 1, 0, 0, 1
-            check(self._lib.soccer_step_ex(C.byref(self._pitch), C.byref(a), stream), "soccer_step_ex")
+            self._step_args = (a, C.byref(a), C.byref(self._pitch))
+        _, a_ref, p_ref = self._step_args
+
+        def launch(stream, base):
+            check(self._lib.soccer_step_ex(p_ref, a_ref, stream), "soccer_step_ex")
         self._roundtrip(launch)
 
-        new_word = int(h[self._OFF_STATE:self._OFF_STATE + 4].view(np.uint32)[0])
-        obs = int(h[self._OFF_OBS:self._OFF_OBS + 4].view(np.int32)[0])
-        reward = float(h[self._OFF_REWARD:self._OFF_REWARD + 4].view(np.float32)[0])
+        new_word = int(self._v_state[0])
+        obs = int(self._v_obs[0])
+        reward = float(self._v_reward[0])
         flags = int(h[self._OFF_FLAGS])
         done = bool(flags & 1)
         prob = self._mp[(flags >> 4) & 0xF] * (1.0, 0.5, 0.25)[(flags >> 2) & 3]   # mp * nsp, SIM:241
@@ -261,7 +290,10 @@ class SoccerSimultaneousEnv:
             rewards['player_b'] *= -1
         dones = {a: done for a in self.return_agent}
         truncateds = {a: self.timestep >= 100 for a in self.return_agent}
-        infos = {a: {"p": np.round(prob, 2)} for a in self.return_agent}
+        p2 = self._round_cache.get(prob)
+        if p2 is None:
+            p2 = self._round_cache[prob] = np.round(prob, 2)         # SIM:405; a handful of distinct values
+        infos = {a: {"p": p2} for a in self.return_agent}
         self.needs_reset = any(dones.values()) or any(truncateds.values())
         return self.observations, rewards, dones, truncateds, infos
 
