@@ -13,6 +13,7 @@ from __future__ import annotations
 import ctypes as C
 from typing import Optional
 
+import numpy as np
 import torch
 
 from .. import _lib
@@ -220,6 +221,51 @@ class SoccerVecEnv:
                 check(self.lib.soccer_step_ex(C.byref(self.pitch), C.byref(a), st), "soccer_step_ex")
         self.step_count += 1
         return obs, reward, flags, reset_obs
+
+    # ------------------------------------------------------------------ the reference's dict-shaped surface, batched
+    def reset_dict(self, seed=None, options=None, rng8: Optional[torch.Tensor] = None):
+        """reset() with the reference's signature and return shape (SIM:410-424): (obs_dict, info_dict) keyed by
+        agent, every value an [N] tensor.  `seed` reseeds like the reference's reset(seed) (Philox key)."""
+        if seed is not None:
+            self.seed = int(seed)
+        obs = self.reset(rng8)
+        p = torch.full((self.num_envs,), float(np.round(1.0 / self.info.n_isd, 2)), dtype=torch.float64,
+                       device=self.device)
+        return {a: obs for a in self.return_agent}, {a: {"p": p} for a in self.return_agent}
+
+    def step_dict(self, action: dict, rng8: Optional[torch.Tensor] = None, rng32: Optional[torch.Tensor] = None):
+        """step() with the reference's signature and return shape (SIM:375-408) for the whole batch:
+        `action` = {'player_a': uint8[N], 'player_b': uint8[N]} (one key in the single-agent modes); returns
+        (obs, rewards, dones, truncateds, infos) dicts keyed by agent whose values are [N] tensors -- obs int32
+        (0 on a goal, like the reference), rewards float32 (B = -A in the multi-agent case, SIM:401-402), dones /
+        truncateds bool, infos {"p": float64 probability of the realised outcome rounded to 2 places, SIM:405}
+        (kernel="rules" only; the table kernel does not track it).  Episodes restart by themselves: the
+        observation a finished env continues from is `self.reset_obs`."""
+        assert isinstance(action, dict), "Action must be a dictionary"
+        assert len(action) == 1 or len(action) == 2, "Action must be a dictionary of length 1 or 2"
+        assert self.policy_a is not None or 'player_a' in action, "A policy for player_a must be provided"
+        assert self.policy_b is not None or 'player_b' in action, "A policy for player_b must be provided"
+        if self.multiagent:
+            assert len(action) == 2, "Action must be a dictionary of length 2 for multiagent case"
+        else:
+            assert len(action) == 1, "Action must be a dictionary of length 1 for single agent case"
+        detail = self.kernel == "rules"
+        obs, reward, flags, _ = self.step(action.get('player_a'), action.get('player_b'), rng8=rng8, rng32=rng32,
+                                          detail=detail)
+        rewards = {a: reward for a in self.return_agent}
+        if self.multiagent:
+            rewards['player_b'] = -reward
+        done, trunc = (flags & 1).bool(), (flags & 2).bool()
+        infos = {a: {} for a in self.return_agent}
+        if detail:
+            if getattr(self, "_p_lut", None) is None:
+                mp = [self.info.slip_combo_prob[c] for c in range(9)] + [0.0] * 7
+                lut = [float(np.round(mp[i >> 2] * (1.0, 0.5, 0.25, 0.0)[i & 3], 2)) for i in range(64)]   # SIM:241, 405
+                self._p_lut = torch.tensor(lut, dtype=torch.float64, device=self.device)
+            p = self._p_lut[(flags >> 2).long()]
+            infos = {a: {"p": p} for a in self.return_agent}
+        return ({a: obs for a in self.return_agent}, rewards, {a: done for a in self.return_agent},
+                {a: trunc for a in self.return_agent}, infos)
 
     def step_many(self, act_a: torch.Tensor, act_b: torch.Tensor, rng8: torch.Tensor, out=None):
         """T lock-steps from [T, N] uint8 CUDA tensors, enqueued by one C call (no per-step Python

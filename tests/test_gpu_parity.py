@@ -142,6 +142,44 @@ def test_step_injected_matches_reference(dev, tag):
     assert np.array_equal(rob, g["reset_obs"])
 
 
+@pytest.mark.parametrize("tag", golden_tags("rollout"))
+def test_step_dict_api_matches_reference(dev, tag):
+    """The reference-shaped batched surface (reset_dict / step_dict): dict keys, reward sign of player B
+    (SIM:401-402), bool dones / truncateds and info["p"] (SIM:405) against the replayed reference."""
+    from gym_soccer_littman94_b200.envs import SoccerVecEnv
+    g = load_golden("rollout", tag)
+    kw, mode = _env_kwargs(tag, g)
+    T, N = g["act_a"].shape
+    T = min(T, 150)
+    env = SoccerVecEnv(N, device=dev, rng_mode="injected", kernel="rules", **kw)
+    obs0, info0 = env.reset_dict(rng8=_t((g["init_rng"] & 3) << 2, dev))
+    agents = {"multi": ["player_a", "player_b"], "a_free": ["player_a"], "b_free": ["player_b"]}[mode]
+    assert list(obs0) == agents and list(info0) == agents
+    assert np.array_equal(obs0[agents[0]].cpu().numpy(), g["init_obs"])
+    for t in range(T):
+        if mode == "multi":
+            action = {"player_a": _t(g["act_a"][t], dev), "player_b": _t(g["act_b"][t], dev)}
+        else:
+            action = {agents[0]: _t(g["act_a"][t], dev)}
+        rng32 = _t(g["rng32"][t].view(np.int32), dev) if "rng32" in g else None
+        obs, rew, dones, truncs, infos = env.step_dict(action, rng8=_t(g["rng8"][t], dev), rng32=rng32)
+        assert list(obs) == agents and list(rew) == agents and list(dones) == agents and list(infos) == agents
+        a0 = agents[0]
+        assert np.array_equal(obs[a0].cpu().numpy(), g["obs"][t])
+        assert np.array_equal(rew[a0].cpu().numpy(), g["reward"][t])
+        if mode == "multi":
+            assert np.array_equal(rew["player_b"].cpu().numpy(), -g["reward"][t])
+        assert dones[a0].dtype == torch.bool and truncs[a0].dtype == torch.bool
+        assert np.array_equal(dones[a0].cpu().numpy(), (g["flags"][t] & 1).astype(bool))
+        assert np.array_equal(truncs[a0].cpu().numpy(), (g["flags"][t] & 2).astype(bool))
+        assert np.array_equal(infos[a0]["p"].cpu().numpy(), g["info_p"][t]), t
+        assert np.array_equal(env.reset_obs.cpu().numpy(), g["reset_obs"][t])
+    with pytest.raises(AssertionError):
+        env.step_dict([0, 1])
+    with pytest.raises(AssertionError):
+        env.step_dict({})
+
+
 def test_step_table_kernel_matches_reference(dev):
     g = load_golden("rollout", "5x4_s000_multi")
     obs, rew, flg, rob = _run_vec(dev, g, dict(width=5, height=4, slip_prob=0.0), "table")
