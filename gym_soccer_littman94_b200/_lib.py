@@ -24,7 +24,7 @@ EXPORTS = (
     "soccer_rollout", "soccer_sweep", "soccer_dense", "soccer_build_step_table", "soccer_step_table",
     "soccer_rollout_table", "soccer_step_table_bytes_host", "soccer_convert_state", "soccer_step_stats",
     "soccer_step_host", "soccer_step_host_scratch_bytes_host", "soccer_step_many", "soccer_bench_stream_mix",
-    "soccer_bench_rollout_probe", "soccer_rollout_table_policy",
+    "soccer_bench_rollout_probe", "soccer_rollout_table_policy", "soccer_step_table_slip",
 )
 
 
@@ -125,6 +125,7 @@ def lib():
         "soccer_step_table": [PP, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp],
         "soccer_rollout_table": [PP, vp, vp, u64, u64, i32, u64, vp, vp, vp, vp, i64, vp],
         "soccer_rollout_table_policy": [PP, vp, vp, vp, vp, u64, u64, i32, u64, vp, vp, vp, vp, i64, vp],
+        "soccer_step_table_slip": [PP, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp],
         "soccer_convert_state": [PP, vp, vp, i32, i64, vp],
         "soccer_step_stats": [vp, vp, i64, vp, vp],
         "soccer_step_host": [PP, C.POINTER(StepHostArgs)],

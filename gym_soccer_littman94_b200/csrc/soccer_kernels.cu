@@ -169,12 +169,22 @@ __device__ __forceinline__ void step_group(const PitchDev& P, const Isd4& I, con
     if (RESET_OBS) st_stream(rob + g, make_uint4(o.robs[0], o.robs[1], o.robs[2], o.robs[3]));
 }
 
-template <bool RESET_OBS>
+// Philox draws of the 4 envs of a group as rng8-compatible bytes (soccer_step_philox: K1 with on-device draws)
+struct PhiloxKey { uint64_t seed, step, env_id_base; };
+__device__ __forceinline__ uint32_t philox_rng8x4(const PhiloxKey& k, int64_t g)
+{
+    uint32_t r[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) r[e] = philox_rng8(philox_word(k.seed, k.env_id_base + (uint64_t)(4 * g + e), k.step));
+    return pack4(r[0], r[1], r[2], r[3]);
+}
+
+template <bool RESET_OBS, bool PHILOX = false>
 __global__ void __launch_bounds__(kThreads)
 k_step_fast(const PitchDev P, uint32_t* __restrict__ state, const uint8_t* __restrict__ act_a,
             const uint8_t* __restrict__ act_b, const uint8_t* __restrict__ rng, int32_t* __restrict__ obs,
             float* __restrict__ reward, uint8_t* __restrict__ flags, int32_t* __restrict__ reset_obs,
-            int64_t n_groups)
+            int64_t n_groups, const PhiloxKey key = PhiloxKey())
 {
     __shared__ __align__(16) uint8_t lut[kLutBytes];
     pdl_launch_dependents();
@@ -195,9 +205,11 @@ k_step_fast(const PitchDev P, uint32_t* __restrict__ state, const uint8_t* __res
     for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_groups; g += 2 * stride) {
         const int64_t g2 = g + stride;
         const bool two = g2 < n_groups;
-        const Group4 x0 = load_group(st4, a4, b4, r4, g);
+        // PHILOX: the draw stream is not read (r4 aliases the action stream, its value is replaced)
+        Group4 x0 = load_group(st4, a4, b4, PHILOX ? a4 : r4, g);
         Group4 x1 = x0;
-        if (two) x1 = load_group(st4, a4, b4, r4, g2);
+        if (two) x1 = load_group(st4, a4, b4, PHILOX ? a4 : r4, g2);
+        if (PHILOX) { x0.r = philox_rng8x4(key, g); if (two) x1.r = philox_rng8x4(key, g2); }
         step_group<RESET_OBS>(P, I, lut, x0, g, st4, o4, w4, f4, q4);
         if (two) step_group<RESET_OBS>(P, I, lut, x1, g2, st4, o4, w4, f4, q4);
     }
@@ -406,7 +418,7 @@ k_get_obs(const PitchDev P, const uint32_t* __restrict__ state, int32_t* __restr
 int table_bytes_of(const PitchDev& P, int64_t* bytes)
 {
     const int64_t nS = 1 + 2 * (int64_t)P.F * P.Fm1;
-    if (nS - 1 > kMaxTableStates || P.slip) return SOCCER_ETABLE;
+    if (nS - 1 > kMaxTableStates) return SOCCER_ETABLE;      // the table itself does not depend on slip_prob
     *bytes = (nS * 200 + 15) / 16 * 16;     // nS rows: row 0 is the absorbing terminal observation
     return SOCCER_OK;
 }
@@ -696,23 +708,42 @@ int soccer_step_ex(const soccer_pitch* pitch, const soccer_step_args* a, soccer_
     cudaStream_t st = (cudaStream_t)stream;
 
     if (a->reserved != 0) return SOCCER_EINVAL;
-    const bool fast_ok = !P.slip && !a->use_philox && a->auto_reset && !a->detail && !a->policy_a && !a->policy_b &&
+    const bool fast_ok = !P.slip && a->auto_reset && !a->detail && !a->policy_a && !a->policy_b &&
                          a->obs && a->reward && a->flags && a->n >= 4 &&
                          aligned(a->state, 16) && aligned(a->obs, 16) && aligned(a->reward, 16) &&
                          (!a->reset_obs || aligned(a->reset_obs, 16)) && aligned(a->act_a, 4) &&
-                         aligned(a->act_b, 4) && aligned(a->rng8, 4) && aligned(a->flags, 4);
+                         aligned(a->act_b, 4) && (a->use_philox || aligned(a->rng8, 4)) && aligned(a->flags, 4);
     int64_t done_n = 0;
-    if (fast_ok) {
+    if (fast_ok && a->use_philox) {
+        // K1 with on-device Philox draws (soccer_step_philox): same byte-parallel kernel, 19 B / env-step
+        const int64_t n_groups = a->n / 4;
+        const PhiloxKey key = { a->seed, a->step, a->env_id_base };
+        if (a->reset_obs) {
+            static const int nb = resident_blocks(k_step_fast<true, true>);
+            const int e1 = launch_pdl(k_step_fast<true, true>, grid_for(n_groups, nb), kThreads, 0, st, P, a->state, a->act_a,
+                                      a->act_b, (const uint8_t*)nullptr, a->obs, a->reward, a->flags, a->reset_obs, n_groups, key);
+            if (e1) return e1;
+        } else {
+            static const int nb = resident_blocks(k_step_fast<false, true>);
+            const int e1 = launch_pdl(k_step_fast<false, true>, grid_for(n_groups, nb), kThreads, 0, st, P, a->state, a->act_a,
+                                      a->act_b, (const uint8_t*)nullptr, a->obs, a->reward, a->flags, (int32_t*)nullptr, n_groups, key);
+            if (e1) return e1;
+        }
+        const int e = launch_status();
+        if (e) return e;
+        done_n = n_groups * 4;
+        if (done_n == a->n) return SOCCER_OK;
+    } else if (fast_ok) {
         const int64_t n_groups = a->n / 4;
         if (a->reset_obs) {
             static const int nb = resident_blocks(k_step_fast<true>);
             const int e1 = launch_pdl(k_step_fast<true>, grid_for(n_groups, nb), kThreads, 0, st,
-                                      P, a->state, a->act_a, a->act_b, a->rng8, a->obs, a->reward, a->flags, a->reset_obs, n_groups);
+                                      P, a->state, a->act_a, a->act_b, a->rng8, a->obs, a->reward, a->flags, a->reset_obs, n_groups, PhiloxKey());
             if (e1) return e1;
         } else {
             static const int nb = resident_blocks(k_step_fast<false>);
             const int e1 = launch_pdl(k_step_fast<false>, grid_for(n_groups, nb), kThreads, 0, st,
-                                      P, a->state, a->act_a, a->act_b, a->rng8, a->obs, a->reward, a->flags, (int32_t*)nullptr, n_groups);
+                                      P, a->state, a->act_a, a->act_b, a->rng8, a->obs, a->reward, a->flags, (int32_t*)nullptr, n_groups, PhiloxKey());
             if (e1) return e1;
         }
         const int e = launch_status();
@@ -820,6 +851,7 @@ int soccer_step_table(const soccer_pitch* pitch, const uint16_t* table, uint32_t
                       int32_t* reset_obs, int64_t n, soccer_stream_t stream)
 {
     if (!table || !state || !act_a || !act_b || !rng8 || !obs || !reward || !flags || n < 0) return SOCCER_EINVAL;
+    if (pitch && pitch->slip_prob != 0.0) return SOCCER_ESLIP;          // soccer_step_table_slip takes the step draw
     PitchDev P; int rc = make_pitch_dev(pitch, &P); if (rc) return rc;
     int64_t bytes; rc = table_bytes_of(P, &bytes); if (rc) return rc;
     if (!aligned(table, 16)) return SOCCER_EINVAL;
@@ -856,6 +888,47 @@ int soccer_step_table(const soccer_pitch* pitch, const uint16_t* table, uint32_t
     return launch_status();
 }
 
+int soccer_step_table_slip(const soccer_pitch* pitch, const uint16_t* table, uint32_t* state, const uint8_t* act_a,
+                           const uint8_t* act_b, const uint8_t* rng8, const uint32_t* rng32, const double* rngf64,
+                           int32_t* obs, float* reward, uint8_t* flags, int32_t* reset_obs, int64_t n,
+                           soccer_stream_t stream)
+{
+    if (!table || !state || !act_a || !act_b || !rng8 || !obs || !reward || !flags || n < 0) return SOCCER_EINVAL;
+    if (!rng32 && !rngf64) return SOCCER_EINVAL;
+    PitchDev P; int rc = make_pitch_dev(pitch, &P); if (rc) return rc;
+    int64_t bytes; rc = table_bytes_of(P, &bytes); if (rc) return rc;
+    if (!aligned(table, 16)) return SOCCER_EINVAL;
+    if (n == 0) return SOCCER_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const void* draw = rngf64 ? (const void*)rngf64 : (const void*)rng32;
+    const bool vec = n >= 4 && aligned(state, 16) && aligned(obs, 16) && aligned(reward, 16) &&
+                     (!reset_obs || aligned(reset_obs, 16)) && aligned(act_a, 4) && aligned(act_b, 4) &&
+                     aligned(rng8, 4) && aligned(flags, 4) && aligned(draw, 16);
+    int64_t done_n = 0;
+    if (vec) {
+        const int64_t n_groups = n / 4;
+#define SOCCER_LAUNCH_SLIP_T(RO, F64)                                                                     \
+        do {                                                                                              \
+            const int e0 = allow_big_smem(k_step_table_slip<RO, F64>, bytes + 16);                        \
+            if (e0) return e0;                                                                            \
+            k_step_table_slip<RO, F64><<<table_grid(n_groups, kSlipThreads), kSlipThreads, (size_t)bytes + 16, st>>>(  \
+                P, table, (uint32_t)bytes, state, act_a, act_b, rng8, draw, obs, reward, flags, reset_obs, n_groups); \
+        } while (0)
+        if (reset_obs) { if (rngf64) SOCCER_LAUNCH_SLIP_T(true, true); else SOCCER_LAUNCH_SLIP_T(true, false); }
+        else { if (rngf64) SOCCER_LAUNCH_SLIP_T(false, true); else SOCCER_LAUNCH_SLIP_T(false, false); }
+#undef SOCCER_LAUNCH_SLIP_T
+        const int e = launch_status();
+        if (e) return e;
+        done_n = n_groups * 4;
+        if (done_n == n) return SOCCER_OK;
+    }
+    const int64_t k = done_n, m = n - k;
+    k_step_table_slip_scalar<<<grid_for(m, 8), kThreads, 0, st>>>(
+        P, table, state + k, act_a + k, act_b + k, rng8 + k, rngf64 ? nullptr : rng32 + k, rngf64 ? rngf64 + k : nullptr,
+        obs + k, reward + k, flags + k, reset_obs ? reset_obs + k : nullptr, m);
+    return launch_status();
+}
+
 int soccer_rollout_table_policy(const soccer_pitch* pitch, const uint16_t* table, uint32_t* state,
                                 const int8_t* policy_a, const int8_t* policy_b, uint64_t seed, uint64_t step0, int32_t K,
                                 uint64_t env_id_base, int32_t* obs, float* reward, uint8_t* flags,
@@ -872,23 +945,24 @@ int soccer_rollout_table_policy(const soccer_pitch* pitch, const uint16_t* table
     const RolloutArgs ra = { state, seed, step0, K, env_id_base, obs, reward, flags, stats, n };
     const bool streams = obs && reward && flags;
     const bool pol = policy_a || policy_b;
-    const int64_t smem = bytes + 16 + (pol ? 2 * ((P.nS + 15) & ~15) : 0);
-#define SOCCER_LAUNCH_ROLLOUT_T(VEC, STR, POL, ITEMS)                                                    \
+    const int64_t smem = bytes + 16 + ((pol || P.slip) ? 2 * ((P.nS + 15) & ~15) : 0);
+#define SOCCER_LAUNCH_ROLLOUT_T(VEC, STR, POL, SLIP, ITEMS)                                              \
     do {                                                                                                 \
-        const int e0 = allow_big_smem(k_rollout_table<VEC, STR, POL>, smem);                             \
+        const int e0 = allow_big_smem(k_rollout_table<VEC, STR, POL, SLIP>, smem);                       \
         if (e0) return e0;                                                                               \
-        k_rollout_table<VEC, STR, POL><<<table_grid(ITEMS, kRolloutThreads), kRolloutThreads, smem, st>>>( \
+        k_rollout_table<VEC, STR, POL, SLIP><<<table_grid(ITEMS, kRolloutThreads), kRolloutThreads, smem, st>>>( \
             P, table, (uint32_t)bytes, policy_a, policy_b, ra);                                          \
     } while (0)
-#define SOCCER_PICK_ROLLOUT_T(POL)                                                                       \
+#define SOCCER_PICK_ROLLOUT_T(POL, SLIP)                                                                 \
     do {                                                                                                 \
-        if (vec && streams) SOCCER_LAUNCH_ROLLOUT_T(4, true, POL, n / 4);                                \
-        else if (vec) SOCCER_LAUNCH_ROLLOUT_T(4, false, POL, n / 4);                                     \
-        else if (streams) SOCCER_LAUNCH_ROLLOUT_T(1, true, POL, n);                                      \
-        else SOCCER_LAUNCH_ROLLOUT_T(1, false, POL, n);                                                  \
+        if (vec && streams) SOCCER_LAUNCH_ROLLOUT_T(4, true, POL, SLIP, n / 4);                          \
+        else if (vec) SOCCER_LAUNCH_ROLLOUT_T(4, false, POL, SLIP, n / 4);                               \
+        else if (streams) SOCCER_LAUNCH_ROLLOUT_T(1, true, POL, SLIP, n);                                \
+        else SOCCER_LAUNCH_ROLLOUT_T(1, false, POL, SLIP, n);                                            \
     } while (0)
-    if (pol) SOCCER_PICK_ROLLOUT_T(true);
-    else SOCCER_PICK_ROLLOUT_T(false);
+    if (P.slip) SOCCER_PICK_ROLLOUT_T(true, true);       // slip: the policy-capable instantiation serves both
+    else if (pol) SOCCER_PICK_ROLLOUT_T(true, false);
+    else SOCCER_PICK_ROLLOUT_T(false, false);
 #undef SOCCER_PICK_ROLLOUT_T
 #undef SOCCER_LAUNCH_ROLLOUT_T
     return launch_status();

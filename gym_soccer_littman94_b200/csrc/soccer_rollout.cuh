@@ -29,33 +29,37 @@ struct RolloutArgs {
 // A variant of this stepper that moved the selects / shifts / compares onto the FMA pipe (mul.hi carries, IMAD
 // packing, 2^23 magic-add int -> float; ALU pipe 81 % -> 71 % busy) measured 2 % SLOWER on B200 in three A/B
 // runs: with 2^20+ envs the kernel sits at the HBM write ceiling (0.92-0.99 of the traffic probe), not on issue.
-template <bool POLICY>
+template <bool POLICY, bool SLIP>
 struct TableStepper {
     TblCtx c;
     uint32_t pol_a, pol_b;      // shared-window addresses of the int8[nS] table policies, 0 = uniform (POLICY only)
+    SlipCtx sc;                 // slip-combination probability table (SLIP only)
     __device__ __forceinline__ void unpack(uint32_t&, uint32_t&) const {}
     __device__ __forceinline__ uint32_t pack(uint32_t s, uint32_t) const { return s; }
     __device__ __forceinline__ uint32_t timestep(uint32_t s, uint32_t) const { return s >> 16; }
     template <int VEC>
     __device__ __forceinline__ void step(uint32_t* s, uint32_t*, const uint32_t* word, uint32_t* oo, uint32_t* rr,
-                                         uint32_t& fw, int32_t& net, uint64_t, uint64_t, uint64_t) const
+                                         uint32_t& fw, int32_t& net, uint64_t seed, uint64_t env0, uint64_t step_abs) const
     {
         uint32_t ff[4] = { 0, 0, 0, 0 };
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
             // jr = mulhi(w, 100) is the table column; (w & 3) * 4 the byte offset of the start observation
             uint32_t jr = philox_jr(word[e]);
-            if (POLICY) {
-                // SIM:187-188: a table policy picks the player's action from the CURRENT observation;
-                // the other player's action and the 2-bit step draw stay the Philox ones
-                const uint32_t cur = min(s[e] & 0xFFFFu, c.last / 100u);
-                uint32_t aa, ab;
+            uint32_t aa = 0, ab = 0;
+            if (POLICY || SLIP) {
                 philox_actions(word[e], aa, ab);
-                if (pol_a) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(aa) : "r"(pol_a + cur));
-                if (pol_b) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(ab) : "r"(pol_b + cur));
+                // SIM:187-188: a table policy picks the player's action from the CURRENT observation;
+                // the other player's action and the draws stay the Philox ones
+                const uint32_t cur = min(s[e] & 0xFFFFu, c.last / 100u);
+                if (POLICY && pol_a) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(aa) : "r"(pol_a + cur));
+                if (POLICY && pol_b) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(ab) : "r"(pol_b + cur));
                 jr = aa * 20u + ab * 4u + (jr & 3u);
             }
-            const TblOut o = table_step(c, s[e], jr, (word[e] << 2) & 0xCu);
+            // slip_prob > 0: the step draw is a 53-bit Philox uniform of a separate counter lane (as in k_rollout)
+            const TblOut o = SLIP ? table_step_slip(c, sc, s[e], aa, ab, philox_u53(seed, env0 + e, step_abs),
+                                                    (word[e] << 2) & 0xCu)
+                                  : table_step(c, s[e], jr, (word[e] << 2) & 0xCu);
             s[e] = o.state; oo[e] = o.obs; rr[e] = __float_as_uint((float)o.rew_i); ff[e] = o.flags;
             net += o.rew_i;
         }
@@ -236,7 +240,7 @@ __device__ __forceinline__ void rollout_body(const Stepper& S, const RolloutArgs
 
 // Shared-memory image: the table, the 4 start observations (16 bytes), then - POLICY only - the two int8[nS]
 // table policies (each padded to 16 bytes; an absent one is not copied and its address stays 0).
-template <int VEC, bool STREAMS, bool POLICY>
+template <int VEC, bool STREAMS, bool POLICY, bool SLIP>
 __global__ void __launch_bounds__(kRolloutThreads, 1)
 k_rollout_table(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t table_bytes,
                 const int8_t* __restrict__ policy_a, const int8_t* __restrict__ policy_b, const RolloutArgs a)
@@ -247,8 +251,11 @@ k_rollout_table(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t 
     __shared__ int blk_net;
     if (threadIdx.x < 4) blk_stats[threadIdx.x] = 0;
     if (threadIdx.x == 4) blk_net = 0;
-    TableStepper<POLICY> S;
+    TableStepper<POLICY, SLIP> S;
     S.pol_a = S.pol_b = 0;
+    __shared__ __align__(8) double prt[27];
+    S.sc.prt = 0; S.sc.first_k = 0;
+    if (SLIP) { slip_build_prt(prt, P); S.sc.prt = smem_u32(prt); S.sc.first_k = slip_first_k(P); }
     if (POLICY) {
         const uint32_t pol_bytes = ((uint32_t)P.nS + 15u) & ~15u;
         uint8_t* pa = smem_raw + table_bytes + 16, *pb = pa + pol_bytes;

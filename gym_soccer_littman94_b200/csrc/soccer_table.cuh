@@ -97,14 +97,10 @@ __device__ __forceinline__ void wait_table(uint64_t* bar)
 // One env-step through the table.  `jr` = (aa*5+ab)*4 + r (0..99), `rsel4` = 4 * reset draw.
 struct TblCtx { uint32_t tbl, isd, last; };    // shared-window addresses of the table / the isd words; last entry index
 struct TblOut { uint32_t state, obs, flags; int32_t rew_i; uint32_t reset_obs; };
-__device__ __forceinline__ TblOut table_step(const TblCtx& c, uint32_t s, uint32_t jr, uint32_t rsel4)
+// everything after the table look-up: observation, reward, done / truncated, fused reset (SIM:399-424, 493)
+__device__ __forceinline__ TblOut table_finish(const TblCtx& c, uint32_t s, int32_t e, uint32_t rsel4)
 {
-    // the clamp keeps a corrupt state word / action byte inside the table
-    const uint32_t idx = min((s & 0xFFFFu) * 100u + jr, c.last);
-    int32_t e;
     uint32_t ro;
-    // volatile: ordered after the (volatile) mbarrier wait that publishes the table
-    asm volatile("ld.shared.s16 %0, [%1];" : "=r"(e) : "r"(c.tbl + idx * 2u));          // sign-extending LDS.S16
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(ro) : "r"(c.isd + rsel4));            // SIM:414-415
     TblOut o;
     o.obs = (uint32_t)e & kTblObsMask;
@@ -118,6 +114,146 @@ __device__ __forceinline__ TblOut table_step(const TblCtx& c, uint32_t s, uint32
     o.reset_obs = reset ? ro : o.obs;
     return o;
 }
+
+__device__ __forceinline__ TblOut table_step(const TblCtx& c, uint32_t s, uint32_t jr, uint32_t rsel4)
+{
+    // the clamp keeps a corrupt state word / action byte inside the table
+    const uint32_t idx = min((s & 0xFFFFu) * 100u + jr, c.last);
+    int32_t e;
+    // volatile: ordered after the (volatile) mbarrier wait that publishes the table
+    asm volatile("ld.shared.s16 %0, [%1];" : "=r"(e) : "r"(c.tbl + idx * 2u));          // sign-extending LDS.S16
+    return table_finish(c, s, e, rsel4);
+}
+
+// ---- slip_prob > 0 through the SAME table (SIM:203-256).
+// The reference lists, for the 9 slip combinations in the order of SIM:209-223, the outcomes of the slipped move
+// pair (ma, mb) with probability mp * nsp and draws with categorical_sample: the first entry whose running fp64
+// sum exceeds u (gym 0.26.2: argmax(cumsum > u), all-False -> 0).  The outcomes of a move pair are exactly the
+// slip-0 transitions of (state, ma, mb) -- a slipped move is NOOP iff the action is (slip_move), so the NOOP-keyed
+// cases 2/3 of SIM:330-344 agree -- i.e. the table row of the state: entry (ma*5+mb)*4 + r, whose bits 10..11
+// hold log2(#outcomes).  Per env-step: 9 look-ups for the outcome counts, the sequential sum in the reference's
+// order with __dadd_rn / __dmul_rn (no FMA contraction), one look-up for the chosen entry.  No rules evaluation,
+// no per-combination branch: ~120 instructions instead of the ~500 of the rules walk (step_slip).
+// LD(byte offset in the row) returns the 16-bit entry zero-extended.
+template <class LD>
+__device__ __forceinline__ uint32_t slip_pick(const PitchDev& P, const LD& ld, uint32_t aa, uint32_t ab, double u)
+{
+    aa = min(aa, 4u); ab = min(ab, 4u);
+    // byte offsets inside the row of the r = 0 entry: (ma * 5 + mb) * 4 entries * 2 bytes
+    const uint32_t oa[3] = { aa * 40u, slip_move(aa, 0) * 40u, slip_move(aa, 1) * 40u };
+    const uint32_t ob[3] = { ab * 8u, slip_move(ab, 0) * 8u, slip_move(ab, 1) * 8u };
+    double cs = 0.0;
+    bool found = false, have_first = false;
+    uint32_t pick = 0, first = 0;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const double mp = P.mp[k];
+        if (mp == 0.0) continue;                                            // SIM:226-227 (same for every env)
+        const uint32_t off = oa[combo_a(k)] + ob[combo_b(k)];
+        const uint32_t nl = (ld(off) >> 10) & 3u;                           // log2(#outcomes) of this move pair
+        if (!have_first) { first = off; have_first = true; }
+        const double pr = __dmul_rn(mp, nl == 2u ? 0.25 : (nl == 1u ? 0.5 : 1.0));   // SIM:241 (exact: power of two)
+        cs = __dadd_rn(cs, pr);
+        if (!found && cs > u) { found = true; pick = off; }                 // outcome slot 0 (draw value 0)
+        if (nl) {                                                           // rare: a collision with 2 or 4 outcomes
+            cs = __dadd_rn(cs, pr);
+            if (!found && cs > u) { found = true; pick = off + (nl == 1u ? 4u : 2u); }   // slot 1: r = 2 of 2, r = 1 of 4
+            if (nl == 2u) {
+                cs = __dadd_rn(cs, pr);
+                if (!found && cs > u) { found = true; pick = off + 4u; }
+                cs = __dadd_rn(cs, pr);
+                if (!found && cs > u) { found = true; pick = off + 6u; }
+            }
+        }
+    }
+    return found ? pick : first;                                            // all-False -> index 0
+}
+
+struct LdShared {
+    uint32_t row;
+    __device__ __forceinline__ uint32_t operator()(uint32_t off) const
+    {
+        uint32_t e;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"(row + off));
+        return e;
+    }
+};
+struct LdGlobal {
+    const uint8_t* row;
+    __device__ __forceinline__ uint32_t operator()(uint32_t off) const
+    {
+        return (uint32_t)__ldg(reinterpret_cast<const uint16_t*>(row + off));
+    }
+};
+
+// Shared-memory fast form of slip_pick (same result, ~4x fewer instructions).  The end-of-combination sums
+// E_k are non-decreasing, so "first entry whose running sum exceeds u" needs no found flag: the candidate moves
+// on to combination k + 1 exactly while E_k <= u.  Per combination: one byte load of the entry's high byte
+// (outcome count in bits 2..3), the probability mp_k * nsp from a 9 x 3 fp64 shared-memory table (no select,
+// no multiply), one DADD, one DSETP, one select.  A combination with 2 or 4 outcomes (< 3 % of them) takes a
+// short branch that adds its partial sums and moves the candidate to the slot inside it.  A zero-probability
+// combination (SIM:226-227) adds 0 and so can never become the pick.
+struct SlipCtx { uint32_t prt; uint32_t first_k; };     // shared address of prt[9][3]; first combination with mp != 0
+__device__ __forceinline__ void slip_build_prt(double* prt, const PitchDev& P)
+{
+    if (threadIdx.x < 27) {
+        const int k = threadIdx.x / 3, j = threadIdx.x % 3;
+        prt[threadIdx.x] = __dmul_rn(P.mp[k], j == 2 ? 0.25 : (j == 1 ? 0.5 : 1.0));     // SIM:241
+    }
+}
+__device__ __forceinline__ uint32_t slip_first_k(const PitchDev& P)
+{
+    uint32_t f = 0;
+    for (int k = 8; k >= 0; --k) if (P.mp[k] != 0.0) f = (uint32_t)k;
+    return f;
+}
+
+__device__ __forceinline__ TblOut table_step_slip(const TblCtx& c, const SlipCtx& sc, uint32_t s, uint32_t aa, uint32_t ab,
+                                                  double u, uint32_t rsel4)
+{
+    const uint32_t row = c.tbl + min(s & 0xFFFFu, c.last / 100u) * 200u;
+    aa = min(aa, 4u); ab = min(ab, 4u);
+    // shared addresses of the r = 0 entry of a move pair: row + (ma * 5 + mb) * 8
+    const uint32_t ra[3] = { row + aa * 40u, row + slip_move(aa, 0) * 40u, row + slip_move(aa, 1) * 40u };
+    const uint32_t ob[3] = { ab * 8u, slip_move(ab, 0) * 8u, slip_move(ab, 1) * 8u };
+    double E = 0.0;
+    bool le = true;                     // E_{k-1} <= u: the pick is not before combination k
+    uint32_t pick = 0;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        uint32_t ent = ra[combo_a(k)] + ob[combo_b(k)];
+        uint32_t hi;
+        asm volatile("ld.shared.u8 %0, [%1+1];" : "=r"(hi) : "r"(ent));           // bits 2..3 = log2(#outcomes)
+        const uint32_t nl4 = hi & 0xCu;
+        double pr;
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(pr) : "r"(sc.prt + k * 24 + nl4 * 2u));
+        E = __dadd_rn(E, pr);
+        if (nl4) {                                                                // rare: 2 or 4 outcomes
+            uint32_t slot = E <= u ? 1u : 0u;
+            E = __dadd_rn(E, pr);
+            if (nl4 == 8u) {
+                slot += E <= u ? 1u : 0u; E = __dadd_rn(E, pr);
+                slot += E <= u ? 1u : 0u; E = __dadd_rn(E, pr);
+                ent += slot * 2u;                                                 // 4-way: draw value r = slot
+            } else {
+                ent += slot * 4u;                                                 // 2-way: r = 2 * slot
+            }
+        }
+        pick = le ? ent : pick;
+        le = E <= u;
+    }
+    if (le) {                                                                     // all-False -> index 0 of the list
+        const uint32_t ca = (uint32_t)combo_a((int)sc.first_k), cb = (uint32_t)combo_b((int)sc.first_k);
+        pick = (ca == 0 ? ra[0] : (ca == 1 ? ra[1] : ra[2])) + (cb == 0 ? ob[0] : (cb == 1 ? ob[1] : ob[2]));
+    }
+    int32_t e;
+    asm volatile("ld.shared.s16 %0, [%1];" : "=r"(e) : "r"(pick));
+    return table_finish(c, s, e, rsel4);
+}
+
+// the injected draw of a slip step as the reference's u in [0, 1): a raw fp64 value, or a 32-bit integer r
+// standing for (r + 0.5) / 2^32 (as in k_step_generic)
+__device__ __forceinline__ double u_from_rng32(uint32_t r) { return ((double)r + 0.5) * (1.0 / 4294967296.0); }
 
 __device__ __forceinline__ TblCtx make_ctx(const uint8_t* smem, uint32_t table_bytes, const PitchDev& P)
 {
@@ -207,6 +343,93 @@ k_step_table_scalar(const PitchDev P, const uint16_t* __restrict__ gtable, uint3
         const uint32_t s = state[i], rg = rng[i];
         const uint32_t idx = min((s & 0xFFFFu) * 100u + (uint32_t)act_a[i] * 20u + (uint32_t)act_b[i] * 4u + (rg & 3u), last);
         const int32_t e = tbl[idx];
+        const uint32_t nobs = (uint32_t)e & kTblObsMask;
+        const bool done = nobs == 0;
+        const uint32_t s1 = s + 0x10000u;
+        const bool trunc = s1 >= kTruncWord, reset = done | trunc;
+        const uint32_t ro = (uint32_t)P.isd_obs[(rg >> 2) & 3u];
+        state[i] = reset ? ro : ((s1 & 0xFFFF0000u) | nobs);
+        obs[i] = (int32_t)nobs;
+        reward[i] = (float)(e >> 14);
+        flags[i] = (uint8_t)((done ? 1u : 0u) + (trunc ? 2u : 0u));
+        if (reset_obs) reset_obs[i] = (int32_t)(reset ? ro : nobs);
+    }
+}
+
+// K1, table variant for slip_prob > 0: same launch shape as k_step_table, one more input stream (the step draw:
+// uint32 or fp64 per env; rng8 still carries the reset draw in bits 2..3).  24 or 28 algorithmic bytes per env-step.
+#ifndef SOCCER_SLIP_THREADS
+#define SOCCER_SLIP_THREADS 1024     // latency-bound (dependent DADD chain): 1024 threads x 64 registers beat 512 x 83 (98 vs 83 G env-steps/s)
+#endif
+constexpr int kSlipThreads = SOCCER_SLIP_THREADS;       // the slip walk keeps 4 envs x (sum, candidate, 6 addresses) live
+template <bool RESET_OBS, bool F64>
+__global__ void __launch_bounds__(kSlipThreads, 1)
+k_step_table_slip(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t table_bytes,
+                  uint32_t* __restrict__ state, const uint8_t* __restrict__ act_a, const uint8_t* __restrict__ act_b,
+                  const uint8_t* __restrict__ rng, const void* __restrict__ draw, int32_t* __restrict__ obs,
+                  float* __restrict__ reward, uint8_t* __restrict__ flags, int32_t* __restrict__ reset_obs, int64_t n_groups)
+{
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ __align__(8) double prt[27];
+    slip_build_prt(prt, P);
+    stage_table(smem_raw, gtable, table_bytes, &bar, P);     // ends with __syncthreads(): prt visible
+    const TblCtx c = make_ctx(smem_raw, table_bytes, P);
+    const SlipCtx sc = { smem_u32(prt), slip_first_k(P) };
+    uint4* st4 = reinterpret_cast<uint4*>(state);
+    const uint32_t* a4 = reinterpret_cast<const uint32_t*>(act_a);
+    const uint32_t* b4 = reinterpret_cast<const uint32_t*>(act_b);
+    const uint32_t* r4 = reinterpret_cast<const uint32_t*>(rng);
+    uint4* o4 = reinterpret_cast<uint4*>(obs);
+    uint4* w4 = reinterpret_cast<uint4*>(reward);
+    uint32_t* f4 = reinterpret_cast<uint32_t*>(flags);
+    uint4* q4 = reinterpret_cast<uint4*>(reset_obs);
+    wait_table(&bar);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_groups; g += stride) {
+        const Group4 x = load_group(st4, a4, b4, r4, g);
+        double u[4];
+        if (F64) {
+            const double2 d0 = __ldcs(reinterpret_cast<const double2*>(draw) + 2 * g);
+            const double2 d1 = __ldcs(reinterpret_cast<const double2*>(draw) + 2 * g + 1);
+            u[0] = d0.x; u[1] = d0.y; u[2] = d1.x; u[3] = d1.y;
+        } else {
+            const uint4 d = __ldcs(reinterpret_cast<const uint4*>(draw) + g);
+            u[0] = u_from_rng32(d.x); u[1] = u_from_rng32(d.y); u[2] = u_from_rng32(d.z); u[3] = u_from_rng32(d.w);
+        }
+        const uint32_t rs4 = x.r & 0x0C0C0C0Cu;
+        const uint32_t sv[4] = { x.s.x, x.s.y, x.s.z, x.s.w };
+        uint32_t so[4], oo[4], ro[4], rr[4], ff[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const TblOut o = table_step_slip(c, sc, sv[e], __byte_perm(x.a, 0, 0x4440 + e), __byte_perm(x.b, 0, 0x4440 + e),
+                                             u[e], __byte_perm(rs4, 0, 0x4440 + e));
+            so[e] = o.state; oo[e] = o.obs; rr[e] = __float_as_uint((float)o.rew_i); ro[e] = o.reset_obs; ff[e] = o.flags;
+        }
+        st_keep(st4 + g, make_uint4(so[0], so[1], so[2], so[3]));
+        st_stream(o4 + g, make_uint4(oo[0], oo[1], oo[2], oo[3]));
+        st_stream(w4 + g, make_uint4(rr[0], rr[1], rr[2], rr[3]));
+        st_stream(f4 + g, __byte_perm(__byte_perm(ff[0], ff[1], 0x0040), __byte_perm(ff[2], ff[3], 0x0040), 0x5410));
+        if (RESET_OBS) st_stream(q4 + g, make_uint4(ro[0], ro[1], ro[2], ro[3]));
+    }
+}
+
+// scalar tail / misaligned fallback of the slip table path (global-memory table, one env per thread)
+__global__ void __launch_bounds__(kThreads)
+k_step_table_slip_scalar(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t* __restrict__ state,
+                         const uint8_t* __restrict__ act_a, const uint8_t* __restrict__ act_b,
+                         const uint8_t* __restrict__ rng, const uint32_t* __restrict__ rng32,
+                         const double* __restrict__ rngf64, int32_t* __restrict__ obs, float* __restrict__ reward,
+                         uint8_t* __restrict__ flags, int32_t* __restrict__ reset_obs, int64_t n)
+{
+    const uint32_t last_row = (uint32_t)P.nS - 1u;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t s = state[i], rg = rng[i];
+        const LdGlobal ld = { reinterpret_cast<const uint8_t*>(gtable) + (size_t)min(s & 0xFFFFu, last_row) * 200u };
+        const double u = rngf64 ? rngf64[i] : u_from_rng32(rng32[i]);
+        const uint32_t pick = slip_pick(P, ld, act_a[i], act_b[i], u);
+        const int32_t e = (int32_t)(int16_t)ld(pick);
         const uint32_t nobs = (uint32_t)e & kTblObsMask;
         const bool done = nobs == 0;
         const uint32_t s1 = s + 0x10000u;

@@ -39,7 +39,7 @@ class SoccerVecEnv:
       rng_mode   "injected": the caller passes the draws (bit-exact replay of the reference);
                  "philox":   Philox4x32-10 keyed (seed, env_id_base + i, step)
       kernel     "rules": rules evaluated inline (any pitch / option);
-                 "table": transition table resident in shared memory (slip_prob == 0, nS <= 1024);
+                 "table": transition table resident in shared memory (nS <= 1024, no folded policy);
                  "auto":  table when it applies, else rules
       env_id_base  global id of env 0 (rank * envs_per_rank when sharded over GPUs)
     """
@@ -76,13 +76,15 @@ class SoccerVecEnv:
         self.policy_b = self._policy_tensor(player_b_policy)
         self.want_reset_obs = bool(want_reset_obs)
 
-        table_ok = self.slip_prob == 0.0 and self.multiagent and (self.nS - 1) <= 1023
+        table_ok = self.multiagent and (self.nS - 1) <= 1023
         if kernel == "table" and not table_ok:
-            raise _lib.SoccerB200Error("kernel='table' needs slip_prob == 0, no folded policy and nS <= 1024")
+            raise _lib.SoccerB200Error("kernel='table' needs no folded policy and nS <= 1024")
         # "auto": the table kernel pays a 152 KB shared-memory fill per CTA per launch, which only
         # amortises over large batches; small batches are launch-latency bound either way
         if kernel == "auto":
-            kernel = "table" if (table_ok and self.num_envs >= 65536) else "rules"
+            # (with slip_prob > 0 the rules walk costs ~500 instructions per env, the table walk ~120: switch early)
+            big = self.num_envs >= (65536 if self.slip_prob == 0.0 else 4096)
+            kernel = "table" if (table_ok and big) else "rules"
         self.kernel = kernel
         self.layout = LAYOUT_INDEX if self.kernel == "table" else LAYOUT_CELL
 
@@ -191,18 +193,32 @@ class SoccerVecEnv:
         with torch.cuda.device(self.device):
             st = _stream(self.device)
             philox = self.rng_mode == "philox"
-            if self.kernel == "table":
-                if philox or detail or not auto_reset:
-                    raise NotImplementedError("kernel='table' offers the injected-draw auto-reset step; "
-                                              "use kernel='rules' for the other options")
-                check(self.lib.soccer_step_table(
-                    C.byref(self.pitch), _ptr(self.table), _ptr(self.state),
-                    _ptr(self._check_vec(act_a, torch.uint8, "act_a")), _ptr(self._check_vec(act_b, torch.uint8, "act_b")),
-                    _ptr(self._check_vec(rng8, torch.uint8, "rng8")), _ptr(obs), _ptr(reward), _ptr(flags),
-                    _ptr(reset_obs), self.num_envs, st), "soccer_step_table")
+            general = philox or detail or not auto_reset          # options only the generic rules kernel offers
+            if self.kernel == "table" and not general:
+                args = (C.byref(self.pitch), _ptr(self.table), _ptr(self.state),
+                        _ptr(self._check_vec(act_a, torch.uint8, "act_a")), _ptr(self._check_vec(act_b, torch.uint8, "act_b")),
+                        _ptr(self._check_vec(rng8, torch.uint8, "rng8")))
+                outs = (_ptr(obs), _ptr(reward), _ptr(flags), _ptr(reset_obs), self.num_envs, st)
+                if self.slip_prob != 0.0:
+                    if rng32 is None and rngf64 is None:
+                        raise ValueError("slip_prob > 0 needs the step draw: rng32 (int32/uint32 bits) or rngf64")
+                    check(self.lib.soccer_step_table_slip(
+                        *args, _ptr(None if rngf64 is not None else self._check_vec(rng32, torch.int32, "rng32")),
+                        _ptr(self._check_vec(rngf64, torch.float64, "rngf64")), *outs), "soccer_step_table_slip")
+                else:
+                    check(self.lib.soccer_step_table(*args, *outs), "soccer_step_table")
             else:
+                # a table env keeps INDEX-layout states: the generic kernel runs on a CELL-layout copy
+                state = self.state
+                if self.kernel == "table":
+                    if not auto_reset:
+                        raise NotImplementedError("kernel='table' states cannot hold needs_reset; use kernel='rules' "
+                                                  "for auto_reset=False")
+                    state = torch.empty_like(self.state)
+                    check(self.lib.soccer_convert_state(C.byref(self.pitch), _ptr(self.state), _ptr(state), LAYOUT_CELL,
+                                                        self.num_envs, st), "soccer_convert_state")
                 a = StepArgs()
-                a.state = self.state.data_ptr()
+                a.state = state.data_ptr()
                 a.act_a = None if self.policy_a is not None else self._check_vec(act_a, torch.uint8, "act_a").data_ptr()
                 a.act_b = None if self.policy_b is not None else self._check_vec(act_b, torch.uint8, "act_b").data_ptr()
                 if not philox:
@@ -219,6 +235,9 @@ class SoccerVecEnv:
                 a.detail = 1 if detail else 0
                 a.seed, a.step, a.env_id_base = self.seed, self.step_count, self.env_id_base
                 check(self.lib.soccer_step_ex(C.byref(self.pitch), C.byref(a), st), "soccer_step_ex")
+                if self.kernel == "table":
+                    check(self.lib.soccer_convert_state(C.byref(self.pitch), _ptr(state), _ptr(self.state), LAYOUT_INDEX,
+                                                        self.num_envs, st), "soccer_convert_state")
         self.step_count += 1
         return obs, reward, flags, reset_obs
 

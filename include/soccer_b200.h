@@ -222,7 +222,16 @@ int soccer_step_table(const soccer_pitch *pitch, const uint16_t *table, uint32_t
                       const uint8_t *act_a, const uint8_t *act_b, const uint8_t *rng8, int32_t *obs,
                       float *reward, uint8_t *flags, int32_t *reset_obs, int64_t n,
                       soccer_stream_t stream);
-/* soccer_rollout (uniform random policy) on SOCCER_LAYOUT_INDEX states */
+/* step() with slip_prob > 0 (SIM:203-256) through the same shared-memory table: the outcome counts of
+ * the 9 slipped move pairs are read from the state's table row, the categorical draw walks them in
+ * the reference's order with sequential fp64 sums (bit-exact), one more look-up yields the chosen
+ * outcome.  The step draw u comes from rngf64[n] (raw) or rng32[n] ((r + 0.5) / 2^32), exactly one of
+ * them; rng8 bits 2..3 carry the reset draw as in soccer_step.  SOCCER_LAYOUT_INDEX states. */
+int soccer_step_table_slip(const soccer_pitch *pitch, const uint16_t *table, uint32_t *state,
+                           const uint8_t *act_a, const uint8_t *act_b, const uint8_t *rng8,
+                           const uint32_t *rng32, const double *rngf64, int32_t *obs, float *reward,
+                           uint8_t *flags, int32_t *reset_obs, int64_t n, soccer_stream_t stream);
+/* soccer_rollout (uniform random policy; slip_prob >= 0) on SOCCER_LAYOUT_INDEX states */
 int soccer_rollout_table(const soccer_pitch *pitch, const uint16_t *table, uint32_t *state,
                          uint64_t seed, uint64_t step0, int32_t K, uint64_t env_id_base,
                          int32_t *obs, float *reward, uint8_t *flags, unsigned long long *stats,

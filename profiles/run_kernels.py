@@ -1,6 +1,6 @@
 """Short driver for ncu captures: a few launches of each hot kernel at its bench size.
 
-    python profiles/run_kernels.py [k1_table|k1_rules|k2_table|k2_rules|replay|all] [--envs N]
+    python profiles/run_kernels.py [k1_table|k1_rules|k2_table|k2_rules|k1_slip|replay|all] [--envs N]
 """
 import argparse
 import os
@@ -34,6 +34,24 @@ def k2(kernel, n, K, iters):
     torch.cuda.synchronize()
 
 
+def k1_slip(n, iters):
+    dev = torch.device("cuda", 0)
+    env = SoccerVecEnv(n, slip_prob=0.2, device=dev, kernel="table", want_reset_obs=False)
+    g = torch.Generator(device=dev).manual_seed(0)
+    a, b, r = (torch.randint(0, hi, (n,), dtype=torch.uint8, device=dev, generator=g) for hi in (5, 5, 16))
+    r32 = torch.randint(-2**31, 2**31 - 1, (n,), dtype=torch.int32, device=dev, generator=g)
+    env.reset(r)
+    for _ in range(iters):
+        env.step(a, b, r, rng32=r32)
+    e2 = SoccerVecEnv(1 << 20, slip_prob=0.2, device=dev, kernel="table", rng_mode="philox")
+    e2.reset()
+    bufs = (torch.empty((16, 1 << 20), dtype=torch.int32, device=dev), torch.empty((16, 1 << 20), dtype=torch.float32, device=dev),
+            torch.empty((16, 1 << 20), dtype=torch.uint8, device=dev))
+    for _ in range(iters):
+        e2.rollout(16, out=bufs)
+    torch.cuda.synchronize()
+
+
 def replay(kernel, n, T, iters):
     dev = torch.device("cuda", 0)
     env = SoccerVecEnv(n, device=dev, kernel=kernel, want_reset_obs=False)
@@ -60,6 +78,8 @@ if __name__ == "__main__":
         k2("table", 1 << 20, 64, args.iters)
     if args.what in ("k2_rules", "all"):
         k2("rules", 1 << 20, 64, args.iters)
+    if args.what in ("k1_slip", "all"):
+        k1_slip(1 << 22, args.iters)
     if args.what in ("replay", "all"):
         replay("table", 1 << 22, 64, 3)
         replay("table", 4096, 4000, 3)

@@ -62,7 +62,15 @@ def test_argument_errors_without_gpu(L):
     nbytes = C.c_int64()
     assert lib.soccer_step_table_bytes_host(C.byref(p), C.byref(nbytes)) == 0 and nbytes.value == 152208   # 761 rows * 100 * 2 B, up to 16
     assert lib.soccer_step_table_bytes_host(C.byref(L.Pitch(6, 4, 0.0)), C.byref(nbytes)) == -5
-    assert lib.soccer_step_table_bytes_host(C.byref(L.Pitch(5, 4, 0.2)), C.byref(nbytes)) == -5
+    # the table does not depend on slip_prob (the slip kernels walk its rows): same size
+    assert lib.soccer_step_table_bytes_host(C.byref(L.Pitch(5, 4, 0.2)), C.byref(nbytes)) == 0 and nbytes.value == 152208
+    # the slip-0 table step refuses a slip pitch; the slip step needs exactly the step draw
+    v16 = C.c_void_p(16)
+    assert lib.soccer_step_table(C.byref(L.Pitch(5, 4, 0.2)), v16, v16, v16, v16, v16, v16, v16, v16, None, 8, None) == -3
+    assert lib.soccer_step_table_slip(C.byref(L.Pitch(5, 4, 0.2)), v16, v16, v16, v16, v16, None, None, v16, v16, v16,
+                                      None, 8, None) == -1
+    assert lib.soccer_step_many(C.byref(L.Pitch(5, 4, 0.2)), None, v16, 4, v16, v16, v16, v16, v16, v16, None, 8, None) == -3
+    assert lib.soccer_step_many(C.byref(p), None, v16, -1, v16, v16, v16, v16, v16, v16, None, 8, None) == -1
 
 
 @pytest.mark.parametrize("tag", [t for t in golden_tags("table") if t.endswith("multi")])
