@@ -253,7 +253,7 @@ k_rollout_table(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t 
     if (threadIdx.x == 4) blk_net = 0;
     TableStepper<POLICY, SLIP> S;
     S.pol_a = S.pol_b = 0;
-    __shared__ __align__(8) double prt[27];
+    __shared__ __align__(16) double prt[kPrtDoubles];
     S.sc.prt = 0; S.sc.first_k = 0;
     if (SLIP) { slip_build_prt(prt, P); S.sc.prt = smem_u32(prt); S.sc.first_k = slip_first_k(P); }
     if (POLICY) {

@@ -3,10 +3,10 @@
 // The table is the reference's P (SIM:167-293) for slip_prob == 0, produced ON THE DEVICE by the
 // rules path (k_build_step_table -> resolve()/finish_step()), compacted to one int16 per
 // (state, joint action, 2-bit draw):
-//     table[obs*100 + (aa*5+ab)*4 + r] = next_obs | nlog2 << 10 | (reward & 3) << 14
-// so that a SIGN-EXTENDING 16-bit shared-memory load yields next_obs = e & 0x3FF and
+//     table[obs*100 + (aa*5+ab)*4 + r] = next_obs | nlog2 << 12 | (reward & 3) << 14
+// so that a SIGN-EXTENDING 16-bit shared-memory load yields next_obs = e & 0xFFF and
 // reward = e >> 14 (arithmetic: -1, 0, +1) with no further decoding.  761 * 100 * 2 = 152,200 bytes
-// for the 5x4 pitch: it fits the 227 KB of one SM once, hence ONE persistent 1024-thread CTA per
+// for the 5x4 pitch, 1105 * 200 = 221,000 for 6x4 (the largest that fits): the 227 KB of one SM hold it once, hence ONE persistent 1024-thread CTA per
 // SM; the copy global -> shared is a TMA bulk copy (cp.async.bulk + mbarrier) that overlaps the
 // first HBM loads.  States use SOCCER_LAYOUT_INDEX: obs | timestep << 16.
 // SIM = /root/reference/gym_soccer/envs/soccer_simultaneous_env.py.
@@ -20,8 +20,8 @@ constexpr int kTableThreads = 1024;          // one CTA per SM owns the whole sh
 #define SOCCER_ROLLOUT_THREADS 512           // K2 keeps 4 envs x 4 Philox words in registers: 128 registers per thread
 #endif
 constexpr int kRolloutThreads = SOCCER_ROLLOUT_THREADS;
-constexpr int kMaxTableStates = 1023;        // next_obs must fit 10 bits
-constexpr uint32_t kTblObsMask = 0x3FFu;
+constexpr int kMaxTableStates = 1130;        // rows * 200 B + start observations + table policies <= 227 KB (next_obs has 12 bits)
+constexpr uint32_t kTblObsMask = 0xFFFu;
 constexpr uint32_t kTruncWord = (uint32_t)kMaxT << 16;   // (obs | t<<16) >= this  <=>  t >= 100
 
 __global__ void __launch_bounds__(kThreads)
@@ -39,7 +39,7 @@ k_build_step_table(const PitchDev P, int32_t nS, uint16_t* __restrict__ table)
         const Resolved o = resolve(lut, a, b, p, aa, ab, aa == 0, ab == 0, r);
         const StepOut f = finish_step<false>(P, o, 0u, 0u, 0u, false);
         const uint32_t rew2 = f.reward > 0.0f ? 1u : (f.reward < 0.0f ? 3u : 0u);
-        table[i] = (uint16_t)((uint32_t)f.obs | (o.nlog2 << 10) | (rew2 << 14));
+        table[i] = (uint16_t)((uint32_t)f.obs | (o.nlog2 << 12) | (rew2 << 14));
     }
 }
 
@@ -130,10 +130,10 @@ __device__ __forceinline__ TblOut table_step(const TblCtx& c, uint32_t s, uint32
 // pair (ma, mb) with probability mp * nsp and draws with categorical_sample: the first entry whose running fp64
 // sum exceeds u (gym 0.26.2: argmax(cumsum > u), all-False -> 0).  The outcomes of a move pair are exactly the
 // slip-0 transitions of (state, ma, mb) -- a slipped move is NOOP iff the action is (slip_move), so the NOOP-keyed
-// cases 2/3 of SIM:330-344 agree -- i.e. the table row of the state: entry (ma*5+mb)*4 + r, whose bits 10..11
+// cases 2/3 of SIM:330-344 agree -- i.e. the table row of the state: entry (ma*5+mb)*4 + r, whose bits 12..13
 // hold log2(#outcomes).  Per env-step: 9 look-ups for the outcome counts, the sequential sum in the reference's
 // order with __dadd_rn / __dmul_rn (no FMA contraction), one look-up for the chosen entry.  No rules evaluation,
-// no per-combination branch: ~120 instructions instead of the ~500 of the rules walk (step_slip).
+// no per-combination branch.
 // LD(byte offset in the row) returns the 16-bit entry zero-extended.
 template <class LD>
 __device__ __forceinline__ uint32_t slip_pick(const PitchDev& P, const LD& ld, uint32_t aa, uint32_t ab, double u)
@@ -150,7 +150,7 @@ __device__ __forceinline__ uint32_t slip_pick(const PitchDev& P, const LD& ld, u
         const double mp = P.mp[k];
         if (mp == 0.0) continue;                                            // SIM:226-227 (same for every env)
         const uint32_t off = oa[combo_a(k)] + ob[combo_b(k)];
-        const uint32_t nl = (ld(off) >> 10) & 3u;                           // log2(#outcomes) of this move pair
+        const uint32_t nl = (ld(off) >> 12) & 3u;                           // log2(#outcomes) of this move pair
         if (!have_first) { first = off; have_first = true; }
         const double pr = __dmul_rn(mp, nl == 2u ? 0.25 : (nl == 1u ? 0.5 : 1.0));   // SIM:241 (exact: power of two)
         cs = __dadd_rn(cs, pr);
@@ -189,16 +189,18 @@ struct LdGlobal {
 // Shared-memory fast form of slip_pick (same result, ~4x fewer instructions).  The end-of-combination sums
 // E_k are non-decreasing, so "first entry whose running sum exceeds u" needs no found flag: the candidate moves
 // on to combination k + 1 exactly while E_k <= u.  Per combination: one byte load of the entry's high byte
-// (outcome count in bits 2..3), the probability mp_k * nsp from a 9 x 3 fp64 shared-memory table (no select,
+// (outcome count in bits 4..5), the probability mp_k * nsp from a 9 x 3 fp64 shared-memory table (no select,
 // no multiply), one DADD, one DSETP, one select.  A combination with 2 or 4 outcomes (< 3 % of them) takes a
 // short branch that adds its partial sums and moves the candidate to the slot inside it.  A zero-probability
 // combination (SIM:226-227) adds 0 and so can never become the pick.
-struct SlipCtx { uint32_t prt; uint32_t first_k; };     // shared address of prt[9][3]; first combination with mp != 0
+struct SlipCtx { uint32_t prt; uint32_t first_k; };     // shared address of prt[9][3] (16-byte stride); first combination with mp != 0
+constexpr int kPrtDoubles = 9 * 3 * 2;
 __device__ __forceinline__ void slip_build_prt(double* prt, const PitchDev& P)
 {
     if (threadIdx.x < 27) {
         const int k = threadIdx.x / 3, j = threadIdx.x % 3;
-        prt[threadIdx.x] = __dmul_rn(P.mp[k], j == 2 ? 0.25 : (j == 1 ? 0.5 : 1.0));     // SIM:241
+        prt[2 * threadIdx.x] = __dmul_rn(P.mp[k], j == 2 ? 0.25 : (j == 1 ? 0.5 : 1.0));     // SIM:241
+        prt[2 * threadIdx.x + 1] = 0.0;
     }
 }
 __device__ __forceinline__ uint32_t slip_first_k(const PitchDev& P)
@@ -223,15 +225,15 @@ __device__ __forceinline__ TblOut table_step_slip(const TblCtx& c, const SlipCtx
     for (int k = 0; k < 9; ++k) {
         uint32_t ent = ra[combo_a(k)] + ob[combo_b(k)];
         uint32_t hi;
-        asm volatile("ld.shared.u8 %0, [%1+1];" : "=r"(hi) : "r"(ent));           // bits 2..3 = log2(#outcomes)
-        const uint32_t nl4 = hi & 0xCu;
+        asm volatile("ld.shared.u8 %0, [%1+1];" : "=r"(hi) : "r"(ent));           // bits 4..5 = log2(#outcomes)
+        const uint32_t nl4 = hi & 0x30u;                                          // 16 * log2(#outcomes) = prt byte offset
         double pr;
-        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(pr) : "r"(sc.prt + k * 24 + nl4 * 2u));
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(pr) : "r"(sc.prt + k * 48 + nl4));
         E = __dadd_rn(E, pr);
         if (nl4) {                                                                // rare: 2 or 4 outcomes
             uint32_t slot = E <= u ? 1u : 0u;
             E = __dadd_rn(E, pr);
-            if (nl4 == 8u) {
+            if (nl4 == 0x20u) {
                 slot += E <= u ? 1u : 0u; E = __dadd_rn(E, pr);
                 slot += E <= u ? 1u : 0u; E = __dadd_rn(E, pr);
                 ent += slot * 2u;                                                 // 4-way: draw value r = slot
@@ -371,7 +373,7 @@ k_step_table_slip(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar;
-    __shared__ __align__(8) double prt[27];
+    __shared__ __align__(16) double prt[kPrtDoubles];
     slip_build_prt(prt, P);
     stage_table(smem_raw, gtable, table_bytes, &bar, P);     // ends with __syncthreads(): prt visible
     const TblCtx c = make_ctx(smem_raw, table_bytes, P);

@@ -39,7 +39,7 @@ class SoccerVecEnv:
       rng_mode   "injected": the caller passes the draws (bit-exact replay of the reference);
                  "philox":   Philox4x32-10 keyed (seed, env_id_base + i, step)
       kernel     "rules": rules evaluated inline (any pitch / option);
-                 "table": transition table resident in shared memory (nS <= 1024, no folded policy);
+                 "table": transition table resident in shared memory (5x4 and 6x4 pitches, no folded policy);
                  "auto":  table when it applies, else rules
       env_id_base  global id of env 0 (rank * envs_per_rank when sharded over GPUs)
     """
@@ -76,9 +76,11 @@ class SoccerVecEnv:
         self.policy_b = self._policy_tensor(player_b_policy)
         self.want_reset_obs = bool(want_reset_obs)
 
-        table_ok = self.multiagent and (self.nS - 1) <= 1023
+        _nb = C.c_int64()
+        table_ok = self.multiagent and self.lib.soccer_step_table_bytes_host(C.byref(self.pitch), C.byref(_nb)) == 0
         if kernel == "table" and not table_ok:
-            raise _lib.SoccerB200Error("kernel='table' needs no folded policy and nS <= 1024")
+            raise _lib.SoccerB200Error("kernel='table' needs no folded policy and a table that fits shared memory "
+                                       "(5x4 and 6x4 pitches)")
         # "auto": the table kernel pays a 152 KB shared-memory fill per CTA per launch, which only
         # amortises over large batches; small batches are launch-latency bound either way
         if kernel == "auto":

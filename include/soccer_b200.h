@@ -206,15 +206,16 @@ int soccer_rollout(const soccer_pitch *pitch, uint32_t *state, const int8_t *pol
 int soccer_sweep(const soccer_pitch *pitch, int32_t n_combos, uint8_t *n_out, uint32_t *next_state,
                  int32_t *next_obs, int8_t *reward, uint8_t *done, soccer_stream_t stream);
 
-/* ---- shared-memory-table variants of K1 / K2 (slip_prob == 0, pitches with nS <= 1024) ---- */
+/* ---- shared-memory-table variants of K1 / K2 (pitches whose table fits the 227 KB of an SM:
+ *      nS <= 1131, i.e. 5x4 and 6x4) ---- */
 #define SOCCER_LAYOUT_CELL  0
 #define SOCCER_LAYOUT_INDEX 1
 #define SOCCER_ETABLE (-5)   /* pitch too large for the shared-memory step table / slip_prob != 0 */
 /* bytes of the step table for this pitch: nS * 100 * sizeof(int16_t), rounded up to 16 */
 int soccer_step_table_bytes_host(const soccer_pitch *pitch, int64_t *bytes);
 /* Fill table[obs*100 + aa*20 + ab*4 + r] for every state, joint action and 2-bit draw by
- * running the rules path (SIM:296-373, 235-240) on the device.  Entry (int16): bits 0..9 next
- * observation (0 = goal), bits 10..11 log2(#outcomes), bits 14..15 the reward as a signed 2-bit
+ * running the rules path (SIM:296-373, 235-240) on the device.  Entry (int16): bits 0..11 next
+ * observation (0 = goal), bits 12..13 log2(#outcomes), bits 14..15 the reward as a signed 2-bit
  * field, so reward = entry >> 14 (arithmetic).  Row 0 is the absorbing terminal observation. */
 int soccer_build_step_table(const soccer_pitch *pitch, uint16_t *table, soccer_stream_t stream);
 /* soccer_step on SOCCER_LAYOUT_INDEX states with the table staged into shared memory by TMA */

@@ -61,7 +61,8 @@ def test_argument_errors_without_gpu(L):
     assert lib.soccer_step_ex(C.byref(p), C.byref(a), None) == -4                                  # SIM:38
     nbytes = C.c_int64()
     assert lib.soccer_step_table_bytes_host(C.byref(p), C.byref(nbytes)) == 0 and nbytes.value == 152208   # 761 rows * 100 * 2 B, up to 16
-    assert lib.soccer_step_table_bytes_host(C.byref(L.Pitch(6, 4, 0.0)), C.byref(nbytes)) == -5
+    assert lib.soccer_step_table_bytes_host(C.byref(L.Pitch(6, 4, 0.0)), C.byref(nbytes)) == 0 and nbytes.value == 221008
+    assert lib.soccer_step_table_bytes_host(C.byref(L.Pitch(5, 5, 0.0)), C.byref(nbytes)) == -5     # 240 KB: does not fit an SM
     # the table does not depend on slip_prob (the slip kernels walk its rows): same size
     assert lib.soccer_step_table_bytes_host(C.byref(L.Pitch(5, 4, 0.2)), C.byref(nbytes)) == 0 and nbytes.value == 152208
     # the slip-0 table step refuses a slip pitch; the slip step needs exactly the step draw

@@ -180,9 +180,11 @@ def test_step_dict_api_matches_reference(dev, tag):
         env.step_dict({})
 
 
-def test_step_table_kernel_matches_reference(dev):
-    g = load_golden("rollout", "5x4_s000_multi")
-    obs, rew, flg, rob = _run_vec(dev, g, dict(width=5, height=4, slip_prob=0.0), "table")
+@pytest.mark.parametrize("tag", ["5x4_s000_multi", "6x4_s000_multi"])
+def test_step_table_kernel_matches_reference(dev, tag):
+    g = load_golden("rollout", tag)
+    w, h, _, _ = parse_tag(tag)
+    obs, rew, flg, rob = _run_vec(dev, g, dict(width=w, height=h, slip_prob=0.0), "table")
     assert np.array_equal(obs, g["obs"]) and np.array_equal(rew, g["reward"])
     assert np.array_equal(flg, g["flags"]) and np.array_equal(rob, g["reset_obs"])
 
@@ -239,6 +241,47 @@ def test_step_table_slip_vs_rules_kernel_and_oracle(dev, oracle, slip, draw):
             assert np.array_equal(outs["table"][0], eo[t]) and np.array_equal(outs["table"][1], er[t])
             assert np.array_equal(outs["table"][2], ef[t]) and np.array_equal(outs["table"][3], ero[t])
     assert np.array_equal(envs["rules"].current_obs().cpu().numpy(), envs["table"].current_obs().cpu().numpy())
+
+
+def test_6x4_table_kernels_vs_oracle(dev, oracle):
+    """The 6x4 pitch (nS = 1105, 221 KB table: the largest that fits an SM) through every table kernel --
+    K2 uniform and with table policies, K1 slip, the fused replay -- against the oracle."""
+    from gym_soccer_littman94_b200.envs import SoccerVecEnv
+    N, K, seed = 4100, 90, 77
+    m = oracle.OracleModel(6, 4, 0.0)
+    rs = np.random.RandomState(11)
+    for pol in (False, True):
+        pa = rs.randint(0, 5, m.nS).astype(np.int8) if pol else None
+        env = SoccerVecEnv(N, width=6, height=4, device=dev, rng_mode="philox", kernel="table", seed=seed)
+        states, ts = m.states_from_obs(env.reset().cpu().numpy()), np.zeros(N, np.int32)
+        eo, er, ef, es = m.rollout_philox(states, ts, K, seed, policy_a=pa, n_threads=8)
+        obs, rew, flg, stats = env.rollout(K, policy_a=pa)
+        assert np.array_equal(obs.cpu().numpy(), eo) and np.array_equal(rew.cpu().numpy(), er)
+        assert np.array_equal(flg.cpu().numpy(), ef) and np.array_equal(stats.cpu().numpy(), es)
+    # injected: fused replay (slip 0) and slip table step (slip 0.3)
+    T = 40
+    init = rs.randint(0, 4, N).astype(np.uint8)
+    act_a, act_b = (rs.randint(0, 5, (T, N)).astype(np.uint8) for _ in range(2))
+    rng8 = rs.randint(0, 16, (T, N)).astype(np.uint8)
+    r32 = rs.randint(0, 2**32, (T, N), dtype=np.uint64).astype(np.uint32)
+    for slip in (0.0, 0.3):
+        mm = oracle.OracleModel(6, 4, slip)
+        states = np.zeros(N, oracle.STATE_DTYPE)
+        for i in range(N):
+            states[i] = mm.isd[int(init[i])][1]
+        ts = np.zeros(N, np.int32)
+        eo, er, ef, ero = mm.rollout_injected(states, ts, act_a, act_b, rng8, rng32=r32 if slip else None, n_threads=8)
+        env = SoccerVecEnv(N, width=6, height=4, slip_prob=slip, device=dev, kernel="table")
+        env.reset(_t(init << 2, dev))
+        if slip == 0.0:
+            obs, rew, flg, rob = env.step_many(_t(act_a, dev), _t(act_b, dev), _t(rng8, dev))
+            got = [x.cpu().numpy() for x in (obs, rew, flg, rob)]
+        else:
+            rows = [[x.cpu().numpy().copy() for x in env.step(_t(act_a[t], dev), _t(act_b[t], dev), _t(rng8[t], dev),
+                                                               rng32=_t(r32[t].view(np.int32), dev))] for t in range(T)]
+            got = [np.stack([r[j] for r in rows]) for j in range(4)]
+        for x, y in zip(got, (eo, er, ef, ero)):
+            assert np.array_equal(x, y), slip
 
 
 def test_table_env_generic_options_roundtrip(dev):
