@@ -227,7 +227,10 @@ struct StepOpts {
 __global__ void __launch_bounds__(kThreads) k_step_generic(const PitchDev P, const StepOpts o)
 {
     __shared__ __align__(16) uint8_t lut[kLutBytes];
-    build_cand_lut(lut, P);
+    __shared__ __align__(16) double prt[kPrtDoubles];
+    if (P.slip) slip_build_prt(prt, P);
+    const SlipCtx sc = { (uint32_t)__cvta_generic_to_shared(prt), P.slip ? slip_first_k(P) : 0u };
+    build_cand_lut(lut, P);                      // ends with __syncthreads(): prt visible as well
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < o.n; i += stride) {
         const uint32_t s = o.state[i];
@@ -261,8 +264,8 @@ __global__ void __launch_bounds__(kThreads) k_step_generic(const PitchDev P, con
             if (o.rngf64) u = o.rngf64[i];
             else if (o.rng32) u = ((double)o.rng32[i] + 0.5) * (1.0 / 4294967296.0);
             else u = philox_u53(o.seed, o.env_id_base + (uint64_t)i, o.step);   // philox mode with slip
-            r = o.auto_reset ? step_slip<true>(P, lut, s, aa, ab, u, (rng >> 2) & 3u, flip)
-                             : step_slip<false>(P, lut, s, aa, ab, u, (rng >> 2) & 3u, flip);
+            r = o.auto_reset ? step_slip<true>(P, lut, sc, s, aa, ab, u, (rng >> 2) & 3u, flip)
+                             : step_slip<false>(P, lut, sc, s, aa, ab, u, (rng >> 2) & 3u, flip);
         } else {
             r = o.auto_reset ? step_noslip<true>(P, lut, s, aa, ab, rng, flip)
                              : step_noslip<false>(P, lut, s, aa, ab, rng, flip);

@@ -68,7 +68,7 @@ struct TableStepper {
 };
 
 struct RulesStepper {
-    const PitchDev& P; const uint8_t* lut; Isd4 I; const int8_t* policy_a; const int8_t* policy_b;
+    const PitchDev& P; const uint8_t* lut; Isd4 I; const int8_t* policy_a; const int8_t* policy_b; SlipCtx sc;
     __device__ __forceinline__ void unpack(uint32_t&, uint32_t&) const {}          // the packed CELL word as is
     __device__ __forceinline__ uint32_t pack(uint32_t s, uint32_t) const { return s; }
     __device__ __forceinline__ uint32_t timestep(uint32_t s, uint32_t) const { return (s >> 16) & 0xFFu; }
@@ -88,7 +88,7 @@ struct RulesStepper {
                     if (policy_a) aa = (uint32_t)policy_a[cur];
                     if (policy_b) ab = (uint32_t)policy_b[cur];
                 }
-                const StepOut o = step_slip<true>(P, lut, s[e], aa, ab, philox_u53(seed, env0 + e, step_abs),
+                const StepOut o = step_slip<true>(P, lut, sc, s[e], aa, ab, philox_u53(seed, env0 + e, step_abs),
                                                   word[e] & 3u, false);
                 s[e] = o.state; oo[e] = (uint32_t)o.obs; rr[e] = __float_as_uint(o.reward);
                 fw |= (o.flags & 3u) << (8 * e);
@@ -277,13 +277,16 @@ __global__ void __launch_bounds__(kThreads)
 k_rollout(const PitchDev P, const int8_t* __restrict__ policy_a, const int8_t* __restrict__ policy_b, const RolloutArgs a)
 {
     __shared__ __align__(16) uint8_t lut[kLutBytes];
+    __shared__ __align__(16) double prt[kPrtDoubles];
     __shared__ unsigned int blk_stats[4];
     __shared__ int blk_net;
+    if (P.slip) slip_build_prt(prt, P);
     build_cand_lut(lut, P);
     if (threadIdx.x < 4) blk_stats[threadIdx.x] = 0;
     if (threadIdx.x == 4) blk_net = 0;
     __syncthreads();
-    const RulesStepper S = { P, lut, make_isd4(P), policy_a, policy_b };
+    const SlipCtx sc = { (uint32_t)__cvta_generic_to_shared(prt), P.slip ? slip_first_k(P) : 0u };
+    const RulesStepper S = { P, lut, make_isd4(P), policy_a, policy_b, sc };
     rollout_body<VEC, STREAMS>(S, a, blk_stats, &blk_net);
 }
 

@@ -296,44 +296,93 @@ __device__ __forceinline__ StepOut step_noslip(const PitchDev& P, const uint8_t*
     return finish_step<AUTO_RESET, DETAIL>(P, o, t, 0u, (rng >> 2) & 3u, flip_reward);
 }
 
-// slip_prob > 0 step of one env: walk the outcome list of SIM:209-256 in order, accumulating
-// p = mp * nsp sequentially in fp64 (no FMA), and take the first entry whose running sum
-// exceeds u -- gym's categorical_sample (argmax(cumsum > u), all-False -> 0).
+// ---- slip_prob > 0 (SIM:203-256)
+// The reference lists, for the 9 slip combinations in the order of SIM:209-223, the outcomes of the slipped move
+// pair with probability mp * nsp and draws with gym's categorical_sample: the first entry whose running fp64 sum
+// exceeds u (argmax(cumsum > u), all-False -> 0).  Shared by the rules kernels here and the table kernels
+// (soccer_table.cuh): a 9 x 3 table of the products mp_k * {1, 0.5, 0.25} (16-byte stride, built per CTA with
+// __dmul_rn like SIM:241) and the first combination with a non-zero probability (SIM:226-227 skips the others;
+// adding their 0.0 leaves the sums unchanged, so they can never become the pick).
+constexpr int kPrtDoubles = 9 * 3 * 2;
+struct SlipCtx { uint32_t prt; uint32_t first_k; };     // shared-window address of the table; first combination with mp != 0
+__device__ __forceinline__ void slip_build_prt(double* prt, const PitchDev& P)
+{
+    if (threadIdx.x < 27) {
+        const int k = threadIdx.x / 3, j = threadIdx.x % 3;
+        prt[2 * threadIdx.x] = __dmul_rn(P.mp[k], j == 2 ? 0.25 : (j == 1 ? 0.5 : 1.0));     // SIM:241
+        prt[2 * threadIdx.x + 1] = 0.0;
+    }
+}
+__device__ __forceinline__ uint32_t slip_first_k(const PitchDev& P)
+{
+    uint32_t f = 0;
+    for (int k = 8; k >= 0; --k) if (P.mp[k] != 0.0) f = (uint32_t)k;
+    return f;
+}
+__device__ __forceinline__ double lds_f64(uint32_t addr)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+
+// slip step of one env by the rules.  The sums at the end of each combination are non-decreasing, so "first
+// entry whose running sum exceeds u" needs no found flag: the candidate moves on to combination k + 1 exactly
+// while E_k <= u.  The outcome COUNT of a combination needs only the collision predicates (6 candidate look-ups
+// and 12 compares shared by the 9 combinations, ~7 logic ops each); the full resolution runs once, for the pick.
+// Sums use __dadd_rn in the reference's order (no FMA contraction): bit-identical to numpy's cumsum.
 template <bool AUTO_RESET>
-__device__ __forceinline__ StepOut step_slip(const PitchDev& P, const uint8_t* __restrict__ lut,
+__device__ __forceinline__ StepOut step_slip(const PitchDev& P, const uint8_t* __restrict__ lut, const SlipCtx& sc,
                                              uint32_t s, uint32_t aa, uint32_t ab, double u,
                                              uint32_t reset_sel, bool flip_reward)
 {
     const uint32_t a = s & 0xFFu, b = (s >> 8) & 0xFFu, t = (s >> 16) & 0xFFu, p = (s >> 24) & 1u;
-    const uint32_t as0 = slip_move(aa, 0), as1 = slip_move(aa, 1);
-    const uint32_t bs0 = slip_move(ab, 0), bs1 = slip_move(ab, 1);
-    double cs = 0.0;
-    bool found = false, have_first = false;
-    Resolved pick = { a, b, p, 0u }, first = pick;
-    uint32_t pick_c = 0, first_c = 0;
-#pragma unroll 1
-    for (int c = 0; c < 9; ++c) {
-        const double mp = P.mp[c];
-        if (mp == 0.0) continue;                            // SIM:226-227
-        const int ca = combo_a(c), cb = combo_b(c);
-        const uint32_t ma = ca == 0 ? aa : (ca == 1 ? as0 : as1);
-        const uint32_t mb = cb == 0 ? ab : (cb == 1 ? bs0 : bs1);
-        const Resolved o0 = resolve(lut, a, b, p, ma, mb, aa == 0, ab == 0, 0u);
-        if (!have_first) { first = o0; first_c = (uint32_t)c; have_first = true; }
-        const uint32_t n = 1u << o0.nlog2;
-        const double pr = __dmul_rn(mp, o0.nlog2 == 2 ? 0.25 : (o0.nlog2 == 1 ? 0.5 : 1.0)); // SIM:241
-        for (uint32_t k = 0; k < n; ++k) {
-            cs = __dadd_rn(cs, pr);
-            if (!found && cs > u) {
-                found = true;
-                pick = resolve(lut, a, b, p, ma, mb, aa == 0, ab == 0, n == 2 ? (k << 1) : k);
-                pick_c = (uint32_t)c;
+    const uint32_t ma[3] = { aa, slip_move(aa, 0), slip_move(aa, 1) };
+    const uint32_t mb[3] = { ab, slip_move(ab, 0), slip_move(ab, 1) };
+    const bool a_noop = aa == 0, b_noop = ab == 0;
+    const uint32_t p8 = p << 3;
+    uint32_t na[3], nb[3];
+    bool aib[3], ast[3], bia[3], bst[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        na[i] = lut[(a << 4) + 8u - p8 + (ma[i] & 7u)];       // SIM:308
+        nb[i] = lut[(b << 4) + p8 + (mb[i] & 7u)];            // SIM:309
+        aib[i] = na[i] == b; ast[i] = na[i] == a; bia[i] = nb[i] == a; bst[i] = nb[i] == b;
+    }
+    double E = 0.0;
+    bool le = true;                     // E_{k-1} <= u: the pick is not before combination k
+    uint32_t pick = 0;                  // combination | draw value << 4
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const int i = combo_a(k), j = combo_b(k);
+        const bool stay = (aib[i] & (bia[j] | bst[j])) | (bia[j] & ast[i]);
+        const bool c2 = (aib[i] & b_noop) | (bia[j] & a_noop);
+        const bool four = (na[i] == nb[j]) & !stay;
+        const uint32_t nl16 = four ? 32u : ((stay & !c2) ? 16u : 0u);           // 16 * log2(#outcomes)
+        const double pr = lds_f64(sc.prt + k * 48 + nl16);
+        E = __dadd_rn(E, pr);
+        uint32_t cand = (uint32_t)k;
+        if (nl16) {                                                             // rare: 2 or 4 outcomes
+            uint32_t slot = E <= u ? 1u : 0u;
+            E = __dadd_rn(E, pr);
+            if (nl16 == 32u) {
+                slot += E <= u ? 1u : 0u; E = __dadd_rn(E, pr);
+                slot += E <= u ? 1u : 0u; E = __dadd_rn(E, pr);
+                cand |= slot << 4;                                              // 4-way: draw value r = slot
+            } else {
+                cand |= slot << 5;                                              // 2-way: r = 2 * slot
             }
         }
-        if (found) break;
+        pick = le ? cand : pick;
+        le = E <= u;
     }
-    if (!found) { pick = first; pick_c = first_c; }
-    return finish_step<AUTO_RESET>(P, pick, t, pick_c, reset_sel, flip_reward);
+    if (le) pick = sc.first_k;                                                  // all-False -> index 0 of the list
+    const uint32_t pk = pick & 15u;
+    const uint32_t ca = (uint32_t)(0x221121000ull >> (pk * 4)) & 3u, cb = (uint32_t)(0x212100210ull >> (pk * 4)) & 3u;
+    const uint32_t mas = ca == 0 ? ma[0] : (ca == 1 ? ma[1] : ma[2]);
+    const uint32_t mbs = cb == 0 ? mb[0] : (cb == 1 ? mb[1] : mb[2]);
+    const Resolved o = resolve(lut, a, b, p, mas, mbs, a_noop, b_noop, pick >> 4);
+    return finish_step<AUTO_RESET>(P, o, t, pk, reset_sel, flip_reward);
 }
 
 } // namespace soccer

@@ -193,23 +193,6 @@ struct LdGlobal {
 // no multiply), one DADD, one DSETP, one select.  A combination with 2 or 4 outcomes (< 3 % of them) takes a
 // short branch that adds its partial sums and moves the candidate to the slot inside it.  A zero-probability
 // combination (SIM:226-227) adds 0 and so can never become the pick.
-struct SlipCtx { uint32_t prt; uint32_t first_k; };     // shared address of prt[9][3] (16-byte stride); first combination with mp != 0
-constexpr int kPrtDoubles = 9 * 3 * 2;
-__device__ __forceinline__ void slip_build_prt(double* prt, const PitchDev& P)
-{
-    if (threadIdx.x < 27) {
-        const int k = threadIdx.x / 3, j = threadIdx.x % 3;
-        prt[2 * threadIdx.x] = __dmul_rn(P.mp[k], j == 2 ? 0.25 : (j == 1 ? 0.5 : 1.0));     // SIM:241
-        prt[2 * threadIdx.x + 1] = 0.0;
-    }
-}
-__device__ __forceinline__ uint32_t slip_first_k(const PitchDev& P)
-{
-    uint32_t f = 0;
-    for (int k = 8; k >= 0; --k) if (P.mp[k] != 0.0) f = (uint32_t)k;
-    return f;
-}
-
 __device__ __forceinline__ TblOut table_step_slip(const TblCtx& c, const SlipCtx& sc, uint32_t s, uint32_t aa, uint32_t ab,
                                                   double u, uint32_t rsel4)
 {
@@ -227,8 +210,7 @@ __device__ __forceinline__ TblOut table_step_slip(const TblCtx& c, const SlipCtx
         uint32_t hi;
         asm volatile("ld.shared.u8 %0, [%1+1];" : "=r"(hi) : "r"(ent));           // bits 4..5 = log2(#outcomes)
         const uint32_t nl4 = hi & 0x30u;                                          // 16 * log2(#outcomes) = prt byte offset
-        double pr;
-        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(pr) : "r"(sc.prt + k * 48 + nl4));
+        const double pr = lds_f64(sc.prt + k * 48 + nl4);
         E = __dadd_rn(E, pr);
         if (nl4) {                                                                // rare: 2 or 4 outcomes
             uint32_t slot = E <= u ? 1u : 0u;
