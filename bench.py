@@ -130,7 +130,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    T, N = 64, 1 << 15
+    T, N = 64, 1 << 18          # 16.8 M env-steps per bench step: ~50 ms on 16 cores, a stable sample
     import numpy as np
     from oracle import soccer_oracle as so
     m = so.OracleModel(5, 4, 0.0)
@@ -454,6 +454,20 @@ def run_ours(args):
             big[kern] = {"env_steps_per_s": n5 / (us * 1e-6), "hbm_gbs_at_12.125B": n5 * 12.125 / (us * 1e-6) / 1e9,
                          "frac_of_hbm_peak": n5 * 12.125 / (us * 1e-6) / 1e9 / peak}
         extra["fused_replay_2^22_envs_T64"] = big
+        # the reference's value iteration (planners.py:4-18) as ONE cooperative kernel launch
+        from gym_soccer_littman94_b200.utils import planners
+        from gym_soccer_littman94_b200.utils.policies import get_random_policy
+        ev = SoccerSimultaneousEnv(5, 4, slip_prob=0.2, player_b_policy=get_random_policy(761, 5, seed=42), device=dev)
+        planners.value_iteration(ev, 1e-10, 0.99)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        _, _, _, vi_cc = planners.value_iteration(ev, 1e-10, 0.99)
+        vi_ms = (time.perf_counter() - t0) * 1e3
+        extra["value_iteration_5x4_slip0.2"] = {
+            "sweeps": vi_cc, "ms": vi_ms, "us_per_sweep": vi_ms * 1e3 / vi_cc,
+            "note": "soccer_plan: whole value iteration (theta 1e-10, gamma 0.99) in one cooperative launch, bit-identical "
+                    "to the reference's planner, which takes 5.6 s for 183 sweeps on this env class in the build "
+                    "container (tests/golden/ref_planner_5x4_s020_a_free.npz vi_seconds)"}
     except Exception as e:  # noqa: BLE001
         extra["error"] = repr(e)
 

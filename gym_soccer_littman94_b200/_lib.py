@@ -25,6 +25,7 @@ EXPORTS = (
     "soccer_rollout_table", "soccer_step_table_bytes_host", "soccer_convert_state", "soccer_step_stats",
     "soccer_step_host", "soccer_step_host_scratch_bytes_host", "soccer_step_many", "soccer_bench_stream_mix",
     "soccer_bench_rollout_probe", "soccer_rollout_table_policy", "soccer_step_table_slip",
+    "soccer_bellman_q", "soccer_plan", "soccer_plan_workspace_bytes_host",
 )
 
 
@@ -127,6 +128,9 @@ def lib():
         "soccer_rollout_table_policy": [PP, vp, vp, vp, vp, u64, u64, i32, u64, vp, vp, vp, vp, i64, vp],
         "soccer_step_table_slip": [PP, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp],
         "soccer_convert_state": [PP, vp, vp, i32, i64, vp],
+        "soccer_bellman_q": [PP, vp, vp, vp, C.c_double, vp, vp],
+        "soccer_plan_workspace_bytes_host": [PP, C.POINTER(i64)],
+        "soccer_plan": [PP, vp, vp, vp, C.c_double, C.c_double, i32, vp, vp, vp, vp, vp, vp],
         "soccer_step_stats": [vp, vp, i64, vp, vp],
         "soccer_step_host": [PP, C.POINTER(StepHostArgs)],
         "soccer_step_many": [PP, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, i64, vp],

@@ -13,6 +13,7 @@
 #include "soccer_rules4.cuh"
 #include "soccer_rollout.cuh"
 #include "soccer_replay.cuh"
+#include "soccer_planner.cuh"
 
 #include <cuda_runtime.h>
 
@@ -1189,6 +1190,53 @@ int soccer_dense(const soccer_pitch* pitch, const int8_t* policy_a, const int8_t
     if (e != cudaSuccess) return (int)e;
     k_dense<<<grid_for((int64_t)nS * nkeys, 4), kThreads, 0, st>>>(P, nS, n_goal_states, policy_a, policy_b, Pmat, Rmat);
     return launch_status();
+}
+
+int soccer_bellman_q(const soccer_pitch* pitch, const int8_t* policy_a, const int8_t* policy_b, const double* V,
+                     double gamma, double* Q, soccer_stream_t stream)
+{
+    if (!V || !Q) return SOCCER_EINVAL;
+    if (policy_a && policy_b) return SOCCER_EPOLICY;
+    PitchDev P; const int rc = make_pitch_dev(pitch, &P); if (rc) return rc;
+    const int nkeys = (policy_a || policy_b) ? 5 : 25;
+    k_bellman_q<<<grid_for((int64_t)P.nS * nkeys, 8), kThreads, 0, (cudaStream_t)stream>>>(P, P.nS, policy_a, policy_b, V,
+                                                                                           gamma, Q);
+    return launch_status();
+}
+
+int soccer_plan_workspace_bytes_host(const soccer_pitch* pitch, int64_t* bytes)
+{
+    if (!bytes) return SOCCER_EINVAL;
+    PitchDev P; const int rc = make_pitch_dev(pitch, &P); if (rc) return rc;
+    *bytes = 2 * (int64_t)P.nS * 8 + 32;
+    return SOCCER_OK;
+}
+
+int soccer_plan(const soccer_pitch* pitch, const int8_t* policy_a, const int8_t* policy_b, const int32_t* pi_in,
+                double theta, double gamma, int32_t max_sweeps, double* V_out, double* Q_out, int32_t* pi_out,
+                int32_t* sweeps_out, void* workspace, soccer_stream_t stream)
+{
+    if (!V_out || !sweeps_out || !workspace || max_sweeps < 1 || !aligned(workspace, 8)) return SOCCER_EINVAL;
+    if (!pi_in && !Q_out) return SOCCER_EINVAL;                     // value iteration returns Q
+    if (policy_a && policy_b) return SOCCER_EPOLICY;
+    PitchDev P; const int rc = make_pitch_dev(pitch, &P); if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t ws = 2 * (int64_t)P.nS * 8 + 32;
+    cudaError_t e = cudaMemsetAsync(workspace, 0, (size_t)ws, st);   // V = 0 (PL:6, 22), delta slots = 0
+    if (e != cudaSuccess) return (int)e;
+    PlanArgs a;
+    a.nS = P.nS; a.policy_a = policy_a; a.policy_b = policy_b; a.pi_in = pi_in;
+    a.theta = theta; a.gamma = gamma; a.max_sweeps = max_sweeps;
+    a.v0 = reinterpret_cast<double*>(workspace); a.v1 = a.v0 + P.nS;
+    a.delta = reinterpret_cast<unsigned long long*>(a.v1 + P.nS);
+    a.V_out = V_out; a.Q_out = Q_out; a.pi_out = pi_out; a.sweeps_out = sweeps_out;
+    // cooperative launch: every CTA must be resident for the grid-wide barriers
+    static const int nb = resident_blocks(k_plan);
+    const int nkeys = (policy_a || policy_b) ? 5 : 25;
+    const int grid = grid_for((int64_t)P.nS * (pi_in ? 1 : nkeys), nb);
+    void* args[] = { (void*)&P, (void*)&a };
+    e = cudaLaunchCooperativeKernel((const void*)k_plan, dim3((unsigned)grid), dim3(kThreads), args, 0, st);
+    return (int)e;
 }
 
 } // extern "C"

@@ -34,11 +34,9 @@ struct TableStepper {
     TblCtx c;
     uint32_t pol_a, pol_b;      // shared-window addresses of the int8[nS] table policies, 0 = uniform (POLICY only)
     SlipCtx sc;                 // slip-combination probability table (SLIP only)
-    __device__ __forceinline__ void unpack(uint32_t&, uint32_t&) const {}
-    __device__ __forceinline__ uint32_t pack(uint32_t s, uint32_t) const { return s; }
-    __device__ __forceinline__ uint32_t timestep(uint32_t s, uint32_t) const { return s >> 16; }
+    __device__ __forceinline__ uint32_t timestep(uint32_t s) const { return s >> 16; }
     template <int VEC>
-    __device__ __forceinline__ void step(uint32_t* s, uint32_t*, const uint32_t* word, uint32_t* oo, uint32_t* rr,
+    __device__ __forceinline__ void step(uint32_t* s, const uint32_t* word, uint32_t* oo, uint32_t* rr,
                                          uint32_t& fw, int32_t& net, uint64_t seed, uint64_t env0, uint64_t step_abs) const
     {
         uint32_t ff[4] = { 0, 0, 0, 0 };
@@ -69,11 +67,9 @@ struct TableStepper {
 
 struct RulesStepper {
     const PitchDev& P; const uint8_t* lut; Isd4 I; const int8_t* policy_a; const int8_t* policy_b; SlipCtx sc;
-    __device__ __forceinline__ void unpack(uint32_t&, uint32_t&) const {}          // the packed CELL word as is
-    __device__ __forceinline__ uint32_t pack(uint32_t s, uint32_t) const { return s; }
-    __device__ __forceinline__ uint32_t timestep(uint32_t s, uint32_t) const { return (s >> 16) & 0xFFu; }
+    __device__ __forceinline__ uint32_t timestep(uint32_t s) const { return (s >> 16) & 0xFFu; }
     template <int VEC>
-    __device__ __forceinline__ void step(uint32_t* s, uint32_t*, const uint32_t* word, uint32_t* oo, uint32_t* rr,
+    __device__ __forceinline__ void step(uint32_t* s, const uint32_t* word, uint32_t* oo, uint32_t* rr,
                                          uint32_t& fw, int32_t& net, uint64_t seed, uint64_t env0, uint64_t step_abs) const
     {
         if (P.slip) {
@@ -160,10 +156,9 @@ __device__ __forceinline__ void rollout_body(const Stepper& S, const RolloutArgs
         } else {
             s[0] = a.state[i0];
         }
-        uint32_t aux[4] = { 0, 0, 0, 0 };
         uint32_t t_in = 0;
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) { S.unpack(s[e], aux[e]); t_in += S.timestep(s[e], aux[e]); }
+        for (int e = 0; e < VEC; ++e) t_in += S.timestep(s[e]);
         uint32_t acc_d = 0, acc_t = 0;
         int32_t* op = a.obs ? a.obs + i0 : nullptr;
         float* rp = a.reward ? a.reward + i0 : nullptr;
@@ -188,7 +183,7 @@ __device__ __forceinline__ void rollout_body(const Stepper& S, const RolloutArgs
                 uint32_t word[4], oo[4], rr[4], fw;
 #pragma unroll
                 for (int e = 0; e < VEC; ++e) word[e] = w[e][j];
-                S.template step<VEC>(s, aux, word, oo, rr, fw, c_net, a.seed, a.env_id_base + (uint64_t)i0, a.step0 + (uint64_t)k);
+                S.template step<VEC>(s, word, oo, rr, fw, c_net, a.seed, a.env_id_base + (uint64_t)i0, a.step0 + (uint64_t)k);
                 acc_d += fw & 0x01010101u;
                 acc_t += (fw >> 1) & ~fw & 0x01010101u;                 // truncated WITHOUT a goal
                 if (VEC == 4) {
@@ -209,7 +204,7 @@ __device__ __forceinline__ void rollout_body(const Stepper& S, const RolloutArgs
         c_done = __dp4a(acc_d, 0x01010101u, c_done); c_trunc = __dp4a(acc_t, 0x01010101u, c_trunc);
         uint32_t t_out = 0;
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) { t_out += S.timestep(s[e], aux[e]); s[e] = S.pack(s[e], aux[e]); }
+        for (int e = 0; e < VEC; ++e) t_out += S.timestep(s[e]);
         c_len += t_in + (uint32_t)K * VEC - t_out;
         c_steps += (uint32_t)K * VEC;
         if (VEC == 4) reinterpret_cast<uint4*>(a.state)[g] = make_uint4(s[0], s[1], s[2], s[3]);

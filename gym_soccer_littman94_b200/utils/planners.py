@@ -1,18 +1,66 @@
-"""Planners over the transition table, on the GPU.
+"""Planners over the transition dynamics, on the GPU.
 
-Same entry points, arguments and return tuples as the reference's gym_soccer/utils/planners.py
-(value_iteration :4-18, policy_iteration :45-55, modified_policy_iteration :73-87), for the
-single-agent (folded-policy) env they are written for.  Where the reference walks Python lists of
-(prob, next_state, reward, done) per (s, a), these run batched Bellman backups
-        Q = Rmat + gamma * Pmat . V          (one fp64 contraction over next states per sweep)
-on the dense Pmat[nS, nS, nA] / Rmat[nS, nA] that the `soccer_dense` kernel emits in the reference's
-own accumulation order.  The `* (not done)` factor of the reference (planners.py:11) only ever
-multiplies V[0] -- done transitions lead to the terminal observation 0 -- and V[0] stays 0, so it is
-dropped.  Results agree with the reference to fp64 round-off (the summation order over next states
-differs): identical greedy policies, |V - V_ref| < 1e-9 (tests/test_gpu_planners.py).
+Same entry points, arguments and return tuples as the reference's gym_soccer/utils/planners.py (= PL) for the
+single-agent (folded-policy) env they are written for.
+
+* value_iteration (PL:4-18), policy_evaluation (PL:20-31), policy_improvement (PL:33-43) and policy_iteration
+  (PL:45-55) walk `env.P` lists in the reference.  Here they call the hand-written kernels behind
+  `soccer_plan` / `soccer_bellman_q` (csrc/soccer_planner.cuh): one thread per (observation, action) enumerates
+  the same list in the same order and accumulates with the reference's fp64 operation order, and a whole value
+  iteration or policy evaluation runs inside ONE cooperative launch.  Results are bit-identical to the
+  reference's: V, Q, the greedy policy and the number of sweeps (tests/test_gpu_planners.py compares with ==).
+* policy_eval (PL:57-70) and modified_policy_iteration (PL:73-87) are written against the dense `Pmat` / `Rmat`
+  in the reference (np.dot); here they run the same contractions in fp64 on the device over the `soccer_dense`
+  kernel's output.  BLAS summation order is not reproducible, so these agree to fp64 round-off
+  (|V - V_ref| < 1e-9, identical greedy policies).
 """
+import ctypes as C
+
 import numpy as np
 import torch
+
+from .. import _lib
+
+MAX_SWEEPS = 1 << 30        # the reference loops until convergence; this only guards against theta <= 0
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _single_agent(env):
+    assert not env.multiagent, "planners act on a single-agent env (one player's policy folded, SIM:266-279)"
+    return env._lib, C.byref(env._pitch), _ptr(env._pol_a), _ptr(env._pol_b), env.device
+
+
+def _plan(env, pi_in, theta, gamma):
+    """soccer_plan: value iteration (pi_in None) or policy evaluation, one cooperative kernel launch."""
+    lib, pitch, pa, pb, dev = _single_agent(env)
+    nS, nA = env.nS, env.nA
+    nbytes = C.c_int64()
+    _lib.check(lib.soccer_plan_workspace_bytes_host(pitch, C.byref(nbytes)), "soccer_plan_workspace_bytes_host")
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+    V = torch.empty(nS, dtype=torch.float64, device=dev)
+    Q = torch.empty((nS, nA), dtype=torch.float64, device=dev) if pi_in is None else None
+    pi = torch.empty(nS, dtype=torch.int32, device=dev) if pi_in is None else None
+    sweeps = torch.zeros(1, dtype=torch.int32, device=dev)
+    pin = None if pi_in is None else torch.as_tensor(np.asarray(pi_in), dtype=torch.int32, device=dev).contiguous()
+    with torch.cuda.device(dev):
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(lib.soccer_plan(pitch, pa, pb, _ptr(pin), float(theta), float(gamma), MAX_SWEEPS, _ptr(V), _ptr(Q),
+                                   _ptr(pi), _ptr(sweeps), _ptr(ws), st), "soccer_plan")
+    return V, Q, pi, int(sweeps.item())
+
+
+def _backup_q(env, V, gamma):
+    """soccer_bellman_q: Q[nS, nA] of one backup of V (a device or host vector)."""
+    lib, pitch, pa, pb, dev = _single_agent(env)
+    Vd = torch.as_tensor(np.asarray(V) if not torch.is_tensor(V) else V, dtype=torch.float64, device=dev).contiguous()
+    Q = torch.empty((env.nS, env.nA), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(lib.soccer_bellman_q(pitch, pa, pb, _ptr(Vd), float(gamma), _ptr(Q), st), "soccer_bellman_q")
+    return Q
 
 
 def _dense(env):
@@ -31,48 +79,27 @@ def _backup(P, R, V, gamma):
 
 
 def value_iteration(env, theta, discount_factor):
-    """planners.py:4-18.  Returns (pi, V, Q, sweeps); V is the value BEFORE the last sweep, as there."""
-    P, R = _dense(env)
-    V = torch.zeros(P.shape[0], dtype=torch.float64, device=P.device)
-    cc = 0
-    while True:
-        Q = _backup(P, R, V, discount_factor)
-        cc += 1
-        newV = Q.max(dim=1).values
-        if float((V - newV).abs().max()) < theta:
-            break
-        V = newV
-    return Q.argmax(dim=1).cpu().numpy(), V.cpu().numpy(), Q.cpu().numpy(), cc
+    """PL:4-18.  Returns (pi, V, Q, sweeps); V is the value BEFORE the last sweep, as there."""
+    V, Q, pi, cc = _plan(env, None, theta, discount_factor)
+    return pi.cpu().numpy().astype(np.int64), V.cpu().numpy(), Q.cpu().numpy(), cc
 
 
 def policy_evaluation(pi, env, theta, discount_factor):
-    """planners.py:20-31: iterate V <- R_pi + gamma P_pi V from zero until the sup-norm change < theta."""
-    P, R = _dense(env)
-    idx = torch.as_tensor(np.asarray(pi), dtype=torch.int64, device=P.device)
-    ar = torch.arange(P.shape[0], device=P.device)
-    P_pi = P[ar, :, idx]                      # [nS, nS]
-    R_pi = R[ar, idx]
-    prev = torch.zeros_like(R_pi)
-    while True:
-        V = R_pi + discount_factor * (P_pi @ prev)
-        if float((prev - V).abs().max()) < theta:
-            break
-        prev = V
+    """PL:20-31: iterate V[s] <- sum over P[s][pi[s]] from zero until the sup-norm change < theta."""
+    V, _, _, _ = _plan(env, pi, theta, discount_factor)
     return V.cpu().numpy()
 
 
 def policy_improvement(V, env, discount_factor):
-    """planners.py:33-43."""
-    P, R = _dense(env)
-    Q = _backup(P, R, torch.as_tensor(V, dtype=torch.float64, device=P.device), discount_factor)
-    return Q.argmax(dim=1).cpu().numpy(), Q.cpu().numpy()
+    """PL:33-43."""
+    Q = _backup_q(env, V, discount_factor).cpu().numpy()
+    return np.argmax(Q, axis=1), Q
 
 
 def policy_iteration(env, theta, discount_factor):
-    """planners.py:45-55 (random initial policy from numpy's global generator, as there)."""
-    P, _ = _dense(env)
+    """PL:45-55 (random initial policy from numpy's global generator, as there)."""
     cc = 0
-    pi = np.random.choice(P.shape[2], P.shape[0])
+    pi = np.random.choice(tuple(range(env.nA)), env.nS)
     while True:
         old_pi = pi.copy()
         V = policy_evaluation(pi, env, theta, discount_factor)

@@ -294,6 +294,27 @@ int soccer_step_host(const soccer_pitch *pitch, const soccer_step_host_args *arg
 int soccer_dense(const soccer_pitch *pitch, const int8_t *policy_a, const int8_t *policy_b,
                  double *Pmat, double *Rmat, soccer_stream_t stream);
 
+/* ---- planners over the transition dynamics (/root/reference/gym_soccer/utils/planners.py = PL) ---- */
+/* One Bellman backup, PL:8-11 / 35-39: Q[s][key] = sum over the reference's P[s][key] list, in list
+ * order, of prob * (reward + gamma * V[next_state] * (not done)), with the reference's fp64 operation
+ * order (bit-identical Q).  key = own action (5) for a single-agent env (one table policy given,
+ * SIM:266-279; rewards from that player's side), the joint action aa*5+ab (25) otherwise.
+ * V fp64[nS], Q fp64[nS][nkeys], device pointers.  The lists are enumerated on the fly by the
+ * rules path; no table is read. */
+int soccer_bellman_q(const soccer_pitch *pitch, const int8_t *policy_a, const int8_t *policy_b,
+                     const double *V, double gamma, double *Q, soccer_stream_t stream);
+/* A whole planner in ONE cooperative launch (grid-wide barriers, no host round trip per sweep):
+ *   pi_in == NULL: value_iteration(env, theta, gamma), PL:4-18 -> V_out (the vector BEFORE the last
+ *                  sweep, as there), Q_out[nS][nkeys], pi_out[nS] = argmax (first maximum), *sweeps_out;
+ *   pi_in != NULL: policy_evaluation(pi_in, env, theta, gamma), PL:20-31 -> V_out, *sweeps_out.
+ * Bit-identical to the reference's results, sweep count included.  workspace: device memory of
+ * soccer_plan_workspace_bytes_host() bytes.  max_sweeps bounds the loop (the reference has none). */
+int soccer_plan_workspace_bytes_host(const soccer_pitch *pitch, int64_t *bytes);
+int soccer_plan(const soccer_pitch *pitch, const int8_t *policy_a, const int8_t *policy_b,
+                const int32_t *pi_in, double theta, double gamma, int32_t max_sweeps, double *V_out,
+                double *Q_out, int32_t *pi_out, int32_t *sweeps_out, void *workspace,
+                soccer_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

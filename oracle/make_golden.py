@@ -131,17 +131,28 @@ def gen_planner(slip, mode, theta=1e-10, gamma=0.99):
     env.P and modified policy iteration over env.Pmat / env.Rmat."""
     sys.path.insert(0, rh.REFERENCE_ROOT)
     env, pol = make_env(5, 4, slip, mode)
-    from gym_soccer.utils.planners import modified_policy_iteration, value_iteration
+    from gym_soccer.utils.planners import (modified_policy_iteration, policy_evaluation, policy_improvement,
+                                           policy_iteration, value_iteration)
     t0 = time.time()
     pi, V, Q, cc = value_iteration(env, theta=theta, discount_factor=gamma)
     t1 = time.time()
     mpi, mV, mQ, mcc = modified_policy_iteration(env, k=1, theta=theta, discount_factor=gamma)
+    t2 = time.time()
+    # the list-walking planners on a fixed (seeded) policy: evaluation, one improvement, full policy iteration
+    pe_pi = np.random.RandomState(99).randint(0, env.nA, env.nS)
+    pe_V = policy_evaluation(pe_pi, env, theta=1e-8, discount_factor=gamma)
+    imp_pi, imp_Q = policy_improvement(pe_V, env, discount_factor=gamma)
+    np.random.seed(4321)
+    it_pi, it_V, it_Q, it_cc = policy_iteration(env, theta=1e-8, discount_factor=gamma)
     tag = f"5x4_s{slip_tag(slip)}_{mode}"
     np.savez_compressed(os.path.join(OUT, f"ref_planner_{tag}.npz"), theta=theta, gamma=gamma,
                         policy=np.array([pol[s] for s in range(env.nS)], np.int8),
                         vi_pi=pi, vi_V=V, vi_Q=Q, vi_cc=cc, mpi_pi=mpi, mpi_V=mV, mpi_Q=mQ, mpi_cc=mcc,
-                        vi_seconds=t1 - t0, mpi_seconds=time.time() - t1)
-    print(f"planner {tag}: VI {cc} sweeps {t1 - t0:.1f}s, MPI {mcc} iterations {time.time() - t1:.1f}s", flush=True)
+                        pe_pi=pe_pi, pe_V=pe_V, pe_theta=1e-8, imp_pi=imp_pi, imp_Q=imp_Q,
+                        it_seed=4321, it_pi=it_pi, it_V=it_V, it_Q=it_Q, it_cc=it_cc,
+                        vi_seconds=t1 - t0, mpi_seconds=t2 - t1, pi_seconds=time.time() - t2)
+    print(f"planner {tag}: VI {cc} sweeps {t1 - t0:.1f}s, MPI {mcc} iterations {t2 - t1:.1f}s, "
+          f"PI {it_cc} iterations {time.time() - t2:.1f}s", flush=True)
 
 
 def main():

@@ -1,11 +1,13 @@
 """GPU planners (gym_soccer_littman94_b200/utils/planners.py) against the reference's planners
 (tests/golden/ref_planner_*.npz, produced by oracle/make_golden.py --planner-only from
-/root/reference/gym_soccer/utils/planners.py), and the best-response checks the reference's own
+/root/reference/gym_soccer/utils/planners.py = PL), and the best-response checks the reference's own
 integration tests make (/root/reference/gym_soccer/tests/test_general.py:304-458).
 
-Tolerance: the batched backup sums over next states in a different order than the reference's
-Python loops, so values agree to fp64 round-off, not bit for bit: |V - V_ref| <= 1e-9 (values are
-O(1), theta = 1e-10), identical greedy policies wherever the reference's own top-two Q gap > 1e-8."""
+The list-walking planners (value_iteration, policy_evaluation, policy_improvement, policy_iteration;
+PL:4-55) run on the hand-written Bellman kernels (soccer_plan / soccer_bellman_q), which reproduce the
+reference's list order and fp64 operation order: V, Q, greedy policy and sweep count are compared with ==.
+modified_policy_iteration (PL:73-87) is np.dot over Pmat / Rmat in the reference (BLAS order): compared to
+fp64 round-off, |V - V_ref| <= 1e-9, identical greedy policies wherever the reference's top-two Q gap > 1e-8."""
 import glob
 import os
 
@@ -40,13 +42,42 @@ def test_planners_match_reference(tag):
     env = _env(tag, g)
     theta, gamma = float(g["theta"]), float(g["gamma"])
     pi, V, Q, cc = planners.value_iteration(env, theta, gamma)
-    assert abs(cc - int(g["vi_cc"])) <= 1
-    assert np.abs(V - g["vi_V"]).max() <= 1e-9 and np.abs(Q - g["vi_Q"]).max() <= 1e-9
-    assert _same_policy(pi, g["vi_pi"], g["vi_Q"])
+    assert cc == int(g["vi_cc"])                                            # same number of sweeps
+    assert np.array_equal(V, g["vi_V"]) and np.array_equal(Q, g["vi_Q"])    # bit for bit
+    assert np.array_equal(pi, g["vi_pi"])
+    # policy evaluation of a fixed policy, one improvement step, full policy iteration (PL:20-55)
+    pe_V = planners.policy_evaluation(g["pe_pi"], env, float(g["pe_theta"]), gamma)
+    assert np.array_equal(pe_V, g["pe_V"])
+    imp_pi, imp_Q = planners.policy_improvement(g["pe_V"], env, gamma)
+    assert np.array_equal(imp_Q, g["imp_Q"]) and np.array_equal(imp_pi, g["imp_pi"])
+    np.random.seed(int(g["it_seed"]))
+    ppi, pV, pQ, pcc = planners.policy_iteration(env, float(g["pe_theta"]), gamma)
+    assert pcc == int(g["it_cc"]) and np.array_equal(ppi, g["it_pi"])
+    assert np.array_equal(pV, g["it_V"]) and np.array_equal(pQ, g["it_Q"])
+    # dense planners: fp64 round-off
     mpi, mV, mQ, mcc = planners.modified_policy_iteration(env, 1, theta, gamma)
     assert np.abs(mV - g["mpi_V"]).max() <= 1e-9 and _same_policy(mpi, g["mpi_pi"], g["mpi_Q"])
-    ppi, pV, pQ, pcc = planners.policy_iteration(env, theta, gamma)
-    assert np.abs(pV - g["vi_V"]).max() <= 1e-7 and _same_policy(ppi, g["vi_pi"], g["vi_Q"])
+
+
+def test_bellman_q_joint_actions_vs_dense():
+    """soccer_bellman_q on the multi-agent env gives the joint-action backup Q[s, aa, ab] (what minimax-Q needs):
+    checked against Rmat + gamma * Pmat . V from the dense kernel's (reference-pinned) matrices."""
+    import ctypes as C
+    from gym_soccer_littman94_b200 import _lib
+    from gym_soccer_littman94_b200.envs import SoccerSimultaneousEnv
+    env = SoccerSimultaneousEnv(width=5, height=4, slip_prob=0.2)
+    dev = env.device
+    V = torch.rand(env.nS, dtype=torch.float64, device=dev, generator=torch.Generator(device=dev).manual_seed(1))
+    V[0] = 0.0
+    Q = torch.empty((env.nS, 25), dtype=torch.float64, device=dev)
+    _lib.check(env._lib.soccer_bellman_q(C.byref(env._pitch), None, None, C.c_void_p(V.data_ptr()), 0.9,
+                                         C.c_void_p(Q.data_ptr()), None), "soccer_bellman_q")
+    torch.cuda.synchronize()
+    P = torch.from_numpy(np.ascontiguousarray(env.Pmat)).to(dev)       # [nS, nS, 5, 5]
+    R = torch.from_numpy(np.ascontiguousarray(env.Rmat)).to(dev)       # [nS, 5, 5]
+    want = (R + 0.9 * torch.einsum("snab,n->sab", P, V)).reshape(env.nS, 25)
+    want[0] = 0.0           # P[0]: the absorbing terminal observation, every entry done (Pmat[0, 0] holds the quirk sum)
+    assert float((Q - want).abs().max()) < 1e-12
 
 
 def test_best_response_beats_stand_and_random_policies():
