@@ -809,15 +809,27 @@ int soccer_rollout(const soccer_pitch* pitch, uint32_t* state, const int8_t* pol
                      (!reward || aligned(reward, 16)) && (!flags || aligned(flags, 4));
     const RolloutArgs ra = { state, seed, step0, K, env_id_base, obs, reward, flags, stats, n };
     const bool streams = obs && reward && flags;
-#define SOCCER_LAUNCH_ROLLOUT(VEC, STR, ITEMS)                                                          \
+#define SOCCER_LAUNCH_ROLLOUT(VEC, STR, SLIP, ITEMS)                                                    \
     do {                                                                                                 \
-        static const int nb = resident_blocks(k_rollout<VEC, STR>);                                      \
-        k_rollout<VEC, STR><<<grid_for(ITEMS, nb), kThreads, 0, st>>>(P, policy_a, policy_b, ra);         \
+        static const int nb = resident_blocks(k_rollout<VEC, STR, SLIP>);                                \
+        k_rollout<VEC, STR, SLIP><<<grid_for(ITEMS, nb), kThreads, 0, st>>>(P, policy_a, policy_b, ra);   \
     } while (0)
-    if (vec && streams) SOCCER_LAUNCH_ROLLOUT(4, true, n / 4);
-    else if (vec) SOCCER_LAUNCH_ROLLOUT(4, false, n / 4);
-    else if (streams) SOCCER_LAUNCH_ROLLOUT(1, true, n);
-    else SOCCER_LAUNCH_ROLLOUT(1, false, n);
+#define SOCCER_PICK_ROLLOUT(SLIP)                                                                        \
+    do {                                                                                                 \
+        if (vec && streams) SOCCER_LAUNCH_ROLLOUT(4, true, SLIP, n / 4);                                 \
+        else if (vec) SOCCER_LAUNCH_ROLLOUT(4, false, SLIP, n / 4);                                      \
+        else if (streams) SOCCER_LAUNCH_ROLLOUT(1, true, SLIP, n);                                       \
+        else SOCCER_LAUNCH_ROLLOUT(1, false, SLIP, n);                                                   \
+    } while (0)
+    if (P.slip) {
+        // the slip walk needs ~170 registers with 4 envs per thread (one 8-warp CTA per SM); one env per thread
+        // keeps 16 warps resident and measures 2.2x faster (44 vs 20 G env-steps/s, profiles/time_k2_rules_vec.py)
+        if (streams) SOCCER_LAUNCH_ROLLOUT(1, true, true, n);
+        else SOCCER_LAUNCH_ROLLOUT(1, false, true, n);
+    } else {
+        SOCCER_PICK_ROLLOUT(false);
+    }
+#undef SOCCER_PICK_ROLLOUT
 #undef SOCCER_LAUNCH_ROLLOUT
     return launch_status();
 }
@@ -964,7 +976,11 @@ int soccer_rollout_table_policy(const soccer_pitch* pitch, const uint16_t* table
         else if (streams) SOCCER_LAUNCH_ROLLOUT_T(1, true, POL, SLIP, n);                                \
         else SOCCER_LAUNCH_ROLLOUT_T(1, false, POL, SLIP, n);                                            \
     } while (0)
-    if (P.slip) SOCCER_PICK_ROLLOUT_T(true, true);       // slip: the policy-capable instantiation serves both
+    if (P.slip) {                                        // slip: the policy-capable instantiation serves both;
+        // one env per thread (the walk's registers): 70 vs 60 G env-steps/s with 4 (profiles/time_k2_rules_vec.py)
+        if (streams) SOCCER_LAUNCH_ROLLOUT_T(1, true, true, true, n);
+        else SOCCER_LAUNCH_ROLLOUT_T(1, false, true, true, n);
+    }
     else if (pol) SOCCER_PICK_ROLLOUT_T(true, false);
     else SOCCER_PICK_ROLLOUT_T(false, false);
 #undef SOCCER_PICK_ROLLOUT_T

@@ -65,6 +65,9 @@ struct TableStepper {
     }
 };
 
+// SLIP is a template parameter so that the slip-0 instantiation carries none of the walk's registers (with a
+// run-time branch the 4-env kernel needed 170 registers instead of 116 and lost its second resident CTA)
+template <bool SLIP>
 struct RulesStepper {
     const PitchDev& P; const uint8_t* lut; Isd4 I; const int8_t* policy_a; const int8_t* policy_b; SlipCtx sc;
     __device__ __forceinline__ uint32_t timestep(uint32_t s) const { return (s >> 16) & 0xFFu; }
@@ -72,7 +75,7 @@ struct RulesStepper {
     __device__ __forceinline__ void step(uint32_t* s, const uint32_t* word, uint32_t* oo, uint32_t* rr,
                                          uint32_t& fw, int32_t& net, uint64_t seed, uint64_t env0, uint64_t step_abs) const
     {
-        if (P.slip) {
+        if (SLIP) {
             // slip_prob > 0 (SIM:203-227): the scalar 9-combination walk with a 53-bit Philox uniform
             fw = 0;
 #pragma unroll
@@ -267,7 +270,7 @@ k_rollout_table(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t 
     rollout_body<VEC, STREAMS>(S, a, blk_stats, &blk_net);
 }
 
-template <int VEC, bool STREAMS>
+template <int VEC, bool STREAMS, bool SLIP>
 __global__ void __launch_bounds__(kThreads)
 k_rollout(const PitchDev P, const int8_t* __restrict__ policy_a, const int8_t* __restrict__ policy_b, const RolloutArgs a)
 {
@@ -275,13 +278,13 @@ k_rollout(const PitchDev P, const int8_t* __restrict__ policy_a, const int8_t* _
     __shared__ __align__(16) double prt[kPrtDoubles];
     __shared__ unsigned int blk_stats[4];
     __shared__ int blk_net;
-    if (P.slip) slip_build_prt(prt, P);
+    if (SLIP) slip_build_prt(prt, P);
     build_cand_lut(lut, P);
     if (threadIdx.x < 4) blk_stats[threadIdx.x] = 0;
     if (threadIdx.x == 4) blk_net = 0;
     __syncthreads();
-    const SlipCtx sc = { (uint32_t)__cvta_generic_to_shared(prt), P.slip ? slip_first_k(P) : 0u };
-    const RulesStepper S = { P, lut, make_isd4(P), policy_a, policy_b, sc };
+    const SlipCtx sc = { (uint32_t)__cvta_generic_to_shared(prt), SLIP ? slip_first_k(P) : 0u };
+    const RulesStepper<SLIP> S = { P, lut, make_isd4(P), policy_a, policy_b, sc };
     rollout_body<VEC, STREAMS>(S, a, blk_stats, &blk_net);
 }
 
