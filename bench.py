@@ -435,7 +435,20 @@ def run_ours(args):
             ef.reset(r[0])
             fused[kern] = timed(lambda: ef.step_many(a, b, r, out=o2), reps=10)
         us_fused = min(fused.values())
+        # the same 4096 envs stepped from HOST buffers, closed loop (every step waits for its results)
+        eh = SoccerVecEnv(n2, device=dev, kernel="auto", want_reset_obs=False)
+        eh.reset(r[0])
+        h3 = [tuple(x[t].cpu().pin_memory() for x in (a, b, r)) for t in range(8)]
+        host_us = {}
+        for name, zc in (("zero_copy", True), ("staged", False)):
+            for t in range(20):
+                eh.step_host(*h3[t % 8], zero_copy=zc)
+            t0 = time.perf_counter()
+            for t in range(500):
+                eh.step_host(*h3[t % 8], zero_copy=zc)
+            host_us[name] = (time.perf_counter() - t0) / 500 * 1e6
         extra["config2_4096_envs"] = {
+            "us_per_step_host_buffers_closed_loop": host_us,
             "k1_kernel": e2.kernel, "us_per_step_k1_python_loop": us_py, "us_per_step_k1_cuda_graph": us_graph,
             "us_per_step_fused_replay": fused, "env_steps_per_s": n2 / (us_fused * 1e-6),
             "note": "82 KB per step: K1 is launch-latency bound here (not graded against the HBM roofline); "

@@ -1135,7 +1135,9 @@ int soccer_step_host(const soccer_pitch* pitch, const soccer_step_host_args* a)
     if (a->n == 0) return SOCCER_OK;
     cudaStream_t s_in = (cudaStream_t)a->s_in, s_k = (cudaStream_t)a->s_compute, s_out = (cudaStream_t)a->s_out;
     const HostScratch sc = host_scratch(a->scratch, a->n);
-    const int64_t chunk = round_up((a->n + a->n_chunks - 1) / a->n_chunks, 256);
+    // slices below 64 Ki envs only add launch / copy latency: small batches go through in one piece
+    int64_t chunk = round_up((a->n + a->n_chunks - 1) / a->n_chunks, 256);
+    if (chunk < 65536) chunk = 65536;
 #define SOCCER_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { rc = (int)e_; goto done; } } while (0)
     int rc = SOCCER_OK;
     cudaEvent_t ev_prev_k = nullptr, ev_prev_out = nullptr, ev_in = nullptr, ev_k = nullptr;

@@ -340,15 +340,19 @@ class SoccerVecEnv:
                 h_reward=torch.empty(n, dtype=torch.int8 if narrow else torch.float32).pin_memory()))
         return self._host_common, getattr(self, key)
 
+    ZERO_COPY_MAX_ENVS = 32768
+
     def step_host(self, act_a: torch.Tensor, act_b: torch.Tensor, rng8: torch.Tensor, narrow: bool = False,
-                  n_chunks: int = 8, sync: bool = True):
+                  n_chunks: int = 8, sync: bool = True, zero_copy: Optional[bool] = None):
         """step() with HOST buffers -- the end-to-end path bench.py reports as `e2e`.
 
         In: uint8 CPU tensors (pinned memory keeps the copies asynchronous).  Out: CPU tensors
         owned by the env and overwritten by the next call -- obs int32 / reward float32 / flags
         uint8, or with narrow=True obs uint16 (viewed as int16 by torch) / reward int8: same values,
         4 instead of 9 bytes per env over PCIe.  The batch is cut into n_chunks slices whose upload,
-        kernel and download overlap on three streams (soccer_step_host in the C ABI)."""
+        kernel and download overlap on three streams (soccer_step_host in the C ABI).  Batches of up to
+        ZERO_COPY_MAX_ENVS envs with pinned inputs skip the staging: the kernel reads and writes the pinned
+        host buffers directly (zero_copy=None: automatic)."""
         if self.slip_prob != 0.0 or not self.multiagent or self.rng_mode != "injected":
             raise NotImplementedError("step_host covers the multi-agent, slip_prob == 0, injected-draw step")
         for name, t in (("act_a", act_a), ("act_b", act_b), ("rng8", rng8)):
@@ -357,6 +361,25 @@ class SoccerVecEnv:
                 raise ValueError(f"{name} must be a contiguous uint8 CPU tensor with {self.num_envs} elements")
         common, hb = self._host_buffers(narrow)
         if self.num_envs == 0:
+            return hb["h_obs"], hb["h_reward"], common["h_flags"]
+        if zero_copy is None:
+            zero_copy = self.num_envs <= self.ZERO_COPY_MAX_ENVS
+        if zero_copy and not narrow and act_a.is_pinned() and act_b.is_pinned() and rng8.is_pinned():
+            # small batch: the step kernel reads the pinned action / draw buffers and writes the pinned result
+            # buffers itself over PCIe (unified addressing): one launch + one synchronize, no copies, no staging
+            with torch.cuda.device(self.device):
+                cur = torch.cuda.current_stream(self.device)
+                st = C.c_void_p(cur.cuda_stream)
+                ptrs = (_ptr(act_a), _ptr(act_b), _ptr(rng8), _ptr(hb["h_obs"]), _ptr(hb["h_reward"]),
+                        _ptr(common["h_flags"]), None, self.num_envs, st)
+                if self.kernel == "table":
+                    check(self.lib.soccer_step_table(C.byref(self.pitch), _ptr(self.table), _ptr(self.state), *ptrs),
+                          "soccer_step_table")
+                else:
+                    check(self.lib.soccer_step(C.byref(self.pitch), _ptr(self.state), *ptrs), "soccer_step")
+                self.step_count += 1
+                if sync:
+                    cur.synchronize()
             return hb["h_obs"], hb["h_reward"], common["h_flags"]
         s_in, s_k, s_out = common["streams"]
         cur = torch.cuda.current_stream(self.device)
