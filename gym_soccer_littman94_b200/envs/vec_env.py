@@ -75,6 +75,8 @@ class SoccerVecEnv:
         self.policy_a = self._policy_tensor(player_a_policy)
         self.policy_b = self._policy_tensor(player_b_policy)
         self.want_reset_obs = bool(want_reset_obs)
+        self._pitch_ref = C.byref(self.pitch)
+        self._plain = self.rng_mode == "injected" and self.multiagent and self.slip_prob == 0.0
 
         _nb = C.c_int64()
         table_ok = self.multiagent and self.lib.soccer_step_table_bytes_host(C.byref(self.pitch), C.byref(_nb)) == 0
@@ -191,6 +193,28 @@ class SoccerVecEnv:
         """
         obs, reward, flags, reset_obs = out if out is not None else (self.obs, self.reward, self.flags, self.reset_obs)
         if self.num_envs == 0:
+            return obs, reward, flags, reset_obs
+        # fast host path for the plain lock-step step (injected draws, slip 0, no folded policy, no options): small
+        # batches are bound by this Python code, so it makes one ctypes call with integer pointers and nothing else
+        if self._plain and auto_reset and not detail and rng32 is None and rngf64 is None \
+                and act_a is not None and act_b is not None and rng8 is not None \
+                and torch.cuda.current_device() == self.device.index:
+            cv, u8 = self._check_vec, torch.uint8
+            st = torch.cuda.current_stream(self.device).cuda_stream
+            ro = None if reset_obs is None else reset_obs.data_ptr()
+            if self.kernel == "table":
+                rc = self.lib.soccer_step_table(self._pitch_ref, self.table.data_ptr(), self.state.data_ptr(),
+                                                cv(act_a, u8, "act_a").data_ptr(), cv(act_b, u8, "act_b").data_ptr(),
+                                                cv(rng8, u8, "rng8").data_ptr(), obs.data_ptr(), reward.data_ptr(),
+                                                flags.data_ptr(), ro, self.num_envs, st)
+            else:
+                rc = self.lib.soccer_step(self._pitch_ref, self.state.data_ptr(),
+                                          cv(act_a, u8, "act_a").data_ptr(), cv(act_b, u8, "act_b").data_ptr(),
+                                          cv(rng8, u8, "rng8").data_ptr(), obs.data_ptr(), reward.data_ptr(),
+                                          flags.data_ptr(), ro, self.num_envs, st)
+            if rc:
+                check(rc, "soccer_step")
+            self.step_count += 1
             return obs, reward, flags, reset_obs
         with torch.cuda.device(self.device):
             st = _stream(self.device)
