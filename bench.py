@@ -176,6 +176,31 @@ def host_info():
     return {"cpu": model, "logical_cpus": os.cpu_count(), "python": sys.version.split()[0], "numpy": numpy.__version__}
 
 
+def bind_near_gpu(local):
+    """Pin this rank to the CPU cores NVML reports as local to its GPU, BEFORE any pinned host buffer is allocated
+    (first touch puts the buffers on that NUMA node): the end-to-end path is PCIe- and host-memory-bound, and with
+    several ranks per box a buffer on the far socket costs a trip over the inter-socket link.  Best effort."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(local).uuid)
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+        except Exception:  # noqa: BLE001
+            h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {i * 64 + b for i, w in enumerate(mask) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:  # noqa: BLE001
+        pass
+    return None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -188,6 +213,7 @@ def run_ours(args):
     assert torch.cuda.is_available(), "bench.py needs a B200; there is no CPU fallback"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cpus = bind_near_gpu(local) if (world > 1 and not args.no_bind) else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     N = args.envs_per_gpu
@@ -514,7 +540,7 @@ def run_ours(args):
         "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": 1, "kind": "port", "sample": cpu_sample, "host": host_info(),
                          "all_cores": {"value": cpu_all_v, "cores": cores}},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 3 * N, "d2h_bytes_per_step": 4 * N,
-                "steps": Ke, "checksum": checksum, "chunks": args.chunks,
+                "steps": Ke, "checksum": checksum, "chunks": args.chunks, "cpus_bound_near_gpu": numa_cpus,
                 "api": "SoccerVecEnv.step_host(narrow=True): uint8 actions/draws up; obs uint16, reward int8, "
                        "flags uint8 down; every step waits for its results",
                 "wide": {"value": e2e[False][0], "d2h_bytes_per_step": 9 * N,
@@ -538,6 +564,7 @@ def main():
     ap.add_argument("--kernel", default="auto", choices=["auto", "rules", "table"])
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--chunks", type=int, default=8, help="pipeline slices of the host-buffer step")
+    ap.add_argument("--no-bind", action="store_true", help="do not pin ranks to the CPU cores local to their GPU")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
