@@ -296,7 +296,7 @@ def run_ours(args):
         _lib.check(env.lib.soccer_bench_stream_mix(
             C.c_void_p(scratch_state.data_ptr()), C.c_void_p(a_.data_ptr()), C.c_void_p(b_.data_ptr()),
             C.c_void_p(r_.data_ptr()), C.c_void_p(o_.data_ptr()), C.c_void_p(w_.data_ptr()), C.c_void_p(f_.data_ptr()),
-            N, cur_stream), "soccer_bench_stream_mix")
+            N, 0, cur_stream), "soccer_bench_stream_mix")
     for i in range(W):
         probe(i)
     barrier()
@@ -429,6 +429,28 @@ def run_ours(args):
         extra["config1_single_env_dropin"] = dict(c1, note="20,000 step() calls of ONE env through the reference's class "
                                                   "surface; latency-bound (one launch + sync per step), reported next to "
                                                   "the reference's 29.6 k steps/s Python loop (BASELINE.md)")
+        # K1 with a state tensor far beyond the L2 (2^26 envs: 268 MB of state, 1.34 GB per step): the DRAM-only figure
+        n6 = 1 << 26
+        e6 = SoccerVecEnv(n6, device=dev, kernel=args.kernel, want_reset_obs=False)
+        g6 = torch.Generator(device=dev).manual_seed(7)
+        in6 = [tuple(torch.randint(0, hi, (n6,), dtype=torch.uint8, device=dev, generator=g6) for hi in (5, 5, 16)) for _ in range(2)]
+        out6 = [(torch.empty(n6, dtype=torch.int32, device=dev), torch.empty(n6, dtype=torch.float32, device=dev),
+                 torch.empty(n6, dtype=torch.uint8, device=dev), None) for _ in range(2)]
+        e6.reset(in6[0][2])
+        for i in range(3):
+            e6.step(*in6[i % 2], out=out6[i % 2])
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        q0.record()
+        for i in range(20):
+            e6.step(*in6[i % 2], out=out6[i % 2])
+        q1.record()
+        torch.cuda.synchronize()
+        ms6 = q0.elapsed_time(q1) / 20
+        extra["k1_2^26_envs"] = {"kernel": e6.kernel, "env_steps_per_s": n6 / (ms6 * 1e-3),
+                                 "hbm_gbs_at_20B": n6 * 20 / (ms6 * 1e-3) / 1e9, "frac_of_hbm_peak": n6 * 20 / (ms6 * 1e-3) / 1e9 / peak}
+        del e6, in6, out6
+        torch.cuda.empty_cache()
         n2, T2 = 4096, 1000
         e2 = SoccerVecEnv(n2, device=dev, kernel="auto", want_reset_obs=False)
         a, b, r = (torch.randint(0, hi, (T2, n2), dtype=torch.uint8, device=dev) for hi in (5, 5, 16))
@@ -530,8 +552,12 @@ def run_ours(args):
                          f"cycle through {RING}-deep rings", "parallelism": f"independent env shards x{world}"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_source": traffic_src, "traffic_note": "DRAM bytes per launch in an "
-                     "isolated (ncu-serialised) launch; below the algorithmic 335.5 MB because dirty lines still sit in L2 "
-                     "when the kernel ends", "peak_source": peak_src, "kernel": kname,
+                     "isolated (ncu-serialised, cache-flushed) launch; below the algorithmic 335.5 MB because dirty lines "
+                     "still sit in L2 when the kernel ends",
+                     "l2_note": "achieved counts ALGORITHMIC bytes: at 2^24 envs the 67 MB state tensor written by step i "
+                                "is partly still in the 126 MB L2 when step i+1 reads it, so frac can exceed the DRAM-only "
+                                "figure (extra.k1_2^26_envs: 268 MB of state, no reuse)",
+                     "peak_source": peak_src, "kernel": kname,
                      "bytes_per_env_step": BYTES_PER_ENV_STEP, "avg_launch_ms": kern_ms, "min_launch_ms": min(per_launch),
                      "stream_mix_probe": {"achieved": probe_gbs, "unit": "GB/s", "kernel_over_probe": achieved / probe_gbs,
                                           "what": "k_stream_mix_probe: K1's streams, access pattern and launch shape "

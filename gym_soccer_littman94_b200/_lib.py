@@ -134,7 +134,7 @@ def lib():
         "soccer_step_stats": [vp, vp, i64, vp, vp],
         "soccer_step_host": [PP, C.POINTER(StepHostArgs)],
         "soccer_step_many": [PP, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, i64, vp],
-        "soccer_bench_stream_mix": [vp, vp, vp, vp, vp, vp, vp, i64, vp],
+        "soccer_bench_stream_mix": [vp, vp, vp, vp, vp, vp, vp, i64, i32, vp],
         "soccer_bench_rollout_probe": [vp, i32, vp, vp, vp, i64, i32, vp],
         "soccer_step_host_scratch_bytes_host": [i64, C.POINTER(i64)],
     }

@@ -431,6 +431,9 @@ int table_bytes_of(const PitchDev& P, int64_t* bytes)
 // access pattern, same cache hints, same launch shape -- with the game logic replaced by a few
 // XORs.  Its throughput is the practical HBM ceiling for K1's 7-bytes-read / 13-bytes-written mix,
 // which a read:write = 1:1 copy benchmark does not measure.
+// MODE 0: K1's order (groups g and g + grid * 1024 per iteration); 1: every CTA streams through ONE contiguous
+// region of the batch; 2: pairs of adjacent 1024-group tiles dealt round-robin over the CTAs
+template <int MODE>
 __global__ void __launch_bounds__(kTableThreads, 1)
 k_stream_mix_probe(uint32_t* __restrict__ state, const uint8_t* __restrict__ act_a, const uint8_t* __restrict__ act_b,
                    const uint8_t* __restrict__ rng, int32_t* __restrict__ obs, float* __restrict__ reward,
@@ -444,9 +447,20 @@ k_stream_mix_probe(uint32_t* __restrict__ state, const uint8_t* __restrict__ act
     uint4* w4 = reinterpret_cast<uint4*>(reward);
     uint32_t* f4 = reinterpret_cast<uint32_t*>(flags);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_groups; g += 2 * stride) {
-        const int64_t g2 = g + stride;
-        const bool two = g2 < n_groups;
+    int64_t g, gend, step2, second;
+    if (MODE == 1) {
+        const int64_t per = ((n_groups + gridDim.x - 1) / gridDim.x + 2 * blockDim.x - 1) / (2 * blockDim.x) * (2 * blockDim.x);
+        g = (int64_t)blockIdx.x * per + threadIdx.x;
+        gend = min(n_groups, (int64_t)(blockIdx.x + 1) * per);
+        step2 = 2 * blockDim.x; second = blockDim.x;
+    } else if (MODE == 2) {
+        g = (int64_t)blockIdx.x * 2 * blockDim.x + threadIdx.x; gend = n_groups; step2 = 2 * stride; second = blockDim.x;
+    } else {
+        g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gend = n_groups; step2 = 2 * stride; second = stride;
+    }
+    for (; g < gend; g += step2) {
+        const int64_t g2 = g + second;
+        const bool two = g2 < gend;
         const Group4 x0 = load_group(st4, a4, b4, r4, g);
         Group4 x1 = x0;
         if (two) x1 = load_group(st4, a4, b4, r4, g2);
@@ -1007,14 +1021,20 @@ int soccer_convert_state(const soccer_pitch* pitch, const uint32_t* in, uint32_t
 }
 
 int soccer_bench_stream_mix(uint32_t* state, const uint8_t* act_a, const uint8_t* act_b, const uint8_t* rng8,
-                            int32_t* obs, float* reward, uint8_t* flags, int64_t n, soccer_stream_t stream)
+                            int32_t* obs, float* reward, uint8_t* flags, int64_t n, int32_t mode, soccer_stream_t stream)
 {
     if (!state || !act_a || !act_b || !rng8 || !obs || !reward || !flags || n < 4 || (n & 3)) return SOCCER_EINVAL;
     if (!aligned(state, 16) || !aligned(obs, 16) || !aligned(reward, 16) || !aligned(act_a, 4) || !aligned(act_b, 4) ||
         !aligned(rng8, 4) || !aligned(flags, 4))
         return SOCCER_EINVAL;
-    k_stream_mix_probe<<<table_grid(n / 4), kTableThreads, 0, (cudaStream_t)stream>>>(state, act_a, act_b, rng8, obs,
-                                                                                      reward, flags, n / 4);
+    const int grid = table_grid(n / 4);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (mode) {
+    case 0: k_stream_mix_probe<0><<<grid, kTableThreads, 0, st>>>(state, act_a, act_b, rng8, obs, reward, flags, n / 4); break;
+    case 1: k_stream_mix_probe<1><<<grid, kTableThreads, 0, st>>>(state, act_a, act_b, rng8, obs, reward, flags, n / 4); break;
+    case 2: k_stream_mix_probe<2><<<grid, kTableThreads, 0, st>>>(state, act_a, act_b, rng8, obs, reward, flags, n / 4); break;
+    default: return SOCCER_EINVAL;
+    }
     return launch_status();
 }
 

@@ -192,11 +192,13 @@ __device__ __forceinline__ uint4 ld_stream(const uint4* p) { return __ldcs(p); }
 __device__ __forceinline__ uint32_t ld_stream(const uint32_t* p) { return __ldcs(p); }
 __device__ __forceinline__ void st_stream(uint4* p, uint4 v) { __stcs(p, v); }
 __device__ __forceinline__ void st_stream(uint32_t* p, uint32_t v) { __stcs(p, v); }
-// The state word is the one stream that is re-read (by the next step): its lines are marked
-// L2::evict_last so that, when the state tensor fits the 126 MB L2, it stays resident and the
-// step's DRAM traffic drops from 20 to 12 bytes per env.  -DSOCCER_STATE_EVICT_LAST=0 disables.
+// The state word is the one stream that is re-read (by the next step).  Marking its lines L2::evict_last
+// (-DSOCCER_STATE_EVICT_LAST=1) was meant to keep the state tensor resident in the 126 MB L2; measured on
+// B200 it LOSES to the default replacement policy -- 2^24 envs (67 MB of state): 308 vs 329 G env-steps/s for
+// the table kernel, 296 vs 310 G for the rules kernel; equal at 2^22 and 2^26 (profiles/r01g_ab_evict_last.log)
+// -- so plain accesses are the default.
 #ifndef SOCCER_STATE_EVICT_LAST
-#define SOCCER_STATE_EVICT_LAST 1
+#define SOCCER_STATE_EVICT_LAST 0
 #endif
 __device__ __forceinline__ uint64_t keep_policy()
 {

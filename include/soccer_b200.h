@@ -174,10 +174,11 @@ int soccer_step_stats(const uint8_t *flags, const float *reward, int64_t n,
 /* Measurement probe, not part of the game: K1's memory traffic (7 bytes read, 13 written per env,
  * same access pattern and cache hints) with no game logic.  bench.py times it next to K1 to show
  * the practical HBM ceiling for K1's read:write mix.  n % 4 == 0, aligned pointers; it overwrites
- * state / obs / reward / flags with meaningless values. */
+ * state / obs / reward / flags with meaningless values.  mode 0 = K1's group order; 1, 2 = order
+ * experiments (see k_stream_mix_probe). */
 int soccer_bench_stream_mix(uint32_t *state, const uint8_t *act_a, const uint8_t *act_b,
                             const uint8_t *rng8, int32_t *obs, float *reward, uint8_t *flags,
-                            int64_t n, soccer_stream_t stream);
+                            int64_t n, int32_t mode, soccer_stream_t stream);
 
 /* Measurement probe for K2: the fused rollout's memory traffic (state in/out once, K x 9 bytes per
  * env streamed to the [K][n] obs / reward / flags arrays with K2's stores, launch shape and slot
