@@ -25,7 +25,7 @@ EXPORTS = (
     "soccer_rollout_table", "soccer_step_table_bytes_host", "soccer_convert_state", "soccer_step_stats",
     "soccer_step_host", "soccer_step_host_scratch_bytes_host", "soccer_step_many", "soccer_bench_stream_mix",
     "soccer_bench_rollout_probe", "soccer_rollout_table_policy", "soccer_step_table_slip",
-    "soccer_bellman_q", "soccer_plan", "soccer_plan_workspace_bytes_host",
+    "soccer_bellman_q", "soccer_plan", "soccer_plan_workspace_bytes_host", "soccer_step_table_philox",
 )
 
 
@@ -124,6 +124,7 @@ def lib():
         "soccer_step_table_bytes_host": [PP, C.POINTER(i64)],
         "soccer_build_step_table": [PP, vp, vp],
         "soccer_step_table": [PP, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp],
+        "soccer_step_table_philox": [PP, vp, vp, vp, vp, u64, u64, u64, vp, vp, vp, vp, i64, vp],
         "soccer_rollout_table": [PP, vp, vp, u64, u64, i32, u64, vp, vp, vp, vp, i64, vp],
         "soccer_rollout_table_policy": [PP, vp, vp, vp, vp, u64, u64, i32, u64, vp, vp, vp, vp, i64, vp],
         "soccer_step_table_slip": [PP, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp],

@@ -170,16 +170,6 @@ __device__ __forceinline__ void step_group(const PitchDev& P, const Isd4& I, con
     if (RESET_OBS) st_stream(rob + g, make_uint4(o.robs[0], o.robs[1], o.robs[2], o.robs[3]));
 }
 
-// Philox draws of the 4 envs of a group as rng8-compatible bytes (soccer_step_philox: K1 with on-device draws)
-struct PhiloxKey { uint64_t seed, step, env_id_base; };
-__device__ __forceinline__ uint32_t philox_rng8x4(const PhiloxKey& k, int64_t g)
-{
-    uint32_t r[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) r[e] = philox_rng8(philox_word(k.seed, k.env_id_base + (uint64_t)(4 * g + e), k.step));
-    return pack4(r[0], r[1], r[2], r[3]);
-}
-
 template <bool RESET_OBS, bool PHILOX = false>
 __global__ void __launch_bounds__(kThreads)
 k_step_fast(const PitchDev P, uint32_t* __restrict__ state, const uint8_t* __restrict__ act_a,
@@ -876,11 +866,16 @@ int soccer_build_step_table(const soccer_pitch* pitch, uint16_t* table, soccer_s
     return launch_status();
 }
 
-int soccer_step_table(const soccer_pitch* pitch, const uint16_t* table, uint32_t* state, const uint8_t* act_a,
-                      const uint8_t* act_b, const uint8_t* rng8, int32_t* obs, float* reward, uint8_t* flags,
-                      int32_t* reset_obs, int64_t n, soccer_stream_t stream)
+} // extern "C"
+namespace {
+using namespace soccer;
+// soccer_step_table / soccer_step_table_philox: the draws come from the rng8 stream or, when it is NULL, from Philox
+int step_table_impl(const soccer_pitch* pitch, const uint16_t* table, uint32_t* state, const uint8_t* act_a,
+                    const uint8_t* act_b, const uint8_t* rng8, const PhiloxKey key, int32_t* obs, float* reward,
+                    uint8_t* flags, int32_t* reset_obs, int64_t n, soccer_stream_t stream)
 {
-    if (!table || !state || !act_a || !act_b || !rng8 || !obs || !reward || !flags || n < 0) return SOCCER_EINVAL;
+    const bool philox = rng8 == nullptr;
+    if (!table || !state || !act_a || !act_b || !obs || !reward || !flags || n < 0) return SOCCER_EINVAL;
     if (pitch && pitch->slip_prob != 0.0) return SOCCER_ESLIP;          // soccer_step_table_slip takes the step draw
     PitchDev P; int rc = make_pitch_dev(pitch, &P); if (rc) return rc;
     int64_t bytes; rc = table_bytes_of(P, &bytes); if (rc) return rc;
@@ -889,33 +884,51 @@ int soccer_step_table(const soccer_pitch* pitch, const uint16_t* table, uint32_t
     cudaStream_t st = (cudaStream_t)stream;
     const bool vec = n >= 4 && aligned(state, 16) && aligned(obs, 16) && aligned(reward, 16) &&
                      (!reset_obs || aligned(reset_obs, 16)) && aligned(act_a, 4) && aligned(act_b, 4) &&
-                     aligned(rng8, 4) && aligned(flags, 4);
+                     (philox || aligned(rng8, 4)) && aligned(flags, 4);
     int64_t done_n = 0;
     if (vec) {
         const int64_t n_groups = n / 4;
-        if (reset_obs) {
-            const int e0 = allow_big_smem(k_step_table<true>, bytes + 16);
-            if (e0) return e0;
-            const int e1 = launch_pdl(k_step_table<true>, table_grid(n_groups), kTableThreads, (size_t)bytes + 16, st,
-                                      P, table, (uint32_t)bytes, state, act_a, act_b, rng8, obs, reward, flags, reset_obs, n_groups);
-            if (e1) return e1;
-        } else {
-            const int e0 = allow_big_smem(k_step_table<false>, bytes + 16);
-            if (e0) return e0;
-            const int e1 = launch_pdl(k_step_table<false>, table_grid(n_groups), kTableThreads, (size_t)bytes + 16, st,
-                                      P, table, (uint32_t)bytes, state, act_a, act_b, rng8, obs, reward, flags, (int32_t*)nullptr, n_groups);
-            if (e1) return e1;
-        }
+#define SOCCER_LAUNCH_STEP_T(RO, PH)                                                                              \
+        do {                                                                                                      \
+            const int e0 = allow_big_smem(k_step_table<RO, PH>, bytes + 16);                                      \
+            if (e0) return e0;                                                                                    \
+            const int e1 = launch_pdl(k_step_table<RO, PH>, table_grid(n_groups), kTableThreads, (size_t)bytes + 16, st, \
+                                      P, table, (uint32_t)bytes, state, act_a, act_b, rng8, obs, reward, flags,   \
+                                      RO ? reset_obs : (int32_t*)nullptr, n_groups, key);                         \
+            if (e1) return e1;                                                                                    \
+        } while (0)
+        if (reset_obs) { if (philox) SOCCER_LAUNCH_STEP_T(true, true); else SOCCER_LAUNCH_STEP_T(true, false); }
+        else { if (philox) SOCCER_LAUNCH_STEP_T(false, true); else SOCCER_LAUNCH_STEP_T(false, false); }
+#undef SOCCER_LAUNCH_STEP_T
         const int e = launch_status();
         if (e) return e;
         done_n = n_groups * 4;
         if (done_n == n) return SOCCER_OK;
     }
     const int64_t k = done_n, m = n - k;
-    k_step_table_scalar<<<grid_for(m, 8), kThreads, 0, st>>>(P, table, state + k, act_a + k, act_b + k, rng8 + k,
-                                                             obs + k, reward + k, flags + k,
-                                                             reset_obs ? reset_obs + k : nullptr, m);
+    const PhiloxKey tail_key = { key.seed, key.step, key.env_id_base + (uint64_t)k };
+    k_step_table_scalar<<<grid_for(m, 8), kThreads, 0, st>>>(P, table, state + k, act_a + k, act_b + k,
+                                                             philox ? nullptr : rng8 + k, obs + k, reward + k, flags + k,
+                                                             reset_obs ? reset_obs + k : nullptr, m, philox ? 1 : 0, tail_key);
     return launch_status();
+}
+} // namespace
+extern "C" {
+
+int soccer_step_table(const soccer_pitch* pitch, const uint16_t* table, uint32_t* state, const uint8_t* act_a,
+                      const uint8_t* act_b, const uint8_t* rng8, int32_t* obs, float* reward, uint8_t* flags,
+                      int32_t* reset_obs, int64_t n, soccer_stream_t stream)
+{
+    if (!rng8) return SOCCER_EINVAL;
+    return step_table_impl(pitch, table, state, act_a, act_b, rng8, PhiloxKey(), obs, reward, flags, reset_obs, n, stream);
+}
+
+int soccer_step_table_philox(const soccer_pitch* pitch, const uint16_t* table, uint32_t* state, const uint8_t* act_a,
+                             const uint8_t* act_b, uint64_t seed, uint64_t step, uint64_t env_id_base, int32_t* obs,
+                             float* reward, uint8_t* flags, int32_t* reset_obs, int64_t n, soccer_stream_t stream)
+{
+    const PhiloxKey key = { seed, step, env_id_base };
+    return step_table_impl(pitch, table, state, act_a, act_b, nullptr, key, obs, reward, flags, reset_obs, n, stream);
 }
 
 int soccer_step_table_slip(const soccer_pitch* pitch, const uint16_t* table, uint32_t* state, const uint8_t* act_a,

@@ -131,15 +131,24 @@ __device__ __forceinline__ uint32_t obs_to_packed(const PitchDev& P, int32_t obs
 }
 
 // ---- Philox4x32-10 (Salmon et al. SC'11), one call = the words of 4 consecutive steps ----
+template <bool WIDE = false>
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                               uint32_t k0, uint32_t k1, uint32_t out[4])
 {
 #pragma unroll
     for (int i = 0; i < 10; ++i) {
-        // mul.hi + mul.lo (both on the FMA pipe) rather than one wide multiply: keeps the ALU pipe,
-        // which bounds the rollout kernels, for the 3-input XORs only
-        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
-        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        uint32_t h0, l0, h1, l1;
+        if (WIDE) {
+            // one 32x32 -> 64 multiply per product (IMAD.WIDE.U32): fewer instructions, but measured SLOWER on B200
+            // (K1 table + Philox at 2^24 envs: 200 vs 236 G env-steps/s, profiles/r01g_time_k1_philox.log) -- A/B only
+            const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+            h0 = (uint32_t)(p0 >> 32); l0 = (uint32_t)p0; h1 = (uint32_t)(p1 >> 32); l1 = (uint32_t)p1;
+        } else {
+            // mul.hi + mul.lo (both on the FMA pipe) rather than one wide multiply: keeps the ALU pipe,
+            // which bounds the rollout kernels, for the 3-input XORs only
+            h0 = __umulhi(0xD2511F53u, c0); l0 = 0xD2511F53u * c0;
+            h1 = __umulhi(0xCD9E8D57u, c2); l1 = 0xCD9E8D57u * c2;
+        }
         const uint32_t n0 = h1 ^ c1 ^ k0;
         const uint32_t n2 = h0 ^ c3 ^ k1;
         c1 = l1; c3 = l0; c0 = n0; c2 = n2;
@@ -148,12 +157,16 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
+#ifndef SOCCER_K1_PHILOX_WIDE
+#define SOCCER_K1_PHILOX_WIDE 0
+#endif
+template <bool WIDE = false>
 __device__ __forceinline__ uint32_t philox_word(uint64_t seed, uint64_t env_id, uint64_t step)
 {
     const uint64_t blk = step >> 2;
     uint32_t o[4];
-    philox4x32_10((uint32_t)env_id, (uint32_t)(env_id >> 32), (uint32_t)blk, (uint32_t)(blk >> 32),
-                  (uint32_t)seed, (uint32_t)(seed >> 32), o);
+    philox4x32_10<WIDE>((uint32_t)env_id, (uint32_t)(env_id >> 32), (uint32_t)blk, (uint32_t)(blk >> 32),
+                        (uint32_t)seed, (uint32_t)(seed >> 32), o);
     const uint32_t k = (uint32_t)step & 3u;
     return k == 0 ? o[0] : (k == 1 ? o[1] : (k == 2 ? o[2] : o[3]));
 }
@@ -170,6 +183,17 @@ __device__ __forceinline__ void philox_actions(uint32_t w, uint32_t& aa, uint32_
 }
 // rng8-compatible nibble: bits 0..1 step draw, bits 2..3 reset draw
 __device__ __forceinline__ uint32_t philox_rng8(uint32_t w) { return (philox_jr(w) & 3u) | ((w & 3u) << 2); }
+
+// Philox draws of the 4 envs of a group as rng8-compatible bytes (soccer_step_philox / soccer_step_table_philox:
+// K1 with on-device draws)
+struct PhiloxKey { uint64_t seed, step, env_id_base; };
+__device__ __forceinline__ uint32_t philox_rng8x4(const PhiloxKey& k, int64_t g)
+{
+    uint32_t r[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) r[e] = philox_rng8(philox_word<SOCCER_K1_PHILOX_WIDE != 0>(k.seed, k.env_id_base + (uint64_t)(4 * g + e), k.step));
+    return r[0] | (r[1] << 8) | (r[2] << 16) | (r[3] << 24);
+}
 
 // slip_prob > 0 needs a fine-grained uniform for the categorical draw over up to 15 outcomes
 // (SIM:395): a 53-bit uniform in [0, 1), like np.random.RandomState.random(), from words 0 and 1

@@ -269,13 +269,15 @@ __device__ __forceinline__ void table_step_group(const TblCtx& c, const Group4& 
     if (RESET_OBS) st_stream(rob + g, make_uint4(ro[0], ro[1], ro[2], ro[3]));
 }
 
-// K1, table variant: persistent, one 1024-thread CTA per SM.
-template <bool RESET_OBS>
+// K1, table variant: persistent, one 1024-thread CTA per SM.  PHILOX (soccer_step_table_philox): the draw stream is
+// not read (19 B / env-step); the draws of a group are computed while the next pair's loads are in flight.
+template <bool RESET_OBS, bool PHILOX = false>
 __global__ void __launch_bounds__(kTableThreads, 1)
 k_step_table(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t table_bytes,
              uint32_t* __restrict__ state, const uint8_t* __restrict__ act_a, const uint8_t* __restrict__ act_b,
              const uint8_t* __restrict__ rng, int32_t* __restrict__ obs, float* __restrict__ reward,
-             uint8_t* __restrict__ flags, int32_t* __restrict__ reset_obs, int64_t n_groups)
+             uint8_t* __restrict__ flags, int32_t* __restrict__ reset_obs, int64_t n_groups,
+             const PhiloxKey key = PhiloxKey())
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar;
@@ -287,7 +289,7 @@ k_step_table(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t tab
     uint4* st4 = reinterpret_cast<uint4*>(state);
     const uint32_t* a4 = reinterpret_cast<const uint32_t*>(act_a);
     const uint32_t* b4 = reinterpret_cast<const uint32_t*>(act_b);
-    const uint32_t* r4 = reinterpret_cast<const uint32_t*>(rng);
+    const uint32_t* r4 = PHILOX ? a4 : reinterpret_cast<const uint32_t*>(rng);   // PHILOX: value replaced below
     uint4* o4 = reinterpret_cast<uint4*>(obs);
     uint4* w4 = reinterpret_cast<uint4*>(reward);
     uint32_t* f4 = reinterpret_cast<uint32_t*>(flags);
@@ -307,6 +309,7 @@ k_step_table(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t tab
         Group4 y0 = x0, y1 = x1;
         if (n_one) y0 = load_group(st4, a4, b4, r4, gn);          // prefetch the next pair
         if (n_two) y1 = load_group(st4, a4, b4, r4, gn + stride);
+        if (PHILOX) { x0.r = philox_rng8x4(key, g); if (two) x1.r = philox_rng8x4(key, g + stride); }
         table_step_group<RESET_OBS>(c, x0, g, st4, o4, w4, f4, q4);
         if (two) table_step_group<RESET_OBS>(c, x1, g + stride, st4, o4, w4, f4, q4);
         x0 = y0; x1 = y1; g = gn; one = n_one; two = n_two;
@@ -318,13 +321,15 @@ __global__ void __launch_bounds__(kThreads)
 k_step_table_scalar(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t* __restrict__ state,
                     const uint8_t* __restrict__ act_a, const uint8_t* __restrict__ act_b,
                     const uint8_t* __restrict__ rng, int32_t* __restrict__ obs, float* __restrict__ reward,
-                    uint8_t* __restrict__ flags, int32_t* __restrict__ reset_obs, int64_t n)
+                    uint8_t* __restrict__ flags, int32_t* __restrict__ reset_obs, int64_t n,
+                    int use_philox = 0, const PhiloxKey key = PhiloxKey())
 {
     const int16_t* tbl = reinterpret_cast<const int16_t*>(gtable);
     const uint32_t last = (uint32_t)P.nS * 100u - 1u;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const uint32_t s = state[i], rg = rng[i];
+        const uint32_t s = state[i];
+        const uint32_t rg = use_philox ? philox_rng8(philox_word(key.seed, key.env_id_base + (uint64_t)i, key.step)) : rng[i];
         const uint32_t idx = min((s & 0xFFFFu) * 100u + (uint32_t)act_a[i] * 20u + (uint32_t)act_b[i] * 4u + (rg & 3u), last);
         const int32_t e = tbl[idx];
         const uint32_t nobs = (uint32_t)e & kTblObsMask;

@@ -220,7 +220,14 @@ class SoccerVecEnv:
             st = _stream(self.device)
             philox = self.rng_mode == "philox"
             general = philox or detail or not auto_reset          # options only the generic rules kernel offers
-            if self.kernel == "table" and not general:
+            if self.kernel == "table" and philox and self.multiagent and self.slip_prob == 0.0 and auto_reset and not detail:
+                # caller-supplied actions + Philox draws through the shared-memory table (19 B / env-step)
+                check(self.lib.soccer_step_table_philox(
+                    C.byref(self.pitch), _ptr(self.table), _ptr(self.state),
+                    _ptr(self._check_vec(act_a, torch.uint8, "act_a")), _ptr(self._check_vec(act_b, torch.uint8, "act_b")),
+                    self.seed, self.step_count, self.env_id_base, _ptr(obs), _ptr(reward), _ptr(flags), _ptr(reset_obs),
+                    self.num_envs, st), "soccer_step_table_philox")
+            elif self.kernel == "table" and not general:
                 args = (C.byref(self.pitch), _ptr(self.table), _ptr(self.state),
                         _ptr(self._check_vec(act_a, torch.uint8, "act_a")), _ptr(self._check_vec(act_b, torch.uint8, "act_b")),
                         _ptr(self._check_vec(rng8, torch.uint8, "rng8")))

@@ -224,6 +224,13 @@ int soccer_step_table(const soccer_pitch *pitch, const uint16_t *table, uint32_t
                       const uint8_t *act_a, const uint8_t *act_b, const uint8_t *rng8, int32_t *obs,
                       float *reward, uint8_t *flags, int32_t *reset_obs, int64_t n,
                       soccer_stream_t stream);
+/* soccer_step_philox (caller-supplied actions, draws from Philox4x32-10 keyed (seed, env_id_base + i,
+ * step) exactly as there) through the shared-memory table: 19 algorithmic bytes per env-step.
+ * SOCCER_LAYOUT_INDEX states; results identical to soccer_step_philox on the converted states. */
+int soccer_step_table_philox(const soccer_pitch *pitch, const uint16_t *table, uint32_t *state,
+                             const uint8_t *act_a, const uint8_t *act_b, uint64_t seed, uint64_t step,
+                             uint64_t env_id_base, int32_t *obs, float *reward, uint8_t *flags,
+                             int32_t *reset_obs, int64_t n, soccer_stream_t stream);
 /* step() with slip_prob > 0 (SIM:203-256) through the same shared-memory table: the outcome counts of
  * the 9 slipped move pairs are read from the state's table row, the categorical draw walks them in
  * the reference's order with sequential fp64 sums (bit-exact), one more look-up yields the chosen

@@ -577,19 +577,22 @@ def test_rollout_and_step_philox_with_slip_vs_oracle(dev, oracle, w, h, n, kerne
         assert np.array_equal(o.cpu().numpy(), eo[k]) and np.array_equal(f.cpu().numpy() & 3, ef[k]), k
 
 
-def test_step_philox_equals_rollout(dev):
-    """K1 in Philox mode fed the actions K2 draws for itself follows the same trajectory."""
+@pytest.mark.parametrize("kernel,N,base", [("rules", 512, 0), ("table", 512, 0), ("table", 4099, 1 << 33), ("rules", 4099, 77)])
+def test_step_philox_equals_rollout(dev, kernel, N, base):
+    """K1 in Philox mode (soccer_step_philox / soccer_step_table_philox, ragged tail included) fed the actions K2
+    draws for itself follows the same trajectory."""
     from gym_soccer_littman94_b200.envs import SoccerVecEnv
     from oracle import soccer_oracle as so
-    N, K, seed = 512, 40, 31337
-    a = SoccerVecEnv(N, device=dev, rng_mode="philox", kernel="rules", seed=seed)
-    b = SoccerVecEnv(N, device=dev, rng_mode="philox", kernel="rules", seed=seed)
+    K, seed = 40, 31337
+    a = SoccerVecEnv(N, device=dev, rng_mode="philox", kernel="rules", seed=seed, env_id_base=base)
+    b = SoccerVecEnv(N, device=dev, rng_mode="philox", kernel=kernel, seed=seed, env_id_base=base)
     a.reset(); b.reset()
     obs, rew, flg, _ = a.rollout(K)
     for k in range(K):
-        acts = np.array([so.philox_decode(so.philox_word(seed, i, k))[:2] for i in range(N)], np.uint8)
-        o, r, f, _ = b.step(_t(acts[:, 0].copy(), dev), _t(acts[:, 1].copy(), dev))
+        acts = np.array([so.philox_decode(so.philox_word(seed, base + i, k))[:2] for i in range(N)], np.uint8)
+        o, r, f, ro = b.step(_t(acts[:, 0].copy(), dev), _t(acts[:, 1].copy(), dev))
         assert torch.equal(o, obs[k]) and torch.equal(r, rew[k]) and torch.equal(f, flg[k])
+        assert torch.equal(ro, b.current_obs())
 
 
 def test_rollout_gpu_count_independence(dev):
