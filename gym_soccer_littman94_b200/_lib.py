@@ -25,7 +25,7 @@ EXPORTS = (
     "soccer_rollout_table", "soccer_step_table_bytes_host", "soccer_convert_state", "soccer_step_stats",
     "soccer_step_host", "soccer_step_host_scratch_bytes_host", "soccer_step_many", "soccer_bench_stream_mix",
     "soccer_bench_rollout_probe", "soccer_rollout_table_policy", "soccer_step_table_slip",
-    "soccer_bellman_q", "soccer_plan", "soccer_plan_workspace_bytes_host", "soccer_step_table_philox",
+    "soccer_bellman_q", "soccer_plan", "soccer_plan_workspace_bytes_host", "soccer_step_table_philox", "soccer_step_table_packed", "soccer_step_narrow", "soccer_host_alloc", "soccer_host_free",
 )
 
 
@@ -52,7 +52,7 @@ class StepArgs(C.Structure):
                 ("policy_b", C.c_void_p), ("obs", C.c_void_p), ("reward", C.c_void_p),
                 ("flags", C.c_void_p), ("reset_obs", C.c_void_p), ("n", C.c_int64),
                 ("auto_reset", C.c_int32), ("use_philox", C.c_int32), ("detail", C.c_int32),
-                ("reserved", C.c_int32), ("seed", C.c_uint64), ("step", C.c_uint64),
+                ("narrow", C.c_int32), ("seed", C.c_uint64), ("step", C.c_uint64),
                 ("env_id_base", C.c_uint64)]
 
 
@@ -125,6 +125,10 @@ def lib():
         "soccer_build_step_table": [PP, vp, vp],
         "soccer_step_table": [PP, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp],
         "soccer_step_table_philox": [PP, vp, vp, vp, vp, u64, u64, u64, vp, vp, vp, vp, i64, vp],
+        "soccer_host_alloc": [C.c_size_t, C.POINTER(C.c_void_p)],
+        "soccer_host_free": [C.c_void_p, C.c_size_t],
+        "soccer_step_narrow": [PP, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp],
+        "soccer_step_table_packed": [PP, vp, vp, vp, vp, vp, i64, vp],
         "soccer_rollout_table": [PP, vp, vp, u64, u64, i32, u64, vp, vp, vp, vp, i64, vp],
         "soccer_rollout_table_policy": [PP, vp, vp, vp, vp, u64, u64, i32, u64, vp, vp, vp, vp, i64, vp],
         "soccer_step_table_slip": [PP, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp],
@@ -159,6 +163,37 @@ def check(rc: int, what: str):
     if rc < 0:
         raise SoccerB200Error(f"{what}: {_ERR.get(rc, rc)}")
     raise SoccerB200Error(f"{what}: CUDA error {rc} (no CPU fallback exists; a B200 is required)")
+
+
+class HostArena:
+    """One pinned, device-mapped host allocation backed by 2 MB huge pages (soccer_host_alloc), handed out as
+    4 KB-aligned torch CPU tensors.  DMA reads from it run at the PCIe rate, which small individual
+    `tensor.pin_memory()` allocations do not reliably reach (profiles/r01g_probe_pcie2.log).  The memory is
+    released when the last tensor carved from it is gone."""
+
+    def __init__(self, nbytes: int):
+        import weakref
+        import numpy as np
+        import torch
+        nbytes = max(int(nbytes), 1)
+        ptr = C.c_void_p()
+        L = lib()
+        check(L.soccer_host_alloc(nbytes, C.byref(ptr)), "soccer_host_alloc")
+        self.nbytes, self.used = nbytes, 0
+        base = np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(ptr.value))
+        fin = weakref.finalize(base, L.soccer_host_free, ptr.value, nbytes)
+        fin.atexit = False                      # at interpreter exit the CUDA context may already be gone
+        self._bytes = torch.from_numpy(base)    # the storage keeps `base` alive
+
+    def take(self, numel: int, dtype):
+        """A pinned tensor of `numel` elements of `dtype` from the arena (4 KB aligned)."""
+        import torch
+        size = int(numel) * torch.empty(0, dtype=dtype).element_size()
+        off = (self.used + 4095) // 4096 * 4096
+        if off + size > self.nbytes:
+            raise SoccerB200Error(f"HostArena exhausted: {off + size} > {self.nbytes} bytes")
+        self.used = off + size
+        return self._bytes[off:off + size].view(dtype)
 
 
 def pitch_info(width: int, height: int, slip_prob: float = 0.0) -> PitchInfo:

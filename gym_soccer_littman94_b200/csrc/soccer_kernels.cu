@@ -16,6 +16,8 @@
 #include "soccer_planner.cuh"
 
 #include <cuda_runtime.h>
+#include <sys/mman.h>
+#include <string.h>
 
 using namespace soccer;
 
@@ -156,7 +158,7 @@ int launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaS
 inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 
 
-template <bool RESET_OBS>
+template <bool RESET_OBS, bool NARROW = false>
 __device__ __forceinline__ void step_group(const PitchDev& P, const Isd4& I, const uint8_t* lut, const Group4& x,
                                            int64_t g, uint4* st, uint4* obs, uint4* rew, uint32_t* flg, uint4* rob)
 {
@@ -164,13 +166,18 @@ __device__ __forceinline__ void step_group(const PitchDev& P, const Isd4& I, con
     Step4 o;
     step4_noslip<RESET_OBS>(P, I, lut, sv, x.a, x.b, x.r, o);     // byte-parallel over the 4 envs
     st_keep(st + g, make_uint4(o.s[0], o.s[1], o.s[2], o.s[3]));
-    st_stream(obs + g, make_uint4(o.obs[0], o.obs[1], o.obs[2], o.obs[3]));
-    st_stream(rew + g, make_uint4(o.rew[0], o.rew[1], o.rew[2], o.rew[3]));
+    if (NARROW) {                                                 // uint16 obs, int8 reward (soccer_step_narrow)
+        st_stream(reinterpret_cast<uint2*>(obs) + g, make_uint2(o.obs[0] | (o.obs[1] << 16), o.obs[2] | (o.obs[3] << 16)));
+        st_stream(reinterpret_cast<uint32_t*>(rew) + g, o.rew4);
+    } else {
+        st_stream(obs + g, make_uint4(o.obs[0], o.obs[1], o.obs[2], o.obs[3]));
+        st_stream(rew + g, make_uint4(o.rew[0], o.rew[1], o.rew[2], o.rew[3]));
+    }
     st_stream(flg + g, o.flags4);
     if (RESET_OBS) st_stream(rob + g, make_uint4(o.robs[0], o.robs[1], o.robs[2], o.robs[3]));
 }
 
-template <bool RESET_OBS, bool PHILOX = false>
+template <bool RESET_OBS, bool PHILOX = false, bool NARROW = false>
 __global__ void __launch_bounds__(kThreads)
 k_step_fast(const PitchDev P, uint32_t* __restrict__ state, const uint8_t* __restrict__ act_a,
             const uint8_t* __restrict__ act_b, const uint8_t* __restrict__ rng, int32_t* __restrict__ obs,
@@ -201,8 +208,8 @@ k_step_fast(const PitchDev P, uint32_t* __restrict__ state, const uint8_t* __res
         Group4 x1 = x0;
         if (two) x1 = load_group(st4, a4, b4, PHILOX ? a4 : r4, g2);
         if (PHILOX) { x0.r = philox_rng8x4(key, g); if (two) x1.r = philox_rng8x4(key, g2); }
-        step_group<RESET_OBS>(P, I, lut, x0, g, st4, o4, w4, f4, q4);
-        if (two) step_group<RESET_OBS>(P, I, lut, x1, g2, st4, o4, w4, f4, q4);
+        step_group<RESET_OBS, NARROW>(P, I, lut, x0, g, st4, o4, w4, f4, q4);
+        if (two) step_group<RESET_OBS, NARROW>(P, I, lut, x1, g2, st4, o4, w4, f4, q4);
     }
 }
 
@@ -213,7 +220,16 @@ struct StepOpts {
     const uint32_t* rng32; const double* rngf64; const int8_t* policy_a; const int8_t* policy_b;
     int32_t* obs; float* reward; uint8_t* flags; int32_t* reset_obs;
     int64_t n; int32_t auto_reset; int32_t use_philox; int32_t detail; uint64_t seed, step, env_id_base;
+    int32_t narrow;      // obs points at uint16[n], reward at int8[n] (soccer_step_narrow)
 };
+__device__ __forceinline__ void put_obs(const StepOpts& o, int64_t i, int32_t v)
+{
+    if (o.narrow) reinterpret_cast<uint16_t*>(o.obs)[i] = (uint16_t)v; else o.obs[i] = v;
+}
+__device__ __forceinline__ void put_reward(const StepOpts& o, int64_t i, float v)
+{
+    if (o.narrow) reinterpret_cast<int8_t*>(o.reward)[i] = (int8_t)(int)v; else o.reward[i] = v;
+}
 
 __global__ void __launch_bounds__(kThreads) k_step_generic(const PitchDev P, const StepOpts o)
 {
@@ -228,8 +244,8 @@ __global__ void __launch_bounds__(kThreads) k_step_generic(const PitchDev P, con
         const uint32_t a = s & 0xFFu, b = (s >> 8) & 0xFFu, p = (s >> 24) & 1u;
         const bool terminal_in = ((a | b) & kGoalBit) != 0;
         if (s & kNeedsReset) {                       // the assert at SIM:376: leave the env alone
-            if (o.obs) o.obs[i] = terminal_in ? 0 : obs_index(P, a, b, p);
-            if (o.reward) o.reward[i] = 0.0f;
+            if (o.obs) put_obs(o, i, terminal_in ? 0 : obs_index(P, a, b, p));
+            if (o.reward) put_reward(o, i, 0.0f);
             if (o.flags) o.flags[i] = 0xFFu;
             if (o.reset_obs) o.reset_obs[i] = terminal_in ? 0 : obs_index(P, a, b, p);
             continue;
@@ -262,8 +278,8 @@ __global__ void __launch_bounds__(kThreads) k_step_generic(const PitchDev P, con
                              : step_noslip<false>(P, lut, s, aa, ab, rng, flip);
         }
         o.state[i] = r.state;
-        if (o.obs) o.obs[i] = r.obs;
-        if (o.reward) o.reward[i] = r.reward;
+        if (o.obs) put_obs(o, i, r.obs);
+        if (o.reward) put_reward(o, i, r.reward);
         if (o.flags) o.flags[i] = (uint8_t)(o.detail ? r.flags : (r.flags & 3u));
         if (o.reset_obs) o.reset_obs[i] = r.reset_obs;
     }
@@ -516,29 +532,6 @@ k_step_stats(const uint8_t* __restrict__ flags, const float* __restrict__ reward
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&stats[4], (unsigned long long)n);
 }
 
-// obs int32 -> uint16, reward float32 -> int8 for the narrow host download (values are exact:
-// obs < nS <= 31501, reward in {-1, 0, +1})
-__global__ void __launch_bounds__(kThreads)
-k_narrow(const int32_t* __restrict__ obs, const float* __restrict__ reward, uint16_t* __restrict__ obs16,
-         int8_t* __restrict__ rew8, int64_t n)
-{
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const int64_t n4 = n / 4;
-    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n4; g += stride) {
-        const uint4 o = __ldcs(reinterpret_cast<const uint4*>(obs) + g);
-        const float4 r = __ldcs(reinterpret_cast<const float4*>(reward) + g);
-        const uint32_t lo = __byte_perm(o.x, o.y, 0x5410), hi = __byte_perm(o.z, o.w, 0x5410);
-        __stcs(reinterpret_cast<uint2*>(obs16) + g, make_uint2(lo, hi));
-        const uint32_t rb = ((uint32_t)(int)r.x & 0xFFu) | (((uint32_t)(int)r.y & 0xFFu) << 8) |
-                            (((uint32_t)(int)r.z & 0xFFu) << 16) | (((uint32_t)(int)r.w & 0xFFu) << 24);
-        __stcs(reinterpret_cast<uint32_t*>(rew8) + g, rb);
-    }
-    for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        obs16[i] = (uint16_t)obs[i];
-        rew8[i] = (int8_t)(int)reward[i];
-    }
-}
-
 int64_t round_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 // scratch layout of soccer_step_host: three input byte streams, flags, obs, reward, obs16, rew8
 struct HostScratch { uint8_t *a, *b, *r, *f; int32_t* obs; float* rew; uint16_t* obs16; int8_t* rew8; int64_t bytes; };
@@ -591,6 +584,37 @@ int allow_big_smem(Kern k, int64_t bytes)
 extern "C" {
 
 int soccer_abi_version(void) { return SOCCER_ABI_VERSION; }
+
+// ---- pinned host memory for the host-buffer path
+// Page-locked memory whose physical pages are 2 MB huge pages (2 MB-aligned anonymous mapping + MADV_HUGEPAGE,
+// touched, then cudaHostRegister): measured on the B200 boxes, DMA reads (host -> device copies and the kernels'
+// zero-copy loads) from a small cudaHostAlloc'd buffer run anywhere between 21 and 55 GB/s depending on the
+// physical pages it happened to get, from such a region always at 50-55 GB/s (profiles/r01g_probe_pcie2.log).
+static const size_t kHuge = (size_t)2 << 20;
+int soccer_host_alloc(size_t bytes, void** ptr)
+{
+    if (!ptr || bytes == 0) return SOCCER_EINVAL;
+    const size_t len = (bytes + kHuge - 1) / kHuge * kHuge;
+    uint8_t* raw = (uint8_t*)mmap(nullptr, len + kHuge, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (raw == MAP_FAILED) return (int)cudaErrorMemoryAllocation;
+    uint8_t* p = (uint8_t*)(((uintptr_t)raw + kHuge - 1) / kHuge * kHuge);
+    if (p > raw) munmap(raw, (size_t)(p - raw));                       // trim the slack on both sides:
+    if (p + len < raw + len + kHuge) munmap(p + len, (size_t)(raw + len + kHuge - (p + len)));   // [p, p + len) stays
+    madvise(p, len, MADV_HUGEPAGE);                                    // best effort; plain pages otherwise
+    memset(p, 0, len);                                                 // fault the pages in before pinning
+    const cudaError_t e = cudaHostRegister(p, len, cudaHostRegisterPortable | cudaHostRegisterMapped);
+    if (e != cudaSuccess) { munmap(p, len); return (int)e; }
+    *ptr = p;
+    return SOCCER_OK;
+}
+int soccer_host_free(void* ptr, size_t bytes)
+{
+    if (!ptr || bytes == 0) return SOCCER_EINVAL;
+    const size_t len = (bytes + kHuge - 1) / kHuge * kHuge;
+    const cudaError_t e = cudaHostUnregister(ptr);
+    munmap(ptr, len);
+    return (int)e;
+}
 
 int soccer_pitch_info_host(const soccer_pitch* pitch, soccer_pitch_info* out) { return fill_info(pitch, out); }
 
@@ -715,45 +739,31 @@ int soccer_step_ex(const soccer_pitch* pitch, const soccer_step_args* a, soccer_
     if (a->n == 0) return SOCCER_OK;
     cudaStream_t st = (cudaStream_t)stream;
 
-    if (a->reserved != 0) return SOCCER_EINVAL;
+    if (a->narrow != 0 && a->narrow != 1) return SOCCER_EINVAL;
+    const bool narrow = a->narrow == 1;
     const bool fast_ok = !P.slip && a->auto_reset && !a->detail && !a->policy_a && !a->policy_b &&
                          a->obs && a->reward && a->flags && a->n >= 4 &&
-                         aligned(a->state, 16) && aligned(a->obs, 16) && aligned(a->reward, 16) &&
+                         aligned(a->state, 16) && aligned(a->obs, narrow ? 8 : 16) && aligned(a->reward, narrow ? 4 : 16) &&
                          (!a->reset_obs || aligned(a->reset_obs, 16)) && aligned(a->act_a, 4) &&
-                         aligned(a->act_b, 4) && (a->use_philox || aligned(a->rng8, 4)) && aligned(a->flags, 4);
+                         aligned(a->act_b, 4) && (a->use_philox || aligned(a->rng8, 4)) && aligned(a->flags, 4) &&
+                         !(narrow && (a->use_philox || a->reset_obs));     // narrow fast path: the plain step only
     int64_t done_n = 0;
-    if (fast_ok && a->use_philox) {
-        // K1 with on-device Philox draws (soccer_step_philox): same byte-parallel kernel, 19 B / env-step
+    if (fast_ok) {
+        // byte-parallel rules kernel; with on-device Philox draws (soccer_step_philox) 19 B / env-step
         const int64_t n_groups = a->n / 4;
         const PhiloxKey key = { a->seed, a->step, a->env_id_base };
-        if (a->reset_obs) {
-            static const int nb = resident_blocks(k_step_fast<true, true>);
-            const int e1 = launch_pdl(k_step_fast<true, true>, grid_for(n_groups, nb), kThreads, 0, st, P, a->state, a->act_a,
-                                      a->act_b, (const uint8_t*)nullptr, a->obs, a->reward, a->flags, a->reset_obs, n_groups, key);
-            if (e1) return e1;
-        } else {
-            static const int nb = resident_blocks(k_step_fast<false, true>);
-            const int e1 = launch_pdl(k_step_fast<false, true>, grid_for(n_groups, nb), kThreads, 0, st, P, a->state, a->act_a,
-                                      a->act_b, (const uint8_t*)nullptr, a->obs, a->reward, a->flags, (int32_t*)nullptr, n_groups, key);
-            if (e1) return e1;
-        }
-        const int e = launch_status();
-        if (e) return e;
-        done_n = n_groups * 4;
-        if (done_n == a->n) return SOCCER_OK;
-    } else if (fast_ok) {
-        const int64_t n_groups = a->n / 4;
-        if (a->reset_obs) {
-            static const int nb = resident_blocks(k_step_fast<true>);
-            const int e1 = launch_pdl(k_step_fast<true>, grid_for(n_groups, nb), kThreads, 0, st,
-                                      P, a->state, a->act_a, a->act_b, a->rng8, a->obs, a->reward, a->flags, a->reset_obs, n_groups, PhiloxKey());
-            if (e1) return e1;
-        } else {
-            static const int nb = resident_blocks(k_step_fast<false>);
-            const int e1 = launch_pdl(k_step_fast<false>, grid_for(n_groups, nb), kThreads, 0, st,
-                                      P, a->state, a->act_a, a->act_b, a->rng8, a->obs, a->reward, a->flags, (int32_t*)nullptr, n_groups, PhiloxKey());
-            if (e1) return e1;
-        }
+#define SOCCER_LAUNCH_FAST(RO, PH, NR)                                                                            \
+        do {                                                                                                      \
+            static const int nb = resident_blocks(k_step_fast<RO, PH, NR>);                                       \
+            const int e1 = launch_pdl(k_step_fast<RO, PH, NR>, grid_for(n_groups, nb), kThreads, 0, st, P, a->state, \
+                                      a->act_a, a->act_b, PH ? (const uint8_t*)nullptr : a->rng8, a->obs, a->reward, \
+                                      a->flags, RO ? a->reset_obs : (int32_t*)nullptr, n_groups, key);            \
+            if (e1) return e1;                                                                                    \
+        } while (0)
+        if (narrow) SOCCER_LAUNCH_FAST(false, false, true);
+        else if (a->use_philox) { if (a->reset_obs) SOCCER_LAUNCH_FAST(true, true, false); else SOCCER_LAUNCH_FAST(false, true, false); }
+        else { if (a->reset_obs) SOCCER_LAUNCH_FAST(true, false, false); else SOCCER_LAUNCH_FAST(false, false, false); }
+#undef SOCCER_LAUNCH_FAST
         const int e = launch_status();
         if (e) return e;
         done_n = n_groups * 4;
@@ -768,12 +778,14 @@ int soccer_step_ex(const soccer_pitch* pitch, const soccer_step_args* a, soccer_
     o.rng32 = a->rng32 ? a->rng32 + k : nullptr;
     o.rngf64 = a->rngf64 ? a->rngf64 + k : nullptr;
     o.policy_a = a->policy_a; o.policy_b = a->policy_b;
-    o.obs = a->obs ? a->obs + k : nullptr;
-    o.reward = a->reward ? a->reward + k : nullptr;
+    // narrow: obs / reward hold 2- / 1-byte elements
+    o.obs = !a->obs ? nullptr : (narrow ? reinterpret_cast<int32_t*>(reinterpret_cast<uint16_t*>(a->obs) + k) : a->obs + k);
+    o.reward = !a->reward ? nullptr : (narrow ? reinterpret_cast<float*>(reinterpret_cast<int8_t*>(a->reward) + k) : a->reward + k);
     o.flags = a->flags ? a->flags + k : nullptr;
     o.reset_obs = a->reset_obs ? a->reset_obs + k : nullptr;
     o.n = a->n - k; o.auto_reset = a->auto_reset; o.use_philox = a->use_philox; o.detail = a->detail;
     o.seed = a->seed; o.step = a->step; o.env_id_base = a->env_id_base + (uint64_t)k;
+    o.narrow = a->narrow;
     return launch_generic(P, o, st);
 }
 
@@ -872,9 +884,10 @@ using namespace soccer;
 // soccer_step_table / soccer_step_table_philox: the draws come from the rng8 stream or, when it is NULL, from Philox
 int step_table_impl(const soccer_pitch* pitch, const uint16_t* table, uint32_t* state, const uint8_t* act_a,
                     const uint8_t* act_b, const uint8_t* rng8, const PhiloxKey key, int32_t* obs, float* reward,
-                    uint8_t* flags, int32_t* reset_obs, int64_t n, soccer_stream_t stream)
+                    uint8_t* flags, int32_t* reset_obs, int64_t n, soccer_stream_t stream, bool narrow = false)
 {
     const bool philox = rng8 == nullptr;
+    if (narrow && (philox || reset_obs)) return SOCCER_EINVAL;
     if (!table || !state || !act_a || !act_b || !obs || !reward || !flags || n < 0) return SOCCER_EINVAL;
     if (pitch && pitch->slip_prob != 0.0) return SOCCER_ESLIP;          // soccer_step_table_slip takes the step draw
     PitchDev P; int rc = make_pitch_dev(pitch, &P); if (rc) return rc;
@@ -882,23 +895,24 @@ int step_table_impl(const soccer_pitch* pitch, const uint16_t* table, uint32_t* 
     if (!aligned(table, 16)) return SOCCER_EINVAL;
     if (n == 0) return SOCCER_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    const bool vec = n >= 4 && aligned(state, 16) && aligned(obs, 16) && aligned(reward, 16) &&
+    const bool vec = n >= 4 && aligned(state, 16) && aligned(obs, narrow ? 8 : 16) && aligned(reward, narrow ? 4 : 16) &&
                      (!reset_obs || aligned(reset_obs, 16)) && aligned(act_a, 4) && aligned(act_b, 4) &&
                      (philox || aligned(rng8, 4)) && aligned(flags, 4);
     int64_t done_n = 0;
     if (vec) {
         const int64_t n_groups = n / 4;
-#define SOCCER_LAUNCH_STEP_T(RO, PH)                                                                              \
+#define SOCCER_LAUNCH_STEP_T(RO, PH, NR)                                                                            \
         do {                                                                                                      \
-            const int e0 = allow_big_smem(k_step_table<RO, PH>, bytes + 16);                                      \
+            const int e0 = allow_big_smem(k_step_table<RO, PH, NR>, bytes + 16);                                  \
             if (e0) return e0;                                                                                    \
-            const int e1 = launch_pdl(k_step_table<RO, PH>, table_grid(n_groups), kTableThreads, (size_t)bytes + 16, st, \
+            const int e1 = launch_pdl(k_step_table<RO, PH, NR>, table_grid(n_groups), kTableThreads, (size_t)bytes + 16, st, \
                                       P, table, (uint32_t)bytes, state, act_a, act_b, rng8, obs, reward, flags,   \
                                       RO ? reset_obs : (int32_t*)nullptr, n_groups, key);                         \
             if (e1) return e1;                                                                                    \
         } while (0)
-        if (reset_obs) { if (philox) SOCCER_LAUNCH_STEP_T(true, true); else SOCCER_LAUNCH_STEP_T(true, false); }
-        else { if (philox) SOCCER_LAUNCH_STEP_T(false, true); else SOCCER_LAUNCH_STEP_T(false, false); }
+        if (narrow) SOCCER_LAUNCH_STEP_T(false, false, true);
+        else if (reset_obs) { if (philox) SOCCER_LAUNCH_STEP_T(true, true, false); else SOCCER_LAUNCH_STEP_T(true, false, false); }
+        else { if (philox) SOCCER_LAUNCH_STEP_T(false, true, false); else SOCCER_LAUNCH_STEP_T(false, false, false); }
 #undef SOCCER_LAUNCH_STEP_T
         const int e = launch_status();
         if (e) return e;
@@ -907,9 +921,12 @@ int step_table_impl(const soccer_pitch* pitch, const uint16_t* table, uint32_t* 
     }
     const int64_t k = done_n, m = n - k;
     const PhiloxKey tail_key = { key.seed, key.step, key.env_id_base + (uint64_t)k };
+    int32_t* obs_k = narrow ? reinterpret_cast<int32_t*>(reinterpret_cast<uint16_t*>(obs) + k) : obs + k;
+    float* rew_k = narrow ? reinterpret_cast<float*>(reinterpret_cast<int8_t*>(reward) + k) : reward + k;
     k_step_table_scalar<<<grid_for(m, 8), kThreads, 0, st>>>(P, table, state + k, act_a + k, act_b + k,
-                                                             philox ? nullptr : rng8 + k, obs + k, reward + k, flags + k,
-                                                             reset_obs ? reset_obs + k : nullptr, m, philox ? 1 : 0, tail_key);
+                                                             philox ? nullptr : rng8 + k, obs_k, rew_k, flags + k,
+                                                             reset_obs ? reset_obs + k : nullptr, m, philox ? 1 : 0, tail_key,
+                                                             narrow ? 1 : 0);
     return launch_status();
 }
 } // namespace
@@ -929,6 +946,49 @@ int soccer_step_table_philox(const soccer_pitch* pitch, const uint16_t* table, u
 {
     const PhiloxKey key = { seed, step, env_id_base };
     return step_table_impl(pitch, table, state, act_a, act_b, nullptr, key, obs, reward, flags, reset_obs, n, stream);
+}
+
+int soccer_step_narrow(const soccer_pitch* pitch, const uint16_t* table, uint32_t* state, const uint8_t* act_a,
+                       const uint8_t* act_b, const uint8_t* rng8, uint16_t* obs16, int8_t* reward8, uint8_t* flags,
+                       int64_t n, soccer_stream_t stream)
+{
+    if (!obs16 || !reward8 || !flags || !rng8) return SOCCER_EINVAL;
+    if (pitch && pitch->slip_prob != 0.0) return SOCCER_ESLIP;
+    if (table)
+        return step_table_impl(pitch, table, state, act_a, act_b, rng8, PhiloxKey(), reinterpret_cast<int32_t*>(obs16),
+                               reinterpret_cast<float*>(reward8), flags, nullptr, n, stream, true);
+    soccer_step_args a = {};
+    a.state = state; a.act_a = act_a; a.act_b = act_b; a.rng8 = rng8; a.obs = reinterpret_cast<int32_t*>(obs16);
+    a.reward = reinterpret_cast<float*>(reward8); a.flags = flags; a.n = n; a.auto_reset = 1; a.narrow = 1;
+    return soccer_step_ex(pitch, &a, stream);
+}
+
+int soccer_step_table_packed(const soccer_pitch* pitch, const uint16_t* table, uint32_t* state, const uint8_t* joint,
+                             const uint8_t* rng8, uint16_t* result, int64_t n, soccer_stream_t stream)
+{
+    if (!table || !state || !joint || !rng8 || !result || n < 0) return SOCCER_EINVAL;
+    if (pitch && pitch->slip_prob != 0.0) return SOCCER_ESLIP;
+    PitchDev P; int rc = make_pitch_dev(pitch, &P); if (rc) return rc;
+    int64_t bytes; rc = table_bytes_of(P, &bytes); if (rc) return rc;
+    if (!aligned(table, 16)) return SOCCER_EINVAL;
+    if (n == 0) return SOCCER_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t done_n = 0;
+    if (n >= 4 && aligned(state, 16) && aligned(joint, 4) && aligned(rng8, 4) && aligned(result, 8)) {
+        const int64_t n_groups = n / 4;
+        const int e0 = allow_big_smem(k_step_table_packed, bytes + 16);
+        if (e0) return e0;
+        const int e1 = launch_pdl(k_step_table_packed, table_grid(n_groups), kTableThreads, (size_t)bytes + 16, st,
+                                  P, table, (uint32_t)bytes, state, joint, rng8, result, n_groups);
+        if (e1) return e1;
+        const int e = launch_status();
+        if (e) return e;
+        done_n = n_groups * 4;
+        if (done_n == n) return SOCCER_OK;
+    }
+    const int64_t k = done_n, m = n - k;
+    k_step_table_packed_scalar<<<grid_for(m, 8), kThreads, 0, st>>>(P, table, state + k, joint + k, rng8 + k, result + k, m);
+    return launch_status();
 }
 
 int soccer_step_table_slip(const soccer_pitch* pitch, const uint16_t* table, uint32_t* state, const uint8_t* act_a,
@@ -1161,9 +1221,11 @@ int soccer_step_host_scratch_bytes_host(int64_t n, int64_t* bytes)
 
 int soccer_step_host(const soccer_pitch* pitch, const soccer_step_host_args* a)
 {
-    if (!a || !a->state || !a->scratch || !a->h_act_a || !a->h_act_b || !a->h_rng8 || !a->h_obs || !a->h_reward ||
-        !a->h_flags || a->n < 0 || a->n_chunks < 1)
+    if (!a || !a->state || !a->scratch || !a->h_act_a || !a->h_rng8 || !a->h_obs || a->n < 0 || a->n_chunks < 1 ||
+        a->narrow < 0 || a->narrow > SOCCER_HOST_PACKED)
         return SOCCER_EINVAL;
+    const bool packed = a->narrow == SOCCER_HOST_PACKED;
+    if (packed ? !a->table : (!a->h_act_b || !a->h_reward || !a->h_flags)) return SOCCER_EINVAL;
     if (pitch && pitch->slip_prob != 0.0) return SOCCER_ESLIP;
     if (a->n == 0) return SOCCER_OK;
     cudaStream_t s_in = (cudaStream_t)a->s_in, s_k = (cudaStream_t)a->s_compute, s_out = (cudaStream_t)a->s_out;
@@ -1184,29 +1246,34 @@ int soccer_step_host(const soccer_pitch* pitch, const soccer_step_host_args* a)
     SOCCER_CUDA(cudaStreamWaitEvent(s_k, ev_prev_out, 0));
     for (int64_t lo = 0; lo < a->n; lo += chunk) {
         const int64_t m = a->n - lo < chunk ? a->n - lo : chunk;
-        SOCCER_CUDA(cudaMemcpyAsync(sc.a + lo, a->h_act_a + lo, m, cudaMemcpyHostToDevice, s_in));
-        SOCCER_CUDA(cudaMemcpyAsync(sc.b + lo, a->h_act_b + lo, m, cudaMemcpyHostToDevice, s_in));
+        SOCCER_CUDA(cudaMemcpyAsync(sc.a + lo, a->h_act_a + lo, m, cudaMemcpyHostToDevice, s_in));   // packed: joint bytes
+        if (!packed) SOCCER_CUDA(cudaMemcpyAsync(sc.b + lo, a->h_act_b + lo, m, cudaMemcpyHostToDevice, s_in));
         SOCCER_CUDA(cudaMemcpyAsync(sc.r + lo, a->h_rng8 + lo, m, cudaMemcpyHostToDevice, s_in));
         SOCCER_CUDA(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
         SOCCER_CUDA(cudaEventRecord(ev_in, s_in));
         SOCCER_CUDA(cudaStreamWaitEvent(s_k, ev_in, 0));
         SOCCER_CUDA(cudaEventDestroy(ev_in)); ev_in = nullptr;
-        if (a->table)
+        if (packed)
+            rc = soccer_step_table_packed(pitch, a->table, a->state + lo, sc.a + lo, sc.r + lo, sc.obs16 + lo, m,
+                                          (soccer_stream_t)s_k);
+        else if (a->narrow == SOCCER_HOST_NARROW)
+            rc = soccer_step_narrow(pitch, a->table, a->state + lo, sc.a + lo, sc.b + lo, sc.r + lo, sc.obs16 + lo,
+                                    sc.rew8 + lo, sc.f + lo, m, (soccer_stream_t)s_k);
+        else if (a->table)
             rc = soccer_step_table(pitch, a->table, a->state + lo, sc.a + lo, sc.b + lo, sc.r + lo, sc.obs + lo,
                                    sc.rew + lo, sc.f + lo, nullptr, m, (soccer_stream_t)s_k);
         else
             rc = soccer_step(pitch, a->state + lo, sc.a + lo, sc.b + lo, sc.r + lo, sc.obs + lo, sc.rew + lo,
                              sc.f + lo, nullptr, m, (soccer_stream_t)s_k);
         if (rc) goto done;
-        if (a->narrow) {
-            k_narrow<<<grid_for(m / 4 + 1, 8), kThreads, 0, s_k>>>(sc.obs + lo, sc.rew + lo, sc.obs16 + lo, sc.rew8 + lo, m);
-            rc = launch_status();
-            if (rc) goto done;
-        }
         SOCCER_CUDA(cudaEventCreateWithFlags(&ev_k, cudaEventDisableTiming));
         SOCCER_CUDA(cudaEventRecord(ev_k, s_k));
         SOCCER_CUDA(cudaStreamWaitEvent(s_out, ev_k, 0));
         SOCCER_CUDA(cudaEventDestroy(ev_k)); ev_k = nullptr;
+        if (packed) {
+            SOCCER_CUDA(cudaMemcpyAsync((uint16_t*)a->h_obs + lo, sc.obs16 + lo, 2 * m, cudaMemcpyDeviceToHost, s_out));
+            continue;
+        }
         if (a->narrow) {
             SOCCER_CUDA(cudaMemcpyAsync((uint16_t*)a->h_obs + lo, sc.obs16 + lo, 2 * m, cudaMemcpyDeviceToHost, s_out));
             SOCCER_CUDA(cudaMemcpyAsync((int8_t*)a->h_reward + lo, sc.rew8 + lo, m, cudaMemcpyDeviceToHost, s_out));

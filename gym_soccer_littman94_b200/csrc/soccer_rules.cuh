@@ -216,6 +216,7 @@ __device__ __forceinline__ uint4 ld_stream(const uint4* p) { return __ldcs(p); }
 __device__ __forceinline__ uint32_t ld_stream(const uint32_t* p) { return __ldcs(p); }
 __device__ __forceinline__ void st_stream(uint4* p, uint4 v) { __stcs(p, v); }
 __device__ __forceinline__ void st_stream(uint32_t* p, uint32_t v) { __stcs(p, v); }
+__device__ __forceinline__ void st_stream(uint2* p, uint2 v) { __stcs(p, v); }
 // The state word is the one stream that is re-read (by the next step).  Marking its lines L2::evict_last
 // (-DSOCCER_STATE_EVICT_LAST=1) was meant to keep the state tensor resident in the 126 MB L2; measured on
 // B200 it LOSES to the default replacement policy -- 2^24 envs (67 MB of state): 308 vs 329 G env-steps/s for

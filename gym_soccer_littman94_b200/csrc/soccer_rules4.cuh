@@ -55,6 +55,7 @@ struct Step4 {
     uint32_t s[4];      // next packed CELL-layout states (post-reset where a reset fired)
     uint32_t obs[4];    // what step() returned (0 on a goal)
     uint32_t rew[4];    // float bits
+    uint32_t rew4;      // the four rewards as int8 bytes
     uint32_t flags4;    // four flags bytes
     uint32_t robs[4];   // observation the next step starts from (only when RESET_OBS)
     int32_t  rew_sum;   // sum of the four rewards (+1 / -1 / 0), for K2's statistics
@@ -138,6 +139,7 @@ __device__ __forceinline__ void step4_noslip(const PitchDev& P, const Isd4& I, c
 #pragma unroll
     for (int e = 0; e < 4; ++e)
         o.rew[e] = __float_as_uint((float)(int)(signed char)(RW >> (8 * e)));
+    o.rew4 = RW;
     o.rew_sum = (int)__dp4a((int)RW, (int)kL, 0);
 
     if (RESET_OBS) {

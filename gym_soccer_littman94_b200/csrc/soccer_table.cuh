@@ -248,7 +248,9 @@ __device__ __forceinline__ TblCtx make_ctx(const uint8_t* smem, uint32_t table_b
     return c;
 }
 
-template <bool RESET_OBS>
+// NARROW (soccer_step_narrow): obs as uint16, reward as int8 -- `obs` then points at uint16[n] (one uint2 per group),
+// `rew` at int8[n] (one word per group); same values, 8 instead of 13 bytes written per env
+template <bool RESET_OBS, bool NARROW = false>
 __device__ __forceinline__ void table_step_group(const TblCtx& c, const Group4& x, int64_t g, uint4* st, uint4* obs,
                                                  uint4* rew, uint32_t* flg, uint4* rob)
 {
@@ -260,18 +262,25 @@ __device__ __forceinline__ void table_step_group(const TblCtx& c, const Group4& 
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         const TblOut o = table_step(c, sv[e], __byte_perm(jr4, 0, 0x4440 + e), __byte_perm(rs4, 0, 0x4440 + e));
-        so[e] = o.state; oo[e] = o.obs; rr[e] = __float_as_uint((float)o.rew_i); ro[e] = o.reset_obs; ff[e] = o.flags;
+        so[e] = o.state; oo[e] = o.obs; ro[e] = o.reset_obs; ff[e] = o.flags;
+        rr[e] = NARROW ? (uint32_t)o.rew_i : __float_as_uint((float)o.rew_i);
     }
     st_keep(st + g, make_uint4(so[0], so[1], so[2], so[3]));
-    st_stream(obs + g, make_uint4(oo[0], oo[1], oo[2], oo[3]));
-    st_stream(rew + g, make_uint4(rr[0], rr[1], rr[2], rr[3]));
+    if (NARROW) {
+        st_stream(reinterpret_cast<uint2*>(obs) + g, make_uint2(oo[0] | (oo[1] << 16), oo[2] | (oo[3] << 16)));
+        st_stream(reinterpret_cast<uint32_t*>(rew) + g,
+                  __byte_perm(__byte_perm(rr[0], rr[1], 0x0040), __byte_perm(rr[2], rr[3], 0x0040), 0x5410));
+    } else {
+        st_stream(obs + g, make_uint4(oo[0], oo[1], oo[2], oo[3]));
+        st_stream(rew + g, make_uint4(rr[0], rr[1], rr[2], rr[3]));
+    }
     st_stream(flg + g, __byte_perm(__byte_perm(ff[0], ff[1], 0x0040), __byte_perm(ff[2], ff[3], 0x0040), 0x5410));
     if (RESET_OBS) st_stream(rob + g, make_uint4(ro[0], ro[1], ro[2], ro[3]));
 }
 
 // K1, table variant: persistent, one 1024-thread CTA per SM.  PHILOX (soccer_step_table_philox): the draw stream is
 // not read (19 B / env-step); the draws of a group are computed while the next pair's loads are in flight.
-template <bool RESET_OBS, bool PHILOX = false>
+template <bool RESET_OBS, bool PHILOX = false, bool NARROW = false>
 __global__ void __launch_bounds__(kTableThreads, 1)
 k_step_table(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t table_bytes,
              uint32_t* __restrict__ state, const uint8_t* __restrict__ act_a, const uint8_t* __restrict__ act_b,
@@ -310,8 +319,8 @@ k_step_table(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t tab
         if (n_one) y0 = load_group(st4, a4, b4, r4, gn);          // prefetch the next pair
         if (n_two) y1 = load_group(st4, a4, b4, r4, gn + stride);
         if (PHILOX) { x0.r = philox_rng8x4(key, g); if (two) x1.r = philox_rng8x4(key, g + stride); }
-        table_step_group<RESET_OBS>(c, x0, g, st4, o4, w4, f4, q4);
-        if (two) table_step_group<RESET_OBS>(c, x1, g + stride, st4, o4, w4, f4, q4);
+        table_step_group<RESET_OBS, NARROW>(c, x0, g, st4, o4, w4, f4, q4);
+        if (two) table_step_group<RESET_OBS, NARROW>(c, x1, g + stride, st4, o4, w4, f4, q4);
         x0 = y0; x1 = y1; g = gn; one = n_one; two = n_two;
     }
 }
@@ -322,7 +331,7 @@ k_step_table_scalar(const PitchDev P, const uint16_t* __restrict__ gtable, uint3
                     const uint8_t* __restrict__ act_a, const uint8_t* __restrict__ act_b,
                     const uint8_t* __restrict__ rng, int32_t* __restrict__ obs, float* __restrict__ reward,
                     uint8_t* __restrict__ flags, int32_t* __restrict__ reset_obs, int64_t n,
-                    int use_philox = 0, const PhiloxKey key = PhiloxKey())
+                    int use_philox = 0, const PhiloxKey key = PhiloxKey(), int narrow = 0)
 {
     const int16_t* tbl = reinterpret_cast<const int16_t*>(gtable);
     const uint32_t last = (uint32_t)P.nS * 100u - 1u;
@@ -338,10 +347,109 @@ k_step_table_scalar(const PitchDev P, const uint16_t* __restrict__ gtable, uint3
         const bool trunc = s1 >= kTruncWord, reset = done | trunc;
         const uint32_t ro = (uint32_t)P.isd_obs[(rg >> 2) & 3u];
         state[i] = reset ? ro : ((s1 & 0xFFFF0000u) | nobs);
-        obs[i] = (int32_t)nobs;
-        reward[i] = (float)(e >> 14);
+        if (narrow) {
+            reinterpret_cast<uint16_t*>(obs)[i] = (uint16_t)nobs;
+            reinterpret_cast<int8_t*>(reward)[i] = (int8_t)(e >> 14);
+        } else {
+            obs[i] = (int32_t)nobs;
+            reward[i] = (float)(e >> 14);
+        }
         flags[i] = (uint8_t)((done ? 1u : 0u) + (trunc ? 2u : 0u));
         if (reset_obs) reset_obs[i] = (int32_t)(reset ? ro : nobs);
+    }
+}
+
+// K1, table variant with PACKED host-facing streams (soccer_step_table_packed): the joint action of an env in one
+// byte (aa | ab << 4), the draws in one byte, and ONE 16-bit result word per env
+//     result = next_obs | terminated << 12 | truncated << 13 | (reward & 3) << 14
+// (as int16: reward = w >> 14, obs = w & 0xFFF) -- 2 bytes in and 2 bytes out per env-step instead of 3 + 9, for
+// the PCIe-bound host path; 12 algorithmic bytes per env-step on the device.  The pointers may be device memory
+// or pinned host memory (zero copy).
+__device__ __forceinline__ uint32_t packed_result(int32_t e, uint32_t flags)
+{
+    return ((uint32_t)e & 0xCFFFu) | (flags << 12);
+}
+struct GroupP { uint4 s; uint32_t j, r; };
+__device__ __forceinline__ GroupP load_group_packed(const uint4* st, const uint32_t* j4, const uint32_t* r4, int64_t g)
+{
+    GroupP x;
+    x.s = ld_keep(st + g);
+    x.j = ld_stream(j4 + g);
+    x.r = ld_stream(r4 + g);
+    return x;
+}
+__device__ __forceinline__ void table_step_group_packed(const TblCtx& c, const GroupP& x, int64_t g, uint4* st, uint2* res)
+{
+    const uint32_t jr4 = (x.j & 0x0F0F0F0Fu) * 20u + ((x.j >> 4) & 0x0F0F0F0Fu) * 4u + (x.r & 0x03030303u);
+    const uint32_t rs4 = x.r & 0x0C0C0C0Cu;
+    const uint32_t sv[4] = { x.s.x, x.s.y, x.s.z, x.s.w };
+    uint32_t so[4], w[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const TblOut o = table_step(c, sv[e], __byte_perm(jr4, 0, 0x4440 + e), __byte_perm(rs4, 0, 0x4440 + e));
+        so[e] = o.state;
+        w[e] = o.obs | (o.flags << 12) | (((uint32_t)o.rew_i & 3u) << 14);
+    }
+    st_keep(st + g, make_uint4(so[0], so[1], so[2], so[3]));
+    st_stream(res + g, make_uint2(w[0] | (w[1] << 16), w[2] | (w[3] << 16)));
+}
+
+__global__ void __launch_bounds__(kTableThreads, 1)
+k_step_table_packed(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t table_bytes,
+                    uint32_t* __restrict__ state, const uint8_t* __restrict__ joint, const uint8_t* __restrict__ rng,
+                    uint16_t* __restrict__ result, int64_t n_groups)
+{
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    pdl_launch_dependents();
+    stage_table(smem_raw, gtable, table_bytes, &bar, P);
+    const TblCtx c = make_ctx(smem_raw, table_bytes, P);
+    pdl_wait();
+
+    uint4* st4 = reinterpret_cast<uint4*>(state);
+    const uint32_t* j4 = reinterpret_cast<const uint32_t*>(joint);
+    const uint32_t* r4 = reinterpret_cast<const uint32_t*>(rng);
+    uint2* w2 = reinterpret_cast<uint2*>(result);
+
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool one = g < n_groups, two = g + stride < n_groups;
+    GroupP x0 = {}, x1 = {};
+    if (one) x0 = load_group_packed(st4, j4, r4, g);
+    if (two) x1 = load_group_packed(st4, j4, r4, g + stride);
+    wait_table(&bar);
+    while (one) {
+        const int64_t gn = g + 2 * stride;
+        const bool n_one = gn < n_groups, n_two = gn + stride < n_groups;
+        GroupP y0 = x0, y1 = x1;
+        if (n_one) y0 = load_group_packed(st4, j4, r4, gn);
+        if (n_two) y1 = load_group_packed(st4, j4, r4, gn + stride);
+        table_step_group_packed(c, x0, g, st4, w2);
+        if (two) table_step_group_packed(c, x1, g + stride, st4, w2);
+        x0 = y0; x1 = y1; g = gn; one = n_one; two = n_two;
+    }
+}
+
+// scalar tail / misaligned fallback of the packed table step (global-memory table, one env per thread)
+__global__ void __launch_bounds__(kThreads)
+k_step_table_packed_scalar(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t* __restrict__ state,
+                           const uint8_t* __restrict__ joint, const uint8_t* __restrict__ rng,
+                           uint16_t* __restrict__ result, int64_t n)
+{
+    const int16_t* tbl = reinterpret_cast<const int16_t*>(gtable);
+    const uint32_t last = (uint32_t)P.nS * 100u - 1u;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t s = state[i], rg = rng[i], j = joint[i];
+        const uint32_t idx = min((s & 0xFFFFu) * 100u + (j & 15u) * 20u + (j >> 4) * 4u + (rg & 3u), last);
+        const int32_t e = tbl[idx];
+        const uint32_t nobs = (uint32_t)e & kTblObsMask;
+        const bool done = nobs == 0;
+        const uint32_t s1 = s + 0x10000u;
+        const bool trunc = s1 >= kTruncWord, reset = done | trunc;
+        const uint32_t ro = (uint32_t)P.isd_obs[(rg >> 2) & 3u];
+        state[i] = reset ? ro : ((s1 & 0xFFFF0000u) | nobs);
+        result[i] = (uint16_t)packed_result(e, (done ? 1u : 0u) + (trunc ? 2u : 0u));
     }
 }
 

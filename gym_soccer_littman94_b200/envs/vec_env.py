@@ -20,6 +20,7 @@ from .. import _lib
 from .._lib import Pitch, StepArgs, check
 
 LAYOUT_CELL, LAYOUT_INDEX = 0, 1
+HOST_WIDE, HOST_NARROW, HOST_PACKED = 0, 1, 2     # soccer_step_host_args.narrow
 INITIAL_RESET_STEP = (1 << 64) - 1   # Philox step index reserved for the very first reset draw
 
 
@@ -356,6 +357,19 @@ class SoccerVecEnv:
         return stats
 
     # ------------------------------------------------------------------ host-buffer path (end to end)
+    def _pinned(self, *dtypes):
+        """num_envs-element pinned host tensors, one per dtype, carved from ONE huge-page-backed allocation
+        (_lib.HostArena: full-rate PCIe reads, unlike small individual pin_memory() allocations)."""
+        n = self.num_envs
+        sizes = [n * torch.empty(0, dtype=d).element_size() for d in dtypes]
+        arena = _lib.HostArena(sum((sz + 4095) // 4096 * 4096 for sz in sizes) + 4096)
+        return tuple(arena.take(n, d) for d in dtypes)
+
+    def alloc_host_inputs(self, packed: bool = False):
+        """One set of pinned host input buffers for step_host / step_host_packed: (act_a, act_b, rng8), or
+        (joint, rng8) with packed=True -- uint8[num_envs] CPU tensors for the caller to fill."""
+        return self._pinned(*([torch.uint8] * (2 if packed else 3)))
+
     def _host_buffers(self, narrow: bool):
         key = "_hb_narrow" if narrow else "_hb_wide"
         if getattr(self, key, None) is None:
@@ -365,13 +379,16 @@ class SoccerVecEnv:
                 check(self.lib.soccer_step_host_scratch_bytes_host(n, C.byref(nbytes)), "scratch_bytes")
                 self._host_common = dict(scratch=torch.empty(nbytes.value, dtype=torch.uint8, device=dev),
                                          streams=[torch.cuda.Stream(device=dev) for _ in range(3)],
-                                         h_flags=torch.empty(n, dtype=torch.uint8).pin_memory())
-            setattr(self, key, dict(
-                h_obs=torch.empty(n, dtype=torch.int16 if narrow else torch.int32).pin_memory(),
-                h_reward=torch.empty(n, dtype=torch.int8 if narrow else torch.float32).pin_memory()))
+                                         h_flags=self._pinned(torch.uint8)[0])
+            h_obs, h_reward = self._pinned(*((torch.int16, torch.int8) if narrow else (torch.int32, torch.float32)))
+            setattr(self, key, dict(h_obs=h_obs, h_reward=h_reward))
         return self._host_common, getattr(self, key)
 
-    ZERO_COPY_MAX_ENVS = 32768
+    # Above this batch size the chunked copy-engine pipeline (soccer_step_host) matches or beats the zero-copy kernel
+    # for the 3-streams-up / 3-streams-down formats (2^24 envs: 10.0-10.6 vs 9.9 G env-steps/s narrow, 5.5 vs 5.3 wide);
+    # below it zero copy wins by up to 2x; the packed format is fastest zero-copy at every size
+    # (profiles/r01g_time_host_paths.log)
+    ZERO_COPY_MAX_ENVS = 1 << 23
 
     def step_host(self, act_a: torch.Tensor, act_b: torch.Tensor, rng8: torch.Tensor, narrow: bool = False,
                   n_chunks: int = 8, sync: bool = True, zero_copy: Optional[bool] = None):
@@ -382,8 +399,9 @@ class SoccerVecEnv:
         uint8, or with narrow=True obs uint16 (viewed as int16 by torch) / reward int8: same values,
         4 instead of 9 bytes per env over PCIe.  The batch is cut into n_chunks slices whose upload,
         kernel and download overlap on three streams (soccer_step_host in the C ABI).  Batches of up to
-        ZERO_COPY_MAX_ENVS envs with pinned inputs skip the staging: the kernel reads and writes the pinned
-        host buffers directly (zero_copy=None: automatic)."""
+        ZERO_COPY_MAX_ENVS envs with pinned inputs skip the staging: the kernel (wide or fused-narrow outputs) reads
+        and writes the pinned host buffers directly (zero_copy=None: automatic).  alloc_host_inputs() hands out
+        input buffers from huge-page-backed pinned memory."""
         if self.slip_prob != 0.0 or not self.multiagent or self.rng_mode != "injected":
             raise NotImplementedError("step_host covers the multi-agent, slip_prob == 0, injected-draw step")
         for name, t in (("act_a", act_a), ("act_b", act_b), ("rng8", rng8)):
@@ -395,19 +413,25 @@ class SoccerVecEnv:
             return hb["h_obs"], hb["h_reward"], common["h_flags"]
         if zero_copy is None:
             zero_copy = self.num_envs <= self.ZERO_COPY_MAX_ENVS
-        if zero_copy and not narrow and act_a.is_pinned() and act_b.is_pinned() and rng8.is_pinned():
-            # small batch: the step kernel reads the pinned action / draw buffers and writes the pinned result
-            # buffers itself over PCIe (unified addressing): one launch + one synchronize, no copies, no staging
+        if zero_copy and act_a.is_pinned() and act_b.is_pinned() and rng8.is_pinned():
+            # the step kernel reads the pinned action / draw buffers and writes the pinned result buffers itself over
+            # PCIe (unified addressing): one launch + one synchronize, no copies, no staging
             with torch.cuda.device(self.device):
                 cur = torch.cuda.current_stream(self.device)
                 st = C.c_void_p(cur.cuda_stream)
-                ptrs = (_ptr(act_a), _ptr(act_b), _ptr(rng8), _ptr(hb["h_obs"]), _ptr(hb["h_reward"]),
-                        _ptr(common["h_flags"]), None, self.num_envs, st)
-                if self.kernel == "table":
-                    check(self.lib.soccer_step_table(C.byref(self.pitch), _ptr(self.table), _ptr(self.state), *ptrs),
-                          "soccer_step_table")
+                tbl = None if self.table is None else _ptr(self.table)
+                if narrow:
+                    check(self.lib.soccer_step_narrow(C.byref(self.pitch), tbl, _ptr(self.state), _ptr(act_a), _ptr(act_b),
+                                                      _ptr(rng8), _ptr(hb["h_obs"]), _ptr(hb["h_reward"]),
+                                                      _ptr(common["h_flags"]), self.num_envs, st), "soccer_step_narrow")
                 else:
-                    check(self.lib.soccer_step(C.byref(self.pitch), _ptr(self.state), *ptrs), "soccer_step")
+                    ptrs = (_ptr(act_a), _ptr(act_b), _ptr(rng8), _ptr(hb["h_obs"]), _ptr(hb["h_reward"]),
+                            _ptr(common["h_flags"]), None, self.num_envs, st)
+                    if self.kernel == "table":
+                        check(self.lib.soccer_step_table(C.byref(self.pitch), tbl, _ptr(self.state), *ptrs),
+                              "soccer_step_table")
+                    else:
+                        check(self.lib.soccer_step(C.byref(self.pitch), _ptr(self.state), *ptrs), "soccer_step")
                 self.step_count += 1
                 if sync:
                     cur.synchronize()
@@ -429,6 +453,87 @@ class SoccerVecEnv:
         if sync:
             s_out.synchronize()
         return hb["h_obs"], hb["h_reward"], common["h_flags"]
+
+    # ------------------------------------------------------------------ packed streams (2 bytes in, 2 bytes out per env)
+    @staticmethod
+    def pack_joint(act_a: torch.Tensor, act_b: torch.Tensor) -> torch.Tensor:
+        """The joint action (aa, ab) -- the key of the reference's P[s] (SIM:181-185) -- in one byte: aa | ab << 4."""
+        return act_a | (act_b << 4)
+
+    @staticmethod
+    def unpack_result(w: torch.Tensor):
+        """(obs, reward, terminated, truncated) from the 16-bit result words of step_packed / step_host_packed
+        (int16 tensor): obs = w & 0xFFF, reward = w >> 14 (arithmetic), bit 12 terminated, bit 13 truncated."""
+        w = w.to(torch.int32)
+        return w & 0xFFF, (w >> 14).to(torch.float32), (w >> 12) & 1 != 0, (w >> 13) & 1 != 0
+
+    def _check_packed(self):
+        if self.kernel != "table" or self.slip_prob != 0.0 or self.rng_mode != "injected":
+            raise NotImplementedError("the packed step needs kernel='table' (5x4 / 6x4 pitch), slip_prob == 0 and "
+                                      "injected draws")
+
+    def step_packed(self, joint: torch.Tensor, rng8: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """step() on device tensors with packed streams (soccer_step_table_packed): joint = aa | ab << 4 (uint8),
+        rng8 as in step(); returns the int16 result words (see unpack_result).  Same transition, reward, flags and
+        fused reset as step(); 12 instead of 20 bytes of HBM traffic per env-step."""
+        self._check_packed()
+        if out is None:
+            if getattr(self, "_result16", None) is None:
+                self._result16 = torch.empty(self.num_envs, dtype=torch.int16, device=self.device)
+            out = self._result16
+        if self.num_envs == 0:
+            return out
+        with torch.cuda.device(self.device):
+            check(self.lib.soccer_step_table_packed(
+                C.byref(self.pitch), _ptr(self.table), _ptr(self.state), _ptr(self._check_vec(joint, torch.uint8, "joint")),
+                _ptr(self._check_vec(rng8, torch.uint8, "rng8")), _ptr(self._check_vec(out, torch.int16, "out")),
+                self.num_envs, _stream(self.device)), "soccer_step_table_packed")
+        self.step_count += 1
+        return out
+
+    def step_host_packed(self, joint: torch.Tensor, rng8: torch.Tensor, n_chunks: int = 8, sync: bool = True,
+                         zero_copy: Optional[bool] = None) -> torch.Tensor:
+        """step_host() with packed streams: 2 bytes up (joint action byte, draw byte) and 2 bytes down (one int16
+        result word, see unpack_result) per env over PCIe instead of 3 + 4.  Returns a pinned CPU int16 tensor owned
+        by the env and overwritten by the next call."""
+        self._check_packed()
+        for name, t in (("joint", joint), ("rng8", rng8)):
+            if not (isinstance(t, torch.Tensor) and not t.is_cuda and t.dtype == torch.uint8 and t.is_contiguous()
+                    and t.numel() == self.num_envs):
+                raise ValueError(f"{name} must be a contiguous uint8 CPU tensor with {self.num_envs} elements")
+        common, _ = self._host_buffers(True)
+        if getattr(self, "_h_result16", None) is None:
+            self._h_result16 = self._pinned(torch.int16)[0]
+        h_res = self._h_result16
+        if self.num_envs == 0:
+            return h_res
+        if zero_copy is None:
+            zero_copy = True
+        with torch.cuda.device(self.device):
+            if zero_copy and joint.is_pinned() and rng8.is_pinned():
+                cur = torch.cuda.current_stream(self.device)
+                check(self.lib.soccer_step_table_packed(C.byref(self.pitch), _ptr(self.table), _ptr(self.state), _ptr(joint),
+                                                        _ptr(rng8), _ptr(h_res), self.num_envs, C.c_void_p(cur.cuda_stream)),
+                      "soccer_step_table_packed")
+                self.step_count += 1
+                if sync:
+                    cur.synchronize()
+                return h_res
+            s_in, s_k, s_out = common["streams"]
+            cur = torch.cuda.current_stream(self.device)
+            s_k.wait_stream(cur)
+            a = _lib.StepHostArgs()
+            a.state, a.table, a.scratch = self.state.data_ptr(), self.table.data_ptr(), common["scratch"].data_ptr()
+            a.h_act_a, a.h_act_b, a.h_rng8 = joint.data_ptr(), None, rng8.data_ptr()
+            a.h_obs, a.h_reward, a.h_flags = h_res.data_ptr(), None, None
+            a.n, a.narrow, a.n_chunks = self.num_envs, HOST_PACKED, max(1, int(n_chunks))
+            a.s_in, a.s_compute, a.s_out = s_in.cuda_stream, s_k.cuda_stream, s_out.cuda_stream
+            check(self.lib.soccer_step_host(C.byref(self.pitch), C.byref(a)), "soccer_step_host")
+            cur.wait_stream(s_k)
+            self.step_count += 1
+            if sync:
+                s_out.synchronize()
+        return h_res
 
     def rollout(self, K: int, policy_a=None, policy_b=None, want_streams: bool = True, stats: Optional[torch.Tensor] = None,
                 out=None):

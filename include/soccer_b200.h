@@ -58,6 +58,7 @@
 #ifndef SOCCER_B200_H
 #define SOCCER_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -159,7 +160,7 @@ typedef struct soccer_step_args {
     int32_t         auto_reset; /* 1: reset fused (vector env); 0: set needs_reset like SIM:406 */
     int32_t         use_philox;
     int32_t         detail;     /* 1: fill flags bits 2..7 (needed for info["p"], SIM:405) */
-    int32_t         reserved;   /* must be 0 */
+    int32_t         narrow;     /* 1: obs points at uint16[n], reward at int8[n] (same values); else 0 */
     uint64_t        seed, step, env_id_base;
 } soccer_step_args;
 int soccer_step_ex(const soccer_pitch *pitch, const soccer_step_args *args, soccer_stream_t stream);
@@ -231,6 +232,22 @@ int soccer_step_table_philox(const soccer_pitch *pitch, const uint16_t *table, u
                              const uint8_t *act_a, const uint8_t *act_b, uint64_t seed, uint64_t step,
                              uint64_t env_id_base, int32_t *obs, float *reward, uint8_t *flags,
                              int32_t *reset_obs, int64_t n, soccer_stream_t stream);
+/* soccer_step / soccer_step_table (table == NULL: rules kernel on CELL-layout states, else the table kernel on
+ * INDEX-layout states) with NARROW result streams: obs as uint16, reward as int8 -- the same values in 8 instead
+ * of 13 written bytes per env-step.  The streams may be device memory or pinned host memory (zero copy). */
+int soccer_step_narrow(const soccer_pitch *pitch, const uint16_t *table, uint32_t *state,
+                       const uint8_t *act_a, const uint8_t *act_b, const uint8_t *rng8, uint16_t *obs16,
+                       int8_t *reward8, uint8_t *flags, int64_t n, soccer_stream_t stream);
+/* soccer_step_table with PACKED host-facing streams, for the PCIe-bound host path: joint[i] = aa | ab << 4 (the
+ * joint action (aa, ab) that keys the reference's P[s], SIM:181-185, in one byte), rng8 as in soccer_step, and
+ * ONE 16-bit result word per env:
+ *     result[i] = obs | terminated << 12 | truncated << 13 | (reward & 3) << 14
+ * i.e. read as int16: reward = w >> 14 (-1 / 0 / +1), obs = w & 0xFFF -- the same values soccer_step_table
+ * returns, 2 bytes in and 2 bytes out per env-step.  joint / rng8 / result may be device memory or pinned host
+ * memory (the kernel then moves them over PCIe itself).  SOCCER_LAYOUT_INDEX states. */
+int soccer_step_table_packed(const soccer_pitch *pitch, const uint16_t *table, uint32_t *state,
+                             const uint8_t *joint, const uint8_t *rng8, uint16_t *result, int64_t n,
+                             soccer_stream_t stream);
 /* step() with slip_prob > 0 (SIM:203-256) through the same shared-memory table: the outcome counts of
  * the 9 slipped move pairs are read from the state's table row, the categorical draw walks them in
  * the reference's order with sequential fp64 sums (bit-exact), one more look-up yields the chosen
@@ -271,15 +288,29 @@ int soccer_step_many(const soccer_pitch *pitch, const uint16_t *table, uint32_t 
                      float *reward, uint8_t *flags, int32_t *reset_obs, int64_t n,
                      soccer_stream_t stream);
 
+/* ---- pinned host memory for the host-buffer path ----
+ * bytes of page-locked, device-mapped host memory backed by 2 MB huge pages where the kernel grants them
+ * (2 MB-aligned anonymous mapping, MADV_HUGEPAGE, cudaHostRegister).  DMA reads from such a region run at the
+ * PCIe rate (50-55 GB/s here); from small cudaHostAlloc'd buffers they were measured at 21-55 GB/s depending on
+ * the physical pages.  Free with the same byte count.  Returns 0, SOCCER_EINVAL or a CUDA error code. */
+int soccer_host_alloc(size_t bytes, void **ptr);
+int soccer_host_free(void *ptr, size_t bytes);
+
 /* ---- step() with HOST buffers (the end-to-end path) ----
  * Uploads the joint actions / draws, steps, downloads the results, software-pipelined over
  * n_chunks slices of the batch on three caller-supplied streams (upload of slice c+1, kernel of
  * slice c and download of slice c-1 overlap; PCIe is full duplex).  Host pointers should be
  * pinned (page-locked); pageable memory works but serialises.  The call only ENQUEUES: results
  * are valid once s_out has been synchronised.  slip_prob must be 0 here.
- *   narrow = 0: h_obs int32[n], h_reward float32[n]      (9 bytes per env come back)
- *   narrow = 1: h_obs uint16[n], h_reward int8[n]        (4 bytes per env come back; same values)
+ *   narrow = SOCCER_HOST_WIDE (0):   h_obs int32[n], h_reward float32[n]   (3 bytes up, 9 down per env)
+ *   narrow = SOCCER_HOST_NARROW (1): h_obs uint16[n], h_reward int8[n]     (3 up, 4 down; same values)
+ *   narrow = SOCCER_HOST_PACKED (2): the streams of soccer_step_table_packed: h_act_a = joint bytes
+ *            aa | ab << 4, h_act_b unused, h_obs = uint16 result words, h_reward / h_flags unused
+ *            (2 up, 2 down); needs table != NULL
  * scratch: device memory, soccer_step_host_scratch_bytes_host(n) bytes, 256-byte aligned. */
+#define SOCCER_HOST_WIDE   0
+#define SOCCER_HOST_NARROW 1
+#define SOCCER_HOST_PACKED 2
 typedef struct soccer_step_host_args {
     uint32_t       *state;      /* device [n]; INDEX layout iff table != NULL, else CELL layout */
     const uint16_t *table;      /* device step table (soccer_build_step_table) or NULL: rules kernel */
@@ -289,7 +320,7 @@ typedef struct soccer_step_host_args {
     void           *h_reward;   /* host [n] */
     uint8_t        *h_flags;    /* host [n] */
     int64_t         n;
-    int32_t         narrow;
+    int32_t         narrow;     /* SOCCER_HOST_WIDE / _NARROW / _PACKED */
     int32_t         n_chunks;   /* >= 1 */
     soccer_stream_t s_in, s_compute, s_out;
 } soccer_step_host_args;

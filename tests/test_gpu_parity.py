@@ -364,7 +364,7 @@ def test_step_host_equals_device_path(dev, kernel, n, chunks):
     from gym_soccer_littman94_b200.envs import SoccerVecEnv
     rs = np.random.RandomState(n)
     ref = SoccerVecEnv(n, device=dev, kernel=kernel)
-    envs = {nr: SoccerVecEnv(n, device=dev, kernel=kernel) for nr in (False, True)}
+    envs = {(nr, zc): SoccerVecEnv(n, device=dev, kernel=kernel) for nr in (False, True) for zc in (False, True)}
     init = rs.randint(0, 16, n).astype(np.uint8)
     for e in [ref] + list(envs.values()):
         e.reset(_t(init, dev))
@@ -372,14 +372,82 @@ def test_step_host_equals_device_path(dev, kernel, n, chunks):
         a, b, r = (rs.randint(0, hi, n).astype(np.uint8) for hi in (5, 5, 16))
         obs, rew, flg, _ = ref.step(_t(a, dev), _t(b, dev), _t(r, dev))
         ha, hb, hr = (torch.from_numpy(x).pin_memory() for x in (a, b, r))
-        for nr, e in envs.items():
-            ho, hw, hf = e.step_host(ha, hb, hr, narrow=nr, n_chunks=chunks)
+        for (nr, zc), e in envs.items():
+            # zero_copy: the kernel (wide or fused-narrow outputs) reads / writes the pinned host buffers itself
+            ho, hw, hf = e.step_host(ha, hb, hr, narrow=nr, n_chunks=chunks, zero_copy=zc)
             ho = ho.numpy().view(np.uint16) if nr else ho.numpy()
-            assert np.array_equal(ho.astype(np.int32), obs.cpu().numpy()), (t, nr)
+            assert np.array_equal(ho.astype(np.int32), obs.cpu().numpy()), (t, nr, zc)
             assert np.array_equal(hw.numpy().astype(np.float32), rew.cpu().numpy())
             assert np.array_equal(hf.numpy(), flg.cpu().numpy())
     for e in envs.values():
         assert torch.equal(e.state, ref.state)
+
+
+@pytest.mark.parametrize("w,h", [(5, 4), (6, 4)])
+@pytest.mark.parametrize("n,chunks", [(1000, 1), (4099, 3), (70001, 8), (1 << 18, 4)])
+def test_packed_step_equals_plain_step(dev, w, h, n, chunks):
+    """soccer_step_table_packed (joint-action byte in, one 16-bit result word out) on device tensors, through the
+    staged host path and through the zero-copy host path == soccer_step_table, step after step, states included;
+    the ragged tail (n % 4 != 0) goes through the scalar kernel."""
+    from gym_soccer_littman94_b200.envs import SoccerVecEnv
+    rs = np.random.RandomState(n + w)
+    ref = SoccerVecEnv(n, width=w, height=h, device=dev, kernel="table")
+    envs = [SoccerVecEnv(n, width=w, height=h, device=dev, kernel="table") for _ in range(3)]
+    init = rs.randint(0, 16, n).astype(np.uint8)
+    for e in [ref] + envs:
+        e.reset(_t(init, dev))
+    for t in range(110):                                   # beyond the 100-step truncation
+        a, b, r = (rs.randint(0, hi, n).astype(np.uint8) for hi in (5, 5, 16))
+        if t % 7 == 3:
+            a[:] = 0; b[:] = 0                              # NOOP stretches let episodes reach the truncation
+        obs, rew, flg, _ = ref.step(_t(a, dev), _t(b, dev), _t(r, dev))
+        j = SoccerVecEnv.pack_joint(torch.from_numpy(a), torch.from_numpy(b))
+        assert np.array_equal(j.numpy(), a | (b << 4))
+        hj, hr = j.pin_memory(), torch.from_numpy(r).pin_memory()
+        words = [envs[0].step_packed(hj.to(dev), hr.to(dev)).cpu(),
+                 envs[1].step_host_packed(hj, hr, n_chunks=chunks, zero_copy=False).clone(),
+                 envs[2].step_host_packed(hj, hr, zero_copy=True).clone()]
+        for wd in words:
+            o, rw, term, trunc = SoccerVecEnv.unpack_result(wd)
+            assert np.array_equal(o.numpy(), obs.cpu().numpy()), t
+            assert np.array_equal(rw.numpy(), rew.cpu().numpy())
+            assert np.array_equal((term.numpy() * 1 + trunc.numpy() * 2).astype(np.uint8), flg.cpu().numpy())
+    for e in envs:
+        assert torch.equal(e.state, ref.state)
+
+
+def test_host_arena(dev):
+    """soccer_host_alloc: pinned, device-mapped, 4 KB-aligned tensors that copy both ways and are released with
+    the last tensor carved from them."""
+    import gc
+    from gym_soccer_littman94_b200 import _lib
+    ar = _lib.HostArena(3 << 20)
+    a, b = ar.take(1000, torch.uint8), ar.take(70000, torch.int16)
+    assert a.is_pinned() and b.is_pinned() and a.data_ptr() % 4096 == 0 and b.data_ptr() % 4096 == 0
+    a.copy_(torch.arange(1000) % 251); b.copy_(torch.arange(70000) % 30000)
+    da, db = a.to(dev, non_blocking=True), b.to(dev, non_blocking=True)
+    torch.cuda.synchronize()
+    assert int(da.sum()) == int((torch.arange(1000) % 251).sum()) and int(db.to(torch.int64).sum()) == int((torch.arange(70000) % 30000).sum())
+    b.copy_(db + 1, non_blocking=True)
+    torch.cuda.synchronize()
+    assert int(b[69999]) == 69999 % 30000 + 1
+    with pytest.raises(_lib.SoccerB200Error):
+        ar.take(4 << 20, torch.uint8)
+    del ar, a, b
+    gc.collect()
+    env_bufs = __import__("gym_soccer_littman94_b200.envs", fromlist=["SoccerVecEnv"]).SoccerVecEnv(4099, device=dev).alloc_host_inputs()
+    assert len(env_bufs) == 3 and all(t.is_pinned() and t.numel() == 4099 and t.dtype == torch.uint8 for t in env_bufs)
+
+
+def test_packed_step_rejects_what_it_cannot_do(dev):
+    from gym_soccer_littman94_b200.envs import SoccerVecEnv
+    z = torch.zeros(8, dtype=torch.uint8)
+    with pytest.raises(NotImplementedError):
+        SoccerVecEnv(8, device=dev, kernel="rules").step_host_packed(z, z)
+    with pytest.raises(NotImplementedError):
+        SoccerVecEnv(8, slip_prob=0.2, device=dev, kernel="table").step_packed(z.to(dev), z.to(dev))
+    with pytest.raises(ValueError):
+        SoccerVecEnv(8, device=dev, kernel="table").step_host_packed(z[:4], z)
 
 
 @pytest.mark.parametrize("n,off", [(0, 0), (5, 0), (4096, 0), (100003, 0), (70000, 3)])
