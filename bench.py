@@ -43,7 +43,7 @@ def ncu_traffic(kernel_prefix):
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             for name, rec in json.load(f).items():
-                if name.startswith(kernel_prefix):
+                if name.startswith(kernel_prefix + "<"):
                     return rec["dram_bytes_per_launch"], rec["source"]
     except Exception:  # noqa: BLE001
         pass
@@ -616,7 +616,7 @@ def run_ours(args):
                                 "is partly still in the 126 MB L2 when step i+1 reads it, so frac can exceed the DRAM-only "
                                 "figure (extra.k1_2^26_envs: 268 MB of state, no reuse)",
                      "peak_source": peak_src, "kernel": kname,
-                     "bytes_per_env_step": BYTES_PER_ENV_STEP, "avg_launch_ms": kern_ms, "min_launch_ms": min(per_launch),
+                     "bytes_per_env_step": BYTES_PER_ENV_STEP, "avg_launch_ms": kern_ms, "min_launch_ms_event_after_every_launch": min(per_launch),
                      "stream_mix_probe": {"achieved": probe_gbs, "unit": "GB/s", "kernel_over_probe": achieved / probe_gbs,
                                           "what": "k_stream_mix_probe: K1's streams, access pattern and launch shape "
                                                   "without the game logic = practical ceiling for its 7 B read / "

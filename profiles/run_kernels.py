@@ -1,6 +1,6 @@
 """Short driver for ncu captures: a few launches of each hot kernel at its bench size.
 
-    python profiles/run_kernels.py [k1_table|k1_rules|k2_table|k2_rules|k1_slip|replay|all] [--envs N]
+    python profiles/run_kernels.py [k1_table|k1_rules|k2_table|k2_rules|k1_slip|k1_philox|k1_packed|replay|all] [--envs N]
 """
 import argparse
 import os
@@ -20,6 +20,37 @@ def k1(kernel, n, iters):
     env.reset(r)
     for _ in range(iters):
         env.step(a, b, r)
+    torch.cuda.synchronize()
+
+
+def k1_philox(n, iters):
+    dev = torch.device("cuda", 0)
+    env = SoccerVecEnv(n, device=dev, kernel="table", rng_mode="philox", want_reset_obs=False)
+    g = torch.Generator(device=dev).manual_seed(0)
+    a, b = (torch.randint(0, 5, (n,), dtype=torch.uint8, device=dev, generator=g) for _ in range(2))
+    env.reset()
+    for _ in range(iters):
+        env.step(a, b)
+    torch.cuda.synchronize()
+
+
+def k1_packed(n, iters):
+    """the packed K1 step on device tensors and on pinned host buffers (zero copy: PCIe-bound)"""
+    dev = torch.device("cuda", 0)
+    env = SoccerVecEnv(n, device=dev, kernel="table", want_reset_obs=False)
+    hj, hr = env.alloc_host_inputs(packed=True)
+    hj.copy_(torch.randint(0, 5, (n,), dtype=torch.uint8) | (torch.randint(0, 5, (n,), dtype=torch.uint8) << 4))
+    hr.copy_(torch.randint(0, 16, (n,), dtype=torch.uint8))
+    dj, dr = hj.to(dev), hr.to(dev)
+    env.reset(dr)
+    for _ in range(iters):
+        env.step_packed(dj, dr)
+    for _ in range(iters):
+        env.step_host_packed(hj, hr)
+    ha, hb, hr3 = env.alloc_host_inputs()
+    ha.copy_(hj & 15); hb.copy_(hj >> 4); hr3.copy_(hr)
+    for _ in range(iters):
+        env.step_host(ha, hb, hr3, narrow=True, zero_copy=True)
     torch.cuda.synchronize()
 
 
@@ -80,6 +111,10 @@ if __name__ == "__main__":
         k2("rules", 1 << 20, 64, args.iters)
     if args.what in ("k1_slip", "all"):
         k1_slip(1 << 22, args.iters)
+    if args.what in ("k1_philox", "all"):
+        k1_philox(args.envs, args.iters)
+    if args.what in ("k1_packed", "all"):
+        k1_packed(args.envs, args.iters)
     if args.what in ("replay", "all"):
         replay("table", 1 << 22, 64, 3)
         replay("table", 4096, 4000, 3)
