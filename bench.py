@@ -29,6 +29,14 @@ UNIT = "env-steps/s"
 BYTES_PER_ENV_STEP = 20   # state u32 r+w (8) + act_a, act_b, rng u8 (3) + obs i32 (4) + reward f32 (4) + flags u8 (1)
 
 
+_JSON_OUT = sys.stdout
+
+
+def emit_json(line):
+    _JSON_OUT.write(line + "\n")
+    _JSON_OUT.flush()
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -150,7 +158,7 @@ def run_reference(args):
     el = time.perf_counter() - t0
     v = args.steps * T * N / el
     sample = f"each step = {N} envs x {T} lock-steps through the oracle port, {cores} threads"
-    print(json.dumps({
+    emit_json(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8/u32 integer state + fp64 categorical draw", "data": "synthetic",
@@ -598,7 +606,7 @@ def run_ours(args):
                         narrow=e2e_narrow, wide=e2e_wide)
     else:
         e2e_line = dict(e2e_narrow, unit=UNIT, steps=Ke, cpus_bound_near_gpu=numa_cpus, wide=e2e_wide)
-    print(json.dumps({
+    emit_json(json.dumps({
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8/u32 integer (f32 reward stream)", "data": "synthetic",
@@ -645,10 +653,17 @@ def main():
     ap.add_argument("--chunks", type=int, default=8, help="pipeline slices of the host-buffer step")
     ap.add_argument("--no-bind", action="store_true", help="do not pin ranks to the CPU cores local to their GPU")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: anything native libraries print there while the bench runs (NCCL's
+    # "NCCL version ..." banner, for one) is sent to stderr instead
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
+    _JSON_OUT.flush()
 
 
 if __name__ == "__main__":
