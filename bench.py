@@ -119,10 +119,11 @@ def time_cpu_port(total_budget_s, n_threads, T=64, N=1 << 15):
     for i in range(N):
         states[i] = m.isd[i & 3][1]
     ts = np.zeros(N, np.int32)
-    m.rollout_injected(states, ts, act_a[:4], act_b[:4], rng8[:4], n_threads=n_threads)   # warm
+    out = (np.zeros((T, N), np.int32), np.zeros((T, N), np.float32), np.zeros((T, N), np.uint8), None)   # pre-faulted
+    m.rollout_injected(states, ts, act_a, act_b, rng8, n_threads=n_threads, out=out)   # warm
     reps, t0 = 0, time.perf_counter()
     while True:
-        m.rollout_injected(states, ts, act_a, act_b, rng8, n_threads=n_threads)
+        m.rollout_injected(states, ts, act_a, act_b, rng8, n_threads=n_threads, out=out)
         reps += 1
         el = time.perf_counter() - t0
         if el >= total_budget_s or reps >= 4096:
@@ -150,11 +151,12 @@ def run_reference(args):
     for i in range(N):
         states[i] = m.isd[i & 3][1]
     ts = np.zeros(N, np.int32)
+    out = (np.zeros((T, N), np.int32), np.zeros((T, N), np.float32), np.zeros((T, N), np.uint8), None)   # pre-faulted
     for _ in range(max(args.warmup, 1)):
-        m.rollout_injected(states, ts, act_a, act_b, rng8, n_threads=cores)
+        m.rollout_injected(states, ts, act_a, act_b, rng8, n_threads=cores, out=out)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        m.rollout_injected(states, ts, act_a, act_b, rng8, n_threads=cores)
+        m.rollout_injected(states, ts, act_a, act_b, rng8, n_threads=cores, out=out)
     el = time.perf_counter() - t0
     v = args.steps * T * N / el
     sample = f"each step = {N} envs x {T} lock-steps through the oracle port, {cores} threads"
