@@ -729,3 +729,97 @@ def test_full_size_properties_2_24(dev):
         outs[kernel] = acc.cpu().numpy()
         del env
     assert np.array_equal(outs["rules"], outs["table"])
+
+
+class _Guarded:
+    """Output tensors carved out of larger buffers pre-filled with a sentinel byte: after the kernels ran, every
+    byte outside the carved views must still be the sentinel (compute-sanitizer is not available on the pool, so
+    this is the out-of-bounds-write check).  `skew` shifts a view by that many ELEMENTS to force misaligned paths."""
+    PAD = 256  # bytes on either side
+
+    def __init__(self, dev):
+        self.dev, self.bufs = dev, []
+
+    def make(self, shape, dtype, skew=0):
+        numel = int(np.prod(shape))
+        es = torch.empty(0, dtype=dtype).element_size()
+        raw = torch.full((2 * self.PAD + (numel + skew) * es,), 0xA5, dtype=torch.uint8, device=self.dev)
+        lo = self.PAD + skew * es
+        view = raw[lo:lo + numel * es].view(dtype).view(shape)
+        self.bufs.append((raw, lo, numel * es))
+        return view
+
+    def check(self):
+        torch.cuda.synchronize()
+        for raw, lo, nb in self.bufs:
+            assert bool((raw[:lo] == 0xA5).all()) and bool((raw[lo + nb:] == 0xA5).all()), "write outside an output buffer"
+
+
+@pytest.mark.parametrize("kernel", ["rules", "table"])
+@pytest.mark.parametrize("n,skew", [(7, 0), (1000, 0), (4099, 0), (4099, 1), (65541, 0), (65536, 3)])
+def test_no_writes_outside_the_output_buffers(dev, kernel, n, skew):
+    """Every K1 / K2 / replay / statistics entry point, ragged and misaligned batches, outputs and the state tensor
+    inside sentinel-filled guard bands."""
+    from gym_soccer_littman94_b200.envs import SoccerVecEnv
+    i32, f32, u8, i16, i8 = torch.int32, torch.float32, torch.uint8, torch.int16, torch.int8
+    g = _Guarded(dev)
+    rs = np.random.RandomState(n + skew)
+    a, b, r = (_t(rs.randint(0, hi, n).astype(np.uint8), dev) for hi in (5, 5, 16))
+    T = 5
+    A, B, R = (_t(rs.randint(0, hi, (T, n)).astype(np.uint8), dev) for hi in (5, 5, 16))
+
+    def fresh(**kw):
+        e = SoccerVecEnv(n, device=dev, kernel=kernel, **kw)
+        st = g.make((n,), i32, skew)
+        st.copy_(e.state)
+        e.state = st
+        return e
+    # K1 injected (+ reset_obs), K1 Philox, K1 narrow / packed on device tensors
+    e = fresh()
+    e.reset(r)
+    e.step(a, b, r, out=(g.make((n,), i32, skew), g.make((n,), f32, skew), g.make((n,), u8, skew), g.make((n,), i32, skew)))
+    e.step(a, b, r, out=(g.make((n,), i32, skew), g.make((n,), f32, skew), g.make((n,), u8, skew), None))
+    e.step_many(A, B, R, out=(g.make((T, n), i32, skew), g.make((T, n), f32, skew), g.make((T, n), u8, skew), None))
+    st6 = g.make((6,), torch.int64)
+    st6.zero_()
+    e.step_stats(stats=st6)
+    if kernel == "table":
+        e.step_packed(a | (b << 4), r, out=g.make((n,), i16, skew))
+    from gym_soccer_littman94_b200 import _lib
+    import ctypes as C
+    o16, r8, f8 = g.make((n,), i16, skew), g.make((n,), i8, skew), g.make((n,), u8, skew)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    _lib.check(e.lib.soccer_step_narrow(C.byref(e.pitch), None if e.table is None else p(e.table), p(e.state), p(a), p(b),
+                                        p(r), p(o16), p(r8), p(f8), n, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
+               "soccer_step_narrow")
+    ep = fresh(rng_mode="philox", seed=3)
+    ep.reset()
+    ep.step(a, b, out=(g.make((n,), i32, skew), g.make((n,), f32, skew), g.make((n,), u8, skew), g.make((n,), i32, skew)))
+    # K2 with streams and statistics
+    ep.rollout(T, out=(g.make((T, n), i32, skew), g.make((T, n), f32, skew), g.make((T, n), u8, skew)), stats=st6)
+    g.check()
+
+
+@pytest.mark.parametrize("w,h,kernel", [(5, 4, "table"), (5, 4, "rules"), (7, 5, "rules")])
+@pytest.mark.parametrize("n,skew", [(1001, 0), (4100, 1)])
+def test_no_writes_outside_the_output_buffers_slip(dev, w, h, kernel, n, skew):
+    """The slip_prob > 0 steppers (table walk, rules walk, K2 SLIP instantiations) inside guard bands."""
+    from gym_soccer_littman94_b200.envs import SoccerVecEnv
+    i32, f32, u8 = torch.int32, torch.float32, torch.uint8
+    g = _Guarded(dev)
+    rs = np.random.RandomState(n)
+    a, b, r = (_t(rs.randint(0, hi, n).astype(np.uint8), dev) for hi in (5, 5, 16))
+    r32 = _t(rs.randint(-2**31, 2**31 - 1, n).astype(np.int32), dev)
+    for mode in ("injected", "philox"):
+        e = SoccerVecEnv(n, width=w, height=h, slip_prob=0.2, device=dev, kernel=kernel, rng_mode=mode, seed=5)
+        st = g.make((n,), i32, skew)
+        st.copy_(e.state)
+        e.state = st
+        e.reset(r if mode == "injected" else None)
+        out = (g.make((n,), i32, skew), g.make((n,), f32, skew), g.make((n,), u8, skew), g.make((n,), i32, skew))
+        if mode == "injected":
+            e.step(a, b, r, rng32=r32, out=out)
+        else:
+            e.step(a, b, out=out)
+            e.rollout(3, out=(g.make((3, n), i32, skew), g.make((3, n), f32, skew), g.make((3, n), u8, skew)))
+    g.check()
