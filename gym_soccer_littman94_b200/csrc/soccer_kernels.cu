@@ -18,6 +18,8 @@
 #include <cuda_runtime.h>
 #include <sys/mman.h>
 #include <string.h>
+#include <mutex>
+#include <unordered_set>
 
 using namespace soccer;
 
@@ -591,25 +593,40 @@ int soccer_abi_version(void) { return SOCCER_ABI_VERSION; }
 // zero-copy loads) from a small cudaHostAlloc'd buffer run anywhere between 21 and 55 GB/s depending on the
 // physical pages it happened to get, from such a region always at 50-55 GB/s (profiles/r01g_probe_pcie2.log).
 static const size_t kHuge = (size_t)2 << 20;
+// allocations that fell back to cudaHostAlloc (mmap or cudaHostRegister refused, e.g. a low RLIMIT_MEMLOCK)
+static std::mutex g_host_mu;
+static std::unordered_set<void*> g_host_plain;
 int soccer_host_alloc(size_t bytes, void** ptr)
 {
     if (!ptr || bytes == 0) return SOCCER_EINVAL;
     const size_t len = (bytes + kHuge - 1) / kHuge * kHuge;
     uint8_t* raw = (uint8_t*)mmap(nullptr, len + kHuge, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
-    if (raw == MAP_FAILED) return (int)cudaErrorMemoryAllocation;
-    uint8_t* p = (uint8_t*)(((uintptr_t)raw + kHuge - 1) / kHuge * kHuge);
-    if (p > raw) munmap(raw, (size_t)(p - raw));                       // trim the slack on both sides:
-    if (p + len < raw + len + kHuge) munmap(p + len, (size_t)(raw + len + kHuge - (p + len)));   // [p, p + len) stays
-    madvise(p, len, MADV_HUGEPAGE);                                    // best effort; plain pages otherwise
-    memset(p, 0, len);                                                 // fault the pages in before pinning
-    const cudaError_t e = cudaHostRegister(p, len, cudaHostRegisterPortable | cudaHostRegisterMapped);
-    if (e != cudaSuccess) { munmap(p, len); return (int)e; }
-    *ptr = p;
+    if (raw != MAP_FAILED) {
+        uint8_t* p = (uint8_t*)(((uintptr_t)raw + kHuge - 1) / kHuge * kHuge);
+        if (p > raw) munmap(raw, (size_t)(p - raw));                       // trim the slack on both sides:
+        if (p + len < raw + len + kHuge) munmap(p + len, (size_t)(raw + len + kHuge - (p + len)));   // [p, p + len) stays
+        madvise(p, len, MADV_HUGEPAGE);                                    // best effort; plain pages otherwise
+        memset(p, 0, len);                                                 // fault the pages in before pinning
+        if (cudaHostRegister(p, len, cudaHostRegisterPortable | cudaHostRegisterMapped) == cudaSuccess) {
+            *ptr = p;
+            return SOCCER_OK;
+        }
+        (void)cudaGetLastError();
+        munmap(p, len);
+    }
+    void* q = nullptr;
+    const cudaError_t e = cudaHostAlloc(&q, bytes, cudaHostAllocPortable | cudaHostAllocMapped);
+    if (e != cudaSuccess) return (int)e;
+    { std::lock_guard<std::mutex> lk(g_host_mu); g_host_plain.insert(q); }
+    *ptr = q;
     return SOCCER_OK;
 }
 int soccer_host_free(void* ptr, size_t bytes)
 {
     if (!ptr || bytes == 0) return SOCCER_EINVAL;
+    bool plain;
+    { std::lock_guard<std::mutex> lk(g_host_mu); plain = g_host_plain.erase(ptr) != 0; }
+    if (plain) return (int)cudaFreeHost(ptr);
     const size_t len = (bytes + kHuge - 1) / kHuge * kHuge;
     const cudaError_t e = cudaHostUnregister(ptr);
     munmap(ptr, len);

@@ -292,7 +292,8 @@ int soccer_step_many(const soccer_pitch *pitch, const uint16_t *table, uint32_t 
  * bytes of page-locked, device-mapped host memory backed by 2 MB huge pages where the kernel grants them
  * (2 MB-aligned anonymous mapping, MADV_HUGEPAGE, cudaHostRegister).  DMA reads from such a region run at the
  * PCIe rate (50-55 GB/s here); from small cudaHostAlloc'd buffers they were measured at 21-55 GB/s depending on
- * the physical pages.  Free with the same byte count.  Returns 0, SOCCER_EINVAL or a CUDA error code. */
+ * the physical pages.  Falls back to cudaHostAlloc when the mapping cannot be registered (e.g. a low
+ * RLIMIT_MEMLOCK).  Free with the same byte count.  Returns 0, SOCCER_EINVAL or a CUDA error code. */
 int soccer_host_alloc(size_t bytes, void **ptr);
 int soccer_host_free(void *ptr, size_t bytes);
 
