@@ -255,6 +255,22 @@ __device__ __forceinline__ void st_keep(uint4* p, uint4 v)
 // One thread owns groups of 4 consecutive envs: 128-bit accesses on the 32-bit streams (state,
 // obs, reward), 32-bit accesses on the byte streams (actions, draws, flags); a warp therefore
 // touches 512 B / 128 B contiguous per instruction.
+// A/B switch: prefetch.global.L2 of the groups SOCCER_K1_L2_PREFETCH iterations ahead of the register prefetch
+// (deepens the load pipeline without registers); 0 = off.  Measured on B200: 1 and 2 both LOSE (2^24 envs 325 -> 290 G
+// env-steps/s, 2^26 280 -> 276 / 273 G; profiles/r01g_ab_k1_l2prefetch.log), so it stays off.
+#ifndef SOCCER_K1_L2_PREFETCH
+#define SOCCER_K1_L2_PREFETCH 0
+#endif
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_group(const uint4* st, const uint32_t* aa, const uint32_t* ab, const uint32_t* rg,
+                                               int64_t g, bool with_rng)
+{
+    prefetch_l2(st + g);
+    if ((threadIdx.x & 31) == 0) {          // one 128-byte line per warp and byte stream
+        prefetch_l2(aa + g); prefetch_l2(ab + g);
+        if (with_rng) prefetch_l2(rg + g);
+    }
+}
 struct Group4 { uint4 s; uint32_t a, b, r; };
 __device__ __forceinline__ Group4 load_group(const uint4* st, const uint32_t* aa, const uint32_t* ab,
                                              const uint32_t* rg, int64_t g)

@@ -318,6 +318,11 @@ k_step_table(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t tab
         Group4 y0 = x0, y1 = x1;
         if (n_one) y0 = load_group(st4, a4, b4, r4, gn);          // prefetch the next pair
         if (n_two) y1 = load_group(st4, a4, b4, r4, gn + stride);
+        if (SOCCER_K1_L2_PREFETCH) {
+            const int64_t gp = gn + (int64_t)SOCCER_K1_L2_PREFETCH * 2 * stride;
+            if (gp < n_groups) prefetch_group(st4, a4, b4, r4, gp, !PHILOX);
+            if (gp + stride < n_groups) prefetch_group(st4, a4, b4, r4, gp + stride, !PHILOX);
+        }
         if (PHILOX) { x0.r = philox_rng8x4(key, g); if (two) x1.r = philox_rng8x4(key, g + stride); }
         table_step_group<RESET_OBS, NARROW>(c, x0, g, st4, o4, w4, f4, q4);
         if (two) table_step_group<RESET_OBS, NARROW>(c, x1, g + stride, st4, o4, w4, f4, q4);

@@ -5,7 +5,7 @@ from gym_soccer_littman94_b200.envs import SoccerVecEnv
 dev = torch.device("cuda", 0)
 tag = os.environ.get("SOCCER_B200_LIB", "default").split("/")[-1]
 RING = 4
-for kernel in ("table", "rules"):
+for kernel in os.environ.get("AB_KERNELS", "table,rules").split(","):
     for n in (1 << 22, 1 << 24, 1 << 26):
         env = SoccerVecEnv(n, device=dev, kernel=kernel, want_reset_obs=False)
         g = torch.Generator(device=dev).manual_seed(0)
