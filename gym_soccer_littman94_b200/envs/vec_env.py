@@ -275,6 +275,36 @@ class SoccerVecEnv:
         self.step_count += 1
         return obs, reward, flags, reset_obs
 
+    # ------------------------------------------------------------------ checkpoint / resume
+    def state_dict(self) -> dict:
+        """Everything a run needs to resume: the packed state words (CELL layout, whatever kernel the env uses) and the
+        Philox coordinates.  Philox is counter-based -- a pure function of (seed, global env id, step) -- so a restored
+        env continues the very trajectory, on any GPU count and with either kernel (the reference checkpoints nothing
+        but policy pickles, utils/policies.py:17-27)."""
+        state = self.state
+        if self.layout == LAYOUT_INDEX and self.num_envs:
+            state = torch.empty_like(self.state)
+            with torch.cuda.device(self.device):
+                check(self.lib.soccer_convert_state(C.byref(self.pitch), _ptr(self.state), _ptr(state), LAYOUT_CELL,
+                                                    self.num_envs, _stream(self.device)), "soccer_convert_state")
+        return {"state": state.detach().cpu().clone(), "layout": LAYOUT_CELL, "step_count": int(self.step_count),
+                "seed": int(self.seed), "env_id_base": int(self.env_id_base), "rng_mode": self.rng_mode,
+                "width": int(self.pitch.width), "height": int(self.pitch.height), "slip_prob": float(self.slip_prob),
+                "num_envs": int(self.num_envs)}
+
+    def load_state_dict(self, sd: dict) -> None:
+        if (sd["width"], sd["height"], sd["num_envs"]) != (int(self.pitch.width), int(self.pitch.height), self.num_envs) \
+                or float(sd["slip_prob"]) != self.slip_prob:
+            raise ValueError("checkpoint belongs to a different pitch, slip_prob or batch size")
+        state = sd["state"].to(self.device, dtype=torch.int32).contiguous()
+        if self.layout == LAYOUT_INDEX and self.num_envs:
+            with torch.cuda.device(self.device):
+                check(self.lib.soccer_convert_state(C.byref(self.pitch), _ptr(state), _ptr(self.state), LAYOUT_INDEX,
+                                                    self.num_envs, _stream(self.device)), "soccer_convert_state")
+        else:
+            self.state.copy_(state)
+        self.step_count, self.seed, self.env_id_base = int(sd["step_count"]), int(sd["seed"]), int(sd["env_id_base"])
+
     # ------------------------------------------------------------------ the reference's dict-shaped surface, batched
     def reset_dict(self, seed=None, options=None, rng8: Optional[torch.Tensor] = None):
         """reset() with the reference's signature and return shape (SIM:410-424): (obs_dict, info_dict) keyed by

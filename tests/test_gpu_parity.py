@@ -823,3 +823,26 @@ def test_no_writes_outside_the_output_buffers_slip(dev, w, h, kernel, n, skew):
             e.step(a, b, out=out)
             e.rollout(3, out=(g.make((3, n), i32, skew), g.make((3, n), f32, skew), g.make((3, n), u8, skew)))
     g.check()
+
+
+@pytest.mark.parametrize("k_save,k_load", [("table", "table"), ("rules", "table"), ("table", "rules")])
+def test_checkpoint_resume_continues_the_trajectory(dev, k_save, k_load, tmp_path):
+    """state_dict / load_state_dict: 2 x 48 steps with a save / torch.save / load into a FRESH env in between (also
+    across kernels: the checkpoint is layout-neutral) == 96 steps in one go; timesteps and statistics included."""
+    from gym_soccer_littman94_b200.envs import SoccerVecEnv
+    N, seed = 4099, 77
+    ref = SoccerVecEnv(N, device=dev, rng_mode="philox", kernel="rules", seed=seed, env_id_base=1000)
+    ref.reset()
+    ro, rr, rf, rs = ref.rollout(96)
+    a = SoccerVecEnv(N, device=dev, rng_mode="philox", kernel=k_save, seed=seed, env_id_base=1000)
+    a.reset()
+    o1, r1, f1, s1 = a.rollout(48)
+    torch.save(a.state_dict(), tmp_path / "ckpt.pt")
+    b = SoccerVecEnv(N, device=dev, rng_mode="philox", kernel=k_load, seed=0, env_id_base=0)
+    b.load_state_dict(torch.load(tmp_path / "ckpt.pt"))
+    o2, r2, f2, s2 = b.rollout(48)
+    assert torch.equal(torch.cat([o1, o2]), ro) and torch.equal(torch.cat([r1, r2]), rr) and torch.equal(torch.cat([f1, f2]), rf)
+    assert torch.equal(s1 + s2, rs)
+    assert torch.equal(b.current_obs(), ref.current_obs()) and torch.equal(b.timesteps(), ref.timesteps())
+    with pytest.raises(ValueError):
+        SoccerVecEnv(N + 1, device=dev).load_state_dict(a.state_dict())
