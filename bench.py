@@ -90,11 +90,11 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:  # noqa: BLE001
             self.proc.kill()
-        sm, mx, reasons = [], None, set()
+        sm, mx, reasons, pw = [], None, set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             try:
-                sm.append(float(r[0])); mx = float(r[1])
+                sm.append(float(r[0])); mx = float(r[1]); pw.append(float(r[2]))
                 for nm, v in zip(names, r[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(nm)
@@ -102,7 +102,7 @@ class ClockSampler:
                 pass
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "sm_mhz_min": sm[0] if sm else None, "power_w_max": max(pw) if pw else None}
 
 
 def time_cpu_port(total_budget_s, n_threads, T=64, N=1 << 15):
@@ -283,7 +283,21 @@ def run_ours(args):
         ev[i + 1].record()
     torch.cuda.synchronize()
     per_launch = [ev[i].elapsed_time(ev[i + 1]) for i in range(K)]
+    # (3) the same launches back to back for about a second: the clock / throttle samples below are taken under THIS
+    # load (the K-step region above lasts a few milliseconds, less than one nvidia-smi sampling period)
+    n_sus = max(K, int(1000.0 / max(kern_ms, 1e-3)))
+    u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    u0.record()
+    for i in range(n_sus):
+        env.step(*ins[i % RING], out=outs[i % RING])
+    u1.record()
+    torch.cuda.synchronize()
+    sustained = {"steps": n_sus, "seconds": u0.elapsed_time(u1) * 1e-3,
+                 "env_steps_per_s_per_gpu": N * n_sus / (u0.elapsed_time(u1) * 1e-3)}
     clocks = sampler.stop() if rank == 0 else None
+    if clocks is not None:
+        clocks["sampled_over"] = "the timed K steps, the per-launch pass and %d further back-to-back launches (%.2f s)" % (
+            n_sus, sustained["seconds"])
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -634,6 +648,7 @@ def run_ours(args):
         "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": 1, "kind": "port", "sample": cpu_sample, "host": host_info(),
                          "all_cores": {"value": cpu_all_v, "cores": cores}},
         "e2e": e2e_line,
+        "sustained": sustained,
         "gpu_launches": K,
         "clocks": clocks,
         "extra": extra,
