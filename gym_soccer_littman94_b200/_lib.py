@@ -25,7 +25,7 @@ EXPORTS = (
     "soccer_rollout_table", "soccer_step_table_bytes_host", "soccer_convert_state", "soccer_step_stats",
     "soccer_step_host", "soccer_step_host_scratch_bytes_host", "soccer_step_many", "soccer_bench_stream_mix",
     "soccer_bench_rollout_probe", "soccer_rollout_table_policy", "soccer_step_table_slip",
-    "soccer_bellman_q", "soccer_plan", "soccer_plan_workspace_bytes_host", "soccer_step_table_philox", "soccer_step_table_packed", "soccer_step_narrow", "soccer_host_alloc", "soccer_host_free",
+    "soccer_bellman_q", "soccer_plan", "soccer_plan_workspace_bytes_host", "soccer_step_table_philox", "soccer_step_table_packed", "soccer_step_narrow", "soccer_host_alloc", "soccer_host_free", "soccer_slip_index_bytes_host", "soccer_build_slip_index",
 )
 
 
@@ -131,7 +131,9 @@ def lib():
         "soccer_step_table_packed": [PP, vp, vp, vp, vp, vp, i64, vp],
         "soccer_rollout_table": [PP, vp, vp, u64, u64, i32, u64, vp, vp, vp, vp, i64, vp],
         "soccer_rollout_table_policy": [PP, vp, vp, vp, vp, u64, u64, i32, u64, vp, vp, vp, vp, i64, vp],
-        "soccer_step_table_slip": [PP, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp],
+        "soccer_step_table_slip": [PP, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp],
+        "soccer_slip_index_bytes_host": [PP, C.POINTER(i64)],
+        "soccer_build_slip_index": [PP, vp, vp, vp],
         "soccer_convert_state": [PP, vp, vp, i32, i64, vp],
         "soccer_bellman_q": [PP, vp, vp, vp, C.c_double, vp, vp],
         "soccer_plan_workspace_bytes_host": [PP, C.POINTER(i64)],

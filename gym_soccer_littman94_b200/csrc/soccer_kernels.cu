@@ -1008,16 +1008,34 @@ int soccer_step_table_packed(const soccer_pitch* pitch, const uint16_t* table, u
     return launch_status();
 }
 
-int soccer_step_table_slip(const soccer_pitch* pitch, const uint16_t* table, uint32_t* state, const uint8_t* act_a,
-                           const uint8_t* act_b, const uint8_t* rng8, const uint32_t* rng32, const double* rngf64,
-                           int32_t* obs, float* reward, uint8_t* flags, int32_t* reset_obs, int64_t n,
+int soccer_slip_index_bytes_host(const soccer_pitch* pitch, int64_t* bytes)
+{
+    if (!bytes) return SOCCER_EINVAL;
+    PitchDev P; const int rc = make_pitch_dev(pitch, &P); if (rc) return rc;
+    int64_t tb; const int rc2 = table_bytes_of(P, &tb); if (rc2) return rc2;
+    *bytes = ((int64_t)P.nS * 25 + 15) / 16 * 16;
+    return SOCCER_OK;
+}
+
+int soccer_build_slip_index(const soccer_pitch* pitch, const uint16_t* table, uint8_t* slip_index, soccer_stream_t stream)
+{
+    if (!table || !slip_index) return SOCCER_EINVAL;
+    PitchDev P; int rc = make_pitch_dev(pitch, &P); if (rc) return rc;
+    int64_t tb; rc = table_bytes_of(P, &tb); if (rc) return rc;
+    k_build_slip_index<<<grid_for((int64_t)P.nS * 25, 4), kThreads, 0, (cudaStream_t)stream>>>(P, P.nS, table, slip_index);
+    return launch_status();
+}
+
+int soccer_step_table_slip(const soccer_pitch* pitch, const uint16_t* table, const uint8_t* slip_index, uint32_t* state,
+                           const uint8_t* act_a, const uint8_t* act_b, const uint8_t* rng8, const uint32_t* rng32,
+                           const double* rngf64, int32_t* obs, float* reward, uint8_t* flags, int32_t* reset_obs, int64_t n,
                            soccer_stream_t stream)
 {
     if (!table || !state || !act_a || !act_b || !rng8 || !obs || !reward || !flags || n < 0) return SOCCER_EINVAL;
     if (!rng32 && !rngf64) return SOCCER_EINVAL;
     PitchDev P; int rc = make_pitch_dev(pitch, &P); if (rc) return rc;
     int64_t bytes; rc = table_bytes_of(P, &bytes); if (rc) return rc;
-    if (!aligned(table, 16)) return SOCCER_EINVAL;
+    if (!aligned(table, 16) || (slip_index && !aligned(slip_index, 16))) return SOCCER_EINVAL;
     if (n == 0) return SOCCER_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const void* draw = rngf64 ? (const void*)rngf64 : (const void*)rng32;
@@ -1027,12 +1045,25 @@ int soccer_step_table_slip(const soccer_pitch* pitch, const uint16_t* table, uin
     int64_t done_n = 0;
     if (vec) {
         const int64_t n_groups = n / 4;
+        // with a slip index, and room for it and the deferral queue next to the table (5x4): constant-prefix fast
+        // path + queued walk; else the in-place walk
+        const int64_t fc_bytes = ((int64_t)P.nS * 25 + 15) / 16 * 16;
+        const int64_t smem_q = bytes + 16 + fc_bytes + 2 * (int64_t)kSlipQueueMax;
+        const bool queued = slip_index && smem_q <= 227 * 1024 - 1024;
 #define SOCCER_LAUNCH_SLIP_T(RO, F64)                                                                     \
         do {                                                                                              \
-            const int e0 = allow_big_smem(k_step_table_slip<RO, F64>, bytes + 16);                        \
-            if (e0) return e0;                                                                            \
-            k_step_table_slip<RO, F64><<<table_grid(n_groups, kSlipThreads), kSlipThreads, (size_t)bytes + 16, st>>>(  \
-                P, table, (uint32_t)bytes, state, act_a, act_b, rng8, draw, obs, reward, flags, reset_obs, n_groups); \
+            if (queued) {                                                                                 \
+                const int e0 = allow_big_smem(k_step_table_slip_q<RO, F64>, smem_q);                      \
+                if (e0) return e0;                                                                        \
+                k_step_table_slip_q<RO, F64><<<table_grid(n_groups, kTableThreads), kTableThreads, (size_t)smem_q, st>>>(  \
+                    P, table, (uint32_t)bytes, slip_index, (uint32_t)fc_bytes, state, act_a, act_b, rng8, draw, obs, reward, \
+                    flags, reset_obs, n_groups);                                                          \
+            } else {                                                                                      \
+                const int e0 = allow_big_smem(k_step_table_slip<RO, F64>, bytes + 16);                    \
+                if (e0) return e0;                                                                        \
+                k_step_table_slip<RO, F64><<<table_grid(n_groups, kSlipThreads), kSlipThreads, (size_t)bytes + 16, st>>>(  \
+                    P, table, (uint32_t)bytes, state, act_a, act_b, rng8, draw, obs, reward, flags, reset_obs, n_groups); \
+            }                                                                                             \
         } while (0)
         if (reset_obs) { if (rngf64) SOCCER_LAUNCH_SLIP_T(true, true); else SOCCER_LAUNCH_SLIP_T(true, false); }
         else { if (rngf64) SOCCER_LAUNCH_SLIP_T(false, true); else SOCCER_LAUNCH_SLIP_T(false, false); }

@@ -11,6 +11,7 @@ kernels behind include/soccer_b200.h.  There is no CPU fallback.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import numpy as np
@@ -101,6 +102,7 @@ class SoccerVecEnv:
         self.reset_obs = torch.zeros(n, dtype=torch.int32, device=dev) if self.want_reset_obs else None
         self.step_count = 0
         self.table = None
+        self.slip_index = None
         if self.kernel == "table":
             nbytes = C.c_int64()
             check(self.lib.soccer_step_table_bytes_host(C.byref(self.pitch), C.byref(nbytes)), "step_table_bytes")
@@ -108,6 +110,14 @@ class SoccerVecEnv:
             with torch.cuda.device(dev):
                 check(self.lib.soccer_build_step_table(C.byref(self.pitch), _ptr(self.table), _stream(dev)),
                       "soccer_build_step_table")
+                if self.slip_prob != 0.0:
+                    # slip index: first slip combination with more than one outcome per (obs, joint action); lets
+                    # soccer_step_table_slip decide most draws from constant prefix sums
+                    ib = C.c_int64()
+                    check(self.lib.soccer_slip_index_bytes_host(C.byref(self.pitch), C.byref(ib)), "slip_index_bytes")
+                    self.slip_index = torch.zeros(ib.value, dtype=torch.uint8, device=dev)
+                    check(self.lib.soccer_build_slip_index(C.byref(self.pitch), _ptr(self.table), _ptr(self.slip_index),
+                                                           _stream(dev)), "soccer_build_slip_index")
                 # the step kernels prefetch the table BEFORE their grid-dependency wait (programmatic
                 # dependent launch), so it must be complete before the first step is enqueued
                 torch.cuda.current_stream(dev).synchronize()
@@ -236,8 +246,10 @@ class SoccerVecEnv:
                 if self.slip_prob != 0.0:
                     if rng32 is None and rngf64 is None:
                         raise ValueError("slip_prob > 0 needs the step draw: rng32 (int32/uint32 bits) or rngf64")
+                    use_index = self.slip_index is not None and os.environ.get("SOCCER_B200_SLIP_WALK", "0") != "1"
                     check(self.lib.soccer_step_table_slip(
-                        *args, _ptr(None if rngf64 is not None else self._check_vec(rng32, torch.int32, "rng32")),
+                        args[0], args[1], _ptr(self.slip_index if use_index else None), *args[2:],
+                        _ptr(None if rngf64 is not None else self._check_vec(rng32, torch.int32, "rng32")),
                         _ptr(self._check_vec(rngf64, torch.float64, "rngf64")), *outs), "soccer_step_table_slip")
                 else:
                     check(self.lib.soccer_step_table(*args, *outs), "soccer_step_table")

@@ -253,10 +253,18 @@ int soccer_step_table_packed(const soccer_pitch *pitch, const uint16_t *table, u
  * the reference's order with sequential fp64 sums (bit-exact), one more look-up yields the chosen
  * outcome.  The step draw u comes from rngf64[n] (raw) or rng32[n] ((r + 0.5) / 2^32), exactly one of
  * them; rng8 bits 2..3 carry the reset draw as in soccer_step.  SOCCER_LAYOUT_INDEX states. */
-int soccer_step_table_slip(const soccer_pitch *pitch, const uint16_t *table, uint32_t *state,
-                           const uint8_t *act_a, const uint8_t *act_b, const uint8_t *rng8,
+int soccer_step_table_slip(const soccer_pitch *pitch, const uint16_t *table, const uint8_t *slip_index,
+                           uint32_t *state, const uint8_t *act_a, const uint8_t *act_b, const uint8_t *rng8,
                            const uint32_t *rng32, const double *rngf64, int32_t *obs, float *reward,
                            uint8_t *flags, int32_t *reset_obs, int64_t n, soccer_stream_t stream);
+/* Optional accelerator of soccer_step_table_slip: slip_index[obs*25 + aa*5 + ab] = the first of the 9 slip
+ * combinations (SIM:209-223 order) whose move pair has more than one outcome, 9 if none -- built on the device
+ * from the step table.  With it, envs whose draw is decided before any such combination (the common case)
+ * take a constant-prefix-sum fast path, the others are walked as before; results are identical.  NULL = walk
+ * every env.  bytes: nS * 25 rounded up to 16. */
+int soccer_slip_index_bytes_host(const soccer_pitch *pitch, int64_t *bytes);
+int soccer_build_slip_index(const soccer_pitch *pitch, const uint16_t *table, uint8_t *slip_index,
+                            soccer_stream_t stream);
 /* soccer_rollout (uniform random policy; slip_prob >= 0) on SOCCER_LAYOUT_INDEX states */
 int soccer_rollout_table(const soccer_pitch *pitch, const uint16_t *table, uint32_t *state,
                          uint64_t seed, uint64_t step0, int32_t K, uint64_t env_id_base,

@@ -846,3 +846,52 @@ def test_checkpoint_resume_continues_the_trajectory(dev, k_save, k_load, tmp_pat
     assert torch.equal(b.current_obs(), ref.current_obs()) and torch.equal(b.timesteps(), ref.timesteps())
     with pytest.raises(ValueError):
         SoccerVecEnv(N + 1, device=dev).load_state_dict(a.state_dict())
+
+
+@pytest.mark.parametrize("slip", [0.2, 0.5, 1.0, 1e-9])
+@pytest.mark.parametrize("n", [4099, 1 << 16, (1 << 18) + 4])
+def test_slip_fast_path_with_queue_equals_walk(dev, slip, n, monkeypatch):
+    """soccer_step_table_slip with the slip index (constant-prefix fast path, deferred envs walked from a shared-memory
+    queue) == the in-place walk of every env, step after step: obs, reward, flags, reset_obs and states; uint32 and
+    raw fp64 draws incl. u = 0, u just below 1 and u on the constant thresholds; a population forced onto collision
+    states so that whole warps are deferred."""
+    from gym_soccer_littman94_b200.envs import SoccerVecEnv
+    rs = np.random.RandomState(n)
+    envs = {}
+    for mode in ("walk", "queued"):
+        monkeypatch.setenv("SOCCER_B200_SLIP_WALK", "1" if mode == "walk" else "0")
+        envs[mode] = SoccerVecEnv(n, slip_prob=slip, device=dev, kernel="table")
+    assert envs["queued"].slip_index is not None
+    init = _t(rs.randint(0, 16, n).astype(np.uint8), dev)
+    for e in envs.values():
+        e.reset(init)
+    # E_k of slip_prob (sequential fp64 sums of the 9 combination probabilities, SIM:209-223 order)
+    sp = slip
+    mp = [(1 - sp) ** 2] + [(1 - sp) * sp / 2] * 4 + [sp * sp / 4] * 4
+    E = np.cumsum(np.array(mp, np.float64))
+    for t in range(60):
+        a, b, r = (_t(rs.randint(0, hi, n).astype(np.uint8), dev) for hi in (5, 5, 16))
+        if t == 20:                                            # adjacent players walking into each other: collisions everywhere
+            obs_adj = envs["walk"].current_obs().clone()
+            from gym_soccer_littman94_b200.envs import SoccerSimultaneousEnv
+            idx = SoccerSimultaneousEnv(device=dev)._state_to_observation((1, 2, 1, 3, 0))
+            obs_adj[::2] = idx
+            for e in envs.values():
+                e.set_state(obs_adj)
+            a[:] = 3; b[:] = 4
+        outs = {}
+        if t % 2 == 0:
+            r32 = _t(rs.randint(-2**31, 2**31 - 1, n).astype(np.int32), dev)
+            for mode, e in envs.items():
+                monkeypatch.setenv("SOCCER_B200_SLIP_WALK", "1" if mode == "walk" else "0")
+                outs[mode] = [x.clone() for x in e.step(a, b, r, rng32=r32)]
+        else:
+            u = rs.random_sample(n)
+            u[:9] = E; u[9:18] = np.nextafter(E, 0); u[18] = 0.0; u[19] = 1.0 - 2.0 ** -53; u[20:29] = np.nextafter(E, 2)
+            uf = _t(u, dev)
+            for mode, e in envs.items():
+                monkeypatch.setenv("SOCCER_B200_SLIP_WALK", "1" if mode == "walk" else "0")
+                outs[mode] = [x.clone() for x in e.step(a, b, r, rngf64=uf)]
+        for x, y in zip(outs["walk"], outs["queued"]):
+            assert torch.equal(x, y), t
+        assert torch.equal(envs["walk"].state, envs["queued"].state), t
