@@ -1048,7 +1048,9 @@ int soccer_step_table_slip(const soccer_pitch* pitch, const uint16_t* table, con
         // with a slip index, and room for it and the deferral queue next to the table (5x4): constant-prefix fast
         // path + queued walk; else the in-place walk
         const int64_t fc_bytes = ((int64_t)P.nS * 25 + 15) / 16 * 16;
-        const int64_t smem_q = bytes + 16 + fc_bytes + 2 * (int64_t)kSlipQueueMax;
+        const int64_t smem_q = bytes + 16 + fc_bytes + (int64_t)kSlipQueueBytes;
+        SlipE E;                                      // E_k: sequential fp64 sums of the combination probabilities (SIM:241, nsp = 1)
+        { double acc = 0.0; for (int c = 0; c < 9; ++c) { acc += P.mp[c]; E.e[c] = acc; } }
         const bool queued = slip_index && smem_q <= 227 * 1024 - 1024;
 #define SOCCER_LAUNCH_SLIP_T(RO, F64)                                                                     \
         do {                                                                                              \
@@ -1056,7 +1058,7 @@ int soccer_step_table_slip(const soccer_pitch* pitch, const uint16_t* table, con
                 const int e0 = allow_big_smem(k_step_table_slip_q<RO, F64>, smem_q);                      \
                 if (e0) return e0;                                                                        \
                 k_step_table_slip_q<RO, F64><<<table_grid(n_groups, kTableThreads), kTableThreads, (size_t)smem_q, st>>>(  \
-                    P, table, (uint32_t)bytes, slip_index, (uint32_t)fc_bytes, state, act_a, act_b, rng8, draw, obs, reward, \
+                    P, table, (uint32_t)bytes, slip_index, (uint32_t)fc_bytes, E, state, act_a, act_b, rng8, draw, obs, reward, \
                     flags, reset_obs, n_groups);                                                          \
             } else {                                                                                      \
                 const int e0 = allow_big_smem(k_step_table_slip<RO, F64>, bytes + 16);                    \

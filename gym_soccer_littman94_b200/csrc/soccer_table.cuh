@@ -525,7 +525,7 @@ k_step_table_slip(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_
 // (k_build_slip_index), decides that with one byte load.  Envs with k >= fc -- a few percent -- are not walked
 // in place (one such lane would hold its whole warp in the 150-instruction walk): their ids go to the warp's
 // shared-memory queue (ballot + popc), and after the fast pass over its 256 envs the warp takes the queued envs
-// through table_step_slip 32 at a time, densely.  Results are bit-identical to k_step_table_slip (and to the reference): same sums, same compares.
+// through table_step_slip 32 at a time.  Results are bit-identical to k_step_table_slip (and to the reference): same sums, same compares.
 __global__ void __launch_bounds__(kThreads)
 k_build_slip_index(const PitchDev P, int32_t nS, const uint16_t* __restrict__ table, uint8_t* __restrict__ fc)
 {
@@ -543,8 +543,10 @@ k_build_slip_index(const PitchDev P, int32_t nS, const uint16_t* __restrict__ ta
     }
 }
 
-constexpr int kSlipQueueMax = 2 * 4 * kTableThreads;        // every env of a tile can be deferred (256 per warp)
-struct SlipFast { uint32_t fc, ecum, cacb, mv3; };          // shared-window addresses
+constexpr int kSlipQueueWarp = 256;                         // per warp: all 2 x 32 x 4 envs of an iteration can be deferred
+constexpr int kSlipQueueBytes = kSlipQueueWarp * (kTableThreads / 32);   // one byte per entry: every KB of shared memory saved is L1 for the walk's re-reads
+struct SlipFast { uint32_t fc, cacb, mv3; };                // shared-window addresses
+struct SlipE { double e[9]; };                              // E_k, a kernel parameter: DSETP reads it from the constant bank
 __device__ __forceinline__ uint32_t lds_u8(uint32_t addr)
 {
     uint32_t v;
@@ -552,15 +554,15 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr)
     return v;
 }
 // fast path of one env: returns the finished step and whether it has to be redone by the walk
-__device__ __forceinline__ TblOut table_step_slip_fast(const TblCtx& c, const SlipFast& f, uint32_t s, uint32_t aa,
-                                                       uint32_t ab, double u, uint32_t rsel4, bool& defer)
+__device__ __forceinline__ TblOut table_step_slip_fast(const TblCtx& c, const SlipFast& f, const SlipE& E, uint32_t s,
+                                                       uint32_t aa, uint32_t ab, double u, uint32_t rsel4, bool& defer)
 {
     const uint32_t obsi = min(s & 0xFFFFu, c.last / 100u);
     aa = min(aa, 4u); ab = min(ab, 4u);
     const uint32_t fcv = lds_u8(f.fc + obsi * 25u + aa * 5u + ab);
     uint32_t k = 0;
 #pragma unroll
-    for (int j = 0; j < 9; ++j) k += lds_f64(f.ecum + 8u * j) <= u ? 1u : 0u;      // E_j non-decreasing: k = first E_k > u
+    for (int j = 0; j < 9; ++j) k += E.e[j] <= u ? 1u : 0u;                       // E_j non-decreasing: k = first E_k > u
     defer = k >= fcv;                                                              // incl. k == 9: all-False -> walk
     const uint32_t cc = lds_u8(f.cacb + min(k, 8u));
     const uint32_t ma = lds_u8(f.mv3 + aa * 3u + (cc & 3u)), mb = lds_u8(f.mv3 + ab * 3u + (cc >> 4));
@@ -572,7 +574,7 @@ __device__ __forceinline__ TblOut table_step_slip_fast(const TblCtx& c, const Sl
 template <bool RESET_OBS, bool F64>
 __global__ void __launch_bounds__(kTableThreads, 1)
 k_step_table_slip_q(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t table_bytes,
-                    const uint8_t* __restrict__ gfc, uint32_t fc_bytes,
+                    const uint8_t* __restrict__ gfc, uint32_t fc_bytes, const SlipE E,
                     uint32_t* __restrict__ state, const uint8_t* __restrict__ act_a, const uint8_t* __restrict__ act_b,
                     const uint8_t* __restrict__ rng, const void* __restrict__ draw, int32_t* __restrict__ obs,
                     float* __restrict__ reward, uint8_t* __restrict__ flags, int32_t* __restrict__ reset_obs, int64_t n_groups)
@@ -580,17 +582,12 @@ k_step_table_slip_q(const PitchDev P, const uint16_t* __restrict__ gtable, uint3
     extern __shared__ __align__(128) uint8_t smem_raw[];     // [table][isd 16 B][fc][queue u16 x kSlipQueueMax]
     __shared__ __align__(8) uint64_t bar;
     __shared__ __align__(16) double prt[kPrtDoubles];
-    __shared__ __align__(16) double ecum[10];
     __shared__ uint8_t cacb[16], mv3[16];
     slip_build_prt(prt, P);
     if (threadIdx.x < 9) cacb[threadIdx.x] = (uint8_t)(combo_a((int)threadIdx.x) | (combo_b((int)threadIdx.x) << 4));
     if (threadIdx.x < 15) {
         const uint32_t a = threadIdx.x / 3u, cmb = threadIdx.x % 3u;
         mv3[threadIdx.x] = (uint8_t)(cmb == 0 ? a : slip_move(a, (int)cmb - 1));
-    }
-    if (threadIdx.x == 0) {
-        double E = 0.0;
-        for (int k = 0; k < 9; ++k) { E = __dadd_rn(E, __dmul_rn(P.mp[k], 1.0)); ecum[k] = E; }   // SIM:241 with nsp = 1
     }
     // stage table + slip index with ONE mbarrier
     if (threadIdx.x == 0) {
@@ -607,8 +604,8 @@ k_step_table_slip_q(const PitchDev P, const uint16_t* __restrict__ gtable, uint3
     __syncthreads();
     const TblCtx c = make_ctx(smem_raw, table_bytes, P);
     const SlipCtx sc = { smem_u32(prt), slip_first_k(P) };
-    const SlipFast sf = { c.isd + 16u, smem_u32(ecum), smem_u32(cacb), smem_u32(mv3) };
-    uint16_t* queue = reinterpret_cast<uint16_t*>(smem_raw + table_bytes + 16 + fc_bytes);
+    const SlipFast sf = { c.isd + 16u, smem_u32(cacb), smem_u32(mv3) };
+    uint8_t* queue = smem_raw + table_bytes + 16 + fc_bytes;
     uint4* st4 = reinterpret_cast<uint4*>(state);
     const uint32_t* a4 = reinterpret_cast<const uint32_t*>(act_a);
     const uint32_t* b4 = reinterpret_cast<const uint32_t*>(act_b);
@@ -620,16 +617,28 @@ k_step_table_slip_q(const PitchDev P, const uint16_t* __restrict__ gtable, uint3
     wait_table(&bar);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const uint32_t lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u;
-    uint16_t* wq = queue + (threadIdx.x >> 5) * 256;        // this warp's queue: its 2 x 32 x 4 envs can all be deferred
+    uint8_t* wq = queue + (threadIdx.x >> 5) * kSlipQueueWarp;   // this warp's queue: (half << 7 | lane << 2 | env) of the iteration
     // warp-level deferral: no CTA barrier, so the warps of the CTA drift apart and their loads overlap the others' walks
+    uint32_t cnt = 0;                                        // warp-uniform: queued envs of this warp
+    // the walk of up to 32 queued envs of the iteration at `wbase`, one per lane (exact: table_step_slip)
+    auto walk = [&](int64_t wbase, uint32_t first, uint32_t count) {
+        if (lane < count) {
+            const uint32_t id = wq[first + lane];
+            const int64_t env = (wbase + (int64_t)(id >> 7) * stride + ((id >> 2) & 31u)) * 4 + (id & 3u);
+            const uint32_t s = __ldcg(state + env), rg = rng[env];
+            const double ud = F64 ? reinterpret_cast<const double*>(draw)[env]
+                                  : u_from_rng32(reinterpret_cast<const uint32_t*>(draw)[env]);
+            const TblOut o = table_step_slip(c, sc, s, act_a[env], act_b[env], ud, rg & 0xCu);
+            state[env] = o.state; obs[env] = (int32_t)o.obs; reward[env] = (float)o.rew_i; flags[env] = (uint8_t)o.flags;
+            if (RESET_OBS) reset_obs[env] = (int32_t)o.reset_obs;
+        }
+    };
     for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < n_groups; base += 2 * stride) {
-        uint32_t cnt = 0;                                    // warp-uniform
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int64_t g = base + (int64_t)h * stride + threadIdx.x;
             const bool valid = g < n_groups;
             Group4 x = {};
-            uint4 d32 = make_uint4(0, 0, 0, 0);
             double u[4] = { 0.0, 0.0, 0.0, 0.0 };
             if (valid) {
                 x = load_group(st4, a4, b4, r4, g);
@@ -638,7 +647,7 @@ k_step_table_slip_q(const PitchDev P, const uint16_t* __restrict__ gtable, uint3
                     const double2 d1 = __ldcs(reinterpret_cast<const double2*>(draw) + 2 * g + 1);
                     u[0] = d0.x; u[1] = d0.y; u[2] = d1.x; u[3] = d1.y;
                 } else {
-                    d32 = __ldcs(reinterpret_cast<const uint4*>(draw) + g);
+                    const uint4 d32 = __ldcs(reinterpret_cast<const uint4*>(draw) + g);
                     u[0] = u_from_rng32(d32.x); u[1] = u_from_rng32(d32.y); u[2] = u_from_rng32(d32.z); u[3] = u_from_rng32(d32.w);
                 }
             }
@@ -648,13 +657,13 @@ k_step_table_slip_q(const PitchDev P, const uint16_t* __restrict__ gtable, uint3
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 bool defer;
-                const TblOut o = table_step_slip_fast(c, sf, sv[e], __byte_perm(x.a, 0, 0x4440 + e), __byte_perm(x.b, 0, 0x4440 + e),
+                const TblOut o = table_step_slip_fast(c, sf, E, sv[e], __byte_perm(x.a, 0, 0x4440 + e), __byte_perm(x.b, 0, 0x4440 + e),
                                                       u[e], __byte_perm(rs4, 0, 0x4440 + e), defer);
                 defer &= valid;
                 so[e] = defer ? sv[e] : o.state;             // deferred: the ORIGINAL state stays for the walk to read
                 oo[e] = o.obs; rr[e] = __float_as_uint((float)o.rew_i); ro[e] = o.reset_obs; ff[e] = o.flags;
                 const uint32_t m = __ballot_sync(0xFFFFFFFFu, defer);
-                if (defer) wq[cnt + __popc(m & lt_mask)] = (uint16_t)((h << 7) | (lane << 2) | e);
+                if (defer) wq[cnt + __popc(m & lt_mask)] = (uint8_t)((h << 7) | (lane << 2) | e);
                 cnt += __popc(m);
             }
             if (valid) {
@@ -665,18 +674,12 @@ k_step_table_slip_q(const PitchDev P, const uint16_t* __restrict__ gtable, uint3
                 if (RESET_OBS) st_stream(q4 + g, make_uint4(ro[0], ro[1], ro[2], ro[3]));
             }
         }
-        __syncwarp();                                        // queue complete, the warp's stores ordered before the fix-ups
-        const int64_t wbase = base + (threadIdx.x & ~31u);
-        for (uint32_t i = lane; i < cnt; i += 32) {
-            const uint32_t id = wq[i];
-            const int64_t env = (wbase + (int64_t)(id >> 7) * stride + ((id >> 2) & 31u)) * 4 + (id & 3u);
-            const uint32_t s = __ldcg(state + env), rg = rng[env];
-            const double ud = F64 ? reinterpret_cast<const double*>(draw)[env]
-                                  : u_from_rng32(reinterpret_cast<const uint32_t*>(draw)[env]);
-            const TblOut o = table_step_slip(c, sc, s, act_a[env], act_b[env], ud, rg & 0xCu);
-            state[env] = o.state; obs[env] = (int32_t)o.obs; reward[env] = (float)o.rew_i; flags[env] = (uint8_t)o.flags;
-            if (RESET_OBS) reset_obs[env] = (int32_t)o.reset_obs;
-        }
+        __syncwarp();                                        // queue entries and the placeholder stores ordered before the walks
+        // Walk them right away, while the lines the fast pass has just written are still in L2.  (Carrying fewer
+        // than 32 queued envs over to the next iteration keeps the walk's lanes full -- 144 vs 134 G env-steps/s at
+        // 2^22 envs -- but the late 1- and 4-byte fix-ups then hit lines already evicted to HBM: 120 vs 148 G at 2^24.)
+        for (uint32_t first = 0; first < cnt; first += 32u) walk(base + (threadIdx.x & ~31u), first, min(32u, cnt - first));
+        cnt = 0;
         __syncwarp();                                        // queue drained before the warp refills it
     }
 }
