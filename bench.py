@@ -505,6 +505,42 @@ def run_ours(args):
                                  "hbm_gbs_at_20B": n6 * 20 / (ms6 * 1e-3) / 1e9, "frac_of_hbm_peak": n6 * 20 / (ms6 * 1e-3) / 1e9 / peak}
         del e6, in6, out6
         torch.cuda.empty_cache()
+        # K1 variants at 2^24 envs: slip_prob = 0.2 with injected 32-bit step draws (24 B per
+        # env-step) and slip 0 with on-device Philox draws (19 B), both through the shared-memory table
+        try:
+            n7 = 1 << 24
+            g7 = torch.Generator(device=dev).manual_seed(11)
+            in7 = [tuple(torch.randint(0, hi, (n7,), dtype=torch.uint8, device=dev, generator=g7) for hi in (5, 5, 16)) +
+                   (torch.randint(-2**31, 2**31 - 1, (n7,), dtype=torch.int32, device=dev, generator=g7),) for _ in range(2)]
+            variants = {}
+            for tag, kw, nbytes in (("slip0.2_injected", dict(slip_prob=0.2), 24), ("philox_draws", dict(rng_mode="philox"), 19)):
+                e7 = SoccerVecEnv(n7, device=dev, kernel="table", want_reset_obs=False, **kw)
+
+                def step7(i):
+                    a_, b_, r_, r32_ = in7[i % 2]
+                    if tag.startswith("slip"):
+                        e7.step(a_, b_, r_, rng32=r32_)
+                    else:
+                        e7.step(a_, b_)
+                e7.reset(in7[0][2] if tag.startswith("slip") else None)
+                for i in range(30):                 # play the population in (the slip fast path depends on it)
+                    step7(i)
+                q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                q0.record()
+                for i in range(20):
+                    step7(i)
+                q1.record()
+                torch.cuda.synchronize()
+                ms7 = q0.elapsed_time(q1) / 20
+                variants[tag] = {"env_steps_per_s": n7 / (ms7 * 1e-3), "bytes_per_env_step": nbytes,
+                                 "hbm_gbs": n7 * nbytes / (ms7 * 1e-3) / 1e9, "frac_of_hbm_peak": n7 * nbytes / (ms7 * 1e-3) / 1e9 / peak}
+                del e7
+            extra["k1_variants_2^24_envs"] = variants
+            del in7
+            torch.cuda.empty_cache()
+        except Exception as e:  # noqa: BLE001
+            extra["k1_variants_2^24_envs"] = {"error": repr(e)}
         n2, T2 = 4096, 1000
         e2 = SoccerVecEnv(n2, device=dev, kernel="auto", want_reset_obs=False)
         a, b, r = (torch.randint(0, hi, (T2, n2), dtype=torch.uint8, device=dev) for hi in (5, 5, 16))
