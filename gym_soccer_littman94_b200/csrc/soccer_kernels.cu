@@ -1103,8 +1103,9 @@ int soccer_rollout_table_policy(const soccer_pitch* pitch, const uint16_t* table
     do {                                                                                                 \
         const int e0 = allow_big_smem(k_rollout_table<VEC, STR, POL, SLIP>, smem);                       \
         if (e0) return e0;                                                                               \
-        k_rollout_table<VEC, STR, POL, SLIP><<<table_grid(ITEMS, kRolloutThreads), kRolloutThreads, smem, st>>>( \
-            P, table, (uint32_t)bytes, policy_a, policy_b, ra);                                          \
+        const int e1 = launch_pdl(k_rollout_table<VEC, STR, POL, SLIP>, table_grid(ITEMS, kRolloutThreads),      \
+                                  kRolloutThreads, (size_t)smem, st, P, table, (uint32_t)bytes, policy_a, policy_b, ra); \
+        if (e1) return e1;                                                                               \
     } while (0)
 #define SOCCER_PICK_ROLLOUT_T(POL, SLIP)                                                                 \
     do {                                                                                                 \

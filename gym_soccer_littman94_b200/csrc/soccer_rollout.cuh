@@ -247,6 +247,9 @@ k_rollout_table(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t 
     __shared__ __align__(8) uint64_t bar;
     __shared__ unsigned int blk_stats[4];
     __shared__ int blk_net;
+    // programmatic dependent launch: back-to-back rollouts stage their table (and policies: constant inputs) while
+    // the previous launch drains; state, streams and statistics are only touched after pdl_wait()
+    pdl_launch_dependents();
     if (threadIdx.x < 4) blk_stats[threadIdx.x] = 0;
     if (threadIdx.x == 4) blk_net = 0;
     TableStepper<POLICY, SLIP> S;
@@ -267,6 +270,7 @@ k_rollout_table(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t 
     stage_table(smem_raw, gtable, table_bytes, &bar, P);      // ends with __syncthreads(): policies visible
     S.c = make_ctx(smem_raw, table_bytes, P);
     wait_table(&bar);
+    pdl_wait();
     rollout_body<VEC, STREAMS>(S, a, blk_stats, &blk_net);
 }
 

@@ -3,7 +3,7 @@ import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from gym_soccer_littman94_b200.envs import SoccerVecEnv
 dev = torch.device("cuda", 0)
-for kernel in ("table", "rules"):
+for kernel in os.environ.get("AB_KERNELS", "table,rules").split(","):
     for n in (1 << 20, 1 << 21):
         K = 64
         e = SoccerVecEnv(n, device=dev, kernel=kernel, rng_mode="philox", seed=0)
