@@ -262,6 +262,10 @@ def run_ours(args):
     # (1) the timed region: EXACTLY K steps between two events, nothing else in the stream
     start, k_done, end = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     barrier()
+    if world > 1:
+        # device-side rendezvous right before the start event: the host-side barrier lets the ranks go tens of
+        # microseconds apart, which the closing all-reduce would otherwise charge to the early ranks' K steps
+        dist.all_reduce(torch.zeros(1, device=dev))
     start.record()
     for i in range(K):
         env.step(*ins[i % RING], out=outs[i % RING])
