@@ -10,7 +10,7 @@ way the reference's own tests exercise the reference class:
 import numpy as np
 import pytest
 
-from .conftest import load_golden, parse_tag
+from .conftest import parse_tag
 
 torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
