@@ -520,26 +520,40 @@ k_step_table_slip(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_
 // 97 % of all (state, move pair)s have ONE outcome, and the walk ends at the first combination in 64 % of the draws
 // (slip_prob 0.2), so for most envs the reference's cumulative sums are the CONSTANT prefix sums E_k of the nine
 // combination probabilities mp_k (accumulated like the reference: sequential __dadd_rn), and the pick is
-// k = #{E_j <= u} -- exact as long as no combination up to k has 2 or 4 outcomes.  The slip index fc[obs][aa*5+ab] =
-// first combination with more than one outcome (9 = none), built once on the device from the step table
-// (k_build_slip_index), decides that with one byte load.  Envs with k >= fc -- a few percent -- are not walked
+// k = #{E_j <= u} -- exact as long as combination k has one outcome and the true end-of-combination sums up to k
+// equal the constant ones bit for bit.  The slip index -- one byte per (obs, aa*5+ab): bit k set <=> pick k must be
+// walked, built once on the device from the step table and the env's slip_prob (k_build_slip_index) -- decides that
+// with one byte load.  Envs whose pick has its bit set (or is 8 or 9) -- a few percent -- are not walked
 // in place (one such lane would hold its whole warp in the 150-instruction walk): their ids go to the warp's
 // shared-memory queue (ballot + popc), and after the fast pass over its 256 envs the warp takes the queued envs
 // through table_step_slip 32 at a time.  Results are bit-identical to k_step_table_slip (and to the reference): same sums, same compares.
 __global__ void __launch_bounds__(kThreads)
 k_build_slip_index(const PitchDev P, int32_t nS, const uint16_t* __restrict__ table, uint8_t* __restrict__ fc)
 {
+    // Entry = 8-bit mask: bit k set <=> a draw whose constant-prefix pick is combination k must be walked.  That is the
+    // case when combination k itself has 2 or 4 outcomes (the pick falls on a slot inside it), or when some end-of-
+    // combination sum up to k differs from the constant E_j in ANY bit (a 2- or 4-outcome combination adds mp/2 twice
+    // or mp/4 four times instead of mp once; the roundings almost always agree, this checks it).  Picks 8 and 9 (the
+    // last combination, 1 % of the draws, and the all-False case) are always walked, so 8 bits suffice.
     const int64_t total = (int64_t)nS * 25;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
         const uint32_t obs = (uint32_t)(i / 25), ja = (uint32_t)(i % 25), aa = ja / 5u, ab = ja % 5u;
-        uint32_t first = 9u;
-        for (int k = 8; k >= 0; --k) {
+        uint32_t mask = 0;
+        double ec = 0.0, et = 0.0;
+        bool off = false;                           // the true sums have left the constant ones
+        for (int k = 0; k < 8; ++k) {
             const int ca = combo_a(k), cb = combo_b(k);
             const uint32_t ma = ca == 0 ? aa : slip_move(aa, ca - 1), mb = cb == 0 ? ab : slip_move(ab, cb - 1);
-            if ((table[obs * 100u + (ma * 5u + mb) * 4u] >> 12) & 3u) first = (uint32_t)k;
+            const uint32_t nl = (table[obs * 100u + (ma * 5u + mb) * 4u] >> 12) & 3u;
+            const double mp = P.mp[k];
+            ec = __dadd_rn(ec, __dmul_rn(mp, 1.0));
+            const double pr = __dmul_rn(mp, nl == 2u ? 0.25 : (nl == 1u ? 0.5 : 1.0));       // SIM:241
+            for (uint32_t j = 0; j < (1u << nl); ++j) et = __dadd_rn(et, pr);                // the reference's running sum
+            off |= __double_as_longlong(et) != __double_as_longlong(ec);
+            if ((nl != 0u && mp != 0.0) || off) mask |= 1u << k;
         }
-        fc[i] = (uint8_t)first;
+        fc[i] = (uint8_t)mask;
     }
 }
 
@@ -559,11 +573,11 @@ __device__ __forceinline__ TblOut table_step_slip_fast(const TblCtx& c, const Sl
 {
     const uint32_t obsi = min(s & 0xFFFFu, c.last / 100u);
     aa = min(aa, 4u); ab = min(ab, 4u);
-    const uint32_t fcv = lds_u8(f.fc + obsi * 25u + aa * 5u + ab);
+    const uint32_t dm = lds_u8(f.fc + obsi * 25u + aa * 5u + ab);                  // bit k: pick k must be walked
     uint32_t k = 0;
 #pragma unroll
     for (int j = 0; j < 9; ++j) k += E.e[j] <= u ? 1u : 0u;                       // E_j non-decreasing: k = first E_k > u
-    defer = k >= fcv;                                                              // incl. k == 9: all-False -> walk
+    defer = k >= 8u || ((dm >> k) & 1u) != 0u;                                     // incl. k == 9: all-False -> walk
     const uint32_t cc = lds_u8(f.cacb + min(k, 8u));
     const uint32_t ma = lds_u8(f.mv3 + aa * 3u + (cc & 3u)), mb = lds_u8(f.mv3 + ab * 3u + (cc >> 4));
     int32_t e;

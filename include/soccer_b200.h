@@ -257,11 +257,12 @@ int soccer_step_table_slip(const soccer_pitch *pitch, const uint16_t *table, con
                            uint32_t *state, const uint8_t *act_a, const uint8_t *act_b, const uint8_t *rng8,
                            const uint32_t *rng32, const double *rngf64, int32_t *obs, float *reward,
                            uint8_t *flags, int32_t *reset_obs, int64_t n, soccer_stream_t stream);
-/* Optional accelerator of soccer_step_table_slip: slip_index[obs*25 + aa*5 + ab] = the first of the 9 slip
- * combinations (SIM:209-223 order) whose move pair has more than one outcome, 9 if none -- built on the device
- * from the step table.  With it, envs whose draw is decided before any such combination (the common case)
- * take a constant-prefix-sum fast path, the others are walked as before; results are identical.  NULL = walk
- * every env.  bytes: nS * 25 rounded up to 16. */
+/* Optional accelerator of soccer_step_table_slip: slip_index[obs*25 + aa*5 + ab] = an 8-bit mask over the first 8 of
+ * the 9 slip combinations (SIM:209-223 order): bit k set <=> a draw that the CONSTANT prefix sums of the combination
+ * probabilities assign to combination k has to take the reference's walk (combination k has 2 or 4 outcomes, or an
+ * earlier one changed a running sum in some bit).  Built on the device from the step table and the pitch's
+ * slip_prob.  With it, most envs take a constant-prefix-sum fast path, the others (and picks 8, 9) are walked as
+ * before; results are identical.  NULL = walk every env.  bytes: nS * 25 rounded up to 16. */
 int soccer_slip_index_bytes_host(const soccer_pitch *pitch, int64_t *bytes);
 int soccer_build_slip_index(const soccer_pitch *pitch, const uint16_t *table, uint8_t *slip_index,
                             soccer_stream_t stream);
