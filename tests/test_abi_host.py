@@ -125,3 +125,26 @@ def test_host_state_packing_and_obs_index_vs_reference(L, tag):
         assert lib.soccer_pack_state_host(C.byref(p), C.byref(tup), 0, 0, C.byref(C.c_uint32())) == -1
     assert lib.soccer_obs_to_state_host(C.byref(p), 0, C.byref(C.c_uint32())) == -1
     assert lib.soccer_obs_to_state_host(C.byref(p), int(g["nS"]), C.byref(C.c_uint32())) == -1
+
+
+def test_packed_stream_formats_host_side():
+    """SoccerVecEnv.pack_joint / unpack_result (pure tensor code, no GPU): the joint-action byte and the 16-bit result
+    word of soccer_step_table_packed as include/soccer_b200.h documents them."""
+    import numpy as np
+    import torch
+    from gym_soccer_littman94_b200.envs import SoccerVecEnv
+    a = torch.arange(5, dtype=torch.uint8).repeat_interleave(5)
+    b = torch.arange(5, dtype=torch.uint8).repeat(5)
+    j = SoccerVecEnv.pack_joint(a, b)
+    assert j.dtype == torch.uint8 and torch.equal(j & 15, a) and torch.equal(j >> 4, b)
+    words, want = [], []
+    for obs in (0, 1, 253, 760, 4095):
+        for rew in (-1, 0, 1):
+            for term in (0, 1):
+                for trunc in (0, 1):
+                    w = obs | term << 12 | trunc << 13 | (rew & 3) << 14
+                    words.append(np.uint16(w).astype(np.int16))        # the host buffer is int16
+                    want.append((obs, float(rew), bool(term), bool(trunc)))
+    o, r, t, tr = SoccerVecEnv.unpack_result(torch.tensor(np.array(words)))
+    got = list(zip(o.tolist(), r.tolist(), t.tolist(), tr.tolist()))
+    assert got == want
