@@ -270,6 +270,7 @@ k_rollout_table(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t 
     stage_table(smem_raw, gtable, table_bytes, &bar, P);      // ends with __syncthreads(): policies visible
     S.c = make_ctx(smem_raw, table_bytes, P);
     wait_table(&bar);
+    if (SLIP) { launder(S.c.tbl); launder(S.c.isd); launder(S.sc.prt); }   // table_step_slip's relaxed loads stay below the wait
     pdl_wait();
     rollout_body<VEC, STREAMS>(S, a, blk_stats, &blk_net);
 }

@@ -368,6 +368,46 @@ __device__ __forceinline__ double lds_f64(uint32_t addr)
     asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
     return v;
 }
+// Relaxed (non-volatile) shared-memory loads for the look-up chains of the table slip steppers.  `asm volatile`
+// statements keep their program order, which serialises the dependent chains of the 4 envs of a thread (env 1's first
+// load cannot issue before env 0's last one, which waits for env 0's earlier loads): ILP 1.  Without `volatile` the
+// compiler interleaves them -- and could also hoist them above the barrier / mbarrier wait that publishes the data,
+// so every base address they use is passed through launder() AFTER that point: a value the compiler cannot see
+// through, hence no load that depends on it can move above it.
+#ifndef SOCCER_LDS_RELAXED
+#define SOCCER_LDS_RELAXED 1
+#endif
+__device__ __forceinline__ void launder(uint32_t& x) { asm volatile("" : "+r"(x) :: "memory"); }
+__device__ __forceinline__ double lds_f64_r(uint32_t addr)
+{
+    double v;
+#if SOCCER_LDS_RELAXED
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+#else
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+#endif
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u8_r(uint32_t addr)
+{
+    uint32_t v;
+#if SOCCER_LDS_RELAXED
+    asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+#else
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+#endif
+    return v;
+}
+__device__ __forceinline__ int32_t lds_s16_r(uint32_t addr)
+{
+    int32_t v;
+#if SOCCER_LDS_RELAXED
+    asm("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(addr));
+#else
+    asm volatile("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(addr));
+#endif
+    return v;
+}
 
 // slip step of one env by the rules.  The sums at the end of each combination are non-decreasing, so "first
 // entry whose running sum exceeds u" needs no found flag: the candidate moves on to combination k + 1 exactly

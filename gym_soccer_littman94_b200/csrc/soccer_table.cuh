@@ -207,10 +207,9 @@ __device__ __forceinline__ TblOut table_step_slip(const TblCtx& c, const SlipCtx
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
         uint32_t ent = ra[combo_a(k)] + ob[combo_b(k)];
-        uint32_t hi;
-        asm volatile("ld.shared.u8 %0, [%1+1];" : "=r"(hi) : "r"(ent));           // bits 4..5 = log2(#outcomes)
+        const uint32_t hi = lds_u8_r(ent + 1u);                                   // bits 4..5 = log2(#outcomes)
         const uint32_t nl4 = hi & 0x30u;                                          // 16 * log2(#outcomes) = prt byte offset
-        const double pr = lds_f64(sc.prt + k * 48 + nl4);
+        const double pr = lds_f64_r(sc.prt + k * 48 + nl4);
         E = __dadd_rn(E, pr);
         if (nl4) {                                                                // rare: 2 or 4 outcomes
             uint32_t slot = E <= u ? 1u : 0u;
@@ -230,8 +229,7 @@ __device__ __forceinline__ TblOut table_step_slip(const TblCtx& c, const SlipCtx
         const uint32_t ca = (uint32_t)combo_a((int)sc.first_k), cb = (uint32_t)combo_b((int)sc.first_k);
         pick = (ca == 0 ? ra[0] : (ca == 1 ? ra[1] : ra[2])) + (cb == 0 ? ob[0] : (cb == 1 ? ob[1] : ob[2]));
     }
-    int32_t e;
-    asm volatile("ld.shared.s16 %0, [%1];" : "=r"(e) : "r"(pick));
+    const int32_t e = lds_s16_r(pick);
     return table_finish(c, s, e, rsel4);
 }
 
@@ -476,8 +474,8 @@ k_step_table_slip(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_
     __shared__ __align__(16) double prt[kPrtDoubles];
     slip_build_prt(prt, P);
     stage_table(smem_raw, gtable, table_bytes, &bar, P);     // ends with __syncthreads(): prt visible
-    const TblCtx c = make_ctx(smem_raw, table_bytes, P);
-    const SlipCtx sc = { smem_u32(prt), slip_first_k(P) };
+    TblCtx c = make_ctx(smem_raw, table_bytes, P);
+    SlipCtx sc = { smem_u32(prt), slip_first_k(P) };
     uint4* st4 = reinterpret_cast<uint4*>(state);
     const uint32_t* a4 = reinterpret_cast<const uint32_t*>(act_a);
     const uint32_t* b4 = reinterpret_cast<const uint32_t*>(act_b);
@@ -487,6 +485,7 @@ k_step_table_slip(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_
     uint32_t* f4 = reinterpret_cast<uint32_t*>(flags);
     uint4* q4 = reinterpret_cast<uint4*>(reset_obs);
     wait_table(&bar);
+    launder(c.tbl); launder(c.isd); launder(sc.prt);        // the relaxed loads below stay below the wait
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_groups; g += stride) {
         const Group4 x = load_group(st4, a4, b4, r4, g);
@@ -559,29 +558,32 @@ k_build_slip_index(const PitchDev P, int32_t nS, const uint16_t* __restrict__ ta
 
 constexpr int kSlipQueueWarp = 256;                         // per warp: all 2 x 32 x 4 envs of an iteration can be deferred
 constexpr int kSlipQueueBytes = kSlipQueueWarp * (kTableThreads / 32);   // one byte per entry: every KB of shared memory saved is L1 for the walk's re-reads
-struct SlipFast { uint32_t fc, cacb, mv3; };                // shared-window addresses
+struct SlipFast { uint32_t fc, cacb, mv3, klut; };          // shared-window addresses
 struct SlipE { double e[9]; };                              // E_k, a kernel parameter: DSETP reads it from the constant bank
-__device__ __forceinline__ uint32_t lds_u8(uint32_t addr)
-{
-    uint32_t v;
-    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
-}
-// fast path of one env: returns the finished step and whether it has to be redone by the walk
+// fast path of one env: returns the finished step and whether it has to be redone by the walk.  The draw is the raw
+// fp64 u (F64: nine compares against the constant bank), or the uint32 r standing for (r + 0.5) / 2^32: k(r) is a step
+// function of r with nine steps, so a 4096-entry shared-memory table indexed by the top 12 bits of r yields k with
+// ONE load for every bucket that contains no step; the <= 9 buckets that do are marked 0xFF and walked.
+constexpr int kSlipLutBits = 12;
+template <bool F64>
 __device__ __forceinline__ TblOut table_step_slip_fast(const TblCtx& c, const SlipFast& f, const SlipE& E, uint32_t s,
-                                                       uint32_t aa, uint32_t ab, double u, uint32_t rsel4, bool& defer)
+                                                       uint32_t aa, uint32_t ab, double u, uint32_t r32, uint32_t rsel4,
+                                                       bool& defer)
 {
     const uint32_t obsi = min(s & 0xFFFFu, c.last / 100u);
     aa = min(aa, 4u); ab = min(ab, 4u);
-    const uint32_t dm = lds_u8(f.fc + obsi * 25u + aa * 5u + ab);                  // bit k: pick k must be walked
+    const uint32_t dm = lds_u8_r(f.fc + obsi * 25u + aa * 5u + ab);                  // bit k: pick k must be walked
     uint32_t k = 0;
+    if (F64) {
 #pragma unroll
-    for (int j = 0; j < 9; ++j) k += E.e[j] <= u ? 1u : 0u;                       // E_j non-decreasing: k = first E_k > u
-    defer = k >= 8u || ((dm >> k) & 1u) != 0u;                                     // incl. k == 9: all-False -> walk
-    const uint32_t cc = lds_u8(f.cacb + min(k, 8u));
-    const uint32_t ma = lds_u8(f.mv3 + aa * 3u + (cc & 3u)), mb = lds_u8(f.mv3 + ab * 3u + (cc >> 4));
-    int32_t e;
-    asm volatile("ld.shared.s16 %0, [%1];" : "=r"(e) : "r"(c.tbl + obsi * 200u + (ma * 5u + mb) * 8u));
+        for (int j = 0; j < 9; ++j) k += E.e[j] <= u ? 1u : 0u;                   // E_j non-decreasing: k = first E_k > u
+    } else {
+        k = lds_u8_r(f.klut + (r32 >> (32 - kSlipLutBits)));                         // 0xFF: a step of k(r) inside the bucket
+    }
+    defer = k >= 8u || ((dm >> k) & 1u) != 0u;                                     // incl. k == 9 (all-False) and 0xFF: walk
+    const uint32_t cc = lds_u8_r(f.cacb + min(k, 8u));
+    const uint32_t ma = lds_u8_r(f.mv3 + aa * 3u + (cc & 3u)), mb = lds_u8_r(f.mv3 + ab * 3u + (cc >> 4));
+    const int32_t e = lds_s16_r(c.tbl + obsi * 200u + (ma * 5u + mb) * 8u);
     return table_finish(c, s, e, rsel4);
 }
 
@@ -597,11 +599,23 @@ k_step_table_slip_q(const PitchDev P, const uint16_t* __restrict__ gtable, uint3
     __shared__ __align__(8) uint64_t bar;
     __shared__ __align__(16) double prt[kPrtDoubles];
     __shared__ uint8_t cacb[16], mv3[16];
+    __shared__ __align__(16) uint8_t klut[F64 ? 16 : (1 << kSlipLutBits)];
     slip_build_prt(prt, P);
     if (threadIdx.x < 9) cacb[threadIdx.x] = (uint8_t)(combo_a((int)threadIdx.x) | (combo_b((int)threadIdx.x) << 4));
     if (threadIdx.x < 15) {
         const uint32_t a = threadIdx.x / 3u, cmb = threadIdx.x % 3u;
         mv3[threadIdx.x] = (uint8_t)(cmb == 0 ? a : slip_move(a, (int)cmb - 1));
+    }
+    if (!F64) {
+        // k(r) per bucket of 2^20 consecutive draws: the same count at both ends <=> no step inside (k is monotone in r)
+        for (uint32_t b = threadIdx.x; b < (1u << kSlipLutBits); b += blockDim.x) {
+            const uint32_t lo = b << (32 - kSlipLutBits), hi = lo | ((1u << (32 - kSlipLutBits)) - 1u);
+            const double ulo = u_from_rng32(lo), uhi = u_from_rng32(hi);
+            uint32_t klo = 0, khi = 0;
+#pragma unroll
+            for (int j = 0; j < 9; ++j) { klo += E.e[j] <= ulo ? 1u : 0u; khi += E.e[j] <= uhi ? 1u : 0u; }
+            klut[b] = (uint8_t)(klo == khi ? klo : 0xFFu);
+        }
     }
     // stage table + slip index with ONE mbarrier
     if (threadIdx.x == 0) {
@@ -616,9 +630,9 @@ k_step_table_slip_q(const PitchDev P, const uint16_t* __restrict__ gtable, uint3
     }
     if (threadIdx.x < 4) reinterpret_cast<int32_t*>(smem_raw + table_bytes)[threadIdx.x] = P.isd_obs[threadIdx.x];
     __syncthreads();
-    const TblCtx c = make_ctx(smem_raw, table_bytes, P);
-    const SlipCtx sc = { smem_u32(prt), slip_first_k(P) };
-    const SlipFast sf = { c.isd + 16u, smem_u32(cacb), smem_u32(mv3) };
+    TblCtx c = make_ctx(smem_raw, table_bytes, P);
+    SlipCtx sc = { smem_u32(prt), slip_first_k(P) };
+    SlipFast sf = { c.isd + 16u, smem_u32(cacb), smem_u32(mv3), smem_u32(klut) };
     uint8_t* queue = smem_raw + table_bytes + 16 + fc_bytes;
     uint4* st4 = reinterpret_cast<uint4*>(state);
     const uint32_t* a4 = reinterpret_cast<const uint32_t*>(act_a);
@@ -629,6 +643,8 @@ k_step_table_slip_q(const PitchDev P, const uint16_t* __restrict__ gtable, uint3
     uint32_t* f4 = reinterpret_cast<uint32_t*>(flags);
     uint4* q4 = reinterpret_cast<uint4*>(reset_obs);
     wait_table(&bar);
+    launder(c.tbl); launder(c.isd); launder(sc.prt);        // the relaxed loads below stay below the wait
+    launder(sf.fc); launder(sf.cacb); launder(sf.mv3); launder(sf.klut);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const uint32_t lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u;
     uint8_t* wq = queue + (threadIdx.x >> 5) * kSlipQueueWarp;   // this warp's queue: (half << 7 | lane << 2 | env) of the iteration
@@ -647,23 +663,39 @@ k_step_table_slip_q(const PitchDev P, const uint16_t* __restrict__ gtable, uint3
             if (RESET_OBS) reset_obs[env] = (int32_t)o.reset_obs;
         }
     };
+    // one group of inputs: the state / action / draw words of 4 envs + their step draws
+    struct In { Group4 x; uint4 d0, d1; };
+    auto load_in = [&](int64_t g) {
+        In in;
+        in.x = load_group(st4, a4, b4, r4, g);
+        if (F64) {
+            in.d0 = __ldcs(reinterpret_cast<const uint4*>(draw) + 2 * g);
+            in.d1 = __ldcs(reinterpret_cast<const uint4*>(draw) + 2 * g + 1);
+        } else {
+            in.d0 = __ldcs(reinterpret_cast<const uint4*>(draw) + g);
+            in.d1 = in.d0;
+        }
+        return in;
+    };
+    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = g < n_groups;
+    In cur = {};
+    if (valid) cur = load_in(g);
     for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < n_groups; base += 2 * stride) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            const int64_t g = base + (int64_t)h * stride + threadIdx.x;
-            const bool valid = g < n_groups;
-            Group4 x = {};
+            // register prefetch of the thread's next group (the loop has no other way to overlap HBM latency with the
+            // shared-memory look-up chains of the current one)
+            const int64_t gn = g + stride;
+            const bool validn = gn < n_groups;
+            In nxt = cur;
+            if (validn) nxt = load_in(gn);
+            const Group4 x = cur.x;
             double u[4] = { 0.0, 0.0, 0.0, 0.0 };
-            if (valid) {
-                x = load_group(st4, a4, b4, r4, g);
-                if (F64) {
-                    const double2 d0 = __ldcs(reinterpret_cast<const double2*>(draw) + 2 * g);
-                    const double2 d1 = __ldcs(reinterpret_cast<const double2*>(draw) + 2 * g + 1);
-                    u[0] = d0.x; u[1] = d0.y; u[2] = d1.x; u[3] = d1.y;
-                } else {
-                    const uint4 d32 = __ldcs(reinterpret_cast<const uint4*>(draw) + g);
-                    u[0] = u_from_rng32(d32.x); u[1] = u_from_rng32(d32.y); u[2] = u_from_rng32(d32.z); u[3] = u_from_rng32(d32.w);
-                }
+            uint32_t r32[4] = { cur.d0.x, cur.d0.y, cur.d0.z, cur.d0.w };
+            if (F64) {
+                u[0] = __hiloint2double((int)cur.d0.y, (int)cur.d0.x); u[1] = __hiloint2double((int)cur.d0.w, (int)cur.d0.z);
+                u[2] = __hiloint2double((int)cur.d1.y, (int)cur.d1.x); u[3] = __hiloint2double((int)cur.d1.w, (int)cur.d1.z);
             }
             const uint32_t rs4 = x.r & 0x0C0C0C0Cu;
             const uint32_t sv[4] = { x.s.x, x.s.y, x.s.z, x.s.w };
@@ -671,8 +703,9 @@ k_step_table_slip_q(const PitchDev P, const uint16_t* __restrict__ gtable, uint3
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 bool defer;
-                const TblOut o = table_step_slip_fast(c, sf, E, sv[e], __byte_perm(x.a, 0, 0x4440 + e), __byte_perm(x.b, 0, 0x4440 + e),
-                                                      u[e], __byte_perm(rs4, 0, 0x4440 + e), defer);
+                const TblOut o = table_step_slip_fast<F64>(c, sf, E, sv[e], __byte_perm(x.a, 0, 0x4440 + e),
+                                                           __byte_perm(x.b, 0, 0x4440 + e), u[e], r32[e],
+                                                           __byte_perm(rs4, 0, 0x4440 + e), defer);
                 defer &= valid;
                 so[e] = defer ? sv[e] : o.state;             // deferred: the ORIGINAL state stays for the walk to read
                 oo[e] = o.obs; rr[e] = __float_as_uint((float)o.rew_i); ro[e] = o.reset_obs; ff[e] = o.flags;
@@ -687,6 +720,7 @@ k_step_table_slip_q(const PitchDev P, const uint16_t* __restrict__ gtable, uint3
                 st_stream(f4 + g, __byte_perm(__byte_perm(ff[0], ff[1], 0x0040), __byte_perm(ff[2], ff[3], 0x0040), 0x5410));
                 if (RESET_OBS) st_stream(q4 + g, make_uint4(ro[0], ro[1], ro[2], ro[3]));
             }
+            cur = nxt; g = gn; valid = validn;
         }
         __syncwarp();                                        // queue entries and the placeholder stores ordered before the walks
         // Walk them right away, while the lines the fast pass has just written are still in L2.  (Carrying fewer
