@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 #include <sys/mman.h>
 #include <string.h>
+#include <stdlib.h>
 #include <mutex>
 #include <unordered_set>
 

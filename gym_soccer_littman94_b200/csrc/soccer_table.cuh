@@ -556,6 +556,17 @@ k_build_slip_index(const PitchDev P, int32_t nS, const uint16_t* __restrict__ ta
     }
 }
 
+#ifndef SOCCER_SLIP_PLAIN_LOADS
+#define SOCCER_SLIP_PLAIN_LOADS 1
+#endif
+#ifndef SOCCER_SLIP_PLAIN_STORES
+#define SOCCER_SLIP_PLAIN_STORES 1
+#endif
+#if SOCCER_SLIP_PLAIN_STORES
+#define SOCCER_SLIP_ST(p, v) (*(p) = (v))
+#else
+#define SOCCER_SLIP_ST(p, v) st_stream((p), (v))
+#endif
 constexpr int kSlipQueueWarp = 256;                         // per warp: all 2 x 32 x 4 envs of an iteration can be deferred
 constexpr int kSlipQueueBytes = kSlipQueueWarp * (kTableThreads / 32);   // one byte per entry: every KB of shared memory saved is L1 for the walk's re-reads
 struct SlipFast { uint32_t fc, cacb, mv3, klut; };          // shared-window addresses
@@ -667,6 +678,17 @@ k_step_table_slip_q(const PitchDev P, const uint16_t* __restrict__ gtable, uint3
     struct In { Group4 x; uint4 d0, d1; };
     auto load_in = [&](int64_t g) {
         In in;
+#if SOCCER_SLIP_PLAIN_LOADS
+        // evict-normal loads: the walk re-reads the deferred envs' inputs a few microseconds later
+        in.x.s = ld_keep(st4 + g); in.x.a = a4[g]; in.x.b = b4[g]; in.x.r = r4[g];
+        if (F64) {
+            in.d0 = reinterpret_cast<const uint4*>(draw)[2 * g];
+            in.d1 = reinterpret_cast<const uint4*>(draw)[2 * g + 1];
+        } else {
+            in.d0 = reinterpret_cast<const uint4*>(draw)[g];
+            in.d1 = in.d0;
+        }
+#else
         in.x = load_group(st4, a4, b4, r4, g);
         if (F64) {
             in.d0 = __ldcs(reinterpret_cast<const uint4*>(draw) + 2 * g);
@@ -675,6 +697,7 @@ k_step_table_slip_q(const PitchDev P, const uint16_t* __restrict__ gtable, uint3
             in.d0 = __ldcs(reinterpret_cast<const uint4*>(draw) + g);
             in.d1 = in.d0;
         }
+#endif
         return in;
     };
     int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -715,10 +738,13 @@ k_step_table_slip_q(const PitchDev P, const uint16_t* __restrict__ gtable, uint3
             }
             if (valid) {
                 st_keep(st4 + g, make_uint4(so[0], so[1], so[2], so[3]));
-                st_stream(o4 + g, make_uint4(oo[0], oo[1], oo[2], oo[3]));
-                st_stream(w4 + g, make_uint4(rr[0], rr[1], rr[2], rr[3]));
-                st_stream(f4 + g, __byte_perm(__byte_perm(ff[0], ff[1], 0x0040), __byte_perm(ff[2], ff[3], 0x0040), 0x5410));
-                if (RESET_OBS) st_stream(q4 + g, make_uint4(ro[0], ro[1], ro[2], ro[3]));
+                // plain (evict-normal) stores, not st.global.cs: the deferred envs' 1- and 4-byte fix-ups follow within
+                // microseconds and must find these sectors in L2 -- a partial write to a sector already evicted to
+                // (ECC) HBM costs a read-modify-write there
+                SOCCER_SLIP_ST(o4 + g, make_uint4(oo[0], oo[1], oo[2], oo[3]));
+                SOCCER_SLIP_ST(w4 + g, make_uint4(rr[0], rr[1], rr[2], rr[3]));
+                SOCCER_SLIP_ST(f4 + g, __byte_perm(__byte_perm(ff[0], ff[1], 0x0040), __byte_perm(ff[2], ff[3], 0x0040), 0x5410));
+                if (RESET_OBS) SOCCER_SLIP_ST(q4 + g, make_uint4(ro[0], ro[1], ro[2], ro[3]));
             }
             cur = nxt; g = gn; valid = validn;
         }
