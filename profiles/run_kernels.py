@@ -110,7 +110,7 @@ if __name__ == "__main__":
     if args.what in ("k2_rules", "all"):
         k2("rules", 1 << 20, 64, args.iters)
     if args.what in ("k1_slip", "all"):
-        k1_slip(1 << 22, args.iters)
+        k1_slip(args.envs, args.iters)
     if args.what in ("k1_philox", "all"):
         k1_philox(args.envs, args.iters)
     if args.what in ("k1_packed", "all"):
