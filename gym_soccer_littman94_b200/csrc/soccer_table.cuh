@@ -567,7 +567,10 @@ k_build_slip_index(const PitchDev P, int32_t nS, const uint16_t* __restrict__ ta
 #else
 #define SOCCER_SLIP_ST(p, v) st_stream((p), (v))
 #endif
-constexpr int kSlipQueueWarp = 256;                         // per warp: all 2 x 32 x 4 envs of an iteration can be deferred
+#ifndef SOCCER_SLIP_CARRY
+#define SOCCER_SLIP_CARRY 1
+#endif
+constexpr int kSlipQueueWarp = 288;                         // per warp: all 2 x 32 x 4 envs of an iteration + < 32 carried over
 constexpr int kSlipQueueBytes = kSlipQueueWarp * (kTableThreads / 32);   // one byte per entry: every KB of shared memory saved is L1 for the walk's re-reads
 struct SlipFast { uint32_t fc, cacb, mv3, klut; };          // shared-window addresses
 struct SlipE { double e[9]; };                              // E_k, a kernel parameter: DSETP reads it from the constant bank
@@ -662,10 +665,13 @@ k_step_table_slip_q(const PitchDev P, const uint16_t* __restrict__ gtable, uint3
     // warp-level deferral: no CTA barrier, so the warps of the CTA drift apart and their loads overlap the others' walks
     uint32_t cnt = 0;                                        // warp-uniform: queued envs of this warp
     // the walk of up to 32 queued envs of the iteration at `wbase`, one per lane (exact: table_step_slip)
+    uint32_t carry = 0;                                      // warp-uniform: entries [0, carry) come from the previous iteration
+    int64_t wbase_prev = 0;
     auto walk = [&](int64_t wbase, uint32_t first, uint32_t count) {
         if (lane < count) {
-            const uint32_t id = wq[first + lane];
-            const int64_t env = (wbase + (int64_t)(id >> 7) * stride + ((id >> 2) & 31u)) * 4 + (id & 3u);
+            const uint32_t idx = first + lane, id = wq[idx];
+            const int64_t wb = idx < carry ? wbase_prev : wbase;
+            const int64_t env = (wb + (int64_t)(id >> 7) * stride + ((id >> 2) & 31u)) * 4 + (id & 3u);
             const uint32_t s = __ldcg(state + env), rg = rng[env];
             const double ud = F64 ? reinterpret_cast<const double*>(draw)[env]
                                   : u_from_rng32(reinterpret_cast<const uint32_t*>(draw)[env]);
@@ -749,12 +755,29 @@ k_step_table_slip_q(const PitchDev P, const uint16_t* __restrict__ gtable, uint3
             cur = nxt; g = gn; valid = validn;
         }
         __syncwarp();                                        // queue entries and the placeholder stores ordered before the walks
-        // Walk them right away, while the lines the fast pass has just written are still in L2.  (Carrying fewer
-        // than 32 queued envs over to the next iteration keeps the walk's lanes full -- 144 vs 134 G env-steps/s at
-        // 2^22 envs -- but the late 1- and 4-byte fix-ups then hit lines already evicted to HBM: 120 vs 148 G at 2^24.)
+#if SOCCER_SLIP_CARRY
+        // Walk FULL warps of queued envs; fewer than 32 left over wait ONE iteration for company (they sit at the front of
+        // the queue, so the next iteration's first pass takes them), unless this was the last iteration or they already
+        // waited.  With evict-normal loads and stores their lines are still in L2 when they are patched.
+        const int64_t wbase = base + (threadIdx.x & ~31u);
+        const bool last = base + 2 * stride >= n_groups;
+        uint32_t first = 0;
+        while (cnt - first >= 32u) { walk(wbase, first, 32u); first += 32u; }
+        uint32_t rem = cnt - first;
+        if (rem && (last || first < carry)) { walk(wbase, first, rem); first = cnt; rem = 0; }
+        __syncwarp();
+        if (rem) {                                           // compact the leftovers to the front
+            const uint8_t v = lane < rem ? wq[first + lane] : (uint8_t)0;
+            __syncwarp();
+            if (lane < rem) wq[lane] = v;
+        }
+        carry = rem; cnt = rem; wbase_prev = wbase;
+#else
+        // Walk them right away, while the lines the fast pass has just written are still in L2.
         for (uint32_t first = 0; first < cnt; first += 32u) walk(base + (threadIdx.x & ~31u), first, min(32u, cnt - first));
         cnt = 0;
-        __syncwarp();                                        // queue drained before the warp refills it
+#endif
+        __syncwarp();                                        // queue settled before the warp refills it
     }
 }
 
