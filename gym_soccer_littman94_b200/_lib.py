@@ -15,7 +15,7 @@ _DEFAULT_SO = os.path.join(_HERE, "libsoccer_b200.so")
 # SOCCER_B200_LIB points at an alternative build of the SAME sources (A/B kernel experiments)
 SO_PATH = os.environ.get("SOCCER_B200_LIB", _DEFAULT_SO)
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 EXPORTS = (
     "soccer_abi_version", "soccer_pitch_info_host", "soccer_pack_state_host", "soccer_unpack_state_host",
@@ -26,6 +26,7 @@ EXPORTS = (
     "soccer_step_host", "soccer_step_host_scratch_bytes_host", "soccer_step_many", "soccer_bench_stream_mix",
     "soccer_bench_rollout_probe", "soccer_rollout_table_policy", "soccer_step_table_slip",
     "soccer_bellman_q", "soccer_plan", "soccer_plan_workspace_bytes_host", "soccer_step_table_philox", "soccer_step_table_packed", "soccer_step_narrow", "soccer_host_alloc", "soccer_host_free", "soccer_slip_index_bytes_host", "soccer_build_slip_index",
+    "soccer_step_table_packed_philox",
 )
 
 
@@ -53,7 +54,8 @@ class StepArgs(C.Structure):
                 ("flags", C.c_void_p), ("reset_obs", C.c_void_p), ("n", C.c_int64),
                 ("auto_reset", C.c_int32), ("use_philox", C.c_int32), ("detail", C.c_int32),
                 ("narrow", C.c_int32), ("seed", C.c_uint64), ("step", C.c_uint64),
-                ("env_id_base", C.c_uint64)]
+                ("env_id_base", C.c_uint64), ("stats", C.c_void_p), ("table", C.c_void_p),
+                ("slip_index", C.c_void_p)]
 
 
 class StepHostArgs(C.Structure):
@@ -118,7 +120,7 @@ def lib():
         "soccer_step": [PP, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp],
         "soccer_step_philox": [PP, vp, vp, vp, u64, u64, u64, vp, vp, vp, vp, i64, vp],
         "soccer_step_ex": [PP, C.POINTER(StepArgs), vp],
-        "soccer_rollout": [PP, vp, vp, vp, u64, u64, i32, u64, vp, vp, vp, vp, i64, vp],
+        "soccer_rollout": [PP, vp, vp, vp, u64, u64, i32, u64, i32, vp, vp, vp, vp, i64, vp],
         "soccer_sweep": [PP, i32, vp, vp, vp, vp, vp, vp],
         "soccer_dense": [PP, vp, vp, vp, vp, vp],
         "soccer_step_table_bytes_host": [PP, C.POINTER(i64)],
@@ -130,7 +132,8 @@ def lib():
         "soccer_step_narrow": [PP, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp],
         "soccer_step_table_packed": [PP, vp, vp, vp, vp, vp, i64, vp],
         "soccer_rollout_table": [PP, vp, vp, u64, u64, i32, u64, vp, vp, vp, vp, i64, vp],
-        "soccer_rollout_table_policy": [PP, vp, vp, vp, vp, u64, u64, i32, u64, vp, vp, vp, vp, i64, vp],
+        "soccer_rollout_table_policy": [PP, vp, vp, vp, vp, vp, u64, u64, i32, u64, i32, vp, vp, vp, vp, i64, vp],
+        "soccer_step_table_packed_philox": [PP, vp, vp, vp, u64, u64, u64, vp, i64, vp],
         "soccer_step_table_slip": [PP, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp],
         "soccer_slip_index_bytes_host": [PP, C.POINTER(i64)],
         "soccer_build_slip_index": [PP, vp, vp, vp],

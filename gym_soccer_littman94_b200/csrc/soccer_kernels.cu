@@ -163,11 +163,18 @@ inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_
 
 template <bool RESET_OBS, bool NARROW = false>
 __device__ __forceinline__ void step_group(const PitchDev& P, const Isd4& I, const uint8_t* lut, const Group4& x,
-                                           int64_t g, uint4* st, uint4* obs, uint4* rew, uint32_t* flg, uint4* rob)
+                                           int64_t g, uint4* st, uint4* obs, uint4* rew, uint32_t* flg, uint4* rob,
+                                           bool want_stats, K1Stats& acc)
 {
     const uint32_t sv[4] = { x.s.x, x.s.y, x.s.z, x.s.w };
     Step4 o;
     step4_noslip<RESET_OBS>(P, I, lut, sv, x.a, x.b, x.r, o);     // byte-parallel over the 4 envs
+    if (want_stats) {
+        // timesteps live in byte 2 of the CELL-layout words
+        const uint32_t ti = (sv[0] & 0xFF0000u) + (sv[1] & 0xFF0000u) + (sv[2] & 0xFF0000u) + (sv[3] & 0xFF0000u);
+        const uint32_t to = (o.s[0] & 0xFF0000u) + (o.s[1] & 0xFF0000u) + (o.s[2] & 0xFF0000u) + (o.s[3] & 0xFF0000u);
+        acc.add4(o.flags4, o.rew_sum, ti, to);
+    }
     st_keep(st + g, make_uint4(o.s[0], o.s[1], o.s[2], o.s[3]));
     if (NARROW) {                                                 // uint16 obs, int8 reward (soccer_step_narrow)
         st_stream(reinterpret_cast<uint2*>(obs) + g, make_uint2(o.obs[0] | (o.obs[1] << 16), o.obs[2] | (o.obs[3] << 16)));
@@ -185,13 +192,17 @@ __global__ void __launch_bounds__(kThreads)
 k_step_fast(const PitchDev P, uint32_t* __restrict__ state, const uint8_t* __restrict__ act_a,
             const uint8_t* __restrict__ act_b, const uint8_t* __restrict__ rng, int32_t* __restrict__ obs,
             float* __restrict__ reward, uint8_t* __restrict__ flags, int32_t* __restrict__ reset_obs,
-            int64_t n_groups, const PhiloxKey key = PhiloxKey())
+            int64_t n_groups, const PhiloxKey key, unsigned long long* __restrict__ stats)
 {
     __shared__ __align__(16) uint8_t lut[kLutBytes];
+    __shared__ K1StatsBlk sblk;
     pdl_launch_dependents();
+    k1_stats_init(&sblk);
     build_cand_lut(lut, P);
     const Isd4 I = make_isd4(P);
     pdl_wait();                  // everything above overlaps the previous kernel's tail
+    const bool want_stats = stats != nullptr;
+    K1Stats acc = {};
 
     uint4* st4 = reinterpret_cast<uint4*>(state);
     const uint32_t* a4 = reinterpret_cast<const uint32_t*>(act_a);
@@ -211,9 +222,10 @@ k_step_fast(const PitchDev P, uint32_t* __restrict__ state, const uint8_t* __res
         Group4 x1 = x0;
         if (two) x1 = load_group(st4, a4, b4, PHILOX ? a4 : r4, g2);
         if (PHILOX) { x0.r = philox_rng8x4(key, g); if (two) x1.r = philox_rng8x4(key, g2); }
-        step_group<RESET_OBS, NARROW>(P, I, lut, x0, g, st4, o4, w4, f4, q4);
-        if (two) step_group<RESET_OBS, NARROW>(P, I, lut, x1, g2, st4, o4, w4, f4, q4);
+        step_group<RESET_OBS, NARROW>(P, I, lut, x0, g, st4, o4, w4, f4, q4, want_stats, acc);
+        if (two) step_group<RESET_OBS, NARROW>(P, I, lut, x1, g2, st4, o4, w4, f4, q4, want_stats, acc);
     }
+    if (want_stats) k1_stats_flush(acc, &sblk, stats, (unsigned long long)n_groups * 4ull);
 }
 
 // ------------------------------------------------------------------ K1 generic path
@@ -224,6 +236,7 @@ struct StepOpts {
     int32_t* obs; float* reward; uint8_t* flags; int32_t* reset_obs;
     int64_t n; int32_t auto_reset; int32_t use_philox; int32_t detail; uint64_t seed, step, env_id_base;
     int32_t narrow;      // obs points at uint16[n], reward at int8[n] (soccer_step_narrow)
+    unsigned long long* stats;
 };
 __device__ __forceinline__ void put_obs(const StepOpts& o, int64_t i, int32_t v)
 {
@@ -240,6 +253,9 @@ __global__ void __launch_bounds__(kThreads) k_step_generic(const PitchDev P, con
     __shared__ __align__(16) double prt[kPrtDoubles];
     if (P.slip) slip_build_prt(prt, P);
     const SlipCtx sc = { (uint32_t)__cvta_generic_to_shared(prt), P.slip ? slip_first_k(P) : 0u };
+    __shared__ K1StatsBlk sblk;
+    k1_stats_init(&sblk);
+    K1Stats acc = {};
     build_cand_lut(lut, P);                      // ends with __syncthreads(): prt visible as well
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < o.n; i += stride) {
@@ -253,8 +269,8 @@ __global__ void __launch_bounds__(kThreads) k_step_generic(const PitchDev P, con
             if (o.reset_obs) o.reset_obs[i] = terminal_in ? 0 : obs_index(P, a, b, p);
             continue;
         }
-        uint32_t rng = 0;
-        if (o.use_philox) rng = philox_rng8(philox_word(o.seed, o.env_id_base + (uint64_t)i, o.step));
+        uint32_t rng = 0, pw = 0;
+        if (o.use_philox) { pw = philox_word(o.seed, o.env_id_base + (uint64_t)i, o.step); rng = philox_rng8(pw); }
         else if (o.rng8) rng = o.rng8[i];
         const int32_t cur = terminal_in ? 0 : obs_index(P, a, b, p);
         // SIM:187-188: a folded player's action is its table policy at the current observation
@@ -273,7 +289,7 @@ __global__ void __launch_bounds__(kThreads) k_step_generic(const PitchDev P, con
             double u;
             if (o.rngf64) u = o.rngf64[i];
             else if (o.rng32) u = ((double)o.rng32[i] + 0.5) * (1.0 / 4294967296.0);
-            else u = philox_u53(o.seed, o.env_id_base + (uint64_t)i, o.step);   // philox mode with slip
+            else u = u_from_rng32(philox_r32(pw));       // philox mode with slip: the word's 32-bit step draw
             r = o.auto_reset ? step_slip<true>(P, lut, sc, s, aa, ab, u, (rng >> 2) & 3u, flip)
                              : step_slip<false>(P, lut, sc, s, aa, ab, u, (rng >> 2) & 3u, flip);
         } else {
@@ -285,7 +301,11 @@ __global__ void __launch_bounds__(kThreads) k_step_generic(const PitchDev P, con
         if (o.reward) put_reward(o, i, r.reward);
         if (o.flags) o.flags[i] = (uint8_t)(o.detail ? r.flags : (r.flags & 3u));
         if (o.reset_obs) o.reset_obs[i] = r.reset_obs;
+        // statistics by player A's reward sign (the streamed reward is flipped for a player_b env)
+        const int32_t ri = (r.reward > 0.0f) - (r.reward < 0.0f);
+        acc.add1(r.flags, flip ? -ri : ri, ((s >> 16) & 0xFFu) + 1u);
     }
+    if (o.stats) k1_stats_flush(acc, &sblk, o.stats);
 }
 
 // ------------------------------------------------------------------ K3 sweep
@@ -411,7 +431,7 @@ k_set_state(const PitchDev P, int32_t nS, uint32_t* __restrict__ state, const in
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const int32_t o = obs_in[i];
         int32_t t = timestep_in ? timestep_in[i] : 0;
-        t = t < 0 ? 0 : (t > 255 ? 255 : t);
+        t = t < 0 ? 0 : (t > kMaxT ? kMaxT : t);      // the byte-parallel kernels add 28 to t + 1 inside a byte
         if (o >= 1 && o < nS) state[i] = obs_to_packed(P, o) | ((uint32_t)t << 16);
         else state[i] = kNeedsReset | kGoalBit | ((uint32_t)t << 16);   // terminal / invalid: needs reset
     }
@@ -535,6 +555,7 @@ k_step_stats(const uint8_t* __restrict__ flags, const float* __restrict__ reward
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&stats[4], (unsigned long long)n);
 }
 
+constexpr int32_t kMaxRolloutK = 1 << 28;     // per-pass statistics are 32-bit: 4 envs x K flag counts
 int64_t round_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 // scratch layout of soccer_step_host: three input byte streams, flags, obs, reward, obs16, rew8
 struct HostScratch { uint8_t *a, *b, *r, *f; int32_t* obs; float* rew; uint16_t* obs16; int8_t* rew8; int64_t bytes; };
@@ -746,10 +767,16 @@ int soccer_get_obs(const soccer_pitch* pitch, const uint32_t* state, int32_t* ob
     return launch_status();
 }
 
+} // extern "C"
+namespace { int step_table_ex(const soccer_pitch* pitch, const soccer_step_args* a, soccer_stream_t stream); }
+extern "C" {
+
 int soccer_step_ex(const soccer_pitch* pitch, const soccer_step_args* a, soccer_stream_t stream)
 {
     if (!a || !a->state || a->n < 0) return SOCCER_EINVAL;
     if (a->policy_a && a->policy_b) return SOCCER_EPOLICY;                 // SIM:38
+    if (a->table) return step_table_ex(pitch, a, stream);                  // INDEX-layout states, shared-memory table kernels
+    if (a->slip_index) return SOCCER_EINVAL;
     if ((!a->policy_a && !a->act_a) || (!a->policy_b && !a->act_b)) return SOCCER_EINVAL;
     if (!a->use_philox && !a->rng8) return SOCCER_EINVAL;
     PitchDev P; const int rc = make_pitch_dev(pitch, &P); if (rc) return rc;
@@ -764,6 +791,7 @@ int soccer_step_ex(const soccer_pitch* pitch, const soccer_step_args* a, soccer_
                          aligned(a->state, 16) && aligned(a->obs, narrow ? 8 : 16) && aligned(a->reward, narrow ? 4 : 16) &&
                          (!a->reset_obs || aligned(a->reset_obs, 16)) && aligned(a->act_a, 4) &&
                          aligned(a->act_b, 4) && (a->use_philox || aligned(a->rng8, 4)) && aligned(a->flags, 4) &&
+                         !(a->use_philox && (a->env_id_base & 3u)) &&      // Philox contract v2: a thread's 4 envs = one aligned group
                          !(narrow && (a->use_philox || a->reset_obs));     // narrow fast path: the plain step only
     int64_t done_n = 0;
     if (fast_ok) {
@@ -775,7 +803,7 @@ int soccer_step_ex(const soccer_pitch* pitch, const soccer_step_args* a, soccer_
             static const int nb = resident_blocks(k_step_fast<RO, PH, NR>);                                       \
             const int e1 = launch_pdl(k_step_fast<RO, PH, NR>, grid_for(n_groups, nb), kThreads, 0, st, P, a->state, \
                                       a->act_a, a->act_b, PH ? (const uint8_t*)nullptr : a->rng8, a->obs, a->reward, \
-                                      a->flags, RO ? a->reset_obs : (int32_t*)nullptr, n_groups, key);            \
+                                      a->flags, RO ? a->reset_obs : (int32_t*)nullptr, n_groups, key, a->stats);  \
             if (e1) return e1;                                                                                    \
         } while (0)
         if (narrow) SOCCER_LAUNCH_FAST(false, false, true);
@@ -804,6 +832,7 @@ int soccer_step_ex(const soccer_pitch* pitch, const soccer_step_args* a, soccer_
     o.n = a->n - k; o.auto_reset = a->auto_reset; o.use_philox = a->use_philox; o.detail = a->detail;
     o.seed = a->seed; o.step = a->step; o.env_id_base = a->env_id_base + (uint64_t)k;
     o.narrow = a->narrow;
+    o.stats = a->stats;
     return launch_generic(P, o, st);
 }
 
@@ -832,16 +861,17 @@ int soccer_step_philox(const soccer_pitch* pitch, uint32_t* state, const uint8_t
 }
 
 int soccer_rollout(const soccer_pitch* pitch, uint32_t* state, const int8_t* policy_a, const int8_t* policy_b,
-                   uint64_t seed, uint64_t step0, int32_t K, uint64_t env_id_base, int32_t* obs, float* reward,
-                   uint8_t* flags, unsigned long long* stats, int64_t n, soccer_stream_t stream)
+                   uint64_t seed, uint64_t step0, int32_t K, uint64_t env_id_base, int32_t flip_reward, int32_t* obs,
+                   float* reward, uint8_t* flags, unsigned long long* stats, int64_t n, soccer_stream_t stream)
 {
-    if (!state || n < 0 || K < 0) return SOCCER_EINVAL;
+    if (!state || n < 0 || K < 0 || K > kMaxRolloutK) return SOCCER_EINVAL;
     PitchDev P; const int rc = make_pitch_dev(pitch, &P); if (rc) return rc;
     if (n == 0 || K == 0) return SOCCER_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    const bool vec = (n % 4 == 0) && aligned(state, 16) && (!obs || aligned(obs, 16)) &&
+    // Philox contract v2: the 4 envs of a thread must be one aligned group of the GLOBAL env ids
+    const bool vec = (n % 4 == 0) && (env_id_base % 4 == 0) && aligned(state, 16) && (!obs || aligned(obs, 16)) &&
                      (!reward || aligned(reward, 16)) && (!flags || aligned(flags, 4));
-    const RolloutArgs ra = { state, seed, step0, K, env_id_base, obs, reward, flags, stats, n };
+    const RolloutArgs ra = { state, seed, step0, K, env_id_base, obs, reward, flags, stats, n, flip_reward ? 1 : 0 };
     const bool streams = obs && reward && flags;
 #define SOCCER_LAUNCH_ROLLOUT(VEC, STR, SLIP, ITEMS)                                                    \
     do {                                                                                                 \
@@ -899,39 +929,127 @@ int soccer_build_step_table(const soccer_pitch* pitch, uint16_t* table, soccer_s
 } // extern "C"
 namespace {
 using namespace soccer;
-// soccer_step_table / soccer_step_table_philox: the draws come from the rng8 stream or, when it is NULL, from Philox
-int step_table_impl(const soccer_pitch* pitch, const uint16_t* table, uint32_t* state, const uint8_t* act_a,
-                    const uint8_t* act_b, const uint8_t* rng8, const PhiloxKey key, int32_t* obs, float* reward,
-                    uint8_t* flags, int32_t* reset_obs, int64_t n, soccer_stream_t stream, bool narrow = false)
+
+// slip_prob > 0 through the table (k_step_table_slip_q / k_step_table_slip / scalar tail); draws from rng32 / rngf64 or,
+// when both are NULL, from Philox
+int step_table_slip_impl(const PitchDev& P, int64_t bytes, const soccer_step_args* a, cudaStream_t st)
 {
-    const bool philox = rng8 == nullptr;
-    if (narrow && (philox || reset_obs)) return SOCCER_EINVAL;
-    if (!table || !state || !act_a || !act_b || !obs || !reward || !flags || n < 0) return SOCCER_EINVAL;
-    if (pitch && pitch->slip_prob != 0.0) return SOCCER_ESLIP;          // soccer_step_table_slip takes the step draw
-    PitchDev P; int rc = make_pitch_dev(pitch, &P); if (rc) return rc;
-    int64_t bytes; rc = table_bytes_of(P, &bytes); if (rc) return rc;
-    if (!aligned(table, 16)) return SOCCER_EINVAL;
-    if (n == 0) return SOCCER_OK;
-    cudaStream_t st = (cudaStream_t)stream;
-    const bool vec = n >= 4 && aligned(state, 16) && aligned(obs, narrow ? 8 : 16) && aligned(reward, narrow ? 4 : 16) &&
-                     (!reset_obs || aligned(reset_obs, 16)) && aligned(act_a, 4) && aligned(act_b, 4) &&
-                     (philox || aligned(rng8, 4)) && aligned(flags, 4);
+    const bool philox = a->use_philox != 0;
+    const int64_t n = a->n;
+    const uint8_t* act_a = a->act_a; const uint8_t* act_b = a->act_b;
+    const void* draw = a->rngf64 ? (const void*)a->rngf64 : (const void*)a->rng32;
+    const SlipExtra ex = { a->policy_a, a->policy_b, { a->seed, a->step, a->env_id_base } };
+    const bool vec = n >= 4 && aligned(a->state, 16) && aligned(a->obs, 16) && aligned(a->reward, 16) &&
+                     (!a->reset_obs || aligned(a->reset_obs, 16)) && (!act_a || aligned(act_a, 4)) &&
+                     (!act_b || aligned(act_b, 4)) && aligned(a->flags, 4) &&
+                     (philox ? (a->env_id_base & 3u) == 0 : (aligned(a->rng8, 4) && aligned(draw, 16)));
+    const int64_t pol_bytes = (a->policy_a || a->policy_b) ? 2 * (((int64_t)P.nS + 15) & ~15) : 0;
     int64_t done_n = 0;
     if (vec) {
         const int64_t n_groups = n / 4;
-#define SOCCER_LAUNCH_STEP_T(RO, PH, NR)                                                                            \
+        // with a slip index, and room for it and the deferral queue next to the table (5x4): constant-prefix fast
+        // path + queued walk; else the in-place walk
+        const int64_t fc_bytes = ((int64_t)P.nS * 25 + 15) / 16 * 16;
+        const int64_t smem_q = bytes + 16 + fc_bytes + pol_bytes + (int64_t)kSlipQueueBytes;
+        const int64_t smem_w = bytes + 16 + pol_bytes;
+        if (smem_w > 227 * 1024 - 2048) return SOCCER_ETABLE;
+        SlipE E;                                      // E_k: sequential fp64 sums of the combination probabilities (SIM:241, nsp = 1)
+        { double acc = 0.0; for (int c = 0; c < 9; ++c) { acc += P.mp[c]; E.e[c] = acc; } }
+        const bool queued = a->slip_index && smem_q <= 227 * 1024 - 1024 - (a->rngf64 ? 0 : 4096);
+#define SOCCER_LAUNCH_SLIP_T(RO, DRAW)                                                                    \
+        do {                                                                                              \
+            if (queued) {                                                                                 \
+                const int e0 = allow_big_smem(k_step_table_slip_q<RO, DRAW>, smem_q);                     \
+                if (e0) return e0;                                                                        \
+                k_step_table_slip_q<RO, DRAW><<<table_grid(n_groups, kTableThreads), kTableThreads, (size_t)smem_q, st>>>(  \
+                    P, a->table, (uint32_t)bytes, a->slip_index, (uint32_t)fc_bytes, E, a->state, act_a, act_b, a->rng8, \
+                    draw, a->obs, a->reward, a->flags, a->reset_obs, n_groups, ex);                       \
+            } else {                                                                                      \
+                const int e0 = allow_big_smem(k_step_table_slip<RO, DRAW>, smem_w);                       \
+                if (e0) return e0;                                                                        \
+                k_step_table_slip<RO, DRAW><<<table_grid(n_groups, kSlipThreads), kSlipThreads, (size_t)smem_w, st>>>(  \
+                    P, a->table, (uint32_t)bytes, a->state, act_a, act_b, a->rng8, draw, a->obs, a->reward, a->flags, \
+                    a->reset_obs, n_groups, ex);                                                          \
+            }                                                                                             \
+        } while (0)
+#define SOCCER_PICK_SLIP_T(RO)                                                                            \
+        do {                                                                                              \
+            if (philox) SOCCER_LAUNCH_SLIP_T(RO, kDrawPhilox);                                            \
+            else if (a->rngf64) SOCCER_LAUNCH_SLIP_T(RO, kDrawF64);                                       \
+            else SOCCER_LAUNCH_SLIP_T(RO, kDrawU32);                                                      \
+        } while (0)
+        if (a->reset_obs) SOCCER_PICK_SLIP_T(true); else SOCCER_PICK_SLIP_T(false);
+#undef SOCCER_PICK_SLIP_T
+#undef SOCCER_LAUNCH_SLIP_T
+        const int e = launch_status();
+        if (e) return e;
+        done_n = n_groups * 4;
+        if (done_n == n) return SOCCER_OK;
+    }
+    const int64_t k = done_n, m = n - k;
+    const SlipExtra exk = { a->policy_a, a->policy_b, { a->seed, a->step, a->env_id_base + (uint64_t)k } };
+    k_step_table_slip_scalar<<<grid_for(m, 8), kThreads, 0, st>>>(
+        P, a->table, a->state + k, act_a ? act_a + k : nullptr, act_b ? act_b + k : nullptr, philox ? nullptr : a->rng8 + k,
+        (philox || a->rngf64) ? nullptr : a->rng32 + k, (!philox && a->rngf64) ? a->rngf64 + k : nullptr, a->obs + k,
+        a->reward + k, a->flags + k, a->reset_obs ? a->reset_obs + k : nullptr, m, philox ? 1 : 0, exk);
+    return launch_status();
+}
+
+// Every option the shared-memory-table step offers (soccer_step_ex with args->table != NULL): injected or Philox
+// draws, folded table policies (single-agent modes), slip_prob > 0, narrow streams, fused statistics.
+int step_table_ex(const soccer_pitch* pitch, const soccer_step_args* a, soccer_stream_t stream)
+{
+    const bool philox = a->use_philox != 0;
+    const bool narrow = a->narrow == 1;
+    if (a->narrow != 0 && a->narrow != 1) return SOCCER_EINVAL;
+    if (!a->auto_reset || a->detail) return SOCCER_EINVAL;     // INDEX-layout states cannot hold needs_reset / detail flags
+    if (!a->obs || !a->reward || !a->flags) return SOCCER_EINVAL;
+    if ((!a->policy_a && !a->act_a) || (!a->policy_b && !a->act_b)) return SOCCER_EINVAL;
+    if (!philox && !a->rng8) return SOCCER_EINVAL;
+    const bool pol = a->policy_a || a->policy_b;
+    if (narrow && (philox || a->reset_obs || pol)) return SOCCER_EINVAL;
+    PitchDev P; int rc = make_pitch_dev(pitch, &P); if (rc) return rc;
+    int64_t bytes; rc = table_bytes_of(P, &bytes); if (rc) return rc;
+    if (!aligned(a->table, 16) || (a->slip_index && !aligned(a->slip_index, 16))) return SOCCER_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (P.slip) {
+        if (!philox && !a->rng32 && !a->rngf64) return SOCCER_ESLIP;
+        if (narrow || a->stats) return SOCCER_EINVAL;          // not offered by the slip kernels
+        if (a->n == 0) return SOCCER_OK;
+        return step_table_slip_impl(P, bytes, a, st);
+    }
+    if (a->n == 0) return SOCCER_OK;
+    const int64_t n = a->n;
+    const PhiloxKey key = { a->seed, a->step, a->env_id_base };
+    const K1Extra ex = { a->policy_a, a->policy_b, a->stats };
+    const int64_t smem = bytes + 16 + (pol ? 2 * (((int64_t)P.nS + 15) & ~15) : 0);
+    if (smem > 227 * 1024 - 1024) return SOCCER_ETABLE;
+    const bool vec = n >= 4 && aligned(a->state, 16) && aligned(a->obs, narrow ? 8 : 16) && aligned(a->reward, narrow ? 4 : 16) &&
+                     (!a->reset_obs || aligned(a->reset_obs, 16)) && (!a->act_a || aligned(a->act_a, 4)) &&
+                     (!a->act_b || aligned(a->act_b, 4)) && (philox ? (a->env_id_base & 3u) == 0 : aligned(a->rng8, 4)) &&
+                     aligned(a->flags, 4);
+    int64_t done_n = 0;
+    if (vec) {
+        const int64_t n_groups = n / 4;
+#define SOCCER_LAUNCH_STEP_T4(RO, PH, NR, PL, ST)                                                                 \
         do {                                                                                                      \
-            const int e0 = allow_big_smem(k_step_table<RO, PH, NR>, bytes + 16);                                  \
+            const int e0 = allow_big_smem(k_step_table<RO, PH, NR, PL, ST>, smem);                                \
             if (e0) return e0;                                                                                    \
-            const int e1 = launch_pdl(k_step_table<RO, PH, NR>, table_grid(n_groups), kTableThreads, (size_t)bytes + 16, st, \
-                                      P, table, (uint32_t)bytes, state, act_a, act_b, rng8, obs, reward, flags,   \
-                                      RO ? reset_obs : (int32_t*)nullptr, n_groups, key);                         \
+            const int e1 = launch_pdl(k_step_table<RO, PH, NR, PL, ST>, table_grid(n_groups), kTableThreads, (size_t)smem, st, \
+                                      P, a->table, (uint32_t)bytes, a->state, a->act_a, a->act_b, a->rng8, a->obs, a->reward, \
+                                      a->flags, RO ? a->reset_obs : (int32_t*)nullptr, n_groups, key, ex);        \
             if (e1) return e1;                                                                                    \
         } while (0)
-        if (narrow) SOCCER_LAUNCH_STEP_T(false, false, true);
-        else if (reset_obs) { if (philox) SOCCER_LAUNCH_STEP_T(true, true, false); else SOCCER_LAUNCH_STEP_T(true, false, false); }
-        else { if (philox) SOCCER_LAUNCH_STEP_T(false, true, false); else SOCCER_LAUNCH_STEP_T(false, false, false); }
+#define SOCCER_LAUNCH_STEP_T(RO, PH, NR, PL)                                                                      \
+        do { if (a->stats) SOCCER_LAUNCH_STEP_T4(RO, PH, NR, PL, true); else SOCCER_LAUNCH_STEP_T4(RO, PH, NR, PL, false); } while (0)
+#define SOCCER_PICK_STEP_T(RO, PH)                                                                                \
+        do { if (pol) SOCCER_LAUNCH_STEP_T(RO, PH, false, true); else SOCCER_LAUNCH_STEP_T(RO, PH, false, false); } while (0)
+        if (narrow) SOCCER_LAUNCH_STEP_T(false, false, true, false);
+        else if (a->reset_obs) { if (philox) SOCCER_PICK_STEP_T(true, true); else SOCCER_PICK_STEP_T(true, false); }
+        else { if (philox) SOCCER_PICK_STEP_T(false, true); else SOCCER_PICK_STEP_T(false, false); }
+#undef SOCCER_PICK_STEP_T
 #undef SOCCER_LAUNCH_STEP_T
+#undef SOCCER_LAUNCH_STEP_T4
         const int e = launch_status();
         if (e) return e;
         done_n = n_groups * 4;
@@ -939,12 +1057,53 @@ int step_table_impl(const soccer_pitch* pitch, const uint16_t* table, uint32_t* 
     }
     const int64_t k = done_n, m = n - k;
     const PhiloxKey tail_key = { key.seed, key.step, key.env_id_base + (uint64_t)k };
-    int32_t* obs_k = narrow ? reinterpret_cast<int32_t*>(reinterpret_cast<uint16_t*>(obs) + k) : obs + k;
-    float* rew_k = narrow ? reinterpret_cast<float*>(reinterpret_cast<int8_t*>(reward) + k) : reward + k;
-    k_step_table_scalar<<<grid_for(m, 8), kThreads, 0, st>>>(P, table, state + k, act_a + k, act_b + k,
-                                                             philox ? nullptr : rng8 + k, obs_k, rew_k, flags + k,
-                                                             reset_obs ? reset_obs + k : nullptr, m, philox ? 1 : 0, tail_key,
-                                                             narrow ? 1 : 0);
+    int32_t* obs_k = narrow ? reinterpret_cast<int32_t*>(reinterpret_cast<uint16_t*>(a->obs) + k) : a->obs + k;
+    float* rew_k = narrow ? reinterpret_cast<float*>(reinterpret_cast<int8_t*>(a->reward) + k) : a->reward + k;
+    k_step_table_scalar<<<grid_for(m, 8), kThreads, 0, st>>>(P, a->table, a->state + k, a->act_a ? a->act_a + k : nullptr,
+                                                             a->act_b ? a->act_b + k : nullptr,
+                                                             philox ? nullptr : a->rng8 + k, obs_k, rew_k, a->flags + k,
+                                                             a->reset_obs ? a->reset_obs + k : nullptr, m, philox ? 1 : 0, tail_key,
+                                                             narrow ? 1 : 0, ex);
+    return launch_status();
+}
+
+int packed_impl(const soccer_pitch* pitch, const uint16_t* table, uint32_t* state, const uint8_t* joint,
+                const uint8_t* rng8, const PhiloxKey key, uint16_t* result, int64_t n, soccer_stream_t stream)
+{
+    const bool philox = rng8 == nullptr;
+    if (!table || !state || !joint || !result || n < 0) return SOCCER_EINVAL;
+    if (pitch && pitch->slip_prob != 0.0) return SOCCER_ESLIP;
+    PitchDev P; int rc = make_pitch_dev(pitch, &P); if (rc) return rc;
+    int64_t bytes; rc = table_bytes_of(P, &bytes); if (rc) return rc;
+    if (!aligned(table, 16)) return SOCCER_EINVAL;
+    if (n == 0) return SOCCER_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t done_n = 0;
+    if (n >= 4 && aligned(state, 16) && aligned(joint, 4) && aligned(result, 8) &&
+        (philox ? (key.env_id_base & 3u) == 0 : aligned(rng8, 4))) {
+        const int64_t n_groups = n / 4;
+        if (philox) {
+            const int e0 = allow_big_smem(k_step_table_packed<true>, bytes + 16);
+            if (e0) return e0;
+            const int e1 = launch_pdl(k_step_table_packed<true>, table_grid(n_groups), kTableThreads, (size_t)bytes + 16, st,
+                                      P, table, (uint32_t)bytes, state, joint, rng8, result, n_groups, key);
+            if (e1) return e1;
+        } else {
+            const int e0 = allow_big_smem(k_step_table_packed<false>, bytes + 16);
+            if (e0) return e0;
+            const int e1 = launch_pdl(k_step_table_packed<false>, table_grid(n_groups), kTableThreads, (size_t)bytes + 16, st,
+                                      P, table, (uint32_t)bytes, state, joint, rng8, result, n_groups, key);
+            if (e1) return e1;
+        }
+        const int e = launch_status();
+        if (e) return e;
+        done_n = n_groups * 4;
+        if (done_n == n) return SOCCER_OK;
+    }
+    const int64_t k = done_n, m = n - k;
+    const PhiloxKey tail_key = { key.seed, key.step, key.env_id_base + (uint64_t)k };
+    k_step_table_packed_scalar<<<grid_for(m, 8), kThreads, 0, st>>>(P, table, state + k, joint + k, philox ? nullptr : rng8 + k,
+                                                                    result + k, m, philox ? 1 : 0, tail_key);
     return launch_status();
 }
 } // namespace
@@ -954,29 +1113,35 @@ int soccer_step_table(const soccer_pitch* pitch, const uint16_t* table, uint32_t
                       const uint8_t* act_b, const uint8_t* rng8, int32_t* obs, float* reward, uint8_t* flags,
                       int32_t* reset_obs, int64_t n, soccer_stream_t stream)
 {
-    if (!rng8) return SOCCER_EINVAL;
-    return step_table_impl(pitch, table, state, act_a, act_b, rng8, PhiloxKey(), obs, reward, flags, reset_obs, n, stream);
+    if (!table || !state || !rng8 || n < 0) return SOCCER_EINVAL;
+    if (pitch && pitch->slip_prob != 0.0) return SOCCER_ESLIP;          // soccer_step_table_slip takes the step draw
+    soccer_step_args a = {};
+    a.table = table; a.state = state; a.act_a = act_a; a.act_b = act_b; a.rng8 = rng8; a.obs = obs; a.reward = reward;
+    a.flags = flags; a.reset_obs = reset_obs; a.n = n; a.auto_reset = 1;
+    return step_table_ex(pitch, &a, stream);
 }
 
 int soccer_step_table_philox(const soccer_pitch* pitch, const uint16_t* table, uint32_t* state, const uint8_t* act_a,
                              const uint8_t* act_b, uint64_t seed, uint64_t step, uint64_t env_id_base, int32_t* obs,
                              float* reward, uint8_t* flags, int32_t* reset_obs, int64_t n, soccer_stream_t stream)
 {
-    const PhiloxKey key = { seed, step, env_id_base };
-    return step_table_impl(pitch, table, state, act_a, act_b, nullptr, key, obs, reward, flags, reset_obs, n, stream);
+    if (!table || !state || n < 0) return SOCCER_EINVAL;
+    if (pitch && pitch->slip_prob != 0.0) return SOCCER_ESLIP;
+    soccer_step_args a = {};
+    a.table = table; a.state = state; a.act_a = act_a; a.act_b = act_b; a.obs = obs; a.reward = reward;
+    a.flags = flags; a.reset_obs = reset_obs; a.n = n; a.auto_reset = 1; a.use_philox = 1;
+    a.seed = seed; a.step = step; a.env_id_base = env_id_base;
+    return step_table_ex(pitch, &a, stream);
 }
 
 int soccer_step_narrow(const soccer_pitch* pitch, const uint16_t* table, uint32_t* state, const uint8_t* act_a,
                        const uint8_t* act_b, const uint8_t* rng8, uint16_t* obs16, int8_t* reward8, uint8_t* flags,
                        int64_t n, soccer_stream_t stream)
 {
-    if (!obs16 || !reward8 || !flags || !rng8) return SOCCER_EINVAL;
+    if (!state || !obs16 || !reward8 || !flags || !rng8 || n < 0) return SOCCER_EINVAL;
     if (pitch && pitch->slip_prob != 0.0) return SOCCER_ESLIP;
-    if (table)
-        return step_table_impl(pitch, table, state, act_a, act_b, rng8, PhiloxKey(), reinterpret_cast<int32_t*>(obs16),
-                               reinterpret_cast<float*>(reward8), flags, nullptr, n, stream, true);
     soccer_step_args a = {};
-    a.state = state; a.act_a = act_a; a.act_b = act_b; a.rng8 = rng8; a.obs = reinterpret_cast<int32_t*>(obs16);
+    a.table = table; a.state = state; a.act_a = act_a; a.act_b = act_b; a.rng8 = rng8; a.obs = reinterpret_cast<int32_t*>(obs16);
     a.reward = reinterpret_cast<float*>(reward8); a.flags = flags; a.n = n; a.auto_reset = 1; a.narrow = 1;
     return soccer_step_ex(pitch, &a, stream);
 }
@@ -984,29 +1149,16 @@ int soccer_step_narrow(const soccer_pitch* pitch, const uint16_t* table, uint32_
 int soccer_step_table_packed(const soccer_pitch* pitch, const uint16_t* table, uint32_t* state, const uint8_t* joint,
                              const uint8_t* rng8, uint16_t* result, int64_t n, soccer_stream_t stream)
 {
-    if (!table || !state || !joint || !rng8 || !result || n < 0) return SOCCER_EINVAL;
-    if (pitch && pitch->slip_prob != 0.0) return SOCCER_ESLIP;
-    PitchDev P; int rc = make_pitch_dev(pitch, &P); if (rc) return rc;
-    int64_t bytes; rc = table_bytes_of(P, &bytes); if (rc) return rc;
-    if (!aligned(table, 16)) return SOCCER_EINVAL;
-    if (n == 0) return SOCCER_OK;
-    cudaStream_t st = (cudaStream_t)stream;
-    int64_t done_n = 0;
-    if (n >= 4 && aligned(state, 16) && aligned(joint, 4) && aligned(rng8, 4) && aligned(result, 8)) {
-        const int64_t n_groups = n / 4;
-        const int e0 = allow_big_smem(k_step_table_packed, bytes + 16);
-        if (e0) return e0;
-        const int e1 = launch_pdl(k_step_table_packed, table_grid(n_groups), kTableThreads, (size_t)bytes + 16, st,
-                                  P, table, (uint32_t)bytes, state, joint, rng8, result, n_groups);
-        if (e1) return e1;
-        const int e = launch_status();
-        if (e) return e;
-        done_n = n_groups * 4;
-        if (done_n == n) return SOCCER_OK;
-    }
-    const int64_t k = done_n, m = n - k;
-    k_step_table_packed_scalar<<<grid_for(m, 8), kThreads, 0, st>>>(P, table, state + k, joint + k, rng8 + k, result + k, m);
-    return launch_status();
+    if (!rng8) return SOCCER_EINVAL;
+    return packed_impl(pitch, table, state, joint, rng8, PhiloxKey(), result, n, stream);
+}
+
+int soccer_step_table_packed_philox(const soccer_pitch* pitch, const uint16_t* table, uint32_t* state, const uint8_t* joint,
+                                    uint64_t seed, uint64_t step, uint64_t env_id_base, uint16_t* result, int64_t n,
+                                    soccer_stream_t stream)
+{
+    const PhiloxKey key = { seed, step, env_id_base };
+    return packed_impl(pitch, table, state, joint, nullptr, key, result, n, stream);
 }
 
 int soccer_slip_index_bytes_host(const soccer_pitch* pitch, int64_t* bytes)
@@ -1034,72 +1186,37 @@ int soccer_step_table_slip(const soccer_pitch* pitch, const uint16_t* table, con
 {
     if (!table || !state || !act_a || !act_b || !rng8 || !obs || !reward || !flags || n < 0) return SOCCER_EINVAL;
     if (!rng32 && !rngf64) return SOCCER_EINVAL;
+    soccer_step_args a = {};
+    a.table = table; a.slip_index = slip_index; a.state = state; a.act_a = act_a; a.act_b = act_b; a.rng8 = rng8;
+    a.rng32 = rngf64 ? nullptr : rng32; a.rngf64 = rngf64; a.obs = obs; a.reward = reward; a.flags = flags;
+    a.reset_obs = reset_obs; a.n = n; a.auto_reset = 1;
     PitchDev P; int rc = make_pitch_dev(pitch, &P); if (rc) return rc;
     int64_t bytes; rc = table_bytes_of(P, &bytes); if (rc) return rc;
     if (!aligned(table, 16) || (slip_index && !aligned(slip_index, 16))) return SOCCER_EINVAL;
     if (n == 0) return SOCCER_OK;
-    cudaStream_t st = (cudaStream_t)stream;
-    const void* draw = rngf64 ? (const void*)rngf64 : (const void*)rng32;
-    const bool vec = n >= 4 && aligned(state, 16) && aligned(obs, 16) && aligned(reward, 16) &&
-                     (!reset_obs || aligned(reset_obs, 16)) && aligned(act_a, 4) && aligned(act_b, 4) &&
-                     aligned(rng8, 4) && aligned(flags, 4) && aligned(draw, 16);
-    int64_t done_n = 0;
-    if (vec) {
-        const int64_t n_groups = n / 4;
-        // with a slip index, and room for it and the deferral queue next to the table (5x4): constant-prefix fast
-        // path + queued walk; else the in-place walk
-        const int64_t fc_bytes = ((int64_t)P.nS * 25 + 15) / 16 * 16;
-        const int64_t smem_q = bytes + 16 + fc_bytes + (int64_t)kSlipQueueBytes;
-        SlipE E;                                      // E_k: sequential fp64 sums of the combination probabilities (SIM:241, nsp = 1)
-        { double acc = 0.0; for (int c = 0; c < 9; ++c) { acc += P.mp[c]; E.e[c] = acc; } }
-        const bool queued = slip_index && smem_q <= 227 * 1024 - 1024;
-#define SOCCER_LAUNCH_SLIP_T(RO, F64)                                                                     \
-        do {                                                                                              \
-            if (queued) {                                                                                 \
-                const int e0 = allow_big_smem(k_step_table_slip_q<RO, F64>, smem_q);                      \
-                if (e0) return e0;                                                                        \
-                k_step_table_slip_q<RO, F64><<<table_grid(n_groups, kTableThreads), kTableThreads, (size_t)smem_q, st>>>(  \
-                    P, table, (uint32_t)bytes, slip_index, (uint32_t)fc_bytes, E, state, act_a, act_b, rng8, draw, obs, reward, \
-                    flags, reset_obs, n_groups);                                                          \
-            } else {                                                                                      \
-                const int e0 = allow_big_smem(k_step_table_slip<RO, F64>, bytes + 16);                    \
-                if (e0) return e0;                                                                        \
-                k_step_table_slip<RO, F64><<<table_grid(n_groups, kSlipThreads), kSlipThreads, (size_t)bytes + 16, st>>>(  \
-                    P, table, (uint32_t)bytes, state, act_a, act_b, rng8, draw, obs, reward, flags, reset_obs, n_groups); \
-            }                                                                                             \
-        } while (0)
-        if (reset_obs) { if (rngf64) SOCCER_LAUNCH_SLIP_T(true, true); else SOCCER_LAUNCH_SLIP_T(true, false); }
-        else { if (rngf64) SOCCER_LAUNCH_SLIP_T(false, true); else SOCCER_LAUNCH_SLIP_T(false, false); }
-#undef SOCCER_LAUNCH_SLIP_T
-        const int e = launch_status();
-        if (e) return e;
-        done_n = n_groups * 4;
-        if (done_n == n) return SOCCER_OK;
-    }
-    const int64_t k = done_n, m = n - k;
-    k_step_table_slip_scalar<<<grid_for(m, 8), kThreads, 0, st>>>(
-        P, table, state + k, act_a + k, act_b + k, rng8 + k, rngf64 ? nullptr : rng32 + k, rngf64 ? rngf64 + k : nullptr,
-        obs + k, reward + k, flags + k, reset_obs ? reset_obs + k : nullptr, m);
-    return launch_status();
+    return step_table_slip_impl(P, bytes, &a, (cudaStream_t)stream);
 }
 
-int soccer_rollout_table_policy(const soccer_pitch* pitch, const uint16_t* table, uint32_t* state,
+int soccer_rollout_table_policy(const soccer_pitch* pitch, const uint16_t* table, const uint8_t* slip_index, uint32_t* state,
                                 const int8_t* policy_a, const int8_t* policy_b, uint64_t seed, uint64_t step0, int32_t K,
-                                uint64_t env_id_base, int32_t* obs, float* reward, uint8_t* flags,
+                                uint64_t env_id_base, int32_t flip_reward, int32_t* obs, float* reward, uint8_t* flags,
                                 unsigned long long* stats, int64_t n, soccer_stream_t stream)
 {
-    if (!table || !state || n < 0 || K < 0) return SOCCER_EINVAL;
+    if (!table || !state || n < 0 || K < 0 || K > kMaxRolloutK) return SOCCER_EINVAL;
     PitchDev P; int rc = make_pitch_dev(pitch, &P); if (rc) return rc;
     int64_t bytes; rc = table_bytes_of(P, &bytes); if (rc) return rc;
-    if (!aligned(table, 16)) return SOCCER_EINVAL;
+    if (!aligned(table, 16) || (slip_index && !aligned(slip_index, 16))) return SOCCER_EINVAL;
     if (n == 0 || K == 0) return SOCCER_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    const bool vec = (n % 4 == 0) && aligned(state, 16) && (!obs || aligned(obs, 16)) &&
+    // Philox contract v2: the 4 envs of a thread must be one aligned group of the GLOBAL env ids
+    const bool vec = (n % 4 == 0) && (env_id_base % 4 == 0) && aligned(state, 16) && (!obs || aligned(obs, 16)) &&
                      (!reward || aligned(reward, 16)) && (!flags || aligned(flags, 4));
-    const RolloutArgs ra = { state, seed, step0, K, env_id_base, obs, reward, flags, stats, n };
+    const RolloutArgs ra = { state, seed, step0, K, env_id_base, obs, reward, flags, stats, n, flip_reward ? 1 : 0 };
     const bool streams = obs && reward && flags;
     const bool pol = policy_a || policy_b;
-    const int64_t smem = bytes + 16 + ((pol || P.slip) ? 2 * ((P.nS + 15) & ~15) : 0);
+    const int64_t pol_bytes = 2 * (((int64_t)P.nS + 15) & ~15);
+    const int64_t smem = bytes + 16 + ((pol || P.slip) ? pol_bytes : 0);
+    if (smem > 227 * 1024 - 1024) return SOCCER_ETABLE;
 #define SOCCER_LAUNCH_ROLLOUT_T(VEC, STR, POL, SLIP, ITEMS)                                              \
     do {                                                                                                 \
         const int e0 = allow_big_smem(k_rollout_table<VEC, STR, POL, SLIP>, smem);                       \
@@ -1115,9 +1232,28 @@ int soccer_rollout_table_policy(const soccer_pitch* pitch, const uint16_t* table
         else if (streams) SOCCER_LAUNCH_ROLLOUT_T(1, true, POL, SLIP, n);                                \
         else SOCCER_LAUNCH_ROLLOUT_T(1, false, POL, SLIP, n);                                            \
     } while (0)
-    if (P.slip) {                                        // slip: the policy-capable instantiation serves both;
-        // one env per thread (the walk's registers): 70 vs 60 G env-steps/s with 4 (profiles/time_k2_rules_vec.py)
-        if (streams) SOCCER_LAUNCH_ROLLOUT_T(1, true, true, true, n);
+    if (P.slip) {
+        // with the slip index and room for it next to the table (5x4): 4 envs per thread, constant-prefix fast path +
+        // per-step warp queue (k_rollout_table_slipq); else the in-place walk, one env per thread (the walk's registers)
+        const int64_t fc_bytes = ((int64_t)P.nS * 25 + 15) / 16 * 16;
+        const int64_t smem_q = bytes + 16 + fc_bytes + (pol ? pol_bytes : 0) + (int64_t)kXqWarpBytes * (kRolloutThreads / 32);
+        if (slip_index && vec && smem_q <= 227 * 1024 - 6144) {
+            SlipE E;
+            { double acc = 0.0; for (int c = 0; c < 9; ++c) { acc += P.mp[c]; E.e[c] = acc; } }
+#define SOCCER_LAUNCH_ROLLOUT_Q(STR, POL)                                                                \
+            do {                                                                                         \
+                const int e0 = allow_big_smem(k_rollout_table_slipq<STR, POL>, smem_q);                  \
+                if (e0) return e0;                                                                       \
+                const int e1 = launch_pdl(k_rollout_table_slipq<STR, POL>, table_grid(n / 4, kRolloutThreads), kRolloutThreads, \
+                                          (size_t)smem_q, st, P, table, (uint32_t)bytes, slip_index, (uint32_t)fc_bytes, E, \
+                                          policy_a, policy_b, ra);                                       \
+                if (e1) return e1;                                                                       \
+            } while (0)
+            if (streams) { if (pol) SOCCER_LAUNCH_ROLLOUT_Q(true, true); else SOCCER_LAUNCH_ROLLOUT_Q(true, false); }
+            else { if (pol) SOCCER_LAUNCH_ROLLOUT_Q(false, true); else SOCCER_LAUNCH_ROLLOUT_Q(false, false); }
+#undef SOCCER_LAUNCH_ROLLOUT_Q
+        }
+        else if (streams) SOCCER_LAUNCH_ROLLOUT_T(1, true, true, true, n);
         else SOCCER_LAUNCH_ROLLOUT_T(1, false, true, true, n);
     }
     else if (pol) SOCCER_PICK_ROLLOUT_T(true, false);
@@ -1131,8 +1267,8 @@ int soccer_rollout_table(const soccer_pitch* pitch, const uint16_t* table, uint3
                          uint64_t step0, int32_t K, uint64_t env_id_base, int32_t* obs, float* reward,
                          uint8_t* flags, unsigned long long* stats, int64_t n, soccer_stream_t stream)
 {
-    return soccer_rollout_table_policy(pitch, table, state, nullptr, nullptr, seed, step0, K, env_id_base, obs, reward,
-                                       flags, stats, n, stream);
+    return soccer_rollout_table_policy(pitch, table, nullptr, state, nullptr, nullptr, seed, step0, K, env_id_base, 0, obs,
+                                       reward, flags, stats, n, stream);
 }
 
 int soccer_convert_state(const soccer_pitch* pitch, const uint32_t* in, uint32_t* out, int32_t to_layout, int64_t n,

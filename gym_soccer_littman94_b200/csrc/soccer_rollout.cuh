@@ -1,19 +1,21 @@
-// soccer_rollout.cuh -- K2: K fused steps with the state register-resident, two variants.
+// soccer_rollout.cuh -- K2: K fused steps with the state register-resident.
 //
-//   k_rollout_table  5x4-class pitches: transition table in shared memory (soccer_table.cuh),
-//                    uniform random policy; 148 x 512-thread CTAs
-//   k_rollout        any pitch: rules inline -- byte-parallel step4_noslip() for the uniform policy,
-//                    the scalar step for on-device TABLE policies (int8[nS], the reference's
-//                    utils/policies.py dict format); 256-thread CTAs
+//   k_rollout_table        5x4-class pitches: transition table in shared memory (soccer_table.cuh), uniform or table
+//                          policies; 148 x 512-thread CTAs
+//   k_rollout_table_slipq  the same for slip_prob > 0: constant-prefix fast path + a per-step warp queue for the envs
+//                          whose draw needs the reference's cumulative walk
+//   k_rollout              any pitch: rules inline -- byte-parallel step4_noslip() for the uniform policy,
+//                          the scalar step for on-device TABLE policies (int8[nS], the reference's
+//                          utils/policies.py dict format); 256-thread CTAs
 //
-// Each thread owns VEC envs for all K steps; state, timestep and the current Philox block (one
-// Philox4x32-10 call = the words of 4 consecutive steps) stay in registers; only the obs / reward /
-// flags streams ([K][n]) are written, as 128 / 128 / 32-bit stores when VEC == 4.  The k loop walks
-// Philox blocks with a static word index and 32-bit step arithmetic.
+// Each thread owns VEC envs for all K steps; state and timestep stay in registers; only the obs / reward / flags
+// streams ([K][n]) are written, as 128 / 128 / 32-bit stores when VEC == 4.  Randomness: Philox contract v2
+// (soccer_rules.cuh) -- ONE Philox4x32-10 call per step yields the words of the thread's four envs (an aligned
+// group of the global env ids).
 // Episode statistics cost ~2 instructions per env-step: episodes / truncations by byte-parallel
 // accumulation of the packed flags word (flushed with dp4a every 64 steps); goals_A - goals_B =
 // sum of rewards; sum_episode_len from sum(t_in) + K*VEC = sum(finished lengths) + sum(t_out).
-// slip_prob == 0.  SIM = /root/reference/gym_soccer/envs/soccer_simultaneous_env.py.
+// SIM = /root/reference/gym_soccer/envs/soccer_simultaneous_env.py.
 #pragma once
 #include "soccer_rules4.cuh"
 #include "soccer_table.cuh"
@@ -23,21 +25,25 @@ namespace soccer {
 struct RolloutArgs {
     uint32_t* state; uint64_t seed, step0; int32_t K; uint64_t env_id_base;
     int32_t* obs; float* reward; uint8_t* flags; unsigned long long* stats; int64_t n;
+    int32_t flip;    // 1: the streamed reward is player B's (= -A's): the env's return agent is player_b (SIM:243-244).
+                     // The goals_A / goals_B statistics always count by the unflipped sign.
 };
 
-// ---- steppers: advance the VEC envs of a thread by one step given their Philox words
-// A variant of this stepper that moved the selects / shifts / compares onto the FMA pipe (mul.hi carries, IMAD
+// ---- steppers: advance the VEC envs of a thread by one step given their Philox words.
+// kCollective: step() contains warp-level exchanges, so every lane of the warp has to call it every step.
+// A variant of the table stepper that moved the selects / shifts / compares onto the FMA pipe (mul.hi carries, IMAD
 // packing, 2^23 magic-add int -> float; ALU pipe 81 % -> 71 % busy) measured 2 % SLOWER on B200 in three A/B
 // runs: with 2^20+ envs the kernel sits at the HBM write ceiling (0.92-0.99 of the traffic probe), not on issue.
 template <bool POLICY, bool SLIP>
 struct TableStepper {
+    static constexpr bool kCollective = false;
     TblCtx c;
     uint32_t pol_a, pol_b;      // shared-window addresses of the int8[nS] table policies, 0 = uniform (POLICY only)
     SlipCtx sc;                 // slip-combination probability table (SLIP only)
     __device__ __forceinline__ uint32_t timestep(uint32_t s) const { return s >> 16; }
     template <int VEC>
     __device__ __forceinline__ void step(uint32_t* s, const uint32_t* word, uint32_t* oo, uint32_t* rr,
-                                         uint32_t& fw, int32_t& net, uint64_t seed, uint64_t env0, uint64_t step_abs) const
+                                         uint32_t& fw, int32_t& net, bool flip) const
     {
         uint32_t ff[4] = { 0, 0, 0, 0 };
 #pragma unroll
@@ -54,14 +60,100 @@ struct TableStepper {
                 if (POLICY && pol_b) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(ab) : "r"(pol_b + cur));
                 jr = aa * 20u + ab * 4u + (jr & 3u);
             }
-            // slip_prob > 0: the step draw is a 53-bit Philox uniform of a separate counter lane (as in k_rollout)
-            const TblOut o = SLIP ? table_step_slip(c, sc, s[e], aa, ab, philox_u53(seed, env0 + e, step_abs),
+            // slip_prob > 0: the in-place walk with the word's 32-bit step draw (6x4, where the slip index does not fit)
+            const TblOut o = SLIP ? table_step_slip(c, sc, s[e], aa, ab, u_from_rng32(philox_r32(word[e])),
                                                     (word[e] << 2) & 0xCu)
                                   : table_step(c, s[e], jr, (word[e] << 2) & 0xCu);
-            s[e] = o.state; oo[e] = o.obs; rr[e] = __float_as_uint((float)o.rew_i); ff[e] = o.flags;
+            s[e] = o.state; oo[e] = o.obs; rr[e] = __float_as_uint((float)(flip ? -o.rew_i : o.rew_i)); ff[e] = o.flags;
             net += o.rew_i;
         }
         fw = VEC == 4 ? pack4(ff[0], ff[1], ff[2], ff[3]) : ff[0];
+    }
+};
+
+// slip_prob > 0 with the slip index (5x4): the K1 fast path (table_step_slip_fast: constant-prefix pick through the
+// 4096-bucket table of the 32-bit draw + one mask byte per (obs, joint action)) for the ~85 % of the env-steps it
+// decides, and a PER-STEP warp queue for the rest.  The state lives in the owner's registers, so a deferred env
+// travels through a 12-byte slot of the warp's shared-memory exchange area: the owner writes (state, draw, actions),
+// lane j of the warp walks queue entry j with the reference's cumulative sums (table_step_slip) and writes the result
+// back, the owner picks it up.  One walk pass per warp and step serves all of its deferred envs (19 of 128 on
+// average at slip 0.2) instead of one divergent walk per env slot.  Bit-identical to the in-place walk.
+constexpr int kXqSlot = 12;                        // bytes per exchange slot
+constexpr int kXqWarpBytes = 128 * kXqSlot;        // every env of the warp could be deferred
+template <bool POLICY>
+struct TableSlipQStepper {
+    static constexpr bool kCollective = true;
+    TblCtx c; SlipCtx sc; SlipFast sf;
+    uint32_t pol_a, pol_b;
+    uint32_t xq;                                    // shared-window address of this warp's exchange slots
+    __device__ __forceinline__ uint32_t timestep(uint32_t s) const { return s >> 16; }
+    template <int VEC>
+    __device__ __forceinline__ void step(uint32_t* s, const uint32_t* word, uint32_t* oo, uint32_t* rr,
+                                         uint32_t& fw, int32_t& net, bool flip) const
+    {
+        static_assert(VEC == 4, "the queued slip stepper owns 4 envs per thread");
+        const uint32_t lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u;
+        const SlipE noE = {};
+        uint32_t ff[4], pos[4], cnt = 0;
+        int32_t rw[4];
+        bool df[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            uint32_t aa, ab;
+            philox_actions(word[e], aa, ab);
+            if (POLICY) {
+                const uint32_t cur = min(s[e] & 0xFFFFu, c.last / 100u);
+                if (pol_a) aa = lds_u8_r(pol_a + cur);
+                if (pol_b) ab = lds_u8_r(pol_b + cur);
+            }
+            const uint32_t r32 = philox_r32(word[e]), rsel4 = (word[e] << 2) & 0xCu;
+            bool defer;
+            const TblOut o = table_step_slip_fast<false>(c, sf, noE, s[e], aa, ab, 0.0, r32, rsel4, defer);
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, defer);
+            pos[e] = cnt + __popc(m & lt_mask);
+            cnt += __popc(m);
+            df[e] = defer;
+            if (defer) {
+                const uint32_t slot = xq + pos[e] * kXqSlot;
+                asm volatile("st.shared.u32 [%0], %1;" :: "r"(slot), "r"(s[e]) : "memory");
+                asm volatile("st.shared.u32 [%0], %1;" :: "r"(slot + 4u), "r"(r32) : "memory");
+                asm volatile("st.shared.u32 [%0], %1;" :: "r"(slot + 8u), "r"(aa | (ab << 4) | (rsel4 << 8)) : "memory");
+            } else {
+                s[e] = o.state;
+            }
+            oo[e] = o.obs; rw[e] = o.rew_i; ff[e] = o.flags;
+        }
+        if (cnt) {                                                       // warp-uniform
+            __syncwarp();
+            for (uint32_t first = 0; first < cnt; first += 32u) {
+                const uint32_t idx = first + lane;
+                if (idx < cnt) {
+                    const uint32_t slot = xq + idx * kXqSlot;
+                    uint32_t qs, qr, qm;
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(qs) : "r"(slot) : "memory");
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(qr) : "r"(slot + 4u) : "memory");
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(qm) : "r"(slot + 8u) : "memory");
+                    const TblOut o = table_step_slip(c, sc, qs, qm & 15u, (qm >> 4) & 15u, u_from_rng32(qr), (qm >> 8) & 0xCu);
+                    asm volatile("st.shared.u32 [%0], %1;" :: "r"(slot), "r"(o.state) : "memory");
+                    asm volatile("st.shared.u32 [%0], %1;" :: "r"(slot + 4u), "r"(o.obs | (o.flags << 12) | (((uint32_t)o.rew_i & 3u) << 14)) : "memory");
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (df[e]) {
+                    const uint32_t slot = xq + pos[e] * kXqSlot;
+                    uint32_t qs; int32_t qw;
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(qs) : "r"(slot) : "memory");
+                    asm volatile("ld.shared.s16 %0, [%1];" : "=r"(qw) : "r"(slot + 4u) : "memory");
+                    s[e] = qs; oo[e] = (uint32_t)qw & kTblObsMask; ff[e] = ((uint32_t)qw >> 12) & 3u; rw[e] = qw >> 14;
+                }
+            }
+            __syncwarp();                                                // slots free before the next step refills them
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { rr[e] = __float_as_uint((float)(flip ? -rw[e] : rw[e])); net += rw[e]; }
+        fw = pack4(ff[0], ff[1], ff[2], ff[3]);
     }
 };
 
@@ -69,14 +161,15 @@ struct TableStepper {
 // run-time branch the 4-env kernel needed 170 registers instead of 116 and lost its second resident CTA)
 template <bool SLIP>
 struct RulesStepper {
+    static constexpr bool kCollective = false;
     const PitchDev& P; const uint8_t* lut; Isd4 I; const int8_t* policy_a; const int8_t* policy_b; SlipCtx sc;
     __device__ __forceinline__ uint32_t timestep(uint32_t s) const { return (s >> 16) & 0xFFu; }
     template <int VEC>
     __device__ __forceinline__ void step(uint32_t* s, const uint32_t* word, uint32_t* oo, uint32_t* rr,
-                                         uint32_t& fw, int32_t& net, uint64_t seed, uint64_t env0, uint64_t step_abs) const
+                                         uint32_t& fw, int32_t& net, bool flip) const
     {
         if (SLIP) {
-            // slip_prob > 0 (SIM:203-227): the scalar 9-combination walk with a 53-bit Philox uniform
+            // slip_prob > 0 (SIM:203-227): the scalar 9-combination walk with the word's 32-bit step draw
             fw = 0;
 #pragma unroll
             for (int e = 0; e < VEC; ++e) {
@@ -87,11 +180,12 @@ struct RulesStepper {
                     if (policy_a) aa = (uint32_t)policy_a[cur];
                     if (policy_b) ab = (uint32_t)policy_b[cur];
                 }
-                const StepOut o = step_slip<true>(P, lut, sc, s[e], aa, ab, philox_u53(seed, env0 + e, step_abs),
+                const StepOut o = step_slip<true>(P, lut, sc, s[e], aa, ab, u_from_rng32(philox_r32(word[e])),
                                                   word[e] & 3u, false);
-                s[e] = o.state; oo[e] = (uint32_t)o.obs; rr[e] = __float_as_uint(o.reward);
+                const int32_t ri = (o.reward > 0.0f) - (o.reward < 0.0f);
+                s[e] = o.state; oo[e] = (uint32_t)o.obs; rr[e] = __float_as_uint((float)(flip ? -ri : ri));
                 fw |= (o.flags & 3u) << (8 * e);
-                net += (o.reward > 0.0f) - (o.reward < 0.0f);
+                net += ri;
             }
         } else if (VEC == 4 && !policy_a && !policy_b) {
             uint32_t aa[4], ab[4], rg[4];
@@ -101,7 +195,10 @@ struct RulesStepper {
             step4_noslip<false>(P, I, lut, s, pack4(aa[0], aa[1], aa[2], aa[3]), pack4(ab[0], ab[1], ab[2], ab[3]),
                                 pack4(rg[0], rg[1], rg[2], rg[3]), o);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) { s[e] = o.s[e]; oo[e] = o.obs[e]; rr[e] = o.rew[e]; }
+            for (int e = 0; e < 4; ++e) {
+                s[e] = o.s[e]; oo[e] = o.obs[e];
+                rr[e] = flip ? __float_as_uint((float)(-(int)(signed char)(o.rew4 >> (8 * e)))) : o.rew[e];
+            }
             fw = o.flags4;
             net += o.rew_sum;
         } else {
@@ -116,24 +213,36 @@ struct RulesStepper {
                     if (policy_b) ab = (uint32_t)policy_b[cur];
                 }
                 const StepOut o = step_noslip<true, false>(P, lut, s[e], aa, ab, philox_rng8(word[e]), false);
-                s[e] = o.state; oo[e] = (uint32_t)o.obs; rr[e] = __float_as_uint(o.reward);
+                const int32_t ri = (o.reward > 0.0f) - (o.reward < 0.0f);
+                s[e] = o.state; oo[e] = (uint32_t)o.obs; rr[e] = __float_as_uint((float)(flip ? -ri : ri));
                 fw |= (o.flags & 3u) << (8 * e);
-                net += (o.reward > 0.0f) - (o.reward < 0.0f);
+                net += ri;
             }
         }
     }
 };
 
-// ---- the K-step loop shared by both variants.  STREAMS: all three output streams present.
-template <int VEC, bool STREAMS, class Stepper>
-__device__ __forceinline__ void rollout_body(const Stepper& S, const RolloutArgs& a, unsigned int* blk_stats, int* blk_net)
+// 64-bit warp sum (statistics only; once per thread at the end of the kernel)
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
 {
-    uint32_t c_done = 0, c_trunc = 0, c_len = 0, c_steps = 0;
-    int32_t c_net = 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    return v;
+}
+
+// per-CTA statistics block in shared memory: done, trunc_only, steps, len (unsigned) and net (signed, two's complement)
+struct BlkStats { unsigned long long v[5]; };
+
+// ---- the K-step loop shared by all variants.  STREAMS: all three output streams present.
+template <int VEC, bool STREAMS, class Stepper>
+__device__ __forceinline__ void rollout_body(const Stepper& S, const RolloutArgs& a, BlkStats* blk)
+{
+    // 64-bit totals (a CTA of a 2^26-env batch steps 450 k envs: 32-bit counters would wrap at K ~ 9.5 k)
+    unsigned long long c_done = 0, c_trunc = 0, c_len = 0, c_steps = 0;
+    long long c_net = 0;
     const int64_t n_groups = a.n / VEC;
     const int32_t K = a.K;
-    const int32_t k_first = -(int32_t)(a.step0 & 3u);         // relative index of word 0 of the first Philox block
-    const uint64_t blk0 = a.step0 >> 2;
+    const bool flip = a.flip != 0;
     const uint32_t key0 = (uint32_t)a.seed, key1 = (uint32_t)(a.seed >> 32);
     // Slot order (a slot = 32 threads x VEC envs).  Full passes are CTA-major: the 16 warps of a CTA own 16
     // adjacent slots, so every step the SM writes 8 KB / 8 KB / 2 KB contiguous per stream - measured with the
@@ -148,9 +257,13 @@ __device__ __forceinline__ void rollout_body(const Stepper& S, const RolloutArgs
     for (int64_t pass = 0; pass <= full; ++pass) {
         const int64_t slot = pass < full ? (pass * gridDim.x + blockIdx.x) * wpc + wib
                                          : full * per_pass + (int64_t)wib * gridDim.x + blockIdx.x;
-        if (slot >= n_slots) break;
-        const int64_t g = slot * 32 + (threadIdx.x & 31);
-        if (g >= n_groups) break;
+        if (slot >= n_slots) break;                                      // warp-uniform
+        int64_t g = slot * 32 + (threadIdx.x & 31);
+        const bool valid = g < n_groups;
+        if (!valid) {
+            if (!Stepper::kCollective) break;
+            g = n_groups - 1;                                            // keeps the warp whole: computes, stores nothing
+        }
         const int64_t i0 = g * VEC;
         uint32_t s[4] = { 0, 0, 0, 0 };
         if (VEC == 4) {
@@ -162,77 +275,84 @@ __device__ __forceinline__ void rollout_body(const Stepper& S, const RolloutArgs
         uint32_t t_in = 0;
 #pragma unroll
         for (int e = 0; e < VEC; ++e) t_in += S.timestep(s[e]);
-        uint32_t acc_d = 0, acc_t = 0;
-        int32_t* op = a.obs ? a.obs + i0 : nullptr;
-        float* rp = a.reward ? a.reward + i0 : nullptr;
-        uint8_t* fp = a.flags ? a.flags + i0 : nullptr;
-        uint32_t env_lo[4], env_hi[4];
+        uint32_t acc_d = 0, acc_t = 0, p_done = 0, p_trunc = 0;
+        int32_t p_net = 0;
+        int32_t* op = (a.obs && valid) ? a.obs + i0 : nullptr;
+        float* rp = (a.reward && valid) ? a.reward + i0 : nullptr;
+        uint8_t* fp = (a.flags && valid) ? a.flags + i0 : nullptr;
+        // contract v2: the thread's VEC == 4 envs are one aligned group of the global ids (the dispatcher sends
+        // env_id_base % 4 != 0 to the VEC == 1 kernels, which pick their env's word of the group's call)
+        const uint64_t env0 = a.env_id_base + (uint64_t)i0;
+        const uint64_t grp = env0 >> 2;
+        const uint32_t grp_lo = (uint32_t)grp, grp_hi = (uint32_t)(grp >> 32), widx = (uint32_t)env0 & 3u;
+        uint64_t step = a.step0;
+        for (int32_t k = 0; k < K; ++k, ++step) {
+            uint32_t w[4], word[4], oo[4], rr[4], fw;
+            philox4x32_10(grp_lo, grp_hi, (uint32_t)step, (uint32_t)(step >> 32), key0, key1, w);
+            if (VEC == 4) {
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) {
-            const uint64_t env = a.env_id_base + (uint64_t)(i0 + e);
-            env_lo[e] = (uint32_t)env; env_hi[e] = (uint32_t)(env >> 32);
-        }
-        int32_t flush_at = 64;
-        uint64_t blk = blk0;
-        for (int32_t kb = k_first; kb < K; kb += 4, ++blk) {
-            uint32_t w[4][4];
-#pragma unroll
-            for (int e = 0; e < VEC; ++e)
-                philox4x32_10(env_lo[e], env_hi[e], (uint32_t)blk, (uint32_t)(blk >> 32), key0, key1, w[e]);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int32_t k = kb + j;
-                if (k < 0 || k >= K) continue;                          // warp-uniform
-                uint32_t word[4], oo[4], rr[4], fw;
-#pragma unroll
-                for (int e = 0; e < VEC; ++e) word[e] = w[e][j];
-                S.template step<VEC>(s, word, oo, rr, fw, c_net, a.seed, a.env_id_base + (uint64_t)i0, a.step0 + (uint64_t)k);
-                acc_d += fw & 0x01010101u;
-                acc_t += (fw >> 1) & ~fw & 0x01010101u;                 // truncated WITHOUT a goal
-                if (VEC == 4) {
-                    if (STREAMS || op) { st_stream(reinterpret_cast<uint4*>(op), make_uint4(oo[0], oo[1], oo[2], oo[3])); op += a.n; }
-                    if (STREAMS || rp) { st_stream(reinterpret_cast<uint4*>(rp), make_uint4(rr[0], rr[1], rr[2], rr[3])); rp += a.n; }
-                    if (STREAMS || fp) { st_stream(reinterpret_cast<uint32_t*>(fp), fw); fp += a.n; }
-                } else {
-                    if (STREAMS || op) { *op = (int32_t)oo[0]; op += a.n; }
-                    if (STREAMS || rp) { *rp = __uint_as_float(rr[0]); rp += a.n; }
-                    if (STREAMS || fp) { *fp = (uint8_t)fw; fp += a.n; }
-                }
+                for (int e = 0; e < 4; ++e) word[e] = w[e];
+            } else {
+                word[0] = widx == 0 ? w[0] : (widx == 1 ? w[1] : (widx == 2 ? w[2] : w[3]));
             }
-            if (kb + 4 >= flush_at) {                                   // bytes hold at most 64 + 3 counts
-                c_done = __dp4a(acc_d, 0x01010101u, c_done); c_trunc = __dp4a(acc_t, 0x01010101u, c_trunc);
-                acc_d = acc_t = 0; flush_at += 64;
+            S.template step<VEC>(s, word, oo, rr, fw, p_net, flip);
+            acc_d += fw & 0x01010101u;
+            acc_t += (fw >> 1) & ~fw & 0x01010101u;                     // truncated WITHOUT a goal
+            const bool with_streams = STREAMS && (!Stepper::kCollective || valid);
+            if (VEC == 4) {
+                if (with_streams || op) { st_stream(reinterpret_cast<uint4*>(op), make_uint4(oo[0], oo[1], oo[2], oo[3])); op += a.n; }
+                if (with_streams || rp) { st_stream(reinterpret_cast<uint4*>(rp), make_uint4(rr[0], rr[1], rr[2], rr[3])); rp += a.n; }
+                if (with_streams || fp) { st_stream(reinterpret_cast<uint32_t*>(fp), fw); fp += a.n; }
+            } else {
+                if (with_streams || op) { *op = (int32_t)oo[0]; op += a.n; }
+                if (with_streams || rp) { *rp = __uint_as_float(rr[0]); rp += a.n; }
+                if (with_streams || fp) { *fp = (uint8_t)fw; fp += a.n; }
+            }
+            if ((k & 63) == 63) {                                       // bytes hold at most 64 counts
+                p_done = __dp4a(acc_d, 0x01010101u, p_done); p_trunc = __dp4a(acc_t, 0x01010101u, p_trunc);
+                acc_d = acc_t = 0;
             }
         }
-        c_done = __dp4a(acc_d, 0x01010101u, c_done); c_trunc = __dp4a(acc_t, 0x01010101u, c_trunc);
+        p_done = __dp4a(acc_d, 0x01010101u, p_done); p_trunc = __dp4a(acc_t, 0x01010101u, p_trunc);
         uint32_t t_out = 0;
 #pragma unroll
         for (int e = 0; e < VEC; ++e) t_out += S.timestep(s[e]);
-        c_len += t_in + (uint32_t)K * VEC - t_out;
-        c_steps += (uint32_t)K * VEC;
-        if (VEC == 4) reinterpret_cast<uint4*>(a.state)[g] = make_uint4(s[0], s[1], s[2], s[3]);
-        else a.state[i0] = s[0];
+        if (valid) {
+            c_done += p_done; c_trunc += p_trunc; c_net += p_net;
+            c_len += (unsigned long long)t_in + (unsigned long long)K * VEC - t_out;
+            c_steps += (unsigned long long)K * VEC;
+            if (VEC == 4) reinterpret_cast<uint4*>(a.state)[g] = make_uint4(s[0], s[1], s[2], s[3]);
+            else a.state[i0] = s[0];
+        }
     }
     if (a.stats) {
-        uint32_t v[4] = { c_done, c_trunc, c_steps, c_len };
+        unsigned long long v[5] = { c_done, c_trunc, c_steps, c_len, (unsigned long long)c_net };
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint32_t r = __reduce_add_sync(0xFFFFFFFFu, v[j]);
-            if ((threadIdx.x & 31) == 0 && r) atomicAdd(&blk_stats[j], r);
+        for (int j = 0; j < 5; ++j) {
+            const unsigned long long r = warp_sum_u64(v[j]);
+            if ((threadIdx.x & 31) == 0 && r) atomicAdd(&blk->v[j], r);
         }
-        const int32_t rn = __reduce_add_sync(0xFFFFFFFFu, c_net);
-        if ((threadIdx.x & 31) == 0 && rn) atomicAdd(blk_net, rn);
         __syncthreads();
         if (threadIdx.x == 0) {
             // episodes = goals + truncated-only (a goal on step 100 carries both flags and counts once)
-            const long long d = blk_stats[0], tr_only = blk_stats[1], net = *blk_net;
+            const long long d = (long long)blk->v[0], tr_only = (long long)blk->v[1], net = (long long)blk->v[4];
             atomicAdd(&a.stats[0], (unsigned long long)(d + tr_only));
             atomicAdd(&a.stats[1], (unsigned long long)((d + net) / 2));      // goals_A (reward +1)
             atomicAdd(&a.stats[2], (unsigned long long)((d - net) / 2));      // goals_B (reward -1)
             atomicAdd(&a.stats[3], (unsigned long long)tr_only);
-            atomicAdd(&a.stats[4], (unsigned long long)blk_stats[2]);
-            atomicAdd(&a.stats[5], (unsigned long long)blk_stats[3]);
+            atomicAdd(&a.stats[4], blk->v[2]);
+            atomicAdd(&a.stats[5], blk->v[3]);
         }
+    }
+}
+
+// int8[nS] table policies: global -> shared (clamped so the column stays inside the row).  Called AFTER the grid
+// dependency wait: a policy tensor may have been produced by the preceding kernel in the stream.
+__device__ __forceinline__ void stage_policies(uint8_t* pa, uint8_t* pb, const int8_t* policy_a, const int8_t* policy_b, int nS)
+{
+    for (int i = threadIdx.x; i < nS; i += blockDim.x) {
+        if (policy_a) pa[i] = (uint8_t)min(max((int)policy_a[i], 0), 4);
+        if (policy_b) pb[i] = (uint8_t)min(max((int)policy_b[i], 0), 4);
     }
 }
 
@@ -245,34 +365,71 @@ k_rollout_table(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t 
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar;
-    __shared__ unsigned int blk_stats[4];
-    __shared__ int blk_net;
-    // programmatic dependent launch: back-to-back rollouts stage their table (and policies: constant inputs) while
-    // the previous launch drains; state, streams and statistics are only touched after pdl_wait()
+    __shared__ BlkStats blk;
+    // programmatic dependent launch: back-to-back rollouts stage their table (a constant input) while the previous
+    // launch drains; policies, state, streams and statistics are only touched after pdl_wait()
     pdl_launch_dependents();
-    if (threadIdx.x < 4) blk_stats[threadIdx.x] = 0;
-    if (threadIdx.x == 4) blk_net = 0;
+    if (threadIdx.x < 5) blk.v[threadIdx.x] = 0;
     TableStepper<POLICY, SLIP> S;
     S.pol_a = S.pol_b = 0;
     __shared__ __align__(16) double prt[kPrtDoubles];
     S.sc.prt = 0; S.sc.first_k = 0;
     if (SLIP) { slip_build_prt(prt, P); S.sc.prt = smem_u32(prt); S.sc.first_k = slip_first_k(P); }
-    if (POLICY) {
-        const uint32_t pol_bytes = ((uint32_t)P.nS + 15u) & ~15u;
-        uint8_t* pa = smem_raw + table_bytes + 16, *pb = pa + pol_bytes;
-        for (int i = threadIdx.x; i < P.nS; i += blockDim.x) {
-            if (policy_a) pa[i] = (uint8_t)min(max((int)policy_a[i], 0), 4);      // keep the column inside the row
-            if (policy_b) pb[i] = (uint8_t)min(max((int)policy_b[i], 0), 4);
-        }
-        if (policy_a) S.pol_a = smem_u32(pa);
-        if (policy_b) S.pol_b = smem_u32(pb);
-    }
-    stage_table(smem_raw, gtable, table_bytes, &bar, P);      // ends with __syncthreads(): policies visible
+    stage_table(smem_raw, gtable, table_bytes, &bar, P);      // ends with __syncthreads()
     S.c = make_ctx(smem_raw, table_bytes, P);
     wait_table(&bar);
     if (SLIP) { launder(S.c.tbl); launder(S.c.isd); launder(S.sc.prt); }   // table_step_slip's relaxed loads stay below the wait
     pdl_wait();
-    rollout_body<VEC, STREAMS>(S, a, blk_stats, &blk_net);
+    if (POLICY) {
+        const uint32_t pol_bytes = ((uint32_t)P.nS + 15u) & ~15u;
+        uint8_t* pa = smem_raw + table_bytes + 16, *pb = pa + pol_bytes;
+        stage_policies(pa, pb, policy_a, policy_b, P.nS);
+        if (policy_a) S.pol_a = smem_u32(pa);
+        if (policy_b) S.pol_b = smem_u32(pb);
+        __syncthreads();
+    }
+    rollout_body<VEC, STREAMS>(S, a, &blk);
+}
+
+// slip_prob > 0 with the slip index.  Shared-memory image: [table][isd 16 B][slip index][policy a][policy b]
+// [exchange slots: one kXqWarpBytes area per warp].
+template <bool STREAMS, bool POLICY>
+__global__ void __launch_bounds__(kRolloutThreads, 1)
+k_rollout_table_slipq(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t table_bytes,
+                      const uint8_t* __restrict__ gfc, uint32_t fc_bytes, const SlipE E,
+                      const int8_t* __restrict__ policy_a, const int8_t* __restrict__ policy_b, const RolloutArgs a)
+{
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ BlkStats blk;
+    __shared__ __align__(16) double prt[kPrtDoubles];
+    __shared__ uint8_t cacb[16], mv3[16];
+    __shared__ __align__(16) uint8_t klut[1 << kSlipLutBits];
+    pdl_launch_dependents();
+    if (threadIdx.x < 5) blk.v[threadIdx.x] = 0;
+    slip_build_prt(prt, P);
+    slip_fast_build_luts<false>(cacb, mv3, klut, E);
+    stage_table_and_index(smem_raw, gtable, table_bytes, gfc, fc_bytes, &bar, P);     // ends with __syncthreads()
+    TableSlipQStepper<POLICY> S;
+    S.c = make_ctx(smem_raw, table_bytes, P);
+    S.sc.prt = smem_u32(prt); S.sc.first_k = slip_first_k(P);
+    S.sf.fc = S.c.isd + 16u; S.sf.cacb = smem_u32(cacb); S.sf.mv3 = smem_u32(mv3); S.sf.klut = smem_u32(klut);
+    S.pol_a = S.pol_b = 0;
+    const uint32_t pol_bytes = POLICY ? (((uint32_t)P.nS + 15u) & ~15u) : 0u;
+    uint8_t* pa = smem_raw + table_bytes + 16 + fc_bytes, *pb = pa + pol_bytes;
+    S.xq = smem_u32(pb + pol_bytes) + (threadIdx.x >> 5) * kXqWarpBytes;
+    wait_table(&bar);
+    launder(S.c.tbl); launder(S.c.isd); launder(S.sc.prt);
+    launder(S.sf.fc); launder(S.sf.cacb); launder(S.sf.mv3); launder(S.sf.klut);
+    pdl_wait();
+    if (POLICY) {
+        stage_policies(pa, pb, policy_a, policy_b, P.nS);
+        if (policy_a) S.pol_a = smem_u32(pa);
+        if (policy_b) S.pol_b = smem_u32(pb);
+        __syncthreads();
+        launder(S.pol_a); launder(S.pol_b);
+    }
+    rollout_body<4, STREAMS>(S, a, &blk);
 }
 
 // (forcing 3 resident CTAs - 80 registers - measured 283 vs 291 G env-steps/s: the kernel is issue-bound)
@@ -282,16 +439,14 @@ k_rollout(const PitchDev P, const int8_t* __restrict__ policy_a, const int8_t* _
 {
     __shared__ __align__(16) uint8_t lut[kLutBytes];
     __shared__ __align__(16) double prt[kPrtDoubles];
-    __shared__ unsigned int blk_stats[4];
-    __shared__ int blk_net;
+    __shared__ BlkStats blk;
     if (SLIP) slip_build_prt(prt, P);
     build_cand_lut(lut, P);
-    if (threadIdx.x < 4) blk_stats[threadIdx.x] = 0;
-    if (threadIdx.x == 4) blk_net = 0;
+    if (threadIdx.x < 5) blk.v[threadIdx.x] = 0;
     __syncthreads();
     const SlipCtx sc = { (uint32_t)__cvta_generic_to_shared(prt), SLIP ? slip_first_k(P) : 0u };
     const RulesStepper<SLIP> S = { P, lut, make_isd4(P), policy_a, policy_b, sc };
-    rollout_body<VEC, STREAMS>(S, a, blk_stats, &blk_net);
+    rollout_body<VEC, STREAMS>(S, a, &blk);
 }
 
 // Measurement probe, not part of the game: K2's memory traffic (state read and written once, K x

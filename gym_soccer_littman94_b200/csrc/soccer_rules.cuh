@@ -130,7 +130,11 @@ __device__ __forceinline__ uint32_t obs_to_packed(const PitchDev& P, int32_t obs
     return a | (b << 8) | (p << 24);
 }
 
-// ---- Philox4x32-10 (Salmon et al. SC'11), one call = the words of 4 consecutive steps ----
+// ---- Philox4x32-10 (Salmon et al. SC'11).  Contract v2: ONE call = the words of the 4 envs of an ALIGNED GROUP
+// (global env id >> 2) at ONE step: counter = (group_lo, group_hi, step_lo, step_hi), key = seed, word index =
+// env id & 3.  Every kernel here owns 4 consecutive envs per thread, so K1 and K2 alike pay one call per four
+// env-steps (v1 keyed the counter by env and gave K1 one word of four: 40 multiplies per env-step).  Still a pure
+// function of (seed, global env id, step): independent of GPU count, K and launch boundaries.
 template <bool WIDE = false>
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                               uint32_t k0, uint32_t k1, uint32_t out[4])
@@ -140,7 +144,7 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
         uint32_t h0, l0, h1, l1;
         if (WIDE) {
             // one 32x32 -> 64 multiply per product (IMAD.WIDE.U32): fewer instructions, but measured SLOWER on B200
-            // (K1 table + Philox at 2^24 envs: 200 vs 236 G env-steps/s, profiles/r01g_time_k1_philox.log) -- A/B only
+            // (profiles/r01g_time_k1_philox.log) -- A/B only
             const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
             h0 = (uint32_t)(p0 >> 32); l0 = (uint32_t)p0; h1 = (uint32_t)(p1 >> 32); l1 = (uint32_t)p1;
         } else {
@@ -160,21 +164,31 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 #ifndef SOCCER_K1_PHILOX_WIDE
 #define SOCCER_K1_PHILOX_WIDE 0
 #endif
+// the four words of group `group` at `step`
+template <bool WIDE = false>
+__device__ __forceinline__ void philox_group(uint64_t seed, uint64_t group, uint64_t step, uint32_t out[4])
+{
+    philox4x32_10<WIDE>((uint32_t)group, (uint32_t)(group >> 32), (uint32_t)step, (uint32_t)(step >> 32),
+                        (uint32_t)seed, (uint32_t)(seed >> 32), out);
+}
+// one env's word (the one-env-per-thread paths: generic kernel, scalar tails, unaligned env_id_base)
 template <bool WIDE = false>
 __device__ __forceinline__ uint32_t philox_word(uint64_t seed, uint64_t env_id, uint64_t step)
 {
-    const uint64_t blk = step >> 2;
     uint32_t o[4];
-    philox4x32_10<WIDE>((uint32_t)env_id, (uint32_t)(env_id >> 32), (uint32_t)blk, (uint32_t)(blk >> 32),
-                        (uint32_t)seed, (uint32_t)(seed >> 32), o);
-    const uint32_t k = (uint32_t)step & 3u;
+    philox_group<WIDE>(seed, env_id >> 2, step, o);
+    const uint32_t k = (uint32_t)env_id & 3u;
     return k == 0 ? o[0] : (k == 1 ? o[1] : (k == 2 ? o[2] : o[3]));
 }
 
-// decode of one word.  jr = mulhi(w, 100) is uniform on 0..99 and carries the joint action and
-// the step draw at once -- jr = (aa*5 + ab)*4 + r, exactly the column index of the step table --
-// and the two lowest bits of w are the reset draw.
+// Decode of one word w, read as the fixed-point number x = w / 2^32 in [0, 1):
+//   joint action ja = floor(25 x) = mulhi(w, 25), aa = ja / 5, ab = ja % 5;
+//   step draw    r32 = frac(25 x) * 2^32 = lo32(25 w): u = (r32 + 0.5) / 2^32, the rng32 format (25 is odd, so
+//                w -> r32 is a bijection: exactly uniform).  slip_prob == 0 needs its top two bits only, and
+//                jr = mulhi(w, 100) = ja * 4 + (r32 >> 30) is at once the column index of the step table;
+//   reset draw   w & 3.
 __device__ __forceinline__ uint32_t philox_jr(uint32_t w) { return __umulhi(w, 100u); }
+__device__ __forceinline__ uint32_t philox_r32(uint32_t w) { return w * 25u; }
 __device__ __forceinline__ void philox_actions(uint32_t w, uint32_t& aa, uint32_t& ab)
 {
     const uint32_t ja = philox_jr(w) >> 2;
@@ -185,25 +199,18 @@ __device__ __forceinline__ void philox_actions(uint32_t w, uint32_t& aa, uint32_
 __device__ __forceinline__ uint32_t philox_rng8(uint32_t w) { return (philox_jr(w) & 3u) | ((w & 3u) << 2); }
 
 // Philox draws of the 4 envs of a group as rng8-compatible bytes (soccer_step_philox / soccer_step_table_philox:
-// K1 with on-device draws)
+// K1 with on-device draws).  env_id_base is a multiple of 4 here (the dispatcher sends other bases to the
+// one-env-per-thread kernel), so local group g is global group (env_id_base >> 2) + g.
 struct PhiloxKey { uint64_t seed, step, env_id_base; };
+__device__ __forceinline__ void philox_words4(const PhiloxKey& k, int64_t g, uint32_t w[4])
+{
+    philox_group<SOCCER_K1_PHILOX_WIDE != 0>(k.seed, (k.env_id_base >> 2) + (uint64_t)g, k.step, w);
+}
 __device__ __forceinline__ uint32_t philox_rng8x4(const PhiloxKey& k, int64_t g)
 {
-    uint32_t r[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) r[e] = philox_rng8(philox_word<SOCCER_K1_PHILOX_WIDE != 0>(k.seed, k.env_id_base + (uint64_t)(4 * g + e), k.step));
-    return r[0] | (r[1] << 8) | (r[2] << 16) | (r[3] << 24);
-}
-
-// slip_prob > 0 needs a fine-grained uniform for the categorical draw over up to 15 outcomes
-// (SIM:395): a 53-bit uniform in [0, 1), like np.random.RandomState.random(), from words 0 and 1
-// of a SEPARATE counter lane (the top bit of the counter is never set by the per-step words).
-__device__ __forceinline__ double philox_u53(uint64_t seed, uint64_t env_id, uint64_t step)
-{
     uint32_t w[4];
-    philox4x32_10((uint32_t)env_id, (uint32_t)(env_id >> 32), (uint32_t)step, (uint32_t)(step >> 32) | 0x80000000u,
-                  (uint32_t)seed, (uint32_t)(seed >> 32), w);
-    return (double)(((uint64_t)(w[0] >> 5) << 26) | (uint64_t)(w[1] >> 6)) * (1.0 / 9007199254740992.0);
+    philox_words4(k, g, w);
+    return philox_rng8(w[0]) | (philox_rng8(w[1]) << 8) | (philox_rng8(w[2]) << 16) | (philox_rng8(w[3]) << 24);
 }
 
 // ---- programmatic dependent launch (no-ops unless the launch carries the PDL attribute) ----

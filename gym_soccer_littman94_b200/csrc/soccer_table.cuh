@@ -246,23 +246,100 @@ __device__ __forceinline__ TblCtx make_ctx(const uint8_t* smem, uint32_t table_b
     return c;
 }
 
+// ---- episode statistics fused into K1 (optional `stats` argument of the step entry points): what K2 accumulates,
+// for ONE lock-step step -- stats[0] += episodes ended, [1] += goals_A, [2] += goals_B (by player A's reward sign,
+// whatever the return agent), [3] += truncations without a goal, [4] += env-steps, [5] += summed length of the
+// episodes that ended.  ~2.5 instructions per env: byte-parallel flag counts (dp4a), sum of the rewards, and
+// sum(len) from sum(t_in + 1) - sum(t_out) (an env that continues contributes 0, one that ended t_in + 1).
+struct K1Stats {
+    // dt: episodes that ended with a goal (low 16 bits) | truncated-only (high 16 bits): a thread steps < 2^14 groups
+    // for any batch that fits the GPU's memory.  `steps` is only used by the one-env-per-thread kernels (the 4-env
+    // kernels step every env of the batch: the flush adds n).
+    uint32_t dt, len, steps; int32_t net;
+    // s_in_sum / s_out_sum: the sums of the four INDEX-layout state words (obs | t << 16; four observations cannot
+    // carry into bit 16), or of the four timesteps << 16
+    __device__ __forceinline__ void add4(uint32_t fw, int32_t rew_sum, uint32_t s_in_sum, uint32_t s_out_sum)
+    {
+        dt = __dp4a(fw & 0x01010101u, 0x01010101u, dt);
+        dt += __dp4a((fw >> 1) & ~fw & 0x01010101u, 0x01010101u, 0u) << 16;
+        net += rew_sum; len += (s_in_sum >> 16) + 4u - (s_out_sum >> 16);
+    }
+    __device__ __forceinline__ void add1(uint32_t f, int32_t rew, uint32_t ep_len)
+    {
+        dt += (f & 1u) | (((f >> 1) & ~f & 1u) << 16); net += rew; steps += 1u; len += (f & 3u) ? ep_len : 0u;
+    }
+};
+struct K1StatsBlk { unsigned long long v[4]; long long net; };
+__device__ __forceinline__ void k1_stats_init(K1StatsBlk* blk)
+{
+    if (threadIdx.x < 4) blk->v[threadIdx.x] = 0;
+    if (threadIdx.x == 4) blk->net = 0;
+}
+// every thread of the CTA calls this once at the end of the kernel (contains a CTA barrier); all_steps: env-steps the
+// whole launch made when the per-thread `steps` counters are not used (added once, by CTA 0)
+__device__ __forceinline__ void k1_stats_flush(const K1Stats& a, K1StatsBlk* blk, unsigned long long* stats,
+                                               unsigned long long all_steps = 0)
+{
+    const uint32_t v[4] = { a.dt & 0xFFFFu, a.dt >> 16, a.steps, a.len };
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t r = __reduce_add_sync(0xFFFFFFFFu, v[j]);
+        if ((threadIdx.x & 31) == 0 && r) atomicAdd(&blk->v[j], (unsigned long long)r);
+    }
+    const int32_t rn = __reduce_add_sync(0xFFFFFFFFu, a.net);
+    if ((threadIdx.x & 31) == 0 && rn) atomicAdd(reinterpret_cast<unsigned long long*>(&blk->net), (unsigned long long)(long long)rn);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const long long d = (long long)blk->v[0], tr = (long long)blk->v[1], net = blk->net;
+        const unsigned long long steps = blk->v[2] + (blockIdx.x == 0 ? all_steps : 0ull);
+        if (d + tr) atomicAdd(&stats[0], (unsigned long long)(d + tr));
+        if (d + net) atomicAdd(&stats[1], (unsigned long long)((d + net) / 2));
+        if (d - net) atomicAdd(&stats[2], (unsigned long long)((d - net) / 2));
+        if (tr) atomicAdd(&stats[3], (unsigned long long)tr);
+        if (steps) atomicAdd(&stats[4], steps);
+        if (blk->v[3]) atomicAdd(&stats[5], blk->v[3]);
+    }
+}
+
+// Folded table policies of the single-agent modes (SIM:187-188: the folded player's action is its int8[nS] policy at
+// the CURRENT observation; SIM:243-244: the reward is flipped when the return agent is player_b, i.e. when player A
+// is the folded one).  Shared-window addresses, 0 = that player is not folded.
+struct K1Policy { uint32_t pol_a, pol_b; };
+
 // NARROW (soccer_step_narrow): obs as uint16, reward as int8 -- `obs` then points at uint16[n] (one uint2 per group),
 // `rew` at int8[n] (one word per group); same values, 8 instead of 13 bytes written per env
-template <bool RESET_OBS, bool NARROW = false>
+template <bool RESET_OBS, bool NARROW = false, bool POLICY = false, bool STATS = false>
 __device__ __forceinline__ void table_step_group(const TblCtx& c, const Group4& x, int64_t g, uint4* st, uint4* obs,
-                                                 uint4* rew, uint32_t* flg, uint4* rob)
+                                                 uint4* rew, uint32_t* flg, uint4* rob, const K1Policy& pol, K1Stats& acc)
 {
-    // byte-parallel: jr = aa*20 + ab*4 + (rng & 3) for all four envs in three instructions
-    const uint32_t jr4 = x.a * 20u + x.b * 4u + (x.r & 0x03030303u);
+    // byte-parallel: jr = aa*20 + ab*4 + (rng & 3) for all four envs in three instructions.  Action bytes are masked
+    // to 3 bits so that an out-of-range byte (>= 13 would carry into the neighbour's column) stays inside its own env;
+    // the index clamp in table_step() then keeps it inside the table.
+    const uint32_t jr4 = (x.a & 0x07070707u) * 20u + (x.b & 0x07070707u) * 4u + (x.r & 0x03030303u);
     const uint32_t rs4 = x.r & 0x0C0C0C0Cu;
     const uint32_t sv[4] = { x.s.x, x.s.y, x.s.z, x.s.w };
+    const bool flip = POLICY && pol.pol_a != 0u;
     uint32_t so[4], oo[4], ro[4], rr[4], ff[4];
+    int32_t rsum = 0;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-        const TblOut o = table_step(c, sv[e], __byte_perm(jr4, 0, 0x4440 + e), __byte_perm(rs4, 0, 0x4440 + e));
+        uint32_t jr = __byte_perm(jr4, 0, 0x4440 + e);
+        if (POLICY) {
+            const uint32_t cur = min(sv[e] & 0xFFFFu, c.last / 100u);
+            uint32_t aa = __byte_perm(x.a, 0, 0x4440 + e) & 7u, ab = __byte_perm(x.b, 0, 0x4440 + e) & 7u;
+            if (pol.pol_a) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(aa) : "r"(pol.pol_a + cur));
+            if (pol.pol_b) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(ab) : "r"(pol.pol_b + cur));
+            jr = aa * 20u + ab * 4u + (__byte_perm(x.r, 0, 0x4440 + e) & 3u);
+        }
+        const TblOut o = table_step(c, sv[e], jr, __byte_perm(rs4, 0, 0x4440 + e));
         so[e] = o.state; oo[e] = o.obs; ro[e] = o.reset_obs; ff[e] = o.flags;
-        rr[e] = NARROW ? (uint32_t)o.rew_i : __float_as_uint((float)o.rew_i);
+        const int32_t rv = flip ? -o.rew_i : o.rew_i;
+        rr[e] = NARROW ? (uint32_t)rv : __float_as_uint((float)rv);
+        rsum += o.rew_i;
     }
+    const uint32_t fw = __byte_perm(__byte_perm(ff[0], ff[1], 0x0040), __byte_perm(ff[2], ff[3], 0x0040), 0x5410);
+    if (STATS)
+        acc.add4(fw, rsum, sv[0] + sv[1] + sv[2] + sv[3], so[0] + so[1] + so[2] + so[3]);
     st_keep(st + g, make_uint4(so[0], so[1], so[2], so[3]));
     if (NARROW) {
         st_stream(reinterpret_cast<uint2*>(obs) + g, make_uint2(oo[0] | (oo[1] << 16), oo[2] | (oo[3] << 16)));
@@ -272,30 +349,54 @@ __device__ __forceinline__ void table_step_group(const TblCtx& c, const Group4& 
         st_stream(obs + g, make_uint4(oo[0], oo[1], oo[2], oo[3]));
         st_stream(rew + g, make_uint4(rr[0], rr[1], rr[2], rr[3]));
     }
-    st_stream(flg + g, __byte_perm(__byte_perm(ff[0], ff[1], 0x0040), __byte_perm(ff[2], ff[3], 0x0040), 0x5410));
+    st_stream(flg + g, fw);
     if (RESET_OBS) st_stream(rob + g, make_uint4(ro[0], ro[1], ro[2], ro[3]));
 }
 
+// int8[nS] table policies global -> shared (after the grid-dependency wait: a policy tensor may come from the
+// preceding kernel), clamped to 0..4; returns the shared-window addresses
+__device__ __forceinline__ K1Policy stage_k1_policies(uint8_t* dst, const int8_t* policy_a, const int8_t* policy_b, int nS)
+{
+    const uint32_t pol_bytes = ((uint32_t)nS + 15u) & ~15u;
+    uint8_t* pa = dst, *pb = dst + pol_bytes;
+    for (int i = threadIdx.x; i < nS; i += blockDim.x) {
+        if (policy_a) pa[i] = (uint8_t)min(max((int)policy_a[i], 0), 4);
+        if (policy_b) pb[i] = (uint8_t)min(max((int)policy_b[i], 0), 4);
+    }
+    __syncthreads();
+    K1Policy k = { policy_a ? smem_u32(pa) : 0u, policy_b ? smem_u32(pb) : 0u };
+    return k;
+}
+
 // K1, table variant: persistent, one 1024-thread CTA per SM.  PHILOX (soccer_step_table_philox): the draw stream is
-// not read (19 B / env-step); the draws of a group are computed while the next pair's loads are in flight.
-template <bool RESET_OBS, bool PHILOX = false, bool NARROW = false>
+// not read (19 B / env-step); the draws of a group -- ONE Philox call, contract v2 -- are computed while the next
+// pair's loads are in flight.  POLICY: a folded player's action stream is not read either (its pointer aliases the
+// other player's); shared-memory image [table][isd 16 B][policy a][policy b].
+struct K1Extra { const int8_t* policy_a; const int8_t* policy_b; unsigned long long* stats; };
+template <bool RESET_OBS, bool PHILOX = false, bool NARROW = false, bool POLICY = false, bool STATS = false>
 __global__ void __launch_bounds__(kTableThreads, 1)
 k_step_table(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t table_bytes,
              uint32_t* __restrict__ state, const uint8_t* __restrict__ act_a, const uint8_t* __restrict__ act_b,
              const uint8_t* __restrict__ rng, int32_t* __restrict__ obs, float* __restrict__ reward,
              uint8_t* __restrict__ flags, int32_t* __restrict__ reset_obs, int64_t n_groups,
-             const PhiloxKey key = PhiloxKey())
+             const PhiloxKey key, const K1Extra ex)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar;
+    __shared__ K1StatsBlk sblk;
     pdl_launch_dependents();
+    if (STATS) k1_stats_init(&sblk);
     stage_table(smem_raw, gtable, table_bytes, &bar, P);     // the table is constant: safe before pdl_wait
     const TblCtx c = make_ctx(smem_raw, table_bytes, P);
     pdl_wait();                  // the table fill overlaps the previous kernel's tail
+    K1Policy pol = { 0u, 0u };
+    if (POLICY) pol = stage_k1_policies(smem_raw + table_bytes + 16, ex.policy_a, ex.policy_b, P.nS);
+    K1Stats acc = {};
 
     uint4* st4 = reinterpret_cast<uint4*>(state);
-    const uint32_t* a4 = reinterpret_cast<const uint32_t*>(act_a);
-    const uint32_t* b4 = reinterpret_cast<const uint32_t*>(act_b);
+    // a folded player's action stream does not exist: alias the other one (loaded, never used)
+    const uint32_t* a4 = reinterpret_cast<const uint32_t*>(act_a ? act_a : act_b);
+    const uint32_t* b4 = reinterpret_cast<const uint32_t*>(act_b ? act_b : act_a);
     const uint32_t* r4 = PHILOX ? a4 : reinterpret_cast<const uint32_t*>(rng);   // PHILOX: value replaced below
     uint4* o4 = reinterpret_cast<uint4*>(obs);
     uint4* w4 = reinterpret_cast<uint4*>(reward);
@@ -322,10 +423,11 @@ k_step_table(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t tab
             if (gp + stride < n_groups) prefetch_group(st4, a4, b4, r4, gp + stride, !PHILOX);
         }
         if (PHILOX) { x0.r = philox_rng8x4(key, g); if (two) x1.r = philox_rng8x4(key, g + stride); }
-        table_step_group<RESET_OBS, NARROW>(c, x0, g, st4, o4, w4, f4, q4);
-        if (two) table_step_group<RESET_OBS, NARROW>(c, x1, g + stride, st4, o4, w4, f4, q4);
+        table_step_group<RESET_OBS, NARROW, POLICY, STATS>(c, x0, g, st4, o4, w4, f4, q4, pol, acc);
+        if (two) table_step_group<RESET_OBS, NARROW, POLICY, STATS>(c, x1, g + stride, st4, o4, w4, f4, q4, pol, acc);
         x0 = y0; x1 = y1; g = gn; one = n_one; two = n_two;
     }
+    if (STATS) k1_stats_flush(acc, &sblk, ex.stats, (unsigned long long)n_groups * 4ull);
 }
 
 // scalar tail / misaligned fallback of the table path (global-memory table, one env per thread)
@@ -334,15 +436,23 @@ k_step_table_scalar(const PitchDev P, const uint16_t* __restrict__ gtable, uint3
                     const uint8_t* __restrict__ act_a, const uint8_t* __restrict__ act_b,
                     const uint8_t* __restrict__ rng, int32_t* __restrict__ obs, float* __restrict__ reward,
                     uint8_t* __restrict__ flags, int32_t* __restrict__ reset_obs, int64_t n,
-                    int use_philox = 0, const PhiloxKey key = PhiloxKey(), int narrow = 0)
+                    int use_philox, const PhiloxKey key, int narrow, const K1Extra ex)
 {
+    __shared__ K1StatsBlk sblk;
+    k1_stats_init(&sblk);
+    __syncthreads();
+    K1Stats acc = {};
     const int16_t* tbl = reinterpret_cast<const int16_t*>(gtable);
     const uint32_t last = (uint32_t)P.nS * 100u - 1u;
+    const bool flip = ex.policy_a != nullptr;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const uint32_t s = state[i];
         const uint32_t rg = use_philox ? philox_rng8(philox_word(key.seed, key.env_id_base + (uint64_t)i, key.step)) : rng[i];
-        const uint32_t idx = min((s & 0xFFFFu) * 100u + (uint32_t)act_a[i] * 20u + (uint32_t)act_b[i] * 4u + (rg & 3u), last);
+        const uint32_t cur = min(s & 0xFFFFu, (uint32_t)P.nS - 1u);
+        const uint32_t aa = ex.policy_a ? (uint32_t)min(max((int)ex.policy_a[cur], 0), 4) : ((uint32_t)act_a[i] & 7u);
+        const uint32_t ab = ex.policy_b ? (uint32_t)min(max((int)ex.policy_b[cur], 0), 4) : ((uint32_t)act_b[i] & 7u);
+        const uint32_t idx = min((s & 0xFFFFu) * 100u + aa * 20u + ab * 4u + (rg & 3u), last);
         const int32_t e = tbl[idx];
         const uint32_t nobs = (uint32_t)e & kTblObsMask;
         const bool done = nobs == 0;
@@ -350,16 +460,20 @@ k_step_table_scalar(const PitchDev P, const uint16_t* __restrict__ gtable, uint3
         const bool trunc = s1 >= kTruncWord, reset = done | trunc;
         const uint32_t ro = (uint32_t)P.isd_obs[(rg >> 2) & 3u];
         state[i] = reset ? ro : ((s1 & 0xFFFF0000u) | nobs);
+        const int32_t rv = flip ? -(e >> 14) : (e >> 14);
         if (narrow) {
             reinterpret_cast<uint16_t*>(obs)[i] = (uint16_t)nobs;
-            reinterpret_cast<int8_t*>(reward)[i] = (int8_t)(e >> 14);
+            reinterpret_cast<int8_t*>(reward)[i] = (int8_t)rv;
         } else {
             obs[i] = (int32_t)nobs;
-            reward[i] = (float)(e >> 14);
+            reward[i] = (float)rv;
         }
-        flags[i] = (uint8_t)((done ? 1u : 0u) + (trunc ? 2u : 0u));
+        const uint32_t f = (done ? 1u : 0u) + (trunc ? 2u : 0u);
+        flags[i] = (uint8_t)f;
         if (reset_obs) reset_obs[i] = (int32_t)(reset ? ro : nobs);
+        acc.add1(f, e >> 14, s1 >> 16);
     }
+    if (ex.stats) k1_stats_flush(acc, &sblk, ex.stats);
 }
 
 // K1, table variant with PACKED host-facing streams (soccer_step_table_packed): the joint action of an env in one
@@ -373,17 +487,19 @@ __device__ __forceinline__ uint32_t packed_result(int32_t e, uint32_t flags)
     return ((uint32_t)e & 0xCFFFu) | (flags << 12);
 }
 struct GroupP { uint4 s; uint32_t j, r; };
+template <bool PHILOX>
 __device__ __forceinline__ GroupP load_group_packed(const uint4* st, const uint32_t* j4, const uint32_t* r4, int64_t g)
 {
     GroupP x;
     x.s = ld_keep(st + g);
     x.j = ld_stream(j4 + g);
-    x.r = ld_stream(r4 + g);
+    x.r = PHILOX ? 0u : ld_stream(r4 + g);
     return x;
 }
 __device__ __forceinline__ void table_step_group_packed(const TblCtx& c, const GroupP& x, int64_t g, uint4* st, uint2* res)
 {
-    const uint32_t jr4 = (x.j & 0x0F0F0F0Fu) * 20u + ((x.j >> 4) & 0x0F0F0F0Fu) * 4u + (x.r & 0x03030303u);
+    // nibbles masked to 3 bits: an out-of-range action stays inside its own env (see table_step_group)
+    const uint32_t jr4 = (x.j & 0x07070707u) * 20u + ((x.j >> 4) & 0x07070707u) * 4u + (x.r & 0x03030303u);
     const uint32_t rs4 = x.r & 0x0C0C0C0Cu;
     const uint32_t sv[4] = { x.s.x, x.s.y, x.s.z, x.s.w };
     uint32_t so[4], w[4];
@@ -397,10 +513,12 @@ __device__ __forceinline__ void table_step_group_packed(const TblCtx& c, const G
     st_stream(res + g, make_uint2(w[0] | (w[1] << 16), w[2] | (w[3] << 16)));
 }
 
+// PHILOX: no draw stream (1 byte in, 2 bytes out per env-step): the draws come from the env's Philox word
+template <bool PHILOX>
 __global__ void __launch_bounds__(kTableThreads, 1)
 k_step_table_packed(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t table_bytes,
                     uint32_t* __restrict__ state, const uint8_t* __restrict__ joint, const uint8_t* __restrict__ rng,
-                    uint16_t* __restrict__ result, int64_t n_groups)
+                    uint16_t* __restrict__ result, int64_t n_groups, const PhiloxKey key)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar;
@@ -418,15 +536,16 @@ k_step_table_packed(const PitchDev P, const uint16_t* __restrict__ gtable, uint3
     int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool one = g < n_groups, two = g + stride < n_groups;
     GroupP x0 = {}, x1 = {};
-    if (one) x0 = load_group_packed(st4, j4, r4, g);
-    if (two) x1 = load_group_packed(st4, j4, r4, g + stride);
+    if (one) x0 = load_group_packed<PHILOX>(st4, j4, r4, g);
+    if (two) x1 = load_group_packed<PHILOX>(st4, j4, r4, g + stride);
     wait_table(&bar);
     while (one) {
         const int64_t gn = g + 2 * stride;
         const bool n_one = gn < n_groups, n_two = gn + stride < n_groups;
         GroupP y0 = x0, y1 = x1;
-        if (n_one) y0 = load_group_packed(st4, j4, r4, gn);
-        if (n_two) y1 = load_group_packed(st4, j4, r4, gn + stride);
+        if (n_one) y0 = load_group_packed<PHILOX>(st4, j4, r4, gn);
+        if (n_two) y1 = load_group_packed<PHILOX>(st4, j4, r4, gn + stride);
+        if (PHILOX) { x0.r = philox_rng8x4(key, g); if (two) x1.r = philox_rng8x4(key, g + stride); }
         table_step_group_packed(c, x0, g, st4, w2);
         if (two) table_step_group_packed(c, x1, g + stride, st4, w2);
         x0 = y0; x1 = y1; g = gn; one = n_one; two = n_two;
@@ -437,14 +556,15 @@ k_step_table_packed(const PitchDev P, const uint16_t* __restrict__ gtable, uint3
 __global__ void __launch_bounds__(kThreads)
 k_step_table_packed_scalar(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t* __restrict__ state,
                            const uint8_t* __restrict__ joint, const uint8_t* __restrict__ rng,
-                           uint16_t* __restrict__ result, int64_t n)
+                           uint16_t* __restrict__ result, int64_t n, int use_philox, const PhiloxKey key)
 {
     const int16_t* tbl = reinterpret_cast<const int16_t*>(gtable);
     const uint32_t last = (uint32_t)P.nS * 100u - 1u;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const uint32_t s = state[i], rg = rng[i], j = joint[i];
-        const uint32_t idx = min((s & 0xFFFFu) * 100u + (j & 15u) * 20u + (j >> 4) * 4u + (rg & 3u), last);
+        const uint32_t s = state[i], j = joint[i];
+        const uint32_t rg = use_philox ? philox_rng8(philox_word(key.seed, key.env_id_base + (uint64_t)i, key.step)) : rng[i];
+        const uint32_t idx = min((s & 0xFFFFu) * 100u + (j & 7u) * 20u + ((j >> 4) & 7u) * 4u + (rg & 3u), last);
         const int32_t e = tbl[idx];
         const uint32_t nobs = (uint32_t)e & kTblObsMask;
         const bool done = nobs == 0;
@@ -458,27 +578,82 @@ k_step_table_packed_scalar(const PitchDev P, const uint16_t* __restrict__ gtable
 
 // K1, table variant for slip_prob > 0: same launch shape as k_step_table, one more input stream (the step draw:
 // uint32 or fp64 per env; rng8 still carries the reset draw in bits 2..3).  24 or 28 algorithmic bytes per env-step.
+// DRAW: where the step draw comes from -- kDrawU32 (rng32 stream, u = (r + 0.5) / 2^32), kDrawF64 (raw fp64 stream),
+// kDrawPhilox (no draw / rng8 streams: r32 = lo32(25 w) and the reset draw from the env's Philox word; 19 B).
 #ifndef SOCCER_SLIP_THREADS
 #define SOCCER_SLIP_THREADS 1024     // latency-bound (dependent DADD chain): 1024 threads x 64 registers beat 512 x 83 (98 vs 83 G env-steps/s)
 #endif
 constexpr int kSlipThreads = SOCCER_SLIP_THREADS;       // the slip walk keeps 4 envs x (sum, candidate, 6 addresses) live
-template <bool RESET_OBS, bool F64>
+constexpr int kDrawU32 = 0, kDrawF64 = 1, kDrawPhilox = 2;
+
+// the 4 envs' step draws + rng8 bytes of one group
+struct SlipIn { Group4 x; uint4 d0, d1; };
+template <int DRAW, bool PLAIN>
+__device__ __forceinline__ SlipIn slip_load_in(const uint4* st4, const uint32_t* a4, const uint32_t* b4, const uint32_t* r4,
+                                               const void* draw, int64_t g)
+{
+    SlipIn in;
+    if (PLAIN) {
+        // evict-normal loads: the queued walk re-reads the deferred envs' inputs a few microseconds later
+        in.x.s = ld_keep(st4 + g); in.x.a = a4[g]; in.x.b = b4[g];
+        in.x.r = DRAW == kDrawPhilox ? 0u : r4[g];
+        if (DRAW == kDrawF64) {
+            in.d0 = reinterpret_cast<const uint4*>(draw)[2 * g];
+            in.d1 = reinterpret_cast<const uint4*>(draw)[2 * g + 1];
+        } else if (DRAW == kDrawU32) {
+            in.d0 = reinterpret_cast<const uint4*>(draw)[g];
+            in.d1 = in.d0;
+        } else {
+            in.d0 = in.d1 = make_uint4(0, 0, 0, 0);
+        }
+    } else {
+        in.x.s = ld_keep(st4 + g); in.x.a = ld_stream(a4 + g); in.x.b = ld_stream(b4 + g);
+        in.x.r = DRAW == kDrawPhilox ? 0u : ld_stream(r4 + g);
+        if (DRAW == kDrawF64) {
+            in.d0 = __ldcs(reinterpret_cast<const uint4*>(draw) + 2 * g);
+            in.d1 = __ldcs(reinterpret_cast<const uint4*>(draw) + 2 * g + 1);
+        } else if (DRAW == kDrawU32) {
+            in.d0 = __ldcs(reinterpret_cast<const uint4*>(draw) + g);
+            in.d1 = in.d0;
+        } else {
+            in.d0 = in.d1 = make_uint4(0, 0, 0, 0);
+        }
+    }
+    return in;
+}
+// Philox mode: fill the draws of group g (one call, contract v2)
+__device__ __forceinline__ void slip_philox_fill(SlipIn& in, const PhiloxKey& key, int64_t g)
+{
+    uint32_t w[4];
+    philox_words4(key, g, w);
+    in.d0 = make_uint4(philox_r32(w[0]), philox_r32(w[1]), philox_r32(w[2]), philox_r32(w[3]));
+    in.d1 = in.d0;
+    in.x.r = ((w[0] & 3u) << 2) | ((w[1] & 3u) << 10) | ((w[2] & 3u) << 18) | ((w[3] & 3u) << 26);
+}
+
+struct SlipExtra { const int8_t* policy_a; const int8_t* policy_b; PhiloxKey key; };
+
+template <bool RESET_OBS, int DRAW>
 __global__ void __launch_bounds__(kSlipThreads, 1)
 k_step_table_slip(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t table_bytes,
                   uint32_t* __restrict__ state, const uint8_t* __restrict__ act_a, const uint8_t* __restrict__ act_b,
                   const uint8_t* __restrict__ rng, const void* __restrict__ draw, int32_t* __restrict__ obs,
-                  float* __restrict__ reward, uint8_t* __restrict__ flags, int32_t* __restrict__ reset_obs, int64_t n_groups)
+                  float* __restrict__ reward, uint8_t* __restrict__ flags, int32_t* __restrict__ reset_obs, int64_t n_groups,
+                  const SlipExtra ex)
 {
-    extern __shared__ __align__(128) uint8_t smem_raw[];
+    extern __shared__ __align__(128) uint8_t smem_raw[];     // [table][isd 16 B][policy a][policy b]
     __shared__ __align__(8) uint64_t bar;
     __shared__ __align__(16) double prt[kPrtDoubles];
     slip_build_prt(prt, P);
     stage_table(smem_raw, gtable, table_bytes, &bar, P);     // ends with __syncthreads(): prt visible
     TblCtx c = make_ctx(smem_raw, table_bytes, P);
     SlipCtx sc = { smem_u32(prt), slip_first_k(P) };
+    K1Policy pol = { 0u, 0u };
+    if (ex.policy_a || ex.policy_b) pol = stage_k1_policies(smem_raw + table_bytes + 16, ex.policy_a, ex.policy_b, P.nS);
+    const bool flip = pol.pol_a != 0u;
     uint4* st4 = reinterpret_cast<uint4*>(state);
-    const uint32_t* a4 = reinterpret_cast<const uint32_t*>(act_a);
-    const uint32_t* b4 = reinterpret_cast<const uint32_t*>(act_b);
+    const uint32_t* a4 = reinterpret_cast<const uint32_t*>(act_a ? act_a : act_b);
+    const uint32_t* b4 = reinterpret_cast<const uint32_t*>(act_b ? act_b : act_a);
     const uint32_t* r4 = reinterpret_cast<const uint32_t*>(rng);
     uint4* o4 = reinterpret_cast<uint4*>(obs);
     uint4* w4 = reinterpret_cast<uint4*>(reward);
@@ -486,26 +661,31 @@ k_step_table_slip(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_
     uint4* q4 = reinterpret_cast<uint4*>(reset_obs);
     wait_table(&bar);
     launder(c.tbl); launder(c.isd); launder(sc.prt);        // the relaxed loads below stay below the wait
+    launder(pol.pol_a); launder(pol.pol_b);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_groups; g += stride) {
-        const Group4 x = load_group(st4, a4, b4, r4, g);
+        SlipIn in = slip_load_in<DRAW, false>(st4, a4, b4, r4, draw, g);
+        if (DRAW == kDrawPhilox) slip_philox_fill(in, ex.key, g);
+        const Group4 x = in.x;
         double u[4];
-        if (F64) {
-            const double2 d0 = __ldcs(reinterpret_cast<const double2*>(draw) + 2 * g);
-            const double2 d1 = __ldcs(reinterpret_cast<const double2*>(draw) + 2 * g + 1);
-            u[0] = d0.x; u[1] = d0.y; u[2] = d1.x; u[3] = d1.y;
+        if (DRAW == kDrawF64) {
+            u[0] = __hiloint2double((int)in.d0.y, (int)in.d0.x); u[1] = __hiloint2double((int)in.d0.w, (int)in.d0.z);
+            u[2] = __hiloint2double((int)in.d1.y, (int)in.d1.x); u[3] = __hiloint2double((int)in.d1.w, (int)in.d1.z);
         } else {
-            const uint4 d = __ldcs(reinterpret_cast<const uint4*>(draw) + g);
-            u[0] = u_from_rng32(d.x); u[1] = u_from_rng32(d.y); u[2] = u_from_rng32(d.z); u[3] = u_from_rng32(d.w);
+            u[0] = u_from_rng32(in.d0.x); u[1] = u_from_rng32(in.d0.y); u[2] = u_from_rng32(in.d0.z); u[3] = u_from_rng32(in.d0.w);
         }
         const uint32_t rs4 = x.r & 0x0C0C0C0Cu;
         const uint32_t sv[4] = { x.s.x, x.s.y, x.s.z, x.s.w };
         uint32_t so[4], oo[4], ro[4], rr[4], ff[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            const TblOut o = table_step_slip(c, sc, sv[e], __byte_perm(x.a, 0, 0x4440 + e), __byte_perm(x.b, 0, 0x4440 + e),
-                                             u[e], __byte_perm(rs4, 0, 0x4440 + e));
-            so[e] = o.state; oo[e] = o.obs; rr[e] = __float_as_uint((float)o.rew_i); ro[e] = o.reset_obs; ff[e] = o.flags;
+            uint32_t aa = __byte_perm(x.a, 0, 0x4440 + e), ab = __byte_perm(x.b, 0, 0x4440 + e);
+            const uint32_t cur = min(sv[e] & 0xFFFFu, c.last / 100u);
+            if (pol.pol_a) aa = lds_u8_r(pol.pol_a + cur);
+            if (pol.pol_b) ab = lds_u8_r(pol.pol_b + cur);
+            const TblOut o = table_step_slip(c, sc, sv[e], aa, ab, u[e], __byte_perm(rs4, 0, 0x4440 + e));
+            so[e] = o.state; oo[e] = o.obs; rr[e] = __float_as_uint((float)(flip ? -o.rew_i : o.rew_i));
+            ro[e] = o.reset_obs; ff[e] = o.flags;
         }
         st_keep(st4 + g, make_uint4(so[0], so[1], so[2], so[3]));
         st_stream(o4 + g, make_uint4(oo[0], oo[1], oo[2], oo[3]));
@@ -601,20 +781,11 @@ __device__ __forceinline__ TblOut table_step_slip_fast(const TblCtx& c, const Sl
     return table_finish(c, s, e, rsel4);
 }
 
-template <bool RESET_OBS, bool F64>
-__global__ void __launch_bounds__(kTableThreads, 1)
-k_step_table_slip_q(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t table_bytes,
-                    const uint8_t* __restrict__ gfc, uint32_t fc_bytes, const SlipE E,
-                    uint32_t* __restrict__ state, const uint8_t* __restrict__ act_a, const uint8_t* __restrict__ act_b,
-                    const uint8_t* __restrict__ rng, const void* __restrict__ draw, int32_t* __restrict__ obs,
-                    float* __restrict__ reward, uint8_t* __restrict__ flags, int32_t* __restrict__ reset_obs, int64_t n_groups)
+// the small look-up tables of the fast path, built by every CTA: cacb[k] = move selectors of combination k,
+// mv3[a * 3 + sel] = the (slipped) move, klut[top 12 bits of r] = k(r) or 0xFF (uint32 draws only)
+template <bool F64>
+__device__ __forceinline__ void slip_fast_build_luts(uint8_t* cacb, uint8_t* mv3, uint8_t* klut, const SlipE& E)
 {
-    extern __shared__ __align__(128) uint8_t smem_raw[];     // [table][isd 16 B][fc][queue u16 x kSlipQueueMax]
-    __shared__ __align__(8) uint64_t bar;
-    __shared__ __align__(16) double prt[kPrtDoubles];
-    __shared__ uint8_t cacb[16], mv3[16];
-    __shared__ __align__(16) uint8_t klut[F64 ? 16 : (1 << kSlipLutBits)];
-    slip_build_prt(prt, P);
     if (threadIdx.x < 9) cacb[threadIdx.x] = (uint8_t)(combo_a((int)threadIdx.x) | (combo_b((int)threadIdx.x) << 4));
     if (threadIdx.x < 15) {
         const uint32_t a = threadIdx.x / 3u, cmb = threadIdx.x % 3u;
@@ -631,26 +802,58 @@ k_step_table_slip_q(const PitchDev P, const uint16_t* __restrict__ gtable, uint3
             klut[b] = (uint8_t)(klo == khi ? klo : 0xFFu);
         }
     }
-    // stage table + slip index with ONE mbarrier
+}
+// stage table + slip index with ONE mbarrier; ends with __syncthreads()
+__device__ __forceinline__ void stage_table_and_index(uint8_t* smem, const uint16_t* gtable, uint32_t table_bytes,
+                                                      const uint8_t* gfc, uint32_t fc_bytes, uint64_t* bar, const PitchDev& P)
+{
     if (threadIdx.x == 0) {
-        mbar_init(&bar, 1);
+        mbar_init(bar, 1);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(&bar, table_bytes + fc_bytes);
+        mbar_expect_tx(bar, table_bytes + fc_bytes);
         const uint32_t chunk = 16384;
         for (uint32_t off = 0; off < table_bytes; off += chunk)
-            tma_load_1d(smem_raw + off, reinterpret_cast<const uint8_t*>(gtable) + off, min(chunk, table_bytes - off), &bar);
+            tma_load_1d(smem + off, reinterpret_cast<const uint8_t*>(gtable) + off, min(chunk, table_bytes - off), bar);
         for (uint32_t off = 0; off < fc_bytes; off += chunk)
-            tma_load_1d(smem_raw + table_bytes + 16 + off, gfc + off, min(chunk, fc_bytes - off), &bar);
+            tma_load_1d(smem + table_bytes + 16 + off, gfc + off, min(chunk, fc_bytes - off), bar);
     }
-    if (threadIdx.x < 4) reinterpret_cast<int32_t*>(smem_raw + table_bytes)[threadIdx.x] = P.isd_obs[threadIdx.x];
+    if (threadIdx.x < 4) reinterpret_cast<int32_t*>(smem + table_bytes)[threadIdx.x] = P.isd_obs[threadIdx.x];
     __syncthreads();
+}
+
+// shared-memory image: [table][isd 16 B][slip index][policy a][policy b][queues]
+template <bool RESET_OBS, int DRAW>
+__global__ void __launch_bounds__(kTableThreads, 1)
+k_step_table_slip_q(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t table_bytes,
+                    const uint8_t* __restrict__ gfc, uint32_t fc_bytes, const SlipE E,
+                    uint32_t* __restrict__ state, const uint8_t* __restrict__ act_a, const uint8_t* __restrict__ act_b,
+                    const uint8_t* __restrict__ rng, const void* __restrict__ draw, int32_t* __restrict__ obs,
+                    float* __restrict__ reward, uint8_t* __restrict__ flags, int32_t* __restrict__ reset_obs, int64_t n_groups,
+                    const SlipExtra ex)
+{
+    constexpr bool F64 = DRAW == kDrawF64;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ __align__(16) double prt[kPrtDoubles];
+    __shared__ uint8_t cacb[16], mv3[16];
+    __shared__ __align__(16) uint8_t klut[F64 ? 16 : (1 << kSlipLutBits)];
+    slip_build_prt(prt, P);
+    slip_fast_build_luts<F64>(cacb, mv3, klut, E);
+    stage_table_and_index(smem_raw, gtable, table_bytes, gfc, fc_bytes, &bar, P);
     TblCtx c = make_ctx(smem_raw, table_bytes, P);
     SlipCtx sc = { smem_u32(prt), slip_first_k(P) };
     SlipFast sf = { c.isd + 16u, smem_u32(cacb), smem_u32(mv3), smem_u32(klut) };
-    uint8_t* queue = smem_raw + table_bytes + 16 + fc_bytes;
+    const bool has_pol = ex.policy_a || ex.policy_b;
+    const uint32_t pol_total = has_pol ? 2u * (((uint32_t)P.nS + 15u) & ~15u) : 0u;
+    K1Policy pol = { 0u, 0u };
+    if (has_pol) pol = stage_k1_policies(smem_raw + table_bytes + 16 + fc_bytes, ex.policy_a, ex.policy_b, P.nS);
+    const bool flip = pol.pol_a != 0u;
+    uint8_t* queue = smem_raw + table_bytes + 16 + fc_bytes + pol_total;
     uint4* st4 = reinterpret_cast<uint4*>(state);
-    const uint32_t* a4 = reinterpret_cast<const uint32_t*>(act_a);
-    const uint32_t* b4 = reinterpret_cast<const uint32_t*>(act_b);
+    const uint8_t* act_a1 = act_a ? act_a : act_b;           // a folded player's stream does not exist: alias the other
+    const uint8_t* act_b1 = act_b ? act_b : act_a;
+    const uint32_t* a4 = reinterpret_cast<const uint32_t*>(act_a1);
+    const uint32_t* b4 = reinterpret_cast<const uint32_t*>(act_b1);
     const uint32_t* r4 = reinterpret_cast<const uint32_t*>(rng);
     uint4* o4 = reinterpret_cast<uint4*>(obs);
     uint4* w4 = reinterpret_cast<uint4*>(reward);
@@ -659,6 +862,7 @@ k_step_table_slip_q(const PitchDev P, const uint16_t* __restrict__ gtable, uint3
     wait_table(&bar);
     launder(c.tbl); launder(c.isd); launder(sc.prt);        // the relaxed loads below stay below the wait
     launder(sf.fc); launder(sf.cacb); launder(sf.mv3); launder(sf.klut);
+    launder(pol.pol_a); launder(pol.pol_b);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const uint32_t lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u;
     uint8_t* wq = queue + (threadIdx.x >> 5) * kSlipQueueWarp;   // this warp's queue: (half << 7 | lane << 2 | env) of the iteration
@@ -672,44 +876,29 @@ k_step_table_slip_q(const PitchDev P, const uint16_t* __restrict__ gtable, uint3
             const uint32_t idx = first + lane, id = wq[idx];
             const int64_t wb = idx < carry ? wbase_prev : wbase;
             const int64_t env = (wb + (int64_t)(id >> 7) * stride + ((id >> 2) & 31u)) * 4 + (id & 3u);
-            const uint32_t s = __ldcg(state + env), rg = rng[env];
-            const double ud = F64 ? reinterpret_cast<const double*>(draw)[env]
-                                  : u_from_rng32(reinterpret_cast<const uint32_t*>(draw)[env]);
-            const TblOut o = table_step_slip(c, sc, s, act_a[env], act_b[env], ud, rg & 0xCu);
-            state[env] = o.state; obs[env] = (int32_t)o.obs; reward[env] = (float)o.rew_i; flags[env] = (uint8_t)o.flags;
+            const uint32_t s = __ldcg(state + env);
+            uint32_t rg; double ud;
+            if (DRAW == kDrawPhilox) {
+                const uint32_t w = philox_word(ex.key.seed, ex.key.env_id_base + (uint64_t)env, ex.key.step);
+                rg = (w & 3u) << 2; ud = u_from_rng32(philox_r32(w));
+            } else {
+                rg = rng[env];
+                ud = F64 ? reinterpret_cast<const double*>(draw)[env] : u_from_rng32(reinterpret_cast<const uint32_t*>(draw)[env]);
+            }
+            uint32_t aa = act_a1[env], ab = act_b1[env];
+            const uint32_t cur = min(s & 0xFFFFu, c.last / 100u);
+            if (pol.pol_a) aa = lds_u8_r(pol.pol_a + cur);
+            if (pol.pol_b) ab = lds_u8_r(pol.pol_b + cur);
+            const TblOut o = table_step_slip(c, sc, s, aa, ab, ud, rg & 0xCu);
+            state[env] = o.state; obs[env] = (int32_t)o.obs; reward[env] = (float)(flip ? -o.rew_i : o.rew_i);
+            flags[env] = (uint8_t)o.flags;
             if (RESET_OBS) reset_obs[env] = (int32_t)o.reset_obs;
         }
     };
-    // one group of inputs: the state / action / draw words of 4 envs + their step draws
-    struct In { Group4 x; uint4 d0, d1; };
-    auto load_in = [&](int64_t g) {
-        In in;
-#if SOCCER_SLIP_PLAIN_LOADS
-        // evict-normal loads: the walk re-reads the deferred envs' inputs a few microseconds later
-        in.x.s = ld_keep(st4 + g); in.x.a = a4[g]; in.x.b = b4[g]; in.x.r = r4[g];
-        if (F64) {
-            in.d0 = reinterpret_cast<const uint4*>(draw)[2 * g];
-            in.d1 = reinterpret_cast<const uint4*>(draw)[2 * g + 1];
-        } else {
-            in.d0 = reinterpret_cast<const uint4*>(draw)[g];
-            in.d1 = in.d0;
-        }
-#else
-        in.x = load_group(st4, a4, b4, r4, g);
-        if (F64) {
-            in.d0 = __ldcs(reinterpret_cast<const uint4*>(draw) + 2 * g);
-            in.d1 = __ldcs(reinterpret_cast<const uint4*>(draw) + 2 * g + 1);
-        } else {
-            in.d0 = __ldcs(reinterpret_cast<const uint4*>(draw) + g);
-            in.d1 = in.d0;
-        }
-#endif
-        return in;
-    };
     int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool valid = g < n_groups;
-    In cur = {};
-    if (valid) cur = load_in(g);
+    SlipIn cur = {};
+    if (valid) cur = slip_load_in<DRAW, SOCCER_SLIP_PLAIN_LOADS != 0>(st4, a4, b4, r4, draw, g);
     for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < n_groups; base += 2 * stride) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -717,8 +906,9 @@ k_step_table_slip_q(const PitchDev P, const uint16_t* __restrict__ gtable, uint3
             // shared-memory look-up chains of the current one)
             const int64_t gn = g + stride;
             const bool validn = gn < n_groups;
-            In nxt = cur;
-            if (validn) nxt = load_in(gn);
+            SlipIn nxt = cur;
+            if (validn) nxt = slip_load_in<DRAW, SOCCER_SLIP_PLAIN_LOADS != 0>(st4, a4, b4, r4, draw, gn);
+            if (DRAW == kDrawPhilox && valid) slip_philox_fill(cur, ex.key, g);
             const Group4 x = cur.x;
             double u[4] = { 0.0, 0.0, 0.0, 0.0 };
             uint32_t r32[4] = { cur.d0.x, cur.d0.y, cur.d0.z, cur.d0.w };
@@ -732,12 +922,17 @@ k_step_table_slip_q(const PitchDev P, const uint16_t* __restrict__ gtable, uint3
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 bool defer;
-                const TblOut o = table_step_slip_fast<F64>(c, sf, E, sv[e], __byte_perm(x.a, 0, 0x4440 + e),
-                                                           __byte_perm(x.b, 0, 0x4440 + e), u[e], r32[e],
+                uint32_t aa = __byte_perm(x.a, 0, 0x4440 + e), ab = __byte_perm(x.b, 0, 0x4440 + e);
+                if (pol.pol_a | pol.pol_b) {                 // warp-uniform
+                    const uint32_t cs = min(sv[e] & 0xFFFFu, c.last / 100u);
+                    if (pol.pol_a) aa = lds_u8_r(pol.pol_a + cs);
+                    if (pol.pol_b) ab = lds_u8_r(pol.pol_b + cs);
+                }
+                const TblOut o = table_step_slip_fast<F64>(c, sf, E, sv[e], aa, ab, u[e], r32[e],
                                                            __byte_perm(rs4, 0, 0x4440 + e), defer);
                 defer &= valid;
                 so[e] = defer ? sv[e] : o.state;             // deferred: the ORIGINAL state stays for the walk to read
-                oo[e] = o.obs; rr[e] = __float_as_uint((float)o.rew_i); ro[e] = o.reset_obs; ff[e] = o.flags;
+                oo[e] = o.obs; rr[e] = __float_as_uint((float)(flip ? -o.rew_i : o.rew_i)); ro[e] = o.reset_obs; ff[e] = o.flags;
                 const uint32_t m = __ballot_sync(0xFFFFFFFFu, defer);
                 if (defer) wq[cnt + __popc(m & lt_mask)] = (uint8_t)((h << 7) | (lane << 2) | e);
                 cnt += __popc(m);
@@ -787,15 +982,26 @@ k_step_table_slip_scalar(const PitchDev P, const uint16_t* __restrict__ gtable, 
                          const uint8_t* __restrict__ act_a, const uint8_t* __restrict__ act_b,
                          const uint8_t* __restrict__ rng, const uint32_t* __restrict__ rng32,
                          const double* __restrict__ rngf64, int32_t* __restrict__ obs, float* __restrict__ reward,
-                         uint8_t* __restrict__ flags, int32_t* __restrict__ reset_obs, int64_t n)
+                         uint8_t* __restrict__ flags, int32_t* __restrict__ reset_obs, int64_t n, int use_philox,
+                         const SlipExtra ex)
 {
     const uint32_t last_row = (uint32_t)P.nS - 1u;
+    const bool flip = ex.policy_a != nullptr;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const uint32_t s = state[i], rg = rng[i];
-        const LdGlobal ld = { reinterpret_cast<const uint8_t*>(gtable) + (size_t)min(s & 0xFFFFu, last_row) * 200u };
-        const double u = rngf64 ? rngf64[i] : u_from_rng32(rng32[i]);
-        const uint32_t pick = slip_pick(P, ld, act_a[i], act_b[i], u);
+        const uint32_t s = state[i];
+        uint32_t rg; double u;
+        if (use_philox) {
+            const uint32_t w = philox_word(ex.key.seed, ex.key.env_id_base + (uint64_t)i, ex.key.step);
+            rg = (w & 3u) << 2; u = u_from_rng32(philox_r32(w));
+        } else {
+            rg = rng[i]; u = rngf64 ? rngf64[i] : u_from_rng32(rng32[i]);
+        }
+        const uint32_t cur = min(s & 0xFFFFu, last_row);
+        const LdGlobal ld = { reinterpret_cast<const uint8_t*>(gtable) + (size_t)cur * 200u };
+        const uint32_t aa = ex.policy_a ? (uint32_t)min(max((int)ex.policy_a[cur], 0), 4) : (uint32_t)act_a[i];
+        const uint32_t ab = ex.policy_b ? (uint32_t)min(max((int)ex.policy_b[cur], 0), 4) : (uint32_t)act_b[i];
+        const uint32_t pick = slip_pick(P, ld, aa, ab, u);
         const int32_t e = (int32_t)(int16_t)ld(pick);
         const uint32_t nobs = (uint32_t)e & kTblObsMask;
         const bool done = nobs == 0;
@@ -804,7 +1010,7 @@ k_step_table_slip_scalar(const PitchDev P, const uint16_t* __restrict__ gtable, 
         const uint32_t ro = (uint32_t)P.isd_obs[(rg >> 2) & 3u];
         state[i] = reset ? ro : ((s1 & 0xFFFF0000u) | nobs);
         obs[i] = (int32_t)nobs;
-        reward[i] = (float)(e >> 14);
+        reward[i] = (float)(flip ? -(e >> 14) : (e >> 14));
         flags[i] = (uint8_t)((done ? 1u : 0u) + (trunc ? 2u : 0u));
         if (reset_obs) reset_obs[i] = (int32_t)(reset ? ro : nobs);
     }

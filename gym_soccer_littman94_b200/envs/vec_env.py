@@ -41,9 +41,14 @@ class SoccerVecEnv:
       rng_mode   "injected": the caller passes the draws (bit-exact replay of the reference);
                  "philox":   Philox4x32-10 keyed (seed, env_id_base + i, step)
       kernel     "rules": rules evaluated inline (any pitch / option);
-                 "table": transition table resident in shared memory (5x4 and 6x4 pitches, no folded policy);
+                 "table": transition table resident in shared memory (5x4 and 6x4 pitches; multi-agent or
+                          single-agent with the folded player's table policy next to the table);
                  "auto":  table when it applies, else rules
-      env_id_base  global id of env 0 (rank * envs_per_rank when sharded over GPUs)
+      env_id_base  global id of env 0 (rank * envs_per_rank when sharded over GPUs; a multiple of 4 keeps the
+                   Philox kernels on their 4-envs-per-thread path, see include/soccer_b200.h)
+
+    Pitch limit of this library (the reference has none): width * height <= 126 and height <= 16 -- one-byte cell
+    codes and 16-bit observation lanes in the kernels; larger pitches raise ValueError.
     """
 
     def __init__(self, num_envs: int, width: int = 5, height: int = 4, slip_prob: float = 0.0,
@@ -55,6 +60,9 @@ class SoccerVecEnv:
         assert width >= 5, "Width must be at least 5 columns."                       # SIM:45
         assert height >= 4, "Height must be at least 4 rows."                        # SIM:46
         assert rng_mode in ("injected", "philox") and kernel in ("auto", "rules", "table")
+        if int(width) * int(height) > 126 or int(height) > 16:
+            raise ValueError(f"pitch {width}x{height} is beyond this library's limit (width * height <= 126, height <= 16: "
+                             "one-byte cell codes, 16-bit observation lanes); the reference itself has no upper limit")
         self.lib = _lib.lib()
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -81,10 +89,12 @@ class SoccerVecEnv:
         self._plain = self.rng_mode == "injected" and self.multiagent and self.slip_prob == 0.0
 
         _nb = C.c_int64()
-        table_ok = self.multiagent and self.lib.soccer_step_table_bytes_host(C.byref(self.pitch), C.byref(_nb)) == 0
+        table_ok = self.lib.soccer_step_table_bytes_host(C.byref(self.pitch), C.byref(_nb)) == 0
+        if table_ok and not self.multiagent:                 # the folded policies ride next to the table (6x4: no room)
+            table_ok = _nb.value + 16 + 2 * ((self.nS + 15) & ~15) <= 227 * 1024 - 1024
         if kernel == "table" and not table_ok:
-            raise _lib.SoccerB200Error("kernel='table' needs no folded policy and a table that fits shared memory "
-                                       "(5x4 and 6x4 pitches)")
+            raise _lib.SoccerB200Error("kernel='table' needs a table that fits shared memory (5x4 and 6x4 pitches; "
+                                       "5x4 with a folded policy)")
         # "auto": the table kernel pays a 152 KB shared-memory fill per CTA per launch, which only
         # amortises over large batches; small batches are launch-latency bound either way
         if kernel == "auto":
@@ -132,13 +142,26 @@ class SoccerVecEnv:
         assert t.numel() == self.nS, "a table policy needs one action per observation index"
         return t.to(self.device).contiguous()
 
-    def _check_vec(self, t, dtype, name):
+    def _check_vec(self, t, dtype, name, host=False):
+        """A [num_envs] stream the kernels read or write through its raw pointer: dtype, device, contiguity and
+        length are checked here because the C ABI cannot (a strided row or a wrong dtype would be an out-of-bounds
+        device access).  host=True: a PINNED CPU tensor instead (zero copy: the kernel moves it over PCIe)."""
         if t is None:
             return None
-        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == dtype and t.is_contiguous()
-                and t.numel() == self.num_envs):
-            raise ValueError(f"{name} must be a contiguous {dtype} CUDA tensor with {self.num_envs} elements")
+        ok = isinstance(t, torch.Tensor) and t.dtype == dtype and t.is_contiguous() and t.numel() == self.num_envs
+        if ok and host:
+            ok = (not t.is_cuda) and t.is_pinned()
+        elif ok:
+            ok = t.is_cuda and t.device == self.device
+        if not ok:
+            where = "pinned CPU" if host else f"CUDA ({self.device})"
+            raise ValueError(f"{name} must be a contiguous {dtype} {where} tensor with {self.num_envs} elements")
         return t
+
+    def _check_out(self, out, host=False):
+        obs, reward, flags, reset_obs = out
+        return (self._check_vec(obs, torch.int32, "out obs", host), self._check_vec(reward, torch.float32, "out reward", host),
+                self._check_vec(flags, torch.uint8, "out flags", host), self._check_vec(reset_obs, torch.int32, "out reset_obs", host))
 
     def _to_layout(self):
         if self.layout == LAYOUT_INDEX:
@@ -194,23 +217,30 @@ class SoccerVecEnv:
 
     def step(self, act_a: Optional[torch.Tensor], act_b: Optional[torch.Tensor] = None,
              rng8: Optional[torch.Tensor] = None, rng32: Optional[torch.Tensor] = None,
-             rngf64: Optional[torch.Tensor] = None, out=None, detail: bool = False, auto_reset: bool = True):
+             rngf64: Optional[torch.Tensor] = None, out=None, detail: bool = False, auto_reset: bool = True,
+             stats: Optional[torch.Tensor] = None, _host: bool = False):
         """One lock-step step() of all envs (SIM:375-408) + fused reset (SIM:410-424).
 
         Returns (obs, reward, flags, reset_obs) device tensors: obs is what the reference's
         step() returned (0 on a goal), reward the first return agent's reward, flags bit 0
         terminated / bit 1 truncated, reset_obs the observation the next step starts from.
         `out` may supply the four output tensors (e.g. rows of a [T, N] buffer).
+        `stats` (int64[6] CUDA tensor): accumulate this step's episode statistics inside the step kernel
+        ([episodes, goals_A, goals_B, truncations, steps, sum_episode_len], the vector rollout() returns).
         """
-        obs, reward, flags, reset_obs = out if out is not None else (self.obs, self.reward, self.flags, self.reset_obs)
+        if out is not None:
+            obs, reward, flags, reset_obs = self._check_out(out, _host)
+        else:
+            obs, reward, flags, reset_obs = self.obs, self.reward, self.flags, self.reset_obs
         if self.num_envs == 0:
             return obs, reward, flags, reset_obs
         # fast host path for the plain lock-step step (injected draws, slip 0, no folded policy, no options): small
         # batches are bound by this Python code, so it makes one ctypes call with integer pointers and nothing else
-        if self._plain and auto_reset and not detail and rng32 is None and rngf64 is None \
+        if self._plain and auto_reset and not detail and rng32 is None and rngf64 is None and stats is None \
                 and act_a is not None and act_b is not None and rng8 is not None \
                 and torch.cuda.current_device() == self.device.index:
-            cv, u8 = self._check_vec, torch.uint8
+            u8 = torch.uint8
+            cv = lambda t, d, nm: self._check_vec(t, d, nm, _host)      # noqa: E731
             st = torch.cuda.current_stream(self.device).cuda_stream
             ro = None if reset_obs is None else reset_obs.data_ptr()
             if self.kernel == "table":
@@ -227,63 +257,64 @@ class SoccerVecEnv:
                 check(rc, "soccer_step")
             self.step_count += 1
             return obs, reward, flags, reset_obs
+        cv = lambda t, d, nm: self._check_vec(t, d, nm, _host)          # noqa: E731
+        if stats is not None and not (isinstance(stats, torch.Tensor) and stats.is_cuda and stats.dtype == torch.int64
+                                      and stats.is_contiguous() and stats.numel() >= 6):
+            raise ValueError("stats must be a contiguous int64 CUDA tensor with 6 elements")
         with torch.cuda.device(self.device):
             st = _stream(self.device)
             philox = self.rng_mode == "philox"
-            general = philox or detail or not auto_reset          # options only the generic rules kernel offers
-            if self.kernel == "table" and philox and self.multiagent and self.slip_prob == 0.0 and auto_reset and not detail:
-                # caller-supplied actions + Philox draws through the shared-memory table (19 B / env-step)
-                check(self.lib.soccer_step_table_philox(
-                    C.byref(self.pitch), _ptr(self.table), _ptr(self.state),
-                    _ptr(self._check_vec(act_a, torch.uint8, "act_a")), _ptr(self._check_vec(act_b, torch.uint8, "act_b")),
-                    self.seed, self.step_count, self.env_id_base, _ptr(obs), _ptr(reward), _ptr(flags), _ptr(reset_obs),
-                    self.num_envs, st), "soccer_step_table_philox")
-            elif self.kernel == "table" and not general:
-                args = (C.byref(self.pitch), _ptr(self.table), _ptr(self.state),
-                        _ptr(self._check_vec(act_a, torch.uint8, "act_a")), _ptr(self._check_vec(act_b, torch.uint8, "act_b")),
-                        _ptr(self._check_vec(rng8, torch.uint8, "rng8")))
-                outs = (_ptr(obs), _ptr(reward), _ptr(flags), _ptr(reset_obs), self.num_envs, st)
-                if self.slip_prob != 0.0:
-                    if rng32 is None and rngf64 is None:
-                        raise ValueError("slip_prob > 0 needs the step draw: rng32 (int32/uint32 bits) or rngf64")
-                    use_index = self.slip_index is not None and os.environ.get("SOCCER_B200_SLIP_WALK", "0") != "1"
-                    check(self.lib.soccer_step_table_slip(
-                        args[0], args[1], _ptr(self.slip_index if use_index else None), *args[2:],
-                        _ptr(None if rngf64 is not None else self._check_vec(rng32, torch.int32, "rng32")),
-                        _ptr(self._check_vec(rngf64, torch.float64, "rngf64")), *outs), "soccer_step_table_slip")
-                else:
-                    check(self.lib.soccer_step_table(*args, *outs), "soccer_step_table")
-            else:
-                # a table env keeps INDEX-layout states: the generic kernel runs on a CELL-layout copy
-                state = self.state
-                if self.kernel == "table":
-                    if not auto_reset:
-                        raise NotImplementedError("kernel='table' states cannot hold needs_reset; use kernel='rules' "
-                                                  "for auto_reset=False")
-                    state = torch.empty_like(self.state)
-                    check(self.lib.soccer_convert_state(C.byref(self.pitch), _ptr(self.state), _ptr(state), LAYOUT_CELL,
-                                                        self.num_envs, st), "soccer_convert_state")
-                a = StepArgs()
-                a.state = state.data_ptr()
-                a.act_a = None if self.policy_a is not None else self._check_vec(act_a, torch.uint8, "act_a").data_ptr()
-                a.act_b = None if self.policy_b is not None else self._check_vec(act_b, torch.uint8, "act_b").data_ptr()
-                if not philox:
-                    a.rng8 = self._check_vec(rng8, torch.uint8, "rng8").data_ptr()
-                a.rng32 = None if rng32 is None else self._check_vec(rng32, torch.int32, "rng32").data_ptr()
-                a.rngf64 = None if rngf64 is None else self._check_vec(rngf64, torch.float64, "rngf64").data_ptr()
-                a.policy_a = None if self.policy_a is None else self.policy_a.data_ptr()
-                a.policy_b = None if self.policy_b is None else self.policy_b.data_ptr()
-                a.obs, a.reward, a.flags = obs.data_ptr(), reward.data_ptr(), flags.data_ptr()
-                a.reset_obs = None if reset_obs is None else reset_obs.data_ptr()
-                a.n = self.num_envs
-                a.auto_reset = 1 if auto_reset else 0
-                a.use_philox = 1 if philox else 0
-                a.detail = 1 if detail else 0
-                a.seed, a.step, a.env_id_base = self.seed, self.step_count, self.env_id_base
-                check(self.lib.soccer_step_ex(C.byref(self.pitch), C.byref(a), st), "soccer_step_ex")
-                if self.kernel == "table":
-                    check(self.lib.soccer_convert_state(C.byref(self.pitch), _ptr(state), _ptr(self.state), LAYOUT_INDEX,
-                                                        self.num_envs, st), "soccer_convert_state")
+            # the table kernels serve everything but the per-outcome detail flags and auto_reset=False (an INDEX-layout
+            # state cannot hold needs_reset); fused statistics are not offered together with slip_prob > 0 there
+            on_table = self.kernel == "table" and not detail and auto_reset
+            fused_stats = stats is not None and not (on_table and self.slip_prob != 0.0)
+            state = self.state
+            if self.kernel == "table" and not on_table:
+                if not auto_reset:
+                    raise NotImplementedError("kernel='table' states cannot hold needs_reset; use kernel='rules' "
+                                              "for auto_reset=False")
+                # a table env keeps INDEX-layout states: the generic rules kernel runs on a CELL-layout copy
+                state = torch.empty_like(self.state)
+                check(self.lib.soccer_convert_state(C.byref(self.pitch), _ptr(self.state), _ptr(state), LAYOUT_CELL,
+                                                    self.num_envs, st), "soccer_convert_state")
+            a = StepArgs()
+            a.state = state.data_ptr()
+            a.act_a = None if self.policy_a is not None else cv(act_a, torch.uint8, "act_a").data_ptr()
+            a.act_b = None if self.policy_b is not None else cv(act_b, torch.uint8, "act_b").data_ptr()
+            if not philox:
+                a.rng8 = cv(rng8, torch.uint8, "rng8").data_ptr()
+                if self.slip_prob != 0.0 and rng32 is None and rngf64 is None:
+                    raise ValueError("slip_prob > 0 needs the step draw: rng32 (int32/uint32 bits) or rngf64")
+                if rngf64 is not None:
+                    a.rngf64 = cv(rngf64, torch.float64, "rngf64").data_ptr()
+                elif rng32 is not None:
+                    a.rng32 = cv(rng32, torch.int32, "rng32").data_ptr()
+            a.policy_a = None if self.policy_a is None else self.policy_a.data_ptr()
+            a.policy_b = None if self.policy_b is None else self.policy_b.data_ptr()
+            a.obs, a.reward, a.flags = obs.data_ptr(), reward.data_ptr(), flags.data_ptr()
+            a.reset_obs = None if reset_obs is None else reset_obs.data_ptr()
+            a.n = self.num_envs
+            a.auto_reset = 1 if auto_reset else 0
+            a.use_philox = 1 if philox else 0
+            a.detail = 1 if detail else 0
+            a.seed, a.step, a.env_id_base = self.seed, self.step_count, self.env_id_base
+            a.stats = stats.data_ptr() if fused_stats else None
+            if on_table:
+                a.table = self.table.data_ptr()
+                use_index = self.slip_index is not None and os.environ.get("SOCCER_B200_SLIP_WALK", "0") != "1"
+                a.slip_index = self.slip_index.data_ptr() if use_index else None
+            check(self.lib.soccer_step_ex(C.byref(self.pitch), C.byref(a), st), "soccer_step_ex")
+            if state is not self.state:
+                check(self.lib.soccer_convert_state(C.byref(self.pitch), _ptr(state), _ptr(self.state), LAYOUT_INDEX,
+                                                    self.num_envs, st), "soccer_convert_state")
+            if stats is not None and not fused_stats:
+                # separate pass over the streams (counts goals by the sign of the STREAMED reward: swap them back for a
+                # player_b env, whose reward stream is negated; sum_episode_len is not available here)
+                tmp = torch.zeros(6, dtype=torch.int64, device=self.device)
+                check(self.lib.soccer_step_stats(_ptr(flags), _ptr(reward), self.num_envs, _ptr(tmp), st), "soccer_step_stats")
+                if self.policy_a is not None:
+                    tmp = tmp[[0, 2, 1, 3, 4, 5]]
+                stats[:6] += tmp
         self.step_count += 1
         return obs, reward, flags, reset_obs
 
@@ -432,8 +463,10 @@ class SoccerVecEnv:
     # (profiles/r01g_time_host_paths.log)
     ZERO_COPY_MAX_ENVS = 1 << 23
 
-    def step_host(self, act_a: torch.Tensor, act_b: torch.Tensor, rng8: torch.Tensor, narrow: bool = False,
-                  n_chunks: int = 8, sync: bool = True, zero_copy: Optional[bool] = None):
+    def step_host(self, act_a: Optional[torch.Tensor], act_b: Optional[torch.Tensor] = None,
+                  rng8: Optional[torch.Tensor] = None, narrow: bool = False, n_chunks: int = 8, sync: bool = True,
+                  zero_copy: Optional[bool] = None, rng32: Optional[torch.Tensor] = None,
+                  rngf64: Optional[torch.Tensor] = None):
         """step() with HOST buffers -- the end-to-end path bench.py reports as `e2e`.
 
         In: uint8 CPU tensors (pinned memory keeps the copies asynchronous).  Out: CPU tensors
@@ -443,9 +476,24 @@ class SoccerVecEnv:
         kernel and download overlap on three streams (soccer_step_host in the C ABI).  Batches of up to
         ZERO_COPY_MAX_ENVS envs with pinned inputs skip the staging: the kernel (wide or fused-narrow outputs) reads
         and writes the pinned host buffers directly (zero_copy=None: automatic).  alloc_host_inputs() hands out
-        input buffers from huge-page-backed pinned memory."""
-        if self.slip_prob != 0.0 or not self.multiagent or self.rng_mode != "injected":
-            raise NotImplementedError("step_host covers the multi-agent, slip_prob == 0, injected-draw step")
+        input buffers from huge-page-backed pinned memory.
+
+        Every other mode of the env -- slip_prob > 0 (rng32 / rngf64 host tensors carry the step draw), the
+        single-agent modes (the folded player's action tensor is None) and rng_mode='philox' (no draw tensors at all)
+        -- runs zero copy with the natural dtypes: the step kernel of that mode reads the pinned input tensors and
+        writes pinned int32 / float32 / uint8 result tensors itself, one launch and one synchronize per step."""
+        if not self._plain:
+            if narrow:
+                raise NotImplementedError("narrow host streams exist for the plain step only (multi-agent, slip 0, injected)")
+            common, hb = self._host_buffers(False)
+            if self.num_envs == 0:
+                return hb["h_obs"], hb["h_reward"], common["h_flags"]
+            cur = torch.cuda.current_stream(self.device)
+            self.step(act_a, act_b, rng8, rng32=rng32, rngf64=rngf64,
+                      out=(hb["h_obs"], hb["h_reward"], common["h_flags"], None), _host=True)
+            if sync:
+                cur.synchronize()
+            return hb["h_obs"], hb["h_reward"], common["h_flags"]
         for name, t in (("act_a", act_a), ("act_b", act_b), ("rng8", rng8)):
             if not (isinstance(t, torch.Tensor) and not t.is_cuda and t.dtype == torch.uint8 and t.is_contiguous()
                     and t.numel() == self.num_envs):
@@ -510,14 +558,25 @@ class SoccerVecEnv:
         return w & 0xFFF, (w >> 14).to(torch.float32), (w >> 12) & 1 != 0, (w >> 13) & 1 != 0
 
     def _check_packed(self):
-        if self.kernel != "table" or self.slip_prob != 0.0 or self.rng_mode != "injected":
-            raise NotImplementedError("the packed step needs kernel='table' (5x4 / 6x4 pitch), slip_prob == 0 and "
-                                      "injected draws")
+        if self.kernel != "table" or self.slip_prob != 0.0 or not self.multiagent:
+            raise NotImplementedError("the packed step needs kernel='table' (5x4 / 6x4 pitch), slip_prob == 0 and the "
+                                      "multi-agent mode")
 
-    def step_packed(self, joint: torch.Tensor, rng8: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def _packed_call(self, joint_ptr, rng8_ptr, res_ptr, stream):
+        """soccer_step_table_packed, or soccer_step_table_packed_philox for rng_mode='philox' (no draw stream)."""
+        if self.rng_mode == "philox":
+            check(self.lib.soccer_step_table_packed_philox(C.byref(self.pitch), _ptr(self.table), _ptr(self.state), joint_ptr,
+                                                           self.seed, self.step_count, self.env_id_base, res_ptr,
+                                                           self.num_envs, stream), "soccer_step_table_packed_philox")
+        else:
+            check(self.lib.soccer_step_table_packed(C.byref(self.pitch), _ptr(self.table), _ptr(self.state), joint_ptr,
+                                                    rng8_ptr, res_ptr, self.num_envs, stream), "soccer_step_table_packed")
+
+    def step_packed(self, joint: torch.Tensor, rng8: Optional[torch.Tensor] = None,
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """step() on device tensors with packed streams (soccer_step_table_packed): joint = aa | ab << 4 (uint8),
-        rng8 as in step(); returns the int16 result words (see unpack_result).  Same transition, reward, flags and
-        fused reset as step(); 12 instead of 20 bytes of HBM traffic per env-step."""
+        rng8 as in step() (None with rng_mode='philox'); returns the int16 result words (see unpack_result).  Same
+        transition, reward, flags and fused reset as step(); 12 instead of 20 bytes of HBM traffic per env-step."""
         self._check_packed()
         if out is None:
             if getattr(self, "_result16", None) is None:
@@ -525,21 +584,24 @@ class SoccerVecEnv:
             out = self._result16
         if self.num_envs == 0:
             return out
+        philox = self.rng_mode == "philox"
         with torch.cuda.device(self.device):
-            check(self.lib.soccer_step_table_packed(
-                C.byref(self.pitch), _ptr(self.table), _ptr(self.state), _ptr(self._check_vec(joint, torch.uint8, "joint")),
-                _ptr(self._check_vec(rng8, torch.uint8, "rng8")), _ptr(self._check_vec(out, torch.int16, "out")),
-                self.num_envs, _stream(self.device)), "soccer_step_table_packed")
+            self._packed_call(_ptr(self._check_vec(joint, torch.uint8, "joint")),
+                              None if philox else _ptr(self._check_vec(rng8, torch.uint8, "rng8")),
+                              _ptr(self._check_vec(out, torch.int16, "out")), _stream(self.device))
         self.step_count += 1
         return out
 
-    def step_host_packed(self, joint: torch.Tensor, rng8: torch.Tensor, n_chunks: int = 8, sync: bool = True,
-                         zero_copy: Optional[bool] = None) -> torch.Tensor:
+    def step_host_packed(self, joint: torch.Tensor, rng8: Optional[torch.Tensor] = None, n_chunks: int = 8,
+                         sync: bool = True, zero_copy: Optional[bool] = None) -> torch.Tensor:
         """step_host() with packed streams: 2 bytes up (joint action byte, draw byte) and 2 bytes down (one int16
         result word, see unpack_result) per env over PCIe instead of 3 + 4.  Returns a pinned CPU int16 tensor owned
-        by the env and overwritten by the next call."""
+        by the env and overwritten by the next call.  rng_mode='philox': no draw stream -- 1 byte up, 2 down."""
         self._check_packed()
-        for name, t in (("joint", joint), ("rng8", rng8)):
+        philox = self.rng_mode == "philox"
+        if philox:
+            rng8, zero_copy = None, True
+        for name, t in (("joint", joint),) + (() if philox else (("rng8", rng8),)):
             if not (isinstance(t, torch.Tensor) and not t.is_cuda and t.dtype == torch.uint8 and t.is_contiguous()
                     and t.numel() == self.num_envs):
                 raise ValueError(f"{name} must be a contiguous uint8 CPU tensor with {self.num_envs} elements")
@@ -552,15 +614,15 @@ class SoccerVecEnv:
         if zero_copy is None:
             zero_copy = True
         with torch.cuda.device(self.device):
-            if zero_copy and joint.is_pinned() and rng8.is_pinned():
+            if zero_copy and joint.is_pinned() and (philox or rng8.is_pinned()):
                 cur = torch.cuda.current_stream(self.device)
-                check(self.lib.soccer_step_table_packed(C.byref(self.pitch), _ptr(self.table), _ptr(self.state), _ptr(joint),
-                                                        _ptr(rng8), _ptr(h_res), self.num_envs, C.c_void_p(cur.cuda_stream)),
-                      "soccer_step_table_packed")
+                self._packed_call(_ptr(joint), _ptr(rng8), _ptr(h_res), C.c_void_p(cur.cuda_stream))
                 self.step_count += 1
                 if sync:
                     cur.synchronize()
                 return h_res
+            if philox:
+                raise ValueError("step_host_packed with rng_mode='philox' needs a pinned joint tensor (alloc_host_inputs)")
             s_in, s_k, s_out = common["streams"]
             cur = torch.cuda.current_stream(self.device)
             s_k.wait_stream(cur)
@@ -582,11 +644,18 @@ class SoccerVecEnv:
         """K fused steps with on-device Philox draws and a uniform or table policy (K2).
 
         Returns (obs[K,N], reward[K,N], flags[K,N], stats[6]); stats accumulates
-        [episodes, goals_A, goals_B, truncations, steps, sum_episode_len].
+        [episodes, goals_A, goals_B, truncations, steps, sum_episode_len].  The reward stream is the env's return
+        agent's, exactly what step() returns: player B's (negated) for an env constructed with player_a_policy
+        (SIM:243-244); goals_A / goals_B always count by player A's sign.
         """
         n, dev = self.num_envs, self.device
+        K = int(K)
         if out is not None:
             obs, reward, flags = out
+            for name, t, dt in (("obs", obs, torch.int32), ("reward", reward, torch.float32), ("flags", flags, torch.uint8)):
+                if t is not None and not (isinstance(t, torch.Tensor) and t.is_cuda and t.device == dev and t.dtype == dt
+                                          and t.is_contiguous() and t.numel() == K * n):
+                    raise ValueError(f"out {name} must be a contiguous {dt} CUDA tensor of shape ({K}, {n})")
         elif want_streams:
             obs = torch.empty((K, n), dtype=torch.int32, device=dev)
             reward = torch.empty((K, n), dtype=torch.float32, device=dev)
@@ -597,18 +666,20 @@ class SoccerVecEnv:
             stats = torch.zeros(6, dtype=torch.int64, device=dev)
         pa = self._policy_tensor(policy_a) if policy_a is not None else self.policy_a
         pb = self._policy_tensor(policy_b) if policy_b is not None else self.policy_b
+        flip = 1 if self.policy_a is not None else 0          # the env's return agent is player_b (SIM:243-244)
         if n == 0 or K == 0:
             return obs, reward, flags, stats
         with torch.cuda.device(dev):
             st = _stream(dev)
             if self.kernel == "table":
+                use_index = self.slip_index is not None and os.environ.get("SOCCER_B200_SLIP_WALK", "0") != "1"
                 check(self.lib.soccer_rollout_table_policy(
-                    C.byref(self.pitch), _ptr(self.table), _ptr(self.state), _ptr(pa), _ptr(pb), self.seed,
-                    self.step_count, int(K), self.env_id_base, _ptr(obs), _ptr(reward), _ptr(flags), _ptr(stats), n, st),
-                    "soccer_rollout_table_policy")
+                    C.byref(self.pitch), _ptr(self.table), _ptr(self.slip_index if use_index else None), _ptr(self.state),
+                    _ptr(pa), _ptr(pb), self.seed, self.step_count, K, self.env_id_base, flip, _ptr(obs), _ptr(reward),
+                    _ptr(flags), _ptr(stats), n, st), "soccer_rollout_table_policy")
             else:
                 check(self.lib.soccer_rollout(C.byref(self.pitch), _ptr(self.state), _ptr(pa), _ptr(pb), self.seed,
-                                              self.step_count, int(K), self.env_id_base, _ptr(obs), _ptr(reward),
+                                              self.step_count, K, self.env_id_base, flip, _ptr(obs), _ptr(reward),
                                               _ptr(flags), _ptr(stats), n, st), "soccer_rollout")
-        self.step_count += int(K)
+        self.step_count += K
         return obs, reward, flags, stats

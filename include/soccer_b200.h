@@ -10,9 +10,11 @@
  *
  * Conventions
  *   - Every pointer named in a kernel call is a DEVICE pointer into caller-owned memory
- *     (e.g. a torch tensor's data_ptr()).  The library never allocates, keeps no global
- *     state, and is re-entrant across streams.  Entry points ending in _host() are pure
- *     host helpers and need no GPU.
+ *     (e.g. a torch tensor's data_ptr()).  Kernel entry points never allocate, keep no global
+ *     state, and are re-entrant across streams.  The one exception is the pinned-host-memory pair
+ *     soccer_host_alloc / soccer_host_free: it allocates (mmap + cudaHostRegister, or cudaHostAlloc)
+ *     and keeps a mutex-protected set of the allocations that took the cudaHostAlloc fallback.
+ *     Entry points ending in _host() are pure host helpers and need no GPU.
  *   - Every kernel call is asynchronous on `stream` (a cudaStream_t / CUstream).
  *   - Return value: 0 = OK, negative = argument error (SOCCER_E*), positive = cudaError_t.
  *   - There is no CPU fallback: without a CUDA device kernel calls return a cudaError_t.
@@ -37,10 +39,16 @@
  *   rng32 : step draw for slip_prob > 0, u = (r + 0.5)/2^32
  *   rngf64: step draw for slip_prob > 0 as the raw fp64 uniform the reference's
  *           np_random.random() returned (SIM:395)
- * Counter-based randomness: Philox4x32-10, key = seed, counter = (env_id, step >> 2),
- *   output word step & 3:  jr = mulhi(w, 100) = (w * 100) >> 32 is uniform on 0..99 and carries
- *   the joint action and the step draw at once: ja = jr >> 2, aa = ja / 5, ab = ja % 5, step draw
- *   = jr & 3;  the two lowest bits of w = reset draw.
+ * Counter-based randomness (contract v2): Philox4x32-10, key = seed, counter = (group, step) with
+ *   group = global env id >> 2; the env's word w is output word (env id & 3) -- one call serves the 4
+ *   envs of an aligned group at one step, a pure function of (seed, global env id, step).  Decode,
+ *   reading w as the fixed-point number x = w / 2^32:
+ *     joint action ja = floor(25 x) = mulhi(w, 25), aa = ja / 5, ab = ja % 5;
+ *     step draw    r32 = frac(25 x) * 2^32 = lo32(25 w): u = (r32 + 0.5) / 2^32, exactly the rng32
+ *                  format (slip_prob == 0 uses its top two bits: mulhi(w, 100) = ja * 4 + (r32 >> 30));
+ *     reset draw   w & 3.
+ *   Kernels that own 4 envs per thread need env_id_base % 4 == 0 to take their vector path (other
+ *   bases fall to the one-env-per-thread kernels; same results).
  *
  * flags byte: bit 0 terminated (SIM:403), bit 1 truncated (SIM:404).  Only when
  *   soccer_step_args.detail != 0: bits 2..3 = log2(number of outcomes the chosen slip
@@ -65,11 +73,12 @@
 extern "C" {
 #endif
 
-#define SOCCER_ABI_VERSION 1
+#define SOCCER_ABI_VERSION 2   /* 2: Philox contract v2, soccer_step_args.{stats,table,slip_index}, rollout flip_reward / slip_index */
 
 #define SOCCER_OK        0
 #define SOCCER_EINVAL   (-1)  /* NULL where a pointer is required, n < 0, bad option */
-#define SOCCER_EPITCH   (-2)  /* width < 5, height < 4 (SIM:45-46) or width*height > 126 / height > 16 */
+#define SOCCER_EPITCH   (-2)  /* width < 5, height < 4 (SIM:45-46); or width*height > 126 / height > 16: the 7-bit cell code
+                                 and 16-bit observation lanes of this library (the reference has no upper limit) */
 #define SOCCER_ESLIP    (-3)  /* slip_prob > 0 without rng32 / rngf64, or unsupported here */
 #define SOCCER_EPOLICY  (-4)  /* both policies given (SIM:38) */
 
@@ -162,13 +171,26 @@ typedef struct soccer_step_args {
     int32_t         detail;     /* 1: fill flags bits 2..7 (needed for info["p"], SIM:405) */
     int32_t         narrow;     /* 1: obs points at uint16[n], reward at int8[n] (same values); else 0 */
     uint64_t        seed, step, env_id_base;
+    /* optional, NULL = off: episode statistics of this step fused into the kernel (no second pass
+     * over the streams): stats[0] += episodes ended, [1] += goals_A, [2] += goals_B (by player A's
+     * reward sign whatever the return agent), [3] += truncations without a goal, [4] += env-steps,
+     * [5] += summed length of the episodes that ended -- the vector soccer_rollout accumulates and
+     * the multi-GPU path all-reduces.  Not offered together with slip_prob > 0 on the table path. */
+    unsigned long long *stats;
+    /* optional, NULL = rules kernels on SOCCER_LAYOUT_CELL states.  Non-NULL: the step table of
+     * soccer_build_step_table; `state` is then in SOCCER_LAYOUT_INDEX and the shared-memory-table
+     * kernels run (see below): injected or Philox draws, folded table policies (the single-agent
+     * modes, SIM:187-188, 243-244), slip_prob > 0 (rng32 / rngf64 / Philox), narrow streams, stats.
+     * Needs auto_reset == 1 and detail == 0. */
+    const uint16_t *table;
+    const uint8_t  *slip_index; /* optional accelerator of the table path for slip_prob > 0 (soccer_build_slip_index) */
 } soccer_step_args;
 int soccer_step_ex(const soccer_pitch *pitch, const soccer_step_args *args, soccer_stream_t stream);
 
-/* Episode statistics of one lock-step step, from its flags (and, optionally, reward) streams:
- * stats[0] += episodes ended, [1] += goals_A (reward > 0), [2] += goals_B, [3] += truncations
- * without a goal, [4] += n (steps); [5] (sum_episode_len) is left alone.  This vector is what the
- * multi-GPU path all-reduces (the one collective of the path). */
+/* Episode statistics of one lock-step step as a SEPARATE pass over its flags (and, optionally,
+ * reward) streams: stats[0] += episodes ended, [1] += goals_A (reward > 0), [2] += goals_B,
+ * [3] += truncations without a goal, [4] += n (steps); [5] (sum_episode_len) is left alone.
+ * soccer_step_args.stats fuses the same counts (and [5]) into the step kernel itself. */
 int soccer_step_stats(const uint8_t *flags, const float *reward, int64_t n,
                       unsigned long long *stats, soccer_stream_t stream);
 
@@ -192,11 +214,14 @@ int soccer_bench_rollout_probe(uint32_t *state, int32_t K, int32_t *obs, float *
 /* policy_* == NULL -> uniform random joint action from the Philox word; else int8[nS] table.
  * obs/reward/flags are [K][n] streams (each optional).  stats[6] (optional, uint64, accumulated
  * with atomics): episodes, goals_A, goals_B, truncations, steps, sum_episode_len.
- * slip_prob must be 0 here. */
+ * slip_prob >= 0 (slip_prob > 0: the word's 32-bit step draw through the reference's cumulative walk).
+ * flip_reward != 0: the streamed reward is player B's (the negated value) -- what step() returns for an
+ * env whose return agent is player_b (player A folded, SIM:243-244); the goals_A / goals_B statistics
+ * keep counting by the unflipped sign.  K <= 2^28. */
 int soccer_rollout(const soccer_pitch *pitch, uint32_t *state, const int8_t *policy_a,
                    const int8_t *policy_b, uint64_t seed, uint64_t step0, int32_t K,
-                   uint64_t env_id_base, int32_t *obs, float *reward, uint8_t *flags,
-                   unsigned long long *stats, int64_t n, soccer_stream_t stream);
+                   uint64_t env_id_base, int32_t flip_reward, int32_t *obs, float *reward,
+                   uint8_t *flags, unsigned long long *stats, int64_t n, soccer_stream_t stream);
 
 /* ---- K3: exhaustive sweep = the transition table builder (SIM:167-293) ---- */
 /* For every observation s in 1..nS-1, joint action ja = aa*5+ab, slip combination c
@@ -248,6 +273,12 @@ int soccer_step_narrow(const soccer_pitch *pitch, const uint16_t *table, uint32_
 int soccer_step_table_packed(const soccer_pitch *pitch, const uint16_t *table, uint32_t *state,
                              const uint8_t *joint, const uint8_t *rng8, uint16_t *result, int64_t n,
                              soccer_stream_t stream);
+/* the same with Philox draws keyed (seed, env_id_base + i, step): no draw stream, 1 byte in and 2 bytes
+ * out per env-step */
+int soccer_step_table_packed_philox(const soccer_pitch *pitch, const uint16_t *table, uint32_t *state,
+                                    const uint8_t *joint, uint64_t seed, uint64_t step,
+                                    uint64_t env_id_base, uint16_t *result, int64_t n,
+                                    soccer_stream_t stream);
 /* step() with slip_prob > 0 (SIM:203-256) through the same shared-memory table: the outcome counts of
  * the 9 slipped move pairs are read from the state's table row, the categorical draw walks them in
  * the reference's order with sequential fp64 sums (bit-exact), one more look-up yields the chosen
@@ -273,12 +304,16 @@ int soccer_rollout_table(const soccer_pitch *pitch, const uint16_t *table, uint3
                          int64_t n, soccer_stream_t stream);
 /* the same with on-device table policies (int8[nS] each, NULL = uniform random from the Philox
  * word, SIM:187-188 semantics as in soccer_rollout); the policies ride in shared memory next to
- * the table */
-int soccer_rollout_table_policy(const soccer_pitch *pitch, const uint16_t *table, uint32_t *state,
-                                const int8_t *policy_a, const int8_t *policy_b, uint64_t seed,
-                                uint64_t step0, int32_t K, uint64_t env_id_base, int32_t *obs,
-                                float *reward, uint8_t *flags, unsigned long long *stats,
-                                int64_t n, soccer_stream_t stream);
+ * the table.  slip_index (optional, soccer_build_slip_index): with slip_prob > 0 and room for it next to
+ * the table (5x4), 4 envs per thread take the constant-prefix fast path and the envs whose draw needs the
+ * reference's cumulative walk go through a per-step warp queue; NULL = in-place walk.  flip_reward as in
+ * soccer_rollout. */
+int soccer_rollout_table_policy(const soccer_pitch *pitch, const uint16_t *table,
+                                const uint8_t *slip_index, uint32_t *state, const int8_t *policy_a,
+                                const int8_t *policy_b, uint64_t seed, uint64_t step0, int32_t K,
+                                uint64_t env_id_base, int32_t flip_reward, int32_t *obs, float *reward,
+                                uint8_t *flags, unsigned long long *stats, int64_t n,
+                                soccer_stream_t stream);
 /* translate a state tensor between layouts (in place allowed); goal / needs_reset states map
  * to observation 0 in the INDEX layout and cannot be converted back */
 int soccer_convert_state(const soccer_pitch *pitch, const uint32_t *in, uint32_t *out,

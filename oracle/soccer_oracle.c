@@ -525,40 +525,37 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-/* One Philox call serves 4 consecutive steps of one env: counter = (env_lo, env_hi,
- * (step>>2)_lo, (step>>2)_hi), key = (seed_lo, seed_hi), word index = step & 3. */
+/* Philox contract v2.  One Philox call serves the 4 envs of an ALIGNED GROUP at one step:
+ * counter = (group_lo, group_hi, step_lo, step_hi) with group = global env id >> 2, key = (seed_lo,
+ * seed_hi); the env's word is output word (env id & 3).  A pure function of (seed, global env id,
+ * step), hence independent of GPU count, launch boundaries and K. */
 uint32_t orc_philox_word(uint64_t seed, uint64_t env_id, uint64_t step)
 {
-    uint64_t blk = step >> 2;
-    uint32_t ctr[4] = { (uint32_t)env_id, (uint32_t)(env_id >> 32), (uint32_t)blk, (uint32_t)(blk >> 32) };
+    uint64_t grp = env_id >> 2;
+    uint32_t ctr[4] = { (uint32_t)grp, (uint32_t)(grp >> 32), (uint32_t)step, (uint32_t)(step >> 32) };
     uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
     uint32_t out[4];
     orc_philox4x32_10(ctr, key, out);
-    return out[step & 3];
+    return out[env_id & 3];
 }
 
+/* Decode of one word w (fixed point: x = w / 2^32 uniform on [0, 1)):
+ *   joint action  ja = floor(25 x) = mulhi(w, 25)            aa = ja / 5, ab = ja % 5
+ *   step draw     r32 = frac(25 x) * 2^32 = lo32(25 w)       u = (r32 + 0.5) / 2^32, the rng32 format;
+ *                 slip_prob == 0 uses its top two bits (r32 >> 30), which select the same outcome of
+ *                 1 / 2 / 4 equiprobable ones as u does
+ *   reset draw    w & 3
+ * (25 is odd, so w -> r32 is a bijection of the 32-bit words: r32 is exactly uniform.) */
 void orc_philox_decode(uint32_t w, int *aa, int *ab, int *r_step, int *r_reset)
 {
-    /* jr = mulhi(w, 100), uniform on 0..99 = (joint action, step draw) at once; w & 3 = reset draw */
-    uint32_t jr = (uint32_t)(((uint64_t)w * 100u) >> 32);
-    uint32_t ja = jr >> 2;
+    uint32_t ja = (uint32_t)(((uint64_t)w * 25u) >> 32);
+    uint32_t r32 = (uint32_t)((uint64_t)w * 25u);
     *aa = (int)(ja / 5u);
     *ab = (int)(ja % 5u);
-    *r_step = (int)(jr & 3u);
+    *r_step = (int)(r32 >> 30);
     *r_reset = (int)(w & 3u);
 }
-
-/* slip_prob > 0: the categorical draw over up to 15 outcomes (SIM:395) needs a fine-grained
- * uniform; 53 bits from words 0 and 1 of a separate Philox counter lane (top counter bit set). */
-double orc_philox_u53(uint64_t seed, uint64_t env_id, uint64_t step)
-{
-    uint32_t ctr[4] = { (uint32_t)env_id, (uint32_t)(env_id >> 32), (uint32_t)step,
-                        (uint32_t)(step >> 32) | 0x80000000u };
-    uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
-    uint32_t w[4];
-    orc_philox4x32_10(ctr, key, w);
-    return (double)(((uint64_t)(w[0] >> 5) << 26) | (uint64_t)(w[1] >> 6)) * (1.0 / 9007199254740992.0);
-}
+uint32_t orc_philox_r32(uint32_t w) { return (uint32_t)((uint64_t)w * 25u); }
 
 void orc_rollout_philox(const orc_model *m, int64_t K, int64_t N,
                         orc_state *state, int32_t *timestep,
@@ -584,7 +581,8 @@ void orc_rollout_philox(const orc_model *m, int64_t K, int64_t N,
             if (policy_a) aa = policy_a[cur];
             if (policy_b) ab = policy_b[cur];
             int o, d, tr; double r;
-            double u = m->slip != 0.0 ? orc_philox_u53(seed, env_id_base + (uint64_t)i, step0 + (uint64_t)k)
+            /* slip_prob > 0: the 32-bit step draw, u = (r32 + 0.5) / 2^32 like the injected rng32 format */
+            double u = m->slip != 0.0 ? ((double)orc_philox_r32(w) + 0.5) / 4294967296.0
                                       : ((double)rs + 0.5) / 4.0;
             orc_env_step(&e, aa * 5 + ab, u, &o, &r, &d, &tr, NULL);
             s4 += 1;

@@ -134,17 +134,18 @@ void orc_rollout_injected(const orc_model *m, int64_t T, int64_t N,
 /* ---- counter-based randomness (DESIGN.md "Philox contract") ---- */
 /* Philox4x32-10 (Salmon et al., SC'11; Random123 reference constants). */
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
-/* The 32-bit word that drives env `env_id` at absolute step `step`. */
+/* The 32-bit word that drives env `env_id` at absolute step `step` (contract v2: one Philox call =
+ * the 4 envs of the aligned group env_id >> 2 at one step; word index env_id & 3). */
 uint32_t orc_philox_word(uint64_t seed, uint64_t env_id, uint64_t step);
-/* decode a word: jr = mulhi(w, 100) -> joint action jr>>2 and step draw jr&3; reset draw = w & 3 */
+/* decode a word: joint action ja = mulhi(w, 25); step draw r32 = lo32(25 w) (u = (r32 + 0.5) / 2^32;
+ * *r_step = r32 >> 30, the 2-bit draw of slip_prob == 0); reset draw = w & 3 */
 void orc_philox_decode(uint32_t w, int *aa, int *ab, int *r_step, int *r_reset);
-
-/* 53-bit uniform for the slip_prob > 0 categorical draw (separate counter lane) */
-double orc_philox_u53(uint64_t seed, uint64_t env_id, uint64_t step);
+uint32_t orc_philox_r32(uint32_t w);
 
 /* K-step rollout, uniform (policy == NULL) or table policies (int8 obs->action), Philox
  * draws keyed (seed, env_id_base + i, step0 + k).  stats[6] += {episodes, goals_A, goals_B,
- * truncations, steps, sum_episode_len}.  obs/reward/flags may be NULL. slip must be 0. */
+ * truncations, steps, sum_episode_len}.  obs/reward/flags may be NULL.  slip_prob > 0: the step draw
+ * is u = (r32 + 0.5) / 2^32. */
 void orc_rollout_philox(const orc_model *m, int64_t K, int64_t N,
                         orc_state *state, int32_t *timestep,
                         const int8_t *policy_a, const int8_t *policy_b,

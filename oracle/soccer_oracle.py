@@ -93,6 +93,8 @@ def lib():
     L.orc_philox_word.restype = C.c_uint32
     L.orc_philox_word.argtypes = [u64, u64, u64]
     L.orc_philox_decode.argtypes = [C.c_uint32, ip, ip, ip, ip]
+    L.orc_philox_r32.restype = C.c_uint32
+    L.orc_philox_r32.argtypes = [C.c_uint32]
     L.orc_rollout_philox.argtypes = [vp, i64, i64, vp, vp, vp, vp, u64, u64, u64, vp, vp, vp, vp, i]
     _lib = L
     return L
@@ -298,6 +300,11 @@ def philox4x32_10(ctr, key):
 
 def philox_word(seed, env_id, step):
     return int(lib().orc_philox_word(int(seed), int(env_id), int(step)))
+
+
+def philox_r32(w):
+    """The 32-bit step draw of a word: lo32(25 w); u = (r32 + 0.5) / 2^32."""
+    return int(lib().orc_philox_r32(int(w)))
 
 
 def philox_decode(w):

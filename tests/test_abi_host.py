@@ -27,7 +27,7 @@ def test_header_symbols_are_exported(L):
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in include/soccer_b200.h but not exported"
     assert declared == set(L.EXPORTS)
-    assert lib.soccer_abi_version() == 1
+    assert lib.soccer_abi_version() == 2 == L.ABI_VERSION
 
 
 def test_library_is_sm100a_only(L):
@@ -74,6 +74,21 @@ def test_argument_errors_without_gpu(L):
     assert lib.soccer_slip_index_bytes_host(C.byref(L.Pitch(7, 5, 0.2)), C.byref(nbytes)) == -5
     assert lib.soccer_step_many(C.byref(L.Pitch(5, 4, 0.2)), None, v16, 4, v16, v16, v16, v16, v16, v16, None, 8, None) == -3
     assert lib.soccer_step_many(C.byref(p), None, v16, -1, v16, v16, v16, v16, v16, v16, None, 8, None) == -1
+    # soccer_step_ex on the table path: INDEX-layout states cannot hold needs_reset / detail flags; fused statistics
+    # are not offered with slip_prob > 0 there; a Philox packed step refuses a slip pitch like the injected one
+    a = L.StepArgs()
+    a.state = a.table = a.act_a = a.act_b = a.rng8 = a.obs = a.reward = a.flags = 16
+    a.n, a.auto_reset = 8, 0
+    assert lib.soccer_step_ex(C.byref(p), C.byref(a), None) == -1
+    a.auto_reset, a.detail = 1, 1
+    assert lib.soccer_step_ex(C.byref(p), C.byref(a), None) == -1
+    a.detail, a.stats, a.rng32 = 0, 16, 16
+    assert lib.soccer_step_ex(C.byref(L.Pitch(5, 4, 0.2)), C.byref(a), None) == -1
+    a.stats, a.rng32 = None, None
+    assert lib.soccer_step_ex(C.byref(L.Pitch(5, 4, 0.2)), C.byref(a), None) == -3                  # no step draw
+    assert lib.soccer_step_ex(C.byref(L.Pitch(7, 5, 0.0)), C.byref(a), None) == -5                  # no table for 7x5
+    assert lib.soccer_step_table_packed_philox(C.byref(L.Pitch(5, 4, 0.2)), v16, v16, v16, 0, 0, 0, v16, 8, None) == -3
+    assert lib.soccer_rollout(C.byref(p), v16, None, None, 0, 0, (1 << 28) + 1, 0, 0, None, None, None, None, 8, None) == -1
 
 
 @pytest.mark.parametrize("tag", [t for t in golden_tags("table") if t.endswith("multi")])

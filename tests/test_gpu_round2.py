@@ -1,0 +1,376 @@
+"""GPU parity tests added in round 2.
+
+* the BENCHMARKED configurations themselves against the oracle: K1 (table and rules) at 2^24 envs, every env; the
+  headline end-to-end call step_host_packed at 2^24 envs / n_chunks = 8, zero copy and staged; K2 exactly as
+  BASELINE configs 3 / 4 (2^20 and 2^21 envs, K = 64, 16 launches, env_id_base = rank * n) -- the statistics vector
+  of ALL envs and the streams of 4096 sampled env columns
+* the single-agent (folded policy) modes on the shared-memory-table kernels against the reference's golden rollouts
+* statistics fused into K1 == the separate statistics pass == K2's
+* step() and rollout() return the same (flipped) reward for a player_b env (SIM:243-244)
+* Philox contract v2 corner cases: env_id_base % 4 != 0, packed Philox step, K1 slip with Philox draws
+* the host-buffer path in every mode of the env
+All comparisons are ==.
+"""
+import numpy as np
+import pytest
+
+from .conftest import load_golden, parse_tag
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda", 0)
+
+
+def _t(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def _oracle_states(oracle, m, obs, dtype=None):
+    """obs indices -> the oracle's tuple states, vectorised (a 761-entry table instead of one ctypes call per env)."""
+    table = np.zeros(m.nS, oracle.STATE_DTYPE)
+    for o in range(1, m.nS):
+        table[o] = m.obs_to_state(o)
+    return table[np.asarray(obs, dtype=np.int64)].copy()
+
+
+# ----------------------------------------------------------------------------- benchmarked configs, every env
+@pytest.mark.parametrize("kernel", ["table", "rules"])
+def test_k1_at_2_24_envs_vs_oracle_every_env(dev, oracle, kernel):
+    """bench.py's headline workload (K1, 2^24 envs, injected draws): obs / reward / flags / reset_obs / state of ALL
+    envs for 4 steps against the oracle, on a played-in population (64 warm-up steps first)."""
+    from gym_soccer_littman94_b200.envs import SoccerVecEnv
+    N, T = 1 << 24, 4
+    m = oracle.OracleModel(5, 4, 0.0)
+    g = torch.Generator(device=dev).manual_seed(2024)
+
+    def rnd(hi):
+        return torch.randint(0, hi, (N,), dtype=torch.uint8, device=dev, generator=g)
+    env = SoccerVecEnv(N, device=dev, kernel=kernel)
+    env.reset(rnd(16))
+    for _ in range(64):
+        env.step(rnd(5), rnd(5), rnd(16))
+    states = _oracle_states(oracle, m, env.current_obs().cpu().numpy())
+    ts = env.timesteps().cpu().numpy().astype(np.int32)
+    assert ts.max() > 50 and len(np.unique(states)) > 700                  # a mixed population, not the start states
+    acts = [(rnd(5), rnd(5), rnd(16)) for _ in range(T)]
+    a, b, r = (np.stack([x[i].cpu().numpy() for x in acts]) for i in range(3))
+    eo, er, ef, ero = m.rollout_injected(states, ts, a, b, r, n_threads=16)
+    for t in range(T):
+        obs, rew, flg, rob = env.step(*acts[t])
+        assert np.array_equal(obs.cpu().numpy(), eo[t]) and np.array_equal(rew.cpu().numpy(), er[t]), (kernel, t)
+        assert np.array_equal(flg.cpu().numpy(), ef[t]) and np.array_equal(rob.cpu().numpy(), ero[t]), (kernel, t)
+    want_obs = np.where(ef[T - 1] != 0, ero[T - 1], eo[T - 1])
+    assert np.array_equal(env.current_obs().cpu().numpy(), want_obs)
+    assert np.array_equal(env.timesteps().cpu().numpy(), ts)              # rollout_injected advanced ts in place
+
+
+@pytest.mark.parametrize("zero_copy", [True, False])
+def test_step_host_packed_at_2_24_envs_vs_oracle(dev, oracle, zero_copy):
+    """The headline end-to-end call exactly as bench.py makes it (2^24 envs, n_chunks = 8, pinned arena buffers, zero
+    copy; and the staged copy-engine pipeline): the unpacked result words of ALL envs against the oracle."""
+    from gym_soccer_littman94_b200.envs import SoccerVecEnv
+    N, T = 1 << 24, 3
+    m = oracle.OracleModel(5, 4, 0.0)
+    env = SoccerVecEnv(N, device=dev, kernel="table", want_reset_obs=False)
+    rs = np.random.RandomState(77)
+    env.reset(_t(rs.randint(0, 16, N).astype(np.uint8), dev))
+    g = torch.Generator(device=dev).manual_seed(5)
+    for _ in range(40):
+        env.step(*(torch.randint(0, hi, (N,), dtype=torch.uint8, device=dev, generator=g) for hi in (5, 5, 16)))
+    states = _oracle_states(oracle, m, env.current_obs().cpu().numpy())
+    ts = env.timesteps().cpu().numpy().astype(np.int32)
+    a, b, r = (rs.randint(0, hi, (T, N)).astype(np.uint8) for hi in (5, 5, 16))
+    eo, er, ef, _ = m.rollout_injected(states, ts, a, b, r, n_threads=16, want_reset_obs=False)
+    bufs = [env.alloc_host_inputs(packed=True) for _ in range(2)]
+    for t in range(T):
+        jb, rb = bufs[t % 2]
+        jb.copy_(torch.from_numpy(a[t] | (b[t] << 4))); rb.copy_(torch.from_numpy(r[t]))
+        res = env.step_host_packed(jb, rb, n_chunks=8, zero_copy=zero_copy)
+        obs, rew, term, trunc = SoccerVecEnv.unpack_result(res)
+        assert np.array_equal(obs.numpy(), eo[t]) and np.array_equal(rew.numpy(), er[t]), t
+        assert np.array_equal((term.numpy().astype(np.uint8) | (trunc.numpy().astype(np.uint8) << 1)), ef[t]), t
+
+
+@pytest.mark.parametrize("log2n,rank", [(20, 0), (21, 3)])
+def test_k2_as_benchmarked_vs_oracle(dev, oracle, log2n, rank):
+    """BASELINE configs 3 / 4 exactly as bench.py runs them: 2^20 (2^21) envs, K = 64, 16 launches back to back,
+    env_id_base = rank * n.  The statistics vector of ALL envs (1-2 G env-steps through the oracle) and the obs /
+    reward / flags streams of 4096 sampled env columns (64 random aligned runs of 64 envs), every launch."""
+    from gym_soccer_littman94_b200.envs import SoccerVecEnv
+    n, K, L, seed = 1 << log2n, 64, 16, 0
+    base = rank * n
+    m = oracle.OracleModel(5, 4, 0.0)
+    env = SoccerVecEnv(n, device=dev, kernel="auto", rng_mode="philox", seed=seed, env_id_base=base)
+    assert env.kernel == "table"
+    init = env.reset().cpu().numpy()
+    states, ts = _oracle_states(oracle, m, init), np.zeros(n, np.int32)
+    rs = np.random.RandomState(log2n)
+    runs = np.sort(rs.choice(n // 64, 64, replace=False)) * 64
+    cols = (runs[:, None] + np.arange(64)[None, :]).reshape(-1)
+    sub_states, sub_ts = states[cols].copy(), ts[cols].copy()
+    bufs = (torch.empty((K, n), dtype=torch.int32, device=dev), torch.empty((K, n), dtype=torch.float32, device=dev),
+            torch.empty((K, n), dtype=torch.uint8, device=dev))
+    st = torch.zeros(6, dtype=torch.int64, device=dev)
+    tcols = _t(cols, dev)
+    for launch in range(L):
+        step0 = env.step_count
+        env.rollout(K, out=bufs, stats=st)
+        got = [x[:, tcols].cpu().numpy() for x in bufs]
+        for j, lo in enumerate(runs):
+            sl = slice(j * 64, (j + 1) * 64)
+            s_, t_ = sub_states[sl].copy(), sub_ts[sl].copy()
+            eo, er, ef, _ = m.rollout_philox(s_, t_, K, seed, step0=step0, env_id_base=base + int(lo))
+            sub_states[sl], sub_ts[sl] = s_, t_
+            assert np.array_equal(got[0][:, sl], eo) and np.array_equal(got[1][:, sl], er), (launch, lo)
+            assert np.array_equal(got[2][:, sl], ef), (launch, lo)
+    # statistics of the whole population over the 16 launches (K * L steps in one oracle call)
+    _, _, _, es = m.rollout_philox(states, ts, K * L, seed, step0=0, env_id_base=base, n_threads=32, want_streams=False)
+    assert np.array_equal(st.cpu().numpy(), es)
+    fin = _oracle_states(oracle, m, env.current_obs().cpu().numpy())
+    assert np.array_equal(fin, states) and np.array_equal(env.timesteps().cpu().numpy(), ts)
+
+
+# ----------------------------------------------------------------------------- single-agent modes on the table kernels
+@pytest.mark.parametrize("tag", ["5x4_s000_a_free", "5x4_s020_a_free", "5x4_s020_b_free"])
+@pytest.mark.parametrize("n_pad", [0, 3])
+def test_single_agent_table_kernels_match_reference(dev, tag, n_pad):
+    """The folded-policy modes (SIM:187-188, 243-244; the mode the reference's planners and four of its integration
+    tests use) through the shared-memory-table K1 kernels -- slip 0 (k_step_table<POLICY>) and slip 0.2 (fast path +
+    queue with the policy next to the table) -- against the replayed reference, vector and ragged shapes."""
+    from .test_gpu_parity import _env_kwargs, _run_vec
+    g = load_golden("rollout", tag)
+    kw, _ = _env_kwargs(tag, g)
+    obs, rew, flg, rob = _run_vec(dev, g, kw, "table", n_pad, 0)
+    assert np.array_equal(obs, g["obs"]) and np.array_equal(rew, g["reward"])
+    assert np.array_equal(flg, g["flags"]) and np.array_equal(rob, g["reset_obs"])
+
+
+@pytest.mark.parametrize("slip", [0.0, 0.2])
+@pytest.mark.parametrize("side", ["a", "b"])
+def test_single_agent_table_equals_rules_kernel_philox(dev, slip, side):
+    """Single-agent env, Philox draws, 4099 envs (ragged tail): kernel='table' == kernel='rules' step after step
+    (for slip 0.2 this is K1 slip with Philox draws through the table, fast path + queue)."""
+    from gym_soccer_littman94_b200.envs import SoccerVecEnv
+    n, T = 4099, 60
+    pol = np.random.RandomState(3).randint(0, 5, 761).astype(np.int8)
+    kw = {"player_b_policy": pol} if side == "a" else {"player_a_policy": pol}
+    envs = [SoccerVecEnv(n, slip_prob=slip, device=dev, rng_mode="philox", seed=9, kernel=k, **kw) for k in ("rules", "table")]
+    for e in envs:
+        e.reset()
+    g = torch.Generator(device=dev).manual_seed(1)
+    for t in range(T):
+        act = torch.randint(0, 5, (n,), dtype=torch.uint8, device=dev, generator=g)
+        outs = [e.step(act if side == "a" else None, act if side == "b" else None) for e in envs]
+        for x, y in zip(*outs):
+            assert torch.equal(x, y), t
+    assert torch.equal(envs[0].current_obs(), envs[1].current_obs())
+
+
+@pytest.mark.parametrize("kernel", ["rules", "table"])
+@pytest.mark.parametrize("slip", [0.0, 0.2])
+def test_rollout_reward_is_the_return_agents(dev, kernel, slip):
+    """for an env whose return agent is player_b (player A folded), step() returns -reward (SIM:243-244);
+    the fused rollout must stream the same sign.  K steps of rollout() == K calls of step() with the actions the
+    rollout drew for player B; the goals_A / goals_B statistics keep the unflipped sign."""
+    from gym_soccer_littman94_b200.envs import SoccerVecEnv
+    from oracle import soccer_oracle as so
+    n, K, seed = 512, 80, 21
+    pol = np.random.RandomState(8).randint(0, 5, 761).astype(np.int8)
+    a = SoccerVecEnv(n, slip_prob=slip, device=dev, rng_mode="philox", seed=seed, kernel=kernel, player_a_policy=pol)
+    b = SoccerVecEnv(n, slip_prob=slip, device=dev, rng_mode="philox", seed=seed, kernel=kernel, player_a_policy=pol)
+    a.reset(); b.reset()
+    obs, rew, flg, stats = a.rollout(K)
+    tot = torch.zeros(6, dtype=torch.int64, device=dev)
+    for k in range(K):
+        ab = np.array([so.philox_decode(so.philox_word(seed, i, k))[1] for i in range(n)], np.uint8)
+        o, r, f, _ = b.step(None, _t(ab, dev), stats=tot)
+        assert torch.equal(o, obs[k]) and torch.equal(f, flg[k]), k
+        assert torch.equal(r, rew[k]), k
+    assert int((rew != 0).sum()) > 20
+    # player B's reward: +1 when the ball ends in the LEFT goal; goals_B counts exactly those
+    s = stats.cpu().numpy()
+    assert int((rew > 0).sum()) == s[2] and int((rew < 0).sum()) == s[1]
+    assert np.array_equal(tot.cpu().numpy()[:5], s[:5])
+    if not (kernel == "table" and slip != 0.0):        # (the separate statistics pass leaves [5] alone)
+        assert tot.cpu().numpy()[5] == s[5]
+
+
+# ----------------------------------------------------------------------------- statistics fused into K1
+@pytest.mark.parametrize("kernel", ["rules", "table"])
+@pytest.mark.parametrize("n,base", [(4096, 0), (100003, 0), (65536, 6), (5, 0)])
+def test_k1_fused_statistics(dev, oracle, kernel, n, base):
+    """soccer_step_args.stats: K1 (Philox draws, actions = the ones K2 draws) accumulates the very vector K2 returns
+    for the same trajectories, and the injected-draw K1 the vector of the separate soccer_step_stats pass."""
+    from gym_soccer_littman94_b200.envs import SoccerVecEnv
+    K, seed = 130, 17
+    a = SoccerVecEnv(n, device=dev, rng_mode="philox", seed=seed, kernel=kernel, env_id_base=base)
+    b = SoccerVecEnv(n, device=dev, rng_mode="philox", seed=seed, kernel=kernel, env_id_base=base)
+    a.reset(); b.reset()
+    obs, rew, flg, want = a.rollout(K)
+    # the actions K2 drew, recovered from the oracle's decode of the same words
+    m = oracle.OracleModel(5, 4, 0.0)
+    got = torch.zeros(6, dtype=torch.int64, device=dev)
+    ids = np.arange(n, dtype=np.uint64) + np.uint64(base)
+    for k in range(K):
+        acts = np.array([oracle.philox_decode(oracle.philox_word(seed, int(i), k))[:2] for i in ids], np.uint8) \
+            if n <= 4096 else None
+        if acts is None:
+            break
+        o, r, f, _ = b.step(_t(acts[:, 0].copy(), dev), _t(acts[:, 1].copy(), dev), stats=got)
+        assert torch.equal(o, obs[k]) and torch.equal(f, flg[k])
+    if n <= 4096:
+        assert np.array_equal(got.cpu().numpy(), want.cpu().numpy())
+    # injected draws, random actions: fused == separate pass (+ sum_episode_len from the timesteps)
+    e = SoccerVecEnv(n, device=dev, kernel=kernel)
+    g = torch.Generator(device=dev).manual_seed(n)
+
+    def rnd(hi):
+        return torch.randint(0, hi, (n,), dtype=torch.uint8, device=dev, generator=g)
+    e.reset(rnd(16))
+    fused = torch.zeros(6, dtype=torch.int64, device=dev)
+    sep = torch.zeros(6, dtype=torch.int64, device=dev)
+    len_sum = 0
+    for t in range(150):
+        t_before = e.timesteps().clone()
+        o, r, f, _ = e.step(rnd(5), rnd(5), rnd(16), stats=fused)
+        e.step_stats(f, r, sep)
+        len_sum += int((t_before[f != 0] + 1).sum())
+    fz, sp = fused.cpu().numpy(), sep.cpu().numpy()
+    assert np.array_equal(fz[:5], sp[:5]) and fz[5] == len_sum and fz[4] == 150 * n
+
+
+# ----------------------------------------------------------------------------- Philox contract v2
+def test_philox_v2_unaligned_base_and_shards(dev, oracle):
+    """env_id_base % 4 != 0 sends K1 / K2 to their one-env-per-thread kernels: same words (the oracle), and a batch
+    cut at an arbitrary (unaligned) env equals the whole batch."""
+    from gym_soccer_littman94_b200.envs import SoccerVecEnv
+    N, K, seed = 4098, 48, 5
+    for kernel in ("rules", "table"):
+        full = SoccerVecEnv(N, device=dev, rng_mode="philox", seed=seed, kernel=kernel)
+        full.reset()
+        fo, fr, ff, fs = full.rollout(K)
+        tot = torch.zeros(6, dtype=torch.int64, device=dev)
+        for lo, hi in ((0, 1027), (1027, N)):
+            e = SoccerVecEnv(hi - lo, device=dev, rng_mode="philox", seed=seed, kernel=kernel, env_id_base=lo)
+            e.reset()
+            o, r, f, s = e.rollout(K)
+            assert torch.equal(o, fo[:, lo:hi]) and torch.equal(r, fr[:, lo:hi]) and torch.equal(f, ff[:, lo:hi])
+            tot += s
+        assert torch.equal(tot, fs)
+
+
+@pytest.mark.parametrize("n,base", [(4096, 0), (70003, 8), (1000, 5)])
+def test_packed_philox_step(dev, n, base):
+    """soccer_step_table_packed_philox (1 byte in, 2 bytes out) == soccer_step_table_philox, device and host buffers."""
+    from gym_soccer_littman94_b200.envs import SoccerVecEnv
+    a = SoccerVecEnv(n, device=dev, kernel="table", rng_mode="philox", seed=3, env_id_base=base)
+    b = SoccerVecEnv(n, device=dev, kernel="table", rng_mode="philox", seed=3, env_id_base=base)
+    c = SoccerVecEnv(n, device=dev, kernel="table", rng_mode="philox", seed=3, env_id_base=base)
+    for e in (a, b, c):
+        e.reset()
+    g = torch.Generator(device=dev).manual_seed(0)
+    (jh,) = c._pinned(torch.uint8)
+    for t in range(50):
+        aa = torch.randint(0, 5, (n,), dtype=torch.uint8, device=dev, generator=g)
+        ab = torch.randint(0, 5, (n,), dtype=torch.uint8, device=dev, generator=g)
+        o, r, f, _ = a.step(aa, ab)
+        w = b.step_packed(SoccerVecEnv.pack_joint(aa, ab))
+        po, pr, pt, ptr = SoccerVecEnv.unpack_result(w)
+        assert torch.equal(po, o) and torch.equal(pr, r) and torch.equal(pt, (f & 1) != 0) and torch.equal(ptr, (f & 2) != 0)
+        jh.copy_(SoccerVecEnv.pack_joint(aa, ab).cpu())
+        hw = c.step_host_packed(jh)
+        assert torch.equal(hw.to(dev), w)
+    assert torch.equal(a.state, b.state) and torch.equal(a.state, c.state)
+
+
+# ----------------------------------------------------------------------------- host buffers in every mode
+@pytest.mark.parametrize("mode", ["slip_rng32", "slip_rngf64", "a_free", "b_free_slip", "philox", "philox_slip"])
+@pytest.mark.parametrize("kernel", ["rules", "table"])
+def test_step_host_every_mode_equals_device_path(dev, kernel, mode):
+    """step_host() beyond the plain step (VERDICT r1 missing #3): slip_prob > 0 (the registration default 0.2), the
+    single-agent modes and Philox draws -- pinned host tensors in, pinned host tensors out, zero copy -- give exactly
+    what step() gives on device tensors."""
+    from gym_soccer_littman94_b200.envs import SoccerVecEnv
+    n, T = 5003, 40
+    pol = np.random.RandomState(1).randint(0, 5, 761).astype(np.int8)
+    kw = dict(slip_prob=0.2 if "slip" in mode else 0.0, rng_mode="philox" if mode.startswith("philox") else "injected")
+    if mode == "a_free":
+        kw["player_b_policy"] = pol
+    if mode == "b_free_slip":
+        kw["player_a_policy"] = pol
+    d = SoccerVecEnv(n, device=dev, kernel=kernel, seed=4, **kw)
+    h = SoccerVecEnv(n, device=dev, kernel=kernel, seed=4, **kw)
+    rs = np.random.RandomState(12)
+    init = rs.randint(0, 16, n).astype(np.uint8)
+    for e in (d, h):
+        e.reset(None if kw["rng_mode"] == "philox" else _t(init, dev))
+    ha, hb, hr = h.alloc_host_inputs()
+    (h32,) = h._pinned(torch.int32)
+    (h64,) = h._pinned(torch.float64)
+    for t in range(T):
+        aa, ab, r8 = (rs.randint(0, hi, n).astype(np.uint8) for hi in (5, 5, 16))
+        r32 = rs.randint(-2**31, 2**31 - 1, n).astype(np.int32)
+        r64 = rs.random_sample(n)
+        ha.copy_(torch.from_numpy(aa)); hb.copy_(torch.from_numpy(ab)); hr.copy_(torch.from_numpy(r8))
+        h32.copy_(torch.from_numpy(r32)); h64.copy_(torch.from_numpy(r64))
+        inj = kw["rng_mode"] == "injected"
+        dkw, hkw = {}, {}
+        if inj and "slip" in mode:
+            if mode == "slip_rngf64":
+                dkw, hkw = dict(rngf64=_t(r64, dev)), dict(rngf64=h64)
+            else:
+                dkw, hkw = dict(rng32=_t(r32, dev)), dict(rng32=h32)
+        da = None if d.policy_a is not None else _t(aa, dev)
+        db = None if d.policy_b is not None else _t(ab, dev)
+        o, r, f, _ = d.step(da, db, _t(r8, dev) if inj else None, **dkw)
+        ho, hrw, hf = h.step_host(None if h.policy_a is not None else ha, None if h.policy_b is not None else hb,
+                                  hr if inj else None, **hkw)
+        assert torch.equal(ho.to(dev), o) and torch.equal(hrw.to(dev), r) and torch.equal(hf.to(dev), f), (mode, t)
+    assert torch.equal(d.state, h.state)
+
+
+def test_out_tensors_are_checked(dev):
+    """user-supplied out tensors reach the kernels as raw pointers, so dtype / device / contiguity / length
+    are checked in Python; out-of-range action bytes stay inside their own env on the byte-parallel table path."""
+    from gym_soccer_littman94_b200.envs import SoccerVecEnv
+    n = 4096
+    env = SoccerVecEnv(n, device=dev, kernel="table")
+    z8 = torch.zeros(n, dtype=torch.uint8, device=dev)
+    env.reset(z8)
+    good = (torch.empty(n, dtype=torch.int32, device=dev), torch.empty(n, dtype=torch.float32, device=dev),
+            torch.empty(n, dtype=torch.uint8, device=dev), torch.empty(n, dtype=torch.int32, device=dev))
+    env.step(z8, z8, z8, out=good)
+    for i, bad in ((0, torch.empty(n, dtype=torch.int64, device=dev)), (1, torch.empty(2 * n, dtype=torch.float32, device=dev)[::2]),
+                   (2, torch.empty(n - 1, dtype=torch.uint8, device=dev)), (3, torch.empty(n, dtype=torch.int32))):
+        out = list(good)
+        out[i] = bad
+        with pytest.raises(ValueError):
+            env.step(z8, z8, z8, out=tuple(out))
+    penv = SoccerVecEnv(n, device=dev, kernel="table", rng_mode="philox")
+    penv.reset()
+    with pytest.raises(ValueError):
+        penv.rollout(4, out=(torch.empty((4, n), dtype=torch.int64, device=dev), torch.empty((4, n), dtype=torch.float32, device=dev),
+                             torch.empty((4, n), dtype=torch.uint8, device=dev)))
+    with pytest.raises(ValueError):
+        penv.rollout(4, out=(torch.empty((3, n), dtype=torch.int32, device=dev), torch.empty((4, n), dtype=torch.float32, device=dev),
+                             torch.empty((4, n), dtype=torch.uint8, device=dev)))
+    # an action byte of 200 in env 1 must not disturb envs 0, 2, 3 of its group
+    ref = SoccerVecEnv(n, device=dev, kernel="table")
+    ref.reset(z8)
+    g = torch.Generator(device=dev).manual_seed(0)
+    a = torch.randint(0, 5, (n,), dtype=torch.uint8, device=dev, generator=g)
+    b = torch.randint(0, 5, (n,), dtype=torch.uint8, device=dev, generator=g)
+    o1, r1, f1, _ = ref.step(a, b, z8)
+    a2 = a.clone()
+    a2[1::4] = 200
+    o2, r2, f2, _ = env.step(a2, b, z8)
+    keep = torch.ones(n, dtype=torch.bool, device=dev)
+    keep[1::4] = False
+    assert torch.equal(o1[keep], o2[keep]) and torch.equal(r1[keep], r2[keep]) and torch.equal(f1[keep], f2[keep])
+    with pytest.raises(ValueError):
+        SoccerVecEnv(8, width=20, height=8, device=dev)                   # beyond the library's pitch limit

@@ -33,19 +33,26 @@ def test_random123_known_answers(oracle):
 
 
 def test_word_and_decode_contract(oracle):
+    """Contract v2: one Philox call = the 4 envs of the aligned group env >> 2 at one step (counter = (group, step)),
+    word index env & 3; ja = mulhi(w, 25), step draw r32 = lo32(25 w), reset draw w & 3."""
     rs = np.random.RandomState(0)
     for _ in range(200):
         seed, env, step = (int(rs.randint(0, 2 ** 62)) for _ in range(3))
-        blk = step >> 2
-        words = philox_py((env & 0xFFFFFFFF, env >> 32, blk & 0xFFFFFFFF, blk >> 32), (seed & 0xFFFFFFFF, seed >> 32))
+        grp = env >> 2
+        words = philox_py((grp & 0xFFFFFFFF, grp >> 32, step & 0xFFFFFFFF, step >> 32), (seed & 0xFFFFFFFF, seed >> 32))
         w = oracle.philox_word(seed, env, step)
-        assert w == words[step & 3]
-        jr = (w * 100) >> 32
-        assert oracle.philox_decode(w) == ((jr >> 2) // 5, (jr >> 2) % 5, jr & 3, w & 3)
+        assert w == words[env & 3]
+        ja, r32 = (w * 25) >> 32, (w * 25) & 0xFFFFFFFF
+        assert oracle.philox_decode(w) == (ja // 5, ja % 5, r32 >> 30, w & 3)
+        assert oracle.philox_r32(w) == r32
+        # the table column index the kernels use: jr = mulhi(w, 100) = ja * 4 + (r32 >> 30)
+        assert (w * 100) >> 32 == ja * 4 + (r32 >> 30)
+    # the initial reset uses step 2^64 - 1
+    assert oracle.philox_word(5, 9, (1 << 64) - 1) == philox_py((2, 0, 0xFFFFFFFF, 0xFFFFFFFF), (5, 0))[1]
 
 
 def test_decode_is_uniform_over_joint_action_and_draw(oracle):
-    # every (joint action, step draw) cell owns 2^32/100 +- 1 of the 2^32 words, and within a cell
+    # every (joint action, 2-bit step draw) cell owns 2^32/100 +- 1 of the 2^32 words, and within a cell
     # the reset draw (w & 3) is uniform to within one word
     edges = [-(-(c << 32) // 100) for c in range(101)]          # first w with mulhi(w, 100) == c
     sizes = np.diff(np.array(edges, dtype=np.int64))
@@ -53,3 +60,9 @@ def test_decode_is_uniform_over_joint_action_and_draw(oracle):
     for c in (0, 37, 99):
         assert (int(edges[c]) * 100) >> 32 == c and ((int(edges[c]) - 1) * 100) >> 32 == c - 1
     assert all(abs((e1 - e0) // 4 - ((e1 - e0 + 3) // 4)) <= 1 for e0, e1 in zip(edges, edges[1:]))
+    # r32 = lo32(25 w): 25 is odd, so w -> r32 is a bijection of the 32-bit words (exactly uniform draw); inside one
+    # joint action the draws are the arithmetic progression r0 + 25 j, i.e. uniform at a resolution of 25 / 2^32
+    assert pow(25, -1, 1 << 32) * 25 % (1 << 32) == 1
+    w0 = int(edges[4 * 7])                                      # first word of joint action 7
+    assert [((w0 + j) * 25) & 0xFFFFFFFF for j in range(3)] == [(w0 * 25 + 25 * j) & 0xFFFFFFFF for j in range(3)]
+    assert (w0 * 25) & 0xFFFFFFFF < 25
