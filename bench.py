@@ -26,6 +26,11 @@ if ROOT not in sys.path:
 
 METRIC = "lockstep_env_steps_per_sec"
 UNIT = "env-steps/s"
+# all-reduced statistics of 2^24 GLOBAL envs (5x4, slip 0, Philox seed 20261018, reset() + 64 lock-steps of uniform play):
+# computed by the CPU oracle (oracle/make_shard_invariant.py) -- Philox is keyed by the global env id, so every sharding of
+# that batch over 1, 2, 4 or 8 GPUs must reproduce this vector exactly
+SHARD_INVARIANT = {"envs": 1 << 24, "K": 64, "seed": 20261018,
+                   "stats": [29943569, 14967803, 14975766, 0, 1073741824, 590049320]}
 BYTES_PER_ENV_STEP = 20   # state u32 r+w (8) + act_a, act_b, rng u8 (3) + obs i32 (4) + reward f32 (4) + flags u8 (1)
 
 
@@ -247,13 +252,14 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---------------- device-resident throughput (value) + per-launch roofline
-    def episode_stats(o):
-        return env.step_stats(flags=o[2], reward=o[1])
-
+    # Episode statistics are accumulated INSIDE the K1 kernel (soccer_step_args.stats: byte-parallel flag counts, one
+    # warp reduction + 6 atomics per CTA at the end) at every N, so a step costs the same on 1 GPU and on 8; at N > 1
+    # the one collective of the path -- the sum all-reduce of the 48-byte vector -- follows the last K1 directly.
+    stats = torch.zeros(6, dtype=torch.int64, device=dev)
     for i in range(W):
-        env.step(*ins[i % RING], out=outs[i % RING])
+        env.step(*ins[i % RING], out=outs[i % RING], stats=stats)
     if world > 1:
-        dist.all_reduce(episode_stats(outs[0]))        # warm the communicator
+        dist.all_reduce(stats.clone())                 # warm the communicator
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -261,6 +267,7 @@ def run_ours(args):
         time.sleep(0.3)
     # (1) the timed region: EXACTLY K steps between two events, nothing else in the stream
     start, k_done, end = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    stats.zero_()
     barrier()
     if world > 1:
         # device-side rendezvous right before the start event: the host-side barrier lets the ranks go tens of
@@ -268,22 +275,21 @@ def run_ours(args):
         dist.all_reduce(torch.zeros(1, device=dev))
     start.record()
     for i in range(K):
-        env.step(*ins[i % RING], out=outs[i % RING])
+        env.step(*ins[i % RING], out=outs[i % RING], stats=stats)
     k_done.record()
-    stats = None
     if world > 1:
-        # the one collective of the path: episode statistics of the last step
-        stats = episode_stats(outs[(K - 1) % RING])
-        dist.all_reduce(stats)
+        dist.all_reduce(stats)                         # the one collective of the path
     end.record()
     barrier()
     total_ms = start.elapsed_time(end)
     kern_ms = start.elapsed_time(k_done) / K          # mean launch duration of the dominant kernel
+    tail_us = k_done.elapsed_time(end) * 1e3          # what follows the last K1 inside the timed region (the all-reduce)
+    stats_timed = [int(x) for x in stats.cpu()]       # episodes, goals_A, goals_B, truncations, env-steps, sum of lengths
     # (2) a second pass with an event after every launch, only for the per-launch spread
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
     ev[0].record()
     for i in range(K):
-        env.step(*ins[i % RING], out=outs[i % RING])
+        env.step(*ins[i % RING], out=outs[i % RING], stats=stats)
         ev[i + 1].record()
     torch.cuda.synchronize()
     per_launch = [ev[i].elapsed_time(ev[i + 1]) for i in range(K)]
@@ -293,7 +299,7 @@ def run_ours(args):
     u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     u0.record()
     for i in range(n_sus):
-        env.step(*ins[i % RING], out=outs[i % RING])
+        env.step(*ins[i % RING], out=outs[i % RING], stats=stats)
     u1.record()
     torch.cuda.synchronize()
     sustained = {"steps": n_sus, "seconds": u0.elapsed_time(u1) * 1e-3,
@@ -387,7 +393,132 @@ def run_ours(args):
                       "d2h_bytes_per_step": 2 * N, "checksum": int((h_res[:1024].to(torch.int64) & 0xFFF).sum()),
                       "api": "SoccerVecEnv.step_host_packed: joint-action byte (aa | ab << 4) + draw byte up, one int16 "
                              "result word (obs | terminated << 12 | truncated << 13 | reward << 14) down"}
+        # -- verified: one more end-to-end step whose host-side result words are compared, on a random sample of envs,
+        #    with the CPU oracle stepping the very states (the oracle is the checker here, never the path measured)
+        try:
+            import numpy as np
+            from oracle import soccer_oracle as so
+            m = so.OracleModel(5, 4, 0.0)
+            tab = np.zeros(m.nS, so.STATE_DTYPE)
+            for o in range(1, m.nS):
+                tab[o] = m.obs_to_state(o)
+            idx = np.sort(np.random.RandomState(99 + rank).choice(N, 1 << 16, replace=False))
+            tidx = torch.from_numpy(idx).to(dev)
+            st_before = env.state[tidx].cpu().numpy()
+            jb, rb = h_pk[0]
+            h_res = env.step_host_packed(jb, rb, n_chunks=args.chunks)
+            got = h_res[torch.from_numpy(idx)].numpy().astype(np.int32)
+            jn, rn = jb.numpy()[idx], rb.numpy()[idx]
+            states, ts = tab[st_before & 0xFFFF].copy(), ((st_before >> 16) & 0xFF).astype(np.int32)
+            eo, er, ef, _ = m.rollout_injected(states, ts, (jn & 15)[None, :].copy(), (jn >> 4)[None, :].copy(), rn[None, :].copy(),
+                                               want_reset_obs=False)
+            ok = (np.array_equal(got & 0xFFF, eo[0]) and np.array_equal((got >> 14), er[0].astype(np.int32))
+                  and np.array_equal((got >> 12) & 3, ef[0].astype(np.int32)))
+            e2e_packed["verified"] = bool(ok)
+            e2e_packed["verified_how"] = ("one further step_host_packed call: result words of 65,536 randomly chosen envs == the "
+                                          "CPU oracle stepping the same states with the same actions and draws")
+        except Exception as e:  # noqa: BLE001
+            e2e_packed["verified"] = False
+            e2e_packed["verified_error"] = repr(e)
+        # -- the link's own rate for exactly these byte counts: cudaMemcpyAsync H2D of 2N bytes and D2H of 2N bytes, alone
+        #    and both directions at once (two streams), from / to the same huge-page-backed pinned arena; then the same
+        #    duplex copy on ALL ranks at once (the host side of the box shared by N GPUs)
+        link = {}
+        try:
+            d_up = torch.empty(2 * N, dtype=torch.uint8, device=dev)
+            d_dn = torch.empty(2 * N, dtype=torch.uint8, device=dev)
+            (h_up,) = env._pinned(torch.int16)
+            (h_dn,) = env._pinned(torch.int16)
+            h_up8, h_dn8 = h_up.view(torch.uint8), h_dn.view(torch.uint8)
+            s_up, s_dn = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+            def copy_rate(up, dn, reps=6):
+                torch.cuda.synchronize()
+                c0, c1, c2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                c0.record()
+                s_up.wait_event(c0); s_dn.wait_event(c0)
+                for _ in range(reps):
+                    if up:
+                        with torch.cuda.stream(s_up):
+                            d_up.copy_(h_up8, non_blocking=True)
+                    if dn:
+                        with torch.cuda.stream(s_dn):
+                            h_dn8.copy_(d_dn, non_blocking=True)
+                with torch.cuda.stream(s_up):
+                    c1.record()
+                with torch.cuda.stream(s_dn):
+                    c2.record()
+                torch.cuda.synchronize()
+                ms = max(c0.elapsed_time(c1), c0.elapsed_time(c2)) / reps
+                return 2 * N / (ms * 1e-3) / 1e9            # GB/s per direction
+            copy_rate(True, True, 2)
+            link["h2d_alone_gbs"] = copy_rate(True, False)
+            link["d2h_alone_gbs"] = copy_rate(False, True)
+            link["duplex_gbs_per_direction"] = copy_rate(True, True)
+            barrier()
+            allr = copy_rate(True, True)
+            barrier()
+            t = torch.tensor([allr], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            link["duplex_gbs_per_direction_all_ranks_at_once_min"] = float(t.item())
+            del d_up, d_dn, h_up, h_dn
+        except Exception as e:  # noqa: BLE001
+            link["error"] = repr(e)
+        per_rank_gbs = e2e_packed["value"] / world * 2 / 1e9          # bytes per direction per second on one rank's link
+        e2e_packed["roofline"] = dict(
+            link, bound="pcie", achieved_gbs_per_direction=per_rank_gbs,
+            frac_of_duplex_copy_rate=(per_rank_gbs / link["duplex_gbs_per_direction"]) if link.get("duplex_gbs_per_direction") else None,
+            frac_of_duplex_copy_rate_all_ranks=(per_rank_gbs / link["duplex_gbs_per_direction_all_ranks_at_once_min"])
+            if link.get("duplex_gbs_per_direction_all_ranks_at_once_min") else None,
+            note="closed loop: every step waits for its results, so one launch + one synchronize (~10 us) sit on top of the "
+                 "transfer; the kernel reads / writes the pinned host buffers itself (zero copy), both directions at once")
+        # -- the same closed loop in Philox mode: no draw stream, 1 byte up + 2 bytes down per env (fewer host bytes for
+        #    boxes whose host side, not the link, is the limit at N > 2)
+        try:
+            eph = SoccerVecEnv(N, device=dev, kernel="table", rng_mode="philox", env_id_base=rank * N, seed=1, want_reset_obs=False)
+            eph.reset()
+            for i in range(2):
+                eph.step_host_packed(h_pk[i % 2][0])
+            barrier()
+            e0.record()
+            for i in range(Ke):
+                eph.step_host_packed(h_pk[i % 2][0])
+            e1.record()
+            barrier()
+            t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_packed["philox"] = {"value": world * N * Ke / (float(t.item()) * 1e-3), "h2d_bytes_per_step": N,
+                                    "d2h_bytes_per_step": 2 * N,
+                                    "api": "step_host_packed with rng_mode='philox': joint-action byte up, int16 result word down"}
+            del eph
+        except Exception as e:  # noqa: BLE001
+            e2e_packed["philox"] = {"error": repr(e)}
         del h_pk
+    # -- the registration default slip_prob = 0.2 (gym_soccer/__init__.py:8) from host buffers: natural dtypes, zero copy
+    e2e_slip = None
+    try:
+        n_s = min(N, 1 << 22)
+        es = SoccerVecEnv(n_s, slip_prob=0.2, device=dev, kernel="auto", want_reset_obs=False)
+        sa, sb, sr = es.alloc_host_inputs()
+        (s32,) = es._pinned(torch.int32)
+        sa.copy_(h_in[0][0][:n_s]); sb.copy_(h_in[0][1][:n_s]); sr.copy_(h_in[0][2][:n_s])
+        s32.copy_(torch.randint(-2**31, 2**31 - 1, (n_s,), dtype=torch.int32))
+        es.reset(sr.to(dev))
+        for i in range(2):
+            es.step_host(sa, sb, sr, rng32=s32)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(Ke):
+            es.step_host(sa, sb, sr, rng32=s32)
+        el = time.perf_counter() - t0
+        e2e_slip = {"value_per_gpu": n_s * Ke / el, "envs": n_s, "h2d_bytes_per_step": 7 * n_s, "d2h_bytes_per_step": 9 * n_s,
+                    "api": "step_host(act_a, act_b, rng8, rng32=...) on a slip_prob = 0.2 env: int32 obs / float32 reward / "
+                           "uint8 flags down"}
+        del es
+    except Exception as e:  # noqa: BLE001
+        e2e_slip = {"error": repr(e)}
 
     # ---------------- BASELINE configs 3 / 4 on EVERY rank: fused K = 64 rollouts (2^20 and 2^21 envs per GPU,
     # global env ids rank * n + local), 16 launches back to back = 1024 steps, then ONE all-reduce of the
@@ -456,6 +587,26 @@ def run_ours(args):
     except Exception as e:  # noqa: BLE001
         rollouts["error"] = repr(e)
 
+    # ---------------- hardware proof that trajectories do not depend on the GPU count: the SAME 2^24 global envs, sharded
+    # over the `world` GPUs of this run (contiguous global ids, env_id_base = rank * n), K2 in Philox mode, one NCCL
+    # all-reduce of the statistics; the result must be the constant the CPU oracle computed for the unsharded batch
+    shard = {"expected": SHARD_INVARIANT["stats"], "global_envs": SHARD_INVARIANT["envs"], "K": SHARD_INVARIANT["K"],
+             "seed": SHARD_INVARIANT["seed"], "shards": world}
+    try:
+        n_sh = SHARD_INVARIANT["envs"] // world
+        esh = SoccerVecEnv(n_sh, device=dev, kernel=args.kernel, rng_mode="philox", seed=SHARD_INVARIANT["seed"],
+                           env_id_base=rank * n_sh)
+        esh.reset()
+        _, _, _, st_sh = esh.rollout(SHARD_INVARIANT["K"], want_streams=False)
+        if world > 1:
+            dist.all_reduce(st_sh)
+        shard["stats_allreduce"] = [int(x) for x in st_sh.cpu()]
+        shard["shard_invariant"] = shard["stats_allreduce"] == SHARD_INVARIANT["stats"]
+        del esh
+    except Exception as e:  # noqa: BLE001
+        shard["error"] = repr(e)
+        shard["shard_invariant"] = False
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -517,17 +668,23 @@ def run_ours(args):
             in7 = [tuple(torch.randint(0, hi, (n7,), dtype=torch.uint8, device=dev, generator=g7) for hi in (5, 5, 16)) +
                    (torch.randint(-2**31, 2**31 - 1, (n7,), dtype=torch.int32, device=dev, generator=g7),) for _ in range(2)]
             variants = {}
-            for tag, kw, nbytes in (("slip0.2_injected", dict(slip_prob=0.2), 24), ("philox_draws", dict(rng_mode="philox"), 19)):
+            import numpy as np
+            pol7 = np.random.RandomState(0).randint(0, 5, 761).astype(np.int8)
+            # (tag, constructor kwargs, which inputs step() gets, algorithmic bytes per env-step)
+            cases7 = (("slip0.2_injected", dict(slip_prob=0.2), "abr32", 24),
+                      ("slip0.2_philox", dict(slip_prob=0.2, rng_mode="philox"), "ab", 19),
+                      ("philox_draws", dict(rng_mode="philox"), "ab", 19),
+                      ("single_agent_b_folded", dict(player_b_policy=pol7), "ar", 19),
+                      ("single_agent_a_folded_philox", dict(player_a_policy=pol7, rng_mode="philox"), "b", 18))
+            for tag, kw, use, nbytes in cases7:
                 e7 = SoccerVecEnv(n7, device=dev, kernel="table", want_reset_obs=False, **kw)
 
                 def step7(i):
                     a_, b_, r_, r32_ = in7[i % 2]
-                    if tag.startswith("slip"):
-                        e7.step(a_, b_, r_, rng32=r32_)
-                    else:
-                        e7.step(a_, b_)
-                e7.reset(in7[0][2] if tag.startswith("slip") else None)
-                for i in range(30):                 # play the population in (the slip fast path depends on it)
+                    e7.step(a_ if "a" in use else None, b_ if "b" in use else None, r_ if "r" in use else None,
+                            rng32=r32_ if "32" in use else None)
+                e7.reset(in7[0][2] if e7.rng_mode == "injected" else None)
+                for i in range(30):                 # play the population in
                     step7(i)
                 q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 torch.cuda.synchronize()
@@ -540,6 +697,26 @@ def run_ours(args):
                 variants[tag] = {"env_steps_per_s": n7 / (ms7 * 1e-3), "bytes_per_env_step": nbytes,
                                  "hbm_gbs": n7 * nbytes / (ms7 * 1e-3) / 1e9, "frac_of_hbm_peak": n7 * nbytes / (ms7 * 1e-3) / 1e9 / peak}
                 del e7
+            # K2 with slip_prob = 0.2 (2^22 envs x K = 16): integer-threshold fast path, 4 envs per thread
+            e8 = SoccerVecEnv(1 << 22, slip_prob=0.2, device=dev, kernel="table", rng_mode="philox")
+            e8.reset()
+            b8 = (torch.empty((16, 1 << 22), dtype=torch.int32, device=dev), torch.empty((16, 1 << 22), dtype=torch.float32, device=dev),
+                  torch.empty((16, 1 << 22), dtype=torch.uint8, device=dev))
+            e8.rollout(64, want_streams=False)
+            for _ in range(2):
+                e8.rollout(16, out=b8)
+            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            q0.record()
+            for _ in range(6):
+                e8.rollout(16, out=b8)
+            q1.record()
+            torch.cuda.synchronize()
+            ms8 = q0.elapsed_time(q1) / 6
+            extra["k2_slip0.2_2^22_envs_K16"] = {"env_steps_per_s": (1 << 26) / (ms8 * 1e-3),
+                                                 "hbm_gbs_at_9.125B": (1 << 26) * 9.125 / (ms8 * 1e-3) / 1e9,
+                                                 "frac_of_hbm_peak": (1 << 26) * 9.125 / (ms8 * 1e-3) / 1e9 / peak}
+            del e8, b8
             extra["k1_variants_2^24_envs"] = variants
             del in7
             torch.cuda.empty_cache()
@@ -645,6 +822,16 @@ def run_ours(args):
     cores = os.cpu_count() or 1
     cpu_v, cpu_sample = time_cpu_port(args.cpu_seconds, 1)
     cpu_all_v, _ = time_cpu_port(min(args.cpu_seconds, 5.0), cores)
+    # BASELINE config 1 through the UNMODIFIED Python reference on this host (oracle/_ref, staged by build()): 100,000
+    # step() calls, 1 core, RandomState(123) actions -- BASELINE.md's CPU-baseline plan
+    py_ref = None
+    try:
+        from oracle import time_reference
+        py_ref = time_reference.time_python_reference(100000, 0.0)
+        if py_ref is not None and "error" not in py_ref:
+            py_ref["slip_0_2_steps_per_s"] = (time_reference.time_python_reference(50000, 0.2) or {}).get("steps_per_s")
+    except Exception as e:  # noqa: BLE001
+        py_ref = {"error": repr(e)}
 
     kname = "k_step_table" if env.kernel == "table" else "k_step_fast"
     traffic, traffic_src = ncu_traffic(kname) if N == (1 << 24) else (None, None)
@@ -659,7 +846,7 @@ def run_ours(args):
     if e2e_packed is not None:
         e2e_line = dict(e2e_packed, unit=UNIT, steps=Ke, cpus_bound_near_gpu=numa_cpus,
                         closed_loop="every step waits for its results on the host before the next one is enqueued",
-                        narrow=e2e_narrow, wide=e2e_wide)
+                        narrow=e2e_narrow, wide=e2e_wide, slip_0_2=e2e_slip)
     else:
         e2e_line = dict(e2e_narrow, unit=UNIT, steps=Ke, cpus_bound_near_gpu=numa_cpus, wide=e2e_wide)
     emit_json(json.dumps({
@@ -686,13 +873,19 @@ def run_ours(args):
                                                   "without the game logic = practical ceiling for its 7 B read / "
                                                   "13 B written mix"}},
         "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": 1, "kind": "port", "sample": cpu_sample, "host": host_info(),
-                         "all_cores": {"value": cpu_all_v, "cores": cores}},
+                         "all_cores": {"value": cpu_all_v, "cores": cores},
+                         "python_reference": py_ref if py_ref is not None else
+                         "oracle/_ref absent (build() stages it where /root/reference exists)"},
+        "host": host_info(),
+        "shard_invariant": shard.get("shard_invariant"), "shard_invariant_detail": shard,
+        "timed_region": {"steps": K, "statistics": "fused into K1 (soccer_step_args.stats)", "tail_after_last_step_us": tail_us,
+                         "tail_is": "the NCCL sum all-reduce of the 48-byte statistics vector" if world > 1 else "nothing (1 GPU)"},
         "e2e": e2e_line,
         "sustained": sustained,
         "gpu_launches": K,
         "clocks": clocks,
         "extra": extra,
-        "stats_allreduce": None if stats is None else [int(x) for x in stats.cpu()],
+        "stats_allreduce": stats_timed,
     }))
     if world > 1:
         dist.destroy_process_group()

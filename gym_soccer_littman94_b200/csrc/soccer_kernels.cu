@@ -947,15 +947,27 @@ int step_table_slip_impl(const PitchDev& P, int64_t bytes, const soccer_step_arg
     int64_t done_n = 0;
     if (vec) {
         const int64_t n_groups = n / 4;
-        // with a slip index, and room for it and the deferral queue next to the table (5x4): constant-prefix fast
-        // path + queued walk; else the in-place walk
+        // With a slip index and room for it next to the table (5x4): 32-bit draws (rng32 / Philox) take the integer-
+        // threshold fast path (k_step_table_slip_i, index plane 1), fp64 draws the constant-prefix fast path + queued
+        // walk (k_step_table_slip_q, plane 0); else the in-place walk.
         const int64_t fc_bytes = ((int64_t)P.nS * 25 + 15) / 16 * 16;
         const int64_t smem_q = bytes + 16 + fc_bytes + pol_bytes + (int64_t)kSlipQueueBytes;
+        const int64_t smem_i = bytes + 16 + 2 * fc_bytes + pol_bytes + (int64_t)kSlipIntLutBytes;
         const int64_t smem_w = bytes + 16 + pol_bytes;
         if (smem_w > 227 * 1024 - 2048) return SOCCER_ETABLE;
         SlipE E;                                      // E_k: sequential fp64 sums of the combination probabilities (SIM:241, nsp = 1)
         { double acc = 0.0; for (int c = 0; c < 9; ++c) { acc += P.mp[c]; E.e[c] = acc; } }
-        const bool queued = a->slip_index && smem_q <= 227 * 1024 - 1024 - (a->rngf64 ? 0 : 4096);
+        const bool f64 = !philox && a->rngf64;
+        const bool queued = a->slip_index && f64 && smem_q <= 227 * 1024 - 1024;
+        const bool integer = a->slip_index && !f64 && smem_i <= 227 * 1024 - 1024;
+#define SOCCER_LAUNCH_SLIP_I(RO, PH)                                                                      \
+        do {                                                                                              \
+            const int e0 = allow_big_smem(k_step_table_slip_i<RO, PH>, smem_i);                           \
+            if (e0) return e0;                                                                            \
+            k_step_table_slip_i<RO, PH><<<table_grid(n_groups, kSlipIThreads), kSlipIThreads, (size_t)smem_i, st>>>(  \
+                P, a->table, (uint32_t)bytes, a->slip_index + fc_bytes, (uint32_t)(2 * fc_bytes), E, a->state, act_a, act_b, \
+                a->rng8, a->rng32, a->obs, a->reward, a->flags, a->reset_obs, n_groups, ex);              \
+        } while (0)
 #define SOCCER_LAUNCH_SLIP_T(RO, DRAW)                                                                    \
         do {                                                                                              \
             if (queued) {                                                                                 \
@@ -974,13 +986,15 @@ int step_table_slip_impl(const PitchDev& P, int64_t bytes, const soccer_step_arg
         } while (0)
 #define SOCCER_PICK_SLIP_T(RO)                                                                            \
         do {                                                                                              \
-            if (philox) SOCCER_LAUNCH_SLIP_T(RO, kDrawPhilox);                                            \
+            if (integer) { if (philox) SOCCER_LAUNCH_SLIP_I(RO, true); else SOCCER_LAUNCH_SLIP_I(RO, false); } \
+            else if (philox) SOCCER_LAUNCH_SLIP_T(RO, kDrawPhilox);                                       \
             else if (a->rngf64) SOCCER_LAUNCH_SLIP_T(RO, kDrawF64);                                       \
             else SOCCER_LAUNCH_SLIP_T(RO, kDrawU32);                                                      \
         } while (0)
         if (a->reset_obs) SOCCER_PICK_SLIP_T(true); else SOCCER_PICK_SLIP_T(false);
 #undef SOCCER_PICK_SLIP_T
 #undef SOCCER_LAUNCH_SLIP_T
+#undef SOCCER_LAUNCH_SLIP_I
         const int e = launch_status();
         if (e) return e;
         done_n = n_groups * 4;
@@ -1035,7 +1049,8 @@ int step_table_ex(const soccer_pitch* pitch, const soccer_step_args* a, soccer_s
         do {                                                                                                      \
             const int e0 = allow_big_smem(k_step_table<RO, PH, NR, PL, ST>, smem);                                \
             if (e0) return e0;                                                                                    \
-            const int e1 = launch_pdl(k_step_table<RO, PH, NR, PL, ST>, table_grid(n_groups), kTableThreads, (size_t)smem, st, \
+            constexpr int thr = k1_threads<PH, PL, ST>();                                                         \
+            const int e1 = launch_pdl(k_step_table<RO, PH, NR, PL, ST>, table_grid(n_groups, thr), thr, (size_t)smem, st, \
                                       P, a->table, (uint32_t)bytes, a->state, a->act_a, a->act_b, a->rng8, a->obs, a->reward, \
                                       a->flags, RO ? a->reset_obs : (int32_t*)nullptr, n_groups, key, ex);        \
             if (e1) return e1;                                                                                    \
@@ -1166,7 +1181,7 @@ int soccer_slip_index_bytes_host(const soccer_pitch* pitch, int64_t* bytes)
     if (!bytes) return SOCCER_EINVAL;
     PitchDev P; const int rc = make_pitch_dev(pitch, &P); if (rc) return rc;
     int64_t tb; const int rc2 = table_bytes_of(P, &tb); if (rc2) return rc2;
-    *bytes = ((int64_t)P.nS * 25 + 15) / 16 * 16;
+    *bytes = 3 * (((int64_t)P.nS * 25 + 15) / 16 * 16);      // plane 0 (fp64 draws): bytes; plane 1 (32-bit draws): uint16
     return SOCCER_OK;
 }
 
@@ -1175,7 +1190,10 @@ int soccer_build_slip_index(const soccer_pitch* pitch, const uint16_t* table, ui
     if (!table || !slip_index) return SOCCER_EINVAL;
     PitchDev P; int rc = make_pitch_dev(pitch, &P); if (rc) return rc;
     int64_t tb; rc = table_bytes_of(P, &tb); if (rc) return rc;
-    k_build_slip_index<<<grid_for((int64_t)P.nS * 25, 4), kThreads, 0, (cudaStream_t)stream>>>(P, P.nS, table, slip_index);
+    const int64_t plane = ((int64_t)P.nS * 25 + 15) / 16 * 16;
+    const cudaError_t e = cudaMemsetAsync(slip_index, 0, (size_t)(3 * plane), (cudaStream_t)stream);
+    if (e != cudaSuccess) return (int)e;
+    k_build_slip_index<<<grid_for((int64_t)P.nS * 25, 4), kThreads, 0, (cudaStream_t)stream>>>(P, P.nS, table, slip_index, plane);
     return launch_status();
 }
 
@@ -1233,25 +1251,32 @@ int soccer_rollout_table_policy(const soccer_pitch* pitch, const uint16_t* table
         else SOCCER_LAUNCH_ROLLOUT_T(1, false, POL, SLIP, n);                                            \
     } while (0)
     if (P.slip) {
-        // with the slip index and room for it next to the table (5x4): 4 envs per thread, constant-prefix fast path +
-        // per-step warp queue (k_rollout_table_slipq); else the in-place walk, one env per thread (the walk's registers)
+        // with the slip index and room for it next to the table (5x4): integer-threshold fast path, 4 envs per thread
+        // (k_rollout_table_slipi); else the in-place walk, one env per thread (the walk's registers)
         const int64_t fc_bytes = ((int64_t)P.nS * 25 + 15) / 16 * 16;
-        const int64_t smem_q = bytes + 16 + fc_bytes + (pol ? pol_bytes : 0) + (int64_t)kXqWarpBytes * (kRolloutThreads / 32);
-        if (slip_index && vec && smem_q <= 227 * 1024 - 6144) {
+        const int64_t smem_i = bytes + 16 + 2 * fc_bytes + (pol ? pol_bytes : 0) + (int64_t)kSlipIntLutBytes;
+        if (slip_index && smem_i <= 227 * 1024 - 2048) {
             SlipE E;
             { double acc = 0.0; for (int c = 0; c < 9; ++c) { acc += P.mp[c]; E.e[c] = acc; } }
-#define SOCCER_LAUNCH_ROLLOUT_Q(STR, POL)                                                                \
+#define SOCCER_LAUNCH_ROLLOUT_I(VEC, STR, POL, ITEMS)                                                    \
             do {                                                                                         \
-                const int e0 = allow_big_smem(k_rollout_table_slipq<STR, POL>, smem_q);                  \
+                const int e0 = allow_big_smem(k_rollout_table_slipi<VEC, STR, POL>, smem_i);             \
                 if (e0) return e0;                                                                       \
-                const int e1 = launch_pdl(k_rollout_table_slipq<STR, POL>, table_grid(n / 4, kRolloutThreads), kRolloutThreads, \
-                                          (size_t)smem_q, st, P, table, (uint32_t)bytes, slip_index, (uint32_t)fc_bytes, E, \
-                                          policy_a, policy_b, ra);                                       \
+                const int e1 = launch_pdl(k_rollout_table_slipi<VEC, STR, POL>, table_grid(ITEMS, kRolloutThreads), \
+                                          kRolloutThreads, (size_t)smem_i, st, P, table, (uint32_t)bytes, \
+                                          slip_index + fc_bytes, (uint32_t)(2 * fc_bytes), E, policy_a, policy_b, ra); \
                 if (e1) return e1;                                                                       \
             } while (0)
-            if (streams) { if (pol) SOCCER_LAUNCH_ROLLOUT_Q(true, true); else SOCCER_LAUNCH_ROLLOUT_Q(true, false); }
-            else { if (pol) SOCCER_LAUNCH_ROLLOUT_Q(false, true); else SOCCER_LAUNCH_ROLLOUT_Q(false, false); }
-#undef SOCCER_LAUNCH_ROLLOUT_Q
+#define SOCCER_PICK_ROLLOUT_I(POL)                                                                       \
+            do {                                                                                         \
+                if (vec && streams) SOCCER_LAUNCH_ROLLOUT_I(4, true, POL, n / 4);                        \
+                else if (vec) SOCCER_LAUNCH_ROLLOUT_I(4, false, POL, n / 4);                             \
+                else if (streams) SOCCER_LAUNCH_ROLLOUT_I(1, true, POL, n);                              \
+                else SOCCER_LAUNCH_ROLLOUT_I(1, false, POL, n);                                          \
+            } while (0)
+            if (pol) SOCCER_PICK_ROLLOUT_I(true); else SOCCER_PICK_ROLLOUT_I(false);
+#undef SOCCER_PICK_ROLLOUT_I
+#undef SOCCER_LAUNCH_ROLLOUT_I
         }
         else if (streams) SOCCER_LAUNCH_ROLLOUT_T(1, true, true, true, n);
         else SOCCER_LAUNCH_ROLLOUT_T(1, false, true, true, n);
@@ -1542,6 +1567,58 @@ int soccer_plan(const soccer_pitch* pitch, const int8_t* policy_a, const int8_t*
     const int grid = grid_for((int64_t)P.nS * (pi_in ? 1 : nkeys), nb);
     void* args[] = { (void*)&P, (void*)&a };
     e = cudaLaunchCooperativeKernel((const void*)k_plan, dim3((unsigned)grid), dim3(kThreads), args, 0, st);
+    return (int)e;
+}
+
+int soccer_dense_q(const soccer_pitch* pitch, const int8_t* policy_a, const int8_t* policy_b, const double* v, double gamma,
+                   double* q, soccer_stream_t stream)
+{
+    if (!v || !q) return SOCCER_EINVAL;
+    if (policy_a && policy_b) return SOCCER_EPOLICY;
+    PitchDev P; const int rc = make_pitch_dev(pitch, &P); if (rc) return rc;
+    soccer_pitch_info info; fill_info(pitch, &info);
+    const int nkeys = (policy_a || policy_b) ? 5 : 25;
+    const int n_goal_states = 2 * (2 * info.n_goal_rows) * info.n_field_cells;
+    k_dense_q<<<grid_for((int64_t)P.nS * nkeys, 8), kThreads, 0, (cudaStream_t)stream>>>(P, P.nS, n_goal_states, policy_a, policy_b,
+                                                                                         v, gamma, q);
+    return launch_status();
+}
+
+int soccer_policy_eval_workspace_bytes_host(const soccer_pitch* pitch, int32_t nkeys, int64_t* bytes)
+{
+    if (!bytes || (nkeys != 5 && nkeys != 25)) return SOCCER_EINVAL;
+    PitchDev P; const int rc = make_pitch_dev(pitch, &P); if (rc) return rc;
+    *bytes = 2 * (int64_t)P.nS * 8 + 2 * (int64_t)P.nS * nkeys * 8 + 32;
+    return SOCCER_OK;
+}
+
+int soccer_policy_eval(const soccer_pitch* pitch, const int8_t* policy_a, const int8_t* policy_b, const double* policy,
+                       const double* v_init, double theta, double gamma, int32_t max_sweeps, double* V_out,
+                       int32_t* sweeps_out, void* workspace, soccer_stream_t stream)
+{
+    if (!policy || !V_out || !sweeps_out || !workspace || max_sweeps < 0 || !aligned(workspace, 8)) return SOCCER_EINVAL;
+    if (policy_a && policy_b) return SOCCER_EPOLICY;
+    PitchDev P; const int rc = make_pitch_dev(pitch, &P); if (rc) return rc;
+    soccer_pitch_info info; fill_info(pitch, &info);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nkeys = (policy_a || policy_b) ? 5 : 25;
+    PolicyEvalArgs a;
+    a.nS = P.nS; a.n_goal_states = 2 * (2 * info.n_goal_rows) * info.n_field_cells;
+    a.policy_a = policy_a; a.policy_b = policy_b; a.policy = policy;
+    a.theta = theta; a.gamma = gamma; a.max_sweeps = max_sweeps;
+    a.v0 = reinterpret_cast<double*>(workspace); a.v1 = a.v0 + P.nS;
+    a.part = a.v1 + P.nS;
+    a.delta = reinterpret_cast<unsigned long long*>(a.part + 2 * (int64_t)P.nS * nkeys);
+    a.V_out = V_out; a.sweeps_out = sweeps_out;
+    cudaError_t e = cudaMemsetAsync(a.delta, 0, 32, st);
+    if (e != cudaSuccess) return (int)e;
+    e = v_init ? cudaMemcpyAsync(a.v0, v_init, sizeof(double) * (size_t)P.nS, cudaMemcpyDeviceToDevice, st)
+               : cudaMemsetAsync(a.v0, 0, sizeof(double) * (size_t)P.nS, st);         // PL:58
+    if (e != cudaSuccess) return (int)e;
+    static const int nb = resident_blocks(k_policy_eval);
+    const int grid = grid_for((int64_t)P.nS * nkeys, nb);
+    void* args[] = { (void*)&P, (void*)&a };
+    e = cudaLaunchCooperativeKernel((const void*)k_policy_eval, dim3((unsigned)grid), dim3(kThreads), args, 0, st);
     return (int)e;
 }
 

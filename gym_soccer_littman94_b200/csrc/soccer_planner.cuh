@@ -171,4 +171,131 @@ k_plan(const PitchDev P, const PlanArgs a)
     if (gtid == 0) *a.sweeps_out = sweep;
 }
 
+// ---- the DENSE planners: policy_eval (PL:57-70) and modified_policy_iteration (PL:73-87) are written against
+// Pmat[s][s'][a] / Rmat[s][a] in the reference (np.dot).  Pmat is >= 99.9 % zeros -- a row has at most 15 non-zeros -- so
+// the contraction is done sparsely, over the same on-the-fly list as above:
+//     Rmat[s][a]           = sum over the list of prob * reward                      (SIM:263, same order: bit-identical)
+//     (Pmat[s][:][a] . v)  = sum over the list of prob * v[next_obs]                 (SIM:262 merges equal next_obs first and
+//                                                                                     BLAS sums in its own order: equal to
+//                                                                                     fp64 round-off, ~1e-16 relative)
+// There is no (not done) factor in the dense form: a goal contributes prob * v[0], and row 0 carries the reference's
+// quirk Pmat[0][0][a] = (number of goal states) x sum of the combination probabilities (SIM:182-183, 262).
+struct DenseSA { double r, pv; };
+__device__ __forceinline__ DenseSA dense_backup(const PitchDev& P, const uint8_t* __restrict__ lut, int32_t s_obs, int key,
+                                                const int8_t* __restrict__ policy_a, const int8_t* __restrict__ policy_b,
+                                                const double* v, int32_t n_goal_states)
+{
+    DenseSA o = { 0.0, 0.0 };
+    if (s_obs == 0) {
+        double acc = 0.0;
+        for (int gsi = 0; gsi < n_goal_states; ++gsi)
+            for (int c = 0; c < 9; ++c)
+                if (P.mp[c] != 0.0) acc = __dadd_rn(acc, __dmul_rn(P.mp[c], 1.0));
+        o.pv = __dmul_rn(acc, __ldcg(v));
+        return o;
+    }
+    const uint32_t st = obs_to_packed(P, s_obs);
+    const uint32_t a = st & 0xFFu, b = (st >> 8) & 0xFFu, p = (st >> 24) & 1u;
+    uint32_t aa, ab;
+    if (!policy_a && !policy_b) { aa = (uint32_t)key / 5u; ab = (uint32_t)key % 5u; }
+    else if (policy_b) { aa = (uint32_t)key; ab = (uint32_t)policy_b[s_obs]; }
+    else { aa = (uint32_t)policy_a[s_obs]; ab = (uint32_t)key; }
+    const bool flip = policy_a != nullptr;
+    for (int c = 0; c < 9; ++c) {
+        const double mp = P.mp[c];
+        if (mp == 0.0) continue;
+        const int ca = combo_a(c), cb = combo_b(c);
+        const uint32_t ma = ca == 0 ? aa : slip_move(aa, ca - 1);
+        const uint32_t mb = cb == 0 ? ab : slip_move(ab, cb - 1);
+        const Resolved o0 = resolve(lut, a, b, p, ma, mb, aa == 0, ab == 0, 0u);
+        const uint32_t n = 1u << o0.nlog2;
+        const double pr = __dmul_rn(mp, n == 4 ? 0.25 : (n == 2 ? 0.5 : 1.0));
+        for (uint32_t k = 0; k < n; ++k) {
+            const Resolved r = resolve(lut, a, b, p, ma, mb, aa == 0, ab == 0, n == 2 ? (k << 1) : k);
+            const StepOut f = finish_step<false>(P, r, 0u, 0u, 0u, flip);
+            o.r = __dadd_rn(o.r, __dmul_rn(pr, (double)f.reward));
+            o.pv = __dadd_rn(o.pv, __dmul_rn(pr, __ldcg(v + f.obs)));
+        }
+    }
+    return o;
+}
+
+// q[s][key] = Rmat[s][key] + gamma * (Pmat[s][:][key] . v)   (PL:78-79)
+__global__ void __launch_bounds__(kThreads)
+k_dense_q(const PitchDev P, int32_t nS, int32_t n_goal_states, const int8_t* __restrict__ policy_a,
+          const int8_t* __restrict__ policy_b, const double* __restrict__ v, double gamma, double* __restrict__ q)
+{
+    __shared__ __align__(16) uint8_t lut[kLutBytes];
+    build_cand_lut(lut, P);
+    const int nkeys = (!policy_a && !policy_b) ? 25 : 5;
+    const int64_t total = (int64_t)nS * nkeys;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const DenseSA d = dense_backup(P, lut, (int32_t)(i / nkeys), (int)(i % nkeys), policy_a, policy_b, v, n_goal_states);
+        q[i] = __dadd_rn(d.r, __dmul_rn(gamma, d.pv));
+    }
+}
+
+struct PolicyEvalArgs {
+    int32_t nS, n_goal_states; const int8_t* policy_a; const int8_t* policy_b;
+    const double* policy;          // [nS][nkeys] stochastic policy (PL:57: policy[s, :])
+    double theta, gamma; int32_t max_sweeps;
+    double* v0; double* v1;        // ping-pong vectors [nS]; v0 holds the initial v (PL:58)
+    double* part;                  // [nS][nkeys] per-(s, key) terms of a sweep
+    unsigned long long* delta;     // [3] zero-filled
+    double* V_out; int32_t* sweeps_out;
+};
+
+// policy_eval(env, policy, theta, gamma, k, init) (PL:57-70) in ONE cooperative launch: at most max_sweeps sweeps of
+//     v[s] <- policy[s, :] . Rmat[s, :] + gamma * (Pmat[s, :, :]^T v) . policy[s, :]
+// until the sup-norm change is below theta.  One thread per (s, key) for the sparse contraction, one per s for the
+// policy-weighted sum (in key order, like np.dot over 5 or 25 elements).
+__global__ void __launch_bounds__(kThreads)
+k_policy_eval(const PitchDev P, const PolicyEvalArgs a)
+{
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ __align__(16) uint8_t lut[kLutBytes];
+    __shared__ double red[kThreads / 32];
+    build_cand_lut(lut, P);
+    const int nkeys = (!a.policy_a && !a.policy_b) ? 25 : 5;
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t total = (int64_t)a.nS * nkeys;
+    double* V = a.v0;
+    double* Vn = a.v1;
+    int32_t sweep = 0;
+    while (sweep < a.max_sweeps) {
+        ++sweep;
+        unsigned long long* dslot = a.delta + sweep % 3;
+        if (gtid == 0) a.delta[(sweep + 1) % 3] = 0ull;
+        for (int64_t i = gtid; i < total; i += stride) {
+            const DenseSA d = dense_backup(P, lut, (int32_t)(i / nkeys), (int)(i % nkeys), a.policy_a, a.policy_b, V, a.n_goal_states);
+            const double w = a.policy[i];
+            // r_pi and p_pi terms of this key: combined per state below
+            a.part[2 * i] = __dmul_rn(w, d.r);
+            a.part[2 * i + 1] = __dmul_rn(d.pv, w);
+        }
+        grid.sync();
+        double dl = 0.0;
+        for (int64_t s = gtid; s < a.nS; s += stride) {
+            double r_pi = 0.0, p_pi = 0.0;
+            for (int k = 0; k < nkeys; ++k) {
+                r_pi = __dadd_rn(r_pi, __ldcg(a.part + 2 * (s * nkeys + k)));
+                p_pi = __dadd_rn(p_pi, __ldcg(a.part + 2 * (s * nkeys + k) + 1));
+            }
+            const double val = __dadd_rn(r_pi, __dmul_rn(a.gamma, p_pi));      // PL:65
+            Vn[s] = val;
+            dl = fmax(dl, fabs(val - __ldcg(V + s)));                          // PL:66
+        }
+        block_max_to_global(dl, dslot, red);
+        grid.sync();
+        const double dmax = __longlong_as_double((long long)*(volatile unsigned long long*)dslot);
+        double* t = V; V = Vn; Vn = t;                                         // PL:67
+        if (dmax < a.theta) break;                                             // PL:69-70
+    }
+    for (int64_t s = gtid; s < a.nS; s += stride) a.V_out[s] = __ldcg(V + s);
+    if (gtid == 0) *a.sweeps_out = sweep;
+}
+
 } // namespace soccer

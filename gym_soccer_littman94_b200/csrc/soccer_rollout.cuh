@@ -2,8 +2,8 @@
 //
 //   k_rollout_table        5x4-class pitches: transition table in shared memory (soccer_table.cuh), uniform or table
 //                          policies; 148 x 512-thread CTAs
-//   k_rollout_table_slipq  the same for slip_prob > 0: constant-prefix fast path + a per-step warp queue for the envs
-//                          whose draw needs the reference's cumulative walk
+//   k_rollout_table_slipi  the same for slip_prob > 0: combination and slot of the 32-bit Philox draw from constant
+//                          integer thresholds (slip index plane 1); the reference's cumulative walk only where flagged
 //   k_rollout              any pitch: rules inline -- byte-parallel step4_noslip() for the uniform policy,
 //                          the scalar step for on-device TABLE policies (int8[nS], the reference's
 //                          utils/policies.py dict format); 256-thread CTAs
@@ -36,7 +36,7 @@ struct RolloutArgs {
 // runs: with 2^20+ envs the kernel sits at the HBM write ceiling (0.92-0.99 of the traffic probe), not on issue.
 template <bool POLICY, bool SLIP>
 struct TableStepper {
-    static constexpr bool kCollective = false;
+    static constexpr bool kCollective = false, kHasPolicy = POLICY;
     TblCtx c;
     uint32_t pol_a, pol_b;      // shared-window addresses of the int8[nS] table policies, 0 = uniform (POLICY only)
     SlipCtx sc;                 // slip-combination probability table (SLIP only)
@@ -48,7 +48,7 @@ struct TableStepper {
         uint32_t ff[4] = { 0, 0, 0, 0 };
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
-            // jr = mulhi(w, 100) is the table column; (w & 3) * 4 the byte offset of the start observation
+            // jr = mulhi(w, 100) is the table column; w & 0xC the byte offset of the start observation (reset draw = bits 2..3)
             uint32_t jr = philox_jr(word[e]);
             uint32_t aa = 0, ab = 0;
             if (POLICY || SLIP) {
@@ -62,8 +62,8 @@ struct TableStepper {
             }
             // slip_prob > 0: the in-place walk with the word's 32-bit step draw (6x4, where the slip index does not fit)
             const TblOut o = SLIP ? table_step_slip(c, sc, s[e], aa, ab, u_from_rng32(philox_r32(word[e])),
-                                                    (word[e] << 2) & 0xCu)
-                                  : table_step(c, s[e], jr, (word[e] << 2) & 0xCu);
+                                                    word[e] & 0xCu)
+                                  : table_step(c, s[e], jr, word[e] & 0xCu);
             s[e] = o.state; oo[e] = o.obs; rr[e] = __float_as_uint((float)(flip ? -o.rew_i : o.rew_i)); ff[e] = o.flags;
             net += o.rew_i;
         }
@@ -71,34 +71,26 @@ struct TableStepper {
     }
 };
 
-// slip_prob > 0 with the slip index (5x4): the K1 fast path (table_step_slip_fast: constant-prefix pick through the
-// 4096-bucket table of the 32-bit draw + one mask byte per (obs, joint action)) for the ~85 % of the env-steps it
-// decides, and a PER-STEP warp queue for the rest.  The state lives in the owner's registers, so a deferred env
-// travels through a 12-byte slot of the warp's shared-memory exchange area: the owner writes (state, draw, actions),
-// lane j of the warp walks queue entry j with the reference's cumulative sums (table_step_slip) and writes the result
-// back, the owner picks it up.  One walk pass per warp and step serves all of its deferred envs (19 of 128 on
-// average at slip 0.2) instead of one divergent walk per env slot.  Bit-identical to the in-place walk.
-constexpr int kXqSlot = 12;                        // bytes per exchange slot
-constexpr int kXqWarpBytes = 128 * kXqSlot;        // every env of the warp could be deferred
+// slip_prob > 0 with the slip index (5x4): every Philox draw is a 32-bit draw, so combination AND slot come from
+// constant integer thresholds (table_step_slip_int, soccer_table.cuh); the reference's cumulative walk is only taken
+// by the (in practice non-existent) picks the index flags.  4 envs per thread like the slip-0 stepper.
+// (First version of this round: the fp64 constant-prefix fast path + a per-step warp queue through shared memory
+// for the ~15 % of the env-steps it could not decide -- bit-identical, 150-164 G env-steps/s: one 170-instruction walk
+// pass per warp and step whatever the number of queued envs, + ~25 instructions of queue bookkeeping per env-step;
+// profiles/r02b_time_round2.log, r02b_ncu_k2slip_queue_by_line.txt.)
 template <bool POLICY>
-struct TableSlipQStepper {
-    static constexpr bool kCollective = true;
-    TblCtx c; SlipCtx sc; SlipFast sf;
+struct TableSlipIntStepper {
+    static constexpr bool kCollective = false, kHasPolicy = POLICY;
+    TblCtx c; SlipCtx sc; SlipInt sf;
     uint32_t pol_a, pol_b;
-    uint32_t xq;                                    // shared-window address of this warp's exchange slots
     __device__ __forceinline__ uint32_t timestep(uint32_t s) const { return s >> 16; }
     template <int VEC>
     __device__ __forceinline__ void step(uint32_t* s, const uint32_t* word, uint32_t* oo, uint32_t* rr,
                                          uint32_t& fw, int32_t& net, bool flip) const
     {
-        static_assert(VEC == 4, "the queued slip stepper owns 4 envs per thread");
-        const uint32_t lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u;
-        const SlipE noE = {};
-        uint32_t ff[4], pos[4], cnt = 0;
-        int32_t rw[4];
-        bool df[4];
+        uint32_t ff[4] = { 0, 0, 0, 0 };
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
+        for (int e = 0; e < VEC; ++e) {
             uint32_t aa, ab;
             philox_actions(word[e], aa, ab);
             if (POLICY) {
@@ -106,54 +98,14 @@ struct TableSlipQStepper {
                 if (pol_a) aa = lds_u8_r(pol_a + cur);
                 if (pol_b) ab = lds_u8_r(pol_b + cur);
             }
-            const uint32_t r32 = philox_r32(word[e]), rsel4 = (word[e] << 2) & 0xCu;
-            bool defer;
-            const TblOut o = table_step_slip_fast<false>(c, sf, noE, s[e], aa, ab, 0.0, r32, rsel4, defer);
-            const uint32_t m = __ballot_sync(0xFFFFFFFFu, defer);
-            pos[e] = cnt + __popc(m & lt_mask);
-            cnt += __popc(m);
-            df[e] = defer;
-            if (defer) {
-                const uint32_t slot = xq + pos[e] * kXqSlot;
-                asm volatile("st.shared.u32 [%0], %1;" :: "r"(slot), "r"(s[e]) : "memory");
-                asm volatile("st.shared.u32 [%0], %1;" :: "r"(slot + 4u), "r"(r32) : "memory");
-                asm volatile("st.shared.u32 [%0], %1;" :: "r"(slot + 8u), "r"(aa | (ab << 4) | (rsel4 << 8)) : "memory");
-            } else {
-                s[e] = o.state;
-            }
-            oo[e] = o.obs; rw[e] = o.rew_i; ff[e] = o.flags;
+            const uint32_t r32 = philox_r32(word[e]), rsel4 = word[e] & 0xCu;
+            bool walk;
+            TblOut o = table_step_slip_int<false>(c, sf, s[e], aa, ab, r32, rsel4, walk);
+            if (walk) o = table_step_slip_walk(c, sc, s[e], aa, ab, r32, rsel4);
+            s[e] = o.state; oo[e] = o.obs; rr[e] = __float_as_uint((float)(flip ? -o.rew_i : o.rew_i)); ff[e] = o.flags;
+            net += o.rew_i;
         }
-        if (cnt) {                                                       // warp-uniform
-            __syncwarp();
-            for (uint32_t first = 0; first < cnt; first += 32u) {
-                const uint32_t idx = first + lane;
-                if (idx < cnt) {
-                    const uint32_t slot = xq + idx * kXqSlot;
-                    uint32_t qs, qr, qm;
-                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(qs) : "r"(slot) : "memory");
-                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(qr) : "r"(slot + 4u) : "memory");
-                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(qm) : "r"(slot + 8u) : "memory");
-                    const TblOut o = table_step_slip(c, sc, qs, qm & 15u, (qm >> 4) & 15u, u_from_rng32(qr), (qm >> 8) & 0xCu);
-                    asm volatile("st.shared.u32 [%0], %1;" :: "r"(slot), "r"(o.state) : "memory");
-                    asm volatile("st.shared.u32 [%0], %1;" :: "r"(slot + 4u), "r"(o.obs | (o.flags << 12) | (((uint32_t)o.rew_i & 3u) << 14)) : "memory");
-                }
-            }
-            __syncwarp();
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                if (df[e]) {
-                    const uint32_t slot = xq + pos[e] * kXqSlot;
-                    uint32_t qs; int32_t qw;
-                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(qs) : "r"(slot) : "memory");
-                    asm volatile("ld.shared.s16 %0, [%1];" : "=r"(qw) : "r"(slot + 4u) : "memory");
-                    s[e] = qs; oo[e] = (uint32_t)qw & kTblObsMask; ff[e] = ((uint32_t)qw >> 12) & 3u; rw[e] = qw >> 14;
-                }
-            }
-            __syncwarp();                                                // slots free before the next step refills them
-        }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) { rr[e] = __float_as_uint((float)(flip ? -rw[e] : rw[e])); net += rw[e]; }
-        fw = pack4(ff[0], ff[1], ff[2], ff[3]);
+        fw = VEC == 4 ? pack4(ff[0], ff[1], ff[2], ff[3]) : ff[0];
     }
 };
 
@@ -161,7 +113,7 @@ struct TableSlipQStepper {
 // run-time branch the 4-env kernel needed 170 registers instead of 116 and lost its second resident CTA)
 template <bool SLIP>
 struct RulesStepper {
-    static constexpr bool kCollective = false;
+    static constexpr bool kCollective = false, kHasPolicy = true;
     const PitchDev& P; const uint8_t* lut; Isd4 I; const int8_t* policy_a; const int8_t* policy_b; SlipCtx sc;
     __device__ __forceinline__ uint32_t timestep(uint32_t s) const { return (s >> 16) & 0xFFu; }
     template <int VEC>
@@ -181,7 +133,7 @@ struct RulesStepper {
                     if (policy_b) ab = (uint32_t)policy_b[cur];
                 }
                 const StepOut o = step_slip<true>(P, lut, sc, s[e], aa, ab, u_from_rng32(philox_r32(word[e])),
-                                                  word[e] & 3u, false);
+                                                  (word[e] >> 2) & 3u, false);
                 const int32_t ri = (o.reward > 0.0f) - (o.reward < 0.0f);
                 s[e] = o.state; oo[e] = (uint32_t)o.obs; rr[e] = __float_as_uint((float)(flip ? -ri : ri));
                 fw |= (o.flags & 3u) << (8 * e);
@@ -242,7 +194,8 @@ __device__ __forceinline__ void rollout_body(const Stepper& S, const RolloutArgs
     long long c_net = 0;
     const int64_t n_groups = a.n / VEC;
     const int32_t K = a.K;
-    const bool flip = a.flip != 0;
+    // only an env with a folded policy has a flipped return agent: the uniform-policy instantiations carry no flip code
+    const bool flip = Stepper::kHasPolicy && a.flip != 0;
     const uint32_t key0 = (uint32_t)a.seed, key1 = (uint32_t)(a.seed >> 32);
     // Slot order (a slot = 32 threads x VEC envs).  Full passes are CTA-major: the 16 warps of a CTA own 16
     // adjacent slots, so every step the SM writes 8 KB / 8 KB / 2 KB contiguous per stream - measured with the
@@ -285,30 +238,42 @@ __device__ __forceinline__ void rollout_body(const Stepper& S, const RolloutArgs
         const uint64_t env0 = a.env_id_base + (uint64_t)i0;
         const uint64_t grp = env0 >> 2;
         const uint32_t grp_lo = (uint32_t)grp, grp_hi = (uint32_t)(grp >> 32), widx = (uint32_t)env0 & 3u;
+        // The words do not depend on the state: the four Philox calls of a block of four steps are issued together
+        // (four independent 10-round chains in flight), then the four steps consume them -- one call per step in
+        // program order put the chain's latency in front of every table look-up (measured: -8 % at 2^20 envs).
         uint64_t step = a.step0;
-        for (int32_t k = 0; k < K; ++k, ++step) {
-            uint32_t w[4], word[4], oo[4], rr[4], fw;
-            philox4x32_10(grp_lo, grp_hi, (uint32_t)step, (uint32_t)(step >> 32), key0, key1, w);
-            if (VEC == 4) {
+        for (int32_t kb = 0; kb < K; kb += 4, step += 4) {
+            uint32_t w[4][4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) word[e] = w[e];
-            } else {
-                word[0] = widx == 0 ? w[0] : (widx == 1 ? w[1] : (widx == 2 ? w[2] : w[3]));
+            for (int j = 0; j < 4; ++j) {
+                const uint64_t sj = step + (uint64_t)j;
+                philox4x32_10(grp_lo, grp_hi, (uint32_t)sj, (uint32_t)(sj >> 32), key0, key1, w[j]);
             }
-            S.template step<VEC>(s, word, oo, rr, fw, p_net, flip);
-            acc_d += fw & 0x01010101u;
-            acc_t += (fw >> 1) & ~fw & 0x01010101u;                     // truncated WITHOUT a goal
-            const bool with_streams = STREAMS && (!Stepper::kCollective || valid);
-            if (VEC == 4) {
-                if (with_streams || op) { st_stream(reinterpret_cast<uint4*>(op), make_uint4(oo[0], oo[1], oo[2], oo[3])); op += a.n; }
-                if (with_streams || rp) { st_stream(reinterpret_cast<uint4*>(rp), make_uint4(rr[0], rr[1], rr[2], rr[3])); rp += a.n; }
-                if (with_streams || fp) { st_stream(reinterpret_cast<uint32_t*>(fp), fw); fp += a.n; }
-            } else {
-                if (with_streams || op) { *op = (int32_t)oo[0]; op += a.n; }
-                if (with_streams || rp) { *rp = __uint_as_float(rr[0]); rp += a.n; }
-                if (with_streams || fp) { *fp = (uint8_t)fw; fp += a.n; }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (kb + j >= K) continue;                              // warp-uniform
+                uint32_t word[4], oo[4], rr[4], fw;
+                if (VEC == 4) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) word[e] = w[j][e];
+                } else {
+                    word[0] = widx == 0 ? w[j][0] : (widx == 1 ? w[j][1] : (widx == 2 ? w[j][2] : w[j][3]));
+                }
+                S.template step<VEC>(s, word, oo, rr, fw, p_net, flip);
+                acc_d += fw & 0x01010101u;
+                acc_t += (fw >> 1) & ~fw & 0x01010101u;                 // truncated WITHOUT a goal
+                const bool with_streams = STREAMS && (!Stepper::kCollective || valid);
+                if (VEC == 4) {
+                    if (with_streams || op) { st_stream(reinterpret_cast<uint4*>(op), make_uint4(oo[0], oo[1], oo[2], oo[3])); op += a.n; }
+                    if (with_streams || rp) { st_stream(reinterpret_cast<uint4*>(rp), make_uint4(rr[0], rr[1], rr[2], rr[3])); rp += a.n; }
+                    if (with_streams || fp) { st_stream(reinterpret_cast<uint32_t*>(fp), fw); fp += a.n; }
+                } else {
+                    if (with_streams || op) { *op = (int32_t)oo[0]; op += a.n; }
+                    if (with_streams || rp) { *rp = __uint_as_float(rr[0]); rp += a.n; }
+                    if (with_streams || fp) { *fp = (uint8_t)fw; fp += a.n; }
+                }
             }
-            if ((k & 63) == 63) {                                       // bytes hold at most 64 counts
+            if ((kb & 63) == 60) {                                      // bytes hold at most 64 counts
                 p_done = __dp4a(acc_d, 0x01010101u, p_done); p_trunc = __dp4a(acc_t, 0x01010101u, p_trunc);
                 acc_d = acc_t = 0;
             }
@@ -391,11 +356,11 @@ k_rollout_table(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t 
     rollout_body<VEC, STREAMS>(S, a, &blk);
 }
 
-// slip_prob > 0 with the slip index.  Shared-memory image: [table][isd 16 B][slip index][policy a][policy b]
-// [exchange slots: one kXqWarpBytes area per warp].
-template <bool STREAMS, bool POLICY>
+// slip_prob > 0 with the slip index.  Shared-memory image: [table][isd 16 B][slip index plane 1][policy a][policy b]
+// [look-up tables of the integer fast path].
+template <int VEC, bool STREAMS, bool POLICY>
 __global__ void __launch_bounds__(kRolloutThreads, 1)
-k_rollout_table_slipq(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t table_bytes,
+k_rollout_table_slipi(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t table_bytes,
                       const uint8_t* __restrict__ gfc, uint32_t fc_bytes, const SlipE E,
                       const int8_t* __restrict__ policy_a, const int8_t* __restrict__ policy_b, const RolloutArgs a)
 {
@@ -403,24 +368,22 @@ k_rollout_table_slipq(const PitchDev P, const uint16_t* __restrict__ gtable, uin
     __shared__ __align__(8) uint64_t bar;
     __shared__ BlkStats blk;
     __shared__ __align__(16) double prt[kPrtDoubles];
-    __shared__ uint8_t cacb[16], mv3[16];
-    __shared__ __align__(16) uint8_t klut[1 << kSlipLutBits];
     pdl_launch_dependents();
     if (threadIdx.x < 5) blk.v[threadIdx.x] = 0;
-    slip_build_prt(prt, P);
-    slip_fast_build_luts<false>(cacb, mv3, klut, E);
-    stage_table_and_index(smem_raw, gtable, table_bytes, gfc, fc_bytes, &bar, P);     // ends with __syncthreads()
-    TableSlipQStepper<POLICY> S;
-    S.c = make_ctx(smem_raw, table_bytes, P);
-    S.sc.prt = smem_u32(prt); S.sc.first_k = slip_first_k(P);
-    S.sf.fc = S.c.isd + 16u; S.sf.cacb = smem_u32(cacb); S.sf.mv3 = smem_u32(mv3); S.sf.klut = smem_u32(klut);
-    S.pol_a = S.pol_b = 0;
     const uint32_t pol_bytes = POLICY ? (((uint32_t)P.nS + 15u) & ~15u) : 0u;
     uint8_t* pa = smem_raw + table_bytes + 16 + fc_bytes, *pb = pa + pol_bytes;
-    S.xq = smem_u32(pb + pol_bytes) + (threadIdx.x >> 5) * kXqWarpBytes;
+    uint8_t* luts = pb + pol_bytes;
+    slip_build_prt(prt, P);
+    slip_int_build_luts(luts, E, P);
+    stage_table_and_index(smem_raw, gtable, table_bytes, gfc, fc_bytes, &bar, P);     // ends with __syncthreads()
+    TableSlipIntStepper<POLICY> S;
+    S.c = make_ctx(smem_raw, table_bytes, P);
+    S.sc.prt = smem_u32(prt); S.sc.first_k = slip_first_k(P);
+    S.sf = slip_int_ctx(luts, S.c.isd + 16u);
+    S.pol_a = S.pol_b = 0;
     wait_table(&bar);
     launder(S.c.tbl); launder(S.c.isd); launder(S.sc.prt);
-    launder(S.sf.fc); launder(S.sf.cacb); launder(S.sf.mv3); launder(S.sf.klut);
+    launder(S.sf.fc); launder(S.sf.klo); launder(S.sf.kthr); launder(S.sf.mva); launder(S.sf.mvb); launder(S.sf.sl);
     pdl_wait();
     if (POLICY) {
         stage_policies(pa, pb, policy_a, policy_b, P.nS);
@@ -429,7 +392,7 @@ k_rollout_table_slipq(const PitchDev P, const uint16_t* __restrict__ gtable, uin
         __syncthreads();
         launder(S.pol_a); launder(S.pol_b);
     }
-    rollout_body<4, STREAMS>(S, a, &blk);
+    rollout_body<VEC, STREAMS>(S, a, &blk);
 }
 
 // (forcing 3 resident CTAs - 80 registers - measured 283 vs 291 G env-steps/s: the kernel is issue-bound)

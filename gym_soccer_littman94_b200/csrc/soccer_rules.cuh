@@ -186,7 +186,8 @@ __device__ __forceinline__ uint32_t philox_word(uint64_t seed, uint64_t env_id, 
 //   step draw    r32 = frac(25 x) * 2^32 = lo32(25 w): u = (r32 + 0.5) / 2^32, the rng32 format (25 is odd, so
 //                w -> r32 is a bijection: exactly uniform).  slip_prob == 0 needs its top two bits only, and
 //                jr = mulhi(w, 100) = ja * 4 + (r32 >> 30) is at once the column index of the step table;
-//   reset draw   w & 3.
+//   reset draw   (w >> 2) & 3, i.e. w & 0xC is at once the byte offset into the start-observation words and the
+//                reset field of an rng8 byte.
 __device__ __forceinline__ uint32_t philox_jr(uint32_t w) { return __umulhi(w, 100u); }
 __device__ __forceinline__ uint32_t philox_r32(uint32_t w) { return w * 25u; }
 __device__ __forceinline__ void philox_actions(uint32_t w, uint32_t& aa, uint32_t& ab)
@@ -196,7 +197,7 @@ __device__ __forceinline__ void philox_actions(uint32_t w, uint32_t& aa, uint32_
     ab = ja - aa * 5u;
 }
 // rng8-compatible nibble: bits 0..1 step draw, bits 2..3 reset draw
-__device__ __forceinline__ uint32_t philox_rng8(uint32_t w) { return (philox_jr(w) & 3u) | ((w & 3u) << 2); }
+__device__ __forceinline__ uint32_t philox_rng8(uint32_t w) { return (philox_jr(w) & 3u) | (w & 0xCu); }
 
 // Philox draws of the 4 envs of a group as rng8-compatible bytes (soccer_step_philox / soccer_step_table_philox:
 // K1 with on-device draws).  env_id_base is a multiple of 4 here (the dispatcher sends other bases to the

@@ -373,8 +373,15 @@ __device__ __forceinline__ K1Policy stage_k1_policies(uint8_t* dst, const int8_t
 // pair's loads are in flight.  POLICY: a folded player's action stream is not read either (its pointer aliases the
 // other player's); shared-memory image [table][isd 16 B][policy a][policy b].
 struct K1Extra { const int8_t* policy_a; const int8_t* policy_b; unsigned long long* stats; };
+// Variants that compute Philox words AND carry policies or statistics need more than the 64 registers a 1024-thread
+// CTA leaves per thread (ptxas spilled 40-150 bytes into the loop: 337 -> 251 G env-steps/s); they run 768 threads.
+#ifndef SOCCER_K1_HEAVY_THREADS
+#define SOCCER_K1_HEAVY_THREADS 768
+#endif
+template <bool PHILOX, bool POLICY, bool STATS>
+constexpr int k1_threads() { return (PHILOX && (POLICY || STATS)) ? SOCCER_K1_HEAVY_THREADS : kTableThreads; }
 template <bool RESET_OBS, bool PHILOX = false, bool NARROW = false, bool POLICY = false, bool STATS = false>
-__global__ void __launch_bounds__(kTableThreads, 1)
+__global__ void __launch_bounds__((k1_threads<PHILOX, POLICY, STATS>()), 1)
 k_step_table(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t table_bytes,
              uint32_t* __restrict__ state, const uint8_t* __restrict__ act_a, const uint8_t* __restrict__ act_b,
              const uint8_t* __restrict__ rng, int32_t* __restrict__ obs, float* __restrict__ reward,
@@ -628,7 +635,7 @@ __device__ __forceinline__ void slip_philox_fill(SlipIn& in, const PhiloxKey& ke
     philox_words4(key, g, w);
     in.d0 = make_uint4(philox_r32(w[0]), philox_r32(w[1]), philox_r32(w[2]), philox_r32(w[3]));
     in.d1 = in.d0;
-    in.x.r = ((w[0] & 3u) << 2) | ((w[1] & 3u) << 10) | ((w[2] & 3u) << 18) | ((w[3] & 3u) << 26);
+    in.x.r = (w[0] & 0xCu) | ((w[1] & 0xCu) << 8) | ((w[2] & 0xCu) << 16) | ((w[3] & 0xCu) << 24);
 }
 
 struct SlipExtra { const int8_t* policy_a; const int8_t* policy_b; PhiloxKey key; };
@@ -706,33 +713,65 @@ k_step_table_slip(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_
 // in place (one such lane would hold its whole warp in the 150-instruction walk): their ids go to the warp's
 // shared-memory queue (ballot + popc), and after the fast pass over its 256 envs the warp takes the queued envs
 // through table_step_slip 32 at a time.  Results are bit-identical to k_step_table_slip (and to the reference): same sums, same compares.
-__global__ void __launch_bounds__(kThreads)
-k_build_slip_index(const PitchDev P, int32_t nS, const uint16_t* __restrict__ table, uint8_t* __restrict__ fc)
+// first 32-bit draw r whose u = (r + 0.5) / 2^32 satisfies E <= u, i.e. ceil(E * 2^32 - 0.5) (exact in fp64: a power-of-two
+// scaling and a subtraction of 0.5 below 2^52), clamped to [0, 2^32]: 2^32 = no draw reaches it
+__host__ __device__ inline uint64_t slip_thr(double E)
 {
-    // Entry = 8-bit mask: bit k set <=> a draw whose constant-prefix pick is combination k must be walked.  That is the
-    // case when combination k itself has 2 or 4 outcomes (the pick falls on a slot inside it), or when some end-of-
-    // combination sum up to k differs from the constant E_j in ANY bit (a 2- or 4-outcome combination adds mp/2 twice
-    // or mp/4 four times instead of mp once; the roundings almost always agree, this checks it).  Picks 8 and 9 (the
-    // last combination, 1 % of the draws, and the all-False case) are always walked, so 8 bits suffice.
+    const double x = ceil(E * 4294967296.0 - 0.5);
+    return x <= 0.0 ? 0ull : (x >= 4294967296.0 ? 4294967296ull : (uint64_t)x);
+}
+
+// The slip index has TWO planes, one entry per (obs, aa * 5 + ab); plane_bytes = nS * 25 rounded up to 16:
+//   plane 0, bytes [0, plane_bytes), one BYTE per entry (fp64 draws, k_step_table_slip_q): bit k <=> a draw whose
+//     constant-prefix pick is combination k must be walked: combination k itself has 2 or 4 outcomes (the pick falls on a
+//     slot inside it), or some end-of-combination sum up to k differs from the constant E_j in ANY bit (a 2- or
+//     4-outcome combination adds mp/2 twice or mp/4 four times instead of mp once; the roundings almost always agree,
+//     this checks it).  Picks 8 and 9 are always walked.
+//   plane 1, bytes [plane_bytes, 3 * plane_bytes), one UINT16 per entry (32-bit draws -- injected rng32 and every Philox
+//     draw; table_step_slip_int): with u = (r + 0.5) / 2^32 every comparison "running sum <= u" of the reference's walk is
+//     "r >= slip_thr(running sum)", an INTEGER threshold, and a last-bit difference between the true running sum and the
+//     constant one moves that integer only if an integer lies between them (probability ~2^-21 per threshold).  So the
+//     fast path decides combination AND slot from constant integer thresholds, and bit k (k = 0 .. 8) marks the picks
+//     for which some threshold of combination k or k - 1 -- its end or a slot inside it -- is NOT the constant one, or
+//     cannot be written as a strict 32-bit compare (0 or 2^32): those (in practice none) take the reference's walk.
+//     Bit 9 is always set: pick 9 = "no running sum exceeds u" (and the fast path's code for "undecided").
+__global__ void __launch_bounds__(kThreads)
+k_build_slip_index(const PitchDev P, int32_t nS, const uint16_t* __restrict__ table, uint8_t* __restrict__ fc, int64_t plane_bytes)
+{
+    uint16_t* fc16 = reinterpret_cast<uint16_t*>(fc + plane_bytes);
     const int64_t total = (int64_t)nS * 25;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
         const uint32_t obs = (uint32_t)(i / 25), ja = (uint32_t)(i % 25), aa = ja / 5u, ab = ja % 5u;
-        uint32_t mask = 0;
+        uint32_t mask = 0, imask = 1u << 9;
         double ec = 0.0, et = 0.0;
         bool off = false;                           // the true sums have left the constant ones
-        for (int k = 0; k < 8; ++k) {
+        for (int k = 0; k < 9; ++k) {
             const int ca = combo_a(k), cb = combo_b(k);
             const uint32_t ma = ca == 0 ? aa : slip_move(aa, ca - 1), mb = cb == 0 ? ab : slip_move(ab, cb - 1);
             const uint32_t nl = (table[obs * 100u + (ma * 5u + mb) * 4u] >> 12) & 3u;
             const double mp = P.mp[k];
+            const double ec_prev = ec;
             ec = __dadd_rn(ec, __dmul_rn(mp, 1.0));
             const double pr = __dmul_rn(mp, nl == 2u ? 0.25 : (nl == 1u ? 0.5 : 1.0));       // SIM:241
-            for (uint32_t j = 0; j < (1u << nl); ++j) et = __dadd_rn(et, pr);                // the reference's running sum
+            bool ibad = false;
+            double cc = ec_prev;                    // what the fast path adds up inside combination k: constant prefix + slots
+            for (uint32_t j = 0; j < (1u << nl); ++j) {                                      // the reference's running sum
+                et = __dadd_rn(et, pr);
+                cc = __dadd_rn(cc, pr);
+                // slot thresholds inside the combination come from (constant prefix + j * pr), its end from E_k
+                const bool last = j + 1u == (1u << nl);
+                const uint64_t t_fast = slip_thr(last ? ec : cc);
+                ibad |= slip_thr(et) != t_fast;
+                // inner thresholds are used as strict 32-bit compares r > t - 1: t must lie in [1, 2^32 - 1]
+                if (!last) ibad |= t_fast == 0ull || t_fast > 0xFFFFFFFFull;
+            }
             off |= __double_as_longlong(et) != __double_as_longlong(ec);
-            if ((nl != 0u && mp != 0.0) || off) mask |= 1u << k;
+            if (k < 8 && ((nl != 0u && mp != 0.0) || off)) mask |= 1u << k;
+            if (ibad) imask |= (1u << k) | (1u << min(k + 1, 8));
         }
         fc[i] = (uint8_t)mask;
+        fc16[i] = (uint16_t)imask;
     }
 }
 
@@ -821,6 +860,248 @@ __device__ __forceinline__ void stage_table_and_index(uint8_t* smem, const uint1
     __syncthreads();
 }
 
+// ---- 32-bit draws: combination and slot from constant INTEGER thresholds (plane 1 of the slip index), no queue.
+// Shared look-up tables, built by every CTA from E_k and the combination probabilities:
+//   klo[b]  (4096 bytes)   #{j : E_j <= u(low end of bucket b)}, b = top 12 bits of the draw; 9 = undecided (two or
+//                          more steps of k(r) inside the bucket: tiny slip_prob) -> walk
+//   kthr[b] (4096 uint32)  t - 1 for the ONE step of k(r) inside bucket b (k = klo + (r > kthr)); 0xFFFFFFFF if none
+//   mva[k][a], mvb[k][a]   (10 x 8 bytes each) byte offsets inside the table row of the move player A / B makes in
+//                          combination k with action a: (slipped move) * 40, * 8
+//   sl[k][nl - 1]          (20 rows of uint4) strict thresholds t - 1 of slots 1, 2, 3 inside a 2-way / 4-way
+//                          combination k; unused = 0xFFFFFFFF
+struct SlipInt { uint32_t fc, klo, kthr, mva, mvb, sl; };   // shared-window addresses
+constexpr int kSlipIntLutBytes = (1 << kSlipLutBits) * 5 + 80 + 80 + 20 * 16;
+__device__ __forceinline__ void slip_int_build_luts(uint8_t* base, const SlipE& E, const PitchDev& P)
+{
+    uint32_t* kthr = reinterpret_cast<uint32_t*>(base);
+    uint32_t* sl = kthr + (1 << kSlipLutBits);
+    uint8_t* klo = reinterpret_cast<uint8_t*>(sl + 20 * 4);
+    uint8_t* mva = klo + (1 << kSlipLutBits); uint8_t* mvb = mva + 80;
+    if (threadIdx.x < 80) {
+        const int k = min((int)threadIdx.x >> 3, 8), a = min((int)threadIdx.x & 7, 4);
+        const int ca = combo_a(k), cb = combo_b(k);
+        mva[threadIdx.x] = (uint8_t)((ca == 0 ? (uint32_t)a : slip_move((uint32_t)a, ca - 1)) * 40u);
+        mvb[threadIdx.x] = (uint8_t)((cb == 0 ? (uint32_t)a : slip_move((uint32_t)a, cb - 1)) * 8u);
+    }
+    if (threadIdx.x >= 96 && threadIdx.x < 96 + 20) {
+        const int row = threadIdx.x - 96, k = row >> 1, nl = (row & 1) + 1;
+        uint32_t t[4] = { 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu };
+        if (k < 9) {
+            const double pr = __dmul_rn(P.mp[k], nl == 2 ? 0.25 : 0.5);
+            double cc = k == 0 ? 0.0 : E.e[k - 1];
+            for (int j = 0; j + 1 < (1 << nl); ++j) {
+                cc = __dadd_rn(cc, pr);
+                const uint64_t th = slip_thr(cc);      // 0 or 2^32 here: the index flags every pick that would use it
+                t[j] = (th == 0ull || th > 0xFFFFFFFFull) ? 0xFFFFFFFFu : (uint32_t)(th - 1ull);
+            }
+        }
+        sl[row * 4 + 0] = t[0]; sl[row * 4 + 1] = t[1]; sl[row * 4 + 2] = t[2]; sl[row * 4 + 3] = t[3];
+    }
+    for (uint32_t b = threadIdx.x; b < (1u << kSlipLutBits); b += blockDim.x) {
+        const uint32_t lo = b << (32 - kSlipLutBits), hi = lo | ((1u << (32 - kSlipLutBits)) - 1u);
+        const double ulo = u_from_rng32(lo), uhi = u_from_rng32(hi);
+        uint32_t kl = 0, kh = 0;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) { kl += E.e[j] <= ulo ? 1u : 0u; kh += E.e[j] <= uhi ? 1u : 0u; }
+        uint32_t thr = 0xFFFFFFFFu;
+        if (kh == kl + 1u) thr = (uint32_t)(slip_thr(E.e[kl]) - 1ull);     // the step lies inside (lo, hi]
+        else if (kh != kl) kl = 9u;
+        klo[b] = (uint8_t)kl;
+        kthr[b] = thr;
+    }
+}
+__device__ __forceinline__ SlipInt slip_int_ctx(uint8_t* base, uint32_t fc_addr)
+{
+    const uint32_t b = smem_u32(base), n = 1u << kSlipLutBits;
+    SlipInt f = { fc_addr, b + n * 4u + 320u, b, b + n * 5u + 320u, b + n * 5u + 400u, b + n * 4u };
+    return f;
+}
+__device__ __forceinline__ uint32_t lds_u32_r(uint32_t addr)
+{
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u16_r(uint32_t addr)
+{
+    uint32_t v;
+    asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint4 lds_v4_r(uint32_t addr)
+{
+    uint4 v;
+    asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+// One env-step with a 32-bit draw.  walk == true: the result is void, the caller takes the reference's walk.
+// CLAMP_ACT: the action values come from a caller's stream (Philox-decoded and policy-table actions are < 5 already).
+template <bool CLAMP_ACT>
+__device__ __forceinline__ TblOut table_step_slip_int(const TblCtx& c, const SlipInt& f, uint32_t s, uint32_t aa, uint32_t ab,
+                                                      uint32_t r32, uint32_t rsel4, bool& walk)
+{
+    const uint32_t obsi = min(s & 0xFFFFu, c.last / 100u);
+    if (CLAMP_ACT) { aa = min(aa, 4u); ab = min(ab, 4u); }
+    const uint32_t dm = lds_u16_r(f.fc + (obsi * 25u + aa * 5u + ab) * 2u);
+    const uint32_t b = r32 >> (32 - kSlipLutBits);
+    const uint32_t k = lds_u8_r(f.klo + b) + (r32 > lds_u32_r(f.kthr + b * 4u) ? 1u : 0u);     // 0 .. 9
+    walk = ((dm >> k) & 1u) != 0u;
+    uint32_t ent = c.tbl + obsi * 200u + lds_u8_r(f.mva + k * 8u + aa) + lds_u8_r(f.mvb + k * 8u + ab);
+    int32_t e = lds_s16_r(ent);
+    if ((uint32_t)e & 0x3000u) {                               // 3 % of the (state, move pair)s: 2 or 4 outcomes
+        const uint32_t nl = ((uint32_t)e >> 12) & 3u;
+        const uint4 t = lds_v4_r(f.sl + (k * 2u + nl - 1u) * 16u);
+        const uint32_t slot = (r32 > t.x ? 1u : 0u) + (r32 > t.y ? 1u : 0u) + (r32 > t.z ? 1u : 0u);
+        ent += slot * (nl == 1u ? 4u : 2u);                    // 2-way: draw value 2 * slot; 4-way: draw value slot
+        e = lds_s16_r(ent);
+    }
+    return table_finish(c, s, e, rsel4);
+}
+
+// The reference's walk as an out-of-line call for the integer fast path's (in practice never taken) fallback: inlined
+// four times it cost the K1 kernel 150-190 bytes of spills at 64 registers.
+__device__ __noinline__ uint2 table_step_slip_call(uint32_t tbl, uint32_t isd, uint32_t last, uint32_t prt, uint32_t first_k,
+                                                   uint32_t s, uint32_t aa, uint32_t ab, uint32_t r32, uint32_t rsel4)
+{
+    const TblCtx c = { tbl, isd, last };
+    const SlipCtx sc = { prt, first_k };
+    const TblOut o = table_step_slip(c, sc, s, aa, ab, u_from_rng32(r32), rsel4);
+    // state | obs, flags, reward and the post-reset observation packed into the second word
+    return make_uint2(o.state, o.obs | (o.flags << 12) | (((uint32_t)o.rew_i & 3u) << 14) | (o.reset_obs << 16));
+}
+__device__ __forceinline__ TblOut table_step_slip_walk(const TblCtx& c, const SlipCtx& sc, uint32_t s, uint32_t aa, uint32_t ab,
+                                                       uint32_t r32, uint32_t rsel4)
+{
+    const uint2 w = table_step_slip_call(c.tbl, c.isd, c.last, sc.prt, sc.first_k, s, aa, ab, r32, rsel4);
+    TblOut o;
+    o.state = w.x; o.obs = w.y & kTblObsMask; o.flags = (w.y >> 12) & 3u;
+    o.rew_i = (int32_t)(int16_t)(w.y & 0xFFFFu) >> 14; o.reset_obs = w.y >> 16;
+    return o;
+}
+
+// K1 for slip_prob > 0 and 32-bit draws (injected rng32: 24 B / env-step; Philox: 19 B): k_step_table's structure --
+// persistent 1024-thread CTAs, two groups in flight + register prefetch of the next pair -- around table_step_slip_int.
+// Shared-memory image: [table][isd 16 B][slip index plane 1][policy a][policy b][look-up tables of the fast path].
+struct GroupS { uint4 s; uint32_t a, b, r; uint4 d; };
+template <bool PHILOX>
+__device__ __forceinline__ GroupS load_group_slip(const uint4* st, const uint32_t* aa, const uint32_t* ab, const uint32_t* rg,
+                                                  const uint4* dr, int64_t g)
+{
+    GroupS x;
+    x.s = ld_keep(st + g);
+    x.a = ld_stream(aa + g);
+    x.b = ld_stream(ab + g);
+    if (PHILOX) { x.r = 0u; x.d = make_uint4(0, 0, 0, 0); }
+    else { x.r = ld_stream(rg + g); x.d = __ldcs(dr + g); }
+    return x;
+}
+#ifndef SOCCER_SLIP_I_GROUPS
+#define SOCCER_SLIP_I_GROUPS 2         // groups of 4 envs a thread has in flight (1 or 2)
+#endif
+#ifndef SOCCER_SLIP_I_THREADS
+#define SOCCER_SLIP_I_THREADS 768      // two groups in flight + prefetch of two more: 44 data registers; 1024 threads (64 registers) spill 160-190 bytes
+#endif
+constexpr int kSlipIThreads = SOCCER_SLIP_I_THREADS;
+template <bool RESET_OBS, bool PHILOX>
+__global__ void __launch_bounds__(kSlipIThreads, 1)
+k_step_table_slip_i(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t table_bytes,
+                    const uint8_t* __restrict__ gfc, uint32_t fc_bytes, const SlipE E,
+                    uint32_t* __restrict__ state, const uint8_t* __restrict__ act_a, const uint8_t* __restrict__ act_b,
+                    const uint8_t* __restrict__ rng, const uint32_t* __restrict__ draw, int32_t* __restrict__ obs,
+                    float* __restrict__ reward, uint8_t* __restrict__ flags, int32_t* __restrict__ reset_obs, int64_t n_groups,
+                    const SlipExtra ex)
+{
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ __align__(16) double prt[kPrtDoubles];
+    const bool has_pol = ex.policy_a || ex.policy_b;
+    const uint32_t pol_total = has_pol ? 2u * (((uint32_t)P.nS + 15u) & ~15u) : 0u;
+    uint8_t* luts = smem_raw + table_bytes + 16 + fc_bytes + pol_total;
+    slip_build_prt(prt, P);
+    slip_int_build_luts(luts, E, P);
+    stage_table_and_index(smem_raw, gtable, table_bytes, gfc, fc_bytes, &bar, P);          // ends with __syncthreads()
+    TblCtx c = make_ctx(smem_raw, table_bytes, P);
+    SlipCtx sc = { smem_u32(prt), slip_first_k(P) };
+    SlipInt sf = slip_int_ctx(luts, c.isd + 16u);
+    K1Policy pol = { 0u, 0u };
+    if (has_pol) pol = stage_k1_policies(smem_raw + table_bytes + 16 + fc_bytes, ex.policy_a, ex.policy_b, P.nS);
+    const bool flip = pol.pol_a != 0u;
+    uint4* st4 = reinterpret_cast<uint4*>(state);
+    const uint32_t* a4 = reinterpret_cast<const uint32_t*>(act_a ? act_a : act_b);
+    const uint32_t* b4 = reinterpret_cast<const uint32_t*>(act_b ? act_b : act_a);
+    const uint32_t* r4 = reinterpret_cast<const uint32_t*>(rng);
+    const uint4* d4 = reinterpret_cast<const uint4*>(draw);
+    uint4* o4 = reinterpret_cast<uint4*>(obs);
+    uint4* w4 = reinterpret_cast<uint4*>(reward);
+    uint32_t* f4 = reinterpret_cast<uint32_t*>(flags);
+    uint4* q4 = reinterpret_cast<uint4*>(reset_obs);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool one = g < n_groups, two = SOCCER_SLIP_I_GROUPS == 2 && g + stride < n_groups;
+    GroupS x0 = {}, x1 = {};
+    if (one) x0 = load_group_slip<PHILOX>(st4, a4, b4, r4, d4, g);
+    if (two) x1 = load_group_slip<PHILOX>(st4, a4, b4, r4, d4, g + stride);
+    wait_table(&bar);
+    launder(c.tbl); launder(c.isd); launder(sc.prt);
+    launder(sf.fc); launder(sf.klo); launder(sf.kthr); launder(sf.mva); launder(sf.mvb); launder(sf.sl);
+    launder(pol.pol_a); launder(pol.pol_b);
+    auto do_group = [&](GroupS& x, int64_t gg) {
+        if (PHILOX) {
+            uint32_t w[4];
+            philox_words4(ex.key, gg, w);
+            x.d = make_uint4(philox_r32(w[0]), philox_r32(w[1]), philox_r32(w[2]), philox_r32(w[3]));
+            x.r = (w[0] & 0xCu) | ((w[1] & 0xCu) << 8) | ((w[2] & 0xCu) << 16) | ((w[3] & 0xCu) << 24);
+        }
+        const uint32_t rs4 = x.r & 0x0C0C0C0Cu;
+        const uint32_t sv[4] = { x.s.x, x.s.y, x.s.z, x.s.w };
+        const uint32_t r32[4] = { x.d.x, x.d.y, x.d.z, x.d.w };
+        uint32_t so[4], oo[4], ro[4], rr[4], ff[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            uint32_t aa = __byte_perm(x.a, 0, 0x4440 + e), ab = __byte_perm(x.b, 0, 0x4440 + e);
+            if (pol.pol_a | pol.pol_b) {                     // warp-uniform
+                const uint32_t cs = min(sv[e] & 0xFFFFu, c.last / 100u);
+                if (pol.pol_a) aa = lds_u8_r(pol.pol_a + cs);
+                if (pol.pol_b) ab = lds_u8_r(pol.pol_b + cs);
+            }
+            const uint32_t rsel4 = __byte_perm(rs4, 0, 0x4440 + e);
+            bool walk;
+            TblOut o = table_step_slip_int<true>(c, sf, sv[e], aa, ab, r32[e], rsel4, walk);
+            if (walk) o = table_step_slip_walk(c, sc, sv[e], aa, ab, r32[e], rsel4);     // (in practice never)
+            so[e] = o.state; oo[e] = o.obs; rr[e] = __float_as_uint((float)(flip ? -o.rew_i : o.rew_i));
+            ro[e] = o.reset_obs; ff[e] = o.flags;
+        }
+        st_keep(st4 + gg, make_uint4(so[0], so[1], so[2], so[3]));
+        st_stream(o4 + gg, make_uint4(oo[0], oo[1], oo[2], oo[3]));
+        st_stream(w4 + gg, make_uint4(rr[0], rr[1], rr[2], rr[3]));
+        st_stream(f4 + gg, __byte_perm(__byte_perm(ff[0], ff[1], 0x0040), __byte_perm(ff[2], ff[3], 0x0040), 0x5410));
+        if (RESET_OBS) st_stream(q4 + gg, make_uint4(ro[0], ro[1], ro[2], ro[3]));
+    };
+    if (SOCCER_SLIP_I_GROUPS == 1) {
+        // one group in flight + register prefetch of the next one (half the data registers: 1024 threads fit 64 registers)
+        if (two) { /* x1 was loaded above only in the two-group variant */ }
+        while (one) {
+            const int64_t gn = g + stride;
+            const bool n_one = gn < n_groups;
+            GroupS y0 = x0;
+            if (n_one) y0 = load_group_slip<PHILOX>(st4, a4, b4, r4, d4, gn);
+            do_group(x0, g);
+            x0 = y0; g = gn; one = n_one;
+        }
+        return;
+    }
+    while (one) {
+        const int64_t gn = g + 2 * stride;
+        const bool n_one = gn < n_groups, n_two = gn + stride < n_groups;
+        GroupS y0 = x0, y1 = x1;
+        if (n_one) y0 = load_group_slip<PHILOX>(st4, a4, b4, r4, d4, gn);          // prefetch the next pair
+        if (n_two) y1 = load_group_slip<PHILOX>(st4, a4, b4, r4, d4, gn + stride);
+        do_group(x0, g);
+        if (two) do_group(x1, g + stride);
+        x0 = y0; x1 = y1; g = gn; one = n_one; two = n_two;
+    }
+}
+
 // shared-memory image: [table][isd 16 B][slip index][policy a][policy b][queues]
 template <bool RESET_OBS, int DRAW>
 __global__ void __launch_bounds__(kTableThreads, 1)
@@ -880,7 +1161,7 @@ k_step_table_slip_q(const PitchDev P, const uint16_t* __restrict__ gtable, uint3
             uint32_t rg; double ud;
             if (DRAW == kDrawPhilox) {
                 const uint32_t w = philox_word(ex.key.seed, ex.key.env_id_base + (uint64_t)env, ex.key.step);
-                rg = (w & 3u) << 2; ud = u_from_rng32(philox_r32(w));
+                rg = w & 0xCu; ud = u_from_rng32(philox_r32(w));
             } else {
                 rg = rng[env];
                 ud = F64 ? reinterpret_cast<const double*>(draw)[env] : u_from_rng32(reinterpret_cast<const uint32_t*>(draw)[env]);
@@ -993,7 +1274,7 @@ k_step_table_slip_scalar(const PitchDev P, const uint16_t* __restrict__ gtable, 
         uint32_t rg; double u;
         if (use_philox) {
             const uint32_t w = philox_word(ex.key.seed, ex.key.env_id_base + (uint64_t)i, ex.key.step);
-            rg = (w & 3u) << 2; u = u_from_rng32(philox_r32(w));
+            rg = w & 0xCu; u = u_from_rng32(philox_r32(w));
         } else {
             rg = rng[i]; u = rngf64 ? rngf64[i] : u_from_rng32(rng32[i]);
         }

@@ -10,9 +10,11 @@ single-agent (folded-policy) env they are written for.
   iteration or policy evaluation runs inside ONE cooperative launch.  Results are bit-identical to the
   reference's: V, Q, the greedy policy and the number of sweeps (tests/test_gpu_planners.py compares with ==).
 * policy_eval (PL:57-70) and modified_policy_iteration (PL:73-87) are written against the dense `Pmat` / `Rmat`
-  in the reference (np.dot); here they run the same contractions in fp64 on the device over the `soccer_dense`
-  kernel's output.  BLAS summation order is not reproducible, so these agree to fp64 round-off
-  (|V - V_ref| < 1e-9, identical greedy policies).
+  in the reference (np.dot).  Pmat has at most 15 non-zeros per (state, action), so here the contraction runs
+  sparsely over the same on-the-fly transition lists, in the hand-written kernels `soccer_dense_q` and
+  `soccer_policy_eval` (a whole policy_eval loop in one cooperative launch) -- no dense matrix, no library GEMM.
+  Rmat comes out bit-identical; Pmat . v is summed in list order where the reference's BLAS has its own order, so
+  these agree to fp64 round-off (|V - V_ref| < 1e-9, identical greedy policies).
 """
 import ctypes as C
 
@@ -63,19 +65,29 @@ def _backup_q(env, V, gamma):
     return Q
 
 
-def _dense(env):
-    """(Pmat[nS, nS, nA], Rmat[nS, nA]) as fp64 CUDA tensors, cached on the env."""
-    cache = getattr(env, "_planner_dense", None)
-    if cache is None:
-        assert not env.multiagent, "planners act on a single-agent env (one player's policy folded, SIM:266-279)"
-        dev = getattr(env, "device", torch.device("cuda"))
-        cache = (torch.from_numpy(np.ascontiguousarray(env.Pmat)).to(dev), torch.from_numpy(np.ascontiguousarray(env.Rmat)).to(dev))
-        env._planner_dense = cache
-    return cache
+def _dense_q(env, v, gamma):
+    """soccer_dense_q: q[nS, nA] = Rmat + gamma * (Pmat . v), contracted sparsely over the transition lists (PL:78-79)."""
+    lib, pitch, pa, pb, dev = _single_agent(env)
+    q = torch.empty((env.nS, env.nA), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(lib.soccer_dense_q(pitch, pa, pb, _ptr(v), float(gamma), _ptr(q), st), "soccer_dense_q")
+    return q
 
 
-def _backup(P, R, V, gamma):
-    return R + gamma * torch.einsum("sna,n->sa", P, V)
+def _policy_eval(env, policy, theta, gamma, k, init):
+    """soccer_policy_eval: the whole PL:57-70 loop in one cooperative launch; device tensors in and out."""
+    lib, pitch, pa, pb, dev = _single_agent(env)
+    nbytes = C.c_int64()
+    _lib.check(lib.soccer_policy_eval_workspace_bytes_host(pitch, env.nA, C.byref(nbytes)), "soccer_policy_eval_workspace_bytes_host")
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+    V = torch.empty(env.nS, dtype=torch.float64, device=dev)
+    sweeps = torch.zeros(1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(lib.soccer_policy_eval(pitch, pa, pb, _ptr(policy), _ptr(init), float(theta), float(gamma),
+                                          int(min(k, MAX_SWEEPS)), _ptr(V), _ptr(sweeps), _ptr(ws), st), "soccer_policy_eval")
+    return V, sweeps
 
 
 def value_iteration(env, theta, discount_factor):
@@ -111,38 +123,34 @@ def policy_iteration(env, theta, discount_factor):
 
 
 def policy_eval(env, policy, theta, discount_factor, k=10000000, init=None):
-    """planners.py:57-70: at most k sweeps of v <- r_pi + gamma P_pi v for a stochastic policy [nS, nA]."""
-    P, R = _dense(env)
-    pol = torch.as_tensor(np.asarray(policy), dtype=torch.float64, device=P.device)
-    v = torch.zeros(P.shape[0], dtype=torch.float64, device=P.device) if init is None \
-        else torch.as_tensor(np.asarray(init), dtype=torch.float64, device=P.device).clone()
-    r_pi = (pol * R).sum(dim=1)
-    P_pi = torch.einsum("sna,sa->sn", P, pol)
-    cc = 0
-    for _ in range(k):
-        new_v = r_pi + discount_factor * (P_pi @ v)
-        delta = float((new_v - v).abs().max())
-        v = new_v
-        cc += 1
-        if delta < theta:
-            break
-    return v.cpu().numpy(), cc
+    """planners.py:57-70: at most k sweeps of v <- r_pi + gamma P_pi v for a stochastic policy [nS, nA]; returns (v, sweeps).
+    Like the reference, a given `init` array receives the result (PL:58, 67: `v[:] = value_fc`)."""
+    dev = env.device
+    pol = torch.as_tensor(np.asarray(policy), dtype=torch.float64, device=dev).contiguous()
+    assert tuple(pol.shape) == (env.nS, env.nA), "policy must be [nS, nA]"
+    v0 = None if init is None else torch.as_tensor(np.asarray(init), dtype=torch.float64, device=dev).contiguous()
+    V, sweeps = _policy_eval(env, pol, theta, discount_factor, k, v0)
+    out = V.cpu().numpy()
+    if isinstance(init, np.ndarray):
+        init[:] = out
+        out = init
+    return out, int(sweeps.item())
 
 
 def modified_policy_iteration(env, k, theta, discount_factor):
-    """planners.py:73-87.  Returns (pi, greedy_v, q, outer_iterations)."""
-    P, R = _dense(env)
-    nA = P.shape[2]
-    v = torch.zeros(P.shape[0], dtype=torch.float64, device=P.device)
+    """planners.py:73-87.  Returns (pi, greedy_v, q, outer_iterations).  The dense contractions of the reference
+    (np.dot over Pmat / Rmat) run on the hand-written sparse kernels soccer_dense_q / soccer_policy_eval."""
+    dev, nA = env.device, env.nA
+    v = torch.zeros(env.nS, dtype=torch.float64, device=dev)
     threshold = (theta * (1 - discount_factor)) / (2 * discount_factor)
     counter = 0
     while True:
-        q = _backup(P, R, v, discount_factor)
-        greedy_v, best = q.max(dim=1)
+        q = _dense_q(env, v, discount_factor)
+        greedy_v, best = q.max(dim=1)                      # np.max / np.argmax (first maximum)
+        best = torch.argmax((q == greedy_v[:, None]).to(torch.uint8), dim=1)
         if float((v - greedy_v).abs().max()) <= threshold:
             return best.cpu().numpy(), greedy_v.cpu().numpy(), q.cpu().numpy(), counter
-        policy = torch.nn.functional.one_hot(best, nA).to(torch.float64)
-        v_np, _ = policy_eval(env, policy.cpu().numpy(), theta=theta, discount_factor=discount_factor, k=k,
-                              init=greedy_v.cpu().numpy())
-        v = torch.as_tensor(v_np, dtype=torch.float64, device=P.device)
+        policy = torch.zeros((env.nS, nA), dtype=torch.float64, device=dev)
+        policy[torch.arange(env.nS, device=dev), best] = 1.0          # np.eye(nA)[best_action]
+        v, _ = _policy_eval(env, policy, theta, discount_factor, k, greedy_v)
         counter += 1

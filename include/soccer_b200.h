@@ -46,7 +46,7 @@
  *     joint action ja = floor(25 x) = mulhi(w, 25), aa = ja / 5, ab = ja % 5;
  *     step draw    r32 = frac(25 x) * 2^32 = lo32(25 w): u = (r32 + 0.5) / 2^32, exactly the rng32
  *                  format (slip_prob == 0 uses its top two bits: mulhi(w, 100) = ja * 4 + (r32 >> 30));
- *     reset draw   w & 3.
+ *     reset draw   (w >> 2) & 3.
  *   Kernels that own 4 envs per thread need env_id_base % 4 == 0 to take their vector path (other
  *   bases fall to the one-env-per-thread kernels; same results).
  *
@@ -288,12 +288,19 @@ int soccer_step_table_slip(const soccer_pitch *pitch, const uint16_t *table, con
                            uint32_t *state, const uint8_t *act_a, const uint8_t *act_b, const uint8_t *rng8,
                            const uint32_t *rng32, const double *rngf64, int32_t *obs, float *reward,
                            uint8_t *flags, int32_t *reset_obs, int64_t n, soccer_stream_t stream);
-/* Optional accelerator of soccer_step_table_slip: slip_index[obs*25 + aa*5 + ab] = an 8-bit mask over the first 8 of
- * the 9 slip combinations (SIM:209-223 order): bit k set <=> a draw that the CONSTANT prefix sums of the combination
- * probabilities assign to combination k has to take the reference's walk (combination k has 2 or 4 outcomes, or an
- * earlier one changed a running sum in some bit).  Built on the device from the step table and the pitch's
- * slip_prob.  With it, most envs take a constant-prefix-sum fast path, the others (and picks 8, 9) are walked as
- * before; results are identical.  NULL = walk every env.  bytes: nS * 25 rounded up to 16. */
+/* Optional accelerator of the slip_prob > 0 table kernels, built on the device from the step table and the pitch's
+ * slip_prob; two planes with one entry per (obs, aa*5 + ab), P = nS * 25 rounded up to 16:
+ *   plane 0, bytes [0, P), one byte per entry, fp64 draws (rngf64): an 8-bit mask over the first 8 of the 9 slip combinations (SIM:209-223 order): bit k
+ *     set <=> a draw that the CONSTANT prefix sums of the combination probabilities assign to combination k has to take
+ *     the reference's walk (combination k has 2 or 4 outcomes, or an earlier one changed a running sum in some bit).
+ *     Most envs take the constant-prefix fast path, the others (and picks 8, 9) go through a warp-level queue.
+ *   plane 1, bytes [P, 3P), one uint16 per entry, 32-bit draws (rng32 and every Philox draw): with u = (r + 0.5) / 2^32 each comparison "running sum <= u" of
+ *     the reference's walk is "r >= ceil(sum * 2^32 - 0.5)", an integer threshold, and a last-bit difference between the
+ *     true running sum and the constant one moves that integer only if an integer lies between the two.  The fast path
+ *     therefore decides combination AND slot from constant integer thresholds; bit k (0 .. 8) marks the picks for which
+ *     some threshold is not the constant one (in practice none), bit 9 (always set) the "no sum exceeds u" case: only
+ *     those take the reference's walk.
+ * Results are identical with or without the index.  NULL = walk every env.  bytes: 3 * P. */
 int soccer_slip_index_bytes_host(const soccer_pitch *pitch, int64_t *bytes);
 int soccer_build_slip_index(const soccer_pitch *pitch, const uint16_t *table, uint8_t *slip_index,
                             soccer_stream_t stream);
@@ -398,6 +405,25 @@ int soccer_plan(const soccer_pitch *pitch, const int8_t *policy_a, const int8_t 
                 const int32_t *pi_in, double theta, double gamma, int32_t max_sweeps, double *V_out,
                 double *Q_out, int32_t *pi_out, int32_t *sweeps_out, void *workspace,
                 soccer_stream_t stream);
+
+/* The reference's DENSE planners (PL:57-87) are written against Pmat[s][s'][a] / Rmat[s][a] with np.dot.  Pmat has at
+ * most 15 non-zeros per (s, a), so the contraction runs sparsely over the same on-the-fly transition lists as
+ * soccer_bellman_q (no dense matrix is read, no library GEMM): Rmat[s][a] in the reference's accumulation order
+ * (bit-identical), Pmat[s][:][a] . v as the list-order sum of prob * v[next_obs] (equal to the reference's BLAS sum to
+ * fp64 round-off), including the reference's Pmat[0][0] quirk and no (not done) factor.
+ *   soccer_dense_q:      q[s][key] = Rmat[s][key] + gamma * (Pmat[s][:][key] . v)                     (PL:78-79)
+ *   soccer_policy_eval:  policy_eval(env, policy, theta, gamma, k = max_sweeps, init = v_init) (PL:57-70) in ONE
+ *                        cooperative launch: v <- r_pi + gamma * P_pi v for the stochastic policy[nS][nkeys] until the
+ *                        sup-norm change < theta or max_sweeps sweeps; v_init NULL = zeros; V_out[nS], *sweeps_out.
+ * nkeys = 5 with one table policy folded (the single-agent env the reference's planners are written for), else 25.
+ * workspace: device memory of soccer_policy_eval_workspace_bytes_host(pitch, nkeys) bytes. */
+int soccer_dense_q(const soccer_pitch *pitch, const int8_t *policy_a, const int8_t *policy_b,
+                   const double *v, double gamma, double *q, soccer_stream_t stream);
+int soccer_policy_eval_workspace_bytes_host(const soccer_pitch *pitch, int32_t nkeys, int64_t *bytes);
+int soccer_policy_eval(const soccer_pitch *pitch, const int8_t *policy_a, const int8_t *policy_b,
+                       const double *policy, const double *v_init, double theta, double gamma,
+                       int32_t max_sweeps, double *V_out, int32_t *sweeps_out, void *workspace,
+                       soccer_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -544,7 +544,7 @@ uint32_t orc_philox_word(uint64_t seed, uint64_t env_id, uint64_t step)
  *   step draw     r32 = frac(25 x) * 2^32 = lo32(25 w)       u = (r32 + 0.5) / 2^32, the rng32 format;
  *                 slip_prob == 0 uses its top two bits (r32 >> 30), which select the same outcome of
  *                 1 / 2 / 4 equiprobable ones as u does
- *   reset draw    w & 3
+ *   reset draw    (w >> 2) & 3
  * (25 is odd, so w -> r32 is a bijection of the 32-bit words: r32 is exactly uniform.) */
 void orc_philox_decode(uint32_t w, int *aa, int *ab, int *r_step, int *r_reset)
 {
@@ -553,7 +553,7 @@ void orc_philox_decode(uint32_t w, int *aa, int *ab, int *r_step, int *r_reset)
     *aa = (int)(ja / 5u);
     *ab = (int)(ja % 5u);
     *r_step = (int)(r32 >> 30);
-    *r_reset = (int)(w & 3u);
+    *r_reset = (int)((w >> 2) & 3u);
 }
 uint32_t orc_philox_r32(uint32_t w) { return (uint32_t)((uint64_t)w * 25u); }
 

@@ -138,7 +138,7 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
  * the 4 envs of the aligned group env_id >> 2 at one step; word index env_id & 3). */
 uint32_t orc_philox_word(uint64_t seed, uint64_t env_id, uint64_t step);
 /* decode a word: joint action ja = mulhi(w, 25); step draw r32 = lo32(25 w) (u = (r32 + 0.5) / 2^32;
- * *r_step = r32 >> 30, the 2-bit draw of slip_prob == 0); reset draw = w & 3 */
+ * *r_step = r32 >> 30, the 2-bit draw of slip_prob == 0); reset draw = (w >> 2) & 3 */
 void orc_philox_decode(uint32_t w, int *aa, int *ab, int *r_step, int *r_reset);
 uint32_t orc_philox_r32(uint32_t w);
 

@@ -1,6 +1,6 @@
 """Short driver for ncu captures: a few launches of each hot kernel at its bench size.
 
-    python profiles/run_kernels.py [k1_table|k1_rules|k2_table|k2_rules|k1_slip|k1_philox|k1_packed|replay|all] [--envs N]
+    python profiles/run_kernels.py [k1_table|k1_rules|k2_table|k2_rules|k1_slip|k2_slip|k1_philox|k1_packed|replay|all] [--envs N]
 """
 import argparse
 import os
@@ -83,6 +83,18 @@ def k1_slip(n, iters):
     torch.cuda.synchronize()
 
 
+def k2_slip(n, K, iters):
+    dev = torch.device("cuda", 0)
+    e2 = SoccerVecEnv(n, slip_prob=0.2, device=dev, kernel="table", rng_mode="philox")
+    e2.reset()
+    e2.rollout(64, want_streams=False)          # a played-in population
+    bufs = (torch.empty((K, n), dtype=torch.int32, device=dev), torch.empty((K, n), dtype=torch.float32, device=dev),
+            torch.empty((K, n), dtype=torch.uint8, device=dev))
+    for _ in range(iters):
+        e2.rollout(K, out=bufs)
+    torch.cuda.synchronize()
+
+
 def replay(kernel, n, T, iters):
     dev = torch.device("cuda", 0)
     env = SoccerVecEnv(n, device=dev, kernel=kernel, want_reset_obs=False)
@@ -111,6 +123,8 @@ if __name__ == "__main__":
         k2("rules", 1 << 20, 64, args.iters)
     if args.what in ("k1_slip", "all"):
         k1_slip(args.envs, args.iters)
+    if args.what in ("k2_slip", "all"):
+        k2_slip(1 << 22, 16, args.iters)
     if args.what in ("k1_philox", "all"):
         k1_philox(args.envs, args.iters)
     if args.what in ("k1_packed", "all"):

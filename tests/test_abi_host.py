@@ -70,7 +70,7 @@ def test_argument_errors_without_gpu(L):
     assert lib.soccer_step_table(C.byref(L.Pitch(5, 4, 0.2)), v16, v16, v16, v16, v16, v16, v16, v16, None, 8, None) == -3
     assert lib.soccer_step_table_slip(C.byref(L.Pitch(5, 4, 0.2)), v16, None, v16, v16, v16, v16, None, None, v16, v16, v16,
                                       None, 8, None) == -1
-    assert lib.soccer_slip_index_bytes_host(C.byref(L.Pitch(5, 4, 0.2)), C.byref(nbytes)) == 0 and nbytes.value == 19040   # 761 * 25, up to 16
+    assert lib.soccer_slip_index_bytes_host(C.byref(L.Pitch(5, 4, 0.2)), C.byref(nbytes)) == 0 and nbytes.value == 57120   # plane 0: bytes, plane 1: uint16, each 761 * 25 entries up to 16
     assert lib.soccer_slip_index_bytes_host(C.byref(L.Pitch(7, 5, 0.2)), C.byref(nbytes)) == -5
     assert lib.soccer_step_many(C.byref(L.Pitch(5, 4, 0.2)), None, v16, 4, v16, v16, v16, v16, v16, v16, None, 8, None) == -3
     assert lib.soccer_step_many(C.byref(p), None, v16, -1, v16, v16, v16, v16, v16, v16, None, 8, None) == -1

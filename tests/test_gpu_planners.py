@@ -102,3 +102,47 @@ def test_best_response_beats_stand_and_random_policies():
             ep, ga, gb, tr, steps, length = [int(x) for x in st.cpu().numpy()]
             wins = ga if side == "a" else gb
             assert ep > 10000 and wins / ep >= min_win, (side, wins, ep, tr)
+
+
+@pytest.mark.parametrize("side,slip", [("a", 0.2), ("b", 0.0)])
+def test_dense_planners_vs_numpy_on_the_dense_matrices(side, slip):
+    """policy_eval / the q backup of modified_policy_iteration (PL:57-87) on the hand-written SPARSE kernels
+    (soccer_policy_eval, soccer_dense_q) against the reference's own formulas evaluated with numpy on the dense
+    Pmat / Rmat (which test_dense_pmat_rmat_match_reference pins bit for bit to the reference): every sweep count,
+    values to fp64 round-off (the reference sums with BLAS, the kernel in list order)."""
+    from gym_soccer_littman94_b200.envs import SoccerSimultaneousEnv
+    from gym_soccer_littman94_b200.utils import planners
+    from gym_soccer_littman94_b200.utils.policies import get_random_policy
+    opp = get_random_policy(761, 5, seed=7)
+    kw = {"player_b_policy": opp} if side == "a" else {"player_a_policy": opp}
+    env = SoccerSimultaneousEnv(width=5, height=4, slip_prob=slip, **kw)
+    P, R = np.asarray(env.Pmat), np.asarray(env.Rmat)                   # [nS, nS, 5], [nS, 5]
+    rs = np.random.RandomState(3)
+    policy = rs.dirichlet(np.ones(5), size=env.nS)
+    gamma = 0.97
+
+    def ref_policy_eval(theta, k, init):                                 # PL:57-70, vectorised over s
+        v = np.zeros(env.nS) if init is None else init.copy()
+        cc = 0
+        for _ in range(k):
+            r_pi = (policy * R).sum(axis=1)
+            pv = np.einsum("sna,n->sa", P, v)
+            val = r_pi + gamma * (pv * policy).sum(axis=1)
+            delta = np.abs(val - v).max()
+            v = val
+            cc += 1
+            if delta < theta:
+                break
+        return v, cc
+    for theta, k, init in ((1e-10, 10000000, None), (1e-3, 10000000, rs.rand(env.nS)), (0.0, 7, rs.rand(env.nS)), (1.0, 0, rs.rand(env.nS))):
+        if init is not None:
+            init[0] = 0.0          # (Pmat[0, 0] holds the reference's quirk sum of 160: v[0] != 0 would blow up there as here)
+        want, wcc = ref_policy_eval(theta, k, init)
+        got, cc = planners.policy_eval(env, policy, theta, gamma, k=k, init=None if init is None else init.copy())
+        assert cc == wcc, (theta, k)
+        assert np.abs(got - want).max() <= 1e-12 * max(1.0, np.abs(want).max())
+    v = rs.rand(env.nS)
+    q = planners._dense_q(env, torch.as_tensor(v, device=env.device), gamma).cpu().numpy()
+    assert np.abs(q - (R + gamma * np.einsum("sna,n->sa", P, v))).max() <= 1e-12 * 160
+    # the quirk row: Pmat[0, 0, a] = number of goal states x sum of the combination probabilities
+    assert np.allclose(q[0], gamma * P[0, 0] * v[0], rtol=1e-15)

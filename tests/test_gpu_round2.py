@@ -374,3 +374,61 @@ def test_out_tensors_are_checked(dev):
     assert torch.equal(o1[keep], o2[keep]) and torch.equal(r1[keep], r2[keep]) and torch.equal(f1[keep], f2[keep])
     with pytest.raises(ValueError):
         SoccerVecEnv(8, width=20, height=8, device=dev)                   # beyond the library's pitch limit
+
+
+# ----------------------------------------------------------------------------- slip: integer-threshold fast path
+@pytest.mark.parametrize("slip", [0.2, 0.5, 1.0, 1e-9, 0.123456789, 0.9])
+def test_slip_integer_thresholds_equal_walk(dev, slip, monkeypatch):
+    """32-bit draws (rng32 / Philox) through the shared-memory table with the slip index: combination and slot come
+    from constant INTEGER thresholds (index plane 1).  Against the reference's cumulative walk of every env
+    (SOCCER_B200_SLIP_WALK=1), with the draws sitting ON and next to every threshold -- end of each combination and
+    the slots inside 2-way / 4-way combinations -- and on 0 and 2^32 - 1, on a population full of collision states."""
+    from gym_soccer_littman94_b200.envs import SoccerSimultaneousEnv, SoccerVecEnv
+    n = 1 << 16
+    rs = np.random.RandomState(7)
+    envs = {}
+    for mode in ("walk", "index"):
+        monkeypatch.setenv("SOCCER_B200_SLIP_WALK", "1" if mode == "walk" else "0")
+        envs[mode] = SoccerVecEnv(n, slip_prob=slip, device=dev, kernel="table")
+    idx = envs["index"].slip_index.cpu().numpy()
+    plane = idx.size // 3
+    p1 = idx[plane:].view(np.uint16)[:761 * 25]
+    assert np.all(p1 & 0x200)                             # bit 9: the "no sum exceeds u" pick is always walked
+    flagged = int(((p1 & 0x1FF) != 0).sum())
+    if slip not in (1.0, 1e-9):                           # (zero-probability / 1e-19 combinations flag their picks)
+        assert flagged <= 0.01 * 761 * 25, flagged        # the walk is a rare fallback (expected: none at all)
+    # candidate draws: thresholds of the constant sums (numpy restatement: sequential fp64 adds like SIM:241)
+    mp = [(1 - slip) * (1 - slip)] + [(1 - slip) * slip * 0.5] * 2 + [slip * (1 - slip) * 0.5] * 2 + [slip * slip * 0.25] * 4
+    cand, acc = [0, 1, 2 ** 32 - 1, 2 ** 32 - 2], 0.0
+    for k in range(9):
+        for f, cnt in ((0.5, 2), (0.25, 4)):
+            cc = acc
+            for _ in range(cnt):
+                cc = cc + mp[k] * f
+                cand.append(int(np.ceil(cc * 4294967296.0 - 0.5)))
+        acc = acc + mp[k]
+        cand.append(int(np.ceil(acc * 4294967296.0 - 0.5)))
+    cand = np.array(sorted({min(max(c + d, 0), 2 ** 32 - 1) for c in cand for d in (-1, 0, 1)}), dtype=np.uint64)
+    init = _t(rs.randint(0, 16, n).astype(np.uint8), dev)
+    for e in envs.values():
+        e.reset(init)
+    adj = SoccerSimultaneousEnv(device=dev)
+    coll = [adj._state_to_observation(t) for t in ((1, 2, 1, 3, 0), (1, 2, 1, 3, 1), (2, 3, 1, 3, 0), (1, 3, 2, 3, 1), (1, 2, 1, 4, 0))]
+    for t in range(40):
+        a, b, r = (_t(rs.randint(0, hi, n).astype(np.uint8), dev) for hi in (5, 5, 16))
+        r32 = rs.randint(0, 2 ** 32, n, dtype=np.uint64)
+        pick = rs.rand(n) < 0.7
+        r32[pick] = cand[rs.randint(0, len(cand), int(pick.sum()))]
+        r32 = _t(r32.astype(np.uint32).view(np.int32), dev)
+        if t % 4 == 0:                                     # players next to each other: 2-way / 4-way outcomes everywhere
+            o = envs["walk"].current_obs().clone()
+            o[::2] = torch.tensor(coll, dtype=torch.int32, device=dev)[torch.from_numpy(rs.randint(0, len(coll), n // 2)).to(dev)]
+            for e in envs.values():
+                e.set_state(o)
+        outs = {}
+        for mode, e in envs.items():
+            monkeypatch.setenv("SOCCER_B200_SLIP_WALK", "1" if mode == "walk" else "0")
+            outs[mode] = [x.clone() for x in e.step(a, b, r, rng32=r32)]
+        for x, y in zip(outs["walk"], outs["index"]):
+            assert torch.equal(x, y), (slip, t)
+        assert torch.equal(envs["walk"].state, envs["index"].state)

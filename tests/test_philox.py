@@ -34,7 +34,7 @@ def test_random123_known_answers(oracle):
 
 def test_word_and_decode_contract(oracle):
     """Contract v2: one Philox call = the 4 envs of the aligned group env >> 2 at one step (counter = (group, step)),
-    word index env & 3; ja = mulhi(w, 25), step draw r32 = lo32(25 w), reset draw w & 3."""
+    word index env & 3; ja = mulhi(w, 25), step draw r32 = lo32(25 w), reset draw (w >> 2) & 3."""
     rs = np.random.RandomState(0)
     for _ in range(200):
         seed, env, step = (int(rs.randint(0, 2 ** 62)) for _ in range(3))
@@ -43,7 +43,7 @@ def test_word_and_decode_contract(oracle):
         w = oracle.philox_word(seed, env, step)
         assert w == words[env & 3]
         ja, r32 = (w * 25) >> 32, (w * 25) & 0xFFFFFFFF
-        assert oracle.philox_decode(w) == (ja // 5, ja % 5, r32 >> 30, w & 3)
+        assert oracle.philox_decode(w) == (ja // 5, ja % 5, r32 >> 30, (w >> 2) & 3)
         assert oracle.philox_r32(w) == r32
         # the table column index the kernels use: jr = mulhi(w, 100) = ja * 4 + (r32 >> 30)
         assert (w * 100) >> 32 == ja * 4 + (r32 >> 30)
@@ -53,13 +53,13 @@ def test_word_and_decode_contract(oracle):
 
 def test_decode_is_uniform_over_joint_action_and_draw(oracle):
     # every (joint action, 2-bit step draw) cell owns 2^32/100 +- 1 of the 2^32 words, and within a cell
-    # the reset draw (w & 3) is uniform to within one word
+    # the reset draw ((w >> 2) & 3) is uniform to within four words
     edges = [-(-(c << 32) // 100) for c in range(101)]          # first w with mulhi(w, 100) == c
     sizes = np.diff(np.array(edges, dtype=np.int64))
     assert sizes.min() >= (1 << 32) // 100 and sizes.max() <= (1 << 32) // 100 + 1
     for c in (0, 37, 99):
         assert (int(edges[c]) * 100) >> 32 == c and ((int(edges[c]) - 1) * 100) >> 32 == c - 1
-    assert all(abs((e1 - e0) // 4 - ((e1 - e0 + 3) // 4)) <= 1 for e0, e1 in zip(edges, edges[1:]))
+    assert all(abs((e1 - e0) // 16 - ((e1 - e0 + 15) // 16)) <= 1 for e0, e1 in zip(edges, edges[1:]))
     # r32 = lo32(25 w): 25 is odd, so w -> r32 is a bijection of the 32-bit words (exactly uniform draw); inside one
     # joint action the draws are the arithmetic progression r0 + 25 j, i.e. uniform at a resolution of 25 / 2^32
     assert pow(25, -1, 1 << 32) * 25 % (1 << 32) == 1
