@@ -62,7 +62,7 @@ class StepHostArgs(C.Structure):
     _fields_ = [("state", C.c_void_p), ("table", C.c_void_p), ("scratch", C.c_void_p), ("h_act_a", C.c_void_p),
                 ("h_act_b", C.c_void_p), ("h_rng8", C.c_void_p), ("h_obs", C.c_void_p), ("h_reward", C.c_void_p),
                 ("h_flags", C.c_void_p), ("n", C.c_int64), ("narrow", C.c_int32), ("n_chunks", C.c_int32),
-                ("s_in", C.c_void_p), ("s_compute", C.c_void_p), ("s_out", C.c_void_p)]
+                ("s_in", C.c_void_p), ("s_compute", C.c_void_p), ("s_out", C.c_void_p), ("d2h_zero_copy", C.c_int32)]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

@@ -871,7 +871,7 @@ int soccer_rollout(const soccer_pitch* pitch, uint32_t* state, const int8_t* pol
     // Philox contract v2: the 4 envs of a thread must be one aligned group of the GLOBAL env ids
     const bool vec = (n % 4 == 0) && (env_id_base % 4 == 0) && aligned(state, 16) && (!obs || aligned(obs, 16)) &&
                      (!reward || aligned(reward, 16)) && (!flags || aligned(flags, 4));
-    const RolloutArgs ra = { state, seed, step0, K, env_id_base, obs, reward, flags, stats, n, flip_reward ? 1 : 0 };
+    const RolloutArgs ra = { state, seed, step0, K, env_id_base, obs, reward, flags, stats, n, philox_round_keys(seed), flip_reward ? 1 : 0 };
     const bool streams = obs && reward && flags;
 #define SOCCER_LAUNCH_ROLLOUT(VEC, STR, SLIP, ITEMS)                                                    \
     do {                                                                                                 \
@@ -964,7 +964,7 @@ int step_table_slip_impl(const PitchDev& P, int64_t bytes, const soccer_step_arg
         do {                                                                                              \
             const int e0 = allow_big_smem(k_step_table_slip_i<RO, PH>, smem_i);                           \
             if (e0) return e0;                                                                            \
-            k_step_table_slip_i<RO, PH><<<table_grid(n_groups, kSlipIThreads), kSlipIThreads, (size_t)smem_i, st>>>(  \
+            k_step_table_slip_i<RO, PH><<<table_grid(n_groups, slip_i_threads<PH>()), slip_i_threads<PH>(), (size_t)smem_i, st>>>(  \
                 P, a->table, (uint32_t)bytes, a->slip_index + fc_bytes, (uint32_t)(2 * fc_bytes), E, a->state, act_a, act_b, \
                 a->rng8, a->rng32, a->obs, a->reward, a->flags, a->reset_obs, n_groups, ex);              \
         } while (0)
@@ -1229,7 +1229,7 @@ int soccer_rollout_table_policy(const soccer_pitch* pitch, const uint16_t* table
     // Philox contract v2: the 4 envs of a thread must be one aligned group of the GLOBAL env ids
     const bool vec = (n % 4 == 0) && (env_id_base % 4 == 0) && aligned(state, 16) && (!obs || aligned(obs, 16)) &&
                      (!reward || aligned(reward, 16)) && (!flags || aligned(flags, 4));
-    const RolloutArgs ra = { state, seed, step0, K, env_id_base, obs, reward, flags, stats, n, flip_reward ? 1 : 0 };
+    const RolloutArgs ra = { state, seed, step0, K, env_id_base, obs, reward, flags, stats, n, philox_round_keys(seed), flip_reward ? 1 : 0 };
     const bool streams = obs && reward && flags;
     const bool pol = policy_a || policy_b;
     const int64_t pol_bytes = 2 * (((int64_t)P.nS + 15) & ~15);
@@ -1329,7 +1329,7 @@ int soccer_bench_rollout_probe(uint32_t* state, int32_t K, int32_t* obs, float* 
 {
     if (!state || !obs || !reward || !flags || K < 0 || n < 8 || (n & 7)) return SOCCER_EINVAL;
     if (!aligned(state, 16) || !aligned(obs, 16) || !aligned(reward, 16) || !aligned(flags, 4)) return SOCCER_EINVAL;
-    const RolloutArgs ra = { state, 0, 0, K, 0, obs, reward, flags, nullptr, n };
+    const RolloutArgs ra = { state, 0, 0, K, 0, obs, reward, flags, nullptr, n, philox_round_keys(0), 0 };
     const int grid = table_grid(n / 4, kRolloutThreads);
     cudaStream_t st = (cudaStream_t)stream;
     switch (mode) {
@@ -1439,6 +1439,7 @@ int soccer_step_host(const soccer_pitch* pitch, const soccer_step_host_args* a)
         return SOCCER_EINVAL;
     const bool packed = a->narrow == SOCCER_HOST_PACKED;
     if (packed ? !a->table : (!a->h_act_b || !a->h_reward || !a->h_flags)) return SOCCER_EINVAL;
+    if (a->d2h_zero_copy && !packed) return SOCCER_EINVAL;
     if (pitch && pitch->slip_prob != 0.0) return SOCCER_ESLIP;
     if (a->n == 0) return SOCCER_OK;
     cudaStream_t s_in = (cudaStream_t)a->s_in, s_k = (cudaStream_t)a->s_compute, s_out = (cudaStream_t)a->s_out;
@@ -1467,8 +1468,8 @@ int soccer_step_host(const soccer_pitch* pitch, const soccer_step_host_args* a)
         SOCCER_CUDA(cudaStreamWaitEvent(s_k, ev_in, 0));
         SOCCER_CUDA(cudaEventDestroy(ev_in)); ev_in = nullptr;
         if (packed)
-            rc = soccer_step_table_packed(pitch, a->table, a->state + lo, sc.a + lo, sc.r + lo, sc.obs16 + lo, m,
-                                          (soccer_stream_t)s_k);
+            rc = soccer_step_table_packed(pitch, a->table, a->state + lo, sc.a + lo, sc.r + lo,
+                                          a->d2h_zero_copy ? (uint16_t*)a->h_obs + lo : sc.obs16 + lo, m, (soccer_stream_t)s_k);
         else if (a->narrow == SOCCER_HOST_NARROW)
             rc = soccer_step_narrow(pitch, a->table, a->state + lo, sc.a + lo, sc.b + lo, sc.r + lo, sc.obs16 + lo,
                                     sc.rew8 + lo, sc.f + lo, m, (soccer_stream_t)s_k);
@@ -1479,6 +1480,7 @@ int soccer_step_host(const soccer_pitch* pitch, const soccer_step_host_args* a)
             rc = soccer_step(pitch, a->state + lo, sc.a + lo, sc.b + lo, sc.r + lo, sc.obs + lo, sc.rew + lo,
                              sc.f + lo, nullptr, m, (soccer_stream_t)s_k);
         if (rc) goto done;
+        if (packed && a->d2h_zero_copy) continue;               // the kernel wrote the slice's results into h_obs itself
         SOCCER_CUDA(cudaEventCreateWithFlags(&ev_k, cudaEventDisableTiming));
         SOCCER_CUDA(cudaEventRecord(ev_k, s_k));
         SOCCER_CUDA(cudaStreamWaitEvent(s_out, ev_k, 0));

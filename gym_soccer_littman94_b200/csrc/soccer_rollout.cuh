@@ -22,9 +22,13 @@
 
 namespace soccer {
 
+#ifndef SOCCER_K2_PHILOX_WIDE
+#define SOCCER_K2_PHILOX_WIDE 1
+#endif
 struct RolloutArgs {
     uint32_t* state; uint64_t seed, step0; int32_t K; uint64_t env_id_base;
     int32_t* obs; float* reward; uint8_t* flags; unsigned long long* stats; int64_t n;
+    PhiloxRoundKeys rk;   // philox_round_keys(seed)
     int32_t flip;    // 1: the streamed reward is player B's (= -A's): the env's return agent is player_b (SIM:243-244).
                      // The goals_A / goals_B statistics always count by the unflipped sign.
 };
@@ -196,7 +200,6 @@ __device__ __forceinline__ void rollout_body(const Stepper& S, const RolloutArgs
     const int32_t K = a.K;
     // only an env with a folded policy has a flipped return agent: the uniform-policy instantiations carry no flip code
     const bool flip = Stepper::kHasPolicy && a.flip != 0;
-    const uint32_t key0 = (uint32_t)a.seed, key1 = (uint32_t)(a.seed >> 32);
     // Slot order (a slot = 32 threads x VEC envs).  Full passes are CTA-major: the 16 warps of a CTA own 16
     // adjacent slots, so every step the SM writes 8 KB / 8 KB / 2 KB contiguous per stream - measured with the
     // traffic probe (profiles/probe_modes.py), 8 KB chunks written by ONE SM reach 5.9-6.4 TB/s where 512 B chunks
@@ -247,7 +250,10 @@ __device__ __forceinline__ void rollout_body(const Stepper& S, const RolloutArgs
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const uint64_t sj = step + (uint64_t)j;
-                philox4x32_10(grp_lo, grp_hi, (uint32_t)sj, (uint32_t)(sj >> 32), key0, key1, w[j]);
+                // <true>: one IMAD.WIDE per product.  The round-1 build of this loop got that from the compiler's own fusion of
+                // mul.hi + mul.lo; with the per-step counters it stopped fusing (85 IMAD.HI + 85 IMAD in the 4-step body
+                // instead of 45 IMAD.WIDE: +5 instructions per env-step), so it is asked for explicitly
+                philox4x32_10_rk<SOCCER_K2_PHILOX_WIDE != 0>(grp_lo, grp_hi, (uint32_t)sj, (uint32_t)(sj >> 32), a.rk, w[j]);
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {

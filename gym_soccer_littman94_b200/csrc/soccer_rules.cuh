@@ -161,6 +161,37 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
+// The same with the ten round keys precomputed (kernel parameters -> constant bank operands of the XORs): the rollout
+// kernels call it once per step, and 20 key additions per call are a third of the multiplies
+struct PhiloxRoundKeys { uint32_t k0[10], k1[10]; };
+inline PhiloxRoundKeys philox_round_keys(uint64_t seed)
+{
+    PhiloxRoundKeys r;
+    uint32_t a = (uint32_t)seed, b = (uint32_t)(seed >> 32);
+    for (int i = 0; i < 10; ++i) { r.k0[i] = a; r.k1[i] = b; a += 0x9E3779B9u; b += 0xBB67AE85u; }
+    return r;
+}
+template <bool WIDE = false>
+__device__ __forceinline__ void philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                 const PhiloxRoundKeys& rk, uint32_t out[4])
+{
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        uint32_t h0, l0, h1, l1;
+        if (WIDE) {
+            const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+            h0 = (uint32_t)(p0 >> 32); l0 = (uint32_t)p0; h1 = (uint32_t)(p1 >> 32); l1 = (uint32_t)p1;
+        } else {
+            h0 = __umulhi(0xD2511F53u, c0); l0 = 0xD2511F53u * c0;
+            h1 = __umulhi(0xCD9E8D57u, c2); l1 = 0xCD9E8D57u * c2;
+        }
+        const uint32_t n0 = h1 ^ c1 ^ rk.k0[i];
+        const uint32_t n2 = h0 ^ c3 ^ rk.k1[i];
+        c1 = l1; c3 = l0; c0 = n0; c2 = n2;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
 #ifndef SOCCER_K1_PHILOX_WIDE
 #define SOCCER_K1_PHILOX_WIDE 0
 #endif

@@ -995,15 +995,20 @@ __device__ __forceinline__ GroupS load_group_slip(const uint4* st, const uint32_
     else { x.r = ld_stream(rg + g); x.d = __ldcs(dr + g); }
     return x;
 }
+// Launch shape, measured on B200 at 2^24 envs (profiles/r02g_time_k1slip.log; groups in flight x threads):
+//   injected rng32  2 x 768: 151 G   1 x 1024: 183 G   1 x 768: 186 G   2 x 512: 187 G   1 x 512: 203 G env-steps/s
+//   Philox          2 x 768: 187 G   1 x 1024: 215 G   1 x 768: 239 G   2 x 512: 226 G   1 x 512: 232 G
+// (a group + its prefetched successor are 22 data registers; 1024 threads = 64 registers spill, 512 leave 16 warps)
 #ifndef SOCCER_SLIP_I_GROUPS
-#define SOCCER_SLIP_I_GROUPS 2         // groups of 4 envs a thread has in flight (1 or 2)
+#define SOCCER_SLIP_I_GROUPS 1         // groups of 4 envs a thread has in flight (1 or 2)
 #endif
 #ifndef SOCCER_SLIP_I_THREADS
-#define SOCCER_SLIP_I_THREADS 768      // two groups in flight + prefetch of two more: 44 data registers; 1024 threads (64 registers) spill 160-190 bytes
+#define SOCCER_SLIP_I_THREADS 0        // 0: 512 for injected draws, 768 for Philox
 #endif
-constexpr int kSlipIThreads = SOCCER_SLIP_I_THREADS;
+template <bool PHILOX>
+constexpr int slip_i_threads() { return SOCCER_SLIP_I_THREADS ? SOCCER_SLIP_I_THREADS : (PHILOX ? 768 : 512); }
 template <bool RESET_OBS, bool PHILOX>
-__global__ void __launch_bounds__(kSlipIThreads, 1)
+__global__ void __launch_bounds__((slip_i_threads<PHILOX>()), 1)
 k_step_table_slip_i(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t table_bytes,
                     const uint8_t* __restrict__ gfc, uint32_t fc_bytes, const SlipE E,
                     uint32_t* __restrict__ state, const uint8_t* __restrict__ act_a, const uint8_t* __restrict__ act_b,

@@ -596,7 +596,12 @@ class SoccerVecEnv:
                          sync: bool = True, zero_copy: Optional[bool] = None) -> torch.Tensor:
         """step_host() with packed streams: 2 bytes up (joint action byte, draw byte) and 2 bytes down (one int16
         result word, see unpack_result) per env over PCIe instead of 3 + 4.  Returns a pinned CPU int16 tensor owned
-        by the env and overwritten by the next call.  rng_mode='philox': no draw stream -- 1 byte up, 2 down."""
+        by the env and overwritten by the next call.  rng_mode='philox': no draw stream -- 1 byte up, 2 down.
+        zero_copy: True = the kernel reads and writes the pinned host buffers itself; False = copy engines both ways,
+        pipelined over n_chunks slices; "out" = hybrid: the copy engine uploads slice by slice while each slice's kernel
+        writes its result words straight to the host (posted PCIe writes run at the link rate, the kernel's PCIe reads
+        do not); None = True, the fastest measured at every batch size (2^24 envs: zero copy 18.8 G env-steps/s, hybrid and
+        staged 16.3 G with 4 slices -- the chunked uploads only reach 32 GB/s; profiles/r02h_time_host_paths.log)."""
         self._check_packed()
         philox = self.rng_mode == "philox"
         if philox:
@@ -613,8 +618,9 @@ class SoccerVecEnv:
             return h_res
         if zero_copy is None:
             zero_copy = True
+        hybrid = zero_copy == "out"
         with torch.cuda.device(self.device):
-            if zero_copy and joint.is_pinned() and (philox or rng8.is_pinned()):
+            if zero_copy is True and joint.is_pinned() and (philox or rng8.is_pinned()):
                 cur = torch.cuda.current_stream(self.device)
                 self._packed_call(_ptr(joint), _ptr(rng8), _ptr(h_res), C.c_void_p(cur.cuda_stream))
                 self.step_count += 1
@@ -632,11 +638,12 @@ class SoccerVecEnv:
             a.h_obs, a.h_reward, a.h_flags = h_res.data_ptr(), None, None
             a.n, a.narrow, a.n_chunks = self.num_envs, HOST_PACKED, max(1, int(n_chunks))
             a.s_in, a.s_compute, a.s_out = s_in.cuda_stream, s_k.cuda_stream, s_out.cuda_stream
+            a.d2h_zero_copy = 1 if hybrid else 0
             check(self.lib.soccer_step_host(C.byref(self.pitch), C.byref(a)), "soccer_step_host")
             cur.wait_stream(s_k)
             self.step_count += 1
             if sync:
-                s_out.synchronize()
+                (s_k if hybrid else s_out).synchronize()
         return h_res
 
     def rollout(self, K: int, policy_a=None, policy_b=None, want_streams: bool = True, stats: Optional[torch.Tensor] = None,

@@ -375,6 +375,11 @@ typedef struct soccer_step_host_args {
     int32_t         narrow;     /* SOCCER_HOST_WIDE / _NARROW / _PACKED */
     int32_t         n_chunks;   /* >= 1 */
     soccer_stream_t s_in, s_compute, s_out;
+    int32_t         d2h_zero_copy; /* 1 (SOCCER_HOST_PACKED only; h_obs must be pinned + device-mapped, e.g. soccer_host_alloc):
+                                      uploads go through the copy engine slice by slice as above, but each slice's kernel
+                                      WRITES its result words straight into h_obs over PCIe (posted writes run at the link
+                                      rate, unlike the kernel's PCIe reads) -- no download copies; results are valid once
+                                      s_compute has been synchronised */
 } soccer_step_host_args;
 int soccer_step_host_scratch_bytes_host(int64_t n, int64_t *bytes);
 int soccer_step_host(const soccer_pitch *pitch, const soccer_step_host_args *args);

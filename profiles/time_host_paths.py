@@ -44,4 +44,6 @@ for logn in (24, 22, 20, 17):
     run("zero-copy narrow", lambda i: env.step_host(*ins[i % 2], narrow=True, zero_copy=True), 3, 4)
     run("zero-copy wide", lambda i: env.step_host(*ins[i % 2], narrow=False, zero_copy=True), 3, 9)
     run("zero-copy packed", lambda i: env.step_host_packed(*pk[i % 2], zero_copy=True), 2, 2)
+    for ch in (2, 4, 8, 16, 32):
+        run(f"hybrid packed chunks={ch}", lambda i: env.step_host_packed(*pk[i % 2], n_chunks=ch, zero_copy="out"), 2, 2)
     del env

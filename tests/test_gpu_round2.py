@@ -69,10 +69,11 @@ def test_k1_at_2_24_envs_vs_oracle_every_env(dev, oracle, kernel):
     assert np.array_equal(env.timesteps().cpu().numpy(), ts)              # rollout_injected advanced ts in place
 
 
-@pytest.mark.parametrize("zero_copy", [True, False])
+@pytest.mark.parametrize("zero_copy", [None, True, False, "out"])
 def test_step_host_packed_at_2_24_envs_vs_oracle(dev, oracle, zero_copy):
-    """The headline end-to-end call exactly as bench.py makes it (2^24 envs, n_chunks = 8, pinned arena buffers, zero
-    copy; and the staged copy-engine pipeline): the unpacked result words of ALL envs against the oracle."""
+    """The headline end-to-end call exactly as bench.py makes it (2^24 envs, n_chunks = 8, pinned arena buffers;
+    None = the automatic choice bench.py gets, True = zero copy both ways, False = the staged copy-engine pipeline,
+    "out" = copy-engine uploads + zero-copy result writes): the unpacked result words of ALL envs against the oracle."""
     from gym_soccer_littman94_b200.envs import SoccerVecEnv
     N, T = 1 << 24, 3
     m = oracle.OracleModel(5, 4, 0.0)
