@@ -271,12 +271,16 @@ def run_ours(args):
         time.sleep(0.3)
     # (1) the timed region: EXACTLY K steps between two events, nothing else in the stream
     start, k_done, end = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-    stats.zero_()
     barrier()
     if world > 1:
         # device-side rendezvous right before the start event: the host-side barrier lets the ranks go tens of
         # microseconds apart, which the closing all-reduce would otherwise charge to the early ranks' K steps
         dist.all_reduce(torch.zeros(1, device=dev))
+    # the W warm-up steps run DIRECTLY ahead of the timed ones, in the same stream: the clock sampler's start-up above
+    # left the GPU idle for 0.3 s, and the first launches after an idle gap run ~10 % slower than steady state
+    for i in range(W):
+        env.step(*ins[i % RING], out=outs[i % RING], stats=stats)
+    stats.zero_()
     start.record()
     for i in range(K):
         env.step(*ins[i % RING], out=outs[i % RING], stats=stats)

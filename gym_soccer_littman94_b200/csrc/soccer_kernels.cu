@@ -1288,6 +1288,76 @@ int soccer_rollout_table_policy(const soccer_pitch* pitch, const uint16_t* table
     return launch_status();
 }
 
+int soccer_cluster_table_bytes_host(const soccer_pitch* pitch, int64_t* bytes, int32_t* cluster_size)
+{
+    if (!bytes) return SOCCER_EINVAL;
+    PitchDev P; const int rc = make_pitch_dev(pitch, &P); if (rc) return rc;
+    if (P.nS > 4096) return SOCCER_ETABLE;                    // 12-bit next-observation field of the 16-bit entries
+    const int64_t tb = ((int64_t)P.nS * 200 + 15) / 16 * 16;
+    int cl = 1;
+    while ((int64_t)cl * kClusterSliceBytes < tb) cl *= 2;
+    if (cl > 8) return SOCCER_ETABLE;
+    *bytes = tb;
+    if (cluster_size) *cluster_size = cl;
+    return SOCCER_OK;
+}
+
+int soccer_build_cluster_table(const soccer_pitch* pitch, uint16_t* table, soccer_stream_t stream)
+{
+    if (!table) return SOCCER_EINVAL;
+    PitchDev P; int rc = make_pitch_dev(pitch, &P); if (rc) return rc;
+    int64_t bytes; rc = soccer_cluster_table_bytes_host(pitch, &bytes, nullptr); if (rc) return rc;
+    k_build_step_table<<<grid_for((int64_t)P.nS * 100, 4), kThreads, 0, (cudaStream_t)stream>>>(P, P.nS, table);
+    return launch_status();
+}
+
+int soccer_rollout_table_cluster(const soccer_pitch* pitch, const uint16_t* table, uint32_t* state, uint64_t seed,
+                                 uint64_t step0, int32_t K, uint64_t env_id_base, int32_t* obs, float* reward,
+                                 uint8_t* flags, unsigned long long* stats, int64_t n, soccer_stream_t stream)
+{
+    if (!table || !state || n < 0 || K < 0 || K > kMaxRolloutK) return SOCCER_EINVAL;
+    if (pitch && pitch->slip_prob != 0.0) return SOCCER_ESLIP;
+    PitchDev P; int rc = make_pitch_dev(pitch, &P); if (rc) return rc;
+    int64_t bytes; int32_t cl; rc = soccer_cluster_table_bytes_host(pitch, &bytes, &cl); if (rc) return rc;
+    if (!aligned(table, 16)) return SOCCER_EINVAL;
+    if (n == 0 || K == 0) return SOCCER_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool vec = (n % 4 == 0) && (env_id_base % 4 == 0) && aligned(state, 16) && (!obs || aligned(obs, 16)) &&
+                     (!reward || aligned(reward, 16)) && (!flags || aligned(flags, 4));
+    const RolloutArgs ra = { state, seed, step0, K, env_id_base, obs, reward, flags, stats, n, philox_round_keys(seed), 0 };
+    const bool streams = obs && reward && flags;
+    const size_t smem = (size_t)kClusterSliceBytes + 16;
+#define SOCCER_LAUNCH_ROLLOUT_C(VEC, STR, ITEMS)                                                          \
+    do {                                                                                                  \
+        auto kern = k_rollout_table_cluster<VEC, STR>;                                                    \
+        const int e0 = allow_big_smem(kern, (int64_t)smem);                                               \
+        if (e0) return e0;                                                                                \
+        cudaLaunchConfig_t cfg = {};                                                                      \
+        cfg.blockDim = dim3(kRolloutThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;               \
+        cudaLaunchAttribute attr[1];                                                                      \
+        attr[0].id = cudaLaunchAttributeClusterDimension;                                                 \
+        attr[0].val.clusterDim.x = (unsigned)cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1; \
+        cfg.attrs = attr; cfg.numAttrs = 1;                                                               \
+        cfg.gridDim = dim3((unsigned)cl);                                                                 \
+        int n_clusters = 0;                                                                               \
+        if (cudaOccupancyMaxActiveClusters(&n_clusters, kern, &cfg) != cudaSuccess || n_clusters < 1) {   \
+            (void)cudaGetLastError(); n_clusters = sm_count() / cl;                                       \
+        }                                                                                                 \
+        const int64_t need = ((ITEMS) + kRolloutThreads - 1) / kRolloutThreads;                           \
+        int64_t ctas = (int64_t)n_clusters * cl;                                                          \
+        if (need < ctas) ctas = (need + cl - 1) / cl * cl;                                                \
+        cfg.gridDim = dim3((unsigned)ctas);                                                               \
+        const cudaError_t e1 = cudaLaunchKernelEx(&cfg, kern, P, table, (uint32_t)bytes, ra);             \
+        if (e1 != cudaSuccess) return (int)e1;                                                            \
+    } while (0)
+    if (vec && streams) SOCCER_LAUNCH_ROLLOUT_C(4, true, n / 4);
+    else if (vec) SOCCER_LAUNCH_ROLLOUT_C(4, false, n / 4);
+    else if (streams) SOCCER_LAUNCH_ROLLOUT_C(1, true, n);
+    else SOCCER_LAUNCH_ROLLOUT_C(1, false, n);
+#undef SOCCER_LAUNCH_ROLLOUT_C
+    return launch_status();
+}
+
 int soccer_rollout_table(const soccer_pitch* pitch, const uint16_t* table, uint32_t* state, uint64_t seed,
                          uint64_t step0, int32_t K, uint64_t env_id_base, int32_t* obs, float* reward,
                          uint8_t* flags, unsigned long long* stats, int64_t n, soccer_stream_t stream)

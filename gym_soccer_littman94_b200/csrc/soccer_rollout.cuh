@@ -401,6 +401,75 @@ k_rollout_table_slipi(const PitchDev P, const uint16_t* __restrict__ gtable, uin
     rollout_body<VEC, STREAMS>(S, a, &blk);
 }
 
+// ---- K2 for mid-size pitches: the step table sharded over the shared memory of a thread-block CLUSTER.
+// A 7x5 table is 476 KB, a 9x5 one 792 KB: more than one SM's 227 KB, but a cluster of 4 / 8 CTAs holds it once, each
+// CTA one 128 KB slice (byte offset >> 17 = owner rank), and every CTA reads any entry through distributed shared
+// memory (mapa + ld.shared::cluster).  Entries keep the 16-bit format, so nS <= 4096 (7x5, 8x5, 9x5, 7x6 ...).
+constexpr uint32_t kClusterSliceLog2 = 17;
+constexpr uint32_t kClusterSliceBytes = 1u << kClusterSliceLog2;
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+struct ClusterTableStepper {
+    static constexpr bool kCollective = false, kHasPolicy = false;
+    uint32_t slice;             // shared::cta address of this CTA's slice (the same offset in every CTA of the cluster)
+    uint32_t isd, last;
+    __device__ __forceinline__ uint32_t timestep(uint32_t s) const { return s >> 16; }
+    template <int VEC>
+    __device__ __forceinline__ void step(uint32_t* s, const uint32_t* word, uint32_t* oo, uint32_t* rr,
+                                         uint32_t& fw, int32_t& net, bool) const
+    {
+        uint32_t ff[4] = { 0, 0, 0, 0 };
+        int32_t e[4];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            const uint32_t off = min((s[i] & 0xFFFFu) * 100u + philox_jr(word[i]), last) * 2u;
+            uint32_t raddr;
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(slice + (off & (kClusterSliceBytes - 1u))), "r"(off >> kClusterSliceLog2));
+            asm volatile("ld.shared::cluster.s16 %0, [%1];" : "=r"(e[i]) : "r"(raddr));
+        }
+        const TblCtx c = { 0u, isd, last };
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            const TblOut o = table_finish(c, s[i], e[i], word[i] & 0xCu);
+            s[i] = o.state; oo[i] = o.obs; rr[i] = __float_as_uint((float)o.rew_i); ff[i] = o.flags;
+            net += o.rew_i;
+        }
+        fw = VEC == 4 ? pack4(ff[0], ff[1], ff[2], ff[3]) : ff[0];
+    }
+};
+
+template <int VEC, bool STREAMS>
+__global__ void __launch_bounds__(kRolloutThreads, 1)
+k_rollout_table_cluster(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t table_bytes, const RolloutArgs a)
+{
+    extern __shared__ __align__(128) uint8_t smem_raw[];     // [slice 128 KB][isd 16 B]
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ BlkStats blk;
+    if (threadIdx.x < 5) blk.v[threadIdx.x] = 0;
+    const uint32_t rank = cluster_ctarank();
+    const uint32_t lo = rank * kClusterSliceBytes;
+    const uint32_t mine = lo < table_bytes ? min(kClusterSliceBytes, table_bytes - lo) : 0u;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&bar, mine);
+        const uint32_t chunk = 16384;
+        for (uint32_t off = 0; off < mine; off += chunk)
+            tma_load_1d(smem_raw + off, reinterpret_cast<const uint8_t*>(gtable) + lo + off, min(chunk, mine - off), &bar);
+    }
+    if (threadIdx.x < 4) reinterpret_cast<int32_t*>(smem_raw + kClusterSliceBytes)[threadIdx.x] = P.isd_obs[threadIdx.x];
+    __syncthreads();
+    wait_table(&bar);
+    cluster_sync_all();                                      // every slice of the cluster is in place
+    ClusterTableStepper S;
+    S.slice = smem_u32(smem_raw); S.isd = S.slice + kClusterSliceBytes; S.last = (uint32_t)P.nS * 100u - 1u;
+    rollout_body<VEC, STREAMS>(S, a, &blk);
+    cluster_sync_all();                                      // no CTA leaves while a neighbour may still read its slice
+}
+
 // (forcing 3 resident CTAs - 80 registers - measured 283 vs 291 G env-steps/s: the kernel is issue-bound)
 template <int VEC, bool STREAMS, bool SLIP>
 __global__ void __launch_bounds__(kThreads)

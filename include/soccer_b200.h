@@ -321,6 +321,16 @@ int soccer_rollout_table_policy(const soccer_pitch *pitch, const uint16_t *table
                                 uint64_t env_id_base, int32_t flip_reward, int32_t *obs, float *reward,
                                 uint8_t *flags, unsigned long long *stats, int64_t n,
                                 soccer_stream_t stream);
+/* ---- K2 for mid-size pitches (7x5, 8x5, 9x5, 7x6: nS <= 4096): the step table sharded over the shared memory of a
+ * thread-block cluster of 2 / 4 / 8 CTAs, 128 KB per CTA, read through distributed shared memory.  Same table format
+ * (soccer_build_cluster_table fills nS * 100 entries), SOCCER_LAYOUT_INDEX states, uniform policy, slip_prob == 0;
+ * results identical to soccer_rollout on the converted states. */
+int soccer_cluster_table_bytes_host(const soccer_pitch *pitch, int64_t *bytes, int32_t *cluster_size);
+int soccer_build_cluster_table(const soccer_pitch *pitch, uint16_t *table, soccer_stream_t stream);
+int soccer_rollout_table_cluster(const soccer_pitch *pitch, const uint16_t *table, uint32_t *state,
+                                 uint64_t seed, uint64_t step0, int32_t K, uint64_t env_id_base,
+                                 int32_t *obs, float *reward, uint8_t *flags, unsigned long long *stats,
+                                 int64_t n, soccer_stream_t stream);
 /* translate a state tensor between layouts (in place allowed); goal / needs_reset states map
  * to observation 0 in the INDEX layout and cannot be converted back */
 int soccer_convert_state(const soccer_pitch *pitch, const uint32_t *in, uint32_t *out,

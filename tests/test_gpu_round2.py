@@ -433,3 +433,41 @@ def test_slip_integer_thresholds_equal_walk(dev, slip, monkeypatch):
         for x, y in zip(outs["walk"], outs["index"]):
             assert torch.equal(x, y), (slip, t)
         assert torch.equal(envs["walk"].state, envs["index"].state)
+
+
+# ----------------------------------------------------------------------------- cluster / DSMEM table (mid-size pitches)
+@pytest.mark.parametrize("w,h,n,base", [(7, 5, 4096, 0), (7, 5, 70003, 0), (9, 5, 8192, 1 << 20), (6, 5, 1000, 4)])
+def test_k2_cluster_table_equals_rules_kernel(dev, w, h, n, base):
+    """soccer_rollout_table_cluster (step table sharded over the shared memory of a 4- / 8-CTA cluster, read through
+    distributed shared memory) == soccer_rollout (rules inline) on the same Philox draws: streams, statistics, states."""
+    import ctypes as C
+    from gym_soccer_littman94_b200 import _lib
+    from gym_soccer_littman94_b200.envs import SoccerVecEnv
+    L = _lib.lib()
+    K, seed = 150, 77
+    pitch = _lib.Pitch(w, h, 0.0)
+    nb, cl = C.c_int64(), C.c_int32()
+    _lib.check(L.soccer_cluster_table_bytes_host(C.byref(pitch), C.byref(nb), C.byref(cl)), "bytes")
+    assert cl.value in (2, 4, 8)
+    p = lambda t: None if t is None else C.c_void_p(t.data_ptr())      # noqa: E731
+    table = torch.zeros(nb.value // 2, dtype=torch.int16, device=dev)
+    _lib.check(L.soccer_build_cluster_table(C.byref(pitch), p(table), None), "build")
+    ref = SoccerVecEnv(n, width=w, height=h, device=dev, rng_mode="philox", kernel="rules", seed=seed, env_id_base=base)
+    ref.reset()
+    st_idx = torch.empty_like(ref.state)
+    _lib.check(L.soccer_convert_state(C.byref(pitch), p(ref.state), p(st_idx), 1, n, None), "convert")
+    ro, rr, rf, rs = ref.rollout(K)
+    co = torch.empty((K, n), dtype=torch.int32, device=dev)
+    cr = torch.empty((K, n), dtype=torch.float32, device=dev)
+    cf = torch.empty((K, n), dtype=torch.uint8, device=dev)
+    cs = torch.zeros(6, dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()
+    _lib.check(L.soccer_rollout_table_cluster(C.byref(pitch), p(table), p(st_idx), seed, 0, K, base, p(co), p(cr), p(cf), p(cs),
+                                              n, None), "cluster rollout")
+    torch.cuda.synchronize()
+    assert torch.equal(co, ro) and torch.equal(cr, rr) and torch.equal(cf, rf) and torch.equal(cs, rs)
+    back = torch.empty_like(st_idx)
+    _lib.check(L.soccer_convert_state(C.byref(pitch), p(st_idx), p(back), 0, n, None), "convert back")
+    torch.cuda.synchronize()
+    assert torch.equal(back, ref.state)
+    assert L.soccer_cluster_table_bytes_host(C.byref(_lib.Pitch(9, 6, 0.0)), C.byref(nb), C.byref(cl)) == -5     # nS > 4096
