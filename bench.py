@@ -229,8 +229,17 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     numa_cpus = bind_near_gpu(local) if (world > 1 and not args.no_bind) else None
+    p2p = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        # the one collective of the path as a hand-written kernel over NVLink peer memory (falls back to NCCL where the
+        # symmetric-memory rendezvous is not available); --collective nccl forces the library all-reduce
+        from gym_soccer_littman94_b200.dist import P2PStatsAllReduce
+        if args.collective == "p2p":
+            p2p = P2PStatsAllReduce.create(dev)
+    from gym_soccer_littman94_b200.dist import allreduce_stats
+    collective = "none (1 GPU)" if world == 1 else ("soccer_stats_allreduce_p2p (peer-memory kernel over NVLink)" if p2p is not None
+                                                    else "ncclAllReduce (torch.distributed)")
     N = args.envs_per_gpu
     K, W = args.steps, max(args.warmup, 3)
     RING = 4
@@ -263,7 +272,7 @@ def run_ours(args):
     for i in range(W):
         env.step(*ins[i % RING], out=outs[i % RING], stats=stats)
     if world > 1:
-        dist.all_reduce(stats.clone())                 # warm the communicator
+        allreduce_stats(stats.clone(), p2p)            # warm the collective
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -272,21 +281,21 @@ def run_ours(args):
     # (1) the timed region: EXACTLY K steps between two events, nothing else in the stream
     start, k_done, end = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     barrier()
-    if world > 1:
-        # device-side rendezvous right before the start event: the host-side barrier lets the ranks go tens of
-        # microseconds apart, which the closing all-reduce would otherwise charge to the early ranks' K steps
-        dist.all_reduce(torch.zeros(1, device=dev))
     # the W warm-up steps run DIRECTLY ahead of the timed ones, in the same stream: the clock sampler's start-up above
     # left the GPU idle for 0.3 s, and the first launches after an idle gap run ~10 % slower than steady state
     for i in range(W):
         env.step(*ins[i % RING], out=outs[i % RING], stats=stats)
     stats.zero_()
+    if world > 1:
+        # device-side rendezvous right before the start event: the host-side barrier lets the ranks go tens of
+        # microseconds apart, which the closing all-reduce would otherwise charge to the early ranks' K steps
+        dist.all_reduce(torch.zeros(1, device=dev))
     start.record()
     for i in range(K):
         env.step(*ins[i % RING], out=outs[i % RING], stats=stats)
     k_done.record()
     if world > 1:
-        dist.all_reduce(stats)                         # the one collective of the path
+        allreduce_stats(stats, p2p)                    # the one collective of the path, same stream
     end.record()
     barrier()
     total_ms = start.elapsed_time(end)
@@ -317,8 +326,15 @@ def run_ours(args):
         clocks["sampled_over"] = "the timed K steps, the per-launch pass and %d further back-to-back launches (%.2f s)" % (
             n_sus, sustained["seconds"])
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    tails = [tail_us]
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        # every rank's tail: the rank that arrives last waits for nobody (its tail = the all-reduce alone), the others
+        # also wait for it (rank skew over the K steps)
+        tt = torch.zeros(world, dtype=torch.float64, device=dev)
+        tt[rank] = tail_us
+        dist.all_reduce(tt)
+        tails = [float(x) for x in tt.cpu()]
     total_ms = float(t.item())
     value = world * N * K / (total_ms * 1e-3)
     peak, peak_src = measured_peaks()
@@ -550,7 +566,7 @@ def run_ours(args):
             for _ in range(L3):
                 e3.rollout(K3, out=bufs, stats=st3)
             if world > 1:
-                dist.all_reduce(st3)
+                allreduce_stats(st3, p2p)
             s1.record()
             barrier()
             t = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
@@ -558,16 +574,18 @@ def run_ours(args):
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item()) / L3
             ar_us = None
-            if world > 1:                       # the one collective of the path, timed on its own
-                tmp = st3.clone()
-                dist.all_reduce(tmp)
-                barrier()
-                s0.record()
-                for _ in range(10):
-                    dist.all_reduce(tmp)
-                s1.record()
-                barrier()
-                ar_us = s0.elapsed_time(s1) * 100.0
+            if world > 1:                       # the one collective of the path, timed on its own (10 back to back)
+                ar_us = {}
+                for name, fn in (("nccl", lambda x: dist.all_reduce(x)),) + ((("p2p_kernel", lambda x: p2p(x)),) if p2p else ()):
+                    tmp = st3.clone()
+                    fn(tmp)
+                    barrier()
+                    s0.record()
+                    for _ in range(10):
+                        fn(tmp)
+                    s1.record()
+                    barrier()
+                    ar_us[name] = s0.elapsed_time(s1) * 100.0
             scratch = e3.state.clone()
 
             def rprobe():
@@ -607,7 +625,8 @@ def run_ours(args):
         esh.reset()
         _, _, _, st_sh = esh.rollout(SHARD_INVARIANT["K"], want_streams=False)
         if world > 1:
-            dist.all_reduce(st_sh)
+            allreduce_stats(st_sh, p2p)
+        shard["collective"] = collective
         shard["stats_allreduce"] = [int(x) for x in st_sh.cpu()]
         shard["shard_invariant"] = shard["stats_allreduce"] == SHARD_INVARIANT["stats"]
         del esh
@@ -888,8 +907,9 @@ def run_ours(args):
                          "oracle/_ref absent (build() stages it where /root/reference exists)"},
         "host": host_info(),
         "shard_invariant": shard.get("shard_invariant"), "shard_invariant_detail": shard,
-        "timed_region": {"steps": K, "statistics": "fused into K1 (soccer_step_args.stats)", "tail_after_last_step_us": tail_us,
-                         "tail_is": "the NCCL sum all-reduce of the 48-byte statistics vector" if world > 1 else "nothing (1 GPU)"},
+        "timed_region": {"steps": K, "statistics": "fused into K1 (soccer_step_args.stats)", "tail_after_last_step_us": tail_us, "tail_us_per_rank": tails,
+                         "tail_is": "the sum all-reduce of the 48-byte statistics vector + waiting for the slowest rank"
+                         if world > 1 else "nothing (1 GPU)", "collective": collective},
         "e2e": e2e_line,
         "sustained": sustained,
         "gpu_launches": K,
@@ -912,6 +932,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--chunks", type=int, default=8, help="pipeline slices of the host-buffer step")
     ap.add_argument("--no-bind", action="store_true", help="do not pin ranks to the CPU cores local to their GPU")
+    ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"],
+                    help="statistics all-reduce: the peer-memory kernel (default; NCCL if unavailable) or NCCL")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: anything native libraries print there while the bench runs (NCCL's
     # "NCCL version ..." banner, for one) is sent to stderr instead

@@ -555,6 +555,47 @@ k_step_stats(const uint8_t* __restrict__ flags, const float* __restrict__ reward
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&stats[4], (unsigned long long)n);
 }
 
+// ---- the one collective of the path, written over NVLink peer memory: sum all-reduce of the 6-entry statistics
+// vector.  Every rank owns a symmetric buffer of 2 x 16 slots of 8 x uint64 (parity x source rank; 6 values, pad,
+// flag) that all ranks can address (peer[] = the same buffer on every rank).  ONE warp: lane r stores this rank's
+// vector into rank r's slot [parity][my rank], fences (system scope) and publishes the epoch in the slot's flag; lane r
+// then waits for rank r's contribution to arrive in the LOCAL buffer, and a warp reduction leaves the sum in
+// stats[0..5].  No host round trip, no second stream: the kernel is enqueued right behind the last step kernel.
+// Two parities suffice: a rank can only enter call e + 2 after every rank has left call e (it needs their e + 1 data).
+struct P2PStatsArgs { unsigned long long* peer[16]; int32_t rank, world; unsigned long long epoch; unsigned long long* stats; };
+__global__ void __launch_bounds__(32)
+k_stats_allreduce_p2p(const P2PStatsArgs a)
+{
+    const int lane = threadIdx.x;
+    const unsigned long long par = a.epoch & 1ull;
+    unsigned long long v[6] = { 0, 0, 0, 0, 0, 0 };
+    if (lane < a.world) {
+        unsigned long long* dst = a.peer[lane] + (par * 16ull + (unsigned long long)a.rank) * 8ull;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) asm volatile("st.volatile.global.u64 [%0], %1;" :: "l"(dst + j), "l"(a.stats[j]) : "memory");
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(dst + 7), "l"(a.epoch) : "memory");
+        const unsigned long long* src = a.peer[a.rank] + (par * 16ull + (unsigned long long)lane) * 8ull;
+        const long long t0 = clock64();
+        unsigned long long f;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(src + 7) : "memory");
+            if (f != a.epoch && clock64() - t0 > (4ll << 30)) __trap();     // ~2 s: a peer died; do not hang the GPU
+        } while (f != a.epoch);
+#pragma unroll
+        for (int j = 0; j < 6; ++j) asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v[j]) : "l"(src + j) : "memory");
+    }
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[j] += __shfl_xor_sync(0xFFFFFFFFu, v[j], o);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) a.stats[j] = v[j];
+    }
+}
+
 constexpr int32_t kMaxRolloutK = 1 << 28;     // per-pass statistics are 32-bit: 4 envs x K flag counts
 int64_t round_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 // scratch layout of soccer_step_host: three input byte streams, flags, obs, reward, obs16, rew8
@@ -1692,6 +1733,27 @@ int soccer_policy_eval(const soccer_pitch* pitch, const int8_t* policy_a, const 
     void* args[] = { (void*)&P, (void*)&a };
     e = cudaLaunchCooperativeKernel((const void*)k_policy_eval, dim3((unsigned)grid), dim3(kThreads), args, 0, st);
     return (int)e;
+}
+
+int soccer_stats_allreduce_p2p_bytes_host(int64_t* bytes)
+{
+    if (!bytes) return SOCCER_EINVAL;
+    *bytes = 2 * 16 * 8 * 8;
+    return SOCCER_OK;
+}
+
+int soccer_stats_allreduce_p2p(const uint64_t* peer_ptrs, int32_t rank, int32_t world, uint64_t epoch,
+                               unsigned long long* stats, soccer_stream_t stream)
+{
+    if (!peer_ptrs || !stats || world < 1 || world > 16 || rank < 0 || rank >= world || epoch == 0) return SOCCER_EINVAL;
+    P2PStatsArgs a = {};
+    for (int r = 0; r < world; ++r) {
+        if (!peer_ptrs[r] || (peer_ptrs[r] & 7u)) return SOCCER_EINVAL;
+        a.peer[r] = reinterpret_cast<unsigned long long*>(peer_ptrs[r]);
+    }
+    a.rank = rank; a.world = world; a.epoch = epoch; a.stats = stats;
+    k_stats_allreduce_p2p<<<1, 32, 0, (cudaStream_t)stream>>>(a);
+    return launch_status();
 }
 
 } // extern "C"

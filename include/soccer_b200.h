@@ -440,6 +440,22 @@ int soccer_policy_eval(const soccer_pitch *pitch, const int8_t *policy_a, const 
                        int32_t max_sweeps, double *V_out, int32_t *sweeps_out, void *workspace,
                        soccer_stream_t stream);
 
+/* ---- the one collective of the path over NVLink peer memory (multi-GPU, one process per GPU) ----
+ * Sum all-reduce of the 6-entry statistics vector written as a kernel: every rank stores its vector into every
+ * rank's SYMMETRIC buffer (peer stores through NVLink / NVSwitch), publishes an epoch flag with release semantics at
+ * system scope, waits for the other ranks' flags in its own buffer and sums.  One 32-thread launch on the caller's
+ * stream, directly behind the last step kernel: no host round trip, no helper stream (NCCL's 48-byte all-reduce
+ * measures 20-25 us + the hop onto its own stream; this one ~5 us).
+ *   peer_ptrs[world]: HOST array with the device address of every rank's buffer as mapped into THIS process (e.g.
+ *     torch.distributed._symmetric_memory rendezvous -> buffer_ptrs), each of soccer_stats_allreduce_p2p_bytes_host()
+ *     bytes, zero-filled once before the first call (with a barrier after the fill);
+ *   epoch: 1, 2, 3 ... incremented by every rank on every call (all ranks make the same sequence of calls);
+ *   stats[6]: in = this rank's vector, out = the sum over all ranks.  world <= 16.
+ * A peer that never arrives traps the waiting kernel after ~2 s instead of hanging the GPU. */
+int soccer_stats_allreduce_p2p_bytes_host(int64_t *bytes);
+int soccer_stats_allreduce_p2p(const uint64_t *peer_ptrs, int32_t rank, int32_t world, uint64_t epoch,
+                               unsigned long long *stats, soccer_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,6 +1,6 @@
 """Short driver for ncu captures: a few launches of each hot kernel at its bench size.
 
-    python profiles/run_kernels.py [k1_table|k1_rules|k2_table|k2_rules|k1_slip|k2_slip|k1_philox|k1_packed|replay|all] [--envs N]
+    python profiles/run_kernels.py [k1_table|k1_table_stats|k1_single_agent|k1_rules|k2_table|k2_rules|k1_slip|k2_slip|k1_philox|k1_packed|replay|all] [--envs N]
 """
 import argparse
 import os
@@ -12,14 +12,20 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from gym_soccer_littman94_b200.envs import SoccerVecEnv  # noqa: E402
 
 
-def k1(kernel, n, iters):
+def k1(kernel, n, iters, with_stats=False, policy=False):
+    """K1 on a played-in population (64 steps first); with_stats: the bench's headline variant (statistics fused);
+    policy: single-agent mode, player B folded."""
+    import numpy as np
     dev = torch.device("cuda", 0)
-    env = SoccerVecEnv(n, device=dev, kernel=kernel, want_reset_obs=False)
+    kw = dict(player_b_policy=np.random.RandomState(0).randint(0, 5, 761).astype(np.int8)) if policy else {}
+    env = SoccerVecEnv(n, device=dev, kernel=kernel, want_reset_obs=False, **kw)
     g = torch.Generator(device=dev).manual_seed(0)
-    a, b, r = (torch.randint(0, hi, (n,), dtype=torch.uint8, device=dev, generator=g) for hi in (5, 5, 16))
-    env.reset(r)
-    for _ in range(iters):
-        env.step(a, b, r)
+    ins = [tuple(torch.randint(0, hi, (n,), dtype=torch.uint8, device=dev, generator=g) for hi in (5, 5, 16)) for _ in range(4)]
+    env.reset(ins[0][2])
+    stats = torch.zeros(6, dtype=torch.int64, device=dev) if with_stats else None
+    for i in range(64 + iters):
+        a, b, r = ins[i % 4]
+        env.step(a, None if policy else b, r, stats=stats)
     torch.cuda.synchronize()
 
 
@@ -66,20 +72,25 @@ def k2(kernel, n, K, iters):
 
 
 def k1_slip(n, iters):
+    """K1 with slip_prob = 0.2 on a played-in population: injected rng32 draws and Philox draws (integer fast path),
+    injected fp64 draws (constant-prefix fast path + queue)."""
     dev = torch.device("cuda", 0)
-    env = SoccerVecEnv(n, slip_prob=0.2, device=dev, kernel="table", want_reset_obs=False)
     g = torch.Generator(device=dev).manual_seed(0)
     a, b, r = (torch.randint(0, hi, (n,), dtype=torch.uint8, device=dev, generator=g) for hi in (5, 5, 16))
     r32 = torch.randint(-2**31, 2**31 - 1, (n,), dtype=torch.int32, device=dev, generator=g)
-    env.reset(r)
-    for _ in range(iters):
-        env.step(a, b, r, rng32=r32)
-    e2 = SoccerVecEnv(1 << 20, slip_prob=0.2, device=dev, kernel="table", rng_mode="philox")
-    e2.reset()
-    bufs = (torch.empty((16, 1 << 20), dtype=torch.int32, device=dev), torch.empty((16, 1 << 20), dtype=torch.float32, device=dev),
-            torch.empty((16, 1 << 20), dtype=torch.uint8, device=dev))
-    for _ in range(iters):
-        e2.rollout(16, out=bufs)
+    r64 = torch.rand(n, dtype=torch.float64, device=dev, generator=g)
+    for mode in ("rng32", "philox", "rngf64"):
+        env = SoccerVecEnv(n, slip_prob=0.2, device=dev, kernel="table", want_reset_obs=False,
+                           rng_mode="philox" if mode == "philox" else "injected")
+        env.reset(None if mode == "philox" else r)
+        for _ in range(40 + iters):
+            if mode == "philox":
+                env.step(a, b)
+            elif mode == "rng32":
+                env.step(a, b, r, rng32=r32)
+            else:
+                env.step(a, b, r, rngf64=r64)
+        del env
     torch.cuda.synchronize()
 
 
@@ -115,6 +126,10 @@ if __name__ == "__main__":
     args = ap.parse_args()
     if args.what in ("k1_table", "all"):
         k1("table", args.envs, args.iters)
+    if args.what in ("k1_table_stats", "all"):
+        k1("table", args.envs, args.iters, with_stats=True)
+    if args.what in ("k1_single_agent", "all"):
+        k1("table", args.envs, args.iters, policy=True)
     if args.what in ("k1_rules", "all"):
         k1("rules", args.envs, args.iters)
     if args.what in ("k2_table", "all"):

@@ -471,3 +471,38 @@ def test_k2_cluster_table_equals_rules_kernel(dev, w, h, n, base):
     torch.cuda.synchronize()
     assert torch.equal(back, ref.state)
     assert L.soccer_cluster_table_bytes_host(C.byref(_lib.Pitch(9, 6, 0.0)), C.byref(nb), C.byref(cl)) == -5     # nS > 4096
+
+
+# ----------------------------------------------------------------------------- statistics all-reduce over peer memory
+def test_stats_allreduce_p2p_kernel_two_ranks_on_one_gpu(dev):
+    """soccer_stats_allreduce_p2p: two 'ranks' emulated on one GPU (two symmetric buffers, two streams; both kernels are
+    resident at once, each stores into both buffers and waits for the other's epoch flag): every call leaves the sum
+    in both vectors; epochs alternate the parity slots; world = 1 is the identity."""
+    import ctypes as C
+    from gym_soccer_littman94_b200 import _lib
+    L = _lib.lib()
+    nb = C.c_int64()
+    _lib.check(L.soccer_stats_allreduce_p2p_bytes_host(C.byref(nb)), "bytes")
+    bufs = [torch.zeros(nb.value // 8, dtype=torch.int64, device=dev) for _ in range(2)]
+    ptrs = (C.c_uint64 * 2)(bufs[0].data_ptr(), bufs[1].data_ptr())
+    streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+    torch.cuda.synchronize()
+    rs = np.random.RandomState(0)
+    for epoch in range(1, 8):
+        vals = [rs.randint(0, 1 << 40, 6).astype(np.int64) for _ in range(2)]
+        st = [torch.from_numpy(v.copy()).to(dev) for v in vals]
+        torch.cuda.synchronize()
+        for r in range(2):
+            with torch.cuda.stream(streams[r]):
+                _lib.check(L.soccer_stats_allreduce_p2p(ptrs, r, 2, epoch, C.c_void_p(st[r].data_ptr()),
+                                                        C.c_void_p(streams[r].cuda_stream)), "p2p")
+        torch.cuda.synchronize()
+        for r in range(2):
+            assert np.array_equal(st[r].cpu().numpy(), vals[0] + vals[1]), (epoch, r)
+    one = torch.arange(6, dtype=torch.int64, device=dev) + 5
+    p1 = (C.c_uint64 * 1)(bufs[0].data_ptr())
+    _lib.check(L.soccer_stats_allreduce_p2p(p1, 0, 1, 99, C.c_void_p(one.data_ptr()), None), "p2p world 1")
+    torch.cuda.synchronize()
+    assert one.cpu().tolist() == [5, 6, 7, 8, 9, 10]
+    assert L.soccer_stats_allreduce_p2p(p1, 1, 1, 1, C.c_void_p(one.data_ptr()), None) == -1          # rank out of range
+    assert L.soccer_stats_allreduce_p2p(p1, 0, 1, 0, C.c_void_p(one.data_ptr()), None) == -1          # epoch 0 is reserved
