@@ -912,7 +912,7 @@ def run_ours(args):
                          if world > 1 else "nothing (1 GPU)", "collective": collective},
         "e2e": e2e_line,
         "sustained": sustained,
-        "gpu_launches": K,
+        "gpu_launches": K + (1 if p2p is not None else 0),      # K step kernels (+ the peer-memory all-reduce kernel at N > 1)
         "clocks": clocks,
         "extra": extra,
         "stats_allreduce": stats_timed,

@@ -28,7 +28,7 @@ EXPORTS = (
     "soccer_bellman_q", "soccer_plan", "soccer_plan_workspace_bytes_host", "soccer_step_table_philox", "soccer_step_table_packed", "soccer_step_narrow", "soccer_host_alloc", "soccer_host_free", "soccer_slip_index_bytes_host", "soccer_build_slip_index",
     "soccer_step_table_packed_philox", "soccer_dense_q", "soccer_policy_eval", "soccer_policy_eval_workspace_bytes_host",
     "soccer_cluster_table_bytes_host", "soccer_build_cluster_table", "soccer_rollout_table_cluster",
-    "soccer_stats_allreduce_p2p_bytes_host", "soccer_stats_allreduce_p2p",
+    "soccer_stats_allreduce_p2p_bytes_host", "soccer_stats_allreduce_p2p", "soccer_slip_danger_host",
 )
 
 
@@ -144,6 +144,7 @@ def lib():
         "soccer_plan_workspace_bytes_host": [PP, C.POINTER(i64)],
         "soccer_plan": [PP, vp, vp, vp, C.c_double, C.c_double, i32, vp, vp, vp, vp, vp, vp],
         "soccer_step_stats": [vp, vp, i64, vp, vp],
+        "soccer_slip_danger_host": [PP, C.POINTER(C.c_uint32 * 12), C.POINTER(i32)],
         "soccer_stats_allreduce_p2p_bytes_host": [C.POINTER(i64)],
         "soccer_stats_allreduce_p2p": [C.POINTER(C.c_uint64), i32, i32, u64, vp, vp],
         "soccer_cluster_table_bytes_host": [PP, C.POINTER(i64), C.POINTER(i32)],

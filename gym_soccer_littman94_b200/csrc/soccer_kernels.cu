@@ -228,6 +228,62 @@ k_step_fast(const PitchDev P, uint32_t* __restrict__ state, const uint8_t* __res
     if (want_stats) k1_stats_flush(acc, &sblk, stats, (unsigned long long)n_groups * 4ull);
 }
 
+// K1 for slip_prob > 0 on ANY pitch (rules inline): 32-bit draws -- the injected rng32 stream or Philox -- decided by
+// integer thresholds and resolved byte-parallel (step4_slip_int); 24 B / env-step (19 with Philox draws).
+template <bool RESET_OBS, bool PHILOX>
+__global__ void __launch_bounds__(kThreads)
+k_step_fast_slip(const PitchDev P, const RulesSlipArgs sa, uint32_t* __restrict__ state, const uint8_t* __restrict__ act_a,
+                 const uint8_t* __restrict__ act_b, const uint8_t* __restrict__ rng, const uint32_t* __restrict__ draw,
+                 int32_t* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ flags,
+                 int32_t* __restrict__ reset_obs, int64_t n_groups, const PhiloxKey key)
+{
+    __shared__ __align__(16) uint8_t lut[kLutBytes];
+    __shared__ __align__(16) double prt[kPrtDoubles];
+    __shared__ __align__(16) uint8_t ilut[slip_int_lut_bytes(kRulesSlipLutBits)];
+    slip_build_prt(prt, P);
+    slip_int_build_luts(ilut, sa.E, P, kRulesSlipLutBits, 1u, 1u);
+    build_cand_lut(lut, P);                      // ends with __syncthreads()
+    const Isd4 I = make_isd4(P);
+    const SlipCtx sc = { (uint32_t)__cvta_generic_to_shared(prt), slip_first_k(P) };
+    const SlipInt fi = slip_int_ctx(ilut, kRulesSlipLutBits);
+    uint4* st4 = reinterpret_cast<uint4*>(state);
+    const uint32_t* a4 = reinterpret_cast<const uint32_t*>(act_a);
+    const uint32_t* b4 = reinterpret_cast<const uint32_t*>(act_b);
+    const uint32_t* r4 = reinterpret_cast<const uint32_t*>(rng);
+    const uint4* d4 = reinterpret_cast<const uint4*>(draw);
+    uint4* o4 = reinterpret_cast<uint4*>(obs);
+    uint4* w4 = reinterpret_cast<uint4*>(reward);
+    uint32_t* f4 = reinterpret_cast<uint32_t*>(flags);
+    uint4* q4 = reinterpret_cast<uint4*>(reset_obs);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool one = g < n_groups;
+    GroupS x = {};
+    if (one) x = load_group_slip<PHILOX>(st4, a4, b4, r4, d4, g);
+    while (one) {
+        const int64_t gn = g + stride;
+        const bool n_one = gn < n_groups;
+        GroupS y = x;
+        if (n_one) y = load_group_slip<PHILOX>(st4, a4, b4, r4, d4, gn);       // register prefetch of the next group
+        if (PHILOX) {
+            uint32_t w[4];
+            philox_words4(key, g, w);
+            x.d = make_uint4(philox_r32(w[0]), philox_r32(w[1]), philox_r32(w[2]), philox_r32(w[3]));
+            x.r = (w[0] & 0xCu) | ((w[1] & 0xCu) << 8) | ((w[2] & 0xCu) << 16) | ((w[3] & 0xCu) << 24);
+        }
+        const uint32_t sv[4] = { x.s.x, x.s.y, x.s.z, x.s.w };
+        const uint32_t r32[4] = { x.d.x, x.d.y, x.d.z, x.d.w };
+        Step4 o;
+        step4_slip_int<RESET_OBS>(P, I, lut, fi, sa.dg, sc, sv, x.a, x.b, r32, x.r, o);
+        st_keep(st4 + g, make_uint4(o.s[0], o.s[1], o.s[2], o.s[3]));
+        st_stream(o4 + g, make_uint4(o.obs[0], o.obs[1], o.obs[2], o.obs[3]));
+        st_stream(w4 + g, make_uint4(o.rew[0], o.rew[1], o.rew[2], o.rew[3]));
+        st_stream(f4 + g, o.flags4);
+        if (RESET_OBS) st_stream(q4 + g, make_uint4(o.robs[0], o.robs[1], o.robs[2], o.robs[3]));
+        x = y; g = gn; one = n_one;
+    }
+}
+
 // ------------------------------------------------------------------ K1 generic path
 // Every option of soccer_step_args, one env per thread (scalar but warp-coalesced accesses).
 struct StepOpts {
@@ -596,6 +652,49 @@ k_stats_allreduce_p2p(const P2PStatsArgs a)
     }
 }
 
+// E_k (sequential fp64 sums of the combination probabilities, SIM:241 with nsp = 1) and the draws the integer fast path
+// must hand to the reference's walk (see soccer_table.cuh "32-bit draws"): every threshold value x = sum * 2^32 - 0.5 --
+// end of a combination, slot inside a 2-way / 4-way combination -- that lies within kDangerWidth of an integer m makes
+// the draw r == m uncertain; a slot threshold of 0 (sum below 2^-33: leading combinations of almost zero probability)
+// cannot be written as a strict compare and makes r < 4 uncertain.  false: more than 12 such draws (no fast path).
+// SOCCER_B200_SLIP_WALK=1 (tests, A/B): every slip env takes the reference's walk
+bool soccer_force_slip_walk()
+{
+    const char* v = getenv("SOCCER_B200_SLIP_WALK");
+    return v && v[0] == '1';
+}
+constexpr double kDangerWidth = 1e-4;       // > 4 x the bound 48 * 2^-53 * 2^32 = 2.3e-5 on |true - constant| thresholds
+bool slip_consts_host(const PitchDev& P, SlipE* E, SlipDanger* dg)
+{
+    double acc = 0.0;
+    for (int c = 0; c < 9; ++c) { acc += P.mp[c]; E->e[c] = acc; }
+    dg->n = 0;
+    bool ok = true, low = false;
+    auto add = [&](uint32_t r) {
+        for (uint32_t i = 0; i < dg->n; ++i) if (dg->r[i] == r) return;
+        if (dg->n < 12) dg->r[dg->n++] = r; else ok = false;
+    };
+    auto check = [&](double sum) {
+        const double x = sum * 4294967296.0 - 0.5, m = nearbyint(x);
+        if (fabs(x - m) < kDangerWidth && m >= 0.0 && m <= 4294967295.0) add((uint32_t)m);
+    };
+    for (int k = 0; k < 9; ++k) {
+        check(E->e[k]);
+        if (P.mp[k] == 0.0) continue;
+        for (int nl = 1; nl <= 2; ++nl) {
+            const double pr = P.mp[k] * (nl == 2 ? 0.25 : 0.5);
+            double cc = k == 0 ? 0.0 : E->e[k - 1];
+            for (int j = 0; j + 1 < (1 << nl); ++j) {
+                cc += pr;
+                check(cc);
+                if (slip_thr(cc) == 0ull) low = true;
+            }
+        }
+    }
+    if (low) for (uint32_t r = 0; r < 4; ++r) add(r);
+    return ok;
+}
+
 constexpr int32_t kMaxRolloutK = 1 << 28;     // per-pass statistics are 32-bit: 4 envs x K flag counts
 int64_t round_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 // scratch layout of soccer_step_host: three input byte streams, flags, obs, reward, obs16, rew8
@@ -835,6 +934,33 @@ int soccer_step_ex(const soccer_pitch* pitch, const soccer_step_args* a, soccer_
                          !(a->use_philox && (a->env_id_base & 3u)) &&      // Philox contract v2: a thread's 4 envs = one aligned group
                          !(narrow && (a->use_philox || a->reset_obs));     // narrow fast path: the plain step only
     int64_t done_n = 0;
+    // slip_prob > 0 with 32-bit draws (rng32 stream or Philox), the plain options: integer-threshold kernel
+    RulesSlipArgs rsa = {};
+    const bool slip_fast_ok = P.slip && a->auto_reset && !a->detail && !a->policy_a && !a->policy_b && !narrow && !a->stats &&
+                              a->obs && a->reward && a->flags && a->n >= 4 && !a->rngf64 && (a->use_philox || a->rng32) &&
+                              aligned(a->state, 16) && aligned(a->obs, 16) && aligned(a->reward, 16) &&
+                              (!a->reset_obs || aligned(a->reset_obs, 16)) && aligned(a->act_a, 4) && aligned(a->act_b, 4) &&
+                              aligned(a->flags, 4) &&
+                              (a->use_philox ? (a->env_id_base & 3u) == 0 : (aligned(a->rng8, 4) && aligned(a->rng32, 16))) &&
+                              slip_consts_host(P, &rsa.E, &rsa.dg) && !soccer_force_slip_walk();
+    if (slip_fast_ok) {
+        rsa.use_int = 1;
+        const int64_t n_groups = a->n / 4;
+        const PhiloxKey key = { a->seed, a->step, a->env_id_base };
+#define SOCCER_LAUNCH_FAST_SLIP(RO, PH)                                                                           \
+        do {                                                                                                      \
+            static const int nb = resident_blocks(k_step_fast_slip<RO, PH>);                                      \
+            k_step_fast_slip<RO, PH><<<grid_for(n_groups, nb), kThreads, 0, st>>>(P, rsa, a->state, a->act_a, a->act_b, \
+                a->rng8, a->rng32, a->obs, a->reward, a->flags, RO ? a->reset_obs : (int32_t*)nullptr, n_groups, key); \
+        } while (0)
+        if (a->use_philox) { if (a->reset_obs) SOCCER_LAUNCH_FAST_SLIP(true, true); else SOCCER_LAUNCH_FAST_SLIP(false, true); }
+        else { if (a->reset_obs) SOCCER_LAUNCH_FAST_SLIP(true, false); else SOCCER_LAUNCH_FAST_SLIP(false, false); }
+#undef SOCCER_LAUNCH_FAST_SLIP
+        const int e = launch_status();
+        if (e) return e;
+        done_n = n_groups * 4;
+        if (done_n == a->n) return SOCCER_OK;
+    }
     if (fast_ok) {
         // byte-parallel rules kernel; with on-device Philox draws (soccer_step_philox) 19 B / env-step
         const int64_t n_groups = a->n / 4;
@@ -926,10 +1052,22 @@ int soccer_rollout(const soccer_pitch* pitch, uint32_t* state, const int8_t* pol
         else if (streams) SOCCER_LAUNCH_ROLLOUT(1, true, SLIP, n);                                       \
         else SOCCER_LAUNCH_ROLLOUT(1, false, SLIP, n);                                                   \
     } while (0)
+    RulesSlipArgs rsa = {};
     if (P.slip) {
-        // the slip walk needs ~170 registers with 4 envs per thread (one 8-warp CTA per SM); one env per thread
-        // keeps 16 warps resident and measures 2.2x faster (44 vs 20 G env-steps/s, profiles/time_k2_rules_vec.py)
-        if (streams) SOCCER_LAUNCH_ROLLOUT(1, true, true, n);
+        rsa.use_int = slip_consts_host(P, &rsa.E, &rsa.dg) && !soccer_force_slip_walk() ? 1 : 0;
+        // uniform policy, 4 envs per thread: combination and slot of the 32-bit draw by integer thresholds, resolution
+        // byte-parallel (step4_slip_int).  With table policies (or when the fast path is off) the scalar walk, one env per
+        // thread: it needs ~170 registers with 4 envs per thread and measured 2.2x faster that way (44 vs 20 G env-steps/s)
+        if (rsa.use_int && vec && !policy_a && !policy_b) {
+            if (streams) {
+                static const int nb = resident_blocks(k_rollout_slipi<true>);
+                k_rollout_slipi<true><<<grid_for(n / 4, nb), kThreads, 0, st>>>(P, ra, rsa);
+            } else {
+                static const int nb = resident_blocks(k_rollout_slipi<false>);
+                k_rollout_slipi<false><<<grid_for(n / 4, nb), kThreads, 0, st>>>(P, ra, rsa);
+            }
+        }
+        else if (streams) SOCCER_LAUNCH_ROLLOUT(1, true, true, n);
         else SOCCER_LAUNCH_ROLLOUT(1, false, true, n);
     } else {
         SOCCER_PICK_ROLLOUT(false);
@@ -988,25 +1126,28 @@ int step_table_slip_impl(const PitchDev& P, int64_t bytes, const soccer_step_arg
     int64_t done_n = 0;
     if (vec) {
         const int64_t n_groups = n / 4;
-        // With a slip index and room for it next to the table (5x4): 32-bit draws (rng32 / Philox) take the integer-
-        // threshold fast path (k_step_table_slip_i, index plane 1), fp64 draws the constant-prefix fast path + queued
-        // walk (k_step_table_slip_q, plane 0); else the in-place walk.
+        // 32-bit draws (rng32 / Philox) take the integer-threshold fast path (k_step_table_slip_i; needs no index: 5x4 with
+        // a 12-bit, 6x4 with a 10-bit bucket table); fp64 draws, with a slip index and room for it and the deferral queue
+        // next to the table (5x4), the constant-prefix fast path + queued walk (k_step_table_slip_q, index plane 0); else
+        // the in-place walk.
         const int64_t fc_bytes = ((int64_t)P.nS * 25 + 15) / 16 * 16;
         const int64_t smem_q = bytes + 16 + fc_bytes + pol_bytes + (int64_t)kSlipQueueBytes;
-        const int64_t smem_i = bytes + 16 + 2 * fc_bytes + pol_bytes + (int64_t)kSlipIntLutBytes;
         const int64_t smem_w = bytes + 16 + pol_bytes;
         if (smem_w > 227 * 1024 - 2048) return SOCCER_ETABLE;
-        SlipE E;                                      // E_k: sequential fp64 sums of the combination probabilities (SIM:241, nsp = 1)
-        { double acc = 0.0; for (int c = 0; c < 9; ++c) { acc += P.mp[c]; E.e[c] = acc; } }
+        SlipE E; SlipDanger dg;
+        const bool dg_ok = slip_consts_host(P, &E, &dg);
         const bool f64 = !philox && a->rngf64;
+        int lut_bits = 12;
+        if (smem_w + slip_int_lut_bytes(lut_bits) > 227 * 1024 - 1536) lut_bits = 10;
+        const int64_t smem_i = smem_w + slip_int_lut_bytes(lut_bits);
         const bool queued = a->slip_index && f64 && smem_q <= 227 * 1024 - 1024;
-        const bool integer = a->slip_index && !f64 && smem_i <= 227 * 1024 - 1024;
+        const bool integer = !f64 && dg_ok && smem_i <= 227 * 1024 - 1536 && !soccer_force_slip_walk();
 #define SOCCER_LAUNCH_SLIP_I(RO, PH)                                                                      \
         do {                                                                                              \
             const int e0 = allow_big_smem(k_step_table_slip_i<RO, PH>, smem_i);                           \
             if (e0) return e0;                                                                            \
             k_step_table_slip_i<RO, PH><<<table_grid(n_groups, slip_i_threads<PH>()), slip_i_threads<PH>(), (size_t)smem_i, st>>>(  \
-                P, a->table, (uint32_t)bytes, a->slip_index + fc_bytes, (uint32_t)(2 * fc_bytes), E, a->state, act_a, act_b, \
+                P, a->table, (uint32_t)bytes, E, dg, lut_bits, a->state, act_a, act_b,                     \
                 a->rng8, a->rng32, a->obs, a->reward, a->flags, a->reset_obs, n_groups, ex);              \
         } while (0)
 #define SOCCER_LAUNCH_SLIP_T(RO, DRAW)                                                                    \
@@ -1292,20 +1433,22 @@ int soccer_rollout_table_policy(const soccer_pitch* pitch, const uint16_t* table
         else SOCCER_LAUNCH_ROLLOUT_T(1, false, POL, SLIP, n);                                            \
     } while (0)
     if (P.slip) {
-        // with the slip index and room for it next to the table (5x4): integer-threshold fast path, 4 envs per thread
-        // (k_rollout_table_slipi); else the in-place walk, one env per thread (the walk's registers)
-        const int64_t fc_bytes = ((int64_t)P.nS * 25 + 15) / 16 * 16;
-        const int64_t smem_i = bytes + 16 + 2 * fc_bytes + (pol ? pol_bytes : 0) + (int64_t)kSlipIntLutBytes;
-        if (slip_index && smem_i <= 227 * 1024 - 2048) {
-            SlipE E;
-            { double acc = 0.0; for (int c = 0; c < 9; ++c) { acc += P.mp[c]; E.e[c] = acc; } }
+        // integer-threshold fast path, 4 envs per thread (k_rollout_table_slipi; 5x4 with a 12-bit, 6x4 with a 10-bit
+        // bucket table); else the in-place walk, one env per thread (the walk's registers)
+        SlipE E; SlipDanger dg;
+        const bool dg_ok = slip_consts_host(P, &E, &dg);
+        const int64_t smem_b = bytes + 16 + (pol ? pol_bytes : 0);
+        int lut_bits = 12;
+        if (smem_b + slip_int_lut_bytes(lut_bits) > 227 * 1024 - 2048) lut_bits = 10;
+        const int64_t smem_i = smem_b + slip_int_lut_bytes(lut_bits);
+        if (dg_ok && smem_i <= 227 * 1024 - 2048 && !soccer_force_slip_walk()) {
 #define SOCCER_LAUNCH_ROLLOUT_I(VEC, STR, POL, ITEMS)                                                    \
             do {                                                                                         \
                 const int e0 = allow_big_smem(k_rollout_table_slipi<VEC, STR, POL>, smem_i);             \
                 if (e0) return e0;                                                                       \
                 const int e1 = launch_pdl(k_rollout_table_slipi<VEC, STR, POL>, table_grid(ITEMS, kRolloutThreads), \
                                           kRolloutThreads, (size_t)smem_i, st, P, table, (uint32_t)bytes, \
-                                          slip_index + fc_bytes, (uint32_t)(2 * fc_bytes), E, policy_a, policy_b, ra); \
+                                          E, dg, lut_bits, policy_a, policy_b, ra);                      \
                 if (e1) return e1;                                                                       \
             } while (0)
 #define SOCCER_PICK_ROLLOUT_I(POL)                                                                       \
@@ -1754,6 +1897,17 @@ int soccer_stats_allreduce_p2p(const uint64_t* peer_ptrs, int32_t rank, int32_t 
     a.rank = rank; a.world = world; a.epoch = epoch; a.stats = stats;
     k_stats_allreduce_p2p<<<1, 32, 0, (cudaStream_t)stream>>>(a);
     return launch_status();
+}
+
+int soccer_slip_danger_host(const soccer_pitch* pitch, uint32_t draws[12], int32_t* n)
+{
+    if (!draws || !n) return SOCCER_EINVAL;
+    PitchDev P; const int rc = make_pitch_dev(pitch, &P); if (rc) return rc;
+    SlipE E; SlipDanger dg;
+    const bool ok = slip_consts_host(P, &E, &dg);
+    for (uint32_t i = 0; i < dg.n && i < 12; ++i) draws[i] = dg.r[i];
+    *n = ok ? (int32_t)dg.n : -1;
+    return SOCCER_OK;
 }
 
 } // extern "C"

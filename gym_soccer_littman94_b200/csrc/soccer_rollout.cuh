@@ -22,6 +22,58 @@
 
 namespace soccer {
 
+// ---- slip_prob > 0 for the RULES kernels (any pitch), byte-parallel: the integer-threshold decision of
+// soccer_table.cuh is state-independent, so the four envs of a thread pick their slip combination and their slot inside
+// a 2-way / 4-way collision from the constant tables, and step4_noslip resolves the slipped moves exactly as it resolves
+// chosen ones (a slipped move is NOOP iff the action is, so the NOOP-keyed cases of SIM:330-344 agree).  The (in
+// practice never taken) walk of a listed draw re-does that env with the scalar step_slip().
+// aa / ab: action bytes (values < 5 or clamped here); r32: the 32-bit draws; RST: rng8-style bytes with the reset draw
+// in bits 2..3.
+__device__ __noinline__ StepOut step_slip_call(const PitchDev& P, const uint8_t* lut, uint32_t prt, uint32_t first_k, uint32_t s,
+                                               uint32_t aa, uint32_t ab, uint32_t r32, uint32_t reset_sel)
+{
+    const SlipCtx sc = { prt, first_k };
+    return step_slip<true>(P, lut, sc, s, aa, ab, u_from_rng32(r32), reset_sel, false);
+}
+template <bool RESET_OBS>
+__device__ __forceinline__ void step4_slip_int(const PitchDev& P, const Isd4& I, const uint8_t* __restrict__ lut,
+                                               const SlipInt& f, const SlipDanger& dg, const SlipCtx& sc, const uint32_t sv[4],
+                                               uint32_t A4, uint32_t B4, const uint32_t r32[4], uint32_t RST, Step4& o)
+{
+    uint32_t ma[4], mb[4], r4[4], r2[4], walk = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const uint32_t aa = min(byte_of(A4, e), 4u), ab = min(byte_of(B4, e), 4u);
+        const uint32_t k = slip_int_k(f, dg, r32[e]);
+        walk |= (k >= 9u ? 1u : 0u) << e;
+        const uint32_t kc = min(k, 8u);
+        ma[e] = lds_u8_r(f.mva + kc * 8u + aa);
+        mb[e] = lds_u8_r(f.mvb + kc * 8u + ab);
+        const uint32_t t2 = lds_u32_r(f.sl + kc * 32u);                      // 2-way row: one threshold
+        const uint4 t4 = lds_v4_r(f.sl + kc * 32u + 16u);                    // 4-way row: three
+        r2[e] = r32[e] > t2 ? 2u : 0u;                                       // draw value 2 * slot
+        r4[e] = (r32[e] > t4.x ? 1u : 0u) + (r32[e] > t4.y ? 1u : 0u) + (r32[e] > t4.z ? 1u : 0u);
+    }
+    const uint32_t R4 = pack4(r4[0], r4[1], r4[2], r4[3]) | (RST & 0x0C0C0C0Cu);
+    step4_noslip<RESET_OBS>(P, I, lut, sv, pack4(ma[0], ma[1], ma[2], ma[3]), pack4(mb[0], mb[1], mb[2], mb[3]), R4, o,
+                            pack4(r2[0], r2[1], r2[2], r2[3]));
+    if (walk) {                                                              // (in practice never)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if ((walk >> e) & 1u) {
+                const StepOut w = step_slip_call(P, lut, sc.prt, sc.first_k, sv[e], min(byte_of(A4, e), 4u), min(byte_of(B4, e), 4u),
+                                                 r32[e], (byte_of(RST, e) >> 2) & 3u);
+                const int32_t ri = (w.reward > 0.0f) - (w.reward < 0.0f);
+                o.rew_sum += ri - (int32_t)(signed char)(o.rew4 >> (8 * e));
+                o.s[e] = w.state; o.obs[e] = (uint32_t)w.obs; o.rew[e] = __float_as_uint(w.reward);
+                o.rew4 = (o.rew4 & ~(0xFFu << (8 * e))) | (((uint32_t)ri & 0xFFu) << (8 * e));
+                o.flags4 = (o.flags4 & ~(0xFFu << (8 * e))) | ((w.flags & 3u) << (8 * e));
+                if (RESET_OBS) o.robs[e] = (uint32_t)w.reset_obs;
+            }
+        }
+    }
+}
+
 #ifndef SOCCER_K2_PHILOX_WIDE
 #define SOCCER_K2_PHILOX_WIDE 1
 #endif
@@ -85,7 +137,7 @@ struct TableStepper {
 template <bool POLICY>
 struct TableSlipIntStepper {
     static constexpr bool kCollective = false, kHasPolicy = POLICY;
-    TblCtx c; SlipCtx sc; SlipInt sf;
+    TblCtx c; SlipCtx sc; SlipInt sf; SlipDanger dg;
     uint32_t pol_a, pol_b;
     __device__ __forceinline__ uint32_t timestep(uint32_t s) const { return s >> 16; }
     template <int VEC>
@@ -104,7 +156,7 @@ struct TableSlipIntStepper {
             }
             const uint32_t r32 = philox_r32(word[e]), rsel4 = word[e] & 0xCu;
             bool walk;
-            TblOut o = table_step_slip_int<false>(c, sf, s[e], aa, ab, r32, rsel4, walk);
+            TblOut o = table_step_slip_int<false>(c, sf, dg, s[e], aa, ab, r32, rsel4, walk);
             if (walk) o = table_step_slip_walk(c, sc, s[e], aa, ab, r32, rsel4);
             s[e] = o.state; oo[e] = o.obs; rr[e] = __float_as_uint((float)(flip ? -o.rew_i : o.rew_i)); ff[e] = o.flags;
             net += o.rew_i;
@@ -175,6 +227,34 @@ struct RulesStepper {
                 net += ri;
             }
         }
+    }
+};
+
+// slip_prob > 0, uniform policy, any pitch: four envs per thread, combination and slot by integer thresholds, resolution
+// byte-parallel (step4_slip_int)
+struct RulesSlipIntStepper {
+    static constexpr bool kCollective = false, kHasPolicy = false;
+    const PitchDev& P; const uint8_t* lut; Isd4 I; SlipCtx sc; SlipInt fi; SlipDanger dg;
+    __device__ __forceinline__ uint32_t timestep(uint32_t s) const { return (s >> 16) & 0xFFu; }
+    template <int VEC>
+    __device__ __forceinline__ void step(uint32_t* s, const uint32_t* word, uint32_t* oo, uint32_t* rr,
+                                         uint32_t& fw, int32_t& net, bool) const
+    {
+        static_assert(VEC == 4, "four envs per thread");
+        uint32_t aa[4], ab[4], r32[4], rst = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            philox_actions(word[e], aa[e], ab[e]);
+            r32[e] = philox_r32(word[e]);
+            rst |= (word[e] & 0xCu) << (8 * e);
+        }
+        Step4 o;
+        step4_slip_int<false>(P, I, lut, fi, dg, sc, s, pack4(aa[0], aa[1], aa[2], aa[3]), pack4(ab[0], ab[1], ab[2], ab[3]),
+                              r32, rst, o);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { s[e] = o.s[e]; oo[e] = o.obs[e]; rr[e] = o.rew[e]; }
+        fw = o.flags4;
+        net += o.rew_sum;
     }
 };
 
@@ -362,12 +442,11 @@ k_rollout_table(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t 
     rollout_body<VEC, STREAMS>(S, a, &blk);
 }
 
-// slip_prob > 0 with the slip index.  Shared-memory image: [table][isd 16 B][slip index plane 1][policy a][policy b]
-// [look-up tables of the integer fast path].
+// slip_prob > 0.  Shared-memory image: [table][isd 16 B][policy a][policy b][look-up tables of the integer fast path].
 template <int VEC, bool STREAMS, bool POLICY>
 __global__ void __launch_bounds__(kRolloutThreads, 1)
 k_rollout_table_slipi(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t table_bytes,
-                      const uint8_t* __restrict__ gfc, uint32_t fc_bytes, const SlipE E,
+                      const SlipE E, const SlipDanger dg, int lut_bits,
                       const int8_t* __restrict__ policy_a, const int8_t* __restrict__ policy_b, const RolloutArgs a)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -377,19 +456,20 @@ k_rollout_table_slipi(const PitchDev P, const uint16_t* __restrict__ gtable, uin
     pdl_launch_dependents();
     if (threadIdx.x < 5) blk.v[threadIdx.x] = 0;
     const uint32_t pol_bytes = POLICY ? (((uint32_t)P.nS + 15u) & ~15u) : 0u;
-    uint8_t* pa = smem_raw + table_bytes + 16 + fc_bytes, *pb = pa + pol_bytes;
+    uint8_t* pa = smem_raw + table_bytes + 16, *pb = pa + pol_bytes;
     uint8_t* luts = pb + pol_bytes;
     slip_build_prt(prt, P);
-    slip_int_build_luts(luts, E, P);
-    stage_table_and_index(smem_raw, gtable, table_bytes, gfc, fc_bytes, &bar, P);     // ends with __syncthreads()
+    slip_int_build_luts(luts, E, P, lut_bits);
+    stage_table(smem_raw, gtable, table_bytes, &bar, P);                               // ends with __syncthreads()
     TableSlipIntStepper<POLICY> S;
     S.c = make_ctx(smem_raw, table_bytes, P);
     S.sc.prt = smem_u32(prt); S.sc.first_k = slip_first_k(P);
-    S.sf = slip_int_ctx(luts, S.c.isd + 16u);
+    S.sf = slip_int_ctx(luts, lut_bits);
+    S.dg = dg;
     S.pol_a = S.pol_b = 0;
     wait_table(&bar);
     launder(S.c.tbl); launder(S.c.isd); launder(S.sc.prt);
-    launder(S.sf.fc); launder(S.sf.klo); launder(S.sf.kthr); launder(S.sf.mva); launder(S.sf.mvb); launder(S.sf.sl);
+    launder(S.sf.klo); launder(S.sf.kthr); launder(S.sf.mva); launder(S.sf.mvb); launder(S.sf.sl);
     pdl_wait();
     if (POLICY) {
         stage_policies(pa, pb, policy_a, policy_b, P.nS);
@@ -485,6 +565,28 @@ k_rollout(const PitchDev P, const int8_t* __restrict__ policy_a, const int8_t* _
     const SlipCtx sc = { (uint32_t)__cvta_generic_to_shared(prt), SLIP ? slip_first_k(P) : 0u };
     const RulesStepper<SLIP> S = { P, lut, make_isd4(P), policy_a, policy_b, sc };
     rollout_body<VEC, STREAMS>(S, a, &blk);
+}
+
+// slip_prob > 0, uniform policy, 4 envs per thread (RulesSlipIntStepper).  The 10-bit bucket table + slot thresholds take
+// 5.6 KB of shared memory next to the 4 KB candidate table.
+constexpr int kRulesSlipLutBits = 10;
+struct RulesSlipArgs { SlipE E; SlipDanger dg; int32_t use_int; };
+template <bool STREAMS>
+__global__ void __launch_bounds__(kThreads, 2)
+k_rollout_slipi(const PitchDev P, const RolloutArgs a, const RulesSlipArgs sa)
+{
+    __shared__ __align__(16) uint8_t lut[kLutBytes];
+    __shared__ __align__(16) double prt[kPrtDoubles];
+    __shared__ __align__(16) uint8_t ilut[slip_int_lut_bytes(kRulesSlipLutBits)];
+    __shared__ BlkStats blk;
+    slip_build_prt(prt, P);
+    slip_int_build_luts(ilut, sa.E, P, kRulesSlipLutBits, 1u, 1u);
+    build_cand_lut(lut, P);
+    if (threadIdx.x < 5) blk.v[threadIdx.x] = 0;
+    __syncthreads();
+    const SlipCtx sc = { (uint32_t)__cvta_generic_to_shared(prt), slip_first_k(P) };
+    const RulesSlipIntStepper S = { P, lut, make_isd4(P), sc, slip_int_ctx(ilut, kRulesSlipLutBits), sa.dg };
+    rollout_body<4, STREAMS>(S, a, &blk);
 }
 
 // Measurement probe, not part of the game: K2's memory traffic (state read and written once, K x

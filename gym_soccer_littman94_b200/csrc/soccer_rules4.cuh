@@ -61,10 +61,14 @@ struct Step4 {
     int32_t  rew_sum;   // sum of the four rewards (+1 / -1 / 0), for K2's statistics
 };
 
-// sv: the four state words; MA4 / MB4: action bytes; R4: rng8 bytes (bits 0..1 step draw, 2..3 reset draw)
+// sv: the four state words; MA4 / MB4: action bytes; R4: rng8 bytes (bits 0..1 step draw, 2..3 reset draw).
+// R2: the draw of a 2-outcome collision in bit 1 of each byte; the same as R4 when one 2-bit draw serves both kinds
+// (slip_prob == 0: outcome r of 4, r >> 1 of 2), a separate word for the slip steppers, whose slot inside a 2-way and
+// inside a 4-way combination comes from different thresholds.
 template <bool RESET_OBS>
 __device__ __forceinline__ void step4_noslip(const PitchDev& P, const Isd4& I, const uint8_t* __restrict__ lut,
-                                             const uint32_t sv[4], uint32_t MA4, uint32_t MB4, uint32_t R4, Step4& o)
+                                             const uint32_t sv[4], uint32_t MA4, uint32_t MB4, uint32_t R4, Step4& o,
+                                             uint32_t R2)
 {
     // ---- 4x4 byte transpose: words (a,b,t,p) per env -> A4, B4, T4, P4
     const uint32_t u0 = __byte_perm(sv[0], sv[1], 0x5140), u1 = __byte_perm(sv[2], sv[3], 0x5140);
@@ -95,7 +99,7 @@ __device__ __forceinline__ void step4_noslip(const PitchDev& P, const Isd4& I, c
     const uint32_t move_b = ~stay & (~four | ~rhi) & kH;
     const uint32_t FA = sel4(mask4(move_a), NA, A4), FB = sel4(mask4(move_b), NB, B4);
     const uint32_t pf = P4 << 7;
-    const uint32_t rsel = (four & rlo) | (~four & rhi);
+    const uint32_t rsel = (four & rlo) | (~four & ((R2 << 6) & kH));
     const uint32_t pc = (c2 & ~pf) | (~c2 & rsel);
     const uint32_t sf = stay | four;
     const uint32_t fpf = ((sf & pc) | (~sf & pf)) & kH;             // final possession flag
@@ -150,6 +154,13 @@ __device__ __forceinline__ void step4_noslip(const PitchDev& P, const Isd4& I, c
         const uint32_t z02 = sel4(r02, n02, ob02), z13 = sel4(r13, n13, ob13);
         o.robs[0] = z02 & 0xFFFFu; o.robs[2] = z02 >> 16; o.robs[1] = z13 & 0xFFFFu; o.robs[3] = z13 >> 16;
     }
+}
+
+template <bool RESET_OBS>
+__device__ __forceinline__ void step4_noslip(const PitchDev& P, const Isd4& I, const uint8_t* __restrict__ lut,
+                                             const uint32_t sv[4], uint32_t MA4, uint32_t MB4, uint32_t R4, Step4& o)
+{
+    step4_noslip<RESET_OBS>(P, I, lut, sv, MA4, MB4, R4, o, R4);
 }
 
 } // namespace soccer

@@ -733,8 +733,10 @@ __host__ __device__ inline uint64_t slip_thr(double E)
 //     constant one moves that integer only if an integer lies between them (probability ~2^-21 per threshold).  So the
 //     fast path decides combination AND slot from constant integer thresholds, and bit k (k = 0 .. 8) marks the picks
 //     for which some threshold of combination k or k - 1 -- its end or a slot inside it -- is NOT the constant one, or
-//     cannot be written as a strict 32-bit compare (0 or 2^32): those (in practice none) take the reference's walk.
-//     Bit 9 is always set: pick 9 = "no running sum exceeds u" (and the fast path's code for "undecided").
+//     is 0 and cannot be written as a strict 32-bit compare.  Bit 9 is always set: pick 9 = "no running sum exceeds u".
+//     The kernels do NOT read this plane any more: the integer fast path proves the same thing state-independently
+//     (SlipDanger, below); the plane is the constructive cross-check of that argument -- whenever the danger list of a
+//     slip_prob is empty, bits 0 .. 8 must be clear for every (obs, joint action) (tests/test_gpu_round2.py).
 __global__ void __launch_bounds__(kThreads)
 k_build_slip_index(const PitchDev P, int32_t nS, const uint16_t* __restrict__ table, uint8_t* __restrict__ fc, int64_t plane_bytes)
 {
@@ -763,8 +765,9 @@ k_build_slip_index(const PitchDev P, int32_t nS, const uint16_t* __restrict__ ta
                 const bool last = j + 1u == (1u << nl);
                 const uint64_t t_fast = slip_thr(last ? ec : cc);
                 ibad |= slip_thr(et) != t_fast;
-                // inner thresholds are used as strict 32-bit compares r > t - 1: t must lie in [1, 2^32 - 1]
-                if (!last) ibad |= t_fast == 0ull || t_fast > 0xFFFFFFFFull;
+                // inner thresholds are used as strict 32-bit compares r > t - 1 (2^32 -> 0xFFFFFFFF = never: correct);
+                // t == 0 ("always") cannot be written that way
+                if (!last && mp != 0.0) ibad |= t_fast == 0ull;
             }
             off |= __double_as_longlong(et) != __double_as_longlong(ec);
             if (k < 8 && ((nl != 0u && mp != 0.0) || off)) mask |= 1u << k;
@@ -860,28 +863,42 @@ __device__ __forceinline__ void stage_table_and_index(uint8_t* smem, const uint1
     __syncthreads();
 }
 
-// ---- 32-bit draws: combination and slot from constant INTEGER thresholds (plane 1 of the slip index), no queue.
-// Shared look-up tables, built by every CTA from E_k and the combination probabilities:
-//   klo[b]  (4096 bytes)   #{j : E_j <= u(low end of bucket b)}, b = top 12 bits of the draw; 9 = undecided (two or
-//                          more steps of k(r) inside the bucket: tiny slip_prob) -> walk
-//   kthr[b] (4096 uint32)  t - 1 for the ONE step of k(r) inside bucket b (k = klo + (r > kthr)); 0xFFFFFFFF if none
-//   mva[k][a], mvb[k][a]   (10 x 8 bytes each) byte offsets inside the table row of the move player A / B makes in
-//                          combination k with action a: (slipped move) * 40, * 8
+// ---- 32-bit draws: combination and slot from constant INTEGER thresholds, no queue, no per-state index.
+// With u = (r + 0.5) / 2^32 every comparison "running sum <= u" of the reference's walk is "r >= slip_thr(running sum)".
+// The TRUE running sum (which depends on the outcome counts of the earlier combinations) and the CONSTANT one the fast
+// path uses (E_{k-1} + j * pr) are fp64 sums of the same <= 36 non-negative terms <= 1 in different groupings (the
+// products mp * 0.5, mp * 0.25 are exact), so they differ by < 48 * 2^-53 = 5.3e-15, i.e. by < 2.3e-5 in threshold units
+// (x 2^32): the two integer thresholds can only differ if sum * 2^32 - 0.5 lies within 2.3e-5 of an integer m -- and then
+// only the draw r == m is affected.  The host lists those integers for the env's slip_prob, with a 4x margin (SlipDanger:
+// empty for 0.2, 0.5, 0.9, 0.123456789, ...); a draw on the list, the never-reached "no sum exceeds u" pick and a bucket
+// of k(r) with two steps take the reference's walk, everything else is decided by integer compares.  State-independent:
+// the same code serves the rules kernels of any pitch.  (k_build_slip_index's plane 1 is the constructive check of this
+// argument for the table pitches: tests assert it flags nothing the list does not cover.)
+// Shared look-up tables, built by every CTA from E_k and the combination probabilities (B = 2^bits buckets):
+//   kthr[b] (B uint32)     t - 1 for the ONE step of k(r) inside bucket b (k = klo + (r > kthr)); 0xFFFFFFFF if none
 //   sl[k][nl - 1]          (20 rows of uint4) strict thresholds t - 1 of slots 1, 2, 3 inside a 2-way / 4-way
 //                          combination k; unused = 0xFFFFFFFF
-struct SlipInt { uint32_t fc, klo, kthr, mva, mvb, sl; };   // shared-window addresses
-constexpr int kSlipIntLutBytes = (1 << kSlipLutBits) * 5 + 80 + 80 + 20 * 16;
-__device__ __forceinline__ void slip_int_build_luts(uint8_t* base, const SlipE& E, const PitchDev& P)
+//   klo[b]  (B bytes)      #{j : E_j <= u(low end of bucket b)}, b = top `bits` bits of the draw; 9 = undecided (two or
+//                          more steps of k(r) inside the bucket: tiny slip_prob) -> walk
+//   mva[k][a], mvb[k][a]   (10 x 8 bytes each) byte offsets inside the table row of the move player A / B makes in
+//                          combination k with action a: (slipped move) * 40, * 8
+struct SlipInt { uint32_t klo, kthr, mva, mvb, sl, shift; };   // shared-window addresses; shift = 32 - bits
+struct SlipDanger { uint32_t n; uint32_t r[12]; };             // draws that must take the walk (kernel parameter)
+__host__ __device__ constexpr int slip_int_lut_bytes(int bits) { return (1 << bits) * 5 + 80 + 80 + 20 * 16; }
+// scale_a / scale_b: 40 / 8 = byte offsets inside a table row (table kernels), 1 / 1 = the move ids (rules kernels)
+__device__ __forceinline__ void slip_int_build_luts(uint8_t* base, const SlipE& E, const PitchDev& P, int bits,
+                                                    uint32_t scale_a = 40u, uint32_t scale_b = 8u)
 {
+    const uint32_t nb = 1u << bits;
     uint32_t* kthr = reinterpret_cast<uint32_t*>(base);
-    uint32_t* sl = kthr + (1 << kSlipLutBits);
+    uint32_t* sl = kthr + nb;
     uint8_t* klo = reinterpret_cast<uint8_t*>(sl + 20 * 4);
-    uint8_t* mva = klo + (1 << kSlipLutBits); uint8_t* mvb = mva + 80;
+    uint8_t* mva = klo + nb; uint8_t* mvb = mva + 80;
     if (threadIdx.x < 80) {
         const int k = min((int)threadIdx.x >> 3, 8), a = min((int)threadIdx.x & 7, 4);
         const int ca = combo_a(k), cb = combo_b(k);
-        mva[threadIdx.x] = (uint8_t)((ca == 0 ? (uint32_t)a : slip_move((uint32_t)a, ca - 1)) * 40u);
-        mvb[threadIdx.x] = (uint8_t)((cb == 0 ? (uint32_t)a : slip_move((uint32_t)a, cb - 1)) * 8u);
+        mva[threadIdx.x] = (uint8_t)((ca == 0 ? (uint32_t)a : slip_move((uint32_t)a, ca - 1)) * scale_a);
+        mvb[threadIdx.x] = (uint8_t)((cb == 0 ? (uint32_t)a : slip_move((uint32_t)a, cb - 1)) * scale_b);
     }
     if (threadIdx.x >= 96 && threadIdx.x < 96 + 20) {
         const int row = threadIdx.x - 96, k = row >> 1, nl = (row & 1) + 1;
@@ -891,14 +908,14 @@ __device__ __forceinline__ void slip_int_build_luts(uint8_t* base, const SlipE& 
             double cc = k == 0 ? 0.0 : E.e[k - 1];
             for (int j = 0; j + 1 < (1 << nl); ++j) {
                 cc = __dadd_rn(cc, pr);
-                const uint64_t th = slip_thr(cc);      // 0 or 2^32 here: the index flags every pick that would use it
+                const uint64_t th = slip_thr(cc);      // 0 here: the danger list sends the draws that could use it to the walk
                 t[j] = (th == 0ull || th > 0xFFFFFFFFull) ? 0xFFFFFFFFu : (uint32_t)(th - 1ull);
             }
         }
         sl[row * 4 + 0] = t[0]; sl[row * 4 + 1] = t[1]; sl[row * 4 + 2] = t[2]; sl[row * 4 + 3] = t[3];
     }
-    for (uint32_t b = threadIdx.x; b < (1u << kSlipLutBits); b += blockDim.x) {
-        const uint32_t lo = b << (32 - kSlipLutBits), hi = lo | ((1u << (32 - kSlipLutBits)) - 1u);
+    for (uint32_t b = threadIdx.x; b < nb; b += blockDim.x) {
+        const uint32_t lo = b << (32 - bits), hi = lo | ((1u << (32 - bits)) - 1u);
         const double ulo = u_from_rng32(lo), uhi = u_from_rng32(hi);
         uint32_t kl = 0, kh = 0;
 #pragma unroll
@@ -910,11 +927,25 @@ __device__ __forceinline__ void slip_int_build_luts(uint8_t* base, const SlipE& 
         kthr[b] = thr;
     }
 }
-__device__ __forceinline__ SlipInt slip_int_ctx(uint8_t* base, uint32_t fc_addr)
+__device__ __forceinline__ SlipInt slip_int_ctx(const uint8_t* base, int bits)
 {
-    const uint32_t b = smem_u32(base), n = 1u << kSlipLutBits;
-    SlipInt f = { fc_addr, b + n * 4u + 320u, b, b + n * 5u + 320u, b + n * 5u + 400u, b + n * 4u };
+    const uint32_t b = smem_u32(base), n = 1u << bits;
+    SlipInt f = { b + n * 4u + 320u, b, b + n * 5u + 320u, b + n * 5u + 400u, b + n * 4u, (uint32_t)(32 - bits) };
     return f;
+}
+// combination index of a 32-bit draw: 0 .. 8, or 9 = walk (undecided bucket, "no sum exceeds u", or a listed draw)
+__device__ __forceinline__ uint32_t slip_int_k(const SlipInt& f, const SlipDanger& dg, uint32_t r32)
+{
+    const uint32_t b = r32 >> f.shift;
+    uint32_t k = lds_u8_r(f.klo + b);
+    uint32_t t;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(t) : "r"(f.kthr + b * 4u));
+    k += r32 > t ? 1u : 0u;
+    if (dg.n) {                                                // kernel-uniform; empty for ordinary slip_prob values
+#pragma unroll 1
+        for (uint32_t i = 0; i < dg.n; ++i) k = r32 == dg.r[i] ? 9u : k;
+    }
+    return k;
 }
 __device__ __forceinline__ uint32_t lds_u32_r(uint32_t addr)
 {
@@ -937,15 +968,13 @@ __device__ __forceinline__ uint4 lds_v4_r(uint32_t addr)
 // One env-step with a 32-bit draw.  walk == true: the result is void, the caller takes the reference's walk.
 // CLAMP_ACT: the action values come from a caller's stream (Philox-decoded and policy-table actions are < 5 already).
 template <bool CLAMP_ACT>
-__device__ __forceinline__ TblOut table_step_slip_int(const TblCtx& c, const SlipInt& f, uint32_t s, uint32_t aa, uint32_t ab,
-                                                      uint32_t r32, uint32_t rsel4, bool& walk)
+__device__ __forceinline__ TblOut table_step_slip_int(const TblCtx& c, const SlipInt& f, const SlipDanger& dg, uint32_t s,
+                                                      uint32_t aa, uint32_t ab, uint32_t r32, uint32_t rsel4, bool& walk)
 {
     const uint32_t obsi = min(s & 0xFFFFu, c.last / 100u);
     if (CLAMP_ACT) { aa = min(aa, 4u); ab = min(ab, 4u); }
-    const uint32_t dm = lds_u16_r(f.fc + (obsi * 25u + aa * 5u + ab) * 2u);
-    const uint32_t b = r32 >> (32 - kSlipLutBits);
-    const uint32_t k = lds_u8_r(f.klo + b) + (r32 > lds_u32_r(f.kthr + b * 4u) ? 1u : 0u);     // 0 .. 9
-    walk = ((dm >> k) & 1u) != 0u;
+    const uint32_t k = slip_int_k(f, dg, r32);
+    walk = k >= 9u;
     uint32_t ent = c.tbl + obsi * 200u + lds_u8_r(f.mva + k * 8u + aa) + lds_u8_r(f.mvb + k * 8u + ab);
     int32_t e = lds_s16_r(ent);
     if ((uint32_t)e & 0x3000u) {                               // 3 % of the (state, move pair)s: 2 or 4 outcomes
@@ -981,7 +1010,7 @@ __device__ __forceinline__ TblOut table_step_slip_walk(const TblCtx& c, const Sl
 
 // K1 for slip_prob > 0 and 32-bit draws (injected rng32: 24 B / env-step; Philox: 19 B): k_step_table's structure --
 // persistent 1024-thread CTAs, two groups in flight + register prefetch of the next pair -- around table_step_slip_int.
-// Shared-memory image: [table][isd 16 B][slip index plane 1][policy a][policy b][look-up tables of the fast path].
+// Shared-memory image: [table][isd 16 B][policy a][policy b][look-up tables of the fast path].
 struct GroupS { uint4 s; uint32_t a, b, r; uint4 d; };
 template <bool PHILOX>
 __device__ __forceinline__ GroupS load_group_slip(const uint4* st, const uint32_t* aa, const uint32_t* ab, const uint32_t* rg,
@@ -1002,6 +1031,9 @@ __device__ __forceinline__ GroupS load_group_slip(const uint4* st, const uint32_
 #ifndef SOCCER_SLIP_I_GROUPS
 #define SOCCER_SLIP_I_GROUPS 1         // groups of 4 envs a thread has in flight (1 or 2)
 #endif
+#ifndef SOCCER_SLIP_I_L2_PREFETCH
+#define SOCCER_SLIP_I_L2_PREFETCH 0    // iterations ahead of the register prefetch to pull into L2 (0 = off)
+#endif
 #ifndef SOCCER_SLIP_I_THREADS
 #define SOCCER_SLIP_I_THREADS 0        // 0: 512 for injected draws, 768 for Philox
 #endif
@@ -1010,7 +1042,7 @@ constexpr int slip_i_threads() { return SOCCER_SLIP_I_THREADS ? SOCCER_SLIP_I_TH
 template <bool RESET_OBS, bool PHILOX>
 __global__ void __launch_bounds__((slip_i_threads<PHILOX>()), 1)
 k_step_table_slip_i(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t table_bytes,
-                    const uint8_t* __restrict__ gfc, uint32_t fc_bytes, const SlipE E,
+                    const SlipE E, const SlipDanger dg, int lut_bits,
                     uint32_t* __restrict__ state, const uint8_t* __restrict__ act_a, const uint8_t* __restrict__ act_b,
                     const uint8_t* __restrict__ rng, const uint32_t* __restrict__ draw, int32_t* __restrict__ obs,
                     float* __restrict__ reward, uint8_t* __restrict__ flags, int32_t* __restrict__ reset_obs, int64_t n_groups,
@@ -1021,15 +1053,15 @@ k_step_table_slip_i(const PitchDev P, const uint16_t* __restrict__ gtable, uint3
     __shared__ __align__(16) double prt[kPrtDoubles];
     const bool has_pol = ex.policy_a || ex.policy_b;
     const uint32_t pol_total = has_pol ? 2u * (((uint32_t)P.nS + 15u) & ~15u) : 0u;
-    uint8_t* luts = smem_raw + table_bytes + 16 + fc_bytes + pol_total;
+    uint8_t* luts = smem_raw + table_bytes + 16 + pol_total;
     slip_build_prt(prt, P);
-    slip_int_build_luts(luts, E, P);
-    stage_table_and_index(smem_raw, gtable, table_bytes, gfc, fc_bytes, &bar, P);          // ends with __syncthreads()
+    slip_int_build_luts(luts, E, P, lut_bits);
+    stage_table(smem_raw, gtable, table_bytes, &bar, P);                                   // ends with __syncthreads()
     TblCtx c = make_ctx(smem_raw, table_bytes, P);
     SlipCtx sc = { smem_u32(prt), slip_first_k(P) };
-    SlipInt sf = slip_int_ctx(luts, c.isd + 16u);
+    SlipInt sf = slip_int_ctx(luts, lut_bits);
     K1Policy pol = { 0u, 0u };
-    if (has_pol) pol = stage_k1_policies(smem_raw + table_bytes + 16 + fc_bytes, ex.policy_a, ex.policy_b, P.nS);
+    if (has_pol) pol = stage_k1_policies(smem_raw + table_bytes + 16, ex.policy_a, ex.policy_b, P.nS);
     const bool flip = pol.pol_a != 0u;
     uint4* st4 = reinterpret_cast<uint4*>(state);
     const uint32_t* a4 = reinterpret_cast<const uint32_t*>(act_a ? act_a : act_b);
@@ -1048,7 +1080,7 @@ k_step_table_slip_i(const PitchDev P, const uint16_t* __restrict__ gtable, uint3
     if (two) x1 = load_group_slip<PHILOX>(st4, a4, b4, r4, d4, g + stride);
     wait_table(&bar);
     launder(c.tbl); launder(c.isd); launder(sc.prt);
-    launder(sf.fc); launder(sf.klo); launder(sf.kthr); launder(sf.mva); launder(sf.mvb); launder(sf.sl);
+    launder(sf.klo); launder(sf.kthr); launder(sf.mva); launder(sf.mvb); launder(sf.sl);
     launder(pol.pol_a); launder(pol.pol_b);
     auto do_group = [&](GroupS& x, int64_t gg) {
         if (PHILOX) {
@@ -1071,7 +1103,7 @@ k_step_table_slip_i(const PitchDev P, const uint16_t* __restrict__ gtable, uint3
             }
             const uint32_t rsel4 = __byte_perm(rs4, 0, 0x4440 + e);
             bool walk;
-            TblOut o = table_step_slip_int<true>(c, sf, sv[e], aa, ab, r32[e], rsel4, walk);
+            TblOut o = table_step_slip_int<true>(c, sf, dg, sv[e], aa, ab, r32[e], rsel4, walk);
             if (walk) o = table_step_slip_walk(c, sc, sv[e], aa, ab, r32[e], rsel4);     // (in practice never)
             so[e] = o.state; oo[e] = o.obs; rr[e] = __float_as_uint((float)(flip ? -o.rew_i : o.rew_i));
             ro[e] = o.reset_obs; ff[e] = o.flags;
@@ -1090,6 +1122,19 @@ k_step_table_slip_i(const PitchDev P, const uint16_t* __restrict__ gtable, uint3
             const bool n_one = gn < n_groups;
             GroupS y0 = x0;
             if (n_one) y0 = load_group_slip<PHILOX>(st4, a4, b4, r4, d4, gn);
+            if (SOCCER_SLIP_I_L2_PREFETCH) {
+                // deepen the load pipeline without registers: the lines of the group SOCCER_SLIP_I_L2_PREFETCH iterations
+                // ahead are pulled into L2 now (this kernel has 16-24 warps per SM and one group per thread in flight)
+                const int64_t gp = gn + (int64_t)SOCCER_SLIP_I_L2_PREFETCH * stride;
+                if (gp < n_groups) {
+                    prefetch_l2(st4 + gp);
+                    if (!PHILOX) prefetch_l2(d4 + gp);
+                    if ((threadIdx.x & 31) == 0) {
+                        prefetch_l2(a4 + gp); prefetch_l2(b4 + gp);
+                        if (!PHILOX) prefetch_l2(r4 + gp);
+                    }
+                }
+            }
             do_group(x0, g);
             x0 = y0; g = gn; one = n_one;
         }

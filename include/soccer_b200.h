@@ -298,10 +298,16 @@ int soccer_step_table_slip(const soccer_pitch *pitch, const uint16_t *table, con
  *     the reference's walk is "r >= ceil(sum * 2^32 - 0.5)", an integer threshold, and a last-bit difference between the
  *     true running sum and the constant one moves that integer only if an integer lies between the two.  The fast path
  *     therefore decides combination AND slot from constant integer thresholds; bit k (0 .. 8) marks the picks for which
- *     some threshold is not the constant one (in practice none), bit 9 (always set) the "no sum exceeds u" case: only
- *     those take the reference's walk.
- * Results are identical with or without the index.  NULL = walk every env.  bytes: 3 * P. */
+ *     some threshold is not the constant one, bit 9 is always set.  The kernels do not read this plane: they use the
+ *     state-independent list of soccer_slip_danger_host (same argument, proved by an error bound); the plane is its
+ *     constructive cross-check (tests).
+ * Results are identical with or without the index.  NULL = the fp64 path walks every env (32-bit draws need no index).
+ * bytes: 3 * P. */
 int soccer_slip_index_bytes_host(const soccer_pitch *pitch, int64_t *bytes);
+/* The 32-bit draws that the integer-threshold slip path of this slip_prob hands to the reference's walk (a threshold
+ * within 1e-4 of an integer, where the last bits of the running sums could matter): *n of them
+ * (0 for ordinary values), or *n = -1 when there are more than 12 and the fast path is off.  Host only. */
+int soccer_slip_danger_host(const soccer_pitch *pitch, uint32_t draws[12], int32_t *n);
 int soccer_build_slip_index(const soccer_pitch *pitch, const uint16_t *table, uint8_t *slip_index,
                             soccer_stream_t stream);
 /* soccer_rollout (uniform random policy; slip_prob >= 0) on SOCCER_LAYOUT_INDEX states */

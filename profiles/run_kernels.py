@@ -3,6 +3,7 @@
     python profiles/run_kernels.py [k1_table|k1_table_stats|k1_single_agent|k1_rules|k2_table|k2_rules|k1_slip|k2_slip|k1_philox|k1_packed|replay|all] [--envs N]
 """
 import argparse
+import contextlib
 import os
 import sys
 
@@ -10,6 +11,19 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from gym_soccer_littman94_b200.envs import SoccerVecEnv  # noqa: E402
+
+
+@contextlib.contextmanager
+def profiled():
+    """cudaProfilerStart / Stop around the launches that matter: run ncu with `--profile-from-start off` and only these
+    are captured (the play-in steps before them are not)."""
+    torch.cuda.synchronize()
+    torch.cuda.profiler.start()
+    try:
+        yield
+    finally:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
 
 
 def k1(kernel, n, iters, with_stats=False, policy=False):
@@ -23,10 +37,13 @@ def k1(kernel, n, iters, with_stats=False, policy=False):
     ins = [tuple(torch.randint(0, hi, (n,), dtype=torch.uint8, device=dev, generator=g) for hi in (5, 5, 16)) for _ in range(4)]
     env.reset(ins[0][2])
     stats = torch.zeros(6, dtype=torch.int64, device=dev) if with_stats else None
-    for i in range(64 + iters):
+    for i in range(64):
         a, b, r = ins[i % 4]
         env.step(a, None if policy else b, r, stats=stats)
-    torch.cuda.synchronize()
+    with profiled():
+        for i in range(iters):
+            a, b, r = ins[i % 4]
+            env.step(a, None if policy else b, r, stats=stats)
 
 
 def k1_philox(n, iters):
@@ -35,9 +52,11 @@ def k1_philox(n, iters):
     g = torch.Generator(device=dev).manual_seed(0)
     a, b = (torch.randint(0, 5, (n,), dtype=torch.uint8, device=dev, generator=g) for _ in range(2))
     env.reset()
-    for _ in range(iters):
+    for _ in range(40):
         env.step(a, b)
-    torch.cuda.synchronize()
+    with profiled():
+        for _ in range(iters):
+            env.step(a, b)
 
 
 def k1_packed(n, iters):
@@ -49,15 +68,15 @@ def k1_packed(n, iters):
     hr.copy_(torch.randint(0, 16, (n,), dtype=torch.uint8))
     dj, dr = hj.to(dev), hr.to(dev)
     env.reset(dr)
-    for _ in range(iters):
-        env.step_packed(dj, dr)
-    for _ in range(iters):
-        env.step_host_packed(hj, hr)
     ha, hb, hr3 = env.alloc_host_inputs()
     ha.copy_(hj & 15); hb.copy_(hj >> 4); hr3.copy_(hr)
-    for _ in range(iters):
-        env.step_host(ha, hb, hr3, narrow=True, zero_copy=True)
-    torch.cuda.synchronize()
+    with profiled():
+        for _ in range(iters):
+            env.step_packed(dj, dr)
+        for _ in range(iters):
+            env.step_host_packed(hj, hr)
+        for _ in range(iters):
+            env.step_host(ha, hb, hr3, narrow=True, zero_copy=True)
 
 
 def k2(kernel, n, K, iters):
@@ -66,9 +85,10 @@ def k2(kernel, n, K, iters):
     env.reset()
     bufs = (torch.empty((K, n), dtype=torch.int32, device=dev), torch.empty((K, n), dtype=torch.float32, device=dev),
             torch.empty((K, n), dtype=torch.uint8, device=dev))
-    for _ in range(iters):
-        env.rollout(K, out=bufs)
-    torch.cuda.synchronize()
+    env.rollout(K, out=bufs)
+    with profiled():
+        for _ in range(iters):
+            env.rollout(K, out=bufs)
 
 
 def k1_slip(n, iters):
@@ -83,15 +103,19 @@ def k1_slip(n, iters):
         env = SoccerVecEnv(n, slip_prob=0.2, device=dev, kernel="table", want_reset_obs=False,
                            rng_mode="philox" if mode == "philox" else "injected")
         env.reset(None if mode == "philox" else r)
-        for _ in range(40 + iters):
+        def one():
             if mode == "philox":
                 env.step(a, b)
             elif mode == "rng32":
                 env.step(a, b, r, rng32=r32)
             else:
                 env.step(a, b, r, rngf64=r64)
+        for _ in range(40):
+            one()
+        with profiled():
+            for _ in range(iters):
+                one()
         del env
-    torch.cuda.synchronize()
 
 
 def k2_slip(n, K, iters):
@@ -101,9 +125,10 @@ def k2_slip(n, K, iters):
     e2.rollout(64, want_streams=False)          # a played-in population
     bufs = (torch.empty((K, n), dtype=torch.int32, device=dev), torch.empty((K, n), dtype=torch.float32, device=dev),
             torch.empty((K, n), dtype=torch.uint8, device=dev))
-    for _ in range(iters):
-        e2.rollout(K, out=bufs)
-    torch.cuda.synchronize()
+    e2.rollout(K, out=bufs)
+    with profiled():
+        for _ in range(iters):
+            e2.rollout(K, out=bufs)
 
 
 def replay(kernel, n, T, iters):
@@ -113,9 +138,10 @@ def replay(kernel, n, T, iters):
     out = (torch.empty((T, n), dtype=torch.int32, device=dev), torch.empty((T, n), dtype=torch.float32, device=dev),
            torch.empty((T, n), dtype=torch.uint8, device=dev), None)
     env.reset(r[0])
-    for _ in range(iters):
-        env.step_many(a, b, r, out=out)
-    torch.cuda.synchronize()
+    env.step_many(a, b, r, out=out)
+    with profiled():
+        for _ in range(iters):
+            env.step_many(a, b, r, out=out)
 
 
 if __name__ == "__main__":

@@ -100,13 +100,47 @@ if "k1slip" in what:        # A/B of library variants (SOCCER_B200_LIB): K1 slip
             report(f"[{tag}] K1 {name} n=2^{logn}", n, ms, nb)
             del e
 
+if "rules_slip" in what:    # slip_prob = 0.2 on a pitch without a table (7x5): integer thresholds + byte-parallel rules vs the walk
+    for tag, envv in (("integer thresholds", {}), ("reference walk", {"SOCCER_B200_SLIP_WALK": "1"})):
+        os.environ.update(envv)
+        n = 1 << 24
+        g = torch.Generator(device=dev).manual_seed(1)
+        ins = [tuple(torch.randint(0, hi, (n,), dtype=torch.uint8, device=dev, generator=g) for hi in (5, 5, 16)) for _ in range(2)]
+        outs = [(torch.empty(n, dtype=torch.int32, device=dev), torch.empty(n, dtype=torch.float32, device=dev),
+                 torch.empty(n, dtype=torch.uint8, device=dev), None) for _ in range(2)]
+        r32 = [torch.randint(-2**31, 2**31 - 1, (n,), dtype=torch.int32, device=dev, generator=g) for _ in range(2)]
+        for name, kw, fn, nb in (
+                ("injected rng32", dict(), lambda e, i: e.step(*ins[i % 2], rng32=r32[i % 2], out=outs[i % 2]), 24),
+                ("philox", dict(rng_mode="philox"), lambda e, i: e.step(ins[i % 2][0], ins[i % 2][1], out=outs[i % 2]), 19)):
+            e = SoccerVecEnv(n, width=7, height=5, slip_prob=0.2, device=dev, kernel="rules", want_reset_obs=False, **kw)
+            e.reset(ins[0][2] if e.rng_mode == "injected" else None)
+            for i in range(20):
+                fn(e, i)
+            ms = timed(lambda i: fn(e, i), 10 if envv else 30, warm=2)
+            report(f"K1 rules 7x5 slip 0.2 {name} [{tag}] n=2^24", n, ms, nb)
+            del e
+        del ins, outs, r32
+        torch.cuda.empty_cache()
+        n, K = 1 << 22, 16
+        bufs = (torch.empty((K, n), dtype=torch.int32, device=dev), torch.empty((K, n), dtype=torch.float32, device=dev),
+                torch.empty((K, n), dtype=torch.uint8, device=dev))
+        e = SoccerVecEnv(n, width=7, height=5, slip_prob=0.2, device=dev, rng_mode="philox", kernel="rules")
+        e.reset()
+        e.rollout(32, want_streams=False)
+        ms = timed(lambda i: e.rollout(K, out=bufs), 4, warm=1)
+        report(f"K2 rules 7x5 slip 0.2 [{tag}] n=2^22 K=16", n * K, ms, 9.125)
+        del e, bufs
+        torch.cuda.empty_cache()
+        for k in envv:
+            os.environ.pop(k)
+
 if "k2" in what:
     for logn, K in ((20, 64), (21, 64), (22, 16)):
         n = 1 << logn
         bufs = (torch.empty((K, n), dtype=torch.int32, device=dev), torch.empty((K, n), dtype=torch.float32, device=dev),
                 torch.empty((K, n), dtype=torch.uint8, device=dev))
         for tag, kw, env in (("slip 0 table", dict(kernel="table"), {}),
-                             ("slip 0.2 table fast path + queue", dict(kernel="table", slip_prob=0.2), {}),
+                             ("slip 0.2 table integer thresholds", dict(kernel="table", slip_prob=0.2), {}),
                              ("slip 0.2 table in-place walk", dict(kernel="table", slip_prob=0.2), {"SOCCER_B200_SLIP_WALK": "1"}),
                              ("slip 0 rules", dict(kernel="rules"), {}),
                              ("slip 0.2 rules", dict(kernel="rules", slip_prob=0.2), {})):

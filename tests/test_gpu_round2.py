@@ -378,26 +378,36 @@ def test_out_tensors_are_checked(dev):
 
 
 # ----------------------------------------------------------------------------- slip: integer-threshold fast path
+@pytest.mark.parametrize("kernel,w,h", [("table", 5, 4), ("table", 6, 4), ("rules", 5, 4), ("rules", 7, 5)])
 @pytest.mark.parametrize("slip", [0.2, 0.5, 1.0, 1e-9, 0.123456789, 0.9])
-def test_slip_integer_thresholds_equal_walk(dev, slip, monkeypatch):
-    """32-bit draws (rng32 / Philox) through the shared-memory table with the slip index: combination and slot come
-    from constant INTEGER thresholds (index plane 1).  Against the reference's cumulative walk of every env
-    (SOCCER_B200_SLIP_WALK=1), with the draws sitting ON and next to every threshold -- end of each combination and
-    the slots inside 2-way / 4-way combinations -- and on 0 and 2^32 - 1, on a population full of collision states."""
+def test_slip_integer_thresholds_equal_walk(dev, slip, kernel, w, h, monkeypatch):
+    """32-bit draws (rng32 / Philox) with slip_prob > 0: combination and slot come from constant INTEGER thresholds, in
+    the table kernels (5x4; 6x4 with the 10-bit bucket table) and, state-independently, in the byte-parallel rules
+    kernels of any pitch.  Against the reference's cumulative walk of every env (SOCCER_B200_SLIP_WALK=1), with the draws
+    sitting ON and next to every threshold -- end of each combination and the slots inside 2-way / 4-way combinations --
+    and on 0 and 2^32 - 1, on a population full of collision states.  Where the danger list of the slip_prob is empty,
+    the constructive check (slip index plane 1: true vs constant thresholds per (obs, joint action)) must be empty too."""
+    import ctypes as C
+    from gym_soccer_littman94_b200 import _lib
     from gym_soccer_littman94_b200.envs import SoccerSimultaneousEnv, SoccerVecEnv
-    n = 1 << 16
+    n = 1 << 15
     rs = np.random.RandomState(7)
     envs = {}
     for mode in ("walk", "index"):
         monkeypatch.setenv("SOCCER_B200_SLIP_WALK", "1" if mode == "walk" else "0")
-        envs[mode] = SoccerVecEnv(n, slip_prob=slip, device=dev, kernel="table")
-    idx = envs["index"].slip_index.cpu().numpy()
-    plane = idx.size // 3
-    p1 = idx[plane:].view(np.uint16)[:761 * 25]
-    assert np.all(p1 & 0x200)                             # bit 9: the "no sum exceeds u" pick is always walked
-    flagged = int(((p1 & 0x1FF) != 0).sum())
-    if slip not in (1.0, 1e-9):                           # (zero-probability / 1e-19 combinations flag their picks)
-        assert flagged <= 0.01 * 761 * 25, flagged        # the walk is a rare fallback (expected: none at all)
+        envs[mode] = SoccerVecEnv(n, width=w, height=h, slip_prob=slip, device=dev, kernel=kernel)
+    draws, nd = (C.c_uint32 * 12)(), C.c_int32()
+    _lib.check(_lib.lib().soccer_slip_danger_host(C.byref(_lib.Pitch(w, h, slip)), C.byref(draws), C.byref(nd)), "danger")
+    assert 0 <= nd.value <= 12
+    if kernel == "table" and (w, h) == (5, 4):
+        idx = envs["index"].slip_index.cpu().numpy()
+        plane = idx.size // 3
+        p1 = idx[plane:].view(np.uint16)[:761 * 25]
+        assert np.all(p1 & 0x200)                             # bit 9: the "no sum exceeds u" pick is always walked
+        if nd.value == 0:
+            assert not np.any(p1 & 0x1FF)                     # nothing flagged where the list is empty
+    if slip in (0.2, 0.5, 0.9, 0.123456789):
+        assert nd.value == 0                                  # ordinary values: the walk is never needed
     # candidate draws: thresholds of the constant sums (numpy restatement: sequential fp64 adds like SIM:241)
     mp = [(1 - slip) * (1 - slip)] + [(1 - slip) * slip * 0.5] * 2 + [slip * (1 - slip) * 0.5] * 2 + [slip * slip * 0.25] * 4
     cand, acc = [0, 1, 2 ** 32 - 1, 2 ** 32 - 2], 0.0
@@ -413,7 +423,7 @@ def test_slip_integer_thresholds_equal_walk(dev, slip, monkeypatch):
     init = _t(rs.randint(0, 16, n).astype(np.uint8), dev)
     for e in envs.values():
         e.reset(init)
-    adj = SoccerSimultaneousEnv(device=dev)
+    adj = SoccerSimultaneousEnv(width=w, height=h, device=dev)
     coll = [adj._state_to_observation(t) for t in ((1, 2, 1, 3, 0), (1, 2, 1, 3, 1), (2, 3, 1, 3, 0), (1, 3, 2, 3, 1), (1, 2, 1, 4, 0))]
     for t in range(40):
         a, b, r = (_t(rs.randint(0, hi, n).astype(np.uint8), dev) for hi in (5, 5, 16))
