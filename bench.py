@@ -272,6 +272,7 @@ def run_ours(args):
     for i in range(W):
         env.step(*ins[i % RING], out=outs[i % RING], stats=stats)
     if world > 1:
+        barrier()                                      # the peer-memory kernel has a watchdog: enter it together
         allreduce_stats(stats.clone(), p2p)            # warm the collective
     barrier()
     sampler = ClockSampler(local)
@@ -625,6 +626,7 @@ def run_ours(args):
         esh.reset()
         _, _, _, st_sh = esh.rollout(SHARD_INVARIANT["K"], want_streams=False)
         if world > 1:
+            barrier()
             allreduce_stats(st_sh, p2p)
         shard["collective"] = collective
         shard["stats_allreduce"] = [int(x) for x in st_sh.cpu()]

@@ -241,7 +241,7 @@ k_step_fast_slip(const PitchDev P, const RulesSlipArgs sa, uint32_t* __restrict_
     __shared__ __align__(16) double prt[kPrtDoubles];
     __shared__ __align__(16) uint8_t ilut[slip_int_lut_bytes(kRulesSlipLutBits)];
     slip_build_prt(prt, P);
-    slip_int_build_luts(ilut, sa.E, P, kRulesSlipLutBits, 1u, 1u);
+    slip_int_build_luts(ilut, sa.E, P, kRulesSlipLutBits, 1u, 16u);
     build_cand_lut(lut, P);                      // ends with __syncthreads()
     const Isd4 I = make_isd4(P);
     const SlipCtx sc = { (uint32_t)__cvta_generic_to_shared(prt), slip_first_k(P) };
@@ -274,7 +274,7 @@ k_step_fast_slip(const PitchDev P, const RulesSlipArgs sa, uint32_t* __restrict_
         const uint32_t sv[4] = { x.s.x, x.s.y, x.s.z, x.s.w };
         const uint32_t r32[4] = { x.d.x, x.d.y, x.d.z, x.d.w };
         Step4 o;
-        step4_slip_int<RESET_OBS>(P, I, lut, fi, sa.dg, sc, sv, x.a, x.b, r32, x.r, o);
+        step4_slip_int<RESET_OBS, true>(P, I, lut, fi, sa.dg, sc, sv, ((x.a & 0x07070707u) << 3) | (x.b & 0x07070707u), r32, x.r, o);
         st_keep(st4 + g, make_uint4(o.s[0], o.s[1], o.s[2], o.s[3]));
         st_stream(o4 + g, make_uint4(o.obs[0], o.obs[1], o.obs[2], o.obs[3]));
         st_stream(w4 + g, make_uint4(o.rew[0], o.rew[1], o.rew[2], o.rew[3]));
@@ -636,7 +636,7 @@ k_stats_allreduce_p2p(const P2PStatsArgs a)
         unsigned long long f;
         do {
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(src + 7) : "memory");
-            if (f != a.epoch && clock64() - t0 > (4ll << 30)) __trap();     // ~2 s: a peer died; do not hang the GPU
+            if (f != a.epoch && clock64() - t0 > (40ll << 30)) __trap();    // ~20 s: a peer died; do not hang the GPU
         } while (f != a.epoch);
 #pragma unroll
         for (int j = 0; j < 6; ++j) asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v[j]) : "l"(src + j) : "memory");
@@ -1446,8 +1446,8 @@ int soccer_rollout_table_policy(const soccer_pitch* pitch, const uint16_t* table
             do {                                                                                         \
                 const int e0 = allow_big_smem(k_rollout_table_slipi<VEC, STR, POL>, smem_i);             \
                 if (e0) return e0;                                                                       \
-                const int e1 = launch_pdl(k_rollout_table_slipi<VEC, STR, POL>, table_grid(ITEMS, kRolloutThreads), \
-                                          kRolloutThreads, (size_t)smem_i, st, P, table, (uint32_t)bytes, \
+                const int e1 = launch_pdl(k_rollout_table_slipi<VEC, STR, POL>, table_grid(ITEMS, kRolloutSlipThreads), \
+                                          kRolloutSlipThreads, (size_t)smem_i, st, P, table, (uint32_t)bytes, \
                                           E, dg, lut_bits, policy_a, policy_b, ra);                      \
                 if (e1) return e1;                                                                       \
             } while (0)

@@ -35,34 +35,35 @@ __device__ __noinline__ StepOut step_slip_call(const PitchDev& P, const uint8_t*
     const SlipCtx sc = { prt, first_k };
     return step_slip<true>(P, lut, sc, s, aa, ab, u_from_rng32(r32), reset_sel, false);
 }
-template <bool RESET_OBS>
+// J4: the joint action of each env as one index byte -- WIDE: aa * 8 + ab (caller-supplied action bytes, 3-bit fields),
+// else aa * 5 + ab (the Philox joint action); the move pair of (combination, joint action) is ONE byte ma | mb << 4.
+template <bool RESET_OBS, bool WIDE>
 __device__ __forceinline__ void step4_slip_int(const PitchDev& P, const Isd4& I, const uint8_t* __restrict__ lut,
                                                const SlipInt& f, const SlipDanger& dg, const SlipCtx& sc, const uint32_t sv[4],
-                                               uint32_t A4, uint32_t B4, const uint32_t r32[4], uint32_t RST, Step4& o)
+                                               uint32_t J4, const uint32_t r32[4], uint32_t RST, Step4& o)
 {
-    uint32_t ma[4], mb[4], r4[4], r2[4], walk = 0;
+    uint32_t mv[4], r4[4], r2[4], walk = 0;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-        const uint32_t aa = min(byte_of(A4, e), 4u), ab = min(byte_of(B4, e), 4u);
         const uint32_t k = slip_int_k(f, dg, r32[e]);
         walk |= (k >= 9u ? 1u : 0u) << e;
         const uint32_t kc = min(k, 8u);
-        ma[e] = lds_u8_r(f.mva + kc * 8u + aa);
-        mb[e] = lds_u8_r(f.mvb + kc * 8u + ab);
+        mv[e] = lds_u8_r((WIDE ? f.mvs + kc * 64u : f.mvj + kc * 32u) + byte_of(J4, e));
         const uint32_t t2 = lds_u32_r(f.sl + kc * 32u);                      // 2-way row: one threshold
         const uint4 t4 = lds_v4_r(f.sl + kc * 32u + 16u);                    // 4-way row: three
         r2[e] = r32[e] > t2 ? 2u : 0u;                                       // draw value 2 * slot
         r4[e] = (r32[e] > t4.x ? 1u : 0u) + (r32[e] > t4.y ? 1u : 0u) + (r32[e] > t4.z ? 1u : 0u);
     }
+    const uint32_t MV = pack4(mv[0], mv[1], mv[2], mv[3]);
     const uint32_t R4 = pack4(r4[0], r4[1], r4[2], r4[3]) | (RST & 0x0C0C0C0Cu);
-    step4_noslip<RESET_OBS>(P, I, lut, sv, pack4(ma[0], ma[1], ma[2], ma[3]), pack4(mb[0], mb[1], mb[2], mb[3]), R4, o,
-                            pack4(r2[0], r2[1], r2[2], r2[3]));
+    step4_noslip<RESET_OBS>(P, I, lut, sv, MV & 0x0F0F0F0Fu, (MV >> 4) & 0x0F0F0F0Fu, R4, o, pack4(r2[0], r2[1], r2[2], r2[3]));
     if (walk) {                                                              // (in practice never)
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             if ((walk >> e) & 1u) {
-                const StepOut w = step_slip_call(P, lut, sc.prt, sc.first_k, sv[e], min(byte_of(A4, e), 4u), min(byte_of(B4, e), 4u),
-                                                 r32[e], (byte_of(RST, e) >> 2) & 3u);
+                const uint32_t j = byte_of(J4, e);
+                const StepOut w = step_slip_call(P, lut, sc.prt, sc.first_k, sv[e], WIDE ? min(j >> 3, 4u) : min(j / 5u, 4u),
+                                                 WIDE ? min(j & 7u, 4u) : j % 5u, r32[e], (byte_of(RST, e) >> 2) & 3u);
                 const int32_t ri = (w.reward > 0.0f) - (w.reward < 0.0f);
                 o.rew_sum += ri - (int32_t)(signed char)(o.rew4 >> (8 * e));
                 o.s[e] = w.state; o.obs[e] = (uint32_t)w.obs; o.rew[e] = __float_as_uint(w.reward);
@@ -74,6 +75,9 @@ __device__ __forceinline__ void step4_slip_int(const PitchDev& P, const Isd4& I,
     }
 }
 
+#ifndef SOCCER_K2_SLIPI_BLOCK
+#define SOCCER_K2_SLIPI_BLOCK 4        // steps of the slip table rollout whose Philox calls are issued together (1, 2 or 4)
+#endif
 #ifndef SOCCER_K2_PHILOX_WIDE
 #define SOCCER_K2_PHILOX_WIDE 1
 #endif
@@ -137,6 +141,7 @@ struct TableStepper {
 template <bool POLICY>
 struct TableSlipIntStepper {
     static constexpr bool kCollective = false, kHasPolicy = POLICY;
+    static constexpr int kBlock = SOCCER_K2_SLIPI_BLOCK;
     TblCtx c; SlipCtx sc; SlipInt sf; SlipDanger dg;
     uint32_t pol_a, pol_b;
     __device__ __forceinline__ uint32_t timestep(uint32_t s) const { return s >> 16; }
@@ -147,17 +152,24 @@ struct TableSlipIntStepper {
         uint32_t ff[4] = { 0, 0, 0, 0 };
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
+            const uint32_t r32 = philox_r32(word[e]), rsel4 = word[e] & 0xCu;
+            bool walk;
+            TblOut o;
             uint32_t aa, ab;
-            philox_actions(word[e], aa, ab);
             if (POLICY) {
+                philox_actions(word[e], aa, ab);
                 const uint32_t cur = min(s[e] & 0xFFFFu, c.last / 100u);
                 if (pol_a) aa = lds_u8_r(pol_a + cur);
                 if (pol_b) ab = lds_u8_r(pol_b + cur);
+                o = table_step_slip_int<false>(c, sf, dg, s[e], aa, ab, r32, rsel4, walk);
+            } else {
+                // the joint action mulhi(w, 25) indexes the (combination, joint action) -> move pair table directly
+                o = table_step_slip_int_j<false>(c, sf, dg, s[e], philox_ja(word[e]), r32, rsel4, walk);
             }
-            const uint32_t r32 = philox_r32(word[e]), rsel4 = word[e] & 0xCu;
-            bool walk;
-            TblOut o = table_step_slip_int<false>(c, sf, dg, s[e], aa, ab, r32, rsel4, walk);
-            if (walk) o = table_step_slip_walk(c, sc, s[e], aa, ab, r32, rsel4);
+            if (walk) {                                                       // (in practice never)
+                if (!POLICY) philox_actions(word[e], aa, ab);
+                o = table_step_slip_walk(c, sc, s[e], aa, ab, r32, rsel4);
+            }
             s[e] = o.state; oo[e] = o.obs; rr[e] = __float_as_uint((float)(flip ? -o.rew_i : o.rew_i)); ff[e] = o.flags;
             net += o.rew_i;
         }
@@ -241,22 +253,25 @@ struct RulesSlipIntStepper {
                                          uint32_t& fw, int32_t& net, bool) const
     {
         static_assert(VEC == 4, "four envs per thread");
-        uint32_t aa[4], ab[4], r32[4], rst = 0;
+        uint32_t ja[4], r32[4], rst = 0;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            philox_actions(word[e], aa[e], ab[e]);
+            ja[e] = philox_ja(word[e]);
             r32[e] = philox_r32(word[e]);
             rst |= (word[e] & 0xCu) << (8 * e);
         }
         Step4 o;
-        step4_slip_int<false>(P, I, lut, fi, dg, sc, s, pack4(aa[0], aa[1], aa[2], aa[3]), pack4(ab[0], ab[1], ab[2], ab[3]),
-                              r32, rst, o);
+        step4_slip_int<false, false>(P, I, lut, fi, dg, sc, s, pack4(ja[0], ja[1], ja[2], ja[3]), r32, rst, o);
 #pragma unroll
         for (int e = 0; e < 4; ++e) { s[e] = o.s[e]; oo[e] = o.obs[e]; rr[e] = o.rew[e]; }
         fw = o.flags4;
         net += o.rew_sum;
     }
 };
+
+// steps per Philox block: 4 unless the stepper says otherwise (kBlock)
+template <class S, class = void> struct stepper_block { static constexpr int value = 4; };
+template <class S> struct stepper_block<S, decltype((void)S::kBlock)> { static constexpr int value = S::kBlock; };
 
 // 64-bit warp sum (statistics only; once per thread at the end of the kernel)
 __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
@@ -325,10 +340,11 @@ __device__ __forceinline__ void rollout_body(const Stepper& S, const RolloutArgs
         // (four independent 10-round chains in flight), then the four steps consume them -- one call per step in
         // program order put the chain's latency in front of every table look-up (measured: -8 % at 2^20 envs).
         uint64_t step = a.step0;
-        for (int32_t kb = 0; kb < K; kb += 4, step += 4) {
-            uint32_t w[4][4];
+        constexpr int PB = stepper_block<Stepper>::value;             // steps whose Philox calls are issued together
+        for (int32_t kb = 0; kb < K; kb += PB, step += PB) {
+            uint32_t w[PB][4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < PB; ++j) {
                 const uint64_t sj = step + (uint64_t)j;
                 // <true>: one IMAD.WIDE per product.  The round-1 build of this loop got that from the compiler's own fusion of
                 // mul.hi + mul.lo; with the per-step counters it stopped fusing (85 IMAD.HI + 85 IMAD in the 4-step body
@@ -336,7 +352,7 @@ __device__ __forceinline__ void rollout_body(const Stepper& S, const RolloutArgs
                 philox4x32_10_rk<SOCCER_K2_PHILOX_WIDE != 0>(grp_lo, grp_hi, (uint32_t)sj, (uint32_t)(sj >> 32), a.rk, w[j]);
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < PB; ++j) {
                 if (kb + j >= K) continue;                              // warp-uniform
                 uint32_t word[4], oo[4], rr[4], fw;
                 if (VEC == 4) {
@@ -359,7 +375,7 @@ __device__ __forceinline__ void rollout_body(const Stepper& S, const RolloutArgs
                     if (with_streams || fp) { *fp = (uint8_t)fw; fp += a.n; }
                 }
             }
-            if ((kb & 63) == 60) {                                      // bytes hold at most 64 counts
+            if ((kb & 63) == 64 - PB) {                                 // bytes hold at most 64 counts
                 p_done = __dp4a(acc_d, 0x01010101u, p_done); p_trunc = __dp4a(acc_t, 0x01010101u, p_trunc);
                 acc_d = acc_t = 0;
             }
@@ -443,8 +459,12 @@ k_rollout_table(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t 
 }
 
 // slip_prob > 0.  Shared-memory image: [table][isd 16 B][policy a][policy b][look-up tables of the integer fast path].
+#ifndef SOCCER_K2_SLIPI_THREADS
+#define SOCCER_K2_SLIPI_THREADS SOCCER_ROLLOUT_THREADS
+#endif
+constexpr int kRolloutSlipThreads = SOCCER_K2_SLIPI_THREADS;
 template <int VEC, bool STREAMS, bool POLICY>
-__global__ void __launch_bounds__(kRolloutThreads, 1)
+__global__ void __launch_bounds__(kRolloutSlipThreads, 1)
 k_rollout_table_slipi(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t table_bytes,
                       const SlipE E, const SlipDanger dg, int lut_bits,
                       const int8_t* __restrict__ policy_a, const int8_t* __restrict__ policy_b, const RolloutArgs a)
@@ -469,7 +489,7 @@ k_rollout_table_slipi(const PitchDev P, const uint16_t* __restrict__ gtable, uin
     S.pol_a = S.pol_b = 0;
     wait_table(&bar);
     launder(S.c.tbl); launder(S.c.isd); launder(S.sc.prt);
-    launder(S.sf.klo); launder(S.sf.kthr); launder(S.sf.mva); launder(S.sf.mvb); launder(S.sf.sl);
+    launder(S.sf.kt); launder(S.sf.mva); launder(S.sf.mvb); launder(S.sf.mvj); launder(S.sf.mvs); launder(S.sf.sl);
     pdl_wait();
     if (POLICY) {
         stage_policies(pa, pb, policy_a, policy_b, P.nS);
@@ -580,7 +600,7 @@ k_rollout_slipi(const PitchDev P, const RolloutArgs a, const RulesSlipArgs sa)
     __shared__ __align__(16) uint8_t ilut[slip_int_lut_bytes(kRulesSlipLutBits)];
     __shared__ BlkStats blk;
     slip_build_prt(prt, P);
-    slip_int_build_luts(ilut, sa.E, P, kRulesSlipLutBits, 1u, 1u);
+    slip_int_build_luts(ilut, sa.E, P, kRulesSlipLutBits, 1u, 16u);
     build_cand_lut(lut, P);
     if (threadIdx.x < 5) blk.v[threadIdx.x] = 0;
     __syncthreads();

@@ -221,6 +221,7 @@ __device__ __forceinline__ uint32_t philox_word(uint64_t seed, uint64_t env_id, 
 //                reset field of an rng8 byte.
 __device__ __forceinline__ uint32_t philox_jr(uint32_t w) { return __umulhi(w, 100u); }
 __device__ __forceinline__ uint32_t philox_r32(uint32_t w) { return w * 25u; }
+__device__ __forceinline__ uint32_t philox_ja(uint32_t w) { return __umulhi(w, 25u); }   // with philox_r32: one IMAD.WIDE
 __device__ __forceinline__ void philox_actions(uint32_t w, uint32_t& aa, uint32_t& ab)
 {
     const uint32_t ja = philox_jr(w) >> 2;

@@ -874,31 +874,49 @@ __device__ __forceinline__ void stage_table_and_index(uint8_t* smem, const uint1
 // of k(r) with two steps take the reference's walk, everything else is decided by integer compares.  State-independent:
 // the same code serves the rules kernels of any pitch.  (k_build_slip_index's plane 1 is the constructive check of this
 // argument for the table pitches: tests assert it flags nothing the list does not cover.)
-// Shared look-up tables, built by every CTA from E_k and the combination probabilities (B = 2^bits buckets):
-//   kthr[b] (B uint32)     t - 1 for the ONE step of k(r) inside bucket b (k = klo + (r > kthr)); 0xFFFFFFFF if none
+// Shared look-up tables, built by every CTA from E_k and the combination probabilities (B = 2^bits buckets, S = 32 - bits):
+//   kt[b]   (B uint32)     (klo << S) + (2^S - 1 - low S bits of t - 1), klo = #{j : E_j <= u(low end of bucket b)} and t the
+//                          ONE step of k(r) inside the bucket (none: low part 0), so that
+//                              k = (kt[b] + (r & (2^S - 1))) >> S          = klo + (r > t - 1)
+//                          -- the compare is the carry out of the low S bits: one load, three integer instructions.
+//                          klo = 9 = undecided (two or more steps inside the bucket: tiny slip_prob) -> walk
 //   sl[k][nl - 1]          (20 rows of uint4) strict thresholds t - 1 of slots 1, 2, 3 inside a 2-way / 4-way
 //                          combination k; unused = 0xFFFFFFFF
-//   klo[b]  (B bytes)      #{j : E_j <= u(low end of bucket b)}, b = top `bits` bits of the draw; 9 = undecided (two or
-//                          more steps of k(r) inside the bucket: tiny slip_prob) -> walk
 //   mva[k][a], mvb[k][a]   (10 x 8 bytes each) byte offsets inside the table row of the move player A / B makes in
-//                          combination k with action a: (slipped move) * 40, * 8
-struct SlipInt { uint32_t klo, kthr, mva, mvb, sl, shift; };   // shared-window addresses; shift = 32 - bits
+//                          combination k with action a: (slipped move) * 40, * 8 (kernels with a folded policy)
+//   mvj[k][aa * 5 + ab]    (10 x 32 bytes) both players' moves of combination k in ONE byte, indexed by the Philox joint
+//                          action ja = mulhi(w, 25): ma * 40 + mb * 8 = the byte offset of the move pair inside the table
+//                          row (table kernels), ma | mb << 4 (rules kernels)
+//   mvs[k][aa * 8 + ab]    (10 x 64 bytes) the same indexed by two 3-bit action fields (caller-supplied action bytes,
+//                          combined byte-parallel for the four envs of a thread); actions > 4 act as 4
+struct SlipInt { uint32_t kt, mva, mvb, mvj, mvs, sl, shift, mask; };   // shared-window addresses; shift = 32 - bits
 struct SlipDanger { uint32_t n; uint32_t r[12]; };             // draws that must take the walk (kernel parameter)
-__host__ __device__ constexpr int slip_int_lut_bytes(int bits) { return (1 << bits) * 5 + 80 + 80 + 20 * 16; }
-// scale_a / scale_b: 40 / 8 = byte offsets inside a table row (table kernels), 1 / 1 = the move ids (rules kernels)
+__host__ __device__ constexpr int slip_int_lut_bytes(int bits) { return (1 << bits) * 4 + 20 * 16 + 80 + 80 + 320 + 640; }
+// scale_a / scale_b: 40 / 8 = byte offsets inside a table row (table kernels), 1 / 16 = the move ids (rules kernels)
 __device__ __forceinline__ void slip_int_build_luts(uint8_t* base, const SlipE& E, const PitchDev& P, int bits,
                                                     uint32_t scale_a = 40u, uint32_t scale_b = 8u)
 {
     const uint32_t nb = 1u << bits;
-    uint32_t* kthr = reinterpret_cast<uint32_t*>(base);
-    uint32_t* sl = kthr + nb;
-    uint8_t* klo = reinterpret_cast<uint8_t*>(sl + 20 * 4);
-    uint8_t* mva = klo + nb; uint8_t* mvb = mva + 80;
+    uint32_t* kt = reinterpret_cast<uint32_t*>(base);
+    uint32_t* sl = kt + nb;
+    uint8_t* mva = reinterpret_cast<uint8_t*>(sl + 20 * 4);
+    uint8_t* mvb = mva + 80; uint8_t* mvj = mvb + 80; uint8_t* mvs = mvj + 320;
+    auto move_of = [](int k, uint32_t a, bool second) {
+        const int cmb = second ? combo_b(k) : combo_a(k);
+        return cmb == 0 ? a : slip_move(a, cmb - 1);
+    };
     if (threadIdx.x < 80) {
         const int k = min((int)threadIdx.x >> 3, 8), a = min((int)threadIdx.x & 7, 4);
-        const int ca = combo_a(k), cb = combo_b(k);
-        mva[threadIdx.x] = (uint8_t)((ca == 0 ? (uint32_t)a : slip_move((uint32_t)a, ca - 1)) * scale_a);
-        mvb[threadIdx.x] = (uint8_t)((cb == 0 ? (uint32_t)a : slip_move((uint32_t)a, cb - 1)) * scale_b);
+        mva[threadIdx.x] = (uint8_t)(move_of(k, (uint32_t)a, false) * scale_a);
+        mvb[threadIdx.x] = (uint8_t)(move_of(k, (uint32_t)a, true) * scale_b);
+    }
+    for (uint32_t i = threadIdx.x; i < 320u + 640u; i += blockDim.x) {
+        const bool wide = i >= 320u;
+        const uint32_t j = wide ? i - 320u : i;
+        const int k = min((int)(wide ? j >> 6 : j >> 5), 8);
+        const uint32_t aa = wide ? min((j >> 3) & 7u, 4u) : min((j & 31u) / 5u, 4u);
+        const uint32_t ab = wide ? min(j & 7u, 4u) : (j & 31u) % 5u;
+        (wide ? mvs : mvj)[j] = (uint8_t)(move_of(k, aa, false) * scale_a + move_of(k, ab, true) * scale_b);
     }
     if (threadIdx.x >= 96 && threadIdx.x < 96 + 20) {
         const int row = threadIdx.x - 96, k = row >> 1, nl = (row & 1) + 1;
@@ -914,33 +932,31 @@ __device__ __forceinline__ void slip_int_build_luts(uint8_t* base, const SlipE& 
         }
         sl[row * 4 + 0] = t[0]; sl[row * 4 + 1] = t[1]; sl[row * 4 + 2] = t[2]; sl[row * 4 + 3] = t[3];
     }
+    const uint32_t low = (1u << (32 - bits)) - 1u;
     for (uint32_t b = threadIdx.x; b < nb; b += blockDim.x) {
-        const uint32_t lo = b << (32 - bits), hi = lo | ((1u << (32 - bits)) - 1u);
+        const uint32_t lo = b << (32 - bits), hi = lo | low;
         const double ulo = u_from_rng32(lo), uhi = u_from_rng32(hi);
         uint32_t kl = 0, kh = 0;
 #pragma unroll
         for (int j = 0; j < 9; ++j) { kl += E.e[j] <= ulo ? 1u : 0u; kh += E.e[j] <= uhi ? 1u : 0u; }
         uint32_t thr = 0xFFFFFFFFu;
-        if (kh == kl + 1u) thr = (uint32_t)(slip_thr(E.e[kl]) - 1ull);     // the step lies inside (lo, hi]
+        if (kh == kl + 1u) thr = (uint32_t)(slip_thr(E.e[kl]) - 1ull);     // the step lies inside (lo, hi]: thr in [lo, hi)
         else if (kh != kl) kl = 9u;
-        klo[b] = (uint8_t)kl;
-        kthr[b] = thr;
+        kt[b] = (kl << (32 - bits)) + (low - (thr & low));
     }
 }
 __device__ __forceinline__ SlipInt slip_int_ctx(const uint8_t* base, int bits)
 {
-    const uint32_t b = smem_u32(base), n = 1u << bits;
-    SlipInt f = { b + n * 4u + 320u, b, b + n * 5u + 320u, b + n * 5u + 400u, b + n * 4u, (uint32_t)(32 - bits) };
+    const uint32_t b = smem_u32(base), n = 1u << bits, m = b + n * 4u + 320u;
+    SlipInt f = { b, m, m + 80u, m + 160u, m + 480u, b + n * 4u, (uint32_t)(32 - bits), (1u << (32 - bits)) - 1u };
     return f;
 }
 // combination index of a 32-bit draw: 0 .. 8, or 9 = walk (undecided bucket, "no sum exceeds u", or a listed draw)
 __device__ __forceinline__ uint32_t slip_int_k(const SlipInt& f, const SlipDanger& dg, uint32_t r32)
 {
-    const uint32_t b = r32 >> f.shift;
-    uint32_t k = lds_u8_r(f.klo + b);
-    uint32_t t;
-    asm("ld.shared.u32 %0, [%1];" : "=r"(t) : "r"(f.kthr + b * 4u));
-    k += r32 > t ? 1u : 0u;
+    uint32_t e;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(f.kt + (r32 >> f.shift) * 4u));
+    uint32_t k = (e + (r32 & f.mask)) >> f.shift;
     if (dg.n) {                                                // kernel-uniform; empty for ordinary slip_prob values
 #pragma unroll 1
         for (uint32_t i = 0; i < dg.n; ++i) k = r32 == dg.r[i] ? 9u : k;
@@ -965,17 +981,13 @@ __device__ __forceinline__ uint4 lds_v4_r(uint32_t addr)
     asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
     return v;
 }
-// One env-step with a 32-bit draw.  walk == true: the result is void, the caller takes the reference's walk.
-// CLAMP_ACT: the action values come from a caller's stream (Philox-decoded and policy-table actions are < 5 already).
-template <bool CLAMP_ACT>
-__device__ __forceinline__ TblOut table_step_slip_int(const TblCtx& c, const SlipInt& f, const SlipDanger& dg, uint32_t s,
-                                                      uint32_t aa, uint32_t ab, uint32_t r32, uint32_t rsel4, bool& walk)
+// One env-step with a 32-bit draw whose combination k (slip_int_k, < 9) and move pair (mv = byte offset of the pair
+// inside the table row, from mva + mvb, mvj or mvs) the caller has looked up.
+__device__ __forceinline__ TblOut table_step_slip_int_at(const TblCtx& c, const SlipInt& f, uint32_t s, uint32_t k, uint32_t mv,
+                                                         uint32_t r32, uint32_t rsel4)
 {
     const uint32_t obsi = min(s & 0xFFFFu, c.last / 100u);
-    if (CLAMP_ACT) { aa = min(aa, 4u); ab = min(ab, 4u); }
-    const uint32_t k = slip_int_k(f, dg, r32);
-    walk = k >= 9u;
-    uint32_t ent = c.tbl + obsi * 200u + lds_u8_r(f.mva + k * 8u + aa) + lds_u8_r(f.mvb + k * 8u + ab);
+    uint32_t ent = c.tbl + obsi * 200u + mv;
     int32_t e = lds_s16_r(ent);
     if ((uint32_t)e & 0x3000u) {                               // 3 % of the (state, move pair)s: 2 or 4 outcomes
         const uint32_t nl = ((uint32_t)e >> 12) & 3u;
@@ -985,6 +997,28 @@ __device__ __forceinline__ TblOut table_step_slip_int(const TblCtx& c, const Sli
         e = lds_s16_r(ent);
     }
     return table_finish(c, s, e, rsel4);
+}
+// Separate action values (kernels with a folded policy).  walk == true: the result is void, the caller takes the
+// reference's walk.  CLAMP_ACT: the action values come from a caller's stream (Philox-decoded and policy-table actions
+// are < 5 already).
+template <bool CLAMP_ACT>
+__device__ __forceinline__ TblOut table_step_slip_int(const TblCtx& c, const SlipInt& f, const SlipDanger& dg, uint32_t s,
+                                                      uint32_t aa, uint32_t ab, uint32_t r32, uint32_t rsel4, bool& walk)
+{
+    if (CLAMP_ACT) { aa = min(aa, 4u); ab = min(ab, 4u); }
+    const uint32_t k = slip_int_k(f, dg, r32);
+    walk = k >= 9u;
+    return table_step_slip_int_at(c, f, s, k, lds_u8_r(f.mva + k * 8u + aa) + lds_u8_r(f.mvb + k * 8u + ab), r32, rsel4);
+}
+// The joint action as ONE index: WIDE = false: ja = aa * 5 + ab < 25 (the Philox joint action mulhi(w, 25));
+// WIDE = true: aa * 8 + ab < 64 (two 3-bit fields of caller-supplied action bytes).
+template <bool WIDE>
+__device__ __forceinline__ TblOut table_step_slip_int_j(const TblCtx& c, const SlipInt& f, const SlipDanger& dg, uint32_t s,
+                                                        uint32_t j, uint32_t r32, uint32_t rsel4, bool& walk)
+{
+    const uint32_t k = slip_int_k(f, dg, r32);
+    walk = k >= 9u;
+    return table_step_slip_int_at(c, f, s, k, lds_u8_r((WIDE ? f.mvs + k * 64u : f.mvj + k * 32u) + j), r32, rsel4);
 }
 
 // The reference's walk as an out-of-line call for the integer fast path's (in practice never taken) fallback: inlined
@@ -1080,7 +1114,7 @@ k_step_table_slip_i(const PitchDev P, const uint16_t* __restrict__ gtable, uint3
     if (two) x1 = load_group_slip<PHILOX>(st4, a4, b4, r4, d4, g + stride);
     wait_table(&bar);
     launder(c.tbl); launder(c.isd); launder(sc.prt);
-    launder(sf.klo); launder(sf.kthr); launder(sf.mva); launder(sf.mvb); launder(sf.sl);
+    launder(sf.kt); launder(sf.mva); launder(sf.mvb); launder(sf.mvj); launder(sf.mvs); launder(sf.sl);
     launder(pol.pol_a); launder(pol.pol_b);
     auto do_group = [&](GroupS& x, int64_t gg) {
         if (PHILOX) {
@@ -1093,17 +1127,22 @@ k_step_table_slip_i(const PitchDev P, const uint16_t* __restrict__ gtable, uint3
         const uint32_t sv[4] = { x.s.x, x.s.y, x.s.z, x.s.w };
         const uint32_t r32[4] = { x.d.x, x.d.y, x.d.z, x.d.w };
         uint32_t so[4], oo[4], ro[4], rr[4], ff[4];
+        // both players' action bytes as one index per env, byte-parallel: aa * 8 + ab (3-bit fields; > 4 acts as 4)
+        const uint32_t j4 = ((x.a & 0x07070707u) << 3) | (x.b & 0x07070707u);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
+            const uint32_t rsel4 = __byte_perm(rs4, 0, 0x4440 + e);
+            bool walk;
+            TblOut o;
             uint32_t aa = __byte_perm(x.a, 0, 0x4440 + e), ab = __byte_perm(x.b, 0, 0x4440 + e);
             if (pol.pol_a | pol.pol_b) {                     // warp-uniform
                 const uint32_t cs = min(sv[e] & 0xFFFFu, c.last / 100u);
                 if (pol.pol_a) aa = lds_u8_r(pol.pol_a + cs);
                 if (pol.pol_b) ab = lds_u8_r(pol.pol_b + cs);
+                o = table_step_slip_int<true>(c, sf, dg, sv[e], aa, ab, r32[e], rsel4, walk);
+            } else {
+                o = table_step_slip_int_j<true>(c, sf, dg, sv[e], __byte_perm(j4, 0, 0x4440 + e), r32[e], rsel4, walk);
             }
-            const uint32_t rsel4 = __byte_perm(rs4, 0, 0x4440 + e);
-            bool walk;
-            TblOut o = table_step_slip_int<true>(c, sf, dg, sv[e], aa, ab, r32[e], rsel4, walk);
             if (walk) o = table_step_slip_walk(c, sc, sv[e], aa, ab, r32[e], rsel4);     // (in practice never)
             so[e] = o.state; oo[e] = o.obs; rr[e] = __float_as_uint((float)(flip ? -o.rew_i : o.rew_i));
             ro[e] = o.reset_obs; ff[e] = o.flags;

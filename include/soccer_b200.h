@@ -457,7 +457,7 @@ int soccer_policy_eval(const soccer_pitch *pitch, const int8_t *policy_a, const 
  *     bytes, zero-filled once before the first call (with a barrier after the fill);
  *   epoch: 1, 2, 3 ... incremented by every rank on every call (all ranks make the same sequence of calls);
  *   stats[6]: in = this rank's vector, out = the sum over all ranks.  world <= 16.
- * A peer that never arrives traps the waiting kernel after ~2 s instead of hanging the GPU. */
+ * A peer that never arrives traps the waiting kernel after ~20 s instead of hanging the GPU. */
 int soccer_stats_allreduce_p2p_bytes_host(int64_t *bytes);
 int soccer_stats_allreduce_p2p(const uint64_t *peer_ptrs, int32_t rank, int32_t world, uint64_t epoch,
                                unsigned long long *stats, soccer_stream_t stream);

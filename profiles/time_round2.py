@@ -157,3 +157,19 @@ if "k2" in what:
             del e
         del bufs
         torch.cuda.empty_cache()
+
+if "k2slip" in what:        # A/B of library variants (SOCCER_B200_LIB): K2 slip 0.2, table (5x4) and rules (7x5)
+    tag = os.environ.get("SOCCER_B200_LIB", "default").split("/")[-1]
+    for logn, K in ((20, 64), (22, 16)):
+        n = 1 << logn
+        bufs = (torch.empty((K, n), dtype=torch.int32, device=dev), torch.empty((K, n), dtype=torch.float32, device=dev),
+                torch.empty((K, n), dtype=torch.uint8, device=dev))
+        for name, kw in (("table 5x4", dict(kernel="table")), ("rules 7x5", dict(kernel="rules", width=7, height=5))):
+            e = SoccerVecEnv(n, device=dev, rng_mode="philox", slip_prob=0.2, **kw)
+            e.reset()
+            e.rollout(64, want_streams=False)       # play in
+            ms = timed(lambda i: e.rollout(K, out=bufs), 8, warm=2)
+            report(f"[{tag}] K2 slip 0.2 {name} n=2^{logn} K={K}", n * K, ms, 9.125)
+            del e
+        del bufs
+        torch.cuda.empty_cache()
