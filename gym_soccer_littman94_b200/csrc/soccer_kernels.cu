@@ -102,6 +102,7 @@ int make_pitch_dev(const soccer_pitch* p, PitchDev* d)
     const int rc = fill_info(p, &info);
     if (rc) return rc;
     d->w = p->width; d->H = p->height; d->F = info.n_field_cells; d->Fm1 = d->F - 1; d->nS = info.nS;
+    d->nSm1 = (uint32_t)info.nS - 1u; d->tlast = (uint32_t)info.nS * 100u - 1u;
     d->goal_row_mask = 0;
     for (int i = 0; i < info.n_goal_rows; ++i) d->goal_row_mask |= 1u << info.goal_rows[i];
     // injected 2-bit draw r -> isd index floor(n_isd * (r+0.5)/4): r for 4 starts, r>>1 for 2
@@ -230,8 +231,11 @@ k_step_fast(const PitchDev P, uint32_t* __restrict__ state, const uint8_t* __res
 
 // K1 for slip_prob > 0 on ANY pitch (rules inline): 32-bit draws -- the injected rng32 stream or Philox -- decided by
 // integer thresholds and resolved byte-parallel (step4_slip_int); 24 B / env-step (19 with Philox draws).
+#ifndef SOCCER_FAST_SLIP_MINBLOCKS
+#define SOCCER_FAST_SLIP_MINBLOCKS 2
+#endif
 template <bool RESET_OBS, bool PHILOX>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, SOCCER_FAST_SLIP_MINBLOCKS)
 k_step_fast_slip(const PitchDev P, const RulesSlipArgs sa, uint32_t* __restrict__ state, const uint8_t* __restrict__ act_a,
                  const uint8_t* __restrict__ act_b, const uint8_t* __restrict__ rng, const uint32_t* __restrict__ draw,
                  int32_t* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ flags,
@@ -241,11 +245,11 @@ k_step_fast_slip(const PitchDev P, const RulesSlipArgs sa, uint32_t* __restrict_
     __shared__ __align__(16) double prt[kPrtDoubles];
     __shared__ __align__(16) uint8_t ilut[slip_int_lut_bytes(kRulesSlipLutBits)];
     slip_build_prt(prt, P);
-    slip_int_build_luts(ilut, sa.E, P, kRulesSlipLutBits, 1u, 16u);
+    slip_int_build_luts(ilut, sa.E, P, sa.dg, kRulesSlipLutBits, 1u, 16u);
     build_cand_lut(lut, P);                      // ends with __syncthreads()
     const Isd4 I = make_isd4(P);
     const SlipCtx sc = { (uint32_t)__cvta_generic_to_shared(prt), slip_first_k(P) };
-    const SlipInt fi = slip_int_ctx(ilut, kRulesSlipLutBits);
+    const SlipInt fi = slip_int_ctx(ilut, slip_bits(kRulesSlipLutBits));
     uint4* st4 = reinterpret_cast<uint4*>(state);
     const uint32_t* a4 = reinterpret_cast<const uint32_t*>(act_a);
     const uint32_t* b4 = reinterpret_cast<const uint32_t*>(act_b);
@@ -274,7 +278,7 @@ k_step_fast_slip(const PitchDev P, const RulesSlipArgs sa, uint32_t* __restrict_
         const uint32_t sv[4] = { x.s.x, x.s.y, x.s.z, x.s.w };
         const uint32_t r32[4] = { x.d.x, x.d.y, x.d.z, x.d.w };
         Step4 o;
-        step4_slip_int<RESET_OBS, true>(P, I, lut, fi, sa.dg, sc, sv, ((x.a & 0x07070707u) << 3) | (x.b & 0x07070707u), r32, x.r, o);
+        step4_slip_int<RESET_OBS, true>(P, I, lut, fi, sc, sv, ((x.a & 0x07070707u) << 3) | (x.b & 0x07070707u), r32, x.r, o);
         st_keep(st4 + g, make_uint4(o.s[0], o.s[1], o.s[2], o.s[3]));
         st_stream(o4 + g, make_uint4(o.obs[0], o.obs[1], o.obs[2], o.obs[3]));
         st_stream(w4 + g, make_uint4(o.rew[0], o.rew[1], o.rew[2], o.rew[3]));
@@ -1142,14 +1146,16 @@ int step_table_slip_impl(const PitchDev& P, int64_t bytes, const soccer_step_arg
         const int64_t smem_i = smem_w + slip_int_lut_bytes(lut_bits);
         const bool queued = a->slip_index && f64 && smem_q <= 227 * 1024 - 1024;
         const bool integer = !f64 && dg_ok && smem_i <= 227 * 1024 - 1536 && !soccer_force_slip_walk();
-#define SOCCER_LAUNCH_SLIP_I(RO, PH)                                                                      \
+#define SOCCER_LAUNCH_SLIP_I2(RO, PH, POL)                                                                \
         do {                                                                                              \
-            const int e0 = allow_big_smem(k_step_table_slip_i<RO, PH>, smem_i);                           \
+            const int e0 = allow_big_smem(k_step_table_slip_i<RO, PH, POL>, smem_i);                      \
             if (e0) return e0;                                                                            \
-            k_step_table_slip_i<RO, PH><<<table_grid(n_groups, slip_i_threads<PH>()), slip_i_threads<PH>(), (size_t)smem_i, st>>>(  \
-                P, a->table, (uint32_t)bytes, E, dg, lut_bits, a->state, act_a, act_b,                     \
+            k_step_table_slip_i<RO, PH, POL><<<table_grid(n_groups, slip_i_threads<PH>()), slip_i_threads<PH>(), (size_t)smem_i, st>>>(  \
+                P, a->table, (uint32_t)bytes, E, dg, slip_bits(lut_bits), a->state, act_a, act_b,         \
                 a->rng8, a->rng32, a->obs, a->reward, a->flags, a->reset_obs, n_groups, ex);              \
         } while (0)
+#define SOCCER_LAUNCH_SLIP_I(RO, PH)                                                                      \
+        do { if (pol_bytes) SOCCER_LAUNCH_SLIP_I2(RO, PH, true); else SOCCER_LAUNCH_SLIP_I2(RO, PH, false); } while (0)
 #define SOCCER_LAUNCH_SLIP_T(RO, DRAW)                                                                    \
         do {                                                                                              \
             if (queued) {                                                                                 \
@@ -1448,7 +1454,7 @@ int soccer_rollout_table_policy(const soccer_pitch* pitch, const uint16_t* table
                 if (e0) return e0;                                                                       \
                 const int e1 = launch_pdl(k_rollout_table_slipi<VEC, STR, POL>, table_grid(ITEMS, kRolloutSlipThreads), \
                                           kRolloutSlipThreads, (size_t)smem_i, st, P, table, (uint32_t)bytes, \
-                                          E, dg, lut_bits, policy_a, policy_b, ra);                      \
+                                          E, dg, slip_bits(lut_bits), policy_a, policy_b, ra);                      \
                 if (e1) return e1;                                                                       \
             } while (0)
 #define SOCCER_PICK_ROLLOUT_I(POL)                                                                       \

@@ -39,18 +39,18 @@ __device__ __noinline__ StepOut step_slip_call(const PitchDev& P, const uint8_t*
 // else aa * 5 + ab (the Philox joint action); the move pair of (combination, joint action) is ONE byte ma | mb << 4.
 template <bool RESET_OBS, bool WIDE>
 __device__ __forceinline__ void step4_slip_int(const PitchDev& P, const Isd4& I, const uint8_t* __restrict__ lut,
-                                               const SlipInt& f, const SlipDanger& dg, const SlipCtx& sc, const uint32_t sv[4],
+                                               const SlipInt& f, const SlipCtx& sc, const uint32_t sv[4],
                                                uint32_t J4, const uint32_t r32[4], uint32_t RST, Step4& o)
 {
     uint32_t mv[4], r4[4], r2[4], walk = 0;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-        const uint32_t k = slip_int_k(f, dg, r32[e]);
+        const uint32_t k = slip_int_k(f, r32[e]);
         walk |= (k >= 9u ? 1u : 0u) << e;
         const uint32_t kc = min(k, 8u);
-        mv[e] = lds_u8_r((WIDE ? f.mvs + kc * 64u : f.mvj + kc * 32u) + byte_of(J4, e));
-        const uint32_t t2 = lds_u32_r(f.sl + kc * 32u);                      // 2-way row: one threshold
-        const uint4 t4 = lds_v4_r(f.sl + kc * 32u + 16u);                    // 4-way row: three
+        mv[e] = lds_u8_r((WIDE ? f.mvs() + kc * 64u : f.mvj() + kc * 32u) + byte_of(J4, e));
+        const uint32_t t2 = lds_u32_r(f.sl() + kc * 32u);                      // 2-way row: one threshold
+        const uint4 t4 = lds_v4_r(f.sl() + kc * 32u + 16u);                    // 4-way row: three
         r2[e] = r32[e] > t2 ? 2u : 0u;                                       // draw value 2 * slot
         r4[e] = (r32[e] > t4.x ? 1u : 0u) + (r32[e] > t4.y ? 1u : 0u) + (r32[e] > t4.z ? 1u : 0u);
     }
@@ -115,7 +115,7 @@ struct TableStepper {
                 philox_actions(word[e], aa, ab);
                 // SIM:187-188: a table policy picks the player's action from the CURRENT observation;
                 // the other player's action and the draws stay the Philox ones
-                const uint32_t cur = min(s[e] & 0xFFFFu, c.last / 100u);
+                const uint32_t cur = min(s[e] & 0xFFFFu, c.maxobs);
                 if (POLICY && pol_a) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(aa) : "r"(pol_a + cur));
                 if (POLICY && pol_b) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(ab) : "r"(pol_b + cur));
                 jr = aa * 20u + ab * 4u + (jr & 3u);
@@ -142,36 +142,51 @@ template <bool POLICY>
 struct TableSlipIntStepper {
     static constexpr bool kCollective = false, kHasPolicy = POLICY;
     static constexpr int kBlock = SOCCER_K2_SLIPI_BLOCK;
-    TblCtx c; SlipCtx sc; SlipInt sf; SlipDanger dg;
+    TblCtx c; SlipCtx sc; SlipInt sf;
     uint32_t pol_a, pol_b;
     __device__ __forceinline__ uint32_t timestep(uint32_t s) const { return s >> 16; }
     template <int VEC>
     __device__ __forceinline__ void step(uint32_t* s, const uint32_t* word, uint32_t* oo, uint32_t* rr,
                                          uint32_t& fw, int32_t& net, bool flip) const
     {
-        uint32_t ff[4] = { 0, 0, 0, 0 };
+        uint32_t ff[4] = { 0, 0, 0, 0 }, so[4] = { 0, 0, 0, 0 }, ri[4] = { 0, 0, 0, 0 }, walks = 0;
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
             const uint32_t r32 = philox_r32(word[e]), rsel4 = word[e] & 0xCu;
             bool walk;
             TblOut o;
-            uint32_t aa, ab;
             if (POLICY) {
+                uint32_t aa, ab;
                 philox_actions(word[e], aa, ab);
-                const uint32_t cur = min(s[e] & 0xFFFFu, c.last / 100u);
+                const uint32_t cur = min(s[e] & 0xFFFFu, c.maxobs);
                 if (pol_a) aa = lds_u8_r(pol_a + cur);
                 if (pol_b) ab = lds_u8_r(pol_b + cur);
-                o = table_step_slip_int<false>(c, sf, dg, s[e], aa, ab, r32, rsel4, walk);
+                o = table_step_slip_int<false>(c, sf, s[e], aa, ab, r32, rsel4, walk);
             } else {
                 // the joint action mulhi(w, 25) indexes the (combination, joint action) -> move pair table directly
-                o = table_step_slip_int_j<false>(c, sf, dg, s[e], philox_ja(word[e]), r32, rsel4, walk);
+                o = table_step_slip_int_j<false>(c, sf, s[e], philox_ja(word[e]), r32, rsel4, walk);
             }
-            if (walk) {                                                       // (in practice never)
-                if (!POLICY) philox_actions(word[e], aa, ab);
-                o = table_step_slip_walk(c, sc, s[e], aa, ab, r32, rsel4);
+            walks |= walk ? 1u << e : 0u;
+            so[e] = o.state; oo[e] = o.obs; ri[e] = (uint32_t)o.rew_i; ff[e] = o.flags;
+        }
+        if (walks) {                                                          // (in practice never): ONE test per step
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                if (!((walks >> e) & 1u)) continue;
+                uint32_t aa, ab;
+                philox_actions(word[e], aa, ab);
+                const uint32_t cur = min(s[e] & 0xFFFFu, c.maxobs);
+                if (POLICY && pol_a) aa = lds_u8_r(pol_a + cur);
+                if (POLICY && pol_b) ab = lds_u8_r(pol_b + cur);
+                const TblOut o = table_step_slip_walk(c, sc, s[e], aa, ab, philox_r32(word[e]), word[e] & 0xCu);
+                so[e] = o.state; oo[e] = o.obs; ri[e] = (uint32_t)o.rew_i; ff[e] = o.flags;
             }
-            s[e] = o.state; oo[e] = o.obs; rr[e] = __float_as_uint((float)(flip ? -o.rew_i : o.rew_i)); ff[e] = o.flags;
-            net += o.rew_i;
+        }
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            s[e] = so[e];
+            rr[e] = __float_as_uint((float)(flip ? -(int32_t)ri[e] : (int32_t)ri[e]));
+            net += (int32_t)ri[e];
         }
         fw = VEC == 4 ? pack4(ff[0], ff[1], ff[2], ff[3]) : ff[0];
     }
@@ -246,7 +261,7 @@ struct RulesStepper {
 // byte-parallel (step4_slip_int)
 struct RulesSlipIntStepper {
     static constexpr bool kCollective = false, kHasPolicy = false;
-    const PitchDev& P; const uint8_t* lut; Isd4 I; SlipCtx sc; SlipInt fi; SlipDanger dg;
+    const PitchDev& P; const uint8_t* lut; Isd4 I; SlipCtx sc; SlipInt fi;
     __device__ __forceinline__ uint32_t timestep(uint32_t s) const { return (s >> 16) & 0xFFu; }
     template <int VEC>
     __device__ __forceinline__ void step(uint32_t* s, const uint32_t* word, uint32_t* oo, uint32_t* rr,
@@ -261,7 +276,7 @@ struct RulesSlipIntStepper {
             rst |= (word[e] & 0xCu) << (8 * e);
         }
         Step4 o;
-        step4_slip_int<false, false>(P, I, lut, fi, dg, sc, s, pack4(ja[0], ja[1], ja[2], ja[3]), r32, rst, o);
+        step4_slip_int<false, false>(P, I, lut, fi, sc, s, pack4(ja[0], ja[1], ja[2], ja[3]), r32, rst, o);
 #pragma unroll
         for (int e = 0; e < 4; ++e) { s[e] = o.s[e]; oo[e] = o.obs[e]; rr[e] = o.rew[e]; }
         fw = o.flags4;
@@ -466,7 +481,7 @@ constexpr int kRolloutSlipThreads = SOCCER_K2_SLIPI_THREADS;
 template <int VEC, bool STREAMS, bool POLICY>
 __global__ void __launch_bounds__(kRolloutSlipThreads, 1)
 k_rollout_table_slipi(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t table_bytes,
-                      const SlipE E, const SlipDanger dg, int lut_bits,
+                      const SlipE E, const SlipDanger dg, const SlipBits lut_bits,
                       const int8_t* __restrict__ policy_a, const int8_t* __restrict__ policy_b, const RolloutArgs a)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -479,17 +494,16 @@ k_rollout_table_slipi(const PitchDev P, const uint16_t* __restrict__ gtable, uin
     uint8_t* pa = smem_raw + table_bytes + 16, *pb = pa + pol_bytes;
     uint8_t* luts = pb + pol_bytes;
     slip_build_prt(prt, P);
-    slip_int_build_luts(luts, E, P, lut_bits);
+    slip_int_build_luts(luts, E, P, dg, lut_bits.bits);
     stage_table(smem_raw, gtable, table_bytes, &bar, P);                               // ends with __syncthreads()
     TableSlipIntStepper<POLICY> S;
     S.c = make_ctx(smem_raw, table_bytes, P);
     S.sc.prt = smem_u32(prt); S.sc.first_k = slip_first_k(P);
     S.sf = slip_int_ctx(luts, lut_bits);
-    S.dg = dg;
     S.pol_a = S.pol_b = 0;
     wait_table(&bar);
     launder(S.c.tbl); launder(S.c.isd); launder(S.sc.prt);
-    launder(S.sf.kt); launder(S.sf.mva); launder(S.sf.mvb); launder(S.sf.mvj); launder(S.sf.mvs); launder(S.sf.sl);
+    launder(S.sf.base);
     pdl_wait();
     if (POLICY) {
         stage_policies(pa, pb, policy_a, policy_b, P.nS);
@@ -600,12 +614,12 @@ k_rollout_slipi(const PitchDev P, const RolloutArgs a, const RulesSlipArgs sa)
     __shared__ __align__(16) uint8_t ilut[slip_int_lut_bytes(kRulesSlipLutBits)];
     __shared__ BlkStats blk;
     slip_build_prt(prt, P);
-    slip_int_build_luts(ilut, sa.E, P, kRulesSlipLutBits, 1u, 16u);
+    slip_int_build_luts(ilut, sa.E, P, sa.dg, kRulesSlipLutBits, 1u, 16u);
     build_cand_lut(lut, P);
     if (threadIdx.x < 5) blk.v[threadIdx.x] = 0;
     __syncthreads();
     const SlipCtx sc = { (uint32_t)__cvta_generic_to_shared(prt), slip_first_k(P) };
-    const RulesSlipIntStepper S = { P, lut, make_isd4(P), sc, slip_int_ctx(ilut, kRulesSlipLutBits), sa.dg };
+    const RulesSlipIntStepper S = { P, lut, make_isd4(P), sc, slip_int_ctx(ilut, slip_bits(kRulesSlipLutBits)) };
     rollout_body<4, STREAMS>(S, a, &blk);
 }
 

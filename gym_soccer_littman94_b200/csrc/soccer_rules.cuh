@@ -25,6 +25,7 @@ struct PitchDev {
     int32_t  F;              // w*H
     int32_t  Fm1;
     int32_t  nS;             // 1 + 2F(F-1)
+    uint32_t nSm1, tlast;    // nS - 1 and nS * 100 - 1 (last entry of the step table): clamps read from the constant bank
     uint32_t goal_row_mask;  // bit r set iff r in goal_rows (SIM:60)
     uint32_t isd_state[4];   // packed start states (2-start pitches: s0,s0,s1,s1 so idx = r)
     int32_t  isd_obs[4];

@@ -95,7 +95,7 @@ __device__ __forceinline__ void wait_table(uint64_t* bar)
 }
 
 // One env-step through the table.  `jr` = (aa*5+ab)*4 + r (0..99), `rsel4` = 4 * reset draw.
-struct TblCtx { uint32_t tbl, isd, last; };    // shared-window addresses of the table / the isd words; last entry index
+struct TblCtx { uint32_t tbl, isd, last, maxobs; };    // shared-window addresses of the table / the isd words; last entry index; nS - 1
 struct TblOut { uint32_t state, obs, flags; int32_t rew_i; uint32_t reset_obs; };
 // everything after the table look-up: observation, reward, done / truncated, fused reset (SIM:399-424, 493)
 __device__ __forceinline__ TblOut table_finish(const TblCtx& c, uint32_t s, int32_t e, uint32_t rsel4)
@@ -196,7 +196,7 @@ struct LdGlobal {
 __device__ __forceinline__ TblOut table_step_slip(const TblCtx& c, const SlipCtx& sc, uint32_t s, uint32_t aa, uint32_t ab,
                                                   double u, uint32_t rsel4)
 {
-    const uint32_t row = c.tbl + min(s & 0xFFFFu, c.last / 100u) * 200u;
+    const uint32_t row = c.tbl + min(s & 0xFFFFu, c.maxobs) * 200u;
     aa = min(aa, 4u); ab = min(ab, 4u);
     // shared addresses of the r = 0 entry of a move pair: row + (ma * 5 + mb) * 8
     const uint32_t ra[3] = { row + aa * 40u, row + slip_move(aa, 0) * 40u, row + slip_move(aa, 1) * 40u };
@@ -242,7 +242,8 @@ __device__ __forceinline__ TblCtx make_ctx(const uint8_t* smem, uint32_t table_b
     TblCtx c;
     c.tbl = smem_u32(smem);
     c.isd = c.tbl + table_bytes;
-    c.last = (uint32_t)P.nS * 100u - 1u;
+    c.last = P.tlast;
+    c.maxobs = P.nSm1;
     return c;
 }
 
@@ -325,7 +326,7 @@ __device__ __forceinline__ void table_step_group(const TblCtx& c, const Group4& 
     for (int e = 0; e < 4; ++e) {
         uint32_t jr = __byte_perm(jr4, 0, 0x4440 + e);
         if (POLICY) {
-            const uint32_t cur = min(sv[e] & 0xFFFFu, c.last / 100u);
+            const uint32_t cur = min(sv[e] & 0xFFFFu, c.maxobs);
             uint32_t aa = __byte_perm(x.a, 0, 0x4440 + e) & 7u, ab = __byte_perm(x.b, 0, 0x4440 + e) & 7u;
             if (pol.pol_a) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(aa) : "r"(pol.pol_a + cur));
             if (pol.pol_b) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(ab) : "r"(pol.pol_b + cur));
@@ -687,7 +688,7 @@ k_step_table_slip(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             uint32_t aa = __byte_perm(x.a, 0, 0x4440 + e), ab = __byte_perm(x.b, 0, 0x4440 + e);
-            const uint32_t cur = min(sv[e] & 0xFFFFu, c.last / 100u);
+            const uint32_t cur = min(sv[e] & 0xFFFFu, c.maxobs);
             if (pol.pol_a) aa = lds_u8_r(pol.pol_a + cur);
             if (pol.pol_b) ab = lds_u8_r(pol.pol_b + cur);
             const TblOut o = table_step_slip(c, sc, sv[e], aa, ab, u[e], __byte_perm(rs4, 0, 0x4440 + e));
@@ -806,7 +807,7 @@ __device__ __forceinline__ TblOut table_step_slip_fast(const TblCtx& c, const Sl
                                                        uint32_t aa, uint32_t ab, double u, uint32_t r32, uint32_t rsel4,
                                                        bool& defer)
 {
-    const uint32_t obsi = min(s & 0xFFFFu, c.last / 100u);
+    const uint32_t obsi = min(s & 0xFFFFu, c.maxobs);
     aa = min(aa, 4u); ab = min(ab, 4u);
     const uint32_t dm = lds_u8_r(f.fc + obsi * 25u + aa * 5u + ab);                  // bit k: pick k must be walked
     uint32_t k = 0;
@@ -889,18 +890,33 @@ __device__ __forceinline__ void stage_table_and_index(uint8_t* smem, const uint1
 //                          row (table kernels), ma | mb << 4 (rules kernels)
 //   mvs[k][aa * 8 + ab]    (10 x 64 bytes) the same indexed by two 3-bit action fields (caller-supplied action bytes,
 //                          combined byte-parallel for the four envs of a thread); actions > 4 act as 4
-struct SlipInt { uint32_t kt, mva, mvb, mvj, mvs, sl, shift, mask; };   // shared-window addresses; shift = 32 - bits
+// ONE shared-window base address (one register; every look-up is [base + index + immediate]): the small tables first, the
+// bucket table behind them.  shift = 32 - bits, mask = 2^shift - 1.
+struct SlipInt {
+    uint32_t base, shift, mask;
+    __device__ __forceinline__ uint32_t sl() const { return base; }
+    __device__ __forceinline__ uint32_t mva() const { return base + 320u; }
+    __device__ __forceinline__ uint32_t mvb() const { return base + 400u; }
+    __device__ __forceinline__ uint32_t mvj() const { return base + 480u; }
+    __device__ __forceinline__ uint32_t mvs() const { return base + 800u; }
+    __device__ __forceinline__ uint32_t kt() const { return base + 1440u; }
+};
 struct SlipDanger { uint32_t n; uint32_t r[12]; };             // draws that must take the walk (kernel parameter)
+// bucket shape as a kernel parameter (host-computed, so that shift and mask are constant-bank operands, not registers)
+struct SlipBits { int32_t bits; uint32_t shift, mask; };
+__host__ __device__ constexpr SlipBits slip_bits(int bits) { return SlipBits{ bits, (uint32_t)(32 - bits), (1u << (32 - bits)) - 1u }; }
 __host__ __device__ constexpr int slip_int_lut_bytes(int bits) { return (1 << bits) * 4 + 20 * 16 + 80 + 80 + 320 + 640; }
 // scale_a / scale_b: 40 / 8 = byte offsets inside a table row (table kernels), 1 / 16 = the move ids (rules kernels)
-__device__ __forceinline__ void slip_int_build_luts(uint8_t* base, const SlipE& E, const PitchDev& P, int bits,
+// dg: the listed draws do not cost the hot path anything -- their BUCKET is marked undecided (klo = 9), so every draw of
+// it takes the walk (<= 12 of 2^bits buckets, and none at all for ordinary slip_prob values).
+__device__ __forceinline__ void slip_int_build_luts(uint8_t* base, const SlipE& E, const PitchDev& P, const SlipDanger& dg, int bits,
                                                     uint32_t scale_a = 40u, uint32_t scale_b = 8u)
 {
     const uint32_t nb = 1u << bits;
-    uint32_t* kt = reinterpret_cast<uint32_t*>(base);
-    uint32_t* sl = kt + nb;
-    uint8_t* mva = reinterpret_cast<uint8_t*>(sl + 20 * 4);
+    uint32_t* sl = reinterpret_cast<uint32_t*>(base);
+    uint8_t* mva = base + 320;
     uint8_t* mvb = mva + 80; uint8_t* mvj = mvb + 80; uint8_t* mvs = mvj + 320;
+    uint32_t* kt = reinterpret_cast<uint32_t*>(base + 1440);
     auto move_of = [](int k, uint32_t a, bool second) {
         const int cmb = second ? combo_b(k) : combo_a(k);
         return cmb == 0 ? a : slip_move(a, cmb - 1);
@@ -942,26 +958,25 @@ __device__ __forceinline__ void slip_int_build_luts(uint8_t* base, const SlipE& 
         uint32_t thr = 0xFFFFFFFFu;
         if (kh == kl + 1u) thr = (uint32_t)(slip_thr(E.e[kl]) - 1ull);     // the step lies inside (lo, hi]: thr in [lo, hi)
         else if (kh != kl) kl = 9u;
+#pragma unroll
+        for (uint32_t i = 0; i < 12u; ++i)                                   // constant indices: dg stays in the constant bank
+            if (i < dg.n && (dg.r[i] >> (32 - bits)) == b) kl = 9u;
+        if (kl == 9u) thr = 0xFFFFFFFFu;
         kt[b] = (kl << (32 - bits)) + (low - (thr & low));
     }
 }
-__device__ __forceinline__ SlipInt slip_int_ctx(const uint8_t* base, int bits)
+__device__ __forceinline__ SlipInt slip_int_ctx(const uint8_t* base, const SlipBits& lb)
 {
-    const uint32_t b = smem_u32(base), n = 1u << bits, m = b + n * 4u + 320u;
-    SlipInt f = { b, m, m + 80u, m + 160u, m + 480u, b + n * 4u, (uint32_t)(32 - bits), (1u << (32 - bits)) - 1u };
+    SlipInt f = { smem_u32(base), lb.shift, lb.mask };
     return f;
 }
-// combination index of a 32-bit draw: 0 .. 8, or 9 = walk (undecided bucket, "no sum exceeds u", or a listed draw)
-__device__ __forceinline__ uint32_t slip_int_k(const SlipInt& f, const SlipDanger& dg, uint32_t r32)
+// combination index of a 32-bit draw: 0 .. 8, or 9 = walk (undecided bucket -- incl. the bucket of a listed draw -- or
+// "no sum exceeds u")
+__device__ __forceinline__ uint32_t slip_int_k(const SlipInt& f, uint32_t r32)
 {
     uint32_t e;
-    asm("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(f.kt + (r32 >> f.shift) * 4u));
-    uint32_t k = (e + (r32 & f.mask)) >> f.shift;
-    if (dg.n) {                                                // kernel-uniform; empty for ordinary slip_prob values
-#pragma unroll 1
-        for (uint32_t i = 0; i < dg.n; ++i) k = r32 == dg.r[i] ? 9u : k;
-    }
-    return k;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(f.kt() + (r32 >> f.shift) * 4u));
+    return (e + (r32 & f.mask)) >> f.shift;
 }
 __device__ __forceinline__ uint32_t lds_u32_r(uint32_t addr)
 {
@@ -986,12 +1001,12 @@ __device__ __forceinline__ uint4 lds_v4_r(uint32_t addr)
 __device__ __forceinline__ TblOut table_step_slip_int_at(const TblCtx& c, const SlipInt& f, uint32_t s, uint32_t k, uint32_t mv,
                                                          uint32_t r32, uint32_t rsel4)
 {
-    const uint32_t obsi = min(s & 0xFFFFu, c.last / 100u);
+    const uint32_t obsi = min(s & 0xFFFFu, c.maxobs);
     uint32_t ent = c.tbl + obsi * 200u + mv;
     int32_t e = lds_s16_r(ent);
     if ((uint32_t)e & 0x3000u) {                               // 3 % of the (state, move pair)s: 2 or 4 outcomes
         const uint32_t nl = ((uint32_t)e >> 12) & 3u;
-        const uint4 t = lds_v4_r(f.sl + (k * 2u + nl - 1u) * 16u);
+        const uint4 t = lds_v4_r(f.sl() + (k * 2u + nl - 1u) * 16u);
         const uint32_t slot = (r32 > t.x ? 1u : 0u) + (r32 > t.y ? 1u : 0u) + (r32 > t.z ? 1u : 0u);
         ent += slot * (nl == 1u ? 4u : 2u);                    // 2-way: draw value 2 * slot; 4-way: draw value slot
         e = lds_s16_r(ent);
@@ -1002,23 +1017,23 @@ __device__ __forceinline__ TblOut table_step_slip_int_at(const TblCtx& c, const 
 // reference's walk.  CLAMP_ACT: the action values come from a caller's stream (Philox-decoded and policy-table actions
 // are < 5 already).
 template <bool CLAMP_ACT>
-__device__ __forceinline__ TblOut table_step_slip_int(const TblCtx& c, const SlipInt& f, const SlipDanger& dg, uint32_t s,
+__device__ __forceinline__ TblOut table_step_slip_int(const TblCtx& c, const SlipInt& f, uint32_t s,
                                                       uint32_t aa, uint32_t ab, uint32_t r32, uint32_t rsel4, bool& walk)
 {
     if (CLAMP_ACT) { aa = min(aa, 4u); ab = min(ab, 4u); }
-    const uint32_t k = slip_int_k(f, dg, r32);
+    const uint32_t k = slip_int_k(f, r32);
     walk = k >= 9u;
-    return table_step_slip_int_at(c, f, s, k, lds_u8_r(f.mva + k * 8u + aa) + lds_u8_r(f.mvb + k * 8u + ab), r32, rsel4);
+    return table_step_slip_int_at(c, f, s, k, lds_u8_r(f.mva() + k * 8u + aa) + lds_u8_r(f.mvb() + k * 8u + ab), r32, rsel4);
 }
 // The joint action as ONE index: WIDE = false: ja = aa * 5 + ab < 25 (the Philox joint action mulhi(w, 25));
 // WIDE = true: aa * 8 + ab < 64 (two 3-bit fields of caller-supplied action bytes).
 template <bool WIDE>
-__device__ __forceinline__ TblOut table_step_slip_int_j(const TblCtx& c, const SlipInt& f, const SlipDanger& dg, uint32_t s,
+__device__ __forceinline__ TblOut table_step_slip_int_j(const TblCtx& c, const SlipInt& f, uint32_t s,
                                                         uint32_t j, uint32_t r32, uint32_t rsel4, bool& walk)
 {
-    const uint32_t k = slip_int_k(f, dg, r32);
+    const uint32_t k = slip_int_k(f, r32);
     walk = k >= 9u;
-    return table_step_slip_int_at(c, f, s, k, lds_u8_r((WIDE ? f.mvs + k * 64u : f.mvj + k * 32u) + j), r32, rsel4);
+    return table_step_slip_int_at(c, f, s, k, lds_u8_r((WIDE ? f.mvs() + k * 64u : f.mvj() + k * 32u) + j), r32, rsel4);
 }
 
 // The reference's walk as an out-of-line call for the integer fast path's (in practice never taken) fallback: inlined
@@ -1026,7 +1041,7 @@ __device__ __forceinline__ TblOut table_step_slip_int_j(const TblCtx& c, const S
 __device__ __noinline__ uint2 table_step_slip_call(uint32_t tbl, uint32_t isd, uint32_t last, uint32_t prt, uint32_t first_k,
                                                    uint32_t s, uint32_t aa, uint32_t ab, uint32_t r32, uint32_t rsel4)
 {
-    const TblCtx c = { tbl, isd, last };
+    const TblCtx c = { tbl, isd, last, last / 100u };
     const SlipCtx sc = { prt, first_k };
     const TblOut o = table_step_slip(c, sc, s, aa, ab, u_from_rng32(r32), rsel4);
     // state | obs, flags, reward and the post-reset observation packed into the second word
@@ -1068,15 +1083,19 @@ __device__ __forceinline__ GroupS load_group_slip(const uint4* st, const uint32_
 #ifndef SOCCER_SLIP_I_L2_PREFETCH
 #define SOCCER_SLIP_I_L2_PREFETCH 0    // iterations ahead of the register prefetch to pull into L2 (0 = off)
 #endif
+#ifndef SOCCER_K1_SLIP_WALK_MERGED
+#define SOCCER_K1_SLIP_WALK_MERGED 1   // one walk test per group of 4 envs (else one per env)
+#endif
 #ifndef SOCCER_SLIP_I_THREADS
-#define SOCCER_SLIP_I_THREADS 0        // 0: 512 for injected draws, 768 for Philox
+#define SOCCER_SLIP_I_THREADS 0        // 0: 512 (128 registers; at 768 threads = 80 registers the Philox variant loses 10 %)
 #endif
 template <bool PHILOX>
-constexpr int slip_i_threads() { return SOCCER_SLIP_I_THREADS ? SOCCER_SLIP_I_THREADS : (PHILOX ? 768 : 512); }
-template <bool RESET_OBS, bool PHILOX>
+constexpr int slip_i_threads() { return SOCCER_SLIP_I_THREADS ? SOCCER_SLIP_I_THREADS : 512; }
+// POLICY: a folded player (its table policy in shared memory, separate move look-ups); else both action bytes -> one index
+template <bool RESET_OBS, bool PHILOX, bool POLICY>
 __global__ void __launch_bounds__((slip_i_threads<PHILOX>()), 1)
 k_step_table_slip_i(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t table_bytes,
-                    const SlipE E, const SlipDanger dg, int lut_bits,
+                    const SlipE E, const SlipDanger dg, const SlipBits lut_bits,
                     uint32_t* __restrict__ state, const uint8_t* __restrict__ act_a, const uint8_t* __restrict__ act_b,
                     const uint8_t* __restrict__ rng, const uint32_t* __restrict__ draw, int32_t* __restrict__ obs,
                     float* __restrict__ reward, uint8_t* __restrict__ flags, int32_t* __restrict__ reset_obs, int64_t n_groups,
@@ -1085,18 +1104,18 @@ k_step_table_slip_i(const PitchDev P, const uint16_t* __restrict__ gtable, uint3
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ __align__(16) double prt[kPrtDoubles];
-    const bool has_pol = ex.policy_a || ex.policy_b;
+    const bool has_pol = POLICY && (ex.policy_a || ex.policy_b);
     const uint32_t pol_total = has_pol ? 2u * (((uint32_t)P.nS + 15u) & ~15u) : 0u;
     uint8_t* luts = smem_raw + table_bytes + 16 + pol_total;
     slip_build_prt(prt, P);
-    slip_int_build_luts(luts, E, P, lut_bits);
+    slip_int_build_luts(luts, E, P, dg, lut_bits.bits);
     stage_table(smem_raw, gtable, table_bytes, &bar, P);                                   // ends with __syncthreads()
     TblCtx c = make_ctx(smem_raw, table_bytes, P);
     SlipCtx sc = { smem_u32(prt), slip_first_k(P) };
     SlipInt sf = slip_int_ctx(luts, lut_bits);
     K1Policy pol = { 0u, 0u };
     if (has_pol) pol = stage_k1_policies(smem_raw + table_bytes + 16, ex.policy_a, ex.policy_b, P.nS);
-    const bool flip = pol.pol_a != 0u;
+    const bool flip = POLICY && pol.pol_a != 0u;
     uint4* st4 = reinterpret_cast<uint4*>(state);
     const uint32_t* a4 = reinterpret_cast<const uint32_t*>(act_a ? act_a : act_b);
     const uint32_t* b4 = reinterpret_cast<const uint32_t*>(act_b ? act_b : act_a);
@@ -1114,7 +1133,7 @@ k_step_table_slip_i(const PitchDev P, const uint16_t* __restrict__ gtable, uint3
     if (two) x1 = load_group_slip<PHILOX>(st4, a4, b4, r4, d4, g + stride);
     wait_table(&bar);
     launder(c.tbl); launder(c.isd); launder(sc.prt);
-    launder(sf.kt); launder(sf.mva); launder(sf.mvb); launder(sf.mvj); launder(sf.mvs); launder(sf.sl);
+    launder(sf.base);
     launder(pol.pol_a); launder(pol.pol_b);
     auto do_group = [&](GroupS& x, int64_t gg) {
         if (PHILOX) {
@@ -1129,23 +1148,47 @@ k_step_table_slip_i(const PitchDev P, const uint16_t* __restrict__ gtable, uint3
         uint32_t so[4], oo[4], ro[4], rr[4], ff[4];
         // both players' action bytes as one index per env, byte-parallel: aa * 8 + ab (3-bit fields; > 4 acts as 4)
         const uint32_t j4 = ((x.a & 0x07070707u) << 3) | (x.b & 0x07070707u);
+        uint32_t walks = 0;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const uint32_t rsel4 = __byte_perm(rs4, 0, 0x4440 + e);
             bool walk;
             TblOut o;
-            uint32_t aa = __byte_perm(x.a, 0, 0x4440 + e), ab = __byte_perm(x.b, 0, 0x4440 + e);
-            if (pol.pol_a | pol.pol_b) {                     // warp-uniform
-                const uint32_t cs = min(sv[e] & 0xFFFFu, c.last / 100u);
+            if (POLICY) {
+                uint32_t aa = __byte_perm(x.a, 0, 0x4440 + e), ab = __byte_perm(x.b, 0, 0x4440 + e);
+                const uint32_t cs = min(sv[e] & 0xFFFFu, c.maxobs);
                 if (pol.pol_a) aa = lds_u8_r(pol.pol_a + cs);
                 if (pol.pol_b) ab = lds_u8_r(pol.pol_b + cs);
-                o = table_step_slip_int<true>(c, sf, dg, sv[e], aa, ab, r32[e], rsel4, walk);
+                o = table_step_slip_int<true>(c, sf, sv[e], aa, ab, r32[e], rsel4, walk);
             } else {
-                o = table_step_slip_int_j<true>(c, sf, dg, sv[e], __byte_perm(j4, 0, 0x4440 + e), r32[e], rsel4, walk);
+                o = table_step_slip_int_j<true>(c, sf, sv[e], __byte_perm(j4, 0, 0x4440 + e), r32[e], rsel4, walk);
             }
-            if (walk) o = table_step_slip_walk(c, sc, sv[e], aa, ab, r32[e], rsel4);     // (in practice never)
+#if SOCCER_K1_SLIP_WALK_MERGED
+            walks |= walk ? 1u << e : 0u;
+#else
+            if (walk) {
+                uint32_t aa = __byte_perm(x.a, 0, 0x4440 + e), ab = __byte_perm(x.b, 0, 0x4440 + e);
+                const uint32_t cs = min(sv[e] & 0xFFFFu, c.maxobs);
+                if (POLICY && pol.pol_a) aa = lds_u8_r(pol.pol_a + cs);
+                if (POLICY && pol.pol_b) ab = lds_u8_r(pol.pol_b + cs);
+                o = table_step_slip_walk(c, sc, sv[e], aa, ab, r32[e], rsel4);
+            }
+#endif
             so[e] = o.state; oo[e] = o.obs; rr[e] = __float_as_uint((float)(flip ? -o.rew_i : o.rew_i));
             ro[e] = o.reset_obs; ff[e] = o.flags;
+        }
+        if (walks) {                                         // (in practice never): redo those envs by the reference's walk
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (!((walks >> e) & 1u)) continue;
+                uint32_t aa = __byte_perm(x.a, 0, 0x4440 + e), ab = __byte_perm(x.b, 0, 0x4440 + e);
+                const uint32_t cs = min(sv[e] & 0xFFFFu, c.maxobs);
+                if (POLICY && pol.pol_a) aa = lds_u8_r(pol.pol_a + cs);
+                if (POLICY && pol.pol_b) ab = lds_u8_r(pol.pol_b + cs);
+                const TblOut o = table_step_slip_walk(c, sc, sv[e], aa, ab, r32[e], __byte_perm(rs4, 0, 0x4440 + e));
+                so[e] = o.state; oo[e] = o.obs; rr[e] = __float_as_uint((float)(flip ? -o.rew_i : o.rew_i));
+                ro[e] = o.reset_obs; ff[e] = o.flags;
+            }
         }
         st_keep(st4 + gg, make_uint4(so[0], so[1], so[2], so[3]));
         st_stream(o4 + gg, make_uint4(oo[0], oo[1], oo[2], oo[3]));
@@ -1256,7 +1299,7 @@ k_step_table_slip_q(const PitchDev P, const uint16_t* __restrict__ gtable, uint3
                 ud = F64 ? reinterpret_cast<const double*>(draw)[env] : u_from_rng32(reinterpret_cast<const uint32_t*>(draw)[env]);
             }
             uint32_t aa = act_a1[env], ab = act_b1[env];
-            const uint32_t cur = min(s & 0xFFFFu, c.last / 100u);
+            const uint32_t cur = min(s & 0xFFFFu, c.maxobs);
             if (pol.pol_a) aa = lds_u8_r(pol.pol_a + cur);
             if (pol.pol_b) ab = lds_u8_r(pol.pol_b + cur);
             const TblOut o = table_step_slip(c, sc, s, aa, ab, ud, rg & 0xCu);
@@ -1294,7 +1337,7 @@ k_step_table_slip_q(const PitchDev P, const uint16_t* __restrict__ gtable, uint3
                 bool defer;
                 uint32_t aa = __byte_perm(x.a, 0, 0x4440 + e), ab = __byte_perm(x.b, 0, 0x4440 + e);
                 if (pol.pol_a | pol.pol_b) {                 // warp-uniform
-                    const uint32_t cs = min(sv[e] & 0xFFFFu, c.last / 100u);
+                    const uint32_t cs = min(sv[e] & 0xFFFFu, c.maxobs);
                     if (pol.pol_a) aa = lds_u8_r(pol.pol_a + cs);
                     if (pol.pol_b) ab = lds_u8_r(pol.pol_b + cs);
                 }
