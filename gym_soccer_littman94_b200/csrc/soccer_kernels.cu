@@ -278,7 +278,10 @@ k_step_fast_slip(const PitchDev P, const RulesSlipArgs sa, uint32_t* __restrict_
         const uint32_t sv[4] = { x.s.x, x.s.y, x.s.z, x.s.w };
         const uint32_t r32[4] = { x.d.x, x.d.y, x.d.z, x.d.w };
         Step4 o;
-        step4_slip_int<RESET_OBS, true>(P, I, lut, fi, sc, sv, ((x.a & 0x07070707u) << 3) | (x.b & 0x07070707u), r32, x.r, o);
+        Soa4 so;
+        step4_slip_int<RESET_OBS, true>(P, I, lut, fi, sc, soa4_from_words(sv), ((x.a & 0x07070707u) << 3) | (x.b & 0x07070707u),
+                                        r32, x.r, o, so);
+        soa4_to_words(so, o.s);
         st_keep(st4 + g, make_uint4(o.s[0], o.s[1], o.s[2], o.s[3]));
         st_stream(o4 + g, make_uint4(o.obs[0], o.obs[1], o.obs[2], o.obs[3]));
         st_stream(w4 + g, make_uint4(o.rew[0], o.rew[1], o.rew[2], o.rew[3]));

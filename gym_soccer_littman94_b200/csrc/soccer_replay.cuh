@@ -36,6 +36,8 @@ template <int VEC> __device__ __forceinline__ uint32_t ld_row(const uint8_t* p)
 // ---- steppers: one step of the VEC envs of a thread given their action / draw bytes
 struct ReplayTable {
     TblCtx c;
+    template <int VEC> __device__ __forceinline__ void enter(uint32_t*) const {}
+    template <int VEC> __device__ __forceinline__ void leave(uint32_t*) const {}
     template <int VEC, bool RO>
     __device__ __forceinline__ void step(uint32_t* s, uint32_t a4, uint32_t b4, uint32_t r4, uint32_t* oo, uint32_t* rr,
                                          uint32_t& fw, uint32_t* ro) const
@@ -56,15 +58,27 @@ struct ReplayTable {
 
 struct ReplayRules {
     const PitchDev& P; const uint8_t* lut; Isd4 I;
+    // four envs per thread: the states stay packed bytes (Soa4 in s[0..3]) for all T steps
+    template <int VEC> __device__ __forceinline__ void enter(uint32_t* s) const
+    {
+        if (VEC == 4) { const Soa4 x = soa4_from_words(s); s[0] = x.A; s[1] = x.B; s[2] = x.T; s[3] = x.P; }
+    }
+    template <int VEC> __device__ __forceinline__ void leave(uint32_t* s) const
+    {
+        if (VEC == 4) { const Soa4 x = { s[0], s[1], s[2], s[3] }; soa4_to_words(x, s); }
+    }
     template <int VEC, bool RO>
     __device__ __forceinline__ void step(uint32_t* s, uint32_t a4, uint32_t b4, uint32_t r4, uint32_t* oo, uint32_t* rr,
                                          uint32_t& fw, uint32_t* ro) const
     {
         if (VEC == 4) {
+            const Soa4 in = { s[0], s[1], s[2], s[3] };
+            Soa4 out;
             Step4 o;
-            step4_noslip<RO>(P, I, lut, s, a4, b4, r4, o);
+            step4_core<RO>(P, I, lut, in, a4, b4, r4, o, r4, r4, out);
+            s[0] = out.A; s[1] = out.B; s[2] = out.T; s[3] = out.P;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) { s[e] = o.s[e]; oo[e] = o.obs[e]; rr[e] = o.rew[e]; if (RO) ro[e] = o.robs[e]; }
+            for (int e = 0; e < 4; ++e) { oo[e] = o.obs[e]; rr[e] = o.rew[e]; if (RO) ro[e] = o.robs[e]; }
             fw = o.flags4;
         } else {
             const StepOut o = step_noslip<true, false>(P, lut, s[0], a4 & 0xFFu, b4 & 0xFFu, r4 & 0xFFu, false);
@@ -99,6 +113,7 @@ __device__ __forceinline__ void replay_body(const Stepper& S, const ReplayArgs& 
         } else {
             s[0] = a.state[i0];
         }
+        S.template enter<VEC>(s);
         const uint8_t *pa = a.act_a + i0, *pb = a.act_b + i0, *pr = a.rng8 + i0;
         int32_t* op = a.obs + i0;
         float* rp = a.reward + i0;
@@ -142,6 +157,7 @@ __device__ __forceinline__ void replay_body(const Stepper& S, const ReplayArgs& 
 #pragma unroll
             for (int j = 0; j < kU; ++j) { ia[j] = na[j]; ib[j] = nb[j]; ir[j] = nr[j]; }
         }
+        S.template leave<VEC>(s);
         if (VEC == 4) reinterpret_cast<uint4*>(a.state)[g] = make_uint4(s[0], s[1], s[2], s[3]);
         else a.state[i0] = s[0];
     }

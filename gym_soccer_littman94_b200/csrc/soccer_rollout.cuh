@@ -37,10 +37,11 @@ __device__ __noinline__ StepOut step_slip_call(const PitchDev& P, const uint8_t*
 }
 // J4: the joint action of each env as one index byte -- WIDE: aa * 8 + ab (caller-supplied action bytes, 3-bit fields),
 // else aa * 5 + ab (the Philox joint action); the move pair of (combination, joint action) is ONE byte ma | mb << 4.
+// in / out: the four states as packed bytes (K2 keeps them that way between steps); o.s is not written.
 template <bool RESET_OBS, bool WIDE>
 __device__ __forceinline__ void step4_slip_int(const PitchDev& P, const Isd4& I, const uint8_t* __restrict__ lut,
-                                               const SlipInt& f, const SlipCtx& sc, const uint32_t sv[4],
-                                               uint32_t J4, const uint32_t r32[4], uint32_t RST, Step4& o)
+                                               const SlipInt& f, const SlipCtx& sc, const Soa4& in,
+                                               uint32_t J4, const uint32_t r32[4], uint32_t RST, Step4& o, Soa4& out)
 {
     uint32_t mv[4], r4[4], r2[4], walk = 0;
 #pragma unroll
@@ -55,18 +56,18 @@ __device__ __forceinline__ void step4_slip_int(const PitchDev& P, const Isd4& I,
         r4[e] = (r32[e] > t4.x ? 1u : 0u) + (r32[e] > t4.y ? 1u : 0u) + (r32[e] > t4.z ? 1u : 0u);
     }
     const uint32_t MV = pack4(mv[0], mv[1], mv[2], mv[3]);
-    const uint32_t R4 = pack4(r4[0], r4[1], r4[2], r4[3]) | (RST & 0x0C0C0C0Cu);
-    step4_noslip<RESET_OBS>(P, I, lut, sv, MV & 0x0F0F0F0Fu, (MV >> 4) & 0x0F0F0F0Fu, R4, o, pack4(r2[0], r2[1], r2[2], r2[3]));
+    step4_core<RESET_OBS>(P, I, lut, in, MV, MV >> 4, pack4(r4[0], r4[1], r4[2], r4[3]), o, pack4(r2[0], r2[1], r2[2], r2[3]), RST, out);
     if (walk) {                                                              // (in practice never)
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             if ((walk >> e) & 1u) {
                 const uint32_t j = byte_of(J4, e);
-                const StepOut w = step_slip_call(P, lut, sc.prt, sc.first_k, sv[e], WIDE ? min(j >> 3, 4u) : min(j / 5u, 4u),
+                const StepOut w = step_slip_call(P, lut, sc.prt, sc.first_k, soa4_word(in, e), WIDE ? min(j >> 3, 4u) : min(j / 5u, 4u),
                                                  WIDE ? min(j & 7u, 4u) : j % 5u, r32[e], (byte_of(RST, e) >> 2) & 3u);
                 const int32_t ri = (w.reward > 0.0f) - (w.reward < 0.0f);
                 o.rew_sum += ri - (int32_t)(signed char)(o.rew4 >> (8 * e));
-                o.s[e] = w.state; o.obs[e] = (uint32_t)w.obs; o.rew[e] = __float_as_uint(w.reward);
+                soa4_set_word(out, e, w.state);
+                o.obs[e] = (uint32_t)w.obs; o.rew[e] = __float_as_uint(w.reward);
                 o.rew4 = (o.rew4 & ~(0xFFu << (8 * e))) | (((uint32_t)ri & 0xFFu) << (8 * e));
                 o.flags4 = (o.flags4 & ~(0xFFu << (8 * e))) | ((w.flags & 3u) << (8 * e));
                 if (RESET_OBS) o.robs[e] = (uint32_t)w.reset_obs;
@@ -101,6 +102,8 @@ struct TableStepper {
     uint32_t pol_a, pol_b;      // shared-window addresses of the int8[nS] table policies, 0 = uniform (POLICY only)
     SlipCtx sc;                 // slip-combination probability table (SLIP only)
     __device__ __forceinline__ uint32_t timestep(uint32_t s) const { return s >> 16; }
+    template <int VEC> __device__ __forceinline__ void enter(uint32_t*) const {}
+    template <int VEC> __device__ __forceinline__ void leave(uint32_t*) const {}
     template <int VEC>
     __device__ __forceinline__ void step(uint32_t* s, const uint32_t* word, uint32_t* oo, uint32_t* rr,
                                          uint32_t& fw, int32_t& net, bool flip) const
@@ -145,6 +148,8 @@ struct TableSlipIntStepper {
     TblCtx c; SlipCtx sc; SlipInt sf;
     uint32_t pol_a, pol_b;
     __device__ __forceinline__ uint32_t timestep(uint32_t s) const { return s >> 16; }
+    template <int VEC> __device__ __forceinline__ void enter(uint32_t*) const {}
+    template <int VEC> __device__ __forceinline__ void leave(uint32_t*) const {}
     template <int VEC>
     __device__ __forceinline__ void step(uint32_t* s, const uint32_t* word, uint32_t* oo, uint32_t* rr,
                                          uint32_t& fw, int32_t& net, bool flip) const
@@ -198,7 +203,18 @@ template <bool SLIP>
 struct RulesStepper {
     static constexpr bool kCollective = false, kHasPolicy = true;
     const PitchDev& P; const uint8_t* lut; Isd4 I; const int8_t* policy_a; const int8_t* policy_b; SlipCtx sc;
+    uint32_t jlut;      // shared-window address of the 100-byte decode table of mulhi(w, 100): aa | ab << 3 | r << 6
     __device__ __forceinline__ uint32_t timestep(uint32_t s) const { return (s >> 16) & 0xFFu; }
+    // the byte-parallel path keeps the four states as packed bytes (Soa4 in s[0..3]) between enter() and leave()
+    template <int VEC> __device__ __forceinline__ bool packed() const { return !SLIP && VEC == 4 && !policy_a && !policy_b; }
+    template <int VEC> __device__ __forceinline__ void enter(uint32_t* s) const
+    {
+        if (packed<VEC>()) { const Soa4 x = soa4_from_words(s); s[0] = x.A; s[1] = x.B; s[2] = x.T; s[3] = x.P; }
+    }
+    template <int VEC> __device__ __forceinline__ void leave(uint32_t* s) const
+    {
+        if (packed<VEC>()) { const Soa4 x = { s[0], s[1], s[2], s[3] }; soa4_to_words(x, s); }
+    }
     template <int VEC>
     __device__ __forceinline__ void step(uint32_t* s, const uint32_t* word, uint32_t* oo, uint32_t* rr,
                                          uint32_t& fw, int32_t& net, bool flip) const
@@ -223,15 +239,22 @@ struct RulesStepper {
                 net += ri;
             }
         } else if (VEC == 4 && !policy_a && !policy_b) {
-            uint32_t aa[4], ab[4], rg[4];
+            // decode by table: byte = aa | ab << 3 | r << 6 at index mulhi(w, 100) (one IMAD.HI + one LDS per env on
+            // the idle pipes instead of seven integer instructions on the ALU pipe that binds this kernel); the reset
+            // draw is bits 2..3 of w itself
+            uint32_t d[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) { philox_actions(word[e % VEC], aa[e], ab[e]); rg[e] = philox_rng8(word[e % VEC]); }
+            for (int e = 0; e < 4; ++e) d[e] = lds_u8_r(jlut + philox_jr(word[e % VEC]));
+            const uint32_t D = pack4(d[0], d[1], d[2], d[3]);
+            const uint32_t W = pack4(word[0], word[1 % VEC], word[2 % VEC], word[3 % VEC]);
+            const Soa4 in = { s[0], s[1], s[2], s[3] };
+            Soa4 out;
             Step4 o;
-            step4_noslip<false>(P, I, lut, s, pack4(aa[0], aa[1], aa[2], aa[3]), pack4(ab[0], ab[1], ab[2], ab[3]),
-                                pack4(rg[0], rg[1], rg[2], rg[3]), o);
+            step4_core<false>(P, I, lut, in, D, D >> 3, D >> 6, o, D >> 6, W, out);
+            s[0] = out.A; s[1] = out.B; s[2] = out.T; s[3] = out.P;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                s[e] = o.s[e]; oo[e] = o.obs[e];
+                oo[e] = o.obs[e];
                 rr[e] = flip ? __float_as_uint((float)(-(int)(signed char)(o.rew4 >> (8 * e)))) : o.rew[e];
             }
             fw = o.flags4;
@@ -263,22 +286,33 @@ struct RulesSlipIntStepper {
     static constexpr bool kCollective = false, kHasPolicy = false;
     const PitchDev& P; const uint8_t* lut; Isd4 I; SlipCtx sc; SlipInt fi;
     __device__ __forceinline__ uint32_t timestep(uint32_t s) const { return (s >> 16) & 0xFFu; }
+    template <int VEC> __device__ __forceinline__ void enter(uint32_t* s) const
+    {
+        const Soa4 x = soa4_from_words(s); s[0] = x.A; s[1] = x.B; s[2] = x.T; s[3] = x.P;
+    }
+    template <int VEC> __device__ __forceinline__ void leave(uint32_t* s) const
+    {
+        const Soa4 x = { s[0], s[1], s[2], s[3] }; soa4_to_words(x, s);
+    }
     template <int VEC>
     __device__ __forceinline__ void step(uint32_t* s, const uint32_t* word, uint32_t* oo, uint32_t* rr,
                                          uint32_t& fw, int32_t& net, bool) const
     {
         static_assert(VEC == 4, "four envs per thread");
-        uint32_t ja[4], r32[4], rst = 0;
+        uint32_t ja[4], r32[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             ja[e] = philox_ja(word[e]);
             r32[e] = philox_r32(word[e]);
-            rst |= (word[e] & 0xCu) << (8 * e);
         }
+        const Soa4 in = { s[0], s[1], s[2], s[3] };
+        Soa4 out;
         Step4 o;
-        step4_slip_int<false, false>(P, I, lut, fi, sc, s, pack4(ja[0], ja[1], ja[2], ja[3]), r32, rst, o);
+        step4_slip_int<false, false>(P, I, lut, fi, sc, in, pack4(ja[0], ja[1], ja[2], ja[3]), r32,
+                                     pack4(word[0], word[1], word[2], word[3]), o, out);
+        s[0] = out.A; s[1] = out.B; s[2] = out.T; s[3] = out.P;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) { s[e] = o.s[e]; oo[e] = o.obs[e]; rr[e] = o.rew[e]; }
+        for (int e = 0; e < 4; ++e) { oo[e] = o.obs[e]; rr[e] = o.rew[e]; }
         fw = o.flags4;
         net += o.rew_sum;
     }
@@ -341,6 +375,7 @@ __device__ __forceinline__ void rollout_body(const Stepper& S, const RolloutArgs
         uint32_t t_in = 0;
 #pragma unroll
         for (int e = 0; e < VEC; ++e) t_in += S.timestep(s[e]);
+        S.template enter<VEC>(s);                                        // (rules steppers: words -> packed bytes)
         uint32_t acc_d = 0, acc_t = 0, p_done = 0, p_trunc = 0;
         int32_t p_net = 0;
         int32_t* op = (a.obs && valid) ? a.obs + i0 : nullptr;
@@ -396,6 +431,7 @@ __device__ __forceinline__ void rollout_body(const Stepper& S, const RolloutArgs
             }
         }
         p_done = __dp4a(acc_d, 0x01010101u, p_done); p_trunc = __dp4a(acc_t, 0x01010101u, p_trunc);
+        S.template leave<VEC>(s);
         uint32_t t_out = 0;
 #pragma unroll
         for (int e = 0; e < VEC; ++e) t_out += S.timestep(s[e]);
@@ -531,6 +567,8 @@ struct ClusterTableStepper {
     uint32_t slice;             // shared::cta address of this CTA's slice (the same offset in every CTA of the cluster)
     uint32_t isd, last;
     __device__ __forceinline__ uint32_t timestep(uint32_t s) const { return s >> 16; }
+    template <int VEC> __device__ __forceinline__ void enter(uint32_t*) const {}
+    template <int VEC> __device__ __forceinline__ void leave(uint32_t*) const {}
     template <int VEC>
     __device__ __forceinline__ void step(uint32_t* s, const uint32_t* word, uint32_t* oo, uint32_t* rr,
                                          uint32_t& fw, int32_t& net, bool) const
@@ -592,12 +630,17 @@ k_rollout(const PitchDev P, const int8_t* __restrict__ policy_a, const int8_t* _
     __shared__ __align__(16) uint8_t lut[kLutBytes];
     __shared__ __align__(16) double prt[kPrtDoubles];
     __shared__ BlkStats blk;
+    __shared__ __align__(4) uint8_t jlut[100];
     if (SLIP) slip_build_prt(prt, P);
     build_cand_lut(lut, P);
     if (threadIdx.x < 5) blk.v[threadIdx.x] = 0;
+    if (threadIdx.x < 100) {
+        const uint32_t ja = threadIdx.x >> 2, aa = ja / 5u;
+        jlut[threadIdx.x] = (uint8_t)(aa | ((ja - aa * 5u) << 3) | ((threadIdx.x & 3u) << 6));
+    }
     __syncthreads();
     const SlipCtx sc = { (uint32_t)__cvta_generic_to_shared(prt), SLIP ? slip_first_k(P) : 0u };
-    const RulesStepper<SLIP> S = { P, lut, make_isd4(P), policy_a, policy_b, sc };
+    const RulesStepper<SLIP> S = { P, lut, make_isd4(P), policy_a, policy_b, sc, (uint32_t)__cvta_generic_to_shared(jlut) };
     rollout_body<VEC, STREAMS>(S, a, &blk);
 }
 

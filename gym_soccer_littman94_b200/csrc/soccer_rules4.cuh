@@ -23,7 +23,12 @@ __device__ __forceinline__ uint32_t eq4(uint32_t x, uint32_t y)
     return ~(((z & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | z) & kH;
 }
 // 0x80 flags -> 0xFF byte masks
-__device__ __forceinline__ uint32_t mask4(uint32_t f) { return (f >> 7) * 0xFFu; }
+__device__ __forceinline__ uint32_t mask4(uint32_t f)
+{
+    uint32_t m;                                 // PRMT with the sign-replicate bit of every selector nibble set: ONE instruction
+    asm("prmt.b32 %0, %1, %2, 0xBA98;" : "=r"(m) : "r"(f), "r"(0u));
+    return m;
+}
 // per byte: m ? x : y
 __device__ __forceinline__ uint32_t sel4(uint32_t m, uint32_t x, uint32_t y) { return (x & m) | (y & ~m); }
 __device__ __forceinline__ uint32_t pack4(uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3)
@@ -61,20 +66,49 @@ struct Step4 {
     int32_t  rew_sum;   // sum of the four rewards (+1 / -1 / 0), for K2's statistics
 };
 
-// sv: the four state words; MA4 / MB4: action bytes; R4: rng8 bytes (bits 0..1 step draw, 2..3 reset draw).
-// R2: the draw of a 2-outcome collision in bit 1 of each byte; the same as R4 when one 2-bit draw serves both kinds
-// (slip_prob == 0: outcome r of 4, r >> 1 of 2), a separate word for the slip steppers, whose slot inside a 2-way and
-// inside a 4-way combination comes from different thresholds.
-template <bool RESET_OBS>
-__device__ __forceinline__ void step4_noslip(const PitchDev& P, const Isd4& I, const uint8_t* __restrict__ lut,
-                                             const uint32_t sv[4], uint32_t MA4, uint32_t MB4, uint32_t R4, Step4& o,
-                                             uint32_t R2)
+// The four envs of a thread as packed bytes: cells of A and B, timestep, possession (0 / 1).  K2 and the fused replay keep
+// the state in this form for all their steps (the 4x4 byte transposes are paid once per launch, not once per step).
+struct Soa4 { uint32_t A, B, T, P; };
+__device__ __forceinline__ Soa4 soa4_from_words(const uint32_t sv[4])
 {
-    // ---- 4x4 byte transpose: words (a,b,t,p) per env -> A4, B4, T4, P4
+    // 4x4 byte transpose: words (a,b,t,p) per env -> A4, B4, T4, P4
     const uint32_t u0 = __byte_perm(sv[0], sv[1], 0x5140), u1 = __byte_perm(sv[2], sv[3], 0x5140);
     const uint32_t v0 = __byte_perm(sv[0], sv[1], 0x7362), v1 = __byte_perm(sv[2], sv[3], 0x7362);
-    const uint32_t A4 = __byte_perm(u0, u1, 0x5410), B4 = __byte_perm(u0, u1, 0x7632);
-    const uint32_t T4 = __byte_perm(v0, v1, 0x5410), P4 = __byte_perm(v0, v1, 0x7632) & kL;
+    Soa4 x;
+    x.A = __byte_perm(u0, u1, 0x5410); x.B = __byte_perm(u0, u1, 0x7632);
+    x.T = __byte_perm(v0, v1, 0x5410); x.P = __byte_perm(v0, v1, 0x7632) & kL;
+    return x;
+}
+__device__ __forceinline__ void soa4_to_words(const Soa4& x, uint32_t s[4])
+{
+    const uint32_t w0 = __byte_perm(x.A, x.B, 0x5140), w1 = __byte_perm(x.A, x.B, 0x7362);
+    const uint32_t x0 = __byte_perm(x.T, x.P, 0x5140), x1 = __byte_perm(x.T, x.P, 0x7362);
+    s[0] = __byte_perm(w0, x0, 0x5410); s[1] = __byte_perm(w0, x0, 0x7632);
+    s[2] = __byte_perm(w1, x1, 0x5410); s[3] = __byte_perm(w1, x1, 0x7632);
+}
+// one env's word out of / into the packed form (the slip steppers' never-taken walk)
+__device__ __forceinline__ uint32_t soa4_word(const Soa4& x, int e)
+{
+    return byte_of(x.A, e) | (byte_of(x.B, e) << 8) | (byte_of(x.T, e) << 16) | (byte_of(x.P, e) << 24);
+}
+__device__ __forceinline__ void soa4_set_word(Soa4& x, int e, uint32_t w)
+{
+    const uint32_t m = 0xFFu << (8 * e);
+    x.A = (x.A & ~m) | ((w & 0xFFu) << (8 * e));          x.B = (x.B & ~m) | (((w >> 8) & 0xFFu) << (8 * e));
+    x.T = (x.T & ~m) | (((w >> 16) & 0xFFu) << (8 * e));  x.P = (x.P & ~m) | (((w >> 24) & 1u) << (8 * e));
+}
+
+// in / out: the four states; MA4 / MB4: action bytes (only bits 0..2 of each byte are read); R4: step draw in bits 0..1 of
+// each byte, RST4: reset draw in bits 2..3 (the other bits of R4 / RST4 are ignored: an rng8 word serves as both).
+// R2: the draw of a 2-outcome collision in bit 1 of each byte; the same as R4 when one 2-bit draw serves both kinds
+// (slip_prob == 0: outcome r of 4, r >> 1 of 2), a separate word for the slip steppers, whose slot inside a 2-way and
+// inside a 4-way combination comes from different thresholds.  o.s is NOT written here (step4_noslip does).
+template <bool RESET_OBS>
+__device__ __forceinline__ void step4_core(const PitchDev& P, const Isd4& I, const uint8_t* __restrict__ lut,
+                                           const Soa4& in, uint32_t MA4, uint32_t MB4, uint32_t R4, Step4& o,
+                                           uint32_t R2, uint32_t RST4, Soa4& out)
+{
+    const uint32_t A4 = in.A, B4 = in.B, T4 = in.T, P4 = in.P;
 
     // ---- candidates (SIM:308-309, 364-373): cand[cell*16 + has_ball*8 + move], two lookups per env
     const uint32_t MA = MA4 & 0x07070707u, MB = MB4 & 0x07070707u;
@@ -118,15 +152,11 @@ __device__ __forceinline__ void step4_noslip(const PitchDev& P, const Isd4& I, c
     o.flags4 = done1 | (trunc >> 6);
 
     // ---- fused reset (SIM:410-424): start state from the 2-bit reset draw
-    const uint32_t m1 = mask4((R4 << 5) & kH), m2 = mask4((R4 << 4) & kH), mR = mask4(reset);
+    const uint32_t m1 = mask4((RST4 << 5) & kH), m2 = mask4((RST4 << 4) & kH), mR = mask4(reset);
     const uint32_t An = I.a0 ^ (m1 & I.da1) ^ (m2 & I.da2);
     const uint32_t Bn = I.b0 ^ (m1 & I.db1) ^ (m2 & I.db2);
     const uint32_t Pn = I.p0 ^ (m1 & I.dp1) ^ (m2 & I.dp2);
-    const uint32_t Ao = sel4(mR, An, FA), Bo = sel4(mR, Bn, FB), Po = sel4(mR, Pn, FP), To = T1 & ~mR;
-    const uint32_t w0 = __byte_perm(Ao, Bo, 0x5140), w1 = __byte_perm(Ao, Bo, 0x7362);
-    const uint32_t x0 = __byte_perm(To, Po, 0x5140), x1 = __byte_perm(To, Po, 0x7362);
-    o.s[0] = __byte_perm(w0, x0, 0x5410); o.s[1] = __byte_perm(w0, x0, 0x7632);
-    o.s[2] = __byte_perm(w1, x1, 0x5410); o.s[3] = __byte_perm(w1, x1, 0x7632);
+    out.A = sel4(mR, An, FA); out.B = sel4(mR, Bn, FB); out.P = sel4(mR, Pn, FP); out.T = T1 & ~mR;
 
     // ---- observation index (SIM:487-494) in 16-bit lanes: envs (0,2) and (1,3)
     //      obs = 1 + 2*(a*(F-1) + b) + p - 2*(b > a); no lane ever borrows or overflows
@@ -147,7 +177,7 @@ __device__ __forceinline__ void step4_noslip(const PitchDev& P, const Isd4& I, c
     o.rew_sum = (int)__dp4a((int)RW, (int)kL, 0);
 
     if (RESET_OBS) {
-        const uint32_t s1 = (R4 >> 2) & kL, s2 = (R4 >> 3) & kL;   // reset-draw bits as bytes 0/1
+        const uint32_t s1 = (RST4 >> 2) & kL, s2 = (RST4 >> 3) & kL;   // reset-draw bits as bytes 0/1
         const uint32_t n02 = I.o0 + (s1 & 0x00010001u) * I.od1 + (s2 & 0x00010001u) * I.od2;
         const uint32_t n13 = I.o0 + ((s1 >> 8) & 0x00010001u) * I.od1 + ((s2 >> 8) & 0x00010001u) * I.od2;
         const uint32_t r02 = __byte_perm(mR, 0, 0x2200), r13 = __byte_perm(mR, 0, 0x3311);
@@ -156,6 +186,16 @@ __device__ __forceinline__ void step4_noslip(const PitchDev& P, const Isd4& I, c
     }
 }
 
+// sv: the four state words (CELL layout); R4: rng8 bytes (bits 0..1 step draw, 2..3 reset draw)
+template <bool RESET_OBS>
+__device__ __forceinline__ void step4_noslip(const PitchDev& P, const Isd4& I, const uint8_t* __restrict__ lut,
+                                             const uint32_t sv[4], uint32_t MA4, uint32_t MB4, uint32_t R4, Step4& o,
+                                             uint32_t R2)
+{
+    Soa4 out;
+    step4_core<RESET_OBS>(P, I, lut, soa4_from_words(sv), MA4, MB4, R4, o, R2, R4, out);
+    soa4_to_words(out, o.s);
+}
 template <bool RESET_OBS>
 __device__ __forceinline__ void step4_noslip(const PitchDev& P, const Isd4& I, const uint8_t* __restrict__ lut,
                                              const uint32_t sv[4], uint32_t MA4, uint32_t MB4, uint32_t R4, Step4& o)

@@ -881,8 +881,8 @@ __device__ __forceinline__ void stage_table_and_index(uint8_t* smem, const uint1
 //                              k = (kt[b] + (r & (2^S - 1))) >> S          = klo + (r > t - 1)
 //                          -- the compare is the carry out of the low S bits: one load, three integer instructions.
 //                          klo = 9 = undecided (two or more steps inside the bucket: tiny slip_prob) -> walk
-//   sl[k][nl - 1]          (20 rows of uint4) strict thresholds t - 1 of slots 1, 2, 3 inside a 2-way / 4-way
-//                          combination k; unused = 0xFFFFFFFF
+//   sl[k][nl - 1]          (20 rows of uint4) strict thresholds t - 1 of slots 1, 2, 3 inside a 4-way combination k,
+//                          {t, t, never} for the one threshold of a 2-way one; unused = 0xFFFFFFFF
 //   mva[k][a], mvb[k][a]   (10 x 8 bytes each) byte offsets inside the table row of the move player A / B makes in
 //                          combination k with action a: (slipped move) * 40, * 8 (kernels with a folded policy)
 //   mvj[k][aa * 5 + ab]    (10 x 32 bytes) both players' moves of combination k in ONE byte, indexed by the Philox joint
@@ -946,6 +946,8 @@ __device__ __forceinline__ void slip_int_build_luts(uint8_t* base, const SlipE& 
                 t[j] = (th == 0ull || th > 0xFFFFFFFFull) ? 0xFFFFFFFFu : (uint32_t)(th - 1ull);
             }
         }
+        if (nl == 1) t[1] = t[0];              // 2-way row {t, t, never}: #(r > t_j) = 0 / 2, the 4-way rows count 0 .. 3, so that
+                                               // the entry of the chosen slot is ALWAYS 2 bytes * count behind slot 0
         sl[row * 4 + 0] = t[0]; sl[row * 4 + 1] = t[1]; sl[row * 4 + 2] = t[2]; sl[row * 4 + 3] = t[3];
     }
     const uint32_t low = (1u << (32 - bits)) - 1u;
@@ -1005,10 +1007,11 @@ __device__ __forceinline__ TblOut table_step_slip_int_at(const TblCtx& c, const 
     uint32_t ent = c.tbl + obsi * 200u + mv;
     int32_t e = lds_s16_r(ent);
     if ((uint32_t)e & 0x3000u) {                               // 3 % of the (state, move pair)s: 2 or 4 outcomes
-        const uint32_t nl = ((uint32_t)e >> 12) & 3u;
-        const uint4 t = lds_v4_r(f.sl() + (k * 2u + nl - 1u) * 16u);
-        const uint32_t slot = (r32 > t.x ? 1u : 0u) + (r32 > t.y ? 1u : 0u) + (r32 > t.z ? 1u : 0u);
-        ent += slot * (nl == 1u ? 4u : 2u);                    // 2-way: draw value 2 * slot; 4-way: draw value slot
+        // row (k, nl) of the slot thresholds: 16 bytes at sl + k * 32 + (nl - 1) * 16, and nl * 16 = (e >> 8) & 0x30
+        const uint4 t = lds_v4_r(f.sl() - 16u + k * 32u + (((uint32_t)e >> 8) & 0x30u));
+        if (r32 > t.x) ent += 2u;                              // 2-way: draw value 2 * slot (row {t, t, never}); 4-way: slot
+        if (r32 > t.y) ent += 2u;
+        if (r32 > t.z) ent += 2u;
         e = lds_s16_r(ent);
     }
     return table_finish(c, s, e, rsel4);
