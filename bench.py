@@ -650,8 +650,11 @@ def run_ours(args):
         import numpy as np
         from gym_soccer_littman94_b200.envs import SoccerSimultaneousEnv
         c1 = {}
-        for mode in ("zero_copy", "staged"):
+        for mode in ("speculative", "zero_copy", "staged"):
+            # speculative (the default): one launch per step steps the new state for all 25 joint actions x 4 draws
+            # while the Python loop is busy (soccer_step_speculate); zero_copy / staged: launch and wait per step
             os.environ["SOCCER_B200_SINGLE_ENV_STAGED"] = "1" if mode == "staged" else "0"
+            os.environ["SOCCER_B200_SINGLE_ENV_SPECULATE"] = "1" if mode == "speculative" else "0"
             e1 = SoccerSimultaneousEnv(5, 4, slip_prob=0.0, seed=0, device=dev)
             acts = np.random.RandomState(123).randint(0, 5, (20000, 2))
             e1.reset()
@@ -664,6 +667,7 @@ def run_ours(args):
                     n_ep += 1
             c1[mode] = {"steps_per_s": len(acts) / (time.perf_counter() - t0), "episodes": n_ep}
         os.environ.pop("SOCCER_B200_SINGLE_ENV_STAGED", None)
+        os.environ.pop("SOCCER_B200_SINGLE_ENV_SPECULATE", None)
         extra["config1_single_env_dropin"] = dict(c1, note="20,000 step() calls of ONE env through the reference's class "
                                                   "surface; latency-bound (one launch + sync per step), reported next to "
                                                   "the reference's 29.6 k steps/s Python loop (BASELINE.md)")

@@ -29,6 +29,7 @@ EXPORTS = (
     "soccer_step_table_packed_philox", "soccer_dense_q", "soccer_policy_eval", "soccer_policy_eval_workspace_bytes_host",
     "soccer_cluster_table_bytes_host", "soccer_build_cluster_table", "soccer_rollout_table_cluster",
     "soccer_stats_allreduce_p2p_bytes_host", "soccer_stats_allreduce_p2p", "soccer_slip_danger_host",
+    "soccer_step_speculate",
 )
 
 
@@ -122,6 +123,7 @@ def lib():
         "soccer_step": [PP, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp],
         "soccer_step_philox": [PP, vp, vp, vp, u64, u64, u64, vp, vp, vp, vp, i64, vp],
         "soccer_step_ex": [PP, C.POINTER(StepArgs), vp],
+        "soccer_step_speculate": [PP, C.c_uint32, vp, vp, vp, C.c_uint32, vp],
         "soccer_rollout": [PP, vp, vp, vp, u64, u64, i32, u64, i32, vp, vp, vp, vp, i64, vp],
         "soccer_sweep": [PP, i32, vp, vp, vp, vp, vp, vp],
         "soccer_dense": [PP, vp, vp, vp, vp, vp],

@@ -371,6 +371,38 @@ __global__ void __launch_bounds__(kThreads) k_step_generic(const PitchDev P, con
     if (o.stats) k1_stats_flush(acc, &sblk, o.stats);
 }
 
+// ------------------------------------------------------------------ single-env speculation
+// The single-env drop-in's step() is one launch + one wait per call, all latency.  Between two step() calls the env's
+// state is known but the joint action and the draw are not -- so ONE launch, enqueued as soon as the state is known,
+// steps the env for ALL 25 joint actions x 4 draw values (slip_prob == 0: the draw is 2 bits) and
+// writes the 100 results into (pinned host) memory while the caller is still busy; step() then picks record
+// (aa * 5 + ab) * 4 + floor(4u).  One thread per (joint action, draw); no shared memory, no look-up table: the two
+// candidate cells are computed arithmetically.  Record = { next state word (no auto-reset: needs_reset is set like
+// SIM:406), obs, reward bits, detail flags }; word 400 = seq, stored last with release semantics.
+__global__ void __launch_bounds__(128)
+k_step_speculate(const PitchDev P, uint32_t s, const int8_t* __restrict__ policy_a, const int8_t* __restrict__ policy_b,
+                 uint32_t* __restrict__ rec, uint32_t seq)
+{
+    const uint32_t i = threadIdx.x;
+    if (i < 100u) {
+        const uint32_t ja = i >> 2, r = i & 3u;
+        uint32_t aa = ja / 5u, ab = ja - aa * 5u;
+        const uint32_t a = s & 0xFFu, b = (s >> 8) & 0xFFu, t = (s >> 16) & 0xFFu, p = (s >> 24) & 1u;
+        const int32_t cur = obs_index(P, a, b, p);
+        if (policy_a) aa = (uint32_t)policy_a[cur];        // SIM:187-188: the folded player's table policy
+        if (policy_b) ab = (uint32_t)policy_b[cur];
+        const uint32_t ma = (aa & 7u) > 4u ? 0u : (aa & 7u), mb = (ab & 7u) > 4u ? 0u : (ab & 7u);   // as build_cand_lut
+        const uint32_t na = next_cell_code(P, a, p ^ 1u, ma), nb = next_cell_code(P, b, p, mb);
+        const Resolved o = resolve_cand(na, nb, a, b, p, aa == 0, ab == 0, r);
+        const StepOut out = finish_step<false, true>(P, o, t, 0u, 0u, policy_a != nullptr);
+        uint4 v = make_uint4(out.state, (uint32_t)out.obs, __float_as_uint(out.reward), out.flags);
+        reinterpret_cast<uint4*>(rec)[i] = v;
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (i == 0) asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(rec + 400), "r"(seq) : "memory");
+}
+
 // ------------------------------------------------------------------ K3 sweep
 __global__ void __launch_bounds__(kThreads)
 k_sweep(const PitchDev P, int32_t n_combos, int32_t nS, uint8_t* __restrict__ n_out,
@@ -1905,6 +1937,19 @@ int soccer_stats_allreduce_p2p(const uint64_t* peer_ptrs, int32_t rank, int32_t 
     }
     a.rank = rank; a.world = world; a.epoch = epoch; a.stats = stats;
     k_stats_allreduce_p2p<<<1, 32, 0, (cudaStream_t)stream>>>(a);
+    return launch_status();
+}
+
+int soccer_step_speculate(const soccer_pitch* pitch, uint32_t state_word, const int8_t* policy_a, const int8_t* policy_b,
+                          uint32_t* records, uint32_t seq, soccer_stream_t stream)
+{
+    if (!records || !aligned(records, 16)) return SOCCER_EINVAL;
+    PitchDev P; const int rc = make_pitch_dev(pitch, &P); if (rc) return rc;
+    if (P.slip) return SOCCER_ESLIP;                               // the draw is not 2 bits: nothing to enumerate
+    const uint32_t a = state_word & 0xFFu, b = (state_word >> 8) & 0xFFu;
+    if (((a | b) & kGoalBit) || (state_word & kNeedsReset) || a >= (uint32_t)P.F || b >= (uint32_t)P.F || a == b)
+        return SOCCER_EINVAL;                                      // field-cell states of a running episode only
+    k_step_speculate<<<1, 128, 0, (cudaStream_t)stream>>>(P, state_word, policy_a, policy_b, records, seq);
     return launch_status();
 }
 

@@ -89,13 +89,10 @@ __device__ __forceinline__ void build_cand_lut(uint8_t* lut, const PitchDev& P)
 //   four  = (na == nb) & !stay                         case 4
 struct Resolved { uint32_t a, b, p, nlog2; };
 
-__device__ __forceinline__ Resolved resolve(const uint8_t* __restrict__ lut, uint32_t a, uint32_t b,
-                                            uint32_t p, uint32_t ma, uint32_t mb, bool a_noop,
-                                            bool b_noop, uint32_t r)
+// na / nb: the candidate cells of the two players (SIM:308-309)
+__device__ __forceinline__ Resolved resolve_cand(uint32_t na, uint32_t nb, uint32_t a, uint32_t b, uint32_t p,
+                                                 bool a_noop, bool b_noop, uint32_t r)
 {
-    const uint32_t p8 = p << 3;
-    const uint32_t na = lut[(a << 4) + 8u - p8 + (ma & 7u)];   // A has the ball iff p == 0 (SIM:308)
-    const uint32_t nb = lut[(b << 4) + p8 + (mb & 7u)];        // SIM:309
     // bitwise (not short-circuit) boolean algebra keeps this branch-free
     const bool aib = na == b, bia = nb == a, ast = na == a, bst = nb == b;
     const bool stay = (aib & (bia | bst)) | (bia & ast);
@@ -112,6 +109,15 @@ __device__ __forceinline__ Resolved resolve(const uint8_t* __restrict__ lut, uin
     o.p = (stay | four) ? pc : p;
     o.nlog2 = four ? 2u : ((stay & !c2) ? 1u : 0u);
     return o;
+}
+__device__ __forceinline__ Resolved resolve(const uint8_t* __restrict__ lut, uint32_t a, uint32_t b,
+                                            uint32_t p, uint32_t ma, uint32_t mb, bool a_noop,
+                                            bool b_noop, uint32_t r)
+{
+    const uint32_t p8 = p << 3;
+    const uint32_t na = lut[(a << 4) + 8u - p8 + (ma & 7u)];   // A has the ball iff p == 0 (SIM:308)
+    const uint32_t nb = lut[(b << 4) + p8 + (mb & 7u)];        // SIM:309
+    return resolve_cand(na, nb, a, b, p, a_noop, b_noop, r);
 }
 
 // SIM:487-494 closed form (field-cell states only).

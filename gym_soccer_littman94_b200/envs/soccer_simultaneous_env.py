@@ -22,12 +22,16 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import struct
 
 import numpy as np
 import torch
 
 from .. import _lib, spaces
 from .._lib import Pitch, StepArgs, check
+
+
+_REC = struct.Struct('<IifI')       # one record of soccer_step_speculate: state word, obs, reward, detail flags
 
 
 class SoccerSimultaneousEnv:
@@ -107,6 +111,20 @@ class SoccerSimultaneousEnv:
         self._pol_b = self._policy_tensor(player_b_policy)
         self._stream = torch.cuda.Stream(device=self.device)
         self._stream_ptr = C.c_void_p(self._stream.cuda_stream)
+        # speculative step (slip_prob == 0, soccer_step_speculate): as soon as the state is known ONE launch steps it for
+        # all 25 joint actions x 4 draw values into this pinned buffer; step() then only picks a record.
+        # SOCCER_B200_SINGLE_ENV_SPECULATE=0 keeps every step on the launch-and-wait path (A/B, tests).
+        self._spec_on = (slip_prob == 0 and not self._staged
+                         and os.environ.get("SOCCER_B200_SINGLE_ENV_SPECULATE", "1") == "1")
+        self._spec_key, self._spec_seq = None, 0
+        self._p_ref = C.byref(self._pitch)
+        if self._spec_on:
+            self._sbuf = torch.zeros(1616, dtype=torch.uint8).pin_memory()
+            self._s_bytes = memoryview(self._sbuf.numpy())          # records: struct '<IifI' at 16 * index
+            self._s_u32 = self._s_bytes.cast('I')                  # word 400 = sequence number of the finished launch
+            self._s_ptr = C.c_void_p(self._sbuf.data_ptr())
+            self._s_pol = (C.c_void_p(self._pol_a.data_ptr()) if self._pol_a is not None else None,
+                           C.c_void_p(self._pol_b.data_ptr()) if self._pol_b is not None else None)
         torch.cuda.synchronize(self.device)      # mailbox zero-fill and policy uploads done before the first launch
 
         self._tables = None     # lazily built (P, P_readable)
@@ -198,6 +216,35 @@ class SoccerSimultaneousEnv:
             launch(self._stream_ptr, self._hbuf.data_ptr())
         cur.synchronize()
 
+    def _speculate(self):
+        """Enqueue the step of the CURRENT state for every (joint action, draw) -- returns at once."""
+        self._spec_key = None
+        if not self._spec_on or self.needs_reset or self._state_word is None or not (0 <= self.timestep < 100):
+            return
+        word = (self._state_word & self._STATE_MASK) | (int(self.timestep) << 16)
+        self._spec_seq = seq = (self._spec_seq + 1) & 0x7FFFFFFF or 1
+        spec = self._lib.soccer_step_speculate
+        rc = spec(self._p_ref, word, self._s_pol[0], self._s_pol[1], self._s_ptr, seq, self._stream_ptr)
+        if rc == 400:               # cudaErrorInvalidResourceHandle: another device is current -- retry under a guard
+            with torch.cuda.device(self.device):
+                rc = spec(self._p_ref, word, self._s_pol[0], self._s_pol[1], self._s_ptr, seq, self._stream_ptr)
+        if rc == 0:                 # (a goal tuple injected through `env.state = ...` is refused: launch-and-wait path)
+            self._spec_key = word
+
+    def _speculated(self, word, idx):
+        """Record `idx` of the speculation launched for state `word`, or None if there is none."""
+        if self._spec_key != word or self._spec_key is None:
+            return None
+        flag, seq = self._s_u32, self._spec_seq
+        spins = 0
+        while flag[400] != seq:                       # usually already there: the launch was enqueued a call ago
+            spins += 1
+            if spins > 20000:
+                self._stream.synchronize()
+                if flag[400] != seq:
+                    return None
+        return _REC.unpack_from(self._s_bytes, idx * 16)
+
     def reset(self, seed=None, options=None):
         if seed is not None:
             self.np_random.seed(seed)
@@ -220,6 +267,7 @@ class SoccerSimultaneousEnv:
         self.lastaction = None
         self.needs_reset = False
         self.timestep = 0
+        self._speculate()
         return self.observations, infos
 
     def step(self, action):
@@ -249,10 +297,16 @@ class SoccerSimultaneousEnv:
 
         u = self.np_random.random()                                  # the one draw of SIM:395
         h = self._hnp
+        r2 = min(int(u * 4.0), 3)                                    # floor(4u): exact 2-bit form of u
+        word = (self._state_word & self._STATE_MASK) | ((int(self.timestep) & 0xFF) << 16)
+        spec = self._speculated(word, (aa * 5 + ab) * 4 + r2) if self._spec_key is not None else None
+        if spec is not None:
+            new_word, obs, reward, flags = spec
+            return self._finish_step(action, new_word, obs, reward, flags)
         self._v_u[0] = u
-        self._v_state[0] = (self._state_word & self._STATE_MASK) | ((int(self.timestep) & 0xFF) << 16)
+        self._v_state[0] = word
         h[self._OFF_ACT_A], h[self._OFF_ACT_B] = aa, ab
-        h[self._OFF_RNG8] = min(int(u * 4.0), 3)                     # floor(4u): exact 2-bit form of u
+        h[self._OFF_RNG8] = r2
 
         if self._step_args is None:
             base = self._dbuf.data_ptr() if self._staged else self._hbuf.data_ptr()
@@ -274,27 +328,30 @@ class SoccerSimultaneousEnv:
             check(self._lib.soccer_step_ex(p_ref, a_ref, stream), "soccer_step_ex")
         self._roundtrip(launch)
 
-        new_word = int(self._v_state[0])
-        obs = int(self._v_obs[0])
-        reward = float(self._v_reward[0])
-        flags = int(h[self._OFF_FLAGS])
-        done = bool(flags & 1)
-        prob = self._mp[(flags >> 4) & 0xF] * (1.0, 0.5, 0.25)[(flags >> 2) & 3]   # mp * nsp, SIM:241
+        return self._finish_step(action, int(self._v_state[0]), int(self._v_obs[0]), float(self._v_reward[0]),
+                                 int(h[self._OFF_FLAGS]))
 
+    def _finish_step(self, action, new_word, obs, reward, flags):
+        """The bookkeeping and dict-shaped returns of SIM:396-408 from one step record of the device."""
+        done = bool(flags & 1)
         self._state_word = new_word & self._STATE_MASK
-        self.observations = {a: obs for a in self.return_agent}
-        self.lastaction = action
         self.timestep += 1
-        rewards = {a: reward for a in self.return_agent}
+        trunc = self.timestep >= 100
+        self.needs_reset = done or trunc
+        self._speculate()           # the next step's launch goes out before the dicts below are built
+        prob = self._mp[(flags >> 4) & 0xF] * (1.0, 0.5, 0.25)[(flags >> 2) & 3]   # mp * nsp, SIM:241
+        agents = self.return_agent
+        self.observations = {a: obs for a in agents}
+        self.lastaction = action
+        rewards = {a: reward for a in agents}
         if self.multiagent:
             rewards['player_b'] *= -1
-        dones = {a: done for a in self.return_agent}
-        truncateds = {a: self.timestep >= 100 for a in self.return_agent}
+        dones = {a: done for a in agents}
+        truncateds = {a: trunc for a in agents}
         p2 = self._round_cache.get(prob)
         if p2 is None:
             p2 = self._round_cache[prob] = np.round(prob, 2)         # SIM:405; a handful of distinct values
-        infos = {a: {"p": p2} for a in self.return_agent}
-        self.needs_reset = any(dones.values()) or any(truncateds.values())
+        infos = {a: {"p": p2} for a in agents}
         return self.observations, rewards, dones, truncateds, infos
 
     # ------------------------------------------------------------------ transition tables (K3)

@@ -242,3 +242,41 @@ def test_make_factory():
     assert e.slip_prob == 0.2 and e.width == 7          # gym_soccer/__init__.py:5-12 (commented block)
     v = pkg.make("SoccerSimultaneous-v0", num_envs=8, slip_prob=0.0)
     assert v.num_envs == 8
+
+
+# ---- the speculative step (soccer_step_speculate: every (joint action, draw) of the current state in one launch,
+#      enqueued before the action is known) returns what the launch-and-wait step returns
+@pytest.mark.parametrize("w,h,mode", [(5, 4, "multi"), (5, 4, "a_free"), (5, 4, "b_free"), (7, 5, "multi"), (6, 4, "b_free")])
+def test_speculative_step_equals_launch_and_wait(Env, monkeypatch, w, h, mode):
+    rs = np.random.RandomState(7)
+    kw = {}
+    probe = Env(width=w, height=h)
+    if mode != "multi":
+        pol = {s: int(a) for s, a in enumerate(rs.randint(0, 5, probe.nS))}
+        kw["player_b_policy" if mode == "a_free" else "player_a_policy"] = pol
+    envs = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("SOCCER_B200_SINGLE_ENV_SPECULATE", flag)
+        envs.append(Env(width=w, height=h, seed=11, **kw))
+    spec, plain = envs
+    assert spec._spec_on and not plain._spec_on
+    assert spec.reset() == plain.reset()
+    a0 = spec.return_agent[0]
+    hits = 0
+    for t in range(1500):
+        if t % 97 == 5:                                   # state injection and a changed clock invalidate the speculation
+            st = probe._reverse_state_space[int(rs.randint(1, probe.nS))]
+            spec.state = st
+            plain.state = st
+        if t % 131 == 7:
+            spec.timestep = plain.timestep = int(rs.randint(0, 99))
+        act = {'player_a': int(rs.randint(5)), 'player_b': int(rs.randint(5))} if spec.multiagent else {a0: int(rs.randint(5))}
+        hits += spec._spec_key is not None
+        out_s, out_p = spec.step(act), plain.step(act)
+        assert out_s == out_p, t
+        assert spec.state == plain.state and spec.timestep == plain.timestep and spec.needs_reset == plain.needs_reset
+        for k in out_s[1]:                                # -0.0 == 0.0: compare the sign too (SIM:243-244, B = -A)
+            assert np.signbit(out_s[1][k]) == np.signbit(out_p[1][k])
+        if spec.needs_reset:
+            assert spec.reset() == plain.reset()
+    assert hits > 1300                                    # the speculation is what served the steps
