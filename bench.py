@@ -50,14 +50,18 @@ def measured_peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic(kernel_prefix):
+def ncu_traffic(kernel_prefix, exact=None):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the
-    committed ncu --set full capture (profiles/ncu_traffic.json); None if there is none."""
+    committed ncu --set full capture (profiles/ncu_traffic.json); None if there is none.  `exact`: the instantiation
+    the timed region launches (preferred); else the first instantiation of `kernel_prefix`."""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            for name, rec in json.load(f).items():
-                if name.startswith(kernel_prefix + "<"):
-                    return rec["dram_bytes_per_launch"], rec["source"]
+            recs = {name.split("::")[-1]: rec for name, rec in json.load(f).items()}
+        if exact in recs:
+            return recs[exact]["dram_bytes_per_launch"], recs[exact]["source"] + " [" + exact + "]"
+        for name, rec in recs.items():
+            if name.startswith(kernel_prefix + "<"):
+                return rec["dram_bytes_per_launch"], rec["source"] + " [" + name + "]"
     except Exception:  # noqa: BLE001
         pass
     return None, None
@@ -867,7 +871,9 @@ def run_ours(args):
         py_ref = {"error": repr(e)}
 
     kname = "k_step_table" if env.kernel == "table" else "k_step_fast"
-    traffic, traffic_src = ncu_traffic(kname) if N == (1 << 24) else (None, None)
+    # the timed launches are the STATS instantiations (statistics fused into the step)
+    kexact = "k_step_table<0, 0, 0, 0, 1>" if env.kernel == "table" else "k_step_fast<0, 0, 0>"
+    traffic, traffic_src = ncu_traffic(kname, kexact) if N == (1 << 24) else (None, None)
     narrow_api = ("SoccerVecEnv.step_host(narrow=True): uint8 act_a / act_b / draws up; obs uint16, reward int8, flags "
                   "uint8 down; every step waits for its results")
     e2e_narrow = {"value": e2e_value, "h2d_bytes_per_step": 3 * N, "d2h_bytes_per_step": 4 * N, "checksum": checksum,

@@ -89,6 +89,14 @@ def test_argument_errors_without_gpu(L):
     assert lib.soccer_step_ex(C.byref(L.Pitch(7, 5, 0.0)), C.byref(a), None) == -5                  # no table for 7x5
     assert lib.soccer_step_table_packed_philox(C.byref(L.Pitch(5, 4, 0.2)), v16, v16, v16, 0, 0, 0, v16, 8, None) == -3
     assert lib.soccer_rollout(C.byref(p), v16, None, None, 0, 0, (1 << 28) + 1, 0, 0, None, None, None, None, 8, None) == -1
+    # the speculative single-env step: a 2-bit draw is all it can enumerate (slip 0), field-cell states of a running
+    # episode only (a goal cell / needs_reset / equal cells are refused), a 16-byte aligned record buffer
+    ok_word = 1 | (2 << 8)
+    assert lib.soccer_step_speculate(C.byref(L.Pitch(5, 4, 0.2)), ok_word, None, None, v16, 1, None) == -3
+    assert lib.soccer_step_speculate(C.byref(p), ok_word, None, None, None, 1, None) == -1
+    assert lib.soccer_step_speculate(C.byref(p), ok_word, None, None, C.c_void_p(8), 1, None) == -1
+    for bad in (0x80 | (2 << 8), 1 | (0xC1 << 8), ok_word | (1 << 25), 1 | (1 << 8), 20 | (2 << 8)):
+        assert lib.soccer_step_speculate(C.byref(p), bad, None, None, v16, 1, None) == -1
 
 
 @pytest.mark.parametrize("tag", [t for t in golden_tags("table") if t.endswith("multi")])
