@@ -673,8 +673,10 @@ def run_ours(args):
         os.environ.pop("SOCCER_B200_SINGLE_ENV_STAGED", None)
         os.environ.pop("SOCCER_B200_SINGLE_ENV_SPECULATE", None)
         extra["config1_single_env_dropin"] = dict(c1, note="20,000 step() calls of ONE env through the reference's class "
-                                                  "surface; latency-bound (one launch + sync per step), reported next to "
-                                                  "the reference's 29.6 k steps/s Python loop (BASELINE.md)")
+                                                  "surface; latency-bound: speculative = one launch per step that steps the "
+                                                  "new state for all 25 joint actions x 4 draws ahead of the next call, "
+                                                  "zero_copy / staged = one launch + one wait per step; reported next to "
+                                                  "cpu_baseline.python_reference (the unmodified reference's loop on this host)")
         # K1 with a state tensor far beyond the L2 (2^26 envs: 268 MB of state, 1.34 GB per step): the DRAM-only figure
         n6 = 1 << 26
         e6 = SoccerVecEnv(n6, device=dev, kernel=args.kernel, want_reset_obs=False)
