@@ -378,29 +378,27 @@ __global__ void __launch_bounds__(kThreads) k_step_generic(const PitchDev P, con
 // writes the 100 results into (pinned host) memory while the caller is still busy; step() then picks record
 // (aa * 5 + ab) * 4 + floor(4u).  One thread per (joint action, draw); no shared memory, no look-up table: the two
 // candidate cells are computed arithmetically.  Record = { next state word (no auto-reset: needs_reset is set like
-// SIM:406), obs, reward bits, detail flags }; word 400 = seq, stored last with release semantics.
+// SIM:406), obs, reward bits, detail flags | seq << 8 }, written with ONE 128-bit store: the sequence number travels in
+// the same PCIe write as the data it vouches for, so there is no fence, no barrier and no separate flag on the critical
+// path -- the reader polls the last word of the record it wants.
 __global__ void __launch_bounds__(128)
 k_step_speculate(const PitchDev P, uint32_t s, const int8_t* __restrict__ policy_a, const int8_t* __restrict__ policy_b,
                  uint32_t* __restrict__ rec, uint32_t seq)
 {
     const uint32_t i = threadIdx.x;
-    if (i < 100u) {
-        const uint32_t ja = i >> 2, r = i & 3u;
-        uint32_t aa = ja / 5u, ab = ja - aa * 5u;
-        const uint32_t a = s & 0xFFu, b = (s >> 8) & 0xFFu, t = (s >> 16) & 0xFFu, p = (s >> 24) & 1u;
-        const int32_t cur = obs_index(P, a, b, p);
-        if (policy_a) aa = (uint32_t)policy_a[cur];        // SIM:187-188: the folded player's table policy
-        if (policy_b) ab = (uint32_t)policy_b[cur];
-        const uint32_t ma = (aa & 7u) > 4u ? 0u : (aa & 7u), mb = (ab & 7u) > 4u ? 0u : (ab & 7u);   // as build_cand_lut
-        const uint32_t na = next_cell_code(P, a, p ^ 1u, ma), nb = next_cell_code(P, b, p, mb);
-        const Resolved o = resolve_cand(na, nb, a, b, p, aa == 0, ab == 0, r);
-        const StepOut out = finish_step<false, true>(P, o, t, 0u, 0u, policy_a != nullptr);
-        uint4 v = make_uint4(out.state, (uint32_t)out.obs, __float_as_uint(out.reward), out.flags);
-        reinterpret_cast<uint4*>(rec)[i] = v;
-        __threadfence_system();
-    }
-    __syncthreads();
-    if (i == 0) asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(rec + 400), "r"(seq) : "memory");
+    if (i >= 100u) return;
+    const uint32_t ja = i >> 2, r = i & 3u;
+    uint32_t aa = ja / 5u, ab = ja - aa * 5u;
+    const uint32_t a = s & 0xFFu, b = (s >> 8) & 0xFFu, t = (s >> 16) & 0xFFu, p = (s >> 24) & 1u;
+    const int32_t cur = obs_index(P, a, b, p);
+    if (policy_a) aa = (uint32_t)policy_a[cur];        // SIM:187-188: the folded player's table policy
+    if (policy_b) ab = (uint32_t)policy_b[cur];
+    const uint32_t ma = (aa & 7u) > 4u ? 0u : (aa & 7u), mb = (ab & 7u) > 4u ? 0u : (ab & 7u);   // as build_cand_lut
+    const uint32_t na = next_cell_code(P, a, p ^ 1u, ma), nb = next_cell_code(P, b, p, mb);
+    const Resolved o = resolve_cand(na, nb, a, b, p, aa == 0, ab == 0, r);
+    const StepOut out = finish_step<false, true>(P, o, t, 0u, 0u, policy_a != nullptr);
+    asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" :: "l"(rec + 4u * i), "r"(out.state), "r"((uint32_t)out.obs),
+                 "r"(__float_as_uint(out.reward)), "r"((out.flags & 0xFFu) | (seq << 8)) : "memory");
 }
 
 // ------------------------------------------------------------------ K3 sweep
@@ -1943,7 +1941,7 @@ int soccer_stats_allreduce_p2p(const uint64_t* peer_ptrs, int32_t rank, int32_t 
 int soccer_step_speculate(const soccer_pitch* pitch, uint32_t state_word, const int8_t* policy_a, const int8_t* policy_b,
                           uint32_t* records, uint32_t seq, soccer_stream_t stream)
 {
-    if (!records || !aligned(records, 16)) return SOCCER_EINVAL;
+    if (!records || !aligned(records, 16) || seq >= (1u << 24)) return SOCCER_EINVAL;
     PitchDev P; const int rc = make_pitch_dev(pitch, &P); if (rc) return rc;
     if (P.slip) return SOCCER_ESLIP;                               // the draw is not 2 bits: nothing to enumerate
     const uint32_t a = state_word & 0xFFu, b = (state_word >> 8) & 0xFFu;

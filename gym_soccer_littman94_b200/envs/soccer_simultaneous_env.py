@@ -75,6 +75,7 @@ class SoccerSimultaneousEnv:
         self.multiagent = player_a_policy is None and player_b_policy is None
         self.return_agent = ['player_a', 'player_b'] if self.multiagent else ['player_a'] \
             if player_a_policy is None else ['player_b']
+        self._n_agents = len(self.return_agent)
         self.np_random = np.random.RandomState()
         self.np_random.seed(self.seed)
 
@@ -119,9 +120,9 @@ class SoccerSimultaneousEnv:
         self._spec_key, self._spec_seq = None, 0
         self._p_ref = C.byref(self._pitch)
         if self._spec_on:
-            self._sbuf = torch.zeros(1616, dtype=torch.uint8).pin_memory()
+            self._sbuf = torch.zeros(1600, dtype=torch.uint8).pin_memory()
             self._s_bytes = memoryview(self._sbuf.numpy())          # records: struct '<IifI' at 16 * index
-            self._s_u32 = self._s_bytes.cast('I')                  # word 400 = sequence number of the finished launch
+            self._s_u32 = self._s_bytes.cast('I')                  # word 3 of a record: detail flags | seq << 8
             self._s_ptr = C.c_void_p(self._sbuf.data_ptr())
             self._s_pol = (C.c_void_p(self._pol_a.data_ptr()) if self._pol_a is not None else None,
                            C.c_void_p(self._pol_b.data_ptr()) if self._pol_b is not None else None)
@@ -222,7 +223,7 @@ class SoccerSimultaneousEnv:
         if not self._spec_on or self.needs_reset or self._state_word is None or not (0 <= self.timestep < 100):
             return
         word = (self._state_word & self._STATE_MASK) | (int(self.timestep) << 16)
-        self._spec_seq = seq = (self._spec_seq + 1) & 0x7FFFFFFF or 1
+        self._spec_seq = seq = (self._spec_seq + 1) & 0xFFFFFF or 1
         spec = self._lib.soccer_step_speculate
         rc = spec(self._p_ref, word, self._s_pol[0], self._s_pol[1], self._s_ptr, seq, self._stream_ptr)
         if rc == 400:               # cudaErrorInvalidResourceHandle: another device is current -- retry under a guard
@@ -235,15 +236,17 @@ class SoccerSimultaneousEnv:
         """Record `idx` of the speculation launched for state `word`, or None if there is none."""
         if self._spec_key != word or self._spec_key is None:
             return None
-        flag, seq = self._s_u32, self._spec_seq
+        flag, seq, w = self._s_u32, self._spec_seq, idx * 4 + 3
         spins = 0
-        while flag[400] != seq:                       # usually already there: the launch was enqueued a call ago
+        while flag[w] >> 8 != seq:                    # usually already there: the launch was enqueued a call ago
             spins += 1
             if spins > 20000:
                 self._stream.synchronize()
-                if flag[400] != seq:
+                if flag[w] >> 8 != seq:
                     return None
-        return _REC.unpack_from(self._s_bytes, idx * 16)
+        # the sequence number travelled in the same 16-byte write as the record: read the record only now
+        new_word, obs, reward, flags = _REC.unpack_from(self._s_bytes, idx * 16)
+        return new_word, obs, reward, flags & 0xFF
 
     def reset(self, seed=None, options=None):
         if seed is not None:
@@ -270,8 +273,8 @@ class SoccerSimultaneousEnv:
         self._speculate()
         return self.observations, infos
 
-    def step(self, action):
-        assert not self.needs_reset, "Please reset the environment before taking a step"
+    def _check_action(self, action):
+        """The assert ladder of SIM:376-391, message for message."""
         assert isinstance(action, dict), "Action must be a dictionary"
         assert len(action) == 1 or len(action) == 2, "Action must be a dictionary of length 1 or 2"
         assert self.multiagent or self.player_a_policy is not None or self.player_b_policy is not None, \
@@ -288,6 +291,13 @@ class SoccerSimultaneousEnv:
             assert 'player_a' in action or 'player_b' in action, "Action must contain either 'player_a' or 'player_b'"
             assert not ('player_a' in action and 'player_b' in action), \
                 "Action must contain only one of 'player_a' or 'player_b'"
+
+    def step(self, action):
+        assert not self.needs_reset, "Please reset the environment before taking a step"
+        # a well-formed action (the common case) passes every assert of SIM:376-391: skip the ladder
+        if not (type(action) is dict and len(action) == self._n_agents and self.return_agent[0] in action
+                and self.return_agent[-1] in action):
+            self._check_action(action)
         aa = 0 if self._pol_a is not None else int(action['player_a'])
         ab = 0 if self._pol_b is not None else int(action['player_b'])
         if not (0 <= aa < self.nA and 0 <= ab < self.nA):
@@ -340,19 +350,17 @@ class SoccerSimultaneousEnv:
         self.needs_reset = done or trunc
         self._speculate()           # the next step's launch goes out before the dicts below are built
         prob = self._mp[(flags >> 4) & 0xF] * (1.0, 0.5, 0.25)[(flags >> 2) & 3]   # mp * nsp, SIM:241
-        agents = self.return_agent
-        self.observations = {a: obs for a in agents}
-        self.lastaction = action
-        rewards = {a: reward for a in agents}
-        if self.multiagent:
-            rewards['player_b'] *= -1
-        dones = {a: done for a in agents}
-        truncateds = {a: trunc for a in agents}
         p2 = self._round_cache.get(prob)
         if p2 is None:
             p2 = self._round_cache[prob] = np.round(prob, 2)         # SIM:405; a handful of distinct values
-        infos = {a: {"p": p2} for a in agents}
-        return self.observations, rewards, dones, truncateds, infos
+        self.lastaction = action
+        if self.multiagent:                                          # literal dicts: same keys, same order, less interpreter time
+            self.observations = {'player_a': obs, 'player_b': obs}
+            return (self.observations, {'player_a': reward, 'player_b': reward * -1}, {'player_a': done, 'player_b': done},
+                    {'player_a': trunc, 'player_b': trunc}, {'player_a': {"p": p2}, 'player_b': {"p": p2}})
+        a = self.return_agent[0]
+        self.observations = {a: obs}
+        return self.observations, {a: reward}, {a: done}, {a: trunc}, {a: {"p": p2}}
 
     # ------------------------------------------------------------------ transition tables (K3)
     def _sweep(self):

@@ -192,10 +192,12 @@ int soccer_step_ex(const soccer_pitch *pitch, const soccer_step_args *args, socc
  * state_word: CELL-layout state of a running episode (field cells, timestep in bits 16..23, needs_reset clear).
  * One launch steps that state for all 25 joint actions x 4 values of the 2-bit step draw (a folded player's action is
  * its table policy's, SIM:187-188) WITHOUT auto-reset and writes 100 records of four 32-bit words
- *     { next state word (needs_reset set when the episode ended, SIM:406), obs, reward (float bits), detail flags }
- * to records[(aa * 5 + ab) * 4 + r], then stores `seq` to word 400 of `records` with release semantics at system scope.
- * `records` (1,616 bytes, 16-byte aligned) may be pinned host memory: the caller enqueues this as soon as it knows the
- * state, keeps working, and when the action and the draw arrive polls word 400 for `seq` and reads one record. */
+ *     { next state word (needs_reset set when the episode ended, SIM:406), obs, reward (float bits),
+ *       detail flags in bits 0..7 | seq << 8 }                                   (seq < 2^24)
+ * to records[(aa * 5 + ab) * 4 + r], each with ONE 128-bit store, so the sequence number arrives together with the data
+ * it vouches for.  `records` (1,600 bytes, 16-byte aligned) may be pinned host memory: the caller enqueues this as soon
+ * as it knows the state, keeps working, and when the action and the draw arrive polls the last word of the record it
+ * wants for `seq`, then reads the record. */
 int soccer_step_speculate(const soccer_pitch *pitch, uint32_t state_word, const int8_t *policy_a, const int8_t *policy_b,
                           uint32_t *records, uint32_t seq, soccer_stream_t stream);
 
