@@ -1179,13 +1179,27 @@ int step_table_slip_impl(const PitchDev& P, int64_t bytes, const soccer_step_arg
         const int64_t smem_i = smem_w + slip_int_lut_bytes(lut_bits);
         const bool queued = a->slip_index && f64 && smem_q <= 227 * 1024 - 1024;
         const bool integer = !f64 && dg_ok && smem_i <= 227 * 1024 - 1536 && !soccer_force_slip_walk();
+        // the input ring (cp.async, 2 / 3 stages) where the table leaves room for it: with the 12-bit bucket table if that
+        // fits too, else with the 10-bit one; the 6x4 table (221 KB) leaves none: register prefetch
+        const int64_t smem_cap = 227 * 1024 - 1536;
+        auto ring_bytes = [&](bool ph) { return (int64_t)slip_ring_stages(ph) * slip_i_threads<true>() * slip_ring_stage_bytes(ph); };
+        static_assert(slip_i_threads<true>() == slip_i_threads<false>(), "one CTA size for both draw sources");
+        int ring_lut_bits = 12;
+        if (smem_w + ((slip_int_lut_bytes(12) + 15) & ~15) + ring_bytes(philox) > smem_cap) ring_lut_bits = 10;
+        const int64_t smem_r = smem_w + ((slip_int_lut_bytes(ring_lut_bits) + 15) & ~15) + ring_bytes(philox);
+        const bool ring = SOCCER_SLIP_I_RING && smem_r <= smem_cap;
+#define SOCCER_LAUNCH_SLIP_I3(RO, PH, POL, RING, SMEM, BITS)                                              \
+        do {                                                                                              \
+            const int e0 = allow_big_smem(k_step_table_slip_i<RO, PH, POL, RING>, SMEM);                  \
+            if (e0) return e0;                                                                            \
+            k_step_table_slip_i<RO, PH, POL, RING><<<table_grid(n_groups, slip_i_threads<PH>()), slip_i_threads<PH>(), (size_t)(SMEM), st>>>(  \
+                P, a->table, (uint32_t)bytes, E, dg, slip_bits(BITS), a->state, act_a, act_b,             \
+                a->rng8, a->rng32, a->obs, a->reward, a->flags, a->reset_obs, n_groups, ex);              \
+        } while (0)
 #define SOCCER_LAUNCH_SLIP_I2(RO, PH, POL)                                                                \
         do {                                                                                              \
-            const int e0 = allow_big_smem(k_step_table_slip_i<RO, PH, POL>, smem_i);                      \
-            if (e0) return e0;                                                                            \
-            k_step_table_slip_i<RO, PH, POL><<<table_grid(n_groups, slip_i_threads<PH>()), slip_i_threads<PH>(), (size_t)smem_i, st>>>(  \
-                P, a->table, (uint32_t)bytes, E, dg, slip_bits(lut_bits), a->state, act_a, act_b,         \
-                a->rng8, a->rng32, a->obs, a->reward, a->flags, a->reset_obs, n_groups, ex);              \
+            if (ring) SOCCER_LAUNCH_SLIP_I3(RO, PH, POL, true, smem_r, ring_lut_bits);                    \
+            else SOCCER_LAUNCH_SLIP_I3(RO, PH, POL, false, smem_i, lut_bits);                             \
         } while (0)
 #define SOCCER_LAUNCH_SLIP_I(RO, PH)                                                                      \
         do { if (pol_bytes) SOCCER_LAUNCH_SLIP_I2(RO, PH, true); else SOCCER_LAUNCH_SLIP_I2(RO, PH, false); } while (0)
@@ -1216,6 +1230,8 @@ int step_table_slip_impl(const PitchDev& P, int64_t bytes, const soccer_step_arg
 #undef SOCCER_PICK_SLIP_T
 #undef SOCCER_LAUNCH_SLIP_T
 #undef SOCCER_LAUNCH_SLIP_I
+#undef SOCCER_LAUNCH_SLIP_I2
+#undef SOCCER_LAUNCH_SLIP_I3
         const int e = launch_status();
         if (e) return e;
         done_n = n_groups * 4;

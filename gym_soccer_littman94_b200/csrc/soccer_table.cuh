@@ -1086,6 +1086,9 @@ __device__ __forceinline__ GroupS load_group_slip(const uint4* st, const uint32_
 #ifndef SOCCER_SLIP_I_L2_PREFETCH
 #define SOCCER_SLIP_I_L2_PREFETCH 0    // iterations ahead of the register prefetch to pull into L2 (0 = off)
 #endif
+#ifndef SOCCER_SLIP_I_RING
+#define SOCCER_SLIP_I_RING 1           // cp.async input ring where shared memory allows (0: register prefetch everywhere)
+#endif
 #ifndef SOCCER_K1_SLIP_WALK_MERGED
 #define SOCCER_K1_SLIP_WALK_MERGED 1   // one walk test per group of 4 envs (else one per env)
 #endif
@@ -1094,8 +1097,48 @@ __device__ __forceinline__ GroupS load_group_slip(const uint4* st, const uint32_
 #endif
 template <bool PHILOX>
 constexpr int slip_i_threads() { return SOCCER_SLIP_I_THREADS ? SOCCER_SLIP_I_THREADS : 512; }
-// POLICY: a folded player (its table policy in shared memory, separate move look-ups); else both action bytes -> one index
-template <bool RESET_OBS, bool PHILOX, bool POLICY>
+// ---- asynchronous input ring (cp.async): global -> shared without passing through registers
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+__device__ __forceinline__ uint4 lds_v4_v(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32_v(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+// bytes of one ring stage per thread: state (16) + action bytes (4 + 4), + draw bytes (4) + 32-bit draws (16) when injected
+__host__ __device__ constexpr int slip_ring_stage_bytes(bool philox) { return philox ? 24 : 44; }
+// groups of a thread in flight behind the one being stepped; measured at 2^24 envs (profiles/r02z_time.log):
+//   injected rng32 (44 B per group and thread): register prefetch 209 G, 2 stages 228 G, 3 stages (10-bit bucket table) 219 G
+//   Philox         (24 B):                      register prefetch 246 G, 2 stages 256 G, 3 stages 270 G, 4 stages 266 G
+#ifndef SOCCER_SLIP_I_RING_STAGES
+#define SOCCER_SLIP_I_RING_STAGES 0    // 0: 2 for injected draws, 3 for Philox
+#endif
+__host__ __device__ constexpr int slip_ring_stages(bool philox)
+{
+    return SOCCER_SLIP_I_RING_STAGES ? SOCCER_SLIP_I_RING_STAGES : (philox ? 3 : 2);
+}
+
+// POLICY: a folded player (its table policy in shared memory, separate move look-ups); else both action bytes -> one index.
+// RING: the input streams of the next TWO groups of a thread are in flight as cp.async copies into a per-thread
+// shared-memory ring (the shared memory the table leaves free) while the current group is stepped out of registers --
+// twice the bytes in flight of the register prefetch, with 11 registers fewer.  ncu of the register-prefetch version:
+// 16 warps per SM, long-scoreboard stall 7.3 per issue, DRAM 55 % busy = the kernel waits for its HBM loads.
+template <bool RESET_OBS, bool PHILOX, bool POLICY, bool RING>
 __global__ void __launch_bounds__((slip_i_threads<PHILOX>()), 1)
 k_step_table_slip_i(const PitchDev P, const uint16_t* __restrict__ gtable, uint32_t table_bytes,
                     const SlipE E, const SlipDanger dg, const SlipBits lut_bits,
@@ -1132,8 +1175,29 @@ k_step_table_slip_i(const PitchDev P, const uint16_t* __restrict__ gtable, uint3
     int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool one = g < n_groups, two = SOCCER_SLIP_I_GROUPS == 2 && g + stride < n_groups;
     GroupS x0 = {}, x1 = {};
-    if (one) x0 = load_group_slip<PHILOX>(st4, a4, b4, r4, d4, g);
-    if (two) x1 = load_group_slip<PHILOX>(st4, a4, b4, r4, d4, g + stride);
+    if (RING) {
+        // the first two groups of the thread go out before the table wait (same ring layout as in the loop below)
+        const uint32_t T = blockDim.x, tid = threadIdx.x;
+        const uint32_t ring0 = smem_u32(luts) + ((uint32_t)slip_int_lut_bytes(lut_bits.bits) + 15u & ~15u);
+        const uint32_t stage_bytes = T * (uint32_t)slip_ring_stage_bytes(PHILOX);
+        const uint32_t o_d = T * 16u, o_a = PHILOX ? T * 16u : T * 32u, o_b = o_a + T * 4u, o_r = o_b + T * 4u;
+#pragma unroll
+        for (uint32_t k = 0; k < (uint32_t)slip_ring_stages(PHILOX); ++k) {
+            const int64_t gg = g + (int64_t)k * stride;
+            if (gg < n_groups) {
+                const uint32_t base = ring0 + k * stage_bytes;
+                cp_async16(base + tid * 16u, st4 + gg);
+                if (!PHILOX) cp_async16(base + o_d + tid * 16u, d4 + gg);
+                cp_async4(base + o_a + tid * 4u, a4 + gg);
+                cp_async4(base + o_b + tid * 4u, b4 + gg);
+                if (!PHILOX) cp_async4(base + o_r + tid * 4u, r4 + gg);
+            }
+            cp_async_commit();
+        }
+    } else {
+        if (one) x0 = load_group_slip<PHILOX>(st4, a4, b4, r4, d4, g);
+        if (two) x1 = load_group_slip<PHILOX>(st4, a4, b4, r4, d4, g + stride);
+    }
     wait_table(&bar);
     launder(c.tbl); launder(c.isd); launder(sc.prt);
     launder(sf.base);
@@ -1199,6 +1263,49 @@ k_step_table_slip_i(const PitchDev P, const uint16_t* __restrict__ gtable, uint3
         st_stream(f4 + gg, __byte_perm(__byte_perm(ff[0], ff[1], 0x0040), __byte_perm(ff[2], ff[3], 0x0040), 0x5410));
         if (RESET_OBS) st_stream(q4 + gg, make_uint4(ro[0], ro[1], ro[2], ro[3]));
     };
+    if (RING) {
+        // stage k of the ring: [state 16 B x T][draws 16 B x T (injected)][act_a 4 B x T][act_b 4 B x T][rng8 4 B x T (injected)]
+        const uint32_t T = blockDim.x, tid = threadIdx.x;
+        const uint32_t ring0 = smem_u32(luts) + ((uint32_t)slip_int_lut_bytes(lut_bits.bits) + 15u & ~15u);
+        const uint32_t stage_bytes = T * (uint32_t)slip_ring_stage_bytes(PHILOX);
+        const uint32_t o_d = T * 16u, o_a = PHILOX ? T * 16u : T * 32u, o_b = o_a + T * 4u, o_r = o_b + T * 4u;
+        auto issue = [&](uint32_t k, int64_t gg) {
+            if (gg < n_groups) {
+                const uint32_t base = ring0 + k * stage_bytes;
+                cp_async16(base + tid * 16u, st4 + gg);
+                if (!PHILOX) cp_async16(base + o_d + tid * 16u, d4 + gg);
+                cp_async4(base + o_a + tid * 4u, a4 + gg);
+                cp_async4(base + o_b + tid * 4u, b4 + gg);
+                if (!PHILOX) cp_async4(base + o_r + tid * 4u, r4 + gg);
+            }
+            cp_async_commit();                                       // (an empty group keeps the count uniform)
+        };
+        auto fetch = [&](uint32_t k) {
+            const uint32_t base = ring0 + k * stage_bytes;
+            GroupS x;
+            x.s = lds_v4_v(base + tid * 16u);
+            x.a = lds_u32_v(base + o_a + tid * 4u);
+            x.b = lds_u32_v(base + o_b + tid * 4u);
+            if (PHILOX) { x.r = 0u; x.d = make_uint4(0, 0, 0, 0); }
+            else { x.r = lds_u32_v(base + o_r + tid * 4u); x.d = lds_v4_v(base + o_d + tid * 16u); }
+            return x;
+        };
+        uint32_t k = 0;
+        constexpr int S = slip_ring_stages(PHILOX);
+        cp_async_wait<S - 1>();                                      // the first group (issued before the table wait)
+        if (one) x0 = fetch(0);
+        while (one) {
+            issue(k, g + S * stride);                                // stage k is free: its group sits in x0
+            do_group(x0, g);
+            cp_async_wait<S - 1>();                                  // group g + stride has landed; the later ones may be in flight
+            k = k + 1u == (uint32_t)S ? 0u : k + 1u;
+            g += stride;
+            one = g < n_groups;
+            if (one) x0 = fetch(k);
+        }
+        cp_async_wait<0>();
+        return;
+    }
     if (SOCCER_SLIP_I_GROUPS == 1) {
         // one group in flight + register prefetch of the next one (half the data registers: 1024 threads fit 64 registers)
         if (two) { /* x1 was loaded above only in the two-group variant */ }
