@@ -23,12 +23,21 @@ from __future__ import annotations
 import ctypes as C
 import os
 import struct
+import weakref
 
 import numpy as np
 import torch
 
 from .. import _lib, spaces
 from .._lib import Pitch, StepArgs, check
+
+
+def _drain(stream, *buffers):
+    """Finalizer of an env: wait for its last (speculative) launch; `buffers` are held until then."""
+    try:
+        stream.synchronize()
+    except Exception:  # noqa: BLE001  (interpreter shutdown: the context may be gone)
+        pass
 
 
 _REC = struct.Struct('<IifI')       # one record of soccer_step_speculate: state word, obs, reward, detail flags
@@ -117,7 +126,9 @@ class SoccerSimultaneousEnv:
         # SOCCER_B200_SINGLE_ENV_SPECULATE=0 keeps every step on the launch-and-wait path (A/B, tests).
         self._spec_on = (slip_prob == 0 and not self._staged
                          and os.environ.get("SOCCER_B200_SINGLE_ENV_SPECULATE", "1") == "1")
-        self._spec_key, self._spec_seq = None, 0
+        # sequence numbers start at a per-env random value: a record left in a recycled pinned block by another env's
+        # launch cannot pass for one of this env's
+        self._spec_key, self._spec_seq = None, int.from_bytes(os.urandom(3), "little")
         self._p_ref = C.byref(self._pitch)
         if self._spec_on:
             self._sbuf = torch.zeros(1600, dtype=torch.uint8).pin_memory()
@@ -127,6 +138,9 @@ class SoccerSimultaneousEnv:
             self._s_pol = (C.c_void_p(self._pol_a.data_ptr()) if self._pol_a is not None else None,
                            C.c_void_p(self._pol_b.data_ptr()) if self._pol_b is not None else None)
         torch.cuda.synchronize(self.device)      # mailbox zero-fill and policy uploads done before the first launch
+        # the kernels write into the pinned buffers behind torch's back (raw launches): drain the env's stream before
+        # the buffers can go back to the caching host allocator
+        weakref.finalize(self, _drain, self._stream, self._hbuf, self._dbuf, getattr(self, "_sbuf", None))
 
         self._tables = None     # lazily built (P, P_readable)
         self._dense = None      # lazily built (Pmat, Rmat)
