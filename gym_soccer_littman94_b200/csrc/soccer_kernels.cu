@@ -162,14 +162,35 @@ int launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaS
 inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 
 
-template <bool RESET_OBS, bool NARROW = false>
+// The single-agent modes (SIM:187-188, 243-244) on the byte-parallel rules kernel: the folded player's action byte of each
+// of the four envs is its table policy (int8[nS] in global memory, L1-resident) at the env's CURRENT observation.
+__device__ __forceinline__ uint32_t policy_actions4(const PitchDev& P, const int8_t* __restrict__ policy, const uint32_t sv[4])
+{
+    uint32_t act[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const uint32_t cur = (uint32_t)obs_index(P, sv[e] & 0xFFu, (sv[e] >> 8) & 0xFFu, (sv[e] >> 24) & 1u);
+        act[e] = (uint32_t)(uint8_t)policy[min(cur, P.nSm1)];          // the clamp keeps a corrupt state word inside the table
+    }
+    return pack4(act[0], act[1], act[2], act[3]);
+}
+
+template <bool RESET_OBS, bool NARROW = false, bool POLICY = false>
 __device__ __forceinline__ void step_group(const PitchDev& P, const Isd4& I, const uint8_t* lut, const Group4& x,
                                            int64_t g, uint4* st, uint4* obs, uint4* rew, uint32_t* flg, uint4* rob,
-                                           bool want_stats, K1Stats& acc)
+                                           bool want_stats, K1Stats& acc, const int8_t* __restrict__ policy_a = nullptr,
+                                           const int8_t* __restrict__ policy_b = nullptr)
 {
     const uint32_t sv[4] = { x.s.x, x.s.y, x.s.z, x.s.w };
     Step4 o;
-    step4_noslip<RESET_OBS>(P, I, lut, sv, x.a, x.b, x.r, o);     // byte-parallel over the 4 envs
+    uint32_t A4 = x.a, B4 = x.b;
+    if (POLICY && policy_a) A4 = policy_actions4(P, policy_a, sv);
+    if (POLICY && policy_b) B4 = policy_actions4(P, policy_b, sv);
+    step4_noslip<RESET_OBS>(P, I, lut, sv, A4, B4, x.r, o);       // byte-parallel over the 4 envs
+    if (POLICY && policy_a) {                                     // the return agent is player_b: its reward is -A's (SIM:243-244)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o.rew[e] = __float_as_uint((float)(-(int)(signed char)(o.rew4 >> (8 * e))));
+    }
     if (want_stats) {
         // timesteps live in byte 2 of the CELL-layout words
         const uint32_t ti = (sv[0] & 0xFF0000u) + (sv[1] & 0xFF0000u) + (sv[2] & 0xFF0000u) + (sv[3] & 0xFF0000u);
@@ -188,12 +209,13 @@ __device__ __forceinline__ void step_group(const PitchDev& P, const Isd4& I, con
     if (RESET_OBS) st_stream(rob + g, make_uint4(o.robs[0], o.robs[1], o.robs[2], o.robs[3]));
 }
 
-template <bool RESET_OBS, bool PHILOX = false, bool NARROW = false>
+template <bool RESET_OBS, bool PHILOX = false, bool NARROW = false, bool POLICY = false>
 __global__ void __launch_bounds__(kThreads)
 k_step_fast(const PitchDev P, uint32_t* __restrict__ state, const uint8_t* __restrict__ act_a,
             const uint8_t* __restrict__ act_b, const uint8_t* __restrict__ rng, int32_t* __restrict__ obs,
             float* __restrict__ reward, uint8_t* __restrict__ flags, int32_t* __restrict__ reset_obs,
-            int64_t n_groups, const PhiloxKey key, unsigned long long* __restrict__ stats)
+            int64_t n_groups, const PhiloxKey key, unsigned long long* __restrict__ stats,
+            const int8_t* __restrict__ policy_a = nullptr, const int8_t* __restrict__ policy_b = nullptr)
 {
     __shared__ __align__(16) uint8_t lut[kLutBytes];
     __shared__ K1StatsBlk sblk;
@@ -206,8 +228,9 @@ k_step_fast(const PitchDev P, uint32_t* __restrict__ state, const uint8_t* __res
     K1Stats acc = {};
 
     uint4* st4 = reinterpret_cast<uint4*>(state);
-    const uint32_t* a4 = reinterpret_cast<const uint32_t*>(act_a);
-    const uint32_t* b4 = reinterpret_cast<const uint32_t*>(act_b);
+    // a folded player's action stream does not exist: alias the other one (loaded, never used)
+    const uint32_t* a4 = reinterpret_cast<const uint32_t*>(POLICY && !act_a ? act_b : act_a);
+    const uint32_t* b4 = reinterpret_cast<const uint32_t*>(POLICY && !act_b ? act_a : act_b);
     const uint32_t* r4 = reinterpret_cast<const uint32_t*>(rng);
     uint4* o4 = reinterpret_cast<uint4*>(obs);
     uint4* w4 = reinterpret_cast<uint4*>(reward);
@@ -223,8 +246,8 @@ k_step_fast(const PitchDev P, uint32_t* __restrict__ state, const uint8_t* __res
         Group4 x1 = x0;
         if (two) x1 = load_group(st4, a4, b4, PHILOX ? a4 : r4, g2);
         if (PHILOX) { x0.r = philox_rng8x4(key, g); if (two) x1.r = philox_rng8x4(key, g2); }
-        step_group<RESET_OBS, NARROW>(P, I, lut, x0, g, st4, o4, w4, f4, q4, want_stats, acc);
-        if (two) step_group<RESET_OBS, NARROW>(P, I, lut, x1, g2, st4, o4, w4, f4, q4, want_stats, acc);
+        step_group<RESET_OBS, NARROW, POLICY>(P, I, lut, x0, g, st4, o4, w4, f4, q4, want_stats, acc, policy_a, policy_b);
+        if (two) step_group<RESET_OBS, NARROW, POLICY>(P, I, lut, x1, g2, st4, o4, w4, f4, q4, want_stats, acc, policy_a, policy_b);
     }
     if (want_stats) k1_stats_flush(acc, &sblk, stats, (unsigned long long)n_groups * 4ull);
 }
@@ -963,11 +986,14 @@ int soccer_step_ex(const soccer_pitch* pitch, const soccer_step_args* a, soccer_
 
     if (a->narrow != 0 && a->narrow != 1) return SOCCER_EINVAL;
     const bool narrow = a->narrow == 1;
-    const bool fast_ok = !P.slip && a->auto_reset && !a->detail && !a->policy_a && !a->policy_b &&
+    const bool pol = a->policy_a || a->policy_b;     // single-agent modes: the folded player's action stream may be NULL
+    const bool fast_ok = !P.slip && a->auto_reset && !a->detail && !(pol && narrow) &&
                          a->obs && a->reward && a->flags && a->n >= 4 &&
                          aligned(a->state, 16) && aligned(a->obs, narrow ? 8 : 16) && aligned(a->reward, narrow ? 4 : 16) &&
-                         (!a->reset_obs || aligned(a->reset_obs, 16)) && aligned(a->act_a, 4) &&
-                         aligned(a->act_b, 4) && (a->use_philox || aligned(a->rng8, 4)) && aligned(a->flags, 4) &&
+                         (!a->reset_obs || aligned(a->reset_obs, 16)) &&
+                         (a->policy_a ? (!a->act_a || aligned(a->act_a, 4)) : (a->act_a && aligned(a->act_a, 4))) &&
+                         (a->policy_b ? (!a->act_b || aligned(a->act_b, 4)) : (a->act_b && aligned(a->act_b, 4))) &&
+                         (a->use_philox || aligned(a->rng8, 4)) && aligned(a->flags, 4) &&
                          !(a->use_philox && (a->env_id_base & 3u)) &&      // Philox contract v2: a thread's 4 envs = one aligned group
                          !(narrow && (a->use_philox || a->reset_obs));     // narrow fast path: the plain step only
     int64_t done_n = 0;
@@ -1007,13 +1033,28 @@ int soccer_step_ex(const soccer_pitch* pitch, const soccer_step_args* a, soccer_
             static const int nb = resident_blocks(k_step_fast<RO, PH, NR>);                                       \
             const int e1 = launch_pdl(k_step_fast<RO, PH, NR>, grid_for(n_groups, nb), kThreads, 0, st, P, a->state, \
                                       a->act_a, a->act_b, PH ? (const uint8_t*)nullptr : a->rng8, a->obs, a->reward, \
-                                      a->flags, RO ? a->reset_obs : (int32_t*)nullptr, n_groups, key, a->stats);  \
+                                      a->flags, RO ? a->reset_obs : (int32_t*)nullptr, n_groups, key, a->stats,   \
+                                      (const int8_t*)nullptr, (const int8_t*)nullptr);                            \
             if (e1) return e1;                                                                                    \
         } while (0)
-        if (narrow) SOCCER_LAUNCH_FAST(false, false, true);
+#define SOCCER_LAUNCH_FAST_POL(RO, PH)                                                                            \
+        do {                                                                                                      \
+            static const int nb = resident_blocks(k_step_fast<RO, PH, false, true>);                              \
+            const int e1 = launch_pdl(k_step_fast<RO, PH, false, true>, grid_for(n_groups, nb), kThreads, 0, st, P, a->state, \
+                                      a->act_a, a->act_b, PH ? (const uint8_t*)nullptr : a->rng8, a->obs, a->reward, \
+                                      a->flags, RO ? a->reset_obs : (int32_t*)nullptr, n_groups, key, a->stats,   \
+                                      a->policy_a, a->policy_b);                                                  \
+            if (e1) return e1;                                                                                    \
+        } while (0)
+        if (pol) {
+            if (a->use_philox) { if (a->reset_obs) SOCCER_LAUNCH_FAST_POL(true, true); else SOCCER_LAUNCH_FAST_POL(false, true); }
+            else { if (a->reset_obs) SOCCER_LAUNCH_FAST_POL(true, false); else SOCCER_LAUNCH_FAST_POL(false, false); }
+        }
+        else if (narrow) SOCCER_LAUNCH_FAST(false, false, true);
         else if (a->use_philox) { if (a->reset_obs) SOCCER_LAUNCH_FAST(true, true, false); else SOCCER_LAUNCH_FAST(false, true, false); }
         else { if (a->reset_obs) SOCCER_LAUNCH_FAST(true, false, false); else SOCCER_LAUNCH_FAST(false, false, false); }
 #undef SOCCER_LAUNCH_FAST
+#undef SOCCER_LAUNCH_FAST_POL
         const int e = launch_status();
         if (e) return e;
         done_n = n_groups * 4;
