@@ -206,7 +206,7 @@ struct RulesStepper {
     uint32_t jlut;      // shared-window address of the 100-byte decode table of mulhi(w, 100): aa | ab << 3 | r << 6
     __device__ __forceinline__ uint32_t timestep(uint32_t s) const { return (s >> 16) & 0xFFu; }
     // the byte-parallel path keeps the four states as packed bytes (Soa4 in s[0..3]) between enter() and leave()
-    template <int VEC> __device__ __forceinline__ bool packed() const { return !SLIP && VEC == 4 && !policy_a && !policy_b; }
+    template <int VEC> __device__ __forceinline__ bool packed() const { return !SLIP && VEC == 4; }
     template <int VEC> __device__ __forceinline__ void enter(uint32_t* s) const
     {
         if (packed<VEC>()) { const Soa4 x = soa4_from_words(s); s[0] = x.A; s[1] = x.B; s[2] = x.T; s[3] = x.P; }
@@ -238,7 +238,7 @@ struct RulesStepper {
                 fw |= (o.flags & 3u) << (8 * e);
                 net += ri;
             }
-        } else if (VEC == 4 && !policy_a && !policy_b) {
+        } else if (VEC == 4) {
             // decode by table: byte = aa | ab << 3 | r << 6 at index mulhi(w, 100) (one IMAD.HI + one LDS per env on
             // the idle pipes instead of seven integer instructions on the ALU pipe that binds this kernel); the reset
             // draw is bits 2..3 of w itself
@@ -248,9 +248,21 @@ struct RulesStepper {
             const uint32_t D = pack4(d[0], d[1], d[2], d[3]);
             const uint32_t W = pack4(word[0], word[1 % VEC], word[2 % VEC], word[3 % VEC]);
             const Soa4 in = { s[0], s[1], s[2], s[3] };
+            uint32_t MA4 = D, MB4 = D >> 3;
+            if (policy_a || policy_b) {     // SIM:187-188: a table policy acts on the current observation (gathered per env)
+                uint32_t pa[4], pb[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const uint32_t cur = min((uint32_t)obs_index(P, byte_of(in.A, e), byte_of(in.B, e), byte_of(in.P, e)), P.nSm1);
+                    pa[e] = policy_a ? (uint32_t)(uint8_t)policy_a[cur] : 0u;
+                    pb[e] = policy_b ? (uint32_t)(uint8_t)policy_b[cur] : 0u;
+                }
+                if (policy_a) MA4 = pack4(pa[0], pa[1], pa[2], pa[3]);
+                if (policy_b) MB4 = pack4(pb[0], pb[1], pb[2], pb[3]);
+            }
             Soa4 out;
             Step4 o;
-            step4_core<false>(P, I, lut, in, D, D >> 3, D >> 6, o, D >> 6, W, out);
+            step4_core<false>(P, I, lut, in, MA4, MB4, D >> 6, o, D >> 6, W, out);
             s[0] = out.A; s[1] = out.B; s[2] = out.T; s[3] = out.P;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {

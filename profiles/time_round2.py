@@ -173,3 +173,16 @@ if "k2slip" in what:        # A/B of library variants (SOCCER_B200_LIB): K2 slip
             del e
         del bufs
         torch.cuda.empty_cache()
+
+if "k2pol" in what:         # K2 with an on-device TABLE policy for player A (the evaluation loop of the planners' policies)
+    n, K = 1 << 22, 16
+    bufs = (torch.empty((K, n), dtype=torch.int32, device=dev), torch.empty((K, n), dtype=torch.float32, device=dev),
+            torch.empty((K, n), dtype=torch.uint8, device=dev))
+    for name, kw in (("table 5x4", dict(kernel="table")), ("rules 5x4", dict(kernel="rules")), ("rules 7x5", dict(kernel="rules", width=7, height=5))):
+        e = SoccerVecEnv(n, device=dev, rng_mode="philox", **kw)
+        pol = torch.from_numpy(np.random.RandomState(0).randint(0, 5, e.nS).astype(np.int8)).to(dev)
+        e.reset()
+        e.rollout(64, want_streams=False, policy_a=pol)
+        ms = timed(lambda i: e.rollout(K, out=bufs, policy_a=pol), 8, warm=2)
+        report(f"K2 table policy for A, {name} n=2^22 K=16", n * K, ms, 9.125)
+        del e
