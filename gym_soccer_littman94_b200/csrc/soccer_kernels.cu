@@ -257,12 +257,13 @@ k_step_fast(const PitchDev P, uint32_t* __restrict__ state, const uint8_t* __res
 #ifndef SOCCER_FAST_SLIP_MINBLOCKS
 #define SOCCER_FAST_SLIP_MINBLOCKS 2
 #endif
-template <bool RESET_OBS, bool PHILOX>
+template <bool RESET_OBS, bool PHILOX, bool POLICY = false>
 __global__ void __launch_bounds__(kThreads, SOCCER_FAST_SLIP_MINBLOCKS)
 k_step_fast_slip(const PitchDev P, const RulesSlipArgs sa, uint32_t* __restrict__ state, const uint8_t* __restrict__ act_a,
                  const uint8_t* __restrict__ act_b, const uint8_t* __restrict__ rng, const uint32_t* __restrict__ draw,
                  int32_t* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ flags,
-                 int32_t* __restrict__ reset_obs, int64_t n_groups, const PhiloxKey key)
+                 int32_t* __restrict__ reset_obs, int64_t n_groups, const PhiloxKey key,
+                 const int8_t* __restrict__ policy_a = nullptr, const int8_t* __restrict__ policy_b = nullptr)
 {
     __shared__ __align__(16) uint8_t lut[kLutBytes];
     __shared__ __align__(16) double prt[kPrtDoubles];
@@ -274,8 +275,9 @@ k_step_fast_slip(const PitchDev P, const RulesSlipArgs sa, uint32_t* __restrict_
     const SlipCtx sc = { (uint32_t)__cvta_generic_to_shared(prt), slip_first_k(P) };
     const SlipInt fi = slip_int_ctx(ilut, slip_bits(kRulesSlipLutBits));
     uint4* st4 = reinterpret_cast<uint4*>(state);
-    const uint32_t* a4 = reinterpret_cast<const uint32_t*>(act_a);
-    const uint32_t* b4 = reinterpret_cast<const uint32_t*>(act_b);
+    // a folded player's action stream does not exist: alias the other one (loaded, never used)
+    const uint32_t* a4 = reinterpret_cast<const uint32_t*>(POLICY && !act_a ? act_b : act_a);
+    const uint32_t* b4 = reinterpret_cast<const uint32_t*>(POLICY && !act_b ? act_a : act_b);
     const uint32_t* r4 = reinterpret_cast<const uint32_t*>(rng);
     const uint4* d4 = reinterpret_cast<const uint4*>(draw);
     uint4* o4 = reinterpret_cast<uint4*>(obs);
@@ -302,9 +304,16 @@ k_step_fast_slip(const PitchDev P, const RulesSlipArgs sa, uint32_t* __restrict_
         const uint32_t r32[4] = { x.d.x, x.d.y, x.d.z, x.d.w };
         Step4 o;
         Soa4 so;
-        step4_slip_int<RESET_OBS, true>(P, I, lut, fi, sc, soa4_from_words(sv), ((x.a & 0x07070707u) << 3) | (x.b & 0x07070707u),
+        uint32_t A4 = x.a, B4 = x.b;
+        if (POLICY && policy_a) A4 = policy_actions4(P, policy_a, sv);      // SIM:187-188 (single-agent modes)
+        if (POLICY && policy_b) B4 = policy_actions4(P, policy_b, sv);
+        step4_slip_int<RESET_OBS, true>(P, I, lut, fi, sc, soa4_from_words(sv), ((A4 & 0x07070707u) << 3) | (B4 & 0x07070707u),
                                         r32, x.r, o, so);
         soa4_to_words(so, o.s);
+        if (POLICY && policy_a) {                                           // the return agent is player_b (SIM:243-244)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o.rew[e] = __float_as_uint((float)(-(int)(signed char)(o.rew4 >> (8 * e))));
+        }
         st_keep(st4 + g, make_uint4(o.s[0], o.s[1], o.s[2], o.s[3]));
         st_stream(o4 + g, make_uint4(o.obs[0], o.obs[1], o.obs[2], o.obs[3]));
         st_stream(w4 + g, make_uint4(o.rew[0], o.rew[1], o.rew[2], o.rew[3]));
@@ -999,10 +1008,12 @@ int soccer_step_ex(const soccer_pitch* pitch, const soccer_step_args* a, soccer_
     int64_t done_n = 0;
     // slip_prob > 0 with 32-bit draws (rng32 stream or Philox), the plain options: integer-threshold kernel
     RulesSlipArgs rsa = {};
-    const bool slip_fast_ok = P.slip && a->auto_reset && !a->detail && !a->policy_a && !a->policy_b && !narrow && !a->stats &&
+    const bool slip_fast_ok = P.slip && a->auto_reset && !a->detail && !narrow && !a->stats &&
                               a->obs && a->reward && a->flags && a->n >= 4 && !a->rngf64 && (a->use_philox || a->rng32) &&
                               aligned(a->state, 16) && aligned(a->obs, 16) && aligned(a->reward, 16) &&
-                              (!a->reset_obs || aligned(a->reset_obs, 16)) && aligned(a->act_a, 4) && aligned(a->act_b, 4) &&
+                              (!a->reset_obs || aligned(a->reset_obs, 16)) &&
+                              (a->policy_a ? (!a->act_a || aligned(a->act_a, 4)) : (a->act_a && aligned(a->act_a, 4))) &&
+                              (a->policy_b ? (!a->act_b || aligned(a->act_b, 4)) : (a->act_b && aligned(a->act_b, 4))) &&
                               aligned(a->flags, 4) &&
                               (a->use_philox ? (a->env_id_base & 3u) == 0 : (aligned(a->rng8, 4) && aligned(a->rng32, 16))) &&
                               slip_consts_host(P, &rsa.E, &rsa.dg) && !soccer_force_slip_walk();
@@ -1016,9 +1027,21 @@ int soccer_step_ex(const soccer_pitch* pitch, const soccer_step_args* a, soccer_
             k_step_fast_slip<RO, PH><<<grid_for(n_groups, nb), kThreads, 0, st>>>(P, rsa, a->state, a->act_a, a->act_b, \
                 a->rng8, a->rng32, a->obs, a->reward, a->flags, RO ? a->reset_obs : (int32_t*)nullptr, n_groups, key); \
         } while (0)
-        if (a->use_philox) { if (a->reset_obs) SOCCER_LAUNCH_FAST_SLIP(true, true); else SOCCER_LAUNCH_FAST_SLIP(false, true); }
+#define SOCCER_LAUNCH_FAST_SLIP_POL(RO, PH)                                                                       \
+        do {                                                                                                      \
+            static const int nb = resident_blocks(k_step_fast_slip<RO, PH, true>);                                \
+            k_step_fast_slip<RO, PH, true><<<grid_for(n_groups, nb), kThreads, 0, st>>>(P, rsa, a->state, a->act_a, a->act_b, \
+                a->rng8, a->rng32, a->obs, a->reward, a->flags, RO ? a->reset_obs : (int32_t*)nullptr, n_groups, key, \
+                a->policy_a, a->policy_b);                                                                        \
+        } while (0)
+        if (a->policy_a || a->policy_b) {
+            if (a->use_philox) { if (a->reset_obs) SOCCER_LAUNCH_FAST_SLIP_POL(true, true); else SOCCER_LAUNCH_FAST_SLIP_POL(false, true); }
+            else { if (a->reset_obs) SOCCER_LAUNCH_FAST_SLIP_POL(true, false); else SOCCER_LAUNCH_FAST_SLIP_POL(false, false); }
+        }
+        else if (a->use_philox) { if (a->reset_obs) SOCCER_LAUNCH_FAST_SLIP(true, true); else SOCCER_LAUNCH_FAST_SLIP(false, true); }
         else { if (a->reset_obs) SOCCER_LAUNCH_FAST_SLIP(true, false); else SOCCER_LAUNCH_FAST_SLIP(false, false); }
 #undef SOCCER_LAUNCH_FAST_SLIP
+#undef SOCCER_LAUNCH_FAST_SLIP_POL
         const int e = launch_status();
         if (e) return e;
         done_n = n_groups * 4;

@@ -519,19 +519,21 @@ def test_stats_allreduce_p2p_kernel_two_ranks_on_one_gpu(dev):
 
 
 # ----------------------------------------------------------------------------- single-agent modes on the byte-parallel rules kernel
+@pytest.mark.parametrize("slip", [0.0, 0.2])
 @pytest.mark.parametrize("mode", ["a_free", "b_free"])
 @pytest.mark.parametrize("w,h", [(5, 4), (7, 5), (9, 6)])
-def test_single_agent_rules_kernel_vs_oracle(dev, oracle, w, h, mode):
+def test_single_agent_rules_kernel_vs_oracle(dev, oracle, w, h, mode, slip):
     """SIM:187-188, 243-244 on pitches without a table: the folded player's table policy is gathered inside the
-    byte-parallel rules kernel (k_step_fast<..., POLICY>; round 1 sent this mode to the one-env-per-thread kernel);
-    obs / reward (sign of the return agent) / flags / post-reset obs of every env vs the oracle, ragged batch."""
+    byte-parallel rules kernels (k_step_fast<..., POLICY>, k_step_fast_slip<..., POLICY>; round 1 sent this mode to the
+    one-env-per-thread kernel); obs / reward (sign of the return agent) / flags / post-reset obs of every env vs the
+    oracle, ragged batch, slip 0 (2-bit draws) and slip 0.2 (32-bit draws)."""
     from gym_soccer_littman94_b200.envs import SoccerVecEnv
     N, T = 4099, 300
-    rs = np.random.RandomState(w * 100 + h + (mode == "a_free"))
+    rs = np.random.RandomState(w * 100 + h + (mode == "a_free") + int(slip * 10))
     nS = oracle.n_states(w, h)
     pol = rs.randint(0, 5, nS).astype(np.int8)
     key = "player_b_policy" if mode == "a_free" else "player_a_policy"
-    m = oracle.OracleModel(w, h, 0.0, **{key: {s: int(a) for s, a in enumerate(pol)}})
+    m = oracle.OracleModel(w, h, slip, **{key: {s: int(a) for s, a in enumerate(pol)}})
     n_isd = len(m.isd)
     init = rs.randint(0, 4, N).astype(np.uint8)
     states = np.zeros(N, oracle.STATE_DTYPE)
@@ -540,16 +542,19 @@ def test_single_agent_rules_kernel_vs_oracle(dev, oracle, w, h, mode):
     ts = np.zeros(N, np.int32)
     act = rs.randint(0, 5, (T, N)).astype(np.uint8)
     rng8 = rs.randint(0, 16, (T, N)).astype(np.uint8)
-    eo, er, ef, ero = m.rollout_injected(states, ts, act, act, rng8, n_threads=8)
-    env = SoccerVecEnv(N, width=w, height=h, device=dev, kernel="rules", **{key: pol})
+    r32 = rs.randint(0, 2**32, (T, N), dtype=np.uint64).astype(np.uint32) if slip else None
+    eo, er, ef, ero = m.rollout_injected(states, ts, act, act, rng8, rng32=r32, n_threads=8)
+    env = SoccerVecEnv(N, width=w, height=h, slip_prob=slip, device=dev, kernel="rules", **{key: pol})
     env.reset(_t(init << 2, dev))
-    stats = torch.zeros(6, dtype=torch.int64, device=dev)
+    stats = torch.zeros(6, dtype=torch.int64, device=dev) if not slip else None
     for t in range(T):
         a = _t(act[t], dev)
-        o, r, f, ro = env.step(a if mode == "a_free" else None, None if mode == "a_free" else a, _t(rng8[t], dev), stats=stats)
+        kw = dict(rng32=_t(r32[t].view(np.int32), dev)) if slip else dict(stats=stats)
+        o, r, f, ro = env.step(a if mode == "a_free" else None, None if mode == "a_free" else a, _t(rng8[t], dev), **kw)
         assert np.array_equal(o.cpu().numpy(), eo[t]) and np.array_equal(f.cpu().numpy(), ef[t]), t
         assert np.array_equal(r.cpu().numpy(), er[t]) and np.array_equal(ro.cpu().numpy(), ero[t]), t
-    # fused statistics count by player A's sign whatever the return agent (soccer_b200.h): goals_A - goals_B = -sum(r) for b_free
-    st = stats.cpu().numpy()
-    sign = 1 if mode == "a_free" else -1
-    assert st[4] == N * T and st[1] - st[2] == sign * int(er.sum()) and st[0] == int((ef != 0).sum())
+    if not slip:
+        # fused statistics count by player A's sign whatever the return agent (soccer_b200.h): goals_A - goals_B = -sum(r) for b_free
+        st = stats.cpu().numpy()
+        sign = 1 if mode == "a_free" else -1
+        assert st[4] == N * T and st[1] - st[2] == sign * int(er.sum()) and st[0] == int((ef != 0).sum())
