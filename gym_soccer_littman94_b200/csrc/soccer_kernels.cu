@@ -1157,16 +1157,18 @@ int soccer_rollout(const soccer_pitch* pitch, uint32_t* state, const int8_t* pol
     if (P.slip) {
         rsa.use_int = slip_consts_host(P, &rsa.E, &rsa.dg) && !soccer_force_slip_walk() ? 1 : 0;
         // uniform policy, 4 envs per thread: combination and slot of the 32-bit draw by integer thresholds, resolution
-        // byte-parallel (step4_slip_int).  With table policies (or when the fast path is off) the scalar walk, one env per
+        // byte-parallel (step4_slip_int), table policies gathered per env.  When the fast path is off the scalar walk, one env per
         // thread: it needs ~170 registers with 4 envs per thread and measured 2.2x faster that way (44 vs 20 G env-steps/s)
-        if (rsa.use_int && vec && !policy_a && !policy_b) {
-            if (streams) {
-                static const int nb = resident_blocks(k_rollout_slipi<true>);
-                k_rollout_slipi<true><<<grid_for(n / 4, nb), kThreads, 0, st>>>(P, ra, rsa);
-            } else {
-                static const int nb = resident_blocks(k_rollout_slipi<false>);
-                k_rollout_slipi<false><<<grid_for(n / 4, nb), kThreads, 0, st>>>(P, ra, rsa);
-            }
+        if (rsa.use_int && vec) {
+#define SOCCER_LAUNCH_ROLLOUT_SLIPI(STR, POL)                                                            \
+            do {                                                                                         \
+                static const int nb = resident_blocks(k_rollout_slipi<STR, POL>);                        \
+                k_rollout_slipi<STR, POL><<<grid_for(n / 4, nb), kThreads, 0, st>>>(P, ra, rsa, policy_a, policy_b); \
+            } while (0)
+            const bool polr = policy_a || policy_b;
+            if (streams) { if (polr) SOCCER_LAUNCH_ROLLOUT_SLIPI(true, true); else SOCCER_LAUNCH_ROLLOUT_SLIPI(true, false); }
+            else { if (polr) SOCCER_LAUNCH_ROLLOUT_SLIPI(false, true); else SOCCER_LAUNCH_ROLLOUT_SLIPI(false, false); }
+#undef SOCCER_LAUNCH_ROLLOUT_SLIPI
         }
         else if (streams) SOCCER_LAUNCH_ROLLOUT(1, true, true, n);
         else SOCCER_LAUNCH_ROLLOUT(1, false, true, n);

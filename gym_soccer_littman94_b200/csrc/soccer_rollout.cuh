@@ -294,9 +294,10 @@ struct RulesStepper {
 
 // slip_prob > 0, uniform policy, any pitch: four envs per thread, combination and slot by integer thresholds, resolution
 // byte-parallel (step4_slip_int)
+template <bool POLICY>
 struct RulesSlipIntStepper {
-    static constexpr bool kCollective = false, kHasPolicy = false;
-    const PitchDev& P; const uint8_t* lut; Isd4 I; SlipCtx sc; SlipInt fi;
+    static constexpr bool kCollective = false, kHasPolicy = POLICY;
+    const PitchDev& P; const uint8_t* lut; Isd4 I; SlipCtx sc; SlipInt fi; const int8_t* policy_a; const int8_t* policy_b;
     __device__ __forceinline__ uint32_t timestep(uint32_t s) const { return (s >> 16) & 0xFFu; }
     template <int VEC> __device__ __forceinline__ void enter(uint32_t* s) const
     {
@@ -308,7 +309,7 @@ struct RulesSlipIntStepper {
     }
     template <int VEC>
     __device__ __forceinline__ void step(uint32_t* s, const uint32_t* word, uint32_t* oo, uint32_t* rr,
-                                         uint32_t& fw, int32_t& net, bool) const
+                                         uint32_t& fw, int32_t& net, bool flip) const
     {
         static_assert(VEC == 4, "four envs per thread");
         uint32_t ja[4], r32[4];
@@ -318,13 +319,29 @@ struct RulesSlipIntStepper {
             r32[e] = philox_r32(word[e]);
         }
         const Soa4 in = { s[0], s[1], s[2], s[3] };
+        const uint32_t W = pack4(word[0], word[1], word[2], word[3]);
         Soa4 out;
         Step4 o;
-        step4_slip_int<false, false>(P, I, lut, fi, sc, in, pack4(ja[0], ja[1], ja[2], ja[3]), r32,
-                                     pack4(word[0], word[1], word[2], word[3]), o, out);
+        if (POLICY) {                   // SIM:187-188: a table policy acts on the current observation (gathered per env)
+            uint32_t j8[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                uint32_t aa = (ja[e] * 52u) >> 8, ab = ja[e] - aa * 5u;
+                const uint32_t cur = min((uint32_t)obs_index(P, byte_of(in.A, e), byte_of(in.B, e), byte_of(in.P, e)), P.nSm1);
+                if (policy_a) aa = (uint32_t)(uint8_t)policy_a[cur] & 7u;
+                if (policy_b) ab = (uint32_t)(uint8_t)policy_b[cur] & 7u;
+                j8[e] = aa * 8u + ab;
+            }
+            step4_slip_int<false, true>(P, I, lut, fi, sc, in, pack4(j8[0], j8[1], j8[2], j8[3]), r32, W, o, out);
+        } else {
+            step4_slip_int<false, false>(P, I, lut, fi, sc, in, pack4(ja[0], ja[1], ja[2], ja[3]), r32, W, o, out);
+        }
         s[0] = out.A; s[1] = out.B; s[2] = out.T; s[3] = out.P;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) { oo[e] = o.obs[e]; rr[e] = o.rew[e]; }
+        for (int e = 0; e < 4; ++e) {
+            oo[e] = o.obs[e];
+            rr[e] = flip ? __float_as_uint((float)(-(int)(signed char)(o.rew4 >> (8 * e)))) : o.rew[e];
+        }
         fw = o.flags4;
         net += o.rew_sum;
     }
@@ -660,9 +677,10 @@ k_rollout(const PitchDev P, const int8_t* __restrict__ policy_a, const int8_t* _
 // 5.6 KB of shared memory next to the 4 KB candidate table.
 constexpr int kRulesSlipLutBits = 10;
 struct RulesSlipArgs { SlipE E; SlipDanger dg; int32_t use_int; };
-template <bool STREAMS>
+template <bool STREAMS, bool POLICY>
 __global__ void __launch_bounds__(kThreads, 2)
-k_rollout_slipi(const PitchDev P, const RolloutArgs a, const RulesSlipArgs sa)
+k_rollout_slipi(const PitchDev P, const RolloutArgs a, const RulesSlipArgs sa, const int8_t* __restrict__ policy_a,
+                const int8_t* __restrict__ policy_b)
 {
     __shared__ __align__(16) uint8_t lut[kLutBytes];
     __shared__ __align__(16) double prt[kPrtDoubles];
@@ -674,7 +692,7 @@ k_rollout_slipi(const PitchDev P, const RolloutArgs a, const RulesSlipArgs sa)
     if (threadIdx.x < 5) blk.v[threadIdx.x] = 0;
     __syncthreads();
     const SlipCtx sc = { (uint32_t)__cvta_generic_to_shared(prt), slip_first_k(P) };
-    const RulesSlipIntStepper S = { P, lut, make_isd4(P), sc, slip_int_ctx(ilut, slip_bits(kRulesSlipLutBits)) };
+    const RulesSlipIntStepper<POLICY> S = { P, lut, make_isd4(P), sc, slip_int_ctx(ilut, slip_bits(kRulesSlipLutBits)), policy_a, policy_b };
     rollout_body<4, STREAMS>(S, a, &blk);
 }
 

@@ -178,7 +178,8 @@ if "k2pol" in what:         # K2 with an on-device TABLE policy for player A (th
     n, K = 1 << 22, 16
     bufs = (torch.empty((K, n), dtype=torch.int32, device=dev), torch.empty((K, n), dtype=torch.float32, device=dev),
             torch.empty((K, n), dtype=torch.uint8, device=dev))
-    for name, kw in (("table 5x4", dict(kernel="table")), ("rules 5x4", dict(kernel="rules")), ("rules 7x5", dict(kernel="rules", width=7, height=5))):
+    for name, kw in (("table 5x4", dict(kernel="table")), ("rules 5x4", dict(kernel="rules")), ("rules 7x5", dict(kernel="rules", width=7, height=5)),
+                     ("table 5x4 slip 0.2", dict(kernel="table", slip_prob=0.2)), ("rules 7x5 slip 0.2", dict(kernel="rules", width=7, height=5, slip_prob=0.2))):
         e = SoccerVecEnv(n, device=dev, rng_mode="philox", **kw)
         pol = torch.from_numpy(np.random.RandomState(0).randint(0, 5, e.nS).astype(np.int8)).to(dev)
         e.reset()
