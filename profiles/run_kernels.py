@@ -1,6 +1,6 @@
 """Short driver for ncu captures: a few launches of each hot kernel at its bench size.
 
-    python profiles/run_kernels.py [k1_table|k1_table_stats|k1_single_agent|k1_rules|k2_table|k2_rules|k1_slip|k2_slip|k1_philox|k1_packed|replay|all] [--envs N]
+    python profiles/run_kernels.py [k1_table|k1_table_stats|k1_single_agent|k1_rules|k2_table|k2_rules|k1_slip|k2_slip|k1_philox|k1_packed|rules_modes|replay|all] [--envs N]
 """
 import argparse
 import contextlib
@@ -131,6 +131,43 @@ def k2_slip(n, K, iters):
             e2.rollout(K, out=bufs)
 
 
+def rules_modes(n, iters):
+    """The rules kernels of a pitch without a table (7x5) in the modes round 2 moved onto the byte-parallel paths:
+    K1 slip 0.2 (rng32 / Philox), K1 single-agent (slip 0 and 0.2), K2 slip 0.2, K2 with a table policy."""
+    import numpy as np
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(0)
+    a, b, r = (torch.randint(0, hi, (n,), dtype=torch.uint8, device=dev, generator=g) for hi in (5, 5, 16))
+    r32 = torch.randint(-2**31, 2**31 - 1, (n,), dtype=torch.int32, device=dev, generator=g)
+    probe = SoccerVecEnv(4, width=7, height=5, device=dev, kernel="rules")
+    pol = np.random.RandomState(0).randint(0, 5, probe.nS).astype(np.int8)
+    cases = [(dict(slip_prob=0.2), lambda e: e.step(a, b, r, rng32=r32)),
+             (dict(slip_prob=0.2, rng_mode="philox"), lambda e: e.step(a, b)),
+             (dict(player_b_policy=pol), lambda e: e.step(a, None, r)),
+             (dict(player_b_policy=pol, slip_prob=0.2), lambda e: e.step(a, None, r, rng32=r32))]
+    for kw, one in cases:
+        env = SoccerVecEnv(n, width=7, height=5, device=dev, kernel="rules", want_reset_obs=False, **kw)
+        env.reset(None if env.rng_mode == "philox" else r)
+        for _ in range(30):
+            one(env)
+        with profiled():
+            for _ in range(iters):
+                one(env)
+        del env
+    n2, K = 1 << 22, 16
+    bufs = (torch.empty((K, n2), dtype=torch.int32, device=dev), torch.empty((K, n2), dtype=torch.float32, device=dev),
+            torch.empty((K, n2), dtype=torch.uint8, device=dev))
+    tp = torch.from_numpy(pol).to(dev)
+    for kw, rk in ((dict(slip_prob=0.2), {}), (dict(), dict(policy_a=tp)), (dict(slip_prob=0.2), dict(policy_a=tp))):
+        e2 = SoccerVecEnv(n2, width=7, height=5, device=dev, kernel="rules", rng_mode="philox", **kw)
+        e2.reset()
+        e2.rollout(64, want_streams=False, **rk)
+        with profiled():
+            for _ in range(iters):
+                e2.rollout(K, out=bufs, **rk)
+        del e2
+
+
 def replay(kernel, n, T, iters):
     dev = torch.device("cuda", 0)
     env = SoccerVecEnv(n, device=dev, kernel=kernel, want_reset_obs=False)
@@ -170,6 +207,8 @@ if __name__ == "__main__":
         k1_philox(args.envs, args.iters)
     if args.what in ("k1_packed", "all"):
         k1_packed(args.envs, args.iters)
+    if args.what in ("rules_modes", "all"):
+        rules_modes(args.envs, 2)
     if args.what in ("replay", "all"):
         replay("table", 1 << 22, 64, 3)
         replay("table", 4096, 4000, 3)
