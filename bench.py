@@ -654,12 +654,12 @@ def run_ours(args):
         import numpy as np
         from gym_soccer_littman94_b200.envs import SoccerSimultaneousEnv
         c1 = {}
-        for mode in ("speculative", "zero_copy", "staged"):
+        for mode in ("speculative", "speculative_slip_0.2", "zero_copy", "staged"):
             # speculative (the default): one launch per step steps the new state for all 25 joint actions x 4 draws
             # while the Python loop is busy (soccer_step_speculate); zero_copy / staged: launch and wait per step
             os.environ["SOCCER_B200_SINGLE_ENV_STAGED"] = "1" if mode == "staged" else "0"
-            os.environ["SOCCER_B200_SINGLE_ENV_SPECULATE"] = "1" if mode == "speculative" else "0"
-            e1 = SoccerSimultaneousEnv(5, 4, slip_prob=0.0, seed=0, device=dev)
+            os.environ["SOCCER_B200_SINGLE_ENV_SPECULATE"] = "1" if mode.startswith("speculative") else "0"
+            e1 = SoccerSimultaneousEnv(5, 4, slip_prob=0.2 if mode.endswith("0.2") else 0.0, seed=0, device=dev)
             acts = np.random.RandomState(123).randint(0, 5, (20000, 2))
             e1.reset()
             t0 = time.perf_counter()
@@ -674,7 +674,8 @@ def run_ours(args):
         os.environ.pop("SOCCER_B200_SINGLE_ENV_SPECULATE", None)
         extra["config1_single_env_dropin"] = dict(c1, note="20,000 step() calls of ONE env through the reference's class "
                                                   "surface; latency-bound: speculative = one launch per step that steps the "
-                                                  "new state for all 25 joint actions x 4 draws ahead of the next call, "
+                                                  "new state for all 25 joint actions x 4 draws ahead of the next call (slip 0.2: the 25 joint actions with the "
+                                                  "draw the env's generator is going to make), "
                                                   "zero_copy / staged = one launch + one wait per step; reported next to "
                                                   "cpu_baseline.python_reference (the unmodified reference's loop on this host)")
         # K1 with a state tensor far beyond the L2 (2^26 envs: 268 MB of state, 1.34 GB per step): the DRAM-only figure

@@ -123,7 +123,7 @@ def lib():
         "soccer_step": [PP, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp],
         "soccer_step_philox": [PP, vp, vp, vp, u64, u64, u64, vp, vp, vp, vp, i64, vp],
         "soccer_step_ex": [PP, C.POINTER(StepArgs), vp],
-        "soccer_step_speculate": [PP, C.c_uint32, vp, vp, vp, C.c_uint32, vp],
+        "soccer_step_speculate": [PP, C.c_uint32, vp, vp, C.POINTER(C.c_double), vp, C.c_uint32, vp],
         "soccer_rollout": [PP, vp, vp, vp, u64, u64, i32, u64, i32, vp, vp, vp, vp, i64, vp],
         "soccer_sweep": [PP, i32, vp, vp, vp, vp, vp, vp],
         "soccer_dense": [PP, vp, vp, vp, vp, vp],

@@ -413,23 +413,44 @@ __global__ void __launch_bounds__(kThreads) k_step_generic(const PitchDev P, con
 // SIM:406), obs, reward bits, detail flags | seq << 8 }, written with ONE 128-bit store: the sequence number travels in
 // the same PCIe write as the data it vouches for, so there is no fence, no barrier and no separate flag on the critical
 // path -- the reader polls the last word of the record it wants.
+// slip_prob > 0 (SLIP): the draw is a full fp64 number, so it cannot be enumerated -- the caller hands over the draw
+// the env's generator WILL make (the host mirrors the generator one draw ahead, see the Python class) and the launch
+// steps the 25 joint actions with exactly that u by the reference's cumulative walk (records r = 0 only).
+template <bool SLIP>
 __global__ void __launch_bounds__(128)
 k_step_speculate(const PitchDev P, uint32_t s, const int8_t* __restrict__ policy_a, const int8_t* __restrict__ policy_b,
-                 uint32_t* __restrict__ rec, uint32_t seq)
+                 uint32_t* __restrict__ rec, uint32_t seq, double u)
 {
+    __shared__ __align__(16) uint8_t lut[SLIP ? kLutBytes : 16];
+    __shared__ __align__(16) double prt[SLIP ? kPrtDoubles : 2];
     const uint32_t i = threadIdx.x;
-    if (i >= 100u) return;
-    const uint32_t ja = i >> 2, r = i & 3u;
-    uint32_t aa = ja / 5u, ab = ja - aa * 5u;
     const uint32_t a = s & 0xFFu, b = (s >> 8) & 0xFFu, t = (s >> 16) & 0xFFu, p = (s >> 24) & 1u;
+    if (SLIP) {
+        // the walk reads the candidate table only in the rows of the two occupied cells: 32 entries
+        if (i < 32u) {
+            const uint32_t cell = i < 16u ? a : b, idx = i & 15u, move = idx & 7u;
+            lut[cell * 16u + idx] = (uint8_t)next_cell_code(P, cell, idx >> 3, move > 4u ? 0u : move);
+        }
+        slip_build_prt(prt, P);
+        __syncthreads();
+    }
+    if (i >= (SLIP ? 25u : 100u)) return;
+    const uint32_t ja = SLIP ? i : i >> 2, r = SLIP ? 0u : i & 3u;
+    uint32_t aa = ja / 5u, ab = ja - aa * 5u;
     const int32_t cur = obs_index(P, a, b, p);
     if (policy_a) aa = (uint32_t)policy_a[cur];        // SIM:187-188: the folded player's table policy
     if (policy_b) ab = (uint32_t)policy_b[cur];
-    const uint32_t ma = (aa & 7u) > 4u ? 0u : (aa & 7u), mb = (ab & 7u) > 4u ? 0u : (ab & 7u);   // as build_cand_lut
-    const uint32_t na = next_cell_code(P, a, p ^ 1u, ma), nb = next_cell_code(P, b, p, mb);
-    const Resolved o = resolve_cand(na, nb, a, b, p, aa == 0, ab == 0, r);
-    const StepOut out = finish_step<false, true>(P, o, t, 0u, 0u, policy_a != nullptr);
-    asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" :: "l"(rec + 4u * i), "r"(out.state), "r"((uint32_t)out.obs),
+    StepOut out;
+    if (SLIP) {
+        const SlipCtx sc = { (uint32_t)__cvta_generic_to_shared(prt), slip_first_k(P) };
+        out = step_slip<false>(P, lut, sc, s, aa, ab, u, 0u, policy_a != nullptr);
+    } else {
+        const uint32_t ma = (aa & 7u) > 4u ? 0u : (aa & 7u), mb = (ab & 7u) > 4u ? 0u : (ab & 7u);   // as build_cand_lut
+        const uint32_t na = next_cell_code(P, a, p ^ 1u, ma), nb = next_cell_code(P, b, p, mb);
+        const Resolved o = resolve_cand(na, nb, a, b, p, aa == 0, ab == 0, r);
+        out = finish_step<false, true>(P, o, t, 0u, 0u, policy_a != nullptr);
+    }
+    asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" :: "l"(rec + 4u * (ja * 4u + r)), "r"(out.state), "r"((uint32_t)out.obs),
                  "r"(__float_as_uint(out.reward)), "r"((out.flags & 0xFFu) | (seq << 8)) : "memory");
 }
 
@@ -2021,15 +2042,17 @@ int soccer_stats_allreduce_p2p(const uint64_t* peer_ptrs, int32_t rank, int32_t 
 }
 
 int soccer_step_speculate(const soccer_pitch* pitch, uint32_t state_word, const int8_t* policy_a, const int8_t* policy_b,
-                          uint32_t* records, uint32_t seq, soccer_stream_t stream)
+                          const double* u, uint32_t* records, uint32_t seq, soccer_stream_t stream)
 {
     if (!records || !aligned(records, 16) || seq >= (1u << 24)) return SOCCER_EINVAL;
     PitchDev P; const int rc = make_pitch_dev(pitch, &P); if (rc) return rc;
-    if (P.slip) return SOCCER_ESLIP;                               // the draw is not 2 bits: nothing to enumerate
+    if (P.slip && !u) return SOCCER_ESLIP;                         // the draw is not 2 bits: it has to be handed over
+    if (u && !(*u >= 0.0 && *u < 1.0)) return SOCCER_EINVAL;
     const uint32_t a = state_word & 0xFFu, b = (state_word >> 8) & 0xFFu;
     if (((a | b) & kGoalBit) || (state_word & kNeedsReset) || a >= (uint32_t)P.F || b >= (uint32_t)P.F || a == b)
         return SOCCER_EINVAL;                                      // field-cell states of a running episode only
-    k_step_speculate<<<1, 128, 0, (cudaStream_t)stream>>>(P, state_word, policy_a, policy_b, records, seq);
+    if (P.slip) k_step_speculate<true><<<1, 128, 0, (cudaStream_t)stream>>>(P, state_word, policy_a, policy_b, records, seq, *u);
+    else k_step_speculate<false><<<1, 128, 0, (cudaStream_t)stream>>>(P, state_word, policy_a, policy_b, records, seq, 0.0);
     return launch_status();
 }
 

@@ -124,8 +124,17 @@ class SoccerSimultaneousEnv:
         # speculative step (slip_prob == 0, soccer_step_speculate): as soon as the state is known ONE launch steps it for
         # all 25 joint actions x 4 draw values into this pinned buffer; step() then only picks a record.
         # SOCCER_B200_SINGLE_ENV_SPECULATE=0 keeps every step on the launch-and-wait path (A/B, tests).
-        self._spec_on = (slip_prob == 0 and not self._staged
-                         and os.environ.get("SOCCER_B200_SINGLE_ENV_SPECULATE", "1") == "1")
+        # slip_prob > 0: the draw is a full fp64 number and cannot be enumerated, so the launch is handed the draw the
+        # env's generator is GOING to make: a shadow RandomState with the same state runs one draw ahead (_draw()), and
+        # every draw of np_random is checked against it -- a generator the caller reseeded, replaced or drew from
+        # shows up as a mismatch, the speculation is dropped (launch-and-wait step) and the shadow resynchronised.
+        self._spec_on = (not self._staged and os.environ.get("SOCCER_B200_SINGLE_ENV_SPECULATE", "1") == "1")
+        self._shadow, self._u_ahead, self._spec_u, self._c_u = None, None, None, C.c_double(0.0)
+        self._c_u_ref = C.byref(self._c_u)
+        self._shadow_of = None
+        if self._spec_on and slip_prob != 0:
+            self._shadow = np.random.RandomState()
+            self._resync()
         # sequence numbers start at a per-env random value: a record left in a recycled pinned block by another env's
         # launch cannot pass for one of this env's
         self._spec_key, self._spec_seq = None, int.from_bytes(os.urandom(3), "little")
@@ -231,18 +240,48 @@ class SoccerSimultaneousEnv:
             launch(self._stream_ptr, self._hbuf.data_ptr())
         cur.synchronize()
 
+    def _resync(self):
+        """Give the shadow generator np_random's state (None: np_random is not a RandomState any more -> no speculation)."""
+        self._u_ahead = None
+        try:
+            self._shadow.set_state(self.np_random.get_state())
+            self._shadow_of = self.np_random
+        except Exception:  # noqa: BLE001
+            self._shadow = None
+
+    def _draw(self):
+        """The ONE np_random.random() of SIM:395 / SIM:414, with the shadow kept in step.  Returns (u, in_sync)."""
+        u = self.np_random.random()
+        sh = self._shadow
+        if sh is None:
+            return u, False
+        ua = self._u_ahead
+        if ua is None:
+            ua = sh.random()
+        self._u_ahead = None
+        if ua != u or self._shadow_of is not self.np_random:
+            self._resync()
+            return u, False
+        return u, True
+
     def _speculate(self):
         """Enqueue the step of the CURRENT state for every (joint action, draw) -- returns at once."""
         self._spec_key = None
         if not self._spec_on or self.needs_reset or self._state_word is None or not (0 <= self.timestep < 100):
             return
         word = (self._state_word & self._STATE_MASK) | (int(self.timestep) << 16)
+        u_ref = None
+        if self.slip_prob != 0:
+            if self._shadow is None or self._u_ahead is not None:
+                return
+            self._u_ahead = self._spec_u = self._c_u.value = self._shadow.random()    # the draw the next step() will make
+            u_ref = self._c_u_ref
         self._spec_seq = seq = (self._spec_seq + 1) & 0xFFFFFF or 1
         spec = self._lib.soccer_step_speculate
-        rc = spec(self._p_ref, word, self._s_pol[0], self._s_pol[1], self._s_ptr, seq, self._stream_ptr)
+        rc = spec(self._p_ref, word, self._s_pol[0], self._s_pol[1], u_ref, self._s_ptr, seq, self._stream_ptr)
         if rc == 400:               # cudaErrorInvalidResourceHandle: another device is current -- retry under a guard
             with torch.cuda.device(self.device):
-                rc = spec(self._p_ref, word, self._s_pol[0], self._s_pol[1], self._s_ptr, seq, self._stream_ptr)
+                rc = spec(self._p_ref, word, self._s_pol[0], self._s_pol[1], u_ref, self._s_ptr, seq, self._stream_ptr)
         if rc == 0:                 # (a goal tuple injected through `env.state = ...` is refused: launch-and-wait path)
             self._spec_key = word
 
@@ -265,7 +304,9 @@ class SoccerSimultaneousEnv:
     def reset(self, seed=None, options=None):
         if seed is not None:
             self.np_random.seed(seed)
-        u = self.np_random.random()                                  # the one draw of SIM:414
+            if self._shadow is not None:
+                self._resync()
+        u, _ = self._draw()                                          # the one draw of SIM:414
         n_isd = self._info.n_isd
         idx = min(int(u * n_isd), n_isd - 1)                         # argmax(cumsum > u), exact for 4 / 2 equal parts
         h = self._hnp
@@ -319,11 +360,16 @@ class SoccerSimultaneousEnv:
         if self._state_word is None:
             raise KeyError(None)
 
-        u = self.np_random.random()                                  # the one draw of SIM:395
+        u, in_sync = self._draw()                                    # the one draw of SIM:395
         h = self._hnp
         r2 = min(int(u * 4.0), 3)                                    # floor(4u): exact 2-bit form of u
         word = (self._state_word & self._STATE_MASK) | ((int(self.timestep) & 0xFF) << 16)
-        spec = self._speculated(word, (aa * 5 + ab) * 4 + r2) if self._spec_key is not None else None
+        spec = None
+        if self._spec_key is not None:
+            if self.slip_prob == 0:
+                spec = self._speculated(word, (aa * 5 + ab) * 4 + r2)
+            elif in_sync and u == self._spec_u:                      # the launch was handed exactly this draw
+                spec = self._speculated(word, (aa * 5 + ab) * 4)
         if spec is not None:
             new_word, obs, reward, flags = spec
             return self._finish_step(action, new_word, obs, reward, flags)

@@ -187,19 +187,23 @@ typedef struct soccer_step_args {
 } soccer_step_args;
 int soccer_step_ex(const soccer_pitch *pitch, const soccer_step_args *args, soccer_stream_t stream);
 
-/* Speculative step of ONE env (the single-env drop-in's latency path; slip_prob == 0 only, SOCCER_ESLIP otherwise).
+/* Speculative step of ONE env (the single-env drop-in's latency path).
  * Replaces: SoccerSimultaneousEnv.step, soccer_simultaneous_env.py:375-408, called once per Python-loop iteration.
  * state_word: CELL-layout state of a running episode (field cells, timestep in bits 16..23, needs_reset clear).
- * One launch steps that state for all 25 joint actions x 4 values of the 2-bit step draw (a folded player's action is
- * its table policy's, SIM:187-188) WITHOUT auto-reset and writes 100 records of four 32-bit words
+ * slip_prob == 0 (u == NULL): one launch steps that state for all 25 joint actions x 4 values of the 2-bit step draw
+ * (a folded player's action is its table policy's, SIM:187-188) WITHOUT auto-reset and writes 100 records of four
+ * 32-bit words
  *     { next state word (needs_reset set when the episode ended, SIM:406), obs, reward (float bits),
  *       detail flags in bits 0..7 | seq << 8 }                                   (seq < 2^24)
  * to records[(aa * 5 + ab) * 4 + r], each with ONE 128-bit store, so the sequence number arrives together with the data
- * it vouches for.  `records` (1,600 bytes, 16-byte aligned) may be pinned host memory: the caller enqueues this as soon
- * as it knows the state, keeps working, and when the action and the draw arrive polls the last word of the record it
- * wants for `seq`, then reads the record. */
+ * it vouches for.  slip_prob > 0: the fp64 draw cannot be enumerated; *u (a HOST pointer, read during the call) is the
+ * draw the env's generator is going to make -- the caller mirrors its generator one draw ahead -- and the launch
+ * steps the 25 joint actions with exactly that u by the reference's cumulative walk into records[(aa * 5 + ab) * 4]
+ * (SOCCER_ESLIP when u == NULL).  `records` (1,600 bytes, 16-byte aligned) may be pinned host memory: the caller
+ * enqueues this as soon as it knows the state, keeps working, and when the action (and the draw) arrive polls the last
+ * word of the record it wants for `seq`, then reads the record. */
 int soccer_step_speculate(const soccer_pitch *pitch, uint32_t state_word, const int8_t *policy_a, const int8_t *policy_b,
-                          uint32_t *records, uint32_t seq, soccer_stream_t stream);
+                          const double *u, uint32_t *records, uint32_t seq, soccer_stream_t stream);
 
 /* Episode statistics of one lock-step step as a SEPARATE pass over its flags (and, optionally,
  * reward) streams: stats[0] += episodes ended, [1] += goals_A (reward > 0), [2] += goals_B,

@@ -92,12 +92,14 @@ def test_argument_errors_without_gpu(L):
     # the speculative single-env step: a 2-bit draw is all it can enumerate (slip 0), field-cell states of a running
     # episode only (a goal cell / needs_reset / equal cells are refused), a 16-byte aligned record buffer
     ok_word = 1 | (2 << 8)
-    assert lib.soccer_step_speculate(C.byref(L.Pitch(5, 4, 0.2)), ok_word, None, None, v16, 1, None) == -3
-    assert lib.soccer_step_speculate(C.byref(p), ok_word, None, None, v16, 1 << 24, None) == -1            # seq is 24 bits
-    assert lib.soccer_step_speculate(C.byref(p), ok_word, None, None, None, 1, None) == -1
-    assert lib.soccer_step_speculate(C.byref(p), ok_word, None, None, C.c_void_p(8), 1, None) == -1
+    assert lib.soccer_step_speculate(C.byref(L.Pitch(5, 4, 0.2)), ok_word, None, None, None, v16, 1, None) == -3   # slip needs the draw
+    for bad_u in (1.0, -0.1, float("nan")):
+        assert lib.soccer_step_speculate(C.byref(L.Pitch(5, 4, 0.2)), ok_word, None, None, C.byref(C.c_double(bad_u)), v16, 1, None) == -1
+    assert lib.soccer_step_speculate(C.byref(p), ok_word, None, None, None, v16, 1 << 24, None) == -1            # seq is 24 bits
+    assert lib.soccer_step_speculate(C.byref(p), ok_word, None, None, None, None, 1, None) == -1
+    assert lib.soccer_step_speculate(C.byref(p), ok_word, None, None, None, C.c_void_p(8), 1, None) == -1
     for bad in (0x80 | (2 << 8), 1 | (0xC1 << 8), ok_word | (1 << 25), 1 | (1 << 8), 20 | (2 << 8)):
-        assert lib.soccer_step_speculate(C.byref(p), bad, None, None, v16, 1, None) == -1
+        assert lib.soccer_step_speculate(C.byref(p), bad, None, None, None, v16, 1, None) == -1
 
 
 @pytest.mark.parametrize("tag", [t for t in golden_tags("table") if t.endswith("multi")])

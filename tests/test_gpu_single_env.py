@@ -246,8 +246,12 @@ def test_make_factory():
 
 # ---- the speculative step (soccer_step_speculate: every (joint action, draw) of the current state in one launch,
 #      enqueued before the action is known) returns what the launch-and-wait step returns
+@pytest.mark.parametrize("slip", [0.0, 0.2])
 @pytest.mark.parametrize("w,h,mode", [(5, 4, "multi"), (5, 4, "a_free"), (5, 4, "b_free"), (7, 5, "multi"), (6, 4, "b_free")])
-def test_speculative_step_equals_launch_and_wait(Env, monkeypatch, w, h, mode):
+def test_speculative_step_equals_launch_and_wait(Env, monkeypatch, w, h, mode, slip):
+    """slip 0: all 25 joint actions x 4 draw values per launch; slip 0.2: the 25 joint actions with the draw the env's
+    generator is going to make (shadow generator one draw ahead) -- also when the caller draws from, reseeds or
+    replaces np_random in between."""
     rs = np.random.RandomState(7)
     kw = {}
     probe = Env(width=w, height=h)
@@ -257,7 +261,7 @@ def test_speculative_step_equals_launch_and_wait(Env, monkeypatch, w, h, mode):
     envs = []
     for flag in ("1", "0"):
         monkeypatch.setenv("SOCCER_B200_SINGLE_ENV_SPECULATE", flag)
-        envs.append(Env(width=w, height=h, seed=11, **kw))
+        envs.append(Env(width=w, height=h, slip_prob=slip, seed=11, **kw))
     spec, plain = envs
     assert spec._spec_on and not plain._spec_on
     assert spec.reset() == plain.reset()
@@ -270,13 +274,26 @@ def test_speculative_step_equals_launch_and_wait(Env, monkeypatch, w, h, mode):
             plain.state = st
         if t % 131 == 7:
             spec.timestep = plain.timestep = int(rs.randint(0, 99))
+        if t % 211 == 9:                                  # the caller draws from the env's generator itself
+            assert spec.np_random.random() == plain.np_random.random()
+        if t % 307 == 11:                                 # ... reseeds it behind the env's back
+            spec.np_random.seed(t)
+            plain.np_random.seed(t)
+        if t == 1000:                                     # ... or replaces it
+            spec.np_random = np.random.RandomState(5)
+            plain.np_random = np.random.RandomState(5)
         act = {'player_a': int(rs.randint(5)), 'player_b': int(rs.randint(5))} if spec.multiagent else {a0: int(rs.randint(5))}
-        hits += spec._spec_key is not None
+        before = spec._spec_seq
         out_s, out_p = spec.step(act), plain.step(act)
         assert out_s == out_p, t
         assert spec.state == plain.state and spec.timestep == plain.timestep and spec.needs_reset == plain.needs_reset
         for k in out_s[1]:                                # -0.0 == 0.0: compare the sign too (SIM:243-244, B = -A)
             assert np.signbit(out_s[1][k]) == np.signbit(out_p[1][k])
         if spec.needs_reset:
-            assert spec.reset() == plain.reset()
-    assert hits > 1300                                    # the speculation is what served the steps
+            if t % 3 == 0:
+                assert spec.reset(seed=t) == plain.reset(seed=t)
+            else:
+                assert spec.reset() == plain.reset()
+        hits += spec._spec_key is not None
+    assert hits > 1300                                    # speculative launches went out for (nearly) every step
+    assert spec.np_random.random() == plain.np_random.random()      # the generators end in the same state
