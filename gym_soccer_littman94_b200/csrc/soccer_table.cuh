@@ -1125,6 +1125,7 @@ __host__ __device__ constexpr int slip_ring_stage_bytes(bool philox) { return ph
 // groups of a thread in flight behind the one being stepped; measured at 2^24 envs (profiles/r02z_time.log):
 //   injected rng32 (44 B per group and thread): register prefetch 209 G, 2 stages 228 G, 3 stages (10-bit bucket table) 219 G
 //   Philox         (24 B):                      register prefetch 246 G, 2 stages 256 G, 3 stages 270 G, 4 stages 266 G
+// (injected, only state + draws in a 3-stage ring and the action / draw bytes through L2 prefetch + registers: 176 G)
 #ifndef SOCCER_SLIP_I_RING_STAGES
 #define SOCCER_SLIP_I_RING_STAGES 0    // 0: 2 for injected draws, 3 for Philox
 #endif
